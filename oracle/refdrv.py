@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE (oracle) -- ctypes front end of ``oracle/_ref/libgiraffe_ref.so``.
+
+That library is the reference's own UNMODIFIED element / solution sources
+(``/root/reference/src/{Beam_1,Shell_1,Solid_1,Node,Solution,...}.cpp``) built
+by ``oracle/Makefile`` against the shims in ``oracle/ref_shims/``.  This module
+feeds it a :class:`giraffe_b200.meshes.Model` and drives the same call sequence
+as ``Static::Solve`` (reference ``Static.cpp:161-163,203-212``).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this module.  The product path never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libgiraffe_ref.so")
+
+_I = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_D = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+class RefOracle:
+    """One process-wide instance: the reference keeps its model in a global ``db``."""
+
+    MATS = {"AA": 0, "AB": 1, "BA": 2, "BB": 3}
+
+    def __init__(self, threads: int | None = None):
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(LIB_PATH)
+        L = self.lib
+        L.ref_set_nodes.argtypes = [C.c_int, _D]
+        L.ref_add_hooke.argtypes = [C.c_double] * 3
+        L.ref_add_section.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.ref_get_section.argtypes = [C.c_int, _D]
+        L.ref_add_shell_section.argtypes = [C.c_double]
+        L.ref_add_cs.argtypes = [_D, _D]
+        L.ref_get_cs.argtypes = [C.c_int, _D]
+        L.ref_set_elements.argtypes = [C.c_int, _I, _I, _I, _I, _I, C.c_void_p]
+        L.ref_set_gravity.argtypes = [C.c_double] * 3
+        L.ref_add_nodal_constraint.argtypes = [C.c_int, _I, C.c_int]
+        L.ref_add_nodal_load.argtypes = [C.c_int, _I, C.c_int, C.c_int, _D]
+        L.ref_get_gls.argtypes = [_I]
+        L.ref_set_time.argtypes = [C.c_double, C.c_double]
+        L.ref_set_displacements.argtypes = [_D]
+        L.ref_get_copy_coordinates.argtypes = [_D]
+        L.ref_assemble.argtypes = [C.c_int, _D]
+        L.ref_mount_local.argtypes = [_D]
+        for f in (L.ref_triplet_count, L.ref_csr_nnz):
+            f.argtypes = [C.c_int]
+            f.restype = C.c_long
+        L.ref_csr_rows.argtypes = [C.c_int]
+        L.ref_csr_cols.argtypes = [C.c_int]
+        L.ref_csr_get.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_get_vectors.argtypes = [_D, _D, _D]
+        L.ref_get_element.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_get_state.argtypes = [C.c_int, _D]
+        L.ref_set_threads.argtypes = [C.c_int]
+        if threads:
+            L.ref_set_threads(int(threads))
+        self.model = None
+
+    # ---- model ---------------------------------------------------------
+    def load(self, m, check: bool = True):
+        L = self.lib
+        L.ref_reset()
+        L.ref_set_nodes(m.n_nodes, np.ascontiguousarray(m.xyz, np.float64).reshape(-1))
+        for E, nu, rho in m.hooke:
+            L.ref_add_hooke(float(E), float(nu), float(rho))
+        for kind, a, b in m.section_defs:
+            L.ref_add_section(int(kind), float(a), float(b))
+        for t in m.shell_thickness:
+            L.ref_add_shell_section(float(t))
+        for e1, e3 in m.cs_defs:
+            r = L.ref_add_cs(np.asarray(e1, np.float64), np.asarray(e3, np.float64))
+            if r < 0:
+                raise ValueError("reference rejected the coordinate system")
+        pret = None
+        if m.pretension is not None:
+            self._pret = np.ascontiguousarray(m.pretension, np.float64)
+            pret = self._pret.ctypes.data_as(C.c_void_p)
+        L.ref_set_elements(m.n_elements, m.elem_type.astype(np.int32), m.elem_mat.astype(np.int32),
+                           m.elem_sec.astype(np.int32), m.elem_cs.astype(np.int32),
+                           np.ascontiguousarray(m.elem_nodes, np.int32), pret)
+        if m.gravity is not None:
+            L.ref_set_gravity(*[float(g) for g in m.gravity])
+        for nodes, mask in m.constraints:
+            nodes = np.ascontiguousarray(nodes, np.int32)
+            L.ref_add_nodal_constraint(len(nodes), nodes, int(mask))
+        for nodes, cs, table in m.nodal_loads:
+            nodes = np.ascontiguousarray(nodes, np.int32)
+            table = np.ascontiguousarray(table, np.float64)
+            if L.ref_add_nodal_load(len(nodes), nodes, int(cs), table.shape[0], table.reshape(-1)) < 0:
+                raise ValueError("reference rejected the nodal load")
+        if check:
+            bad = L.ref_check()
+            if bad:
+                raise ValueError(f"reference Element::Check failed on element {bad}")
+        L.ref_precalc()
+        L.ref_setup_dofs()
+        self.model = m
+        return self
+
+    @property
+    def n_free(self) -> int:
+        return self.lib.ref_n_free()
+
+    @property
+    def n_fixed(self) -> int:
+        return self.lib.ref_n_fixed()
+
+    def gls(self) -> np.ndarray:
+        g = np.zeros(self.model.n_nodes * 6, np.int32)
+        self.lib.ref_get_gls(g)
+        return g.reshape(-1, 6)
+
+    def section(self, sid: int) -> np.ndarray:
+        out = np.zeros(6)
+        self.lib.ref_get_section(sid, out)
+        return out
+
+    def cs(self, cid: int) -> np.ndarray:
+        out = np.zeros(9)
+        self.lib.ref_get_cs(cid, out)
+        return out
+
+    # ---- per iteration -------------------------------------------------
+    def set_time(self, last_converged: float, step: float):
+        self.lib.ref_set_time(float(last_converged), float(step))
+
+    def assemble(self, disp: np.ndarray, with_loads: bool = False) -> np.ndarray:
+        """One Newton-iteration assembly; returns the 5 phase times in seconds
+        (MountLocal, MountElementLoads, MountGlobal, MountSparse, Clear+MountLoads)."""
+        self.lib.ref_set_displacements(np.ascontiguousarray(disp, np.float64).reshape(-1))
+        sec = np.zeros(5)
+        self.lib.ref_assemble(1 if with_loads else 0, sec)
+        return sec
+
+    def mount_local(self, disp: np.ndarray) -> np.ndarray:
+        self.lib.ref_set_displacements(np.ascontiguousarray(disp, np.float64).reshape(-1))
+        sec = np.zeros(2)
+        self.lib.ref_mount_local(sec)
+        return sec
+
+    def commit(self):
+        self.lib.ref_commit()
+
+    def copy_coordinates(self) -> np.ndarray:
+        c = np.zeros(self.model.n_nodes * 6)
+        self.lib.ref_get_copy_coordinates(c)
+        return c.reshape(-1, 6)
+
+    # ---- results -------------------------------------------------------
+    def csr(self, which: str = "AA"):
+        w = self.MATS[which]
+        nr, nz = self.lib.ref_csr_rows(w), self.lib.ref_csr_nnz(w)
+        outer = np.zeros(nr + 1, np.int32)
+        inner = np.zeros(nz, np.int32)
+        val = np.zeros(nz, np.float64)
+        self.lib.ref_csr_get(w, outer.ctypes.data, inner.ctypes.data, val.ctypes.data)
+        return outer, inner, val, (nr, self.lib.ref_csr_cols(w))
+
+    def triplets(self, which: str = "AA") -> int:
+        return self.lib.ref_triplet_count(self.MATS[which])
+
+    def vectors(self):
+        pa, ia, pb = np.zeros(self.n_free), np.zeros(self.n_free), np.zeros(self.n_fixed)
+        self.lib.ref_get_vectors(pa, ia, pb)
+        return pa, ia, pb
+
+    def element(self, e: int):
+        n = self.lib.ref_get_element(e, None, None, None)
+        K = np.zeros((n, n))
+        P = np.zeros(n)
+        en = C.c_double(0.0)
+        self.lib.ref_get_element(e, K.ctypes.data, P.ctypes.data, C.addressof(en))
+        return K, P, en.value
+
+    def state(self, e: int) -> np.ndarray:
+        buf = np.zeros(64)
+        n = self.lib.ref_get_state(e, buf)
+        return buf[:n].copy()
