@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE (oracle) -- ctypes front end of ``oracle/libgfa_oracle.so``,
+the builder's plain-C++ restatement of the assembly path (``oracle/port/``).
+
+Same surface as :class:`oracle.refdrv.RefOracle`, so a test can run either
+against the same :class:`giraffe_b200.meshes.Model`.  ``ensure_built()``
+compiles the library with g++ when it is missing (source-only checkouts).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this module.  The product path never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgfa_oracle.so")
+_I = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_D = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def ensure_built(force: bool = False) -> str:
+    src = os.path.join(_HERE, "port", "gfa_oracle.cpp")
+    stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+class PortOracle:
+    MATS = {"AA": 0, "AB": 1, "BA": 2, "BB": 3}
+
+    def __init__(self, threads: int | None = None):
+        self.lib = C.CDLL(ensure_built())
+        L = self.lib
+        L.gfo_set_nodes.argtypes = [C.c_int, _D]
+        L.gfo_set_materials.argtypes = [C.c_int, _D]
+        L.gfo_set_sections.argtypes = [C.c_int, C.c_void_p]
+        L.gfo_set_shell_sections.argtypes = [C.c_int, C.c_void_p]
+        L.gfo_set_cs.argtypes = [C.c_int, C.c_void_p]
+        L.gfo_set_elements.argtypes = [C.c_int, _I, _I, _I, _I, _I, _I, C.c_void_p]
+        L.gfo_set_gravity.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+        L.gfo_set_constraint_mask.argtypes = [_I]
+        L.gfo_get_gls.argtypes = [_I]
+        L.gfo_set_extra_triplets.argtypes = [C.c_int, C.c_long, _I, _I, _D]
+        L.gfo_assemble.argtypes = [_D, C.c_double, _D]
+        for f in (L.gfo_triplet_count, L.gfo_csr_nnz):
+            f.argtypes = [C.c_int]
+            f.restype = C.c_long
+        L.gfo_csr_get.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gfo_get_vectors.argtypes = [_D, _D, _D]
+        L.gfo_get_element.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gfo_get_state.argtypes = [C.c_int, _D]
+        L.gfo_get_copy_coordinates.argtypes = [_D]
+        if threads:
+            L.gfo_set_threads(int(threads))
+        self.model = None
+        self.gravity_factor = 1.0
+
+    def load(self, m):
+        L = self.lib
+        L.gfo_reset()
+        L.gfo_set_nodes(m.n_nodes, np.ascontiguousarray(m.xyz, np.float64).reshape(-1))
+        L.gfo_set_materials(len(m.hooke), np.ascontiguousarray(m.hooke, np.float64).reshape(-1))
+        sec = np.ascontiguousarray(m.sections, np.float64).reshape(-1)
+        L.gfo_set_sections(len(m.sections), sec.ctypes.data)
+        th = np.ascontiguousarray(m.shell_thickness, np.float64)
+        L.gfo_set_shell_sections(len(th), th.ctypes.data)
+        cs = np.ascontiguousarray(m.cs, np.float64).reshape(-1)
+        L.gfo_set_cs(len(m.cs), cs.ctypes.data)
+        pret = None
+        if m.pretension is not None:
+            self._pret = np.ascontiguousarray(m.pretension, np.float64)
+            pret = self._pret.ctypes.data
+        L.gfo_set_elements(m.n_elements, m.elem_type.astype(np.int32), m.elem_mat.astype(np.int32),
+                           m.elem_sec.astype(np.int32), m.elem_cs.astype(np.int32),
+                           m.elem_ptr.astype(np.int32), np.ascontiguousarray(m.elem_nodes, np.int32), pret)
+        if m.gravity is not None:
+            L.gfo_set_gravity(1, *[float(g) for g in m.gravity])
+        L.gfo_set_constraint_mask(m.constraint_mask().astype(np.int32))
+        if L.gfo_precalc() != 0:
+            raise ValueError("unsupported element type")
+        self.model = m
+        return self
+
+    @property
+    def n_free(self) -> int:
+        return self.lib.gfo_n_free()
+
+    @property
+    def n_fixed(self) -> int:
+        return self.lib.gfo_n_fixed()
+
+    def gls(self) -> np.ndarray:
+        g = np.zeros(self.model.n_nodes * 6, np.int32)
+        self.lib.gfo_get_gls(g)
+        return g.reshape(-1, 6)
+
+    def set_time(self, last_converged: float, step: float, start: float = 0.0, end: float = 1.0):
+        """Gravity ramp of a first solution step (BoolTable.cpp:84-106)."""
+        self.gravity_factor = (last_converged + step - start) / (end - start)
+
+    def set_extra_triplets(self, which: str, rows, cols, vals):
+        self.lib.gfo_set_extra_triplets(self.MATS[which], len(vals), np.ascontiguousarray(rows, np.int32),
+                                        np.ascontiguousarray(cols, np.int32), np.ascontiguousarray(vals, np.float64))
+
+    def assemble(self, disp: np.ndarray, with_loads: bool = False) -> np.ndarray:
+        sec = np.zeros(5)
+        self.lib.gfo_assemble(np.ascontiguousarray(disp, np.float64).reshape(-1), float(self.gravity_factor), sec)
+        return sec
+
+    def commit(self):
+        self.lib.gfo_commit()
+
+    def copy_coordinates(self) -> np.ndarray:
+        c = np.zeros(self.model.n_nodes * 6)
+        self.lib.gfo_get_copy_coordinates(c)
+        return c.reshape(-1, 6)
+
+    def csr(self, which: str = "AA"):
+        w = self.MATS[which]
+        nr, nz = self.lib.gfo_csr_rows(w), self.lib.gfo_csr_nnz(w)
+        outer = np.zeros(nr + 1, np.int32)
+        inner = np.zeros(nz, np.int32)
+        val = np.zeros(nz, np.float64)
+        self.lib.gfo_csr_get(w, outer.ctypes.data, inner.ctypes.data, val.ctypes.data)
+        return outer, inner, val, (nr, self.lib.gfo_csr_cols(w))
+
+    def triplets(self, which: str = "AA") -> int:
+        return self.lib.gfo_triplet_count(self.MATS[which])
+
+    def vectors(self):
+        pa, ia, pb = np.zeros(self.n_free), np.zeros(self.n_free), np.zeros(self.n_fixed)
+        self.lib.gfo_get_vectors(pa, ia, pb)
+        return pa, ia, pb
+
+    def element(self, e: int):
+        n = self.lib.gfo_get_element(e, None, None, None)
+        K = np.zeros((n, n))
+        P = np.zeros(n)
+        en = C.c_double(0.0)
+        self.lib.gfo_get_element(e, K.ctypes.data, P.ctypes.data, C.addressof(en))
+        return K, P, en.value
+
+    def state(self, e: int) -> np.ndarray:
+        buf = np.zeros(64)
+        n = self.lib.gfo_get_state(e, buf)
+        return buf[:n].copy()
