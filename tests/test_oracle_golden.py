@@ -1,0 +1,84 @@
+"""CPU: the port restatement (oracle/port) against the committed golden
+fixtures that the reference's own sources produced (tests/golden/make_golden.py).
+This is what pins the oracle on boxes where /root/reference does not exist."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+
+def _load(name):
+    return np.load(os.path.join(util.GOLDEN_DIR, name + ".npz"))
+
+
+def test_tutorial01_structure_and_values(port):
+    """BASELINE.json configs[0]: inputs/tutorial01 as shipped, iterations 1 and 2
+    of increment 1.  Structural facts from SURVEY.md 8c: 60 free / 6 fixed DOF,
+    1449 AA triplets (9 NodalLoad + 144 + 4*324), nnz_AA = 1296, AB 72, BB 36."""
+    z = _load("tutorial01")
+    m = util.model_from_dict(z)
+    port.load(m)
+    assert (port.n_free, port.n_fixed) == (60, 6)
+    assert (port.gls() == z["gls"]).all()
+    assert list(z["it1_triplets"]) == [1449, 72, 72, 36]
+    t0, dt = z["time"]
+    for tag in ("it1", "it2"):
+        disp = z[f"{tag}_disp"]
+        trip, pa_add, pb_add = util.nodal_load_contribution(m, port.gls(), disp, t0 + dt)
+        for w in ("AA", "AB", "BA", "BB"):
+            port.set_extra_triplets(w, *trip[w])
+        port.assemble(disp)
+        if tag == "it1":
+            assert port.triplets("AA") == 1449 and port.triplets("AB") == 72 and port.triplets("BB") == 36
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), port.csr, f"tutorial01 {tag}")
+        pa, ia, pb = port.vectors()
+        np.add.at(pa, pa_add[0], pa_add[1])
+        np.add.at(pb, pb_add[0], pb_add[1])
+        util.assert_parity(z[f"{tag}_PA"], pa, f"tutorial01 {tag} P_A")
+        util.assert_parity(z[f"{tag}_IA"], ia, f"tutorial01 {tag} I_A")
+        util.assert_parity(z[f"{tag}_PB"], pb, f"tutorial01 {tag} P_B")
+    assert len(z["it1_AA_val"]) == 1296
+
+
+@pytest.mark.parametrize("name", ["beam_line", "shell_plate"])
+def test_sequence_with_commit(port, name):
+    """Two iterations, SaveLagrange/SaveConfiguration, one more iteration."""
+    z = _load(name)
+    m = util.model_from_dict(z)
+    port.load(m)
+    port.set_time(*z["time"])
+    assert (port.gls() == z["gls"]).all()
+    for tag, commit in (("it1", False), ("it2", True), ("it3", False)):
+        port.assemble(z[f"{tag}_disp"])
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), port.csr, f"{name} {tag}")
+        for v, key in zip(port.vectors(), ("PA", "IA", "PB")):
+            util.assert_parity(z[f"{tag}_{key}"], v, f"{name} {tag} {key}")
+        K, P, en = port.element(1)
+        util.assert_parity(z[f"{tag}_elem1_K"], K, f"{name} {tag} element K", util.block_scale(z[f"{tag}_elem1_K"]))
+        util.assert_parity(z[f"{tag}_elem1_P"], P, f"{name} {tag} element P")
+        assert abs(en - z[f"{tag}_elem1_energy"][0]) <= 1e-12 * abs(en) + 1e-300
+        if commit:
+            port.commit()
+            util.assert_parity(z[f"{tag}_state1"], port.state(1), f"{name} committed state")
+            util.assert_parity(z[f"{tag}_copy"], port.copy_coordinates(), f"{name} copy_coordinates")
+
+
+def test_shell_gravity_is_applied_twice(port):
+    """Shell_1::MountFieldLoads executes the self-weight block twice
+    (reference Shell_1.cpp:1340-1375); the oracle must reproduce it: at zero
+    displacement P = -2 * consistent weight, and the total vertical load
+    equals 2 * rho * t * g * area."""
+    from giraffe_b200 import meshes as M
+    m = M.shell_plate(3, 2, gravity=(0.0, 0.0, -9.81))
+    m.constraints = []
+    port.load(m)
+    port.set_time(0.0, 1.0)
+    port.assemble(np.zeros((m.n_nodes, 6)))
+    pa, _, _ = port.vectors()
+    gls = port.gls()
+    total_z = pa[gls[:, 2][gls[:, 2] > 0] - 1].sum()
+    area = 3 * 2 * 0.0195 ** 2
+    expect = 2.0 * 8000.0 * 0.002 * 9.81 * area      # P = Fint - Fext, Fext = 2 * weight (downwards)
+    assert abs(total_z - expect) <= 1e-10 * expect

@@ -1,0 +1,61 @@
+"""CPU, build container only: the port restatement against the reference's own
+sources (oracle/_ref) on seeded models that are larger / different from the
+committed fixtures.  Skipped where /root/reference (hence oracle/_ref) is absent."""
+import numpy as np
+import pytest
+
+import util
+from giraffe_b200 import meshes as M
+
+
+def _cases():
+    b = M.beam_line(40, pretension=5.0e4)
+    b.gravity = (0.1, 0.2, -9.81)
+    s = M.shell_plate(5, 7, warp=0.02, gravity=(0.0, 0.0, -9.81))
+    flat = M.shell_plate(4, 3)
+    mixed = M.concat_models([M.beam_line(10), M.shell_plate(3, 3, warp=0.005)])
+    return [("beam", b, M.beam_line_displacements(b)), ("shell", s, M.shell_plate_displacements(s)),
+            ("flat", flat, M.shell_plate_displacements(flat, seed=7)),
+            ("mixed", mixed, M.mask_displacements(mixed, np.random.default_rng(3).uniform(-1e-3, 1e-3, (mixed.n_nodes, 6))))]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_port_matches_reference_sources(ref, port, case):
+    name, m, d = case
+    ref.load(m)
+    port.load(m)
+    ref.set_time(0.0, 0.5)
+    port.set_time(0.0, 0.5)
+    assert (ref.gls() == port.gls()).all()
+    assert (ref.n_free, ref.n_fixed) == (port.n_free, port.n_fixed)
+    for it in range(3):
+        ref.assemble(d)
+        port.assemble(d)
+        for w in ("AA", "AB", "BA", "BB"):
+            assert ref.triplets(w) == port.triplets(w)
+        util.assert_system_parity(ref.csr, port.csr, f"{name} it{it}")
+        for a, b, key in zip(ref.vectors(), port.vectors(), ("PA", "IA", "PB")):
+            util.assert_parity(a, b, f"{name} it{it} {key}")
+        for e in (0, m.n_elements // 2, m.n_elements - 1):
+            Kr, Pr, er = ref.element(e)
+            Kp, Pp, ep = port.element(e)
+            util.assert_parity(Kr, Kp, f"{name} element {e} K", util.block_scale(Kr))
+            assert abs(er - ep) <= 1e-12 * abs(er) + 1e-300
+        ref.commit()
+        port.commit()
+        for e in (0, m.n_elements - 1):
+            util.assert_parity(ref.state(e), port.state(e), f"{name} state of element {e}")
+        util.assert_parity(ref.copy_coordinates(), port.copy_coordinates(), f"{name} copy coordinates")
+        d = 0.5 * d
+
+
+def test_section_and_cs_constants(ref):
+    """meshes.py restates SecRectangle/SecTube::PreCalc and CoordinateSystem::Read."""
+    m = M.beam_line(2)
+    m.section_defs = [(1, 0.65, 0.62), (0, 0.1, 0.25)]
+    m.cs_defs = [((1.0, 0.0, 0.0), (0.0, 0.0, 1.0)), ((2.0, 0.0, 0.0), (0.0, 0.0, 0.5))]
+    M._finish(m)
+    ref.load(m)
+    for k in (1, 2):
+        assert np.array_equal(ref.section(k), m.sections[k - 1])
+        assert np.array_equal(ref.cs(k), m.cs[k - 1])

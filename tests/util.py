@@ -1,0 +1,204 @@
+"""Shared helpers of the parity tests: the parity metric, CSR comparison and
+(de)serialisation of models / captured reference results as .npz fixtures."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from giraffe_b200 import meshes as M
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star tolerance: "Kt/Fint values must agree with the reference's CPU
+# assembly to a relative 1e-12".  Pure relative error is undefined on the
+# explicit zeros the reference pushes and is not attainable on cancellation
+# residue by ANY re-ordering of a FP64 sum: an entry K_ij is a sum of products
+# whose magnitudes are bounded by sqrt(K_ii K_jj), so its rounding error is
+# ~1e-16 * sqrt(K_ii K_jj) however small K_ij itself is (e.g. the shell's
+# membrane/bending couplings are the residue of +/-zeta terms cancelling in the
+# thickness quadrature, Shell_1.cpp:1127-1143; the reference itself moves by
+# that much between MKL versions).  The criterion is therefore
+#       |a - b| <= TOL * max(|a|, |b|, FLOOR * s_ij),   s_ij = sqrt(|K_ii| |K_jj|)
+# with the diagonals taken from the REFERENCE matrices (AA for free DOFs, BB
+# for fixed ones): component-wise 1e-12 for every entry within one decade of
+# its diagonal scale, and 1e-13 * s_ij (diagonally-scaled norm-wise) below.
+# Vectors and single blocks without a diagonal use their max magnitude as s.
+TOL = 1e-12
+FLOOR = 1e-1
+
+
+def parity_error(ref: np.ndarray, got: np.ndarray, scale=None) -> float:
+    """max over entries of |a-b| / max(|a|, |b|, FLOOR*scale); <= TOL means parity.
+    `scale` is a scalar or an array broadcastable to the entries."""
+    ref = np.asarray(ref, float)
+    got = np.asarray(got, float)
+    assert ref.shape == got.shape, (ref.shape, got.shape)
+    if ref.size == 0:
+        return 0.0
+    if scale is None:
+        scale = float(max(np.abs(ref).max(), np.abs(got).max()))
+    denom = np.maximum(np.maximum(np.abs(ref), np.abs(got)), FLOOR * np.asarray(scale, float))
+    diff = np.abs(ref - got)
+    err = np.where(denom > 0, diff / np.where(denom > 0, denom, 1.0), np.where(diff > 0, np.inf, 0.0))
+    return float(err.max())
+
+
+def assert_parity(ref, got, what: str, scale=None, tol: float = TOL):
+    e = parity_error(ref, got, scale)
+    assert e <= tol, f"{what}: parity error {e:.3e} > {tol:.1e}"
+
+
+def block_scale(K: np.ndarray) -> np.ndarray:
+    """s_ij = sqrt(|K_ii| |K_jj|) of a square element block."""
+    d = np.abs(np.diag(K))
+    return np.sqrt(np.outer(d, d))
+
+
+def csr_diag(csr) -> np.ndarray:
+    outer, inner, val, shape = csr
+    d = np.zeros(shape[0])
+    rows = np.repeat(np.arange(shape[0]), np.diff(outer))
+    on = rows == inner
+    d[rows[on]] = np.abs(val[on])
+    return d
+
+
+def assert_csr_parity(ref_csr, got_csr, what: str, drow=None, dcol=None, tol: float = TOL):
+    """Pattern byte-equal (Eigen outerIndexPtr / innerIndexPtr, int32) and values
+    within the diagonally scaled criterion above."""
+    ro, ri, rv, rs = ref_csr
+    go, gi, gv, gs = got_csr
+    assert tuple(rs) == tuple(gs), f"{what}: shape {gs} != {rs}"
+    assert ro.dtype == go.dtype == np.int32 and ri.dtype == gi.dtype == np.int32
+    assert ro.tobytes() == go.tobytes(), f"{what}: outerIndexPtr differs"
+    assert ri.tobytes() == gi.tobytes(), f"{what}: innerIndexPtr differs"
+    if len(rv) == 0:
+        return 0.0
+    if drow is None:
+        drow = dcol = csr_diag(ref_csr)
+    rows = np.repeat(np.arange(rs[0]), np.diff(ro))
+    scale = np.sqrt(drow[rows] * dcol[ri])
+    e = parity_error(rv, gv, scale)
+    assert e <= tol, f"{what}: value parity error {e:.3e} > {tol:.1e}"
+    return e
+
+
+def assert_system_parity(ref_get, got_get, what: str, tol: float = TOL):
+    """All four matrices; ref_get / got_get map 'AA'|'AB'|'BA'|'BB' to a CSR tuple."""
+    rAA, rBB = ref_get("AA"), ref_get("BB")
+    dA, dB = csr_diag(rAA), csr_diag(rBB)
+    worst = 0.0
+    for w, dr, dc in (("AA", dA, dA), ("AB", dA, dB), ("BA", dB, dA), ("BB", dB, dB)):
+        e = assert_csr_parity(ref_get(w), got_get(w), f"{what} {w}", dr, dc, tol)
+        worst = max(worst, e or 0.0)
+    return worst
+
+
+# ---- model <-> npz -------------------------------------------------------
+def model_to_dict(m: M.Model, prefix: str = "m_") -> dict:
+    d = {
+        "xyz": m.xyz, "hooke": m.hooke, "sections": m.sections,
+        "section_defs": np.array(m.section_defs, float).reshape(-1, 3),
+        "shell_thickness": m.shell_thickness,
+        "cs_defs": np.array([list(a) + list(b) for a, b in m.cs_defs], float).reshape(-1, 6),
+        "cs": m.cs, "elem_type": m.elem_type, "elem_mat": m.elem_mat, "elem_sec": m.elem_sec,
+        "elem_cs": m.elem_cs, "elem_ptr": m.elem_ptr, "elem_nodes": m.elem_nodes,
+        "pretension": m.pretension if m.pretension is not None else np.zeros(0),
+        "gravity": np.array(m.gravity if m.gravity is not None else [], float),
+        "n_constraints": np.array([len(m.constraints)]),
+        "n_loads": np.array([len(m.nodal_loads)]),
+    }
+    for i, (nodes, mask) in enumerate(m.constraints):
+        d[f"c{i}_nodes"] = np.asarray(nodes, np.int32)
+        d[f"c{i}_mask"] = np.array([mask])
+    for i, (nodes, cs, table) in enumerate(m.nodal_loads):
+        d[f"l{i}_nodes"] = np.asarray(nodes, np.int32)
+        d[f"l{i}_cs"] = np.array([cs])
+        d[f"l{i}_table"] = np.asarray(table, float)
+    return {prefix + k: np.asarray(v) for k, v in d.items()}
+
+
+def model_from_dict(z, prefix: str = "m_") -> M.Model:
+    g = lambda k: z[prefix + k]
+    m = M.Model(xyz=g("xyz"), hooke=g("hooke"), sections=g("sections"))
+    m.section_defs = [(int(r[0]), float(r[1]), float(r[2])) for r in g("section_defs")]
+    m.shell_thickness = g("shell_thickness")
+    m.cs_defs = [(tuple(r[:3]), tuple(r[3:])) for r in g("cs_defs")]
+    m.cs = g("cs")
+    for k in ("elem_type", "elem_mat", "elem_sec", "elem_cs", "elem_ptr", "elem_nodes"):
+        setattr(m, k, g(k).astype(np.int32))
+    p = g("pretension")
+    m.pretension = p if p.size else None
+    gr = g("gravity")
+    m.gravity = tuple(gr) if gr.size else None
+    m.constraints = [(g(f"c{i}_nodes"), int(g(f"c{i}_mask")[0])) for i in range(int(g("n_constraints")[0]))]
+    m.nodal_loads = [(g(f"l{i}_nodes"), int(g(f"l{i}_cs")[0]), g(f"l{i}_table")) for i in range(int(g("n_loads")[0]))]
+    return m
+
+
+def capture(oracle, tag: str) -> dict:
+    """All four CSR matrices and the three vectors of the oracle's last assembly."""
+    out = {}
+    for w in ("AA", "AB", "BA", "BB"):
+        o, i, v, s = oracle.csr(w)
+        out[f"{tag}_{w}_outer"], out[f"{tag}_{w}_inner"], out[f"{tag}_{w}_val"] = o, i, v
+        out[f"{tag}_{w}_shape"] = np.array(s)
+    pa, ia, pb = oracle.vectors()
+    out[f"{tag}_PA"], out[f"{tag}_IA"], out[f"{tag}_PB"] = pa, ia, pb
+    return out
+
+
+def captured_csr(z, tag: str, w: str):
+    return (z[f"{tag}_{w}_outer"], z[f"{tag}_{w}_inner"], z[f"{tag}_{w}_val"], tuple(z[f"{tag}_{w}_shape"]))
+
+
+def nodal_load_contribution(m: M.Model, gls: np.ndarray, disp: np.ndarray, time: float):
+    """Host restatement of NodalLoad::Mount (reference NodalLoad.cpp:322-401) for
+    numeric tables: returns (triplets per matrix, additions to P_A / P_B).
+    This is the 'coexisting host contributor' of SURVEY.md 8b: it stays on the
+    host and enters the device matrix through gfa_add_host_triplets."""
+    trip = {w: ([], [], []) for w in ("AA", "AB", "BA", "BB")}
+    pa, pb = ([], []), ([], [])
+    active = gls != 0
+    for nodes, cs_id, table in m.nodal_loads:
+        table = np.asarray(table, float)
+        vals = np.array([np.interp(time, table[:, 0], table[:, k]) for k in range(1, 7)])
+        nodes = np.asarray(nodes, int)
+        nf = np.array([active[nodes - 1, k].sum() for k in range(6)], float)
+        mult = 1.0 / nf
+        Q = m.cs[cs_id - 1].reshape(3, 3)      # rows E1,E2,E3 = CoordinateSystem::Q
+        for nd in nodes:
+            f = Q.T @ (mult[:3] * vals[:3])
+            mo = Q.T @ (mult[3:] * vals[3:])
+            a = disp[nd - 1, 3:6]
+            al = np.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])
+            g = 4.0 / (4.0 + al * al)
+            A = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+            Xi = g * (np.eye(3) + 0.5 * A)
+            mo = Xi.T @ mo
+            h = g
+            h2, h4, h8 = 0.5 * h, -0.25 * h * h, -0.5 * h * h
+            skew_t = np.array([[0, -mo[2], mo[1]], [mo[2], 0, -mo[0]], [-mo[1], mo[0], 0]])
+            V = np.outer(h8 * mo - h4 * (A @ mo), a) + h2 * skew_t
+            for lin in range(3):
+                gl = gls[nd - 1, lin]
+                if active[nd - 1, lin]:
+                    (pa if gl > 0 else pb)[0].append(abs(gl) - 1)
+                    (pa if gl > 0 else pb)[1].append(-1.0 * f[lin])
+            for lin in range(3):
+                gl = gls[nd - 1, lin + 3]
+                if active[nd - 1, lin + 3]:
+                    (pa if gl > 0 else pb)[0].append(abs(gl) - 1)
+                    (pa if gl > 0 else pb)[1].append(-1.0 * mo[lin])
+                for col in range(3):
+                    gc = gls[nd - 1, col + 3]
+                    if not active[nd - 1, col + 3]:
+                        continue
+                    w = ("AA" if gc > 0 else "AB") if gl > 0 else ("BA" if gc > 0 else "BB")
+                    if gl == 0:
+                        continue
+                    trip[w][0].append(abs(gl) - 1)
+                    trip[w][1].append(abs(gc) - 1)
+                    trip[w][2].append(-1.0 * V[lin, col])
+    return trip, pa, pb
