@@ -88,35 +88,38 @@ struct Frame {
     double Lx[3], Ly[3];    // dL_a/dx1, dL_a/dx2
 };
 GFA_DI void frame_of(const double (&x)[6][3], Frame& fr) {
+    // strict arithmetic in the reference's order: the shape-function values feed
+    // the strain chain (see gfa_math.cuh, "Strict" arithmetic)
     double d21[3], d31[3], n[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { d21[k] = x[1][k] - x[0][k]; d31[k] = x[2][k] - x[0][k]; }
-    cross3(n, d21, d31);
-    const double nn = norm3(n);
-    const double A = 0.5 * nn;
+    for (int k = 0; k < 3; k++) { d21[k] = s_sub(x[1][k], x[0][k]); d31[k] = s_sub(x[2][k], x[0][k]); }
+    s_cross3(n, d21, d31);
+    const double nn = s_norm3(n);
+    const double A = s_mul(0.5, nn);
     double e3[3], e1[3], e2[3];
+    const double inv = 1.0 / nn;
 #pragma unroll
-    for (int k = 0; k < 3; k++) e3[k] = (1.0 / nn) * n[k];
+    for (int k = 0; k < 3; k++) e3[k] = s_mul(n[k], inv);
     double eg[3] = { 1.0, 0.0, 0.0 };
-    if (fabs(e3[0]) >= 1.0 - 1e-4) { eg[0] = 0.0; eg[1] = 1.0; }
-    const double ege3 = dot3(eg, e3);
+    if (fabs(e3[0]) >= 1.0 - 1e-4) { eg[0] = 0.0; eg[1] = 1.0; }     // Shell_1.cpp:1990
+    const double ege3 = s_dot3(eg, e3);
 #pragma unroll
-    for (int k = 0; k < 3; k++) e1[k] = eg[k] - ege3 * e3[k];
-    const double n1 = norm3(e1);
+    for (int k = 0; k < 3; k++) e1[k] = s_sub(eg[k], s_mul(e3[k], ege3));
+    const double inv1 = 1.0 / s_norm3(e1);
 #pragma unroll
-    for (int k = 0; k < 3; k++) e1[k] = (1.0 / n1) * e1[k];
-    cross3(e2, e3, e1);
+    for (int k = 0; k < 3; k++) e1[k] = s_mul(e1[k], inv1);
+    s_cross3(e2, e3, e1);
 #pragma unroll
     for (int k = 0; k < 3; k++) { fr.R[k] = e1[k]; fr.R[3 + k] = e2[k]; fr.R[6 + k] = e3[k]; }
     fr.area = A;
-    double d23[3], d12[3], d32[3], d13[3];
+    double d23[3], d12[3], d32[3], d13[3], d31b[3], d21b[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        d23[k] = x[1][k] - x[2][k]; d12[k] = x[0][k] - x[1][k];
-        d32[k] = x[2][k] - x[1][k]; d13[k] = x[0][k] - x[2][k];
+        d23[k] = s_sub(x[1][k], x[2][k]); d31b[k] = s_sub(x[2][k], x[0][k]); d12[k] = s_sub(x[0][k], x[1][k]);
+        d32[k] = s_sub(x[2][k], x[1][k]); d13[k] = s_sub(x[0][k], x[2][k]); d21b[k] = s_sub(x[1][k], x[0][k]);
     }
-    fr.Lx[0] = 0.5 * dot3(d23, e2) / A; fr.Lx[1] = 0.5 * dot3(d31, e2) / A; fr.Lx[2] = 0.5 * dot3(d12, e2) / A;
-    fr.Ly[0] = 0.5 * dot3(d32, e1) / A; fr.Ly[1] = 0.5 * dot3(d13, e1) / A; fr.Ly[2] = 0.5 * dot3(d21, e1) / A;
+    fr.Lx[0] = s_mul(0.5, s_dot3(d23, e2)) / A; fr.Lx[1] = s_mul(0.5, s_dot3(d31b, e2)) / A; fr.Lx[2] = s_mul(0.5, s_dot3(d12, e2)) / A;
+    fr.Ly[0] = s_mul(0.5, s_dot3(d32, e1)) / A; fr.Ly[1] = s_mul(0.5, s_dot3(d13, e1)) / A; fr.Ly[2] = s_mul(0.5, s_dot3(d21b, e1)) / A;
 }
 // Shape functions at in-plane point g (located at mid-side node 4+g), :2029-2088
 struct Shape { double N1[6], N2[6], A0[3], A1[3], A2[3]; };
@@ -124,20 +127,22 @@ GFA_DI void shape_of(const double (&x)[6][3], const Frame& fr, int g, Shape& s) 
     const double* xp = x[3 + g];
     double a[3], b[3], c[3], t[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { a[k] = x[0][k] - xp[k]; b[k] = x[1][k] - xp[k]; c[k] = x[2][k] - xp[k]; }
-    cross3(t, b, c); const double L1 = (0.5 * norm3(t)) / fr.area;
-    cross3(t, c, a); const double L2 = (0.5 * norm3(t)) / fr.area;
-    cross3(t, a, b); const double L3 = (0.5 * norm3(t)) / fr.area;
+    for (int k = 0; k < 3; k++) { a[k] = s_sub(x[0][k], xp[k]); b[k] = s_sub(x[1][k], xp[k]); c[k] = s_sub(x[2][k], xp[k]); }
+    s_cross3(t, b, c); const double L1 = s_mul(0.5, s_norm3(t)) / fr.area;
+    s_cross3(t, c, a); const double L2 = s_mul(0.5, s_norm3(t)) / fr.area;
+    s_cross3(t, a, b); const double L3 = s_mul(0.5, s_norm3(t)) / fr.area;
     const double L[3] = { L1, L2, L3 };
     const double* Lx = fr.Lx; const double* Ly = fr.Ly;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        s.N1[k] = 4 * Lx[k] * L[k] - Lx[k];
-        s.N2[k] = 4 * Ly[k] * L[k] - Ly[k];
+        s.N1[k] = s_sub(s_mul(s_mul(4.0, Lx[k]), L[k]), Lx[k]);
+        s.N2[k] = s_sub(s_mul(s_mul(4.0, Ly[k]), L[k]), Ly[k]);
     }
-    s.N1[3] = 4 * Lx[0] * L2 + 4 * L1 * Lx[1]; s.N1[4] = 4 * Lx[1] * L3 + 4 * L2 * Lx[2]; s.N1[5] = 4 * Lx[2] * L1 + 4 * L3 * Lx[0];
-    s.N2[3] = 4 * Ly[0] * L2 + 4 * L1 * Ly[1]; s.N2[4] = 4 * Ly[1] * L3 + 4 * L2 * Ly[2]; s.N2[5] = 4 * Ly[2] * L1 + 4 * L3 * Ly[0];
-    s.A0[0] = 1 - 2 * L3; s.A0[1] = 1 - 2 * L1; s.A0[2] = 1 - 2 * L2;
+#define GFA_MIX(D_, i_, j_) s_add(s_mul(s_mul(4.0, D_[i_]), L[j_]), s_mul(s_mul(4.0, L[i_]), D_[j_]))
+    s.N1[3] = GFA_MIX(Lx, 0, 1); s.N1[4] = GFA_MIX(Lx, 1, 2); s.N1[5] = GFA_MIX(Lx, 2, 0);
+    s.N2[3] = GFA_MIX(Ly, 0, 1); s.N2[4] = GFA_MIX(Ly, 1, 2); s.N2[5] = GFA_MIX(Ly, 2, 0);
+#undef GFA_MIX
+    s.A0[0] = s_sub(1.0, s_mul(2.0, L3)); s.A0[1] = s_sub(1.0, s_mul(2.0, L1)); s.A0[2] = s_sub(1.0, s_mul(2.0, L2));
     s.A1[0] = -2 * Lx[2]; s.A1[1] = -2 * Lx[0]; s.A1[2] = -2 * Lx[1];
     s.A2[0] = -2 * Ly[2]; s.A2[1] = -2 * Ly[0]; s.A2[2] = -2 * Ly[1];
 }
@@ -147,28 +152,28 @@ struct Kin {
     double a[3], a1[3], a2[3], u1[3], u2[3];   // alpha_delta, its x1/x2 derivatives, u_delta,1 u_delta,2
 };
 GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Frame& fr, const Shape& s, Kin& k) {
-    double gu1[3] = { 0, 0, 0 }, gu2[3] = { 0, 0, 0 }, ga[3] = { 0, 0, 0 }, ga1[3] = { 0, 0, 0 }, ga2[3] = { 0, 0, 0 };
+    double gu1[3], gu2[3], ga[3], ga1[3], ga2[3];
 #pragma unroll
     for (int n = 0; n < 6; n++) {
         const double* d = A.disp + 6 * (size_t)nd[n];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const double v = __ldg(d + c);
-            gu1[c] += v * s.N1[n];
-            gu2[c] += v * s.N2[n];
+            gu1[c] = n == 0 ? s_mul(v, s.N1[0]) : s_add(gu1[c], s_mul(v, s.N1[n]));
+            gu2[c] = n == 0 ? s_mul(v, s.N2[0]) : s_add(gu2[c], s_mul(v, s.N2[n]));
         }
         if (n >= 3) {
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 const double r = __ldg(d + 3 + c);
-                ga[c] += r * s.A0[n - 3];
-                ga1[c] += r * s.A1[n - 3];
-                ga2[c] += r * s.A2[n - 3];
+                ga[c] = n == 3 ? s_mul(r, s.A0[0]) : s_add(ga[c], s_mul(r, s.A0[n - 3]));
+                ga1[c] = n == 3 ? s_mul(r, s.A1[0]) : s_add(ga1[c], s_mul(r, s.A1[n - 3]));
+                ga2[c] = n == 3 ? s_mul(r, s.A2[0]) : s_add(ga2[c], s_mul(r, s.A2[n - 3]));
             }
         }
     }
-    mv(k.u1, fr.R, gu1); mv(k.u2, fr.R, gu2);
-    mv(k.a, fr.R, ga); mv(k.a1, fr.R, ga1); mv(k.a2, fr.R, ga2);
+    s_mv(k.u1, fr.R, gu1); s_mv(k.u2, fr.R, gu2);
+    s_mv(k.a, fr.R, ga); s_mv(k.a1, fr.R, ga1); s_mv(k.a2, fr.R, ga2);
 }
 
 GFA_DI void load_nodes(const EvalArgs& A, int e, int* nd, double (&x)[6][3]) {
@@ -198,26 +203,26 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        z1[i] = kn.u1[i] + A.state[(9 + i) * n_gp + gp];      // z,1 = u_delta,1 + z,1^i  (:1010)
-        z2[i] = kn.u2[i] + A.state[(12 + i) * n_gp + gp];
+        z1[i] = s_add(kn.u1[i], A.state[(9 + i) * n_gp + gp]);      // z,1 = u_delta,1 + z,1^i  (:1010)
+        z2[i] = s_add(kn.u2[i], A.state[(12 + i) * n_gp + gp]);
         k1[i] = A.state[(15 + i) * n_gp + gp];
         k2[i] = A.state[(18 + i) * n_gp + gp];
     }
 
     double gg, Qd[9], Xi[9], Xi1[9], Xi2[9], Q[9], Qt[9];
-    rodrigues(kn.a, gg, Qd, Xi);
+    s_rodrigues(kn.a, gg, Qd, Xi);
     d_xi(Xi1, kn.a, kn.a1, gg, Xi);
     d_xi(Xi2, kn.a, kn.a2, gg, Xi);
-    mm(Q, Qd, Qi);
+    s_mm(Q, Qd, Qi);
     m_transpose(Qt, Q);
-    // back-rotated strains (:1017-1020)
+    // back-rotated strains (:1017-1020), strict
     double eta1[3], eta2[3], kap1[3], kap2[3], t3[3];
-    mv(eta1, Qt, z1); eta1[0] -= 1.0;
-    mv(eta2, Qt, z2); eta2[1] -= 1.0;
-    mtv(t3, Xi, kn.a1); mtv(kap1, Qi, t3);
-    mtv(t3, Xi, kn.a2); mtv(kap2, Qi, t3);
+    s_mv(eta1, Qt, z1); eta1[0] = s_sub(eta1[0], 1.0);
+    s_mv(eta2, Qt, z2); eta2[1] = s_sub(eta2[1], 1.0);
+    s_mtv(t3, Xi, kn.a1); s_mtv(kap1, Qi, t3);
+    s_mtv(t3, Xi, kn.a2); s_mtv(kap2, Qi, t3);
 #pragma unroll
-    for (int i = 0; i < 3; i++) { kap1[i] += k1[i]; kap2[i] += k2[i]; }
+    for (int i = 0; i < 3; i++) { kap1[i] = s_add(kap1[i], k1[i]); kap2[i] = s_add(kap2[i], k2[i]); }
 
     // thickness integration (:1056-1163): moments of the tangent blocks and resultants
     double X[3][3][4];
@@ -230,33 +235,39 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     double smu = 0.0;
     double n1[3] = { 0, 0, 0 }, n2[3] = { 0, 0, 0 }, m1[3] = { 0, 0, 0 }, m2[3] = { 0, 0, 0 };
     const double jac = thick / 2.0;
+    const double mu2 = s_mul(2.0, mu);
 #pragma unroll
     for (int q = 0; q < 3; q++) {
         const double csi = (q == 0) ? -0.77459666924148337703585307995648 : (q == 1) ? 0.0 : 0.77459666924148337703585307995648;
         const double al2 = (q == 1) ? 0.88888888888888888888888888888889 : 0.55555555555555555555555555555556;
-        const double zeta = thick * csi / 2.0;
-        // gamma = eta + zeta * kappa x e3
-        const double g11 = eta1[0] + zeta * kap1[1], g12 = eta1[1] + zeta * (-kap1[0]), g13 = eta1[2] + zeta * 0.0;
-        const double g21 = eta2[0] + zeta * kap2[1], g22 = eta2[1] + zeta * (-kap2[0]), g23 = eta2[2] + zeta * 0.0;
-        const double jb = (1.0 + g11) * (1.0 + g22) - g12 * g21;
-        const double v = (lam * (jb * jb * jb - 1.0) + 2.0 * mu * (jb - 1.0)) / (lam * jb * jb * jb + 2.0 * mu * jb);
-        const double dv = ((lam + 2.0 * mu) * (3.0 * lam * jb * jb + 2.0 * mu)) / (jb * jb * (lam * jb * jb + 2.0 * mu) * (lam * jb * jb + 2.0 * mu));
-        const double t1[3] = { mu * v * (1.0 + g22) + mu * (g11 - g22), mu * v * (-g21) + mu * (g12 + g21), 0 + mu * g13 };
-        const double t2[3] = { mu * v * (-g12) + mu * (g12 + g21), mu * v * (1.0 + g11) + mu * (g22 - g11), 0 + mu * g23 };
+        const double zeta = s_mul(thick, csi) / 2.0;
+        // gamma = eta + zeta * kappa x e3   (strict up to the resultants)
+        const double g11 = s_add(eta1[0], s_mul(zeta, kap1[1])), g12 = s_add(eta1[1], s_mul(zeta, -kap1[0])), g13 = eta1[2];
+        const double g21 = s_add(eta2[0], s_mul(zeta, kap2[1])), g22 = s_add(eta2[1], s_mul(zeta, -kap2[0])), g23 = eta2[2];
+        const double p11 = s_add(1.0, g11), p22 = s_add(1.0, g22);
+        const double jb = s_sub(s_mul(p11, p22), s_mul(g12, g21));
+        const double jb3 = s_mul(s_mul(jb, jb), jb);
+        const double ljj = s_mul(s_mul(lam, jb), jb);                      // lambda*jb*jb
+        const double v = s_add(s_mul(lam, s_sub(jb3, 1.0)), s_mul(mu2, s_sub(jb, 1.0))) / s_add(s_mul(ljj, jb), s_mul(mu2, jb));
+        const double cden = s_add(ljj, mu2);
+        const double dv = s_mul(s_add(lam, mu2), s_add(s_mul(s_mul(s_mul(3.0, lam), jb), jb), mu2)) / s_mul(s_mul(s_mul(jb, jb), cden), cden);
+        const double muv = s_mul(mu, v);
+        const double t1[3] = { s_add(s_mul(muv, p22), s_mul(mu, s_sub(g11, g22))), s_add(s_mul(muv, -g21), s_mul(mu, s_add(g12, g21))), s_mul(mu, g13) };
+        const double t2[3] = { s_add(s_mul(muv, -g12), s_mul(mu, s_add(g12, g21))), s_add(s_mul(muv, p11), s_mul(mu, s_sub(g22, g11))), s_mul(mu, g23) };
         double C[3][4];
-        C[0][0] = mu * ((1.0 + g22) * (1.0 + g22) * dv + 1.0);
-        C[0][1] = -mu * (1.0 + g22) * g21 * dv;
+        C[0][0] = mu * (p22 * p22 * dv + 1.0);
+        C[0][1] = -mu * p22 * g21 * dv;
         C[0][2] = C[0][1];
         C[0][3] = mu * (g21 * g21 * dv + 1.0);
         C[2][0] = mu * (g12 * g12 * dv + 1.0);
-        C[2][1] = -mu * ((1.0 + g11) * g12 * dv);
+        C[2][1] = -mu * (p11 * g12 * dv);
         C[2][2] = C[2][1];
-        C[2][3] = mu * ((1.0 + g11) * (1.0 + g11) * dv + 1.0);
-        C[1][0] = -mu * ((1.0 + g22) * g12 * dv);
-        C[1][1] = mu * (v - 1.0 + (1.0 + g11) * (1.0 + g22) * dv);
+        C[2][3] = mu * (p11 * p11 * dv + 1.0);
+        C[1][0] = -mu * (p22 * g12 * dv);
+        C[1][1] = mu * (v - 1.0 + p11 * p22 * dv);
         C[1][2] = mu * (1.0 - v + g12 * g21 * dv);
-        C[1][3] = -mu * ((1.0 + g11) * g21 * dv);
-        const double wj = al2 * jac, wz = wj * zeta, wzz = wz * zeta;
+        C[1][3] = -mu * (p11 * g21 * dv);
+        const double wj = s_mul(al2, jac), wz = s_mul(wj, zeta), wzz = wz * zeta;
 #pragma unroll
         for (int p = 0; p < 3; p++)
 #pragma unroll
@@ -267,13 +278,13 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
             }
         smu += wj * mu;
 #pragma unroll
-        for (int i = 0; i < 3; i++) { n1[i] += wj * t1[i]; n2[i] += wj * t2[i]; }
+        for (int i = 0; i < 3; i++) { n1[i] = s_add(n1[i], s_mul(wj, t1[i])); n2[i] = s_add(n2[i], s_mul(wj, t2[i])); }
         // m += wz * e3 x tau
-        m1[0] += wz * (-t1[1]); m1[1] += wz * t1[0];
-        m2[0] += wz * (-t2[1]); m2[1] += wz * t2[0];
+        m1[0] = s_add(m1[0], s_mul(wz, -t1[1])); m1[1] = s_add(m1[1], s_mul(wz, t1[0]));
+        m2[0] = s_add(m2[0], s_mul(wz, -t2[1])); m2[1] = s_add(m2[1], s_mul(wz, t2[0]));
     }
-    m1[2] = drill * kap1[2];                                  // drilling penalty (:1214-1217)
-    m2[2] = drill * kap2[2];
+    m1[2] = s_mul(drill, kap1[2]);                            // drilling penalty (:1214-1217)
+    m2[2] = s_mul(drill, kap2[2]);
 
     // Psi' = Psi (I5 (x) R): the four distinct left factors and the column-4 blocks (:1239-1270)
     double XiR[9], PA[9], PB[9], Y0[9], Y1[9], Y2[9], Y3[9], tmp[9], tmp2[9];
@@ -515,22 +526,22 @@ __global__ void commit_kernel(EvalArgs A) {
     Shape sh; shape_of(x, fr, g, sh);
     Kin kn; interpolate(A, nd, fr, sh, kn);
     double gg, Qd[9], Xi[9], Qi[9], Qn[9], t3[3], dk[3];
-    rodrigues(kn.a, gg, Qd, Xi);
+    s_rodrigues(kn.a, gg, Qd, Xi);
 #pragma unroll
     for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
-    mtv(t3, Xi, kn.a1); mtv(dk, Qi, t3);
+    s_mtv(t3, Xi, kn.a1); s_mtv(dk, Qi, t3);
 #pragma unroll
-    for (int i = 0; i < 3; i++) A.state[(15 + i) * n_gp + gp] = dk[i] + A.state[(15 + i) * n_gp + gp];
-    mtv(t3, Xi, kn.a2); mtv(dk, Qi, t3);
+    for (int i = 0; i < 3; i++) A.state[(15 + i) * n_gp + gp] = s_add(dk[i], A.state[(15 + i) * n_gp + gp]);
+    s_mtv(t3, Xi, kn.a2); s_mtv(dk, Qi, t3);
 #pragma unroll
-    for (int i = 0; i < 3; i++) A.state[(18 + i) * n_gp + gp] = dk[i] + A.state[(18 + i) * n_gp + gp];
-    mm(Qn, Qd, Qi);
+    for (int i = 0; i < 3; i++) A.state[(18 + i) * n_gp + gp] = s_add(dk[i], A.state[(18 + i) * n_gp + gp]);
+    s_mm(Qn, Qd, Qi);
 #pragma unroll
     for (int i = 0; i < 9; i++) A.state[i * n_gp + gp] = Qn[i];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        A.state[(9 + i) * n_gp + gp] = kn.u1[i] + A.state[(9 + i) * n_gp + gp];
-        A.state[(12 + i) * n_gp + gp] = kn.u2[i] + A.state[(12 + i) * n_gp + gp];
+        A.state[(9 + i) * n_gp + gp] = s_add(kn.u1[i], A.state[(9 + i) * n_gp + gp]);
+        A.state[(12 + i) * n_gp + gp] = s_add(kn.u2[i], A.state[(12 + i) * n_gp + gp]);
     }
 }
 
@@ -557,35 +568,37 @@ GFA_DI void geometry(const EvalArgs& A, int e, int g, const int* nd, const doubl
     for (int i = 0; i < 9; i++) go.R[i] = __ldg(pr + 36 + i);
     double d[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) d[c] = __ldg(A.xyz + 3 * (size_t)nd[2] + c) - __ldg(A.xyz + 3 * (size_t)nd[0] + c);
-    const double len = norm3(d);
+    for (int c = 0; c < 3; c++) d[c] = s_sub(__ldg(A.xyz + 3 * (size_t)nd[2] + c), __ldg(A.xyz + 3 * (size_t)nd[0] + c));
+    const double len = s_norm3(d);
     double e3[3];
+    const double inv = 1.0 / len;
 #pragma unroll
-    for (int c = 0; c < 3; c++) e3[c] = (1.0 / len) * d[c];
-    mv(go.e3r, go.R, e3);                                         // Beam_1.cpp:609-614
+    for (int c = 0; c < 3; c++) e3[c] = s_mul(d[c], inv);
+    s_mv(go.e3r, go.R, e3);                                       // Beam_1.cpp:609-614
     const double T0 = A.pret ? __ldg(A.pret + e) : 0.0;
     const double du0 = T0 / __ldg(pr + 14);                       // D(2,2) = EA  (:616-621)
-    const double length = len / (1.0 + du0);
+    const double length = len / s_add(1.0, du0);
     go.jac = length / 2.0;
     const double xi = g == 0 ? -0.577350269189626 : 0.577350269189626;
-    go.N[0] = 0.5 * xi * (xi - 1.0); go.N[1] = 1.0 - xi * xi; go.N[2] = 0.5 * xi * (1.0 + xi);
-    go.dN[0] = (1.0 / go.jac) * (xi - 0.5); go.dN[1] = (1.0 / go.jac) * (-2.0 * xi); go.dN[2] = (1.0 / go.jac) * (0.5 + xi);
+    const double ij = 1.0 / go.jac;
+    go.N[0] = s_mul(s_mul(0.5, xi), s_sub(xi, 1.0)); go.N[1] = s_sub(1.0, s_mul(xi, xi)); go.N[2] = s_mul(s_mul(0.5, xi), s_add(1.0, xi));
+    go.dN[0] = s_mul(ij, s_sub(xi, 0.5)); go.dN[1] = s_mul(ij, s_mul(-2.0, xi)); go.dN[2] = s_mul(ij, s_add(0.5, xi));
 }
 struct Kin { double a[3], da[3], du[3]; };
 GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Geo& go, Kin& k) {
-    double ga[3] = { 0, 0, 0 }, gda[3] = { 0, 0, 0 }, gdu[3] = { 0, 0, 0 };
+    double ga[3], gda[3], gdu[3];
 #pragma unroll
     for (int n = 0; n < 3; n++) {
         const double* d = A.disp + 6 * (size_t)nd[n];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double r = __ldg(d + 3 + c);
-            ga[c] += r * go.N[n];
-            gda[c] += r * go.dN[n];
-            gdu[c] += __ldg(d + c) * go.dN[n];
+            const double r = __ldg(d + 3 + c), u = __ldg(d + c);
+            ga[c] = n == 0 ? s_mul(r, go.N[0]) : s_add(ga[c], s_mul(r, go.N[n]));
+            gda[c] = n == 0 ? s_mul(r, go.dN[0]) : s_add(gda[c], s_mul(r, go.dN[n]));
+            gdu[c] = n == 0 ? s_mul(u, go.dN[0]) : s_add(gdu[c], s_mul(u, go.dN[n]));
         }
     }
-    mv(k.a, go.R, ga); mv(k.da, go.R, gda); mv(k.du, go.R, gdu);   // :743-746
+    s_mv(k.a, go.R, ga); s_mv(k.da, go.R, gda); s_mv(k.du, go.R, gdu);   // :743-746
 }
 
 // y(3x3) = D_rs (3x3 block of the 6x6 section matrix) * P
@@ -621,26 +634,26 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
 #pragma unroll
     for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
 #pragma unroll
-    for (int i = 0; i < 3; i++) { dz[i] = kn.du[i] + A.state[(9 + i) * n_gp + gp]; ki[i] = A.state[(12 + i) * n_gp + gp]; }
+    for (int i = 0; i < 3; i++) { dz[i] = s_add(kn.du[i], A.state[(9 + i) * n_gp + gp]); ki[i] = A.state[(12 + i) * n_gp + gp]; }
 
     double gg, Qd[9], Xi[9], dXi[9], Q[9], Qt[9];
-    rodrigues(kn.a, gg, Qd, Xi);
+    s_rodrigues(kn.a, gg, Qd, Xi);
     d_xi(dXi, kn.a, kn.da, gg, Xi);
-    mm(Q, Qd, Qi);
+    s_mm(Q, Qd, Qi);
     m_transpose(Qt, Q);
     double eps[6], sig[6], t3[3];
-    mv(eps, Qt, dz);
+    s_mv(eps, Qt, dz);
 #pragma unroll
-    for (int i = 0; i < 3; i++) eps[i] -= go.e3r[i];             // eta_r (:778)
-    mtv(t3, Xi, kn.da); mtv(eps + 3, Qi, t3);
+    for (int i = 0; i < 3; i++) eps[i] = s_sub(eps[i], go.e3r[i]);   // eta_r (:778), strict
+    s_mtv(t3, Xi, kn.da); s_mtv(eps + 3, Qi, t3);
 #pragma unroll
-    for (int i = 0; i < 3; i++) eps[3 + i] += ki[i];             // kappa_r (:779)
+    for (int i = 0; i < 3; i++) eps[3 + i] = s_add(eps[3 + i], ki[i]);   // kappa_r (:779)
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        double s = 0.0;
+        double sacc = s_mul(D6[6 * i], eps[0]);
 #pragma unroll
-        for (int j = 0; j < 6; j++) s += D6[6 * i + j] * eps[j];
-        sig[i] = s;                                               // sigma_r = D eps (:788)
+        for (int j = 1; j < 6; j++) sacc = s_add(sacc, s_mul(D6[6 * i + j], eps[j]));
+        sig[i] = sacc;                                            // sigma_r = D eps (:788)
     }
     double n[3], m[3];
     mv(n, Q, sig); mv(m, Q, sig + 3);                            // spatial resultants (:796-797)
@@ -805,16 +818,16 @@ __global__ void commit_kernel(EvalArgs A) {
     Geo go; geometry(A, e, g, nd, pr, go);
     Kin kn; interpolate(A, nd, go, kn);
     double gg, Qd[9], Xi[9], Qi[9], Qn[9], t3[3], kr[3];
-    rodrigues(kn.a, gg, Qd, Xi);
+    s_rodrigues(kn.a, gg, Qd, Xi);
 #pragma unroll
     for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
-    mtv(t3, Xi, kn.da); mtv(kr, Qi, t3);
+    s_mtv(t3, Xi, kn.da); s_mtv(kr, Qi, t3);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        A.state[(12 + i) * n_gp + gp] = kr[i] + A.state[(12 + i) * n_gp + gp];   // kappa_i_ref = kappa_r
-        A.state[(9 + i) * n_gp + gp] = kn.du[i] + A.state[(9 + i) * n_gp + gp];  // dz_i = d_z
+        A.state[(12 + i) * n_gp + gp] = s_add(kr[i], A.state[(12 + i) * n_gp + gp]);   // kappa_i_ref = kappa_r
+        A.state[(9 + i) * n_gp + gp] = s_add(kn.du[i], A.state[(9 + i) * n_gp + gp]);  // dz_i = d_z
     }
-    mm(Qn, Qd, Qi);
+    s_mm(Qn, Qd, Qi);
 #pragma unroll
     for (int i = 0; i < 9; i++) A.state[i * n_gp + gp] = Qn[i];
 }
@@ -847,58 +860,65 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     const double xi = gpc * sgn[g][0], et = gpc * sgn[g][1], ze = gpc * sgn[g][2];
     const double* pr = A.props + SOLID_PROP_STRIDE * (size_t)__ldg(A.prop + e);
     const double lam = __ldg(pr), mu = __ldg(pr + 1), rho = __ldg(pr + 2);
+    // strict arithmetic up to the second Piola-Kirchhoff stress: E = (F^T F - I)/2
+    // is a difference of O(1) quantities (see gfa_math.cuh)
     double J[9], F[9], dNl[8][3], Nn[8], un[8][3];
-    m_zero(J);
 #pragma unroll
     for (int a = 0; a < 8; a++) {
         const int nd = __ldg(A.conn + 8 * (size_t)e + a);
         const double sx = sgn[a][0], sy = sgn[a][1], sz = sgn[a][2];
-        Nn[a] = 0.125 * (1 + sx * xi) * (1 + sy * et) * (1 + sz * ze);
-        dNl[a][0] = 0.125 * sx * (1 + sy * et) * (1 + sz * ze);
-        dNl[a][1] = 0.125 * sy * (1 + sx * xi) * (1 + sz * ze);
-        dNl[a][2] = 0.125 * sz * (1 + sx * xi) * (1 + sy * et);
+        const double fx = s_add(1.0, s_mul(sx, xi)), fy = s_add(1.0, s_mul(sy, et)), fz = s_add(1.0, s_mul(sz, ze));
+        Nn[a] = s_mul(s_mul(s_mul(0.125, fx), fy), fz);
+        dNl[a][0] = s_mul(s_mul(s_mul(0.125, sx), fy), fz);
+        dNl[a][1] = s_mul(s_mul(s_mul(0.125, sy), fx), fz);
+        dNl[a][2] = s_mul(s_mul(s_mul(0.125, sz), fx), fy);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const double X = __ldg(A.xyz + 3 * (size_t)nd + i);
-            un[a][i] = (__ldg(A.copy + 6 * (size_t)nd + i) - X) + __ldg(A.disp + 6 * (size_t)nd + i);
+            un[a][i] = s_add(s_sub(__ldg(A.copy + 6 * (size_t)nd + i), X), __ldg(A.disp + 6 * (size_t)nd + i));
 #pragma unroll
-            for (int j = 0; j < 3; j++) J[3 * i + j] += X * dNl[a][j];
+            for (int j = 0; j < 3; j++) J[3 * i + j] = a == 0 ? s_mul(X, dNl[0][j]) : s_add(J[3 * i + j], s_mul(X, dNl[a][j]));
         }
     }
-    const double det = J[0] * (J[4] * J[8] - J[5] * J[7]) - J[1] * (J[3] * J[8] - J[5] * J[6]) + J[2] * (J[3] * J[7] - J[4] * J[6]);
+#define GFA_M2(a_, b_, c_, d_) s_sub(s_mul(J[a_], J[b_]), s_mul(J[c_], J[d_]))
+    const double det = s_add(s_sub(s_mul(J[0], GFA_M2(4, 8, 5, 7)), s_mul(J[1], GFA_M2(3, 8, 5, 6))), s_mul(J[2], GFA_M2(3, 7, 4, 6)));
     double Ji[9];
-    Ji[0] = (J[4] * J[8] - J[5] * J[7]) / det; Ji[1] = (J[2] * J[7] - J[1] * J[8]) / det; Ji[2] = (J[1] * J[5] - J[2] * J[4]) / det;
-    Ji[3] = (J[5] * J[6] - J[3] * J[8]) / det; Ji[4] = (J[0] * J[8] - J[2] * J[6]) / det; Ji[5] = (J[2] * J[3] - J[0] * J[5]) / det;
-    Ji[6] = (J[3] * J[7] - J[4] * J[6]) / det; Ji[7] = (J[1] * J[6] - J[0] * J[7]) / det; Ji[8] = (J[0] * J[4] - J[1] * J[3]) / det;
+    Ji[0] = GFA_M2(4, 8, 5, 7) / det; Ji[1] = GFA_M2(2, 7, 1, 8) / det; Ji[2] = GFA_M2(1, 5, 2, 4) / det;
+    Ji[3] = GFA_M2(5, 6, 3, 8) / det; Ji[4] = GFA_M2(0, 8, 2, 6) / det; Ji[5] = GFA_M2(2, 3, 0, 5) / det;
+    Ji[6] = GFA_M2(3, 7, 4, 6) / det; Ji[7] = GFA_M2(1, 6, 0, 7) / det; Ji[8] = GFA_M2(0, 4, 1, 3) / det;
+#undef GFA_M2
     F[0] = 1; F[1] = 0; F[2] = 0; F[3] = 0; F[4] = 1; F[5] = 0; F[6] = 0; F[7] = 0; F[8] = 1;
 #pragma unroll
     for (int a = 0; a < 8; a++) {
         double dN[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            double v = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; k++) v += dNl[a][k] * Ji[3 * k + j];
+            const double v = s_add(s_add(s_mul(dNl[a][0], Ji[j]), s_mul(dNl[a][1], Ji[3 + j])), s_mul(dNl[a][2], Ji[6 + j]));
             dN[j] = v;
             rec[S_OFF + 8 * j + a] = v;
         }
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) F[3 * i + j] += un[a][i] * dN[j];
+            for (int j = 0; j < 3; j++) F[3 * i + j] = s_add(F[3 * i + j], s_mul(un[a][i], dN[j]));
         rec[N_OFF + a] = Nn[a];
     }
     double Cg[9], Bm[9];
-    mtm(Cg, F, F);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            Cg[3 * i + j] = s_add(s_add(s_mul(F[i], F[j]), s_mul(F[3 + i], F[3 + j])), s_mul(F[6 + i], F[6 + j]));
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
         for (int k = 0; k < 3; k++) Bm[3 * i + k] = F[3 * i] * F[3 * k] + F[3 * i + 1] * F[3 * k + 1] + F[3 * i + 2] * F[3 * k + 2];
-    const double E0 = 0.5 * (Cg[0] - 1.0), E1 = 0.5 * (Cg[4] - 1.0), E2 = 0.5 * (Cg[8] - 1.0);
-    const double trE = E0 + E1 + E2;
+    const double E0 = s_mul(0.5, s_sub(Cg[0], 1.0)), E1 = s_mul(0.5, s_sub(Cg[4], 1.0)), E2 = s_mul(0.5, s_sub(Cg[8], 1.0));
+    const double trE = s_add(s_add(E0, E1), E2);
+    const double mu2 = s_mul(2.0, mu), ltr = s_mul(lam, trE);
     double S[9];
-    S[0] = lam * trE + 2 * mu * E0; S[4] = lam * trE + 2 * mu * E1; S[8] = lam * trE + 2 * mu * E2;
-    S[1] = S[3] = mu * Cg[1]; S[5] = S[7] = mu * Cg[5]; S[2] = S[6] = mu * Cg[2];
+    S[0] = s_add(ltr, s_mul(mu2, E0)); S[4] = s_add(ltr, s_mul(mu2, E1)); S[8] = s_add(ltr, s_mul(mu2, E2));
+    S[1] = S[3] = s_mul(mu, Cg[1]); S[5] = S[7] = s_mul(mu, Cg[5]); S[2] = S[6] = s_mul(mu, Cg[2]);
     double P[9];
     mm(P, F, S);
     const double w = det;      // Gauss weights are 1

@@ -139,4 +139,57 @@ GFA_DI void dv_op(double* V, const double* x, const double* dx, const double* t,
             V[3 * i + j] = xd * (w1[i] * x[j]) + w2[i] * dx[j] + w3[i] * x[j] + (h4 * xd) * S[3 * i + j];
 }
 
+// -------------------------------------------------------------------------
+// "Strict" arithmetic: separately rounded multiply / add in a fixed order.
+// The back-rotated strains eta = Q^T z' - e (and J - 1 in the shell's
+// constitutive law) are differences of O(1) quantities; for strains of 1e-5
+// one ulp of Q^T z' is 1e-11 of the strain, hence of the internal force.  To
+// agree with the reference to 1e-12 the kinematic chain from the nodal
+// displacements up to the stress resultants must round exactly like the
+// reference's mul-then-add Matrix arithmetic (no FMA contraction, k-inner
+// accumulation as in Matrix.cpp:218-250).  Everything downstream of the
+// resultants (the bulk of the flops) uses FMA freely.
+// -------------------------------------------------------------------------
+GFA_DI double s_mul(double a, double b) { return __dmul_rn(a, b); }
+GFA_DI double s_add(double a, double b) { return __dadd_rn(a, b); }
+GFA_DI double s_sub(double a, double b) { return __dsub_rn(a, b); }
+GFA_DI double s_dot3(const double* a, const double* b) {
+    return s_add(s_add(s_mul(a[0], b[0]), s_mul(a[1], b[1])), s_mul(a[2], b[2]));
+}
+GFA_DI double s_norm3(const double* a) { return sqrt(s_dot3(a, a)); }
+GFA_DI void s_cross3(double* c, const double* a, const double* b) {
+    c[0] = s_sub(s_mul(a[1], b[2]), s_mul(a[2], b[1]));
+    c[1] = s_sub(s_mul(a[2], b[0]), s_mul(a[0], b[2]));
+    c[2] = s_sub(s_mul(a[0], b[1]), s_mul(a[1], b[0]));
+}
+GFA_DI void s_mv(double* y, const double* A, const double* x) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) y[i] = s_add(s_add(s_mul(A[3 * i], x[0]), s_mul(A[3 * i + 1], x[1])), s_mul(A[3 * i + 2], x[2]));
+}
+GFA_DI void s_mtv(double* y, const double* A, const double* x) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) y[i] = s_add(s_add(s_mul(A[i], x[0]), s_mul(A[3 + i], x[1])), s_mul(A[6 + i], x[2]));
+}
+GFA_DI void s_mm(double* C, const double* A, const double* B) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            C[3 * i + j] = s_add(s_add(s_mul(A[3 * i], B[j]), s_mul(A[3 * i + 1], B[3 + j])), s_mul(A[3 * i + 2], B[6 + j]));
+}
+// Rodrigues pieces with the reference's rounding (Shell_1.cpp:1001-1005)
+GFA_DI void s_rodrigues(const double* a, double& g, double* Qd, double* Xi) {
+    const double al = s_norm3(a);
+    g = 4.0 / s_add(4.0, s_mul(al, al));
+    double A[9], AA[9];
+    skew3(A, a);
+    s_mm(AA, A, A);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+        Qd[i] = s_add(id, s_mul(g, s_add(A[i], s_mul(0.5, AA[i]))));
+        Xi[i] = s_mul(g, s_add(id, s_mul(0.5, A[i])));
+    }
+}
+
 } // namespace gfa
