@@ -27,7 +27,7 @@ EXPORTS = [
     "gfa_csr_dims", "gfa_csr_pattern", "gfa_assemble", "gfa_add_host_triplets", "gfa_add_host_vector",
     "gfa_csr_values", "gfa_csr_values_device", "gfa_vector", "gfa_vector_device", "gfa_element_block",
     "gfa_commit_state", "gfa_element_state", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
-    "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_owned_rows", "gfa_stream",
+    "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library() -> C.CDLL:
         lib.gfa_interface_pack.argtypes = [C.c_void_p, C.c_void_p]
         lib.gfa_interface_unpack.argtypes = [C.c_void_p, C.c_void_p]
         lib.gfa_owned_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+        lib.gfa_local_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
         lib.gfa_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         _lib = lib
     return _lib
@@ -301,6 +302,13 @@ class Assembler:
 
     def interface_unpack(self, device_ptr: int):
         self._check(self.lib.gfa_interface_unpack(self._h, device_ptr))
+
+    def local_rows(self):
+        n = C.c_int64()
+        self._check(self.lib.gfa_local_rows(self._h, C.byref(n), None))
+        rows = np.zeros(n.value, np.int32)
+        self._check(self.lib.gfa_local_rows(self._h, C.byref(n), _ptr(rows)))
+        return rows
 
     def owned_rows(self):
         n = C.c_int64()

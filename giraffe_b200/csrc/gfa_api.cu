@@ -84,13 +84,16 @@ struct TypeBlock {
     long long ke_base = 0;
     int pe_base = 0;
     DevBuf<int> d_conn, d_prop;
-    DevBuf<double> d_props, d_pret, d_state;
+    DevBuf<double> d_props, d_pret, d_state, d_geo, d_shp;
 };
 
 struct HostCsr {
     std::vector<long long> rowptr;
     std::vector<int> inner;
     int rows = 0, cols = 0;
+    // AA only: rows stored on this rank (all rows when world == 1) and the
+    // inverse map global row -> local row (-1 = row lives on other ranks only)
+    std::vector<int> row_ids, row_local;
 };
 
 } // namespace
@@ -120,8 +123,8 @@ struct gfa_handle {
     long long vec_off[3] = { 0, 0, 0 };              // PA, IA, PB
     long long arena_size = 0;
     DevBuf<double> d_arena;
-    DevBuf<long long> d_rowptrAA;
-    DevBuf<int> d_gn_gl, d_inc_ptr;
+    DevBuf<long long> d_gn_row;
+    DevBuf<int> d_gn_gl, d_gn_len, d_inc_ptr;
     DevBuf<Incidence> d_inc;
     int n_gn_local = 0, max_row = 0;
     DevBuf<long long> d_gseg, d_gsrc, d_gdest;
@@ -146,6 +149,7 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
     a.pret = t.any_pret ? t.d_pret.p : nullptr;
     a.xyz = h->d_xyz.p; a.copy = h->d_copy.p; a.disp = h->d_disp.p;
     a.state = t.d_state.p;
+    a.geo = t.d_geo.p; a.shp = t.d_shp.p;
     a.Ke = h->d_Ke.p + t.ke_base;
     a.Pe = h->d_Pe.p + t.pe_base;
     const double f = h->gravity_on ? gfac : 0.0;
@@ -316,11 +320,19 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         if (pe > 0x7fffffffLL) FAIL_FREE(GFA_EUNSUPPORTED, "element force arena exceeds 2^31 entries");
         if (e == cudaSuccess) e = h->d_Ke.alloc((size_t)ke);
         if (e == cudaSuccess) e = h->d_Pe.alloc((size_t)pe);
+        if (e == cudaSuccess) e = h->tb[0].d_geo.alloc(10 * h->tb[0].elems.size());
+        if (e == cudaSuccess) e = h->tb[0].d_shp.alloc(21 * 3 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
         if (e != cudaSuccess) FAIL_FREE(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "device set-up: %s", cudaGetErrorString(e));
     }
 #undef FAIL_FREE
+    // Shell_1::PreCalc on the device (frames, areas, shape functions)
+    launch_shell_precalc(eval_args(h, 0, 0.0), h->tb[0].d_geo.p, h->tb[0].d_shp.p, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        delete h;
+        return fail(GFA_ECUDA, "Shell_1 PreCalc kernel failed");
+    }
     *out = h;
     return GFA_OK;
 }
@@ -396,7 +408,30 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     auto fix_mask = [&](size_t gn) { int mk = 0; for (int k = 0; k < 3; k++) if (gls[3 * gn + k] < 0) mk |= 1 << k; return mk; };
     // note: gls is [node][6] = [group-node][3] with gn = node*2 + grp
 
-    // ---- neighbour lists (sorted group-node ids) -------------------------
+    // ---- which rank evaluates which element (same rule as gfa_create) -----
+    std::vector<int> el_rank;
+    if (h->world > 1) {
+        el_rank.resize(h->n_el);
+        long long seen[3] = { 0, 0, 0 };
+        for (int e = 0; e < h->n_el; e++) {
+            const int s = type_slot(h->el_type[e]);
+            const long long k = seen[s]++;
+            int r = (int)((k * h->world) / std::max<long long>(h->type_count[s], 1));
+            while (r > 0 && k < h->type_count[s] * r / h->world) r--;
+            while (r < h->world - 1 && k >= h->type_count[s] * (r + 1) / h->world) r++;
+            el_rank[e] = r;
+        }
+    }
+    // group-nodes whose rows this rank stores: those its own elements touch
+    std::vector<unsigned char> need(n_gn_all, 0);
+    for (size_t gn = 0; gn < n_gn_all; gn++) {
+        if (gptr[gn] == gptr[gn + 1]) continue;
+        if (h->world == 1) { need[gn] = 1; continue; }
+        for (int p = gptr[gn]; p < gptr[gn + 1]; p++) if (el_rank[ginc_e[p]] == h->rank) { need[gn] = 1; break; }
+    }
+
+    // ---- neighbour lists (sorted group-node ids), over ALL incident elements so
+    //      that a stored row carries its complete global column set ------------
     std::vector<long long> nptr(n_gn_all + 1, 0);
     {
         std::vector<int> cnt(n_gn_all, 0);
@@ -405,7 +440,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
             for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
-                if (gptr[gn] == gptr[gn + 1]) continue;
+                if (!need[gn]) continue;
                 tmp.clear();
                 for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
                     const int e = ginc_e[p], s = type_slot(h->el_type[e]);
@@ -426,7 +461,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
         for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
-            if (gptr[gn] == gptr[gn + 1]) continue;
+            if (!need[gn]) continue;
             tmp.clear();
             for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
                 const int e = ginc_e[p], s = type_slot(h->el_type[e]);
@@ -441,27 +476,41 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
     }
 
-    // ---- AA pattern: rows of a group-node share one column layout ---------
+    // ---- AA pattern: rows of a group-node share one column layout.  Stored
+    //      rows are numbered in ascending global order (all rows when world == 1,
+    //      so the single-GPU CSR is exactly the reference's). ------------------
     HostCsr& AA = h->csr[GFA_AA];
-    AA.rows = n_free; AA.cols = n_free;
-    AA.rowptr.assign((size_t)n_free + 1, 0);
+    AA.cols = n_free;
+    AA.row_local.assign((size_t)n_free, -1);
+    AA.row_ids.clear();
+    if (h->world == 1) {
+        AA.row_ids.resize((size_t)n_free);
+        for (int r = 0; r < n_free; r++) { AA.row_ids[r] = r; AA.row_local[r] = r; }
+    } else {
+        for (size_t gn = 0; gn < n_gn_all; gn++)
+            if (need[gn]) for (int k = 0; k < 3; k++) { const int g = gls[3 * gn + k]; if (g > 0) AA.row_ids.push_back(g - 1); }
+        std::sort(AA.row_ids.begin(), AA.row_ids.end());
+        for (size_t i = 0; i < AA.row_ids.size(); i++) AA.row_local[AA.row_ids[i]] = (int)i;
+    }
+    AA.rows = (int)AA.row_ids.size();
+    AA.rowptr.assign((size_t)AA.rows + 1, 0);
     for (size_t gn = 0; gn < n_gn_all; gn++) {
-        if (gptr[gn] == gptr[gn + 1]) continue;
+        if (!need[gn]) continue;
         long long L = 0;
         for (long long q = nptr[gn]; q < nptr[gn + 1]; q++) L += __builtin_popcount(free_mask((size_t)nbr[q]));
-        for (int k = 0; k < 3; k++) { const int g = gls[3 * gn + k]; if (g > 0) AA.rowptr[g] = L; }
+        for (int k = 0; k < 3; k++) { const int g = gls[3 * gn + k]; if (g > 0) AA.rowptr[AA.row_local[g - 1] + 1] = L; }
     }
-    for (int r = 0; r < n_free; r++) AA.rowptr[r + 1] += AA.rowptr[r];
-    const long long nnzAA = AA.rowptr[n_free];
-    if (nnzAA > 0x7fffffffLL) return fail(GFA_EUNSUPPORTED, "AA has %lld non-zeros; 32-bit CSR (PARDISO/Eigen int) cannot hold it", nnzAA);
+    for (int r = 0; r < AA.rows; r++) AA.rowptr[r + 1] += AA.rowptr[r];
+    const long long nnzAA = AA.rowptr[AA.rows];
+    if (nnzAA > 0x7fffffffLL) return fail(GFA_EUNSUPPORTED, "AA has %lld non-zeros on this rank; 32-bit CSR (PARDISO/Eigen int) cannot hold it", nnzAA);
     AA.inner.resize((size_t)nnzAA);
 #pragma omp parallel for schedule(dynamic, 4096)
     for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
-        if (gptr[gn] == gptr[gn + 1]) continue;
+        if (!need[gn]) continue;
         for (int k = 0; k < 3; k++) {
             const int g = gls[3 * gn + k];
             if (g <= 0) continue;
-            int* out = AA.inner.data() + AA.rowptr[g - 1];
+            int* out = AA.inner.data() + AA.rowptr[AA.row_local[g - 1]];
             for (long long q = nptr[gn]; q < nptr[gn + 1]; q++)
                 for (int c = 0; c < 3; c++) { const int gc = gls[3 * (size_t)nbr[q] + c]; if (gc > 0) *out++ = gc - 1; }
         }
@@ -501,7 +550,9 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         const int nr = (w == GFA_AA || w == GFA_AB) ? n_free : n_fixed, nc = (w == GFA_AA || w == GFA_BA) ? n_free : n_fixed;
         if (r < 0 || r >= nr || c < 0 || c >= nc) return fail(GFA_EINVAL, "extra pattern entry %lld out of range", (long long)i);
         if (w == GFA_AA) {
-            const int* b = AA.inner.data() + AA.rowptr[r]; const int* e2 = AA.inner.data() + AA.rowptr[r + 1];
+            const int lr = AA.row_local[r];
+            if (lr < 0) continue;           // row stored on other ranks only
+            const int* b = AA.inner.data() + AA.rowptr[lr]; const int* e2 = AA.inner.data() + AA.rowptr[lr + 1];
             if (!std::binary_search(b, e2, c))
                 return fail(GFA_EUNSUPPORTED, "extra AA position (%d,%d) lies outside the element pattern; host contributors that couple otherwise unconnected DOFs are not supported yet", r, c);
         } else { Ent en; en.mat = w; en.row = r; en.col = c; en.src = -1; ents.push_back(en); }
@@ -559,25 +610,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     int max_row = 1;
     // interface ownership: owner = lowest rank with an incidence
     std::vector<std::vector<long long> > send_idx(h->world), recv_idx(h->world);
-    auto rank_of = [&](int e) {
-        // rank that evaluates element e (same partition rule as gfa_create)
-        return 0;
-    };
-    (void)rank_of;
-    std::vector<int> el_rank;
-    if (h->world > 1) {
-        el_rank.resize(h->n_el);
-        long long seen[3] = { 0, 0, 0 };
-        for (int e = 0; e < h->n_el; e++) {
-            const int s = type_slot(h->el_type[e]);
-            const long long k = seen[s]++;
-            // smallest r with k < count*(r+1)/world
-            int r = (int)((k * h->world) / std::max<long long>(h->type_count[s], 1));
-            while (r > 0 && k < h->type_count[s] * r / h->world) r--;
-            while (r < h->world - 1 && k >= h->type_count[s] * (r + 1) / h->world) r++;
-            el_rank[e] = r;
-        }
-    }
+    std::vector<long long> gn_row;
+    std::vector<int> gn_len;
     h->owned_rows.clear();
     for (size_t gn = 0; gn < n_gn_all; gn++) {
         if (gptr[gn] == gptr[gn + 1]) continue;
@@ -597,7 +631,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 for (int k = 0; k < 3; k++) {
                     const int g = gls[3 * gn + k];
                     if (g > 0) {
-                        for (long long p = 0; p < L; p++) dst.push_back(h->arena_off[GFA_AA] + AA.rowptr[g - 1] + p);
+                        for (long long p = 0; p < L; p++) dst.push_back(h->arena_off[GFA_AA] + AA.rowptr[AA.row_local[g - 1]] + p);
                         dst.push_back(h->vec_off[GFA_P_A] + g - 1);
                         dst.push_back(h->vec_off[GFA_I_A] + g - 1);
                     } else if (g < 0) dst.push_back(h->vec_off[GFA_P_B] + (-g - 1));
@@ -634,7 +668,12 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         if ((int)incs.size() == first_inc) continue;
         gn_list.push_back((int)gn);
         inc_ptr.push_back((int)incs.size());
-        for (int k = 0; k < 3; k++) gn_gl.push_back(gls[3 * gn + k]);
+        for (int k = 0; k < 3; k++) {
+            const int g = gls[3 * gn + k];
+            gn_gl.push_back(g);
+            gn_row.push_back(g > 0 ? AA.rowptr[AA.row_local[g - 1]] : -1);
+        }
+        gn_len.push_back((int)L);
         if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
     }
     if ((size_t)max_row * 3 * 4 * sizeof(double) > 200 * 1024)
@@ -645,7 +684,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
     CUDA_TRY(cudaMemset(h->d_arena.p, 0, (size_t)h->arena_size * sizeof(double)));
-    CUDA_TRY(h->d_rowptrAA.upload(AA.rowptr));
+    CUDA_TRY(h->d_gn_row.upload(gn_row));
+    CUDA_TRY(h->d_gn_len.upload(gn_len));
     CUDA_TRY(h->d_gn_gl.upload(gn_gl));
     CUDA_TRY(h->d_inc_ptr.upload(inc_ptr));
     CUDA_TRY(h->d_inc.upload(incs));
@@ -707,7 +747,7 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
     if (h->n_gn_local > 0) {
         ScatterArgs a;
         a.n_gn = h->n_gn_local; a.gn_gl = h->d_gn_gl.p; a.inc_ptr = h->d_inc_ptr.p; a.inc = h->d_inc.p;
-        a.rowptr = h->d_rowptrAA.p; a.Ke = h->d_Ke.p; a.Pe = h->d_Pe.p;
+        a.gn_row = h->d_gn_row.p; a.gn_len = h->d_gn_len.p; a.Ke = h->d_Ke.p; a.Pe = h->d_Pe.p;
         a.valAA = h->d_arena.p + h->arena_off[GFA_AA];
         a.PA = h->d_arena.p + h->vec_off[GFA_P_A]; a.IA = h->d_arena.p + h->vec_off[GFA_I_A]; a.PB = h->d_arena.p + h->vec_off[GFA_P_B];
         a.max_row = h->max_row;
@@ -742,11 +782,17 @@ int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, c
     std::vector<long long> order;
     for (int64_t i = 0; i < n; i++) {
         const int r = rows[i], c = cols[i];
-        if (r < 0 || r >= M.rows) return fail(GFA_EPATTERN, "host triplet %lld: row %d outside the matrix", (long long)i, r);
-        const int* b = M.inner.data() + M.rowptr[r]; const int* e = M.inner.data() + M.rowptr[r + 1];
+        const int n_rows_global = (which == GFA_AA || which == GFA_AB) ? h->n_free : h->n_fixed;
+        if (r < 0 || r >= n_rows_global) return fail(GFA_EPATTERN, "host triplet %lld: row %d outside the matrix", (long long)i, r);
+        int lr = r;
+        if (which == GFA_AA) {
+            lr = M.row_local[r];
+            if (lr < 0) return fail(GFA_EPATTERN, "host triplet row %d is not stored on rank %d", r, h->rank);
+        }
+        const int* b = M.inner.data() + M.rowptr[lr]; const int* e = M.inner.data() + M.rowptr[lr + 1];
         const int* p = std::lower_bound(b, e, c);
         if (p == e || *p != c) return fail(GFA_EPATTERN, "host triplet (%d,%d) is not in the registered pattern of matrix %d; list it in gfa_set_dofs", r, c, which);
-        const long long slot = h->arena_off[which] + M.rowptr[r] + (p - b);
+        const long long slot = h->arena_off[which] + M.rowptr[lr] + (p - b);
         auto it = acc.find(slot);
         if (it == acc.end()) { acc[slot] = vals[i]; order.push_back(slot); } else it->second += vals[i];
     }
@@ -892,6 +938,14 @@ int gfa_interface_unpack(gfa_t* h, const double* buf) {
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+int gfa_local_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {
+    if (!h) return fail(GFA_EINVAL, "gfa_local_rows: null handle");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_local_rows before gfa_set_dofs");
+    const std::vector<int>& r = h->csr[GFA_AA].row_ids;
+    if (n_rows) *n_rows = (int64_t)r.size();
+    if (rows_out && !r.empty()) std::memcpy(rows_out, r.data(), r.size() * sizeof(int));
     return GFA_OK;
 }
 int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {

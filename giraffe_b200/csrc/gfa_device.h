@@ -17,6 +17,8 @@ struct EvalArgs {
     const double* xyz;       // [n_nodes*3] Node::ref_coordinates
     const double* copy;      // [n_nodes*6] Node::copy_coordinates
     const double* disp;      // [n_nodes*6] Node::displacements
+    const double* geo;       // Shell_1 PreCalc: R(9), area per element (SoA)
+    const double* shp;       // Shell_1 PreCalc: 21 shape values per Gauss point (SoA)
     double* state;           // committed Gauss-point state (read by eval, written by commit)
     double* Ke;              // [n_el * ndof * ndof] row-major, reference local DOF order
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
@@ -46,7 +48,8 @@ struct ScatterArgs {
     const int* gn_gl;            // [n_gn*3] global DOF ids (Node::GLs) of the group's 3 DOFs
     const int* inc_ptr;          // [n_gn+1]
     const Incidence* inc;        // incidences, element-ascending inside a group-node
-    const long long* rowptr;     // AA row pointers (64-bit)
+    const long long* gn_row;     // [n_gn*3] start of each of the group's rows in valAA (-1: DOF not free)
+    const int* gn_len;           // [n_gn] length of the group's AA rows (identical for its 3 rows)
     const double* Ke;            // arena
     const double* Pe;            // arena
     double* valAA;
@@ -67,6 +70,7 @@ struct GatherArgs {
 void launch_shell_eval(const EvalArgs& a, void* stream);
 void launch_beam_eval(const EvalArgs& a, void* stream);
 void launch_solid_eval(const EvalArgs& a, void* stream);
+void launch_shell_precalc(const EvalArgs& a, double* geo, double* shp, void* stream);
 void launch_shell_commit(const EvalArgs& a, void* stream);
 void launch_beam_commit(const EvalArgs& a, void* stream);
 void launch_node_commit(int n_nodes, double* copy, double* disp, void* stream);

@@ -18,6 +18,7 @@
 //   reference pushes its triplets (Solution.cpp:327-328) -- and writes each
 //   CSR row once, coalesced.  No atomics; results are bitwise reproducible.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "gfa_device.h"
 #include "gfa_math.cuh"
 
@@ -28,14 +29,13 @@ namespace gfa {
 // =========================================================================
 namespace shell {
 
-constexpr int EPW = 10;                 // elements per warp batch (30 Gauss-point lanes)
-constexpr int NGP = 3;
+constexpr int NGP = 3;                  // EPW (elements per warp batch) is a template parameter of eval_kernel
 constexpr int C_OFF = 0;                // 15 upper 3x3 blocks of C' (x weight)
 constexpr int F_OFF = 135;              // f (15)
 constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
 constexpr int AREA_OFF = 171;
 constexpr int REC = 173;                // odd stride
-constexpr int SMEM_BYTES = EPW * NGP * REC * 8;
+constexpr int smem_bytes(int epw) { return epw * NGP * REC * 8; }
 
 // upper-triangular block index of the 5x5 block matrix C'
 __host__ __device__ constexpr int blk(int p, int q) { return p * 5 - (p * (p - 1)) / 2 + (q - p); }
@@ -186,215 +186,301 @@ GFA_DI void load_nodes(const EvalArgs& A, int e, int* nd, double (&x)[6][3]) {
     }
 }
 
-// Phase A for one Gauss point: fills its shared-memory record.
-__device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
+// Per-element / per-point constants produced once by precalc_kernel:
+//   geo[k * n_el + e], k = 0..8 : R (rows e1r,e2r,e3r), k = 9 : area
+//   shp[k * n_gp + gp], k = 0..20: N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
+GFA_DI void load_precalc(const EvalArgs& A, int e, int g, Frame& fr, Shape& sh) {
+    const size_t ne = (size_t)A.n_el, n_gp = ne * NGP, gp = (size_t)e * NGP + g;
+#pragma unroll
+    for (int k = 0; k < 9; k++) fr.R[k] = __ldg(A.geo + k * ne + e);
+    fr.area = __ldg(A.geo + 9 * ne + e);
+#pragma unroll
+    for (int k = 0; k < 6; k++) { sh.N1[k] = __ldg(A.shp + k * n_gp + gp); sh.N2[k] = __ldg(A.shp + (6 + k) * n_gp + gp); }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        sh.A1[k] = __ldg(A.shp + (12 + k) * n_gp + gp);
+        sh.A2[k] = __ldg(A.shp + (15 + k) * n_gp + gp);
+        sh.A0[k] = __ldg(A.shp + (18 + k) * n_gp + gp);
+    }
+}
+__global__ void precalc_kernel(EvalArgs A, double* geo, double* shp) {
+    const size_t ne = (size_t)A.n_el, n_gp = ne * NGP;
+    const size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= n_gp) return;
+    const int e = (int)(gp / NGP), g = (int)(gp % NGP);
     int nd[6];
     double x[6][3];
     load_nodes(A, e, nd, x);
     Frame fr; frame_of(x, fr);
     Shape sh; shape_of(x, fr, g, sh);
-    Kin kn; interpolate(A, nd, fr, sh, kn);
-
-    const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
-    const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
-    const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
-    double Qi[9], z1[3], z2[3], k1[3], k2[3];
+    if (g == 0) {
 #pragma unroll
-    for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        z1[i] = s_add(kn.u1[i], A.state[(9 + i) * n_gp + gp]);      // z,1 = u_delta,1 + z,1^i  (:1010)
-        z2[i] = s_add(kn.u2[i], A.state[(12 + i) * n_gp + gp]);
-        k1[i] = A.state[(15 + i) * n_gp + gp];
-        k2[i] = A.state[(18 + i) * n_gp + gp];
+        for (int k = 0; k < 9; k++) geo[k * ne + e] = fr.R[k];
+        geo[9 * ne + e] = fr.area;
     }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { shp[k * n_gp + gp] = sh.N1[k]; shp[(6 + k) * n_gp + gp] = sh.N2[k]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { shp[(12 + k) * n_gp + gp] = sh.A1[k]; shp[(15 + k) * n_gp + gp] = sh.A2[k]; shp[(18 + k) * n_gp + gp] = sh.A0[k]; }
+}
 
-    double gg, Qd[9], Xi[9], Xi1[9], Xi2[9], Q[9], Qt[9];
-    s_rodrigues(kn.a, gg, Qd, Xi);
-    d_xi(Xi1, kn.a, kn.a1, gg, Xi);
-    d_xi(Xi2, kn.a, kn.a2, gg, Xi);
-    s_mm(Q, Qd, Qi);
-    m_transpose(Qt, Q);
-    // back-rotated strains (:1017-1020), strict
-    double eta1[3], eta2[3], kap1[3], kap2[3], t3[3];
-    s_mv(eta1, Qt, z1); eta1[0] = s_sub(eta1[0], 1.0);
-    s_mv(eta2, Qt, z2); eta2[1] = s_sub(eta2[1], 1.0);
-    s_mtv(t3, Xi, kn.a1); s_mtv(kap1, Qi, t3);
-    s_mtv(t3, Xi, kn.a2); s_mtv(kap2, Qi, t3);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { kap1[i] = s_add(kap1[i], k1[i]); kap2[i] = s_add(kap2[i], k2[i]); }
-
-    // thickness integration (:1056-1163): moments of the tangent blocks and resultants
-    double X[3][3][4];
-#pragma unroll
-    for (int m = 0; m < 3; m++)
-#pragma unroll
-        for (int p = 0; p < 3; p++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) X[m][p][q] = 0.0;
-    double smu = 0.0;
-    double n1[3] = { 0, 0, 0 }, n2[3] = { 0, 0, 0 }, m1[3] = { 0, 0, 0 }, m2[3] = { 0, 0, 0 };
+// Thickness integration at one in-plane point (Shell_1.cpp:1056-1163).
+// RESULTANTS: strict arithmetic, yields n_beta, m_beta (they set the internal
+// force).  Otherwise: the moments X[m][pair][..] of the tangent blocks.
+struct Strains { double eta1[3], eta2[3], kap1[3], kap2[3]; };
+template <bool RESULTANTS>
+GFA_DI void thickness(const Strains& st, double lam, double mu, double thick,
+                      double (&X)[3][3][4], double& smu, double* n1, double* n2, double* m1, double* m2) {
     const double jac = thick / 2.0;
     const double mu2 = s_mul(2.0, mu);
+    if (RESULTANTS) {
 #pragma unroll
+        for (int i = 0; i < 3; i++) { n1[i] = 0.0; n2[i] = 0.0; m1[i] = 0.0; m2[i] = 0.0; }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int p = 0; p < 3; p++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) X[m][p][c] = 0.0;
+        smu = 0.0;
+    }
+    // rolled on purpose: keeps the live register set of the three points apart
+#pragma unroll 1
     for (int q = 0; q < 3; q++) {
         const double csi = (q == 0) ? -0.77459666924148337703585307995648 : (q == 1) ? 0.0 : 0.77459666924148337703585307995648;
         const double al2 = (q == 1) ? 0.88888888888888888888888888888889 : 0.55555555555555555555555555555556;
         const double zeta = s_mul(thick, csi) / 2.0;
-        // gamma = eta + zeta * kappa x e3   (strict up to the resultants)
-        const double g11 = s_add(eta1[0], s_mul(zeta, kap1[1])), g12 = s_add(eta1[1], s_mul(zeta, -kap1[0])), g13 = eta1[2];
-        const double g21 = s_add(eta2[0], s_mul(zeta, kap2[1])), g22 = s_add(eta2[1], s_mul(zeta, -kap2[0])), g23 = eta2[2];
+        // gamma = eta + zeta * kappa x e3
+        const double g11 = s_add(st.eta1[0], s_mul(zeta, st.kap1[1])), g12 = s_add(st.eta1[1], s_mul(zeta, -st.kap1[0])), g13 = st.eta1[2];
+        const double g21 = s_add(st.eta2[0], s_mul(zeta, st.kap2[1])), g22 = s_add(st.eta2[1], s_mul(zeta, -st.kap2[0])), g23 = st.eta2[2];
         const double p11 = s_add(1.0, g11), p22 = s_add(1.0, g22);
         const double jb = s_sub(s_mul(p11, p22), s_mul(g12, g21));
         const double jb3 = s_mul(s_mul(jb, jb), jb);
         const double ljj = s_mul(s_mul(lam, jb), jb);                      // lambda*jb*jb
         const double v = s_add(s_mul(lam, s_sub(jb3, 1.0)), s_mul(mu2, s_sub(jb, 1.0))) / s_add(s_mul(ljj, jb), s_mul(mu2, jb));
-        const double cden = s_add(ljj, mu2);
-        const double dv = s_mul(s_add(lam, mu2), s_add(s_mul(s_mul(s_mul(3.0, lam), jb), jb), mu2)) / s_mul(s_mul(s_mul(jb, jb), cden), cden);
-        const double muv = s_mul(mu, v);
-        const double t1[3] = { s_add(s_mul(muv, p22), s_mul(mu, s_sub(g11, g22))), s_add(s_mul(muv, -g21), s_mul(mu, s_add(g12, g21))), s_mul(mu, g13) };
-        const double t2[3] = { s_add(s_mul(muv, -g12), s_mul(mu, s_add(g12, g21))), s_add(s_mul(muv, p11), s_mul(mu, s_sub(g22, g11))), s_mul(mu, g23) };
-        double C[3][4];
-        C[0][0] = mu * (p22 * p22 * dv + 1.0);
-        C[0][1] = -mu * p22 * g21 * dv;
-        C[0][2] = C[0][1];
-        C[0][3] = mu * (g21 * g21 * dv + 1.0);
-        C[2][0] = mu * (g12 * g12 * dv + 1.0);
-        C[2][1] = -mu * (p11 * g12 * dv);
-        C[2][2] = C[2][1];
-        C[2][3] = mu * (p11 * p11 * dv + 1.0);
-        C[1][0] = -mu * (p22 * g12 * dv);
-        C[1][1] = mu * (v - 1.0 + p11 * p22 * dv);
-        C[1][2] = mu * (1.0 - v + g12 * g21 * dv);
-        C[1][3] = -mu * (p11 * g21 * dv);
-        const double wj = s_mul(al2, jac), wz = s_mul(wj, zeta), wzz = wz * zeta;
+        const double wj = s_mul(al2, jac), wz = s_mul(wj, zeta);
+        if (RESULTANTS) {
+            const double muv = s_mul(mu, v);
+            const double t1[3] = { s_add(s_mul(muv, p22), s_mul(mu, s_sub(g11, g22))), s_add(s_mul(muv, -g21), s_mul(mu, s_add(g12, g21))), s_mul(mu, g13) };
+            const double t2[3] = { s_add(s_mul(muv, -g12), s_mul(mu, s_add(g12, g21))), s_add(s_mul(muv, p11), s_mul(mu, s_sub(g22, g11))), s_mul(mu, g23) };
 #pragma unroll
-        for (int p = 0; p < 3; p++)
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                X[0][p][c] += wj * C[p][c];
-                X[1][p][c] += wz * C[p][c];
-                X[2][p][c] += wzz * C[p][c];
+            for (int i = 0; i < 3; i++) {
+                n1[i] = s_add(n1[i], s_mul(wj, t1[i]));
+                n2[i] = s_add(n2[i], s_mul(wj, t2[i]));
             }
-        smu += wj * mu;
+            // m += wz * e3 x tau
+            m1[0] = s_add(m1[0], s_mul(wz, -t1[1])); m1[1] = s_add(m1[1], s_mul(wz, t1[0]));
+            m2[0] = s_add(m2[0], s_mul(wz, -t2[1])); m2[1] = s_add(m2[1], s_mul(wz, t2[0]));
+        } else {
+            const double cden = s_add(ljj, mu2);
+            const double dv = s_mul(s_add(lam, mu2), s_add(s_mul(s_mul(s_mul(3.0, lam), jb), jb), mu2)) / s_mul(s_mul(s_mul(jb, jb), cden), cden);
+            double C[3][4];
+            C[0][0] = mu * fma(p22 * p22, dv, 1.0);
+            C[0][1] = -mu * p22 * g21 * dv;
+            C[0][2] = C[0][1];
+            C[0][3] = mu * fma(g21 * g21, dv, 1.0);
+            C[2][0] = mu * fma(g12 * g12, dv, 1.0);
+            C[2][1] = -mu * (p11 * g12 * dv);
+            C[2][2] = C[2][1];
+            C[2][3] = mu * fma(p11 * p11, dv, 1.0);
+            C[1][0] = -mu * (p22 * g12 * dv);
+            C[1][1] = mu * (v - 1.0 + p11 * p22 * dv);
+            C[1][2] = mu * (1.0 - v + g12 * g21 * dv);
+            C[1][3] = -mu * (p11 * g21 * dv);
+            const double wzz = wz * zeta;
 #pragma unroll
-        for (int i = 0; i < 3; i++) { n1[i] = s_add(n1[i], s_mul(wj, t1[i])); n2[i] = s_add(n2[i], s_mul(wj, t2[i])); }
-        // m += wz * e3 x tau
-        m1[0] = s_add(m1[0], s_mul(wz, -t1[1])); m1[1] = s_add(m1[1], s_mul(wz, t1[0]));
-        m2[0] = s_add(m2[0], s_mul(wz, -t2[1])); m2[1] = s_add(m2[1], s_mul(wz, t2[0]));
+            for (int p = 0; p < 3; p++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    X[0][p][c] = fma(wj, C[p][c], X[0][p][c]);
+                    X[1][p][c] = fma(wz, C[p][c], X[1][p][c]);
+                    X[2][p][c] = fma(wzz, C[p][c], X[2][p][c]);
+                }
+            smu = fma(wj, mu, smu);
+        }
     }
-    m1[2] = s_mul(drill, kap1[2]);                            // drilling penalty (:1214-1217)
-    m2[2] = s_mul(drill, kap2[2]);
+}
 
-    // Psi' = Psi (I5 (x) R): the four distinct left factors and the column-4 blocks (:1239-1270)
-    double XiR[9], PA[9], PB[9], Y0[9], Y1[9], Y2[9], Y3[9], tmp[9], tmp2[9];
-    mm(PA, Qt, fr.R);                       // Qt R          -> Psi'(0,0) = Psi'(2,2)
-    mm(XiR, Xi, fr.R);
-    mm(PB, Qt, XiR);                        // Qt Xi R       -> Psi'(1,1) = Psi'(3,3)
-    skew_mul(tmp, z1, XiR); mm(Y0, Qt, tmp);   // Qt Z,1 Xi R
-    mm(tmp, Xi1, fr.R); mm(Y1, Qt, tmp);       // Qt Xi,1 R
-    skew_mul(tmp, z2, XiR); mm(Y2, Qt, tmp);
-    mm(tmp, Xi2, fr.R); mm(Y3, Qt, tmp);
+// out = w * R^T G R
+GFA_DI void park_rotated(double* slot, const double* G, const double* R) {
+    double t[9], r[9];
+    mm(t, G, R);
+    mtm(r, R, t);
+#pragma unroll
+    for (int i = 0; i < 9; i++) slot[i] = r[i];
+}
 
+// Geometric blocks of one direction beta (Shell_1.cpp:1277-1302) and the
+// column-4 blocks of Psi' (:1255-1270).  Results are PARKED in the record
+// (slots of the upper-triangle area that are rewritten last).
+GFA_DI void direction_blocks(double* rec, int slotYn, int slotYm, int slotGn, int slotGm, double* G44, double* f4,
+                             const double* a, const double* ab, const double* zb, const double* nb, const double* mb,
+                             const double* Qt, const double* Xi, const double* XiR, const double* R, double gg, bool first) {
+    double Xib[9], tmp[9], Y[9], t3[3];
+    d_xi(Xib, a, ab, gg, Xi);
+    skew_mul(tmp, zb, XiR); mm(Y, Qt, tmp);                    // Qt Z,b Xi R
+#pragma unroll
+    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotYn + i] = Y[i];
+    mtv(t3, Y, nb);
+    if (first) { f4[0] = t3[0]; f4[1] = t3[1]; f4[2] = t3[2]; } else { f4[0] += t3[0]; f4[1] += t3[1]; f4[2] += t3[2]; }
+    mm(tmp, Xib, R); mm(Y, Qt, tmp);                           // Qt Xi,b R
+#pragma unroll
+    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotYm + i] = Y[i];
+    mtv(t3, Y, mb);
+    f4[0] += t3[0]; f4[1] += t3[1]; f4[2] += t3[2];
+
+    double sn[3], sm[3], SnXi[9], V[9], zn[3];
+    mtv(sn, Qt, nb); mtv(sm, Qt, mb);                          // spatial resultants Q n, Q m
+    skew_mul(SnXi, sn, Xi);                                    // skew(n) Xi
+#pragma unroll
+    for (int i = 0; i < 9; i++) tmp[i] = -SnXi[i];
+    park_rotated(rec + C_OFF + 9 * slotGn, tmp, R);            // G(u,b ; alpha) = -skew(n) Xi
+    v_op(V, a, sm, gg);
+    m_transpose(tmp, V);
+    park_rotated(rec + C_OFF + 9 * slotGm, tmp, R);            // G(alpha,b ; alpha) = V(alpha, m)^T
+    // G(alpha;alpha) += Xi^T (Z,b skew(n)) Xi - V(alpha, Z,b n) + dV(alpha, alpha,b, m) - Xi,b^T (skew(m) Xi)
+    skew_mul(tmp, zb, SnXi);
+    if (first) mtm(G44, Xi, tmp); else mtm_acc(G44, Xi, tmp);
+    cross3(zn, zb, sn);
+    v_op(V, a, zn, gg);
+#pragma unroll
+    for (int i = 0; i < 9; i++) G44[i] -= V[i];
+    dv_op(V, a, ab, sm, gg);
+#pragma unroll
+    for (int i = 0; i < 9; i++) G44[i] += V[i];
+    skew_mul(SnXi, sm, Xi);                                    // skew(m) Xi
+    mtm(tmp, Xib, SnXi);
+#pragma unroll
+    for (int i = 0; i < 9; i++) G44[i] -= tmp[i];
+}
+
+// Phase A for one Gauss point: fills its shared-memory record.
+__device__ __noinline__ void physics(const EvalArgs& A, int e, int g, double* rec) {
+    // parking slots inside the upper-triangle area (rewritten by the last step)
+    constexpr int P_Y0 = 0, P_Y1 = 1, P_Y2 = 2, P_Y3 = 3, P_G0 = 5, P_G1 = 6, P_G2 = 7, P_G3 = 9, P_G4 = 10;
+    int nd[6];
+#pragma unroll
+    for (int n = 0; n < 6; n++) nd[n] = __ldg(A.conn + 6 * (size_t)e + n);
+    Frame fr;
+    Kin kn;
+    {
+        // element frame and shape functions come from the PreCalc kernel
+        // (Shell_1::PreCalc runs once per model, Database.cpp:713-714)
+        Shape sh;
+        load_precalc(A, e, g, fr, sh);
+        interpolate(A, nd, fr, sh, kn);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { rec[S_OFF + i] = sh.N1[i]; rec[S_OFF + 6 + i] = sh.N2[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) { rec[S_OFF + 12 + i] = sh.A1[i]; rec[S_OFF + 15 + i] = sh.A2[i]; rec[S_OFF + 18 + i] = sh.A0[i]; }
+        rec[AREA_OFF] = fr.area;
+    }
+    const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
+    const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
     const double w = fr.area / 3.0;                           // alpha1 (:2364)
 
-    // f = Psi'^T sigma  (:1324)
+    double gg, Xi[9], Qt[9], z1[3], z2[3];
+    Strains st;
     {
-        double f[15], t[3];
-        mtv(f + 0, PA, n1); mtv(f + 3, PB, m1); mtv(f + 6, PA, n2); mtv(f + 9, PB, m2);
-        mtv(f + 12, Y0, n1);
-        mtv(t, Y1, m1); f[12] += t[0]; f[13] += t[1]; f[14] += t[2];
-        mtv(t, Y2, n2); f[12] += t[0]; f[13] += t[1]; f[14] += t[2];
-        mtv(t, Y3, m2); f[12] += t[0]; f[13] += t[1]; f[14] += t[2];
+        double Qd[9], Qi[9], Q[9], t3[3];
 #pragma unroll
-        for (int i = 0; i < 15; i++) rec[F_OFF + i] = w * f[i];
+        for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            z1[i] = s_add(kn.u1[i], A.state[(9 + i) * n_gp + gp]);      // z,1 = u_delta,1 + z,1^i  (:1010)
+            z2[i] = s_add(kn.u2[i], A.state[(12 + i) * n_gp + gp]);
+        }
+        s_rodrigues(kn.a, gg, Qd, Xi);
+        s_mm(Q, Qd, Qi);
+        m_transpose(Qt, Q);
+        // back-rotated strains (:1017-1020), strict
+        s_mv(st.eta1, Qt, z1); st.eta1[0] = s_sub(st.eta1[0], 1.0);
+        s_mv(st.eta2, Qt, z2); st.eta2[1] = s_sub(st.eta2[1], 1.0);
+        s_mtv(t3, Xi, kn.a1); s_mtv(st.kap1, Qi, t3);
+        s_mtv(t3, Xi, kn.a2); s_mtv(st.kap2, Qi, t3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            st.kap1[i] = s_add(st.kap1[i], A.state[(15 + i) * n_gp + gp]);
+            st.kap2[i] = s_add(st.kap2[i], A.state[(18 + i) * n_gp + gp]);
+        }
+    }
+    double X[3][3][4], smu = 0.0;
+    {
+        double n1[3], n2[3], m1[3], m2[3];
+        thickness<true>(st, lam, mu, thick, X, smu, n1, n2, m1, m2);
+        m1[2] = s_mul(drill, st.kap1[2]);                         // drilling penalty (:1214-1217)
+        m2[2] = s_mul(drill, st.kap2[2]);
+
+        // Psi' = Psi (I5 (x) R) (:1239-1270): PA = Qt R -> blocks (0,0),(2,2); PB = Qt Xi R -> (1,1),(3,3)
+        double XiR[9], G44[9], f4[3];
+        mm(XiR, Xi, fr.R);
+        {
+            double P[9], t[3];
+            mm(P, Qt, fr.R);                                      // PA
+            mtv(t, P, n1);
+#pragma unroll
+            for (int i = 0; i < 3; i++) rec[F_OFF + i] = w * t[i];
+            mtv(t, P, n2);
+#pragma unroll
+            for (int i = 0; i < 3; i++) rec[F_OFF + 6 + i] = w * t[i];
+            mm(P, Qt, XiR);                                       // PB
+            mtv(t, P, m1);
+#pragma unroll
+            for (int i = 0; i < 3; i++) rec[F_OFF + 3 + i] = w * t[i];
+            mtv(t, P, m2);
+#pragma unroll
+            for (int i = 0; i < 3; i++) rec[F_OFF + 9 + i] = w * t[i];
+        }
+        direction_blocks(rec, P_Y0, P_Y1, P_G0, P_G1, G44, f4, kn.a, kn.a1, z1, n1, m1, Qt, Xi, XiR, fr.R, gg, true);
+        direction_blocks(rec, P_Y2, P_Y3, P_G2, P_G3, G44, f4, kn.a, kn.a2, z2, n2, m2, Qt, Xi, XiR, fr.R, gg, false);
+        park_rotated(rec + C_OFF + 9 * P_G4, G44, fr.R);
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + 12 + i] = w * f4[i];  // f = Psi'^T sigma (:1324)
+    }
+    double PA[9], PB[9];
+    {
+        double XiR[9];
+        mm(PA, Qt, fr.R);
+        mm(XiR, Xi, fr.R);
+        mm(PB, Qt, XiR);
     }
 
-    // geometric blocks G (:1277-1320), rotated: G' = R^T G R
-    double G04[9], G14[9], G24[9], G34[9], G44[9];
-    {
-        const double h = gg;   // 4/(4+alpha^2)
-        double sn1[3], sn2[3], sm1[3], sm2[3];
-        mv(sn1, Q, n1); mv(sn2, Q, n2); mv(sm1, Q, m1); mv(sm2, Q, m2);
-        double Vm1[9], Vm2[9], V[9], zn[3], SnXi[9], SmXi[9], A1[9], B1[9];
-        // beta = 1
-        skew_mul(SnXi, sn1, Xi);                              // skew(n1) Xi
-#pragma unroll
-        for (int i = 0; i < 9; i++) G04[i] = -SnXi[i];
-        v_op(Vm1, kn.a, sm1, h);
-        m_transpose(G14, Vm1);
-        skew_mul(A1, z1, SnXi);                               // Z,1 skew(n1) Xi
-        mtm(G44, Xi, A1);                                     // Xi^T (Z,1 skew(n1)) Xi
-        cross3(zn, z1, sn1);                                  // Z,1 n1
-        v_op(V, kn.a, zn, h);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G44[i] -= V[i];
-        dv_op(V, kn.a, kn.a1, sm1, h);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G44[i] += V[i];
-        skew_mul(SmXi, sm1, Xi);
-        mtm(B1, Xi1, SmXi);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G44[i] -= B1[i];
-        // beta = 2
-        double G44b[9];
-        skew_mul(SnXi, sn2, Xi);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G24[i] = -SnXi[i];
-        v_op(Vm2, kn.a, sm2, h);
-        m_transpose(G34, Vm2);
-        skew_mul(A1, z2, SnXi);
-        mtm(G44b, Xi, A1);
-        cross3(zn, z2, sn2);
-        v_op(V, kn.a, zn, h);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G44b[i] -= V[i];
-        dv_op(V, kn.a, kn.a2, sm2, h);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G44b[i] += V[i];
-        skew_mul(SmXi, sm2, Xi);
-        mtm(B1, Xi2, SmXi);
-#pragma unroll
-        for (int i = 0; i < 9; i++) G44[i] += G44b[i] - B1[i];
-        // rotate to global axes
-        mm(tmp, G04, fr.R); mtm(G04, fr.R, tmp);
-        mm(tmp, G14, fr.R); mtm(G14, fr.R, tmp);
-        mm(tmp, G24, fr.R); mtm(G24, fr.R, tmp);
-        mm(tmp, G34, fr.R); mtm(G34, fr.R, tmp);
-        mm(tmp, G44, fr.R); mtm(G44, fr.R, tmp);
-    }
+    // tangent moments (second pass over the thickness rule; fast arithmetic)
+    thickness<false>(st, lam, mu, thick, X, smu, nullptr, nullptr, nullptr, nullptr);
 
-    // C' = Psi'^T D Psi' + G'  -- upper block triangle (:1273, :1322)
-    const double* PL[4] = { PA, PB, PA, PB };
-#define GFA_UPPER(R_, S_)                                                         \
-    { const DBlk d = getD<R_, S_>(X, smu, drill); dmul(tmp, d, PL[S_]);           \
-      mtm(tmp2, PL[R_], tmp); put_block(rec, blk(R_, S_), w, tmp2); }
+    // C' = Psi'^T D Psi' + G': column 4 first (reads the parked Y / G' blocks) ...
+#define GFA_PL(R_) ((R_) % 2 == 0 ? PA : PB)
+    double tmp[9], tmp2[9];
+    {
+        double C44[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) C44[i] = rec[C_OFF + 9 * P_G4 + i];
+#define GFA_COL4(R_, PG_, PY_)                                                        \
+        { double H[9];                                                                \
+          { const DBlk d = getD<R_, 0>(X, smu, drill); dmul(H, d, rec + C_OFF + 9 * P_Y0); }     \
+          { const DBlk d = getD<R_, 1>(X, smu, drill); dmul_acc(H, d, rec + C_OFF + 9 * P_Y1); } \
+          { const DBlk d = getD<R_, 2>(X, smu, drill); dmul_acc(H, d, rec + C_OFF + 9 * P_Y2); } \
+          { const DBlk d = getD<R_, 3>(X, smu, drill); dmul_acc(H, d, rec + C_OFF + 9 * P_Y3); } \
+          mtm(tmp2, GFA_PL(R_), H);                                                       \
+          _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += rec[C_OFF + 9 * PG_ + i];     \
+          put_block(rec, blk(R_, 4), w, tmp2);                                        \
+          mtm_acc(C44, rec + C_OFF + 9 * PY_, H); }
+        GFA_COL4(0, P_G0, P_Y0) GFA_COL4(1, P_G1, P_Y1) GFA_COL4(2, P_G2, P_Y2) GFA_COL4(3, P_G3, P_Y3)
+#undef GFA_COL4
+        put_block(rec, blk(4, 4), w, C44);
+    }
+    // ... then the 10 upper blocks among the first four groups (overwrite the parking area)
+#define GFA_UPPER(R_, S_)                                                             \
+    { const DBlk d = getD<R_, S_>(X, smu, drill); dmul(tmp, d, GFA_PL(S_));           \
+      mtm(tmp2, GFA_PL(R_), tmp); put_block(rec, blk(R_, S_), w, tmp2); }
     GFA_UPPER(0, 0) GFA_UPPER(0, 1) GFA_UPPER(0, 2) GFA_UPPER(0, 3)
     GFA_UPPER(1, 1) GFA_UPPER(1, 2) GFA_UPPER(1, 3)
     GFA_UPPER(2, 2) GFA_UPPER(2, 3)
     GFA_UPPER(3, 3)
 #undef GFA_UPPER
-    double C44[9];
-    m_copy(C44, G44);
-#define GFA_COL4(R_, GB_)                                                         \
-    { double H[9];                                                                \
-      { const DBlk d = getD<R_, 0>(X, smu, drill); dmul(H, d, Y0); }              \
-      { const DBlk d = getD<R_, 1>(X, smu, drill); dmul_acc(H, d, Y1); }          \
-      { const DBlk d = getD<R_, 2>(X, smu, drill); dmul_acc(H, d, Y2); }          \
-      { const DBlk d = getD<R_, 3>(X, smu, drill); dmul_acc(H, d, Y3); }          \
-      mtm(tmp2, PL[R_], H);                                                       \
-      _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += GB_[i];            \
-      put_block(rec, blk(R_, 4), w, tmp2);                                        \
-      mtm_acc(C44, (R_ == 0 ? Y0 : R_ == 1 ? Y1 : R_ == 2 ? Y2 : Y3), H); }
-    GFA_COL4(0, G04) GFA_COL4(1, G14) GFA_COL4(2, G24) GFA_COL4(3, G34)
-#undef GFA_COL4
-    put_block(rec, blk(4, 4), w, C44);
-
-#pragma unroll
-    for (int i = 0; i < 6; i++) { rec[S_OFF + i] = sh.N1[i]; rec[S_OFF + 6 + i] = sh.N2[i]; }
-#pragma unroll
-    for (int i = 0; i < 3; i++) { rec[S_OFF + 12 + i] = sh.A1[i]; rec[S_OFF + 15 + i] = sh.A2[i]; rec[S_OFF + 18 + i] = sh.A0[i]; }
-    rec[AREA_OFF] = fr.area;
+#undef GFA_PL
 }
 
 // C'[(p,ii),(q,jj)] from the upper-triangular block storage.
@@ -469,13 +555,13 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         for (int a = 0; a < 6; a++) {
             const double n1 = S[a], n2 = S[6 + a];
 #pragma unroll
-            for (int ii = 0; ii < 3; ii++) K[3 * a + ii] += n1 * m[0][ii] + n2 * m[2][ii];
+            for (int ii = 0; ii < 3; ii++) K[3 * a + ii] = fma(n2, m[2][ii], fma(n1, m[0][ii], K[3 * a + ii]));
         }
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             const double a1 = S[12 + a], a2 = S[15 + a], a0 = S[18 + a];
 #pragma unroll
-            for (int ii = 0; ii < 3; ii++) K[18 + 3 * a + ii] += a1 * m[1][ii] + a2 * m[3][ii] + a0 * m[4][ii];
+            for (int ii = 0; ii < 3; ii++) K[18 + 3 * a + ii] = fma(a0, m[4][ii], fma(a2, m[3][ii], fma(a1, m[1][ii], K[18 + 3 * a + ii])));
         }
     }
     const int col = ROT ? 18 + 3 * b + jj : 3 * b + jj;
@@ -484,7 +570,7 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     for (int r = 0; r < 27; r++) Ke[r * 27] = K[r];
     // P = Fint - Fext; self-weight applied twice as in the reference (:1340-1375)
     double fe = 0.0;
-    if (!ROT) {
+    if (!ROT && (A.gx != 0.0 || A.gy != 0.0 || A.gz != 0.0)) {
         const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
         const double one = cowper_factor(b, rec0[AREA_OFF]) * (rho_t * gk);
         fe = one + one;
@@ -492,6 +578,7 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     A.Pe[(size_t)e * 27 + col] = F - fe;
 }
 
+template <int EPW>
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
@@ -520,10 +607,10 @@ __global__ void commit_kernel(EvalArgs A) {
     if (gp >= n_gp) return;
     const int e = (int)(gp / NGP), g = (int)(gp % NGP);
     int nd[6];
-    double x[6][3];
-    load_nodes(A, e, nd, x);
-    Frame fr; frame_of(x, fr);
-    Shape sh; shape_of(x, fr, g, sh);
+#pragma unroll
+    for (int n = 0; n < 6; n++) nd[n] = __ldg(A.conn + 6 * (size_t)e + n);
+    Frame fr; Shape sh;
+    load_precalc(A, e, g, fr, sh);
     Kin kn; interpolate(A, nd, fr, sh, kn);
     double gg, Qd[9], Xi[9], Qi[9], Qn[9], t3[3], dk[3];
     s_rodrigues(kn.a, gg, Qd, Xi);
@@ -1032,11 +1119,10 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
     if (gn >= A.n_gn) return;
     double* acc = smem + (size_t)warp * 3 * A.max_row;
     const int gl0 = A.gn_gl[3 * gn], gl1 = A.gn_gl[3 * gn + 1], gl2 = A.gn_gl[3 * gn + 2];
-    const int first = gl0 > 0 ? gl0 : gl1 > 0 ? gl1 : gl2;
+    const long long r0 = A.gn_row[3 * gn], r1 = A.gn_row[3 * gn + 1], r2 = A.gn_row[3 * gn + 2];
     const int ib = A.inc_ptr[gn], ie = A.inc_ptr[gn + 1];
-    int L = 0;
-    if (first > 0) {
-        L = (int)(A.rowptr[first] - A.rowptr[first - 1]);
+    if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
+        const int L = A.gn_len[gn];
         for (int p = lane; p < 3 * L; p += 32) acc[(p / L) * A.max_row + (p % L)] = 0.0;
         __syncwarp();
         for (int k = ib; k < ie; k++) {
@@ -1048,16 +1134,16 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
                 if ((mask >> c) & 1) {
                     const int pos = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
                     const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
-                    if (gl0 > 0) acc[pos] += row[0];
-                    if (gl1 > 0) acc[A.max_row + pos] += row[n];
-                    if (gl2 > 0) acc[2 * A.max_row + pos] += row[2 * n];
+                    if (r0 >= 0) acc[pos] += row[0];
+                    if (r1 >= 0) acc[A.max_row + pos] += row[n];
+                    if (r2 >= 0) acc[2 * A.max_row + pos] += row[2 * n];
                 }
             }
             __syncwarp();
         }
-        if (gl0 > 0) { double* o = A.valAA + A.rowptr[gl0 - 1]; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
-        if (gl1 > 0) { double* o = A.valAA + A.rowptr[gl1 - 1]; for (int p = lane; p < L; p += 32) o[p] = acc[A.max_row + p]; }
-        if (gl2 > 0) { double* o = A.valAA + A.rowptr[gl2 - 1]; for (int p = lane; p < L; p += 32) o[p] = acc[2 * A.max_row + p]; }
+        if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
+        if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc[A.max_row + p]; }
+        if (r2 >= 0) { double* o = A.valAA + r2; for (int p = lane; p < L; p += 32) o[p] = acc[2 * A.max_row + p]; }
     }
     // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
     if (lane < 3) {
@@ -1109,7 +1195,13 @@ static const int kSMs = 148;
 
 int configure_kernels() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(shell::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::SMEM_BYTES);
+    e = cudaFuncSetAttribute(shell::eval_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(10));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(shell::eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(8));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(shell::eval_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(6));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(shell::eval_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(5));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(beam::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, beam::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -1119,11 +1211,30 @@ int configure_kernels() {
     return (int)e;
 }
 
+// Elements per warp batch: 10 fills 30 of 32 lanes in the Gauss-point phase but
+// leaves 5 resident warps per SM (shared memory); smaller batches trade lane
+// use for occupancy.  GFA_SHELL_EPW overrides the default for experiments.
+static int shell_epw() {
+    static int v = 0;
+    if (!v) {
+        const char* s = getenv("GFA_SHELL_EPW");
+        v = s ? atoi(s) : 10;
+        if (v != 5 && v != 6 && v != 8 && v != 10) v = 10;
+    }
+    return v;
+}
 void launch_shell_eval(const EvalArgs& a, void* s) {
     if (a.n_el <= 0) return;
-    // persistent-style grid: a multiple of the SM count, 5 resident warps per SM
-    const int grid = grid_for(a.n_el, shell::EPW, kSMs * 5 * 8);
-    shell::eval_kernel<<<grid, 32, shell::SMEM_BYTES, (cudaStream_t)s>>>(a);
+    const int epw = shell_epw();
+    const int cap = kSMs * 64;      // a multiple of the SM count; batches are strided over the grid
+    const int grid = grid_for(a.n_el, epw, cap);
+    cudaStream_t st = (cudaStream_t)s;
+    switch (epw) {
+    case 5: shell::eval_kernel<5><<<grid, 32, shell::smem_bytes(5), st>>>(a); break;
+    case 6: shell::eval_kernel<6><<<grid, 32, shell::smem_bytes(6), st>>>(a); break;
+    case 8: shell::eval_kernel<8><<<grid, 32, shell::smem_bytes(8), st>>>(a); break;
+    default: shell::eval_kernel<10><<<grid, 32, shell::smem_bytes(10), st>>>(a); break;
+    }
 }
 void launch_beam_eval(const EvalArgs& a, void* s) {
     if (a.n_el <= 0) return;
@@ -1134,6 +1245,11 @@ void launch_solid_eval(const EvalArgs& a, void* s) {
     if (a.n_el <= 0) return;
     const int grid = grid_for(a.n_el, solid::EPW, kSMs * 8 * 8);
     solid::eval_kernel<<<grid, 32, solid::SMEM_BYTES, (cudaStream_t)s>>>(a);
+}
+void launch_shell_precalc(const EvalArgs& a, double* geo, double* shp, void* s) {
+    if (a.n_el <= 0) return;
+    const long long n = (long long)a.n_el * shell::NGP;
+    shell::precalc_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(a, geo, shp);
 }
 void launch_shell_commit(const EvalArgs& a, void* s) {
     if (a.n_el <= 0) return;

@@ -176,9 +176,12 @@ int gfa_last_timing(gfa_t* h, double* ms4);
 int gfa_last_launch_count(gfa_t* h);
 
 /* ---- multi-GPU (mesh partition by element range) ----------------------
- * Every rank holds the full DOF map and CSR pattern but evaluates only its
- * element partition; rows of nodes on partition interfaces receive partial
- * sums on several ranks.  The exchange step moves only those rows:
+ * Every rank holds the full DOF map but evaluates only its element partition
+ * and stores only the AA rows its elements touch (gfa_local_rows; with one
+ * rank these are all rows, in order, i.e. exactly the reference's CSR).  A
+ * stored row always carries its complete global column set, so rows of nodes
+ * on partition interfaces have the same layout on every rank that holds them
+ * and receive partial sums there.  The exchange step moves only those rows:
  *   gfa_interface_counts : per peer rank, number of doubles this rank sends / receives
  *   gfa_interface_pack   : gathers this rank's partial interface values into
  *                          send_buf (device), segments ordered by peer rank
@@ -189,7 +192,11 @@ int gfa_last_launch_count(gfa_t* h);
 int gfa_interface_counts(gfa_t* h, int64_t* send_counts /* [world] */, int64_t* recv_counts /* [world] */);
 int gfa_interface_pack(gfa_t* h, double* send_buf_device);
 int gfa_interface_unpack(gfa_t* h, const double* recv_buf_device);
-/* rows of AA (and entries of P_A/I_A/P_B) this rank owns after the exchange */
+/* global ids of the AA rows stored on this rank (ascending; row i of
+ * gfa_csr_pattern(GFA_AA) is global row rows_out[i]) */
+int gfa_local_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out /* may be NULL */);
+/* global ids of the AA rows (= entries of P_A/I_A) that are complete on this
+ * rank after the exchange; every row is owned by exactly one rank */
 int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out /* may be NULL */);
 
 /* Raw stream the library launches on (cudaStream_t), for callers that time
