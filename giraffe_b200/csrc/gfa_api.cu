@@ -517,7 +517,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     }
 
     // ---- AB / BA / BB: explicit entry lists of elements that touch a fixed DOF
-    struct Ent { int mat, row, col; long long src; };
+    struct Ent { int mat, row, col; long long src; int rank; };
     std::vector<Ent> ents;      // pattern from all elements; src = -1 when the element is not this rank's
     for (int e = 0; e < h->n_el; e++) {
         const int s = type_slot(h->el_type[e]);
@@ -540,6 +540,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 en.mat = (g1 > 0) ? GFA_AB : (g2 > 0 ? GFA_BA : GFA_BB);
                 en.row = std::abs(g1) - 1; en.col = std::abs(g2) - 1;
                 en.src = mine ? base + (long long)i * ti.ndof + j : -1;
+                en.rank = h->world > 1 ? el_rank[e] : 0;
                 ents.push_back(en);
             }
     }
@@ -555,7 +556,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             const int* b = AA.inner.data() + AA.rowptr[lr]; const int* e2 = AA.inner.data() + AA.rowptr[lr + 1];
             if (!std::binary_search(b, e2, c))
                 return fail(GFA_EUNSUPPORTED, "extra AA position (%d,%d) lies outside the element pattern; host contributors that couple otherwise unconnected DOFs are not supported yet", r, c);
-        } else { Ent en; en.mat = w; en.row = r; en.col = c; en.src = -1; ents.push_back(en); }
+        } else { Ent en; en.mat = w; en.row = r; en.col = c; en.src = -1; en.rank = -1; ents.push_back(en); }
     }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
         if (x.mat != y.mat) return x.mat < y.mat;
@@ -568,7 +569,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         M.rowptr.assign((size_t)M.rows + 1, 0); M.inner.clear();
     }
     std::vector<long long> gseg, gsrc, gdest;
-    std::vector<long long> local_slot;   // per unique dest: slot inside its matrix
+    std::vector<unsigned long long> granks;   // per unique dest: set of ranks whose elements contribute
     {
         size_t i = 0;
         while (i < ents.size()) {
@@ -579,10 +580,13 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             M.rowptr[ents[i].row + 1]++;
             gseg.push_back((long long)gsrc.size());
             gdest.push_back(((long long)ents[i].mat << 56) | slot);   // patched to arena offsets below
+            unsigned long long rs = 0;
             while (j < ents.size() && ents[j].mat == ents[i].mat && ents[j].row == ents[i].row && ents[j].col == ents[i].col) {
                 if (ents[j].src >= 0) gsrc.push_back(ents[j].src);
+                if (ents[j].rank >= 0) rs |= 1ULL << ents[j].rank;
                 j++;
             }
+            granks.push_back(rs);
             i = j;
         }
         gseg.push_back((long long)gsrc.size());
@@ -601,6 +605,16 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         gdest[i] = h->arena_off[w] + (gdest[i] & 0x00ffffffffffffffLL);
     }
     h->n_gdest = (long long)gdest.size();
+    // AB/BA/BB slots fed by several ranks: partial sums travel to the lowest contributing rank
+    std::vector<std::vector<long long> > send_small(h->world), recv_small(h->world);
+    if (h->world > 1)
+        for (size_t i = 0; i < gdest.size(); i++) {
+            const unsigned long long rs = granks[i];
+            if (__builtin_popcountll(rs) < 2 || !((rs >> h->rank) & 1)) continue;
+            const int owner = __builtin_ctzll(rs);
+            if (owner == h->rank) { for (int r = 0; r < h->world; r++) if (r != h->rank && ((rs >> r) & 1)) recv_small[r].push_back(gdest[i]); }
+            else send_small[owner].push_back(gdest[i]);
+        }
 
     // ---- scatter metadata for this rank's group-nodes -----------------------
     std::vector<int> gn_list;            // group-nodes with at least one local incidence
@@ -698,6 +712,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     {
         std::vector<long long> s_all, r_all;
         for (int r = 0; r < h->world; r++) {
+            send_idx[r].insert(send_idx[r].end(), send_small[r].begin(), send_small[r].end());
+            recv_idx[r].insert(recv_idx[r].end(), recv_small[r].begin(), recv_small[r].end());
             h->send_cnt[r] = (long long)send_idx[r].size(); h->recv_cnt[r] = (long long)recv_idx[r].size();
             s_all.insert(s_all.end(), send_idx[r].begin(), send_idx[r].end());
             r_all.insert(r_all.end(), recv_idx[r].begin(), recv_idx[r].end());

@@ -1123,27 +1123,46 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
     const int ib = A.inc_ptr[gn], ie = A.inc_ptr[gn + 1];
     if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
         const int L = A.gn_len[gn];
-        for (int p = lane; p < 3 * L; p += 32) acc[(p / L) * A.max_row + (p % L)] = 0.0;
+        double* acc1 = acc + A.max_row;
+        double* acc2 = acc1 + A.max_row;
+        for (int p = lane; p < L; p += 32) { acc[p] = 0.0; acc1[p] = 0.0; acc2[p] = 0.0; }
         __syncwarp();
-        for (int k = ib; k < ie; k++) {
+        // software-pipelined over the incident elements: the loads of the next
+        // element are in flight while the current one is accumulated
+        int pos = -1, n = 0;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        auto fetch = [&](int k) {
             const Incidence& in = A.inc[k];
-            const int n = in.n_la & 0xff, la = in.n_la >> 8;
+            n = in.n_la & 0xff;
+            const int la = in.n_la >> 8;
+            pos = -1;
             if (lane < n) {
                 const int r = in.roff[lane / 3], c = lane % 3;
                 const int mask = (r >> 28) & 7;
                 if ((mask >> c) & 1) {
-                    const int pos = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
+                    pos = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
                     const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
-                    if (r0 >= 0) acc[pos] += row[0];
-                    if (r1 >= 0) acc[A.max_row + pos] += row[n];
-                    if (r2 >= 0) acc[2 * A.max_row + pos] += row[2 * n];
+                    if (r0 >= 0) v0 = row[0];
+                    if (r1 >= 0) v1 = row[n];
+                    if (r2 >= 0) v2 = row[2 * n];
                 }
+            }
+        };
+        if (ib < ie) fetch(ib);
+        for (int k = ib; k < ie; k++) {
+            const int cpos = pos;
+            const double c0 = v0, c1 = v1, c2 = v2;
+            if (k + 1 < ie) fetch(k + 1);
+            if (cpos >= 0) {
+                if (r0 >= 0) acc[cpos] += c0;
+                if (r1 >= 0) acc1[cpos] += c1;
+                if (r2 >= 0) acc2[cpos] += c2;
             }
             __syncwarp();
         }
         if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
-        if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc[A.max_row + p]; }
-        if (r2 >= 0) { double* o = A.valAA + r2; for (int p = lane; p < L; p += 32) o[p] = acc[2 * A.max_row + p]; }
+        if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc1[p]; }
+        if (r2 >= 0) { double* o = A.valAA + r2; for (int p = lane; p < L; p += 32) o[p] = acc2[p]; }
     }
     // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
     if (lane < 3) {
@@ -1218,8 +1237,8 @@ static int shell_epw() {
     static int v = 0;
     if (!v) {
         const char* s = getenv("GFA_SHELL_EPW");
-        v = s ? atoi(s) : 10;
-        if (v != 5 && v != 6 && v != 8 && v != 10) v = 10;
+        v = s ? atoi(s) : 8;            // measured best on B200 (profiles/r01_notes.md)
+        if (v != 5 && v != 6 && v != 8 && v != 10) v = 8;
     }
     return v;
 }
