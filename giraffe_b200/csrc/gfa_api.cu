@@ -123,8 +123,7 @@ struct gfa_handle {
     long long vec_off[3] = { 0, 0, 0 };              // PA, IA, PB
     long long arena_size = 0;
     DevBuf<double> d_arena;
-    DevBuf<long long> d_gn_row;
-    DevBuf<int> d_gn_gl, d_gn_len, d_inc_ptr;
+    DevBuf<GnRec> d_gn;
     DevBuf<Incidence> d_inc;
     int n_gn_local = 0, max_row = 0;
     DevBuf<long long> d_gseg, d_gsrc, d_gdest;
@@ -618,14 +617,11 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
 
     // ---- scatter metadata for this rank's group-nodes -----------------------
     std::vector<int> gn_list;            // group-nodes with at least one local incidence
-    std::vector<int> inc_ptr(1, 0);
     std::vector<Incidence> incs;
-    std::vector<int> gn_gl;
+    std::vector<GnRec> gn_recs;
     int max_row = 1;
     // interface ownership: owner = lowest rank with an incidence
     std::vector<std::vector<long long> > send_idx(h->world), recv_idx(h->world);
-    std::vector<long long> gn_row;
-    std::vector<int> gn_len;
     h->owned_rows.clear();
     for (size_t gn = 0; gn < n_gn_all; gn++) {
         if (gptr[gn] == gptr[gn + 1]) continue;
@@ -681,13 +677,14 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
         if ((int)incs.size() == first_inc) continue;
         gn_list.push_back((int)gn);
-        inc_ptr.push_back((int)incs.size());
+        GnRec rec;
         for (int k = 0; k < 3; k++) {
             const int g = gls[3 * gn + k];
-            gn_gl.push_back(g);
-            gn_row.push_back(g > 0 ? AA.rowptr[AA.row_local[g - 1]] : -1);
+            rec.gl[k] = g;
+            rec.row[k] = g > 0 ? AA.rowptr[AA.row_local[g - 1]] : -1;
         }
-        gn_len.push_back((int)L);
+        rec.len = (int)L; rec.ib = first_inc; rec.ie = (int)incs.size();
+        gn_recs.push_back(rec);
         if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
     }
     if ((size_t)max_row * 3 * 4 * sizeof(double) > 200 * 1024)
@@ -698,10 +695,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
     CUDA_TRY(cudaMemset(h->d_arena.p, 0, (size_t)h->arena_size * sizeof(double)));
-    CUDA_TRY(h->d_gn_row.upload(gn_row));
-    CUDA_TRY(h->d_gn_len.upload(gn_len));
-    CUDA_TRY(h->d_gn_gl.upload(gn_gl));
-    CUDA_TRY(h->d_inc_ptr.upload(inc_ptr));
+    CUDA_TRY(h->d_gn.upload(gn_recs));
     CUDA_TRY(h->d_inc.upload(incs));
     CUDA_TRY(h->d_gseg.upload(gseg));
     CUDA_TRY(h->d_gsrc.upload(gsrc));
@@ -762,8 +756,8 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
     // MountGlobal + MountSparse
     if (h->n_gn_local > 0) {
         ScatterArgs a;
-        a.n_gn = h->n_gn_local; a.gn_gl = h->d_gn_gl.p; a.inc_ptr = h->d_inc_ptr.p; a.inc = h->d_inc.p;
-        a.gn_row = h->d_gn_row.p; a.gn_len = h->d_gn_len.p; a.Ke = h->d_Ke.p; a.Pe = h->d_Pe.p;
+        a.n_gn = h->n_gn_local; a.gn = h->d_gn.p; a.inc = h->d_inc.p;
+        a.Ke = h->d_Ke.p; a.Pe = h->d_Pe.p;
         a.valAA = h->d_arena.p + h->arena_off[GFA_AA];
         a.PA = h->d_arena.p + h->vec_off[GFA_P_A]; a.IA = h->d_arena.p + h->vec_off[GFA_I_A]; a.PB = h->d_arena.p + h->vec_off[GFA_P_B];
         a.max_row = h->max_row;

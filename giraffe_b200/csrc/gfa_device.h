@@ -43,13 +43,18 @@ struct Incidence {
     int roff[9];        // per local block b: (free-mask(3 bits) << 28) | start of b's run in the AA row
 };
 
+// one record per group-node this rank's elements touch
+struct GnRec {
+    long long row[3];   // start of each of the group's rows in valAA (-1: DOF not free)
+    int gl[3];          // global DOF ids (Node::GLs) of the group's 3 DOFs
+    int len;            // length of the group's AA rows (identical for its 3 rows)
+    int ib, ie;         // incidences [ib, ie), element-ascending
+};
+
 struct ScatterArgs {
     int n_gn;                    // group-nodes touched by this rank's elements
-    const int* gn_gl;            // [n_gn*3] global DOF ids (Node::GLs) of the group's 3 DOFs
-    const int* inc_ptr;          // [n_gn+1]
-    const Incidence* inc;        // incidences, element-ascending inside a group-node
-    const long long* gn_row;     // [n_gn*3] start of each of the group's rows in valAA (-1: DOF not free)
-    const int* gn_len;           // [n_gn] length of the group's AA rows (identical for its 3 rows)
+    const GnRec* gn;
+    const Incidence* inc;
     const double* Ke;            // arena
     const double* Pe;            // arena
     double* valAA;

@@ -1118,47 +1118,47 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
     const long long gn = (long long)blockIdx.x * SCATTER_WARPS + warp;
     if (gn >= A.n_gn) return;
     double* acc = smem + (size_t)warp * 3 * A.max_row;
-    const int gl0 = A.gn_gl[3 * gn], gl1 = A.gn_gl[3 * gn + 1], gl2 = A.gn_gl[3 * gn + 2];
-    const long long r0 = A.gn_row[3 * gn], r1 = A.gn_row[3 * gn + 1], r2 = A.gn_row[3 * gn + 2];
-    const int ib = A.inc_ptr[gn], ie = A.inc_ptr[gn + 1];
+    const GnRec g = A.gn[gn];
+    const long long r0 = g.row[0], r1 = g.row[1], r2 = g.row[2];
+    const int ib = g.ib, ie = g.ie;
     if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
-        const int L = A.gn_len[gn];
+        const int L = g.len;
         double* acc1 = acc + A.max_row;
         double* acc2 = acc1 + A.max_row;
         for (int p = lane; p < L; p += 32) { acc[p] = 0.0; acc1[p] = 0.0; acc2[p] = 0.0; }
         __syncwarp();
-        // software-pipelined over the incident elements: the loads of the next
-        // element are in flight while the current one is accumulated
-        int pos = -1, n = 0;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-        auto fetch = [&](int k) {
-            const Incidence& in = A.inc[k];
-            n = in.n_la & 0xff;
-            const int la = in.n_la >> 8;
-            pos = -1;
-            if (lane < n) {
-                const int r = in.roff[lane / 3], c = lane % 3;
-                const int mask = (r >> 28) & 7;
-                if ((mask >> c) & 1) {
-                    pos = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
-                    const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
-                    if (r0 >= 0) v0 = row[0];
-                    if (r1 >= 0) v1 = row[n];
-                    if (r2 >= 0) v2 = row[2 * n];
+        // up to MLP incident elements are fetched together so that their loads
+        // are in flight at once; the accumulation then runs in element order
+        constexpr int MLP = 6;
+        for (int kb = ib; kb < ie; kb += MLP) {
+            int pos[MLP];
+            double v0[MLP], v1[MLP], v2[MLP];
+#pragma unroll
+            for (int j = 0; j < MLP; j++) {
+                pos[j] = -1; v0[j] = 0.0; v1[j] = 0.0; v2[j] = 0.0;
+                if (kb + j < ie) {
+                    const Incidence& in = A.inc[kb + j];
+                    const int n = in.n_la & 0xff, la = in.n_la >> 8;
+                    if (lane < n) {
+                        const int r = in.roff[lane / 3], c = lane % 3;
+                        const int mask = (r >> 28) & 7;
+                        if ((mask >> c) & 1) {
+                            pos[j] = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
+                            const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
+                            if (r0 >= 0) v0[j] = row[0];
+                            if (r1 >= 0) v1[j] = row[n];
+                            if (r2 >= 0) v2[j] = row[2 * n];
+                        }
+                    }
                 }
             }
-        };
-        if (ib < ie) fetch(ib);
-        for (int k = ib; k < ie; k++) {
-            const int cpos = pos;
-            const double c0 = v0, c1 = v1, c2 = v2;
-            if (k + 1 < ie) fetch(k + 1);
-            if (cpos >= 0) {
-                if (r0 >= 0) acc[cpos] += c0;
-                if (r1 >= 0) acc1[cpos] += c1;
-                if (r2 >= 0) acc2[cpos] += c2;
+#pragma unroll
+            for (int j = 0; j < MLP; j++) {
+                if (kb + j < ie) {
+                    if (pos[j] >= 0) { acc[pos[j]] += v0[j]; acc1[pos[j]] += v1[j]; acc2[pos[j]] += v2[j]; }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
         }
         if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
         if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc1[p]; }
@@ -1166,7 +1166,7 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
     }
     // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
     if (lane < 3) {
-        const int gl = lane == 0 ? gl0 : lane == 1 ? gl1 : gl2;
+        const int gl = g.gl[lane];
         if (gl != 0) {
             double s = 0.0;
             for (int k = ib; k < ie; k++) {
