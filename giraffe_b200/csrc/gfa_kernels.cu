@@ -1127,38 +1127,23 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
         double* acc2 = acc1 + A.max_row;
         for (int p = lane; p < L; p += 32) { acc[p] = 0.0; acc1[p] = 0.0; acc2[p] = 0.0; }
         __syncwarp();
-        // up to MLP incident elements are fetched together so that their loads
-        // are in flight at once; the accumulation then runs in element order
-        constexpr int MLP = 6;
-        for (int kb = ib; kb < ie; kb += MLP) {
-            int pos[MLP];
-            double v0[MLP], v1[MLP], v2[MLP];
-#pragma unroll
-            for (int j = 0; j < MLP; j++) {
-                pos[j] = -1; v0[j] = 0.0; v1[j] = 0.0; v2[j] = 0.0;
-                if (kb + j < ie) {
-                    const Incidence& in = A.inc[kb + j];
-                    const int n = in.n_la & 0xff, la = in.n_la >> 8;
-                    if (lane < n) {
-                        const int r = in.roff[lane / 3], c = lane % 3;
-                        const int mask = (r >> 28) & 7;
-                        if ((mask >> c) & 1) {
-                            pos[j] = (r & 0x0fffffff) + __popc(mask & ((1 << c) - 1));
-                            const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
-                            if (r0 >= 0) v0[j] = row[0];
-                            if (r1 >= 0) v1[j] = row[n];
-                            if (r2 >= 0) v2[j] = row[2 * n];
-                        }
-                    }
+        // incident elements in ascending order (the reference's triplet order)
+        const int lb = lane / 3, cbit = 1 << (lane % 3);
+        for (int k = ib; k < ie; k++) {
+            const Incidence& in = A.inc[k];
+            const int n = in.n_la & 0xff, la = in.n_la >> 8;
+            if (lane < n) {
+                const int r = in.roff[lb];
+                const int mask = (r >> 28) & 7;
+                if (mask & cbit) {
+                    const int pos = (r & 0x0fffffff) + __popc(mask & (cbit - 1));
+                    const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
+                    if (r0 >= 0) acc[pos] += row[0];
+                    if (r1 >= 0) acc1[pos] += row[n];
+                    if (r2 >= 0) acc2[pos] += row[2 * n];
                 }
             }
-#pragma unroll
-            for (int j = 0; j < MLP; j++) {
-                if (kb + j < ie) {
-                    if (pos[j] >= 0) { acc[pos[j]] += v0[j]; acc1[pos[j]] += v1[j]; acc2[pos[j]] += v2[j]; }
-                    __syncwarp();
-                }
-            }
+            __syncwarp();
         }
         if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
         if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc1[p]; }
