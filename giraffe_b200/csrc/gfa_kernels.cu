@@ -356,7 +356,7 @@ GFA_DI void direction_blocks(double* rec, int slotYn, int slotYm, int slotGn, in
 }
 
 // Phase A for one Gauss point: fills its shared-memory record.
-__device__ __noinline__ void physics(const EvalArgs& A, int e, int g, double* rec) {
+__device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     // parking slots inside the upper-triangle area (rewritten by the last step)
     constexpr int P_Y0 = 0, P_Y1 = 1, P_Y2 = 2, P_Y3 = 3, P_G0 = 5, P_G1 = 6, P_G2 = 7, P_G3 = 9, P_G4 = 10;
     int nd[6];
