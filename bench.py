@@ -276,7 +276,7 @@ def run_cuda(args):
     if rank == 0:
         pk, pk_src = peaks()
         n_local = n_el_total // world
-        nnz_local = nnz[0] / world
+        nnz_local = nnz[0]                      # csr_dims are this rank's stored rows
         alg_bytes = n_local * (SHELL_READ_BYTES) + 8.0 * nnz_local + 16.0 * nf / world
         ev, sc = float(np.mean(eval_ms)), float(np.mean(scat_ms))
         dom = "shell::eval_kernel" if ev >= sc else "scatter_kernel"

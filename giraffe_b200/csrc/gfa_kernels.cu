@@ -32,9 +32,7 @@ namespace shell {
 constexpr int NGP = 3;                  // EPW (elements per warp batch) is a template parameter of eval_kernel
 constexpr int C_OFF = 0;                // 15 upper 3x3 blocks of C' (x weight)
 constexpr int F_OFF = 135;              // f (15)
-constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
-constexpr int AREA_OFF = 171;
-constexpr int REC = 173;                // odd stride
+constexpr int REC = 151;                // odd stride; shape values are read from the PreCalc arrays
 constexpr int smem_bytes(int epw) { return epw * NGP * REC * 8; }
 
 // upper-triangular block index of the 5x5 block matrix C'
@@ -149,7 +147,8 @@ GFA_DI void shape_of(const double (&x)[6][3], const Frame& fr, int g, Shape& s) 
 
 // Increment kinematics at one point, in the element frame (:906-1020)
 struct Kin {
-    double a[3], a1[3], a2[3], u1[3], u2[3];   // alpha_delta, its x1/x2 derivatives, u_delta,1 u_delta,2
+    double a[3], a1[3], a2[3], u1[3], u2[3];   // alpha_delta, its x1/x2 derivatives, u_delta,1 u_delta,2 (element frame)
+    double ga[3], ga1[3], ga2[3];               // the same rotation quantities in global axes
 };
 GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Frame& fr, const Shape& s, Kin& k) {
     double gu1[3], gu2[3], ga[3], ga1[3], ga2[3];
@@ -174,6 +173,8 @@ GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Frame& fr, const
     }
     s_mv(k.u1, fr.R, gu1); s_mv(k.u2, fr.R, gu2);
     s_mv(k.a, fr.R, ga); s_mv(k.a1, fr.R, ga1); s_mv(k.a2, fr.R, ga2);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { k.ga[c] = ga[c]; k.ga1[c] = ga1[c]; k.ga2[c] = ga2[c]; }
 }
 
 GFA_DI void load_nodes(const EvalArgs& A, int e, int* nd, double (&x)[6][3]) {
@@ -302,54 +303,50 @@ GFA_DI void thickness(const Strains& st, double lam, double mu, double thick,
     }
 }
 
-// out = w * R^T G R
-GFA_DI void park_rotated(double* slot, const double* G, const double* R) {
-    double t[9], r[9];
-    mm(t, G, R);
-    mtm(r, R, t);
-#pragma unroll
-    for (int i = 0; i < 9; i++) slot[i] = r[i];
-}
-
 // Geometric blocks of one direction beta (Shell_1.cpp:1277-1302) and the
-// column-4 blocks of Psi' (:1255-1270).  Results are PARKED in the record
-// (slots of the upper-triangle area that are rewritten last).
+// column-4 blocks of Psi' (:1255-1270), written directly in GLOBAL axes:
+// with R proper orthogonal, R^T skew(v) R = skew(R^T v) and V, d_V, Xi are
+// frame-covariant, so G' = R^T G R and Psi' = Psi R are obtained by feeding the
+// global-frame vectors (ag = interpolated nodal rotations, zg = R^T z,b,
+// PA^T n = R^T Q n) instead of rotating every 3x3 block.  Results are PARKED in
+// the record (slots of the upper-triangle area that are rewritten last).
 GFA_DI void direction_blocks(double* rec, int slotYn, int slotYm, int slotGn, int slotGm, double* G44, double* f4,
-                             const double* a, const double* ab, const double* zb, const double* nb, const double* mb,
-                             const double* Qt, const double* Xi, const double* XiR, const double* R, double gg, bool first) {
+                             const double* ag, const double* abg, const double* zg, const double* nb, const double* mb,
+                             const double* PA, const double* Xig, double gg, bool first) {
     double Xib[9], tmp[9], Y[9], t3[3];
-    d_xi(Xib, a, ab, gg, Xi);
-    skew_mul(tmp, zb, XiR); mm(Y, Qt, tmp);                    // Qt Z,b Xi R
+    d_xi(Xib, ag, abg, gg, Xig);
+    skew_mul(tmp, zg, Xig); mm(Y, PA, tmp);                    // Qt Z,b Xi R
 #pragma unroll
     for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotYn + i] = Y[i];
     mtv(t3, Y, nb);
     if (first) { f4[0] = t3[0]; f4[1] = t3[1]; f4[2] = t3[2]; } else { f4[0] += t3[0]; f4[1] += t3[1]; f4[2] += t3[2]; }
-    mm(tmp, Xib, R); mm(Y, Qt, tmp);                           // Qt Xi,b R
+    mm(Y, PA, Xib);                                            // Qt Xi,b R
 #pragma unroll
     for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotYm + i] = Y[i];
     mtv(t3, Y, mb);
     f4[0] += t3[0]; f4[1] += t3[1]; f4[2] += t3[2];
 
     double sn[3], sm[3], SnXi[9], V[9], zn[3];
-    mtv(sn, Qt, nb); mtv(sm, Qt, mb);                          // spatial resultants Q n, Q m
-    skew_mul(SnXi, sn, Xi);                                    // skew(n) Xi
+    mtv(sn, PA, nb); mtv(sm, PA, mb);                          // R^T Q n, R^T Q m
+    skew_mul(SnXi, sn, Xig);                                   // skew(n) Xi
 #pragma unroll
-    for (int i = 0; i < 9; i++) tmp[i] = -SnXi[i];
-    park_rotated(rec + C_OFF + 9 * slotGn, tmp, R);            // G(u,b ; alpha) = -skew(n) Xi
-    v_op(V, a, sm, gg);
-    m_transpose(tmp, V);
-    park_rotated(rec + C_OFF + 9 * slotGm, tmp, R);            // G(alpha,b ; alpha) = V(alpha, m)^T
+    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotGn + i] = -SnXi[i];     // G(u,b ; alpha) = -skew(n) Xi
+    v_op(V, ag, sm, gg);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) rec[C_OFF + 9 * slotGm + 3 * i + j] = V[3 * j + i];   // G(alpha,b ; alpha) = V(alpha, m)^T
     // G(alpha;alpha) += Xi^T (Z,b skew(n)) Xi - V(alpha, Z,b n) + dV(alpha, alpha,b, m) - Xi,b^T (skew(m) Xi)
-    skew_mul(tmp, zb, SnXi);
-    if (first) mtm(G44, Xi, tmp); else mtm_acc(G44, Xi, tmp);
-    cross3(zn, zb, sn);
-    v_op(V, a, zn, gg);
+    skew_mul(tmp, zg, SnXi);
+    if (first) mtm(G44, Xig, tmp); else mtm_acc(G44, Xig, tmp);
+    cross3(zn, zg, sn);
+    v_op(V, ag, zn, gg);
 #pragma unroll
     for (int i = 0; i < 9; i++) G44[i] -= V[i];
-    dv_op(V, a, ab, sm, gg);
+    dv_op(V, ag, abg, sm, gg);
 #pragma unroll
     for (int i = 0; i < 9; i++) G44[i] += V[i];
-    skew_mul(SnXi, sm, Xi);                                    // skew(m) Xi
+    skew_mul(SnXi, sm, Xig);                                   // skew(m) Xi
     mtm(tmp, Xib, SnXi);
 #pragma unroll
     for (int i = 0; i < 9; i++) G44[i] -= tmp[i];
@@ -370,11 +367,6 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         Shape sh;
         load_precalc(A, e, g, fr, sh);
         interpolate(A, nd, fr, sh, kn);
-#pragma unroll
-        for (int i = 0; i < 6; i++) { rec[S_OFF + i] = sh.N1[i]; rec[S_OFF + 6 + i] = sh.N2[i]; }
-#pragma unroll
-        for (int i = 0; i < 3; i++) { rec[S_OFF + 12 + i] = sh.A1[i]; rec[S_OFF + 15 + i] = sh.A2[i]; rec[S_OFF + 18 + i] = sh.A0[i]; }
-        rec[AREA_OFF] = fr.area;
     }
     const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
     const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
@@ -407,44 +399,45 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         }
     }
     double X[3][3][4], smu = 0.0;
-    {
-        double n1[3], n2[3], m1[3], m2[3];
-        thickness<true>(st, lam, mu, thick, X, smu, n1, n2, m1, m2);
-        m1[2] = s_mul(drill, st.kap1[2]);                         // drilling penalty (:1214-1217)
-        m2[2] = s_mul(drill, st.kap2[2]);
+    double n1[3], n2[3], m1[3], m2[3];
+    thickness<true>(st, lam, mu, thick, X, smu, n1, n2, m1, m2);
+    m1[2] = s_mul(drill, st.kap1[2]);                             // drilling penalty (:1214-1217)
+    m2[2] = s_mul(drill, st.kap2[2]);
 
-        // Psi' = Psi (I5 (x) R) (:1239-1270): PA = Qt R -> blocks (0,0),(2,2); PB = Qt Xi R -> (1,1),(3,3)
-        double XiR[9], G44[9], f4[3];
-        mm(XiR, Xi, fr.R);
-        {
-            double P[9], t[3];
-            mm(P, Qt, fr.R);                                      // PA
-            mtv(t, P, n1);
-#pragma unroll
-            for (int i = 0; i < 3; i++) rec[F_OFF + i] = w * t[i];
-            mtv(t, P, n2);
-#pragma unroll
-            for (int i = 0; i < 3; i++) rec[F_OFF + 6 + i] = w * t[i];
-            mm(P, Qt, XiR);                                       // PB
-            mtv(t, P, m1);
-#pragma unroll
-            for (int i = 0; i < 3; i++) rec[F_OFF + 3 + i] = w * t[i];
-            mtv(t, P, m2);
-#pragma unroll
-            for (int i = 0; i < 3; i++) rec[F_OFF + 9 + i] = w * t[i];
-        }
-        direction_blocks(rec, P_Y0, P_Y1, P_G0, P_G1, G44, f4, kn.a, kn.a1, z1, n1, m1, Qt, Xi, XiR, fr.R, gg, true);
-        direction_blocks(rec, P_Y2, P_Y3, P_G2, P_G3, G44, f4, kn.a, kn.a2, z2, n2, m2, Qt, Xi, XiR, fr.R, gg, false);
-        park_rotated(rec + C_OFF + 9 * P_G4, G44, fr.R);
-#pragma unroll
-        for (int i = 0; i < 3; i++) rec[F_OFF + 12 + i] = w * f4[i];  // f = Psi'^T sigma (:1324)
-    }
+    // Psi' = Psi (I5 (x) R) (:1239-1270): PA = Qt R -> blocks (0,0),(2,2); PB = Qt Xi R = PA Xi_g -> (1,1),(3,3)
     double PA[9], PB[9];
     {
-        double XiR[9];
+        double Xig[9], G44[9], f4[3], t[3], zg1[3], zg2[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+            Xig[i] = gg * id;
+        }
+        // Xi in global axes: g (I + skew(ag)/2)
+        Xig[1] = -0.5 * gg * kn.ga[2]; Xig[2] = 0.5 * gg * kn.ga[1];
+        Xig[3] = 0.5 * gg * kn.ga[2];  Xig[5] = -0.5 * gg * kn.ga[0];
+        Xig[6] = -0.5 * gg * kn.ga[1]; Xig[7] = 0.5 * gg * kn.ga[0];
         mm(PA, Qt, fr.R);
-        mm(XiR, Xi, fr.R);
-        mm(PB, Qt, XiR);
+        mm(PB, PA, Xig);
+        mtv(zg1, fr.R, z1); mtv(zg2, fr.R, z2);
+        mtv(t, PA, n1);
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + i] = w * t[i];
+        mtv(t, PA, n2);
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + 6 + i] = w * t[i];
+        mtv(t, PB, m1);
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + 3 + i] = w * t[i];
+        mtv(t, PB, m2);
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + 9 + i] = w * t[i];
+        direction_blocks(rec, P_Y0, P_Y1, P_G0, P_G1, G44, f4, kn.ga, kn.ga1, zg1, n1, m1, PA, Xig, gg, true);
+        direction_blocks(rec, P_Y2, P_Y3, P_G2, P_G3, G44, f4, kn.ga, kn.ga2, zg2, n2, m2, PA, Xig, gg, false);
+#pragma unroll
+        for (int i = 0; i < 9; i++) rec[C_OFF + 9 * P_G4 + i] = G44[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) rec[F_OFF + 12 + i] = w * f4[i];  // f = Psi'^T sigma (:1324)
     }
 
     // tangent moments (second pass over the thickness rule; fast arithmetic)
@@ -527,42 +520,46 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
 #pragma unroll
     for (int i = 0; i < 27; i++) K[i] = 0.0;
     double F = 0.0;
+    const size_t n_gp = (size_t)A.n_el * NGP;
 #pragma unroll 1
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
         const double* recJ = rec + jj;
         const double* rec3J = rec + 3 * jj;
-        const double* S = rec + S_OFF;
+        // shape values of this point from the PreCalc arrays (same for all lanes of the element)
+        const double* S = A.shp + ((size_t)e * NGP + g);
+#define GFA_S(k_) __ldg(S + (size_t)(k_) * n_gp)
         double m[5][3];
         if (!ROT) {
-            const double s0 = S[b], s2 = S[6 + b];
-#define GFA_ROW(P_, I_) m[P_][I_] = s0 * c_at<P_, I_, 0>(recJ, rec3J) + s2 * c_at<P_, I_, 2>(recJ, rec3J);
+            const double s0 = GFA_S(b), s2 = GFA_S(6 + b);
+#define GFA_ROW(P_, I_) m[P_][I_] = fma(s2, c_at<P_, I_, 2>(recJ, rec3J), s0 * c_at<P_, I_, 0>(recJ, rec3J));
             GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
             GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
             GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
 #undef GFA_ROW
-            F += s0 * recJ[F_OFF + 0] + s2 * recJ[F_OFF + 6];
+            F = fma(s2, recJ[F_OFF + 6], fma(s0, recJ[F_OFF + 0], F));
         } else {
-            const double s1 = S[12 + b], s3 = S[15 + b], s4 = S[18 + b];
-#define GFA_ROW(P_, I_) m[P_][I_] = s1 * c_at<P_, I_, 1>(recJ, rec3J) + s3 * c_at<P_, I_, 3>(recJ, rec3J) + s4 * c_at<P_, I_, 4>(recJ, rec3J);
+            const double s1 = GFA_S(12 + b), s3 = GFA_S(15 + b), s4 = GFA_S(18 + b);
+#define GFA_ROW(P_, I_) m[P_][I_] = fma(s4, c_at<P_, I_, 4>(recJ, rec3J), fma(s3, c_at<P_, I_, 3>(recJ, rec3J), s1 * c_at<P_, I_, 1>(recJ, rec3J)));
             GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
             GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
             GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
 #undef GFA_ROW
-            F += s1 * recJ[F_OFF + 3] + s3 * recJ[F_OFF + 9] + s4 * recJ[F_OFF + 12];
+            F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
         }
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-            const double n1 = S[a], n2 = S[6 + a];
+            const double n1 = GFA_S(a), n2 = GFA_S(6 + a);
 #pragma unroll
             for (int ii = 0; ii < 3; ii++) K[3 * a + ii] = fma(n2, m[2][ii], fma(n1, m[0][ii], K[3 * a + ii]));
         }
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const double a1 = S[12 + a], a2 = S[15 + a], a0 = S[18 + a];
+            const double a1 = GFA_S(12 + a), a2 = GFA_S(15 + a), a0 = GFA_S(18 + a);
 #pragma unroll
             for (int ii = 0; ii < 3; ii++) K[18 + 3 * a + ii] = fma(a0, m[4][ii], fma(a2, m[3][ii], fma(a1, m[1][ii], K[18 + 3 * a + ii])));
         }
+#undef GFA_S
     }
     const int col = ROT ? 18 + 3 * b + jj : 3 * b + jj;
     double* Ke = A.Ke + (size_t)e * 729 + col;
@@ -572,7 +569,7 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     double fe = 0.0;
     if (!ROT && (A.gx != 0.0 || A.gy != 0.0 || A.gz != 0.0)) {
         const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
-        const double one = cowper_factor(b, rec0[AREA_OFF]) * (rho_t * gk);
+        const double one = cowper_factor(b, __ldg(A.geo + 9 * (size_t)A.n_el + e)) * (rho_t * gk);
         fe = one + one;
     }
     A.Pe[(size_t)e * 27 + col] = F - fe;
@@ -1222,8 +1219,8 @@ static int shell_epw() {
     static int v = 0;
     if (!v) {
         const char* s = getenv("GFA_SHELL_EPW");
-        v = s ? atoi(s) : 8;            // measured best on B200 (profiles/r01_notes.md)
-        if (v != 5 && v != 6 && v != 8 && v != 10) v = 8;
+        v = s ? atoi(s) : 10;
+        if (v != 5 && v != 6 && v != 8 && v != 10) v = 10;
     }
     return v;
 }
