@@ -100,8 +100,13 @@ struct HostCsr {
 
 struct gfa_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // evaluation stream (the one callers may time / order against)
+    cudaStream_t stream2 = nullptr;       // scatter stream of the chunked pipeline
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::vector<cudaEvent_t> chunk_ev;    // evaluation of pipeline step i finished
+    cudaEvent_t ev_scatter_done = nullptr;
+    int n_chunks = 1;                      // pipeline steps per element type
+    std::vector<long long> gn_seq_ptr;    // group-node records ready after pipeline step i: [ptr[i], ptr[i+1])
     int rank = 0, world = 1;
 
     int n_nodes = 0, n_el = 0;
@@ -144,6 +149,7 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
     TypeBlock& t = h->tb[slot];
     EvalArgs a;
     a.n_el = (int)t.elems.size();
+    a.e_begin = 0; a.e_end = a.n_el;
     a.conn = t.d_conn.p; a.prop = t.d_prop.p; a.props = t.d_props.p;
     a.pret = t.any_pret ? t.d_pret.p : nullptr;
     a.xyz = h->d_xyz.p; a.copy = h->d_copy.p; a.disp = h->d_disp.p;
@@ -322,6 +328,8 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         if (e == cudaSuccess) e = h->tb[0].d_geo.alloc(10 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = h->tb[0].d_shp.alloc(21 * 3 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_scatter_done, cudaEventDisableTiming);
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
         if (e != cudaSuccess) FAIL_FREE(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "device set-up: %s", cudaGetErrorString(e));
     }
@@ -340,7 +348,10 @@ int gfa_destroy(gfa_t* h) {
     if (!h) return GFA_OK;
     cudaSetDevice(h->device);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
+    if (h->ev_scatter_done) cudaEventDestroy(h->ev_scatter_done);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
     return GFA_OK;
 }
@@ -619,6 +630,21 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<int> gn_list;            // group-nodes with at least one local incidence
     std::vector<Incidence> incs;
     std::vector<GnRec> gn_recs;
+    std::vector<int> gn_ready;           // pipeline step after which all incident elements are evaluated
+    // chunked pipeline: every element type is evaluated in n_chunks launches; a group-node can be
+    // scattered as soon as the launch holding its last incident element has finished
+    {
+        const char* env = getenv("GFA_CHUNKS");
+        long long biggest = 0;
+        for (int s3 = 0; s3 < 3; s3++) biggest = std::max<long long>(biggest, (long long)h->tb[s3].elems.size());
+        int nc = env ? atoi(env) : (biggest >= 200000 ? 16 : 1);
+        h->n_chunks = std::max(1, std::min(nc, 64));
+    }
+    auto seq_of = [&](int slot, int local) {
+        const long long n = (long long)h->tb[slot].elems.size();
+        const int c = n > 0 ? (int)(((long long)local * h->n_chunks) / n) : 0;
+        return slot * h->n_chunks + c;
+    };
     int max_row = 1;
     // interface ownership: owner = lowest rank with an incidence
     std::vector<std::vector<long long> > send_idx(h->world), recv_idx(h->world);
@@ -653,10 +679,12 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         if (!touched) continue;
         // local incidences (elements of this rank), ascending element order
         const int first_inc = (int)incs.size();
+        int ready = 0;
         for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
             const int e = ginc_e[p];
             if (h->el_owner_slot[e] < 0) continue;
             const int s = h->el_owner_slot[e];
+            ready = std::max(ready, seq_of(s, h->el_local[e]));
             const TypeInfo& ti = kTypes[s];
             Incidence in;
             in.ke_off = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof;
@@ -685,12 +713,30 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
         rec.len = (int)L; rec.ib = first_inc; rec.ie = (int)incs.size();
         gn_recs.push_back(rec);
+        gn_ready.push_back(ready);
         if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
     }
     if ((size_t)max_row * 3 * 4 * sizeof(double) > 200 * 1024)
         return fail(GFA_EUNSUPPORTED, "a row of AA has %d entries; the scatter kernel stages at most %d per row", max_row, (int)(200 * 1024 / (3 * 4 * sizeof(double))));
     (void)fix_mask;
     std::sort(h->owned_rows.begin(), h->owned_rows.end());
+
+    {   // order the records by pipeline step (stable: ascending group-node inside a step)
+        const int n_seq = 3 * h->n_chunks;
+        std::vector<long long> cnt((size_t)n_seq + 1, 0);
+        for (int r : gn_ready) cnt[(size_t)r + 1]++;
+        for (int i = 0; i < n_seq; i++) cnt[i + 1] += cnt[i];
+        h->gn_seq_ptr = cnt;
+        std::vector<GnRec> sorted(gn_recs.size());
+        std::vector<long long> fill(cnt.begin(), cnt.end() - 1);
+        for (size_t i = 0; i < gn_recs.size(); i++) sorted[(size_t)fill[gn_ready[i]]++] = gn_recs[i];
+        gn_recs.swap(sorted);
+        while ((int)h->chunk_ev.size() < n_seq) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->chunk_ev.push_back(e);
+        }
+    }
 
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
@@ -748,20 +794,43 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
     CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
                              st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
-    // MountLocal + MountElementLoads
-    if (!h->tb[0].elems.empty()) { launch_shell_eval(eval_args(h, 0, st->gravity_factor), s); launches++; }
-    if (!h->tb[1].elems.empty()) { launch_beam_eval(eval_args(h, 1, st->gravity_factor), s); launches++; }
-    if (!h->tb[2].elems.empty()) { launch_solid_eval(eval_args(h, 2, st->gravity_factor), s); launches++; }
-    CUDA_TRY(cudaEventRecord(h->ev[2], s));
-    // MountGlobal + MountSparse
-    if (h->n_gn_local > 0) {
-        ScatterArgs a;
-        a.n_gn = h->n_gn_local; a.gn = h->d_gn.p; a.inc = h->d_inc.p;
-        a.Ke = h->d_Ke.p; a.Pe = h->d_Pe.p;
-        a.valAA = h->d_arena.p + h->arena_off[GFA_AA];
-        a.PA = h->d_arena.p + h->vec_off[GFA_P_A]; a.IA = h->d_arena.p + h->vec_off[GFA_I_A]; a.PB = h->d_arena.p + h->vec_off[GFA_P_B];
-        a.max_row = h->max_row;
-        launch_scatter(a, s); launches++;
+    // MountLocal + MountElementLoads on stream `s`, MountGlobal + MountSparse on stream2:
+    // the scatter of the group-nodes completed by evaluation step i overlaps evaluation step i+1
+    // (and reads element blocks that are still in L2).  With n_chunks == 1 this is the plain
+    // evaluate-then-scatter sequence.
+    ScatterArgs sa;
+    sa.gn = h->d_gn.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
+    sa.valAA = h->d_arena.p + h->arena_off[GFA_AA];
+    sa.PA = h->d_arena.p + h->vec_off[GFA_P_A]; sa.IA = h->d_arena.p + h->vec_off[GFA_I_A]; sa.PB = h->d_arena.p + h->vec_off[GFA_P_B];
+    sa.max_row = h->max_row;
+    const bool pipelined = h->n_chunks > 1;
+    cudaStream_t s2 = pipelined ? h->stream2 : s;
+    for (int slot = 0; slot < 3; slot++) {
+        const long long n = (long long)h->tb[slot].elems.size();
+        for (int c = 0; c < h->n_chunks; c++) {
+            const int seq = slot * h->n_chunks + c;
+            // elements whose seq_of() is c: local in [ceil(c n / C), ceil((c+1) n / C))
+            const long long lo = (c * n + h->n_chunks - 1) / h->n_chunks, hi = ((c + 1) * n + h->n_chunks - 1) / h->n_chunks;
+            if (hi > lo) {
+                EvalArgs ea = eval_args(h, slot, st->gravity_factor);
+                ea.e_begin = (int)lo; ea.e_end = (int)hi;
+                if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
+                launches++;
+            }
+            sa.gn_begin = h->gn_seq_ptr[seq]; sa.gn_end = h->gn_seq_ptr[seq + 1];
+            if (sa.gn_end > sa.gn_begin) {
+                if (pipelined) {
+                    CUDA_TRY(cudaEventRecord(h->chunk_ev[seq], s));
+                    CUDA_TRY(cudaStreamWaitEvent(s2, h->chunk_ev[seq], 0));
+                }
+                launch_scatter(sa, s2); launches++;
+            }
+        }
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], s));        // end of the evaluation launches
+    if (pipelined) {
+        CUDA_TRY(cudaEventRecord(h->ev_scatter_done, s2));
+        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_scatter_done, 0));
     }
     if (h->n_gdest > 0) {
         GatherArgs g;

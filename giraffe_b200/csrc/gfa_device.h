@@ -9,7 +9,8 @@ namespace gfa {
 // THIS rank's partition; `conn` holds 0-based node ids.  Gauss-point state is
 // structure-of-arrays: state[k * n_gp + gp], gp = element * NGP + point.
 struct EvalArgs {
-    int n_el;
+    int n_el;                // elements of this type on this rank (array extents)
+    int e_begin, e_end;      // range evaluated by this launch (chunked pipeline)
     const int* conn;
     const int* prop;         // per element index into props
     const double* props;     // per-type property rows (see *_PROP_STRIDE)
@@ -52,7 +53,7 @@ struct GnRec {
 };
 
 struct ScatterArgs {
-    int n_gn;                    // group-nodes touched by this rank's elements
+    long long gn_begin, gn_end;  // range of group-node records handled by this launch
     const GnRec* gn;
     const Incidence* inc;
     const double* Ke;            // arena

@@ -32,7 +32,8 @@ namespace shell {
 constexpr int NGP = 3;                  // EPW (elements per warp batch) is a template parameter of eval_kernel
 constexpr int C_OFF = 0;                // 15 upper 3x3 blocks of C' (x weight)
 constexpr int F_OFF = 135;              // f (15)
-constexpr int REC = 151;                // odd stride; shape values are read from the PreCalc arrays
+constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
+constexpr int REC = 171;                // odd stride
 constexpr int smem_bytes(int epw) { return epw * NGP * REC * 8; }
 
 // upper-triangular block index of the 5x5 block matrix C'
@@ -367,6 +368,10 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         Shape sh;
         load_precalc(A, e, g, fr, sh);
         interpolate(A, nd, fr, sh, kn);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { rec[S_OFF + i] = sh.N1[i]; rec[S_OFF + 6 + i] = sh.N2[i]; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) { rec[S_OFF + 12 + i] = sh.A1[i]; rec[S_OFF + 15 + i] = sh.A2[i]; rec[S_OFF + 18 + i] = sh.A0[i]; }
     }
     const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
     const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
@@ -520,15 +525,13 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
 #pragma unroll
     for (int i = 0; i < 27; i++) K[i] = 0.0;
     double F = 0.0;
-    const size_t n_gp = (size_t)A.n_el * NGP;
 #pragma unroll 1
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
         const double* recJ = rec + jj;
         const double* rec3J = rec + 3 * jj;
-        // shape values of this point from the PreCalc arrays (same for all lanes of the element)
-        const double* S = A.shp + ((size_t)e * NGP + g);
-#define GFA_S(k_) __ldg(S + (size_t)(k_) * n_gp)
+        const double* S = rec + S_OFF;
+#define GFA_S(k_) S[k_]
         double m[5][3];
         if (!ROT) {
             const double s0 = GFA_S(b), s2 = GFA_S(6 + b);
@@ -579,9 +582,9 @@ template <int EPW>
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
-    for (long long batch = blockIdx.x; batch * EPW < A.n_el; batch += gridDim.x) {
-        const int e0 = (int)(batch * EPW);
-        const int ne = min(EPW, A.n_el - e0);
+    for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
+        const int e0 = A.e_begin + (int)(batch * EPW);
+        const int ne = min(EPW, A.e_end - e0);
         if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
         __syncwarp();
         for (int it = lane; it < ne * 18; it += 32) {
@@ -872,9 +875,9 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
-    for (long long batch = blockIdx.x; batch * EPW < A.n_el; batch += gridDim.x) {
-        const int e0 = (int)(batch * EPW);
-        const int ne = min(EPW, A.n_el - e0);
+    for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
+        const int e0 = A.e_begin + (int)(batch * EPW);
+        const int ne = min(EPW, A.e_end - e0);
         if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
         __syncwarp();
         for (int it = lane; it < ne * 9; it += 32) {
@@ -1067,9 +1070,9 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
-    for (long long batch = blockIdx.x; batch * EPW < A.n_el; batch += gridDim.x) {
-        const int e0 = (int)(batch * EPW);
-        const int ne = min(EPW, A.n_el - e0);
+    for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
+        const int e0 = A.e_begin + (int)(batch * EPW);
+        const int ne = min(EPW, A.e_end - e0);
         if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
         __syncwarp();
         for (int it = lane; it < ne * 24; it += 32) {
@@ -1112,8 +1115,8 @@ constexpr int SCATTER_WARPS = 4;
 __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs A) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gn = (long long)blockIdx.x * SCATTER_WARPS + warp;
-    if (gn >= A.n_gn) return;
+    const long long gn = A.gn_begin + (long long)blockIdx.x * SCATTER_WARPS + warp;
+    if (gn >= A.gn_end) return;
     double* acc = smem + (size_t)warp * 3 * A.max_row;
     const GnRec g = A.gn[gn];
     const long long r0 = g.row[0], r1 = g.row[1], r2 = g.row[2];
@@ -1219,16 +1222,16 @@ static int shell_epw() {
     static int v = 0;
     if (!v) {
         const char* s = getenv("GFA_SHELL_EPW");
-        v = s ? atoi(s) : 10;
-        if (v != 5 && v != 6 && v != 8 && v != 10) v = 10;
+        v = s ? atoi(s) : 8;             // measured best on B200 (profiles/r01_notes.md)
+        if (v != 5 && v != 6 && v != 8 && v != 10) v = 8;
     }
     return v;
 }
 void launch_shell_eval(const EvalArgs& a, void* s) {
-    if (a.n_el <= 0) return;
+    if (a.e_end <= a.e_begin) return;
     const int epw = shell_epw();
     const int cap = kSMs * 64;      // a multiple of the SM count; batches are strided over the grid
-    const int grid = grid_for(a.n_el, epw, cap);
+    const int grid = grid_for(a.e_end - a.e_begin, epw, cap);
     cudaStream_t st = (cudaStream_t)s;
     switch (epw) {
     case 5: shell::eval_kernel<5><<<grid, 32, shell::smem_bytes(5), st>>>(a); break;
@@ -1238,13 +1241,13 @@ void launch_shell_eval(const EvalArgs& a, void* s) {
     }
 }
 void launch_beam_eval(const EvalArgs& a, void* s) {
-    if (a.n_el <= 0) return;
-    const int grid = grid_for(a.n_el, beam::EPW, kSMs * 8 * 8);
+    if (a.e_end <= a.e_begin) return;
+    const int grid = grid_for(a.e_end - a.e_begin, beam::EPW, kSMs * 8 * 8);
     beam::eval_kernel<<<grid, 32, beam::SMEM_BYTES, (cudaStream_t)s>>>(a);
 }
 void launch_solid_eval(const EvalArgs& a, void* s) {
-    if (a.n_el <= 0) return;
-    const int grid = grid_for(a.n_el, solid::EPW, kSMs * 8 * 8);
+    if (a.e_end <= a.e_begin) return;
+    const int grid = grid_for(a.e_end - a.e_begin, solid::EPW, kSMs * 8 * 8);
     solid::eval_kernel<<<grid, 32, solid::SMEM_BYTES, (cudaStream_t)s>>>(a);
 }
 void launch_shell_precalc(const EvalArgs& a, double* geo, double* shp, void* s) {
@@ -1267,9 +1270,10 @@ void launch_node_commit(int n_nodes, double* copy, double* disp, void* s) {
     node_commit_kernel<<<(n_nodes + 255) / 256, 256, 0, (cudaStream_t)s>>>(n_nodes, copy, disp);
 }
 void launch_scatter(const ScatterArgs& a, void* s) {
-    if (a.n_gn <= 0) return;
+    const long long count = a.gn_end - a.gn_begin;
+    if (count <= 0) return;
     const size_t smem = (size_t)SCATTER_WARPS * 3 * a.max_row * sizeof(double);
-    scatter_kernel<<<(unsigned)((a.n_gn + SCATTER_WARPS - 1) / SCATTER_WARPS), 32 * SCATTER_WARPS, smem, (cudaStream_t)s>>>(a);
+    scatter_kernel<<<(unsigned)((count + SCATTER_WARPS - 1) / SCATTER_WARPS), 32 * SCATTER_WARPS, smem, (cudaStream_t)s>>>(a);
 }
 void launch_gather(const GatherArgs& a, void* s) {
     if (a.n_dest <= 0) return;
