@@ -637,7 +637,10 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         const char* env = getenv("GFA_CHUNKS");
         long long biggest = 0;
         for (int s3 = 0; s3 < 3; s3++) biggest = std::max<long long>(biggest, (long long)h->tb[s3].elems.size());
-        int nc = env ? atoi(env) : (biggest >= 200000 ? 16 : 1);
+        // measured on B200 (profiles/r01_notes.md): overlapping the two kernels is work-conserving
+        // (7.10 ms with 16 steps vs 7.23 ms with 1 on the 1M-shell plate), so the default is 1
+        (void)biggest;
+        int nc = env ? atoi(env) : 1;
         h->n_chunks = std::max(1, std::min(nc, 64));
     }
     auto seq_of = [&](int slot, int local) {

@@ -1,0 +1,379 @@
+// See GfaHost.h.  Reader and set-up logic restate the in-scope parts of the
+// reference's IO / Database / Solution classes on plain arrays; the assembly
+// itself is the C-ABI (no element arithmetic lives here).
+#include "GfaHost.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace {
+
+const double kPi = 3.1415926535897932384626433832795;
+
+// Whitespace tokens with // and /* */ comments removed (IO.cpp:683-752).
+std::vector<std::string> tokenize(const std::string& text) {
+    std::string clean;
+    clean.reserve(text.size());
+    for (size_t i = 0; i < text.size();) {
+        if (text.compare(i, 2, "//") == 0) { while (i < text.size() && text[i] != '\n') i++; }
+        else if (text.compare(i, 2, "/*") == 0) { size_t e = text.find("*/", i + 2); i = e == std::string::npos ? text.size() : e + 2; clean += ' '; }
+        else clean += text[i++];
+    }
+    std::vector<std::string> tk;
+    std::istringstream ss(clean);
+    std::string t;
+    while (ss >> t) tk.push_back(t);
+    return tk;
+}
+
+bool is_top(const std::string& s) {
+    static const char* k[] = { "Nodes", "Elements", "Materials", "Sections", "ShellSections", "CoordinateSystems", "NodeSets",
+        "Constraints", "Loads", "Environment", "SolutionSteps", "SolverOptions", "Monitor", "PostFiles",
+        "ConvergenceCriteria", "ElementSets", "ExecutionData", "EOF" };
+    for (const char* w : k) if (s == w) return true;
+    return false;
+}
+
+} // namespace
+
+double GfaNodalLoad::GetValueAt(double t, int column) const {
+    const int n = (int)(table.size() / 7);
+    if (n == 0) return 0.0;
+    if (t <= table[0]) return table[column];
+    for (int r = 0; r + 1 < n; r++) {
+        const double t0 = table[7 * r], t1 = table[7 * (r + 1)];
+        if (t <= t1) return table[7 * r + column] + (table[7 * (r + 1) + column] - table[7 * r + column]) * (t - t0) / (t1 - t0);
+    }
+    return table[7 * (n - 1) + column];
+}
+
+GfaHost::~GfaHost() { gfa_destroy(h); }
+
+// IO::ReadFile for the in-scope keyword blocks; other blocks are skipped up to
+// the next known keyword (the reference would parse them on the host anyway).
+bool GfaHost::ReadFile(const char* path) {
+    std::ifstream f(path);
+    if (!f) return fail(std::string("cannot open ") + path);
+    std::stringstream buf;
+    buf << f.rdbuf();
+    const std::vector<std::string> tk = tokenize(buf.str());
+    size_t i = 0;
+    auto num = [&](size_t j) { return j < tk.size() ? atof(tk[j].c_str()) : 0.0; };
+    auto integer = [&](size_t j) { return j < tk.size() ? atoi(tk[j].c_str()) : 0; };
+    elem_node_ptr.assign(1, 0);
+    while (i < tk.size()) {
+        const std::string& kw = tk[i];
+        if (kw == "EOF") break;
+        if (kw == "Nodes") {
+            const int n = integer(i + 1); i += 2;
+            ref_coordinates.assign(3 * (size_t)n, 0.0);
+            for (int r = 0; r < n; r++, i += 5) {
+                if (tk[i] != "Node") return fail("Error reading Nodes block");
+                const int id = integer(i + 1);
+                if (id < 1 || id > n) return fail("Node ids must be consecutive");
+                for (int k = 0; k < 3; k++) ref_coordinates[3 * (size_t)(id - 1) + k] = num(i + 2 + k);
+            }
+        } else if (kw == "Materials") {
+            const int n = integer(i + 1); i += 2;
+            for (int r = 0; r < n; r++, i += 8) {
+                if (tk[i] != "Hooke") return fail("material " + tk[i] + " is outside the accelerated path");
+                hooke.push_back(num(i + 3)); hooke.push_back(num(i + 5)); hooke.push_back(num(i + 7));
+            }
+        } else if (kw == "Sections") {
+            const int n = integer(i + 1); i += 2;
+            for (int r = 0; r < n; r++) {
+                const int kind = tk[i] == "Rectangle" ? 0 : tk[i] == "Tube" ? 1 : -1;
+                if (kind < 0) return fail("section " + tk[i] + " is outside the accelerated path");
+                section_defs.push_back(kind); section_defs.push_back(num(i + 3)); section_defs.push_back(num(i + 5));
+                i += 6;
+                if (i < tk.size() && tk[i] == "AD") i += 7;
+            }
+        } else if (kw == "ShellSections") {
+            const int n = integer(i + 1); i += 2;
+            for (int r = 0; r < n; r++, i += 4) {
+                if (tk[i] != "Homogeneous") return fail("shell section " + tk[i] + " is outside the accelerated path");
+                shell_thickness.push_back(num(i + 3));
+            }
+        } else if (kw == "CoordinateSystems") {
+            const int n = integer(i + 1); i += 2;
+            for (int r = 0; r < n; r++, i += 10) {
+                if (tk[i] != "CS") return fail("Error reading CoordinateSystems block");
+                for (int k = 0; k < 3; k++) cs_defs.push_back(num(i + 3 + k));
+                for (int k = 0; k < 3; k++) cs_defs.push_back(num(i + 7 + k));
+            }
+        } else if (kw == "NodeSets") {
+            const int n = integer(i + 1); i += 2;
+            node_sets.assign(n, std::vector<int>());
+            for (int r = 0; r < n; r++) {
+                if (tk[i] != "NodeSet") return fail("Error reading NodeSets block");
+                const int id = integer(i + 1), cnt = integer(i + 3);
+                std::vector<int>& s = node_sets[id - 1];
+                if (tk[i + 4] == "List") { for (int k = 0; k < cnt; k++) s.push_back(integer(i + 5 + k)); i += 5 + cnt; }
+                else { const int a = integer(i + 6), inc = integer(i + 8); for (int k = 0; k < cnt; k++) s.push_back(a + k * inc); i += 9; }
+            }
+        } else if (kw == "Elements") {
+            const int n = integer(i + 1); i += 2;
+            for (int r = 0; r < n; r++) {
+                const std::string& ty = tk[i];
+                int type = 0, nn = 0, mat = integer(i + 3), sec = 0, c = 0;
+                double T0 = 0.0;
+                size_t nodes_at = 0;
+                if (ty == "Beam_1") { type = GFA_BEAM_1; nn = 3; sec = integer(i + 5); c = integer(i + 7); nodes_at = i + 9; i += 12;
+                    if (i < tk.size() && tk[i] == "PreTension") { T0 = num(i + 1); i += 2; } }
+                else if (ty == "Shell_1") { type = GFA_SHELL_1; nn = 6; sec = integer(i + 5); i += 6;
+                    if (tk[i] == "CS") { c = integer(i + 1); i += 2; }
+                    nodes_at = i + 1; i += 7; }
+                else if (ty == "Solid_1") { type = GFA_SOLID_1; nn = 8; c = integer(i + 5); nodes_at = i + 7; i += 15; }
+                else return fail("element type " + ty + " is outside the accelerated path");
+                elem_type.push_back(type); elem_material.push_back(mat); elem_section.push_back(sec); elem_cs.push_back(c);
+                pretension.push_back(T0);
+                for (int k = 0; k < nn; k++) elem_nodes.push_back(integer(nodes_at + k));
+                elem_node_ptr.push_back((int)elem_nodes.size());
+            }
+        } else if (kw == "Constraints") {
+            const int n = integer(i + 1); i += 2;
+            static const char* names[6] = { "UX", "UY", "UZ", "ROTX", "ROTY", "ROTZ" };
+            for (int r = 0; r < n; r++) {
+                if (tk[i] != "NodalConstraint") return fail("constraint " + tk[i] + " stays on the host");
+                NodalConstraint nc; nc.node_set = integer(i + 3); nc.mask = 0; i += 4;
+                for (;;) {
+                    int k = -1;
+                    for (int q = 0; q < 6 && i < tk.size(); q++) if (tk[i] == names[q]) k = q;
+                    if (k < 0) break;
+                    i += 2;                                    // keyword + "BoolTable"
+                    bool first = true;
+                    while (i < tk.size() && isdigit((unsigned char)tk[i][0])) { if (first && integer(i) == 1) nc.mask |= 1 << k; first = false; i++; }
+                }
+                nodal_constraints.push_back(nc);
+            }
+        } else if (kw == "Loads") {
+            const int n = integer(i + 1); i += 2;
+            for (int r = 0; r < n; r++) {
+                if (tk[i] != "NodalLoad") return fail("load " + tk[i] + " stays on the host");
+                GfaNodalLoad l; l.node_set = integer(i + 3); l.cs = integer(i + 5);
+                const int nt = integer(i + 7); i += 8;
+                for (int k = 0; k < 7 * nt; k++) l.table.push_back(num(i + k));
+                i += 7 * (size_t)nt;
+                loads.push_back(l);
+            }
+        } else if (kw == "Environment") {
+            i++;
+            if (i < tk.size() && tk[i] == "GravityData") {
+                g_exist = true;
+                for (int k = 0; k < 3; k++) G[k] = num(i + 2 + k);
+                i += 5;
+                if (i < tk.size() && tk[i] == "BoolTable") { i++; while (i < tk.size() && isdigit((unsigned char)tk[i][0])) i++; }
+            }
+        } else if (kw == "SolutionSteps") {
+            i += 2;
+            if (i < tk.size() && tk[i] == "Static") {
+                for (size_t j = i + 2; j + 1 < tk.size() && j < i + 20; j += 2) {
+                    if (tk[j] == "EndTime") end_time = num(j + 1);
+                    if (tk[j] == "TimeStep") time_step = num(j + 1);
+                }
+                i += 20;
+            }
+        } else {
+            i++;
+            while (i < tk.size() && !is_top(tk[i])) i++;
+        }
+    }
+    const int n = number_nodes();
+    displacements.assign(6 * (size_t)n, 0.0);
+    constraints.assign(n, 0);
+    for (size_t k = 0; k < elem_nodes.size(); k++)
+        if (elem_nodes[k] < 1 || elem_nodes[k] > n) return fail("element references a node that does not exist");
+    return n > 0 && !elem_type.empty();
+}
+
+// Section::PreCalc (SecRectangle.cpp:82-96, SecTube.cpp:86-94), CoordinateSystem
+// normalisation (CoordinateSystem.cpp:64-77), then Element::PreCalc on the device.
+bool GfaHost::PreCalc(int device) {
+    sections.clear();
+    for (size_t s = 0; s + 2 < section_defs.size() + 0 && s < section_defs.size(); s += 3) {
+        const int kind = (int)section_defs[s];
+        const double a = section_defs[s + 1], b = section_defs[s + 2];
+        double A, I11, I22, I33, It;
+        if (kind == 0) {
+            A = a * b; I11 = a * b * b * b / 12.0; I22 = b * a * a * a / 12.0; I33 = I11 + I22;
+            double temp = 0;
+            for (int n = 1; n < 22; n = n + 2) temp += (1.0 / (pow((double)n, 5))) * tanh(n * kPi * b / (2 * a));
+            It = (1.0 / 3.0) * a * a * a * b * (1.0 - 192.0 * a * temp / (pow(kPi, 5) * b));
+        } else {
+            A = (kPi / 4.0) * (a * a - b * b);
+            I11 = (kPi / 64.0) * (a * a * a * a - b * b * b * b); I22 = I11;
+            I33 = (kPi / 32.0) * (a * a * a * a - b * b * b * b); It = I33;
+        }
+        const double row[6] = { A, I11, I22, 0.0, I33, It };
+        sections.insert(sections.end(), row, row + 6);
+    }
+    cs.clear();
+    for (size_t c = 0; c < cs_defs.size(); c += 6) {
+        double e1[3] = { cs_defs[c], cs_defs[c + 1], cs_defs[c + 2] }, e3[3] = { cs_defs[c + 3], cs_defs[c + 4], cs_defs[c + 5] };
+        double e2[3] = { e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0] };
+        double* v[3] = { e1, e2, e3 };
+        for (int k = 0; k < 3; k++) {
+            const double nrm = sqrt(v[k][0] * v[k][0] + v[k][1] * v[k][1] + v[k][2] * v[k][2]);
+            if (nrm != 1.0) for (int q = 0; q < 3; q++) v[k][q] = (1.0 / nrm) * v[k][q];
+            cs.insert(cs.end(), v[k], v[k] + 3);
+        }
+    }
+    gfa_model_t m;
+    memset(&m, 0, sizeof(m));
+    m.n_nodes = number_nodes(); m.ref_coordinates = ref_coordinates.data();
+    m.n_materials = (int)(hooke.size() / 3); m.hooke = hooke.data();
+    m.n_sections = (int)(sections.size() / 6); m.sections = sections.data();
+    m.n_shell_sections = (int)shell_thickness.size(); m.shell_thickness = shell_thickness.data();
+    m.n_cs = (int)(cs.size() / 9); m.cs = cs.data();
+    m.n_elements = number_elements();
+    m.elem_type = elem_type.data(); m.elem_material = elem_material.data(); m.elem_section = elem_section.data();
+    m.elem_cs = elem_cs.data(); m.elem_node_ptr = elem_node_ptr.data(); m.elem_nodes = elem_nodes.data();
+    m.beam_pretension = pretension.data();
+    m.gravity_on = g_exist ? 1 : 0;
+    for (int k = 0; k < 3; k++) m.gravity[k] = G[k];
+    m.part_rank = 0; m.part_world = 1;
+    gfa_destroy(h); h = nullptr;
+    if (gfa_create(&m, device, &h) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+// Solution::DOFsActive: element DOF masks OR-ed per node, then the nodal constraints
+// of the current solution step (NodalConstraint::Mount, NodalConstraint.cpp:152-173).
+void GfaHost::DOFsActive() {
+    const int n = number_nodes();
+    active_GL.assign(6 * (size_t)n, 0);
+    constraints.assign(n, 0);
+    for (int e = 0; e < number_elements(); e++) {
+        const int nn = elem_node_ptr[e + 1] - elem_node_ptr[e];
+        for (int a = 0; a < nn; a++) {
+            const size_t nd = (size_t)(elem_nodes[elem_node_ptr[e] + a] - 1);
+            for (int k = 0; k < 3; k++) active_GL[6 * nd + k] = 1;
+            const bool rot = elem_type[e] == GFA_BEAM_1 || (elem_type[e] == GFA_SHELL_1 && a > 2);   // Shell_1.cpp:51-68
+            if (rot) for (int k = 3; k < 6; k++) active_GL[6 * nd + k] = 1;
+        }
+    }
+    for (const NodalConstraint& c : nodal_constraints)
+        for (int nd : node_sets[c.node_set - 1]) constraints[nd - 1] |= c.mask;
+}
+
+// Solution::SetGlobalDOFs: node-major, DOF-minor; free ids 1.., fixed ids -1, -2, ...
+void GfaHost::SetGlobalDOFs() {
+    const int n = number_nodes();
+    GLs.assign(6 * (size_t)n, 0);
+    int GL_free = 0, GL_fixed = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < 6; j++) {
+            if (!active_GL[6 * (size_t)i + j]) continue;
+            if ((constraints[i] >> j) & 1) GLs[6 * (size_t)i + j] = --GL_fixed;
+            else GLs[6 * (size_t)i + j] = ++GL_free;
+        }
+    n_GL_free = GL_free; n_GL_fixed = -GL_fixed;
+}
+
+// positions NodalLoad::Mount pushes: 3x3 rotational block of every loaded node (NodalLoad.cpp:384-397)
+void GfaHost::CollectLoadPattern(std::vector<int>& m, std::vector<int>& r, std::vector<int>& c) {
+    for (const GfaNodalLoad& l : loads)
+        for (int nd : node_sets[l.node_set - 1])
+            for (int lin = 0; lin < 3; lin++)
+                for (int col = 0; col < 3; col++) {
+                    const int gl = GLs[6 * (size_t)(nd - 1) + 3 + lin], gc = GLs[6 * (size_t)(nd - 1) + 3 + col];
+                    if (gl == 0 || gc == 0) continue;
+                    m.push_back(gl > 0 ? (gc > 0 ? GFA_AA : GFA_AB) : (gc > 0 ? GFA_BA : GFA_BB));
+                    r.push_back(abs(gl) - 1); c.push_back(abs(gc) - 1);
+                }
+}
+
+bool GfaHost::SetGlobalSize() {
+    std::vector<int> m, r, c;
+    CollectLoadPattern(m, r, c);
+    if (gfa_set_dofs(h, GLs.data(), n_GL_free, n_GL_fixed, (int64_t)m.size(), m.data(), r.data(), c.data()) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+double GfaHost::LoadFactor() const { return (last_converged_time + current_time_step) / end_time; }
+
+bool GfaHost::MountLocal() {
+    gfa_step_t st;
+    st.displacements = displacements.data(); st.displacements_on_device = 0;
+    st.gravity_factor = g_exist ? LoadFactor() : 0.0;
+    if (gfa_assemble(h, &st) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+// NodalLoad::Mount (NodalLoad.cpp:322-401) for numeric tables and the global CS
+// convention Q = rows E1,E2,E3: f, m -> Q^T f; pseudo-moment m -> Xi^T m; stiffness -V(alpha, m).
+bool GfaHost::MountLoads() {
+    std::vector<int> tr[4], tc[4], ia, ib;
+    std::vector<double> tv[4], va, vb;
+    const double t = last_converged_time + current_time_step;
+    for (const GfaNodalLoad& l : loads) {
+        const std::vector<int>& set = node_sets[l.node_set - 1];
+        double mult[6];
+        for (int k = 0; k < 6; k++) { int cnt = 0; for (int nd : set) cnt += active_GL[6 * (size_t)(nd - 1) + k]; mult[k] = 1.0 / cnt; }
+        const double* Q = &cs[9 * (size_t)(l.cs - 1)];
+        for (int nd : set) {
+            double fl[3], ml[3], f[3], m[3];
+            for (int k = 0; k < 3; k++) { fl[k] = mult[k] * l.GetValueAt(t, 1 + k); ml[k] = mult[3 + k] * l.GetValueAt(t, 4 + k); }
+            for (int k = 0; k < 3; k++) { f[k] = Q[k] * fl[0] + Q[3 + k] * fl[1] + Q[6 + k] * fl[2]; m[k] = Q[k] * ml[0] + Q[3 + k] * ml[1] + Q[6 + k] * ml[2]; }
+            const double* a = &displacements[6 * (size_t)(nd - 1) + 3];
+            const double al = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            const double g = 4.0 / (4.0 + al * al);
+            const double A[9] = { 0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0 };
+            double Xi[9], mx[3];
+            for (int q = 0; q < 9; q++) Xi[q] = g * ((q % 4 == 0 ? 1.0 : 0.0) + 0.5 * A[q]);
+            for (int k = 0; k < 3; k++) mx[k] = Xi[k] * m[0] + Xi[3 + k] * m[1] + Xi[6 + k] * m[2];
+            const double h2 = 0.5 * g, h4 = -0.25 * g * g, h8 = -0.5 * g * g;
+            const double xt[3] = { a[1] * mx[2] - a[2] * mx[1], a[2] * mx[0] - a[0] * mx[2], a[0] * mx[1] - a[1] * mx[0] };
+            const double S[9] = { 0, -mx[2], mx[1], mx[2], 0, -mx[0], -mx[1], mx[0], 0 };
+            double V[9];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[3 * i + j] = (h8 * mx[i] - h4 * xt[i]) * a[j] + h2 * S[3 * i + j];
+            const int* gl = &GLs[6 * (size_t)(nd - 1)];
+            for (int lin = 0; lin < 6; lin++) {
+                if (gl[lin] == 0) continue;
+                const double v = -1.0 * (lin < 3 ? f[lin] : mx[lin - 3]);
+                if (gl[lin] > 0) { ia.push_back(gl[lin] - 1); va.push_back(v); } else { ib.push_back(-gl[lin] - 1); vb.push_back(v); }
+            }
+            for (int lin = 0; lin < 3; lin++)
+                for (int col = 0; col < 3; col++) {
+                    const int g1 = gl[3 + lin], g2 = gl[3 + col];
+                    if (g1 == 0 || g2 == 0) continue;
+                    const int w = g1 > 0 ? (g2 > 0 ? GFA_AA : GFA_AB) : (g2 > 0 ? GFA_BA : GFA_BB);
+                    tr[w].push_back(abs(g1) - 1); tc[w].push_back(abs(g2) - 1); tv[w].push_back(-1.0 * V[3 * lin + col]);
+                }
+        }
+    }
+    for (int w = 0; w < 4; w++)
+        if (!tv[w].empty() && gfa_add_host_triplets(h, w, (int64_t)tv[w].size(), tr[w].data(), tc[w].data(), tv[w].data()) != GFA_OK) return fail(gfa_last_error());
+    if (!va.empty() && gfa_add_host_vector(h, GFA_P_A, (int64_t)va.size(), ia.data(), va.data()) != GFA_OK) return fail(gfa_last_error());
+    if (!vb.empty() && gfa_add_host_vector(h, GFA_P_B, (int64_t)vb.size(), ib.data(), vb.data()) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+void GfaHost::UpdateDisps(const double* x_A) {
+    for (size_t k = 0; k < GLs.size(); k++) if (GLs[k] > 0) displacements[k] += x_A[GLs[k] - 1];
+}
+
+bool GfaHost::SaveConfiguration() {
+    if (gfa_commit_state(h) != GFA_OK) return fail(gfa_last_error());
+    std::fill(displacements.begin(), displacements.end(), 0.0);          // Solution::Zeros of the next increment
+    return true;
+}
+
+bool GfaHost::GetCSR(int which, std::vector<int>& outer, std::vector<int>& inner, std::vector<double>& values) {
+    int32_t rows, cols; int64_t nnz;
+    if (gfa_csr_dims(h, which, &rows, &cols, &nnz) != GFA_OK) return fail(gfa_last_error());
+    outer.assign((size_t)rows + 1, 0); inner.assign((size_t)nnz, 0); values.assign((size_t)nnz, 0.0);
+    if (gfa_csr_pattern(h, which, outer.data(), inner.data()) != GFA_OK) return fail(gfa_last_error());
+    if (gfa_csr_values(h, which, values.data()) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+bool GfaHost::GetVector(int which, std::vector<double>& v) {
+    v.assign(which == GFA_P_B ? n_GL_fixed : n_GL_free, 0.0);
+    if (gfa_vector(h, which, v.data()) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}

@@ -170,3 +170,68 @@ def read_inp(path: str):
     m.gravity = gravity
     info["node_sets"] = nodesets
     return _finish(m), info
+
+
+def _r(v) -> str:
+    return repr(float(v))
+
+
+def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0) -> None:
+    """Write a Model in the reference's ``.inp`` syntax, e.g. to
+    hand a synthetic mesh to a GIRAFFE build or to the C++ host mirror."""
+    names = ["UX", "UY", "UZ", "ROTX", "ROTY", "ROTZ"]
+    with open(path, "w") as f:
+        f.write(f"Nodes\t{m.n_nodes}\n")
+        for i, x in enumerate(m.xyz):
+            f.write(f"Node\t{i + 1}\t{_r(x[0])}\t{_r(x[1])}\t{_r(x[2])}\n")
+        sets = [np.asarray(n) for n, _ in m.constraints] + [np.asarray(n) for n, _, _ in m.nodal_loads]
+        if sets:
+            f.write(f"\nNodeSets\t{len(sets)}\n")
+            for k, s in enumerate(sets):
+                f.write(f"NodeSet\t{k + 1}\tNodes\t{len(s)}\tList\t" + "\t".join(str(int(v)) for v in s) + "\n")
+        f.write(f"\nElements\t{m.n_elements}\n")
+        for e in range(m.n_elements):
+            nd = "\t".join(str(int(v)) for v in m.elem_nodes[m.elem_ptr[e]:m.elem_ptr[e + 1]])
+            t = int(m.elem_type[e])
+            if t == BEAM_1:
+                f.write(f"Beam_1\t{e + 1}\tMat\t{m.elem_mat[e]}\tSec\t{m.elem_sec[e]}\tCS\t{m.elem_cs[e]}\tNodes\t{nd}")
+                if m.pretension is not None and m.pretension[e] != 0.0:
+                    f.write(f"\tPreTension\t{float(m.pretension[e])!r}")
+                f.write("\n")
+            elif t == SHELL_1:
+                f.write(f"Shell_1\t{e + 1}\tMat\t{m.elem_mat[e]}\tSec\t{m.elem_sec[e]}\tNodes\t{nd}\n")
+            else:
+                f.write(f"Solid_1\t{e + 1}\tMat\t{m.elem_mat[e]}\tCS\t{m.elem_cs[e]}\tNodes\t{nd}\n")
+        f.write(f"\nMaterials\t{len(m.hooke)}\n")
+        for k, (E, nu, rho) in enumerate(m.hooke):
+            f.write(f"Hooke\t{k + 1}\tE\t{float(E)!r}\tNu\t{float(nu)!r}\tRho\t{float(rho)!r}\n")
+        if m.section_defs:
+            f.write(f"\nSections\t{len(m.section_defs)}\n")
+            for k, (kind, a, b) in enumerate(m.section_defs):
+                f.write((f"Rectangle\t{k + 1}\tB\t{_r(a)}\tH\t{_r(b)}\n") if kind == 0 else (f"Tube\t{k + 1}\tDe\t{_r(a)}\tDi\t{_r(b)}\n"))
+        if len(m.shell_thickness):
+            f.write(f"\nShellSections\t{len(m.shell_thickness)}\n")
+            for k, t in enumerate(m.shell_thickness):
+                f.write(f"Homogeneous\t{k + 1}\tThickness\t{float(t)!r}\n")
+        if m.cs_defs:
+            f.write(f"\nCoordinateSystems\t{len(m.cs_defs)}\n")
+            for k, (e1, e3) in enumerate(m.cs_defs):
+                f.write(f"CS\t{k + 1}\tE1\t{_r(e1[0])}\t{_r(e1[1])}\t{_r(e1[2])}\tE3\t{_r(e3[0])}\t{_r(e3[1])}\t{_r(e3[2])}\n")
+        f.write(f"\nSolutionSteps\t1\nStatic\t1\nEndTime\t{_r(end_time)}\nTimeStep\t{_r(time_step)}\nMaxTimeStep\t{_r(time_step)}\n"
+                "MinTimeStep\t0.001\nMaxIt\t20\nMinIt\t3\nConvIncrease\t4\nIncFactor\t1.0\nSample\t1\n")
+        if m.nodal_loads:
+            f.write(f"\nLoads\t{len(m.nodal_loads)}\n")
+            for k, (nodes, cs, table) in enumerate(m.nodal_loads):
+                table = np.asarray(table, float)
+                f.write(f"NodalLoad\t{k + 1}\tNodeSet\t{len(m.constraints) + k + 1}\tCS\t{cs}\tNTimes\t{len(table)}\n")
+                for row in table:
+                    f.write("\t".join(repr(float(v)) for v in row) + "\n")
+        if m.constraints:
+            f.write(f"\nConstraints\t{len(m.constraints)}\n")
+            for k, (_, mask) in enumerate(m.constraints):
+                f.write(f"NodalConstraint\t{k + 1}\tNodeSet\t{k + 1}\n")
+                for b, nm in enumerate(names):
+                    f.write(f"\t{nm}\tBoolTable\t{(mask >> b) & 1}\n")
+        if m.gravity is not None:
+            f.write(f"\nEnvironment\nGravityData\tG\t{_r(m.gravity[0])}\t{_r(m.gravity[1])}\t{_r(m.gravity[2])}\tBoolTable\t1\n")
+        f.write("\nSolverOptions\nProcessors\t1\tLinSys\tDirect\n")

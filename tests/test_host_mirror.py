@@ -1,0 +1,76 @@
+"""The C++ host mirror (giraffe_b200/host: GfaHost + gfa_run) and the .inp subset
+reader/writer.  CPU: parsing and DOF numbering.  GPU: the reference's call
+sequence (ReadFile, PreCalc, DOFsActive, SetGlobalDOFs, SetGlobalSize, Clear,
+MountLocal, MountElementLoads, MountLoads, MountGlobal, MountSparse) driven from
+C++ agrees with the Python binding of the same C-ABI."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from giraffe_b200 import meshes as M
+from giraffe_b200.inp import read_inp, write_inp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "giraffe_b200", "gfa_run")
+
+
+def _model():
+    m = M.concat_models([M.beam_line(6, pretension=1.0e4), M.shell_plate(3, 2, warp=0.01)])
+    m.gravity = (0.0, 0.0, -9.81)
+    m.nodal_loads = [(np.array([13], np.int32), 1, np.array([[0, 0, 0, 0, 0, 0, 0], [1, 100.0, 0, 50.0, 0, 3.0, 0]]))]
+    return m
+
+
+def test_inp_round_trip(tmp_path):
+    m = _model()
+    p = str(tmp_path / "model.inp")
+    write_inp(m, p, end_time=1.0, time_step=0.25)
+    m2, info = read_inp(p)
+    assert info["time_step"] == 0.25
+    for k in ("xyz", "hooke", "sections", "cs", "elem_type", "elem_mat", "elem_sec", "elem_cs", "elem_nodes", "shell_thickness"):
+        assert np.array_equal(getattr(m, k), getattr(m2, k)), k
+    assert np.array_equal(m.pretension, m2.pretension)
+    assert (M.number_dofs(m)[0] == M.number_dofs(m2)[0]).all()
+    assert m2.gravity == m.gravity and len(m2.nodal_loads) == 1
+
+
+def test_cpp_reader_and_dof_numbering(tmp_path):
+    if not os.path.exists(EXE):
+        pytest.skip("gfa_run not built")
+    m = _model()
+    p = str(tmp_path / "model.inp")
+    write_inp(m, p, time_step=0.25)
+    out = json.loads(subprocess.check_output([EXE, "--parse-only", p]))
+    _, nf, nx = M.number_dofs(m)
+    assert (out["nodes"], out["elements"], out["n_GL_free"], out["n_GL_fixed"]) == (m.n_nodes, m.n_elements, nf, nx)
+    assert out["loads"] == 1 and out["time_step"] == 0.25
+
+
+@pytest.mark.gpu
+def test_cpp_host_sequence_matches_python_binding(tmp_path):
+    from giraffe_b200 import capi
+    m = _model()
+    p = str(tmp_path / "model.inp")
+    write_inp(m, p, time_step=0.25)
+    out = json.loads(subprocess.check_output([EXE, p]))
+    asm = capi.Assembler(m)
+    gls, nf, nx = asm.number_dofs()
+    asm.set_dofs(gls, nf, nx)
+    asm.set_time(0.0, 0.25)
+    d = np.zeros((m.n_nodes, 6))
+    asm.assemble(d)
+    trip, pa_add, pb_add = util.nodal_load_contribution(m, gls, d, 0.25)
+    for w in ("AA", "AB", "BA", "BB"):
+        if trip[w][0]:
+            asm.add_host_triplets(w, *trip[w])
+    asm.add_host_vector(capi.P_A, *pa_add)
+    val = asm.values("AA")
+    pa = asm.vectors()[0]
+    assert out["n_GL_free"] == nf and out["nnz_AA"] == len(val)
+    assert abs(out["sum_AA"] - val.sum()) <= 1e-9 * np.abs(val).sum()
+    assert abs(out["max_AA"] - np.abs(val).max()) <= 1e-12 * np.abs(val).max()
+    assert abs(out["max_P_A"] - np.abs(pa).max()) <= 1e-12 * np.abs(pa).max()
