@@ -821,17 +821,20 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
                 launches++;
             }
             sa.gn_begin = h->gn_seq_ptr[seq]; sa.gn_end = h->gn_seq_ptr[seq + 1];
-            if (sa.gn_end > sa.gn_begin) {
-                if (pipelined) {
-                    CUDA_TRY(cudaEventRecord(h->chunk_ev[seq], s));
-                    CUDA_TRY(cudaStreamWaitEvent(s2, h->chunk_ev[seq], 0));
-                }
+            if (pipelined && sa.gn_end > sa.gn_begin) {
+                CUDA_TRY(cudaEventRecord(h->chunk_ev[seq], s));
+                CUDA_TRY(cudaStreamWaitEvent(s2, h->chunk_ev[seq], 0));
                 launch_scatter(sa, s2); launches++;
             }
         }
     }
-    CUDA_TRY(cudaEventRecord(h->ev[2], s));        // end of the evaluation launches
+    if (!pipelined) {
+        CUDA_TRY(cudaEventRecord(h->ev[2], s));    // evaluation done; one scatter over every group-node
+        sa.gn_begin = h->gn_seq_ptr.front(); sa.gn_end = h->gn_seq_ptr.back();
+        if (sa.gn_end > sa.gn_begin) { launch_scatter(sa, s); launches++; }
+    }
     if (pipelined) {
+        CUDA_TRY(cudaEventRecord(h->ev[2], s));    // end of the evaluation launches
         CUDA_TRY(cudaEventRecord(h->ev_scatter_done, s2));
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_scatter_done, 0));
     }

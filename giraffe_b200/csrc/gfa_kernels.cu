@@ -1113,84 +1113,60 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 // =========================================================================
 constexpr int SCATTER_WARPS = 4;
 
-GFA_DI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Persistent warps with a three-deep software pipeline over their group-nodes:
-//   iteration i loads the record of group-node i+2, prefetches (L2) the incidence
-//   records and the element-block rows of group-node i+1, and accumulates group-node i,
-// so that the dependent chain record -> incidences -> element rows is served by L2
-// instead of three serial HBM round trips per group-node.
+// One warp per group-node.  (A persistent variant with an L2 prefetch pipeline and
+// variants with several incident elements in flight were measured slower on B200:
+// 4.1 ms and 4.8 ms against 3.15 ms for this plain form on the 1M-shell plate,
+// profiles/r01_notes.md -- the kernel is bound by issued instructions and sector
+// traffic, not by the depth of the dependent-load chain.)
 __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs A) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * SCATTER_WARPS;
-    long long gn = A.gn_begin + (long long)blockIdx.x * SCATTER_WARPS + warp;
+    const long long gn = A.gn_begin + (long long)blockIdx.x * SCATTER_WARPS + warp;
     if (gn >= A.gn_end) return;
     double* acc = smem + (size_t)warp * 3 * A.max_row;
-    double* acc1 = acc + A.max_row;
-    double* acc2 = acc1 + A.max_row;
-    const int lb = lane / 3, cbit = 1 << (lane % 3);
-
-    GnRec g = A.gn[gn];
-    GnRec g1 = g, g2 = g;
-    if (gn + stride < A.gn_end) g1 = A.gn[gn + stride];
-    for (; gn < A.gn_end; gn += stride) {
-        const bool has1 = gn + stride < A.gn_end, has2 = gn + 2 * stride < A.gn_end;
-        if (has2) g2 = A.gn[gn + 2 * stride];
-        if (has1) {
-            // prefetch for the next group-node: lane j takes incidence j
-            for (int k = g1.ib + lane; k < g1.ie; k += 32) {
-                const Incidence& in = A.inc[k];
-                const int n = in.n_la & 0xff, la = in.n_la >> 8;
-                const char* base = (const char*)(A.Ke + in.ke_off + (size_t)(3 * la) * n);
-                const char* end = base + (size_t)3 * n * sizeof(double);
-                for (const char* q = (const char*)((size_t)base & ~(size_t)127); q < end; q += 128) prefetch_l2(q);
+    const GnRec g = A.gn[gn];
+    const long long r0 = g.row[0], r1 = g.row[1], r2 = g.row[2];
+    const int ib = g.ib, ie = g.ie;
+    if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
+        const int L = g.len;
+        double* acc1 = acc + A.max_row;
+        double* acc2 = acc1 + A.max_row;
+        for (int p = lane; p < L; p += 32) { acc[p] = 0.0; acc1[p] = 0.0; acc2[p] = 0.0; }
+        __syncwarp();
+        // incident elements in ascending order (the reference's triplet order)
+        const int lb = lane / 3, cbit = 1 << (lane % 3);
+        for (int k = ib; k < ie; k++) {
+            const Incidence& in = A.inc[k];
+            const int n = in.n_la & 0xff, la = in.n_la >> 8;
+            if (lane < n) {
+                const int r = in.roff[lb];
+                const int mask = (r >> 28) & 7;
+                if (mask & cbit) {
+                    const int pos = (r & 0x0fffffff) + __popc(mask & (cbit - 1));
+                    const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
+                    if (r0 >= 0) acc[pos] += row[0];
+                    if (r1 >= 0) acc1[pos] += row[n];
+                    if (r2 >= 0) acc2[pos] += row[2 * n];
+                }
             }
-        }
-        if (has2 && lane == 0) { prefetch_l2(A.inc + g2.ib); if (g2.ie - g2.ib > 2) prefetch_l2((const char*)(A.inc + g2.ib) + 128); }
-
-        const long long r0 = g.row[0], r1 = g.row[1], r2 = g.row[2];
-        const int ib = g.ib, ie = g.ie;
-        if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
-            const int L = g.len;
-            for (int p = lane; p < L; p += 32) { acc[p] = 0.0; acc1[p] = 0.0; acc2[p] = 0.0; }
             __syncwarp();
-            // incident elements in ascending order (the reference's triplet order)
+        }
+        if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
+        if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc1[p]; }
+        if (r2 >= 0) { double* o = A.valAA + r2; for (int p = lane; p < L; p += 32) o[p] = acc2[p]; }
+    }
+    // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
+    if (lane < 3) {
+        const int gl = g.gl[lane];
+        if (gl != 0) {
+            double s = 0.0;
             for (int k = ib; k < ie; k++) {
                 const Incidence& in = A.inc[k];
-                const int n = in.n_la & 0xff, la = in.n_la >> 8;
-                if (lane < n) {
-                    const int r = in.roff[lb];
-                    const int mask = (r >> 28) & 7;
-                    if (mask & cbit) {
-                        const int pos = (r & 0x0fffffff) + __popc(mask & (cbit - 1));
-                        const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
-                        if (r0 >= 0) acc[pos] += row[0];
-                        if (r1 >= 0) acc1[pos] += row[n];
-                        if (r2 >= 0) acc2[pos] += row[2 * n];
-                    }
-                }
-                __syncwarp();
+                s += A.Pe[in.pe_off + 3 * (in.n_la >> 8) + lane];
             }
-            if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
-            if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc1[p]; }
-            if (r2 >= 0) { double* o = A.valAA + r2; for (int p = lane; p < L; p += 32) o[p] = acc2[p]; }
-            __syncwarp();
+            if (gl > 0) { A.PA[gl - 1] = s; A.IA[gl - 1] = s; }
+            else A.PB[-gl - 1] = s;
         }
-        // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
-        if (lane < 3) {
-            const int gl = g.gl[lane];
-            if (gl != 0) {
-                double s = 0.0;
-                for (int k = ib; k < ie; k++) {
-                    const Incidence& in = A.inc[k];
-                    s += A.Pe[in.pe_off + 3 * (in.n_la >> 8) + lane];
-                }
-                if (gl > 0) { A.PA[gl - 1] = s; A.IA[gl - 1] = s; }
-                else A.PB[-gl - 1] = s;
-            }
-        }
-        g = g1; g1 = g2;
     }
 }
 
@@ -1303,9 +1279,7 @@ void launch_scatter(const ScatterArgs& a, void* s) {
     const long long count = a.gn_end - a.gn_begin;
     if (count <= 0) return;
     const size_t smem = (size_t)SCATTER_WARPS * 3 * a.max_row * sizeof(double);
-    // persistent grid: 16 blocks of 4 warps per SM (full occupancy), group-nodes strided over the warps
-    long long blocks = (count + SCATTER_WARPS - 1) / SCATTER_WARPS;
-    if (blocks > kSMs * 16) blocks = kSMs * 16;
+    const long long blocks = (count + SCATTER_WARPS - 1) / SCATTER_WARPS;
     scatter_kernel<<<(unsigned)blocks, 32 * SCATTER_WARPS, smem, (cudaStream_t)s>>>(a);
 }
 void launch_gather(const GatherArgs& a, void* s) {
