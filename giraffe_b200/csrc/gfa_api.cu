@@ -129,7 +129,9 @@ struct gfa_handle {
     long long arena_size = 0;
     DevBuf<double> d_arena;
     DevBuf<GnRec> d_gn;
-    DevBuf<Incidence> d_inc;
+    DevBuf<RunEnt> d_runs;
+    DevBuf<int> d_ovf;
+    DevBuf<PInc> d_inc;
     int n_gn_local = 0, max_row = 0;
     DevBuf<long long> d_gseg, d_gsrc, d_gdest;
     long long n_gdest = 0;
@@ -628,7 +630,10 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
 
     // ---- scatter metadata for this rank's group-nodes -----------------------
     std::vector<int> gn_list;            // group-nodes with at least one local incidence
-    std::vector<Incidence> incs;
+    std::vector<PInc> incs;
+    std::vector<RunEnt> runs;
+    std::vector<int> ovf;
+    std::vector<std::vector<int> > run_src;   // scratch: sources per run of the current group-node
     std::vector<GnRec> gn_recs;
     std::vector<int> gn_ready;           // pipeline step after which all incident elements are evaluated
     // chunked pipeline: every element type is evaluated in n_chunks launches; a group-node can be
@@ -680,8 +685,13 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             else list_for(send_idx[owner]);
         }
         if (!touched) continue;
-        // local incidences (elements of this rank), ascending element order
+        // local incidences (elements of this rank), ascending element order; every block of an
+        // incident element feeds the run of the group-node that block belongs to
         const int first_inc = (int)incs.size();
+        const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
+        const int n_runs = (int)(nb1 - nb0);
+        if ((int)run_src.size() < n_runs) run_src.resize(n_runs);
+        for (int j = 0; j < n_runs; j++) run_src[j].clear();
         int ready = 0;
         for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
             const int e = ginc_e[p];
@@ -689,22 +699,20 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             const int s = h->el_owner_slot[e];
             ready = std::max(ready, seq_of(s, h->el_local[e]));
             const TypeInfo& ti = kTypes[s];
-            Incidence in;
-            in.ke_off = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof;
+            const int la = ginc_b[p];
+            PInc in;
             in.pe_off = h->tb[s].pe_base + h->el_local[e] * ti.ndof;
-            in.n_la = ti.ndof | (ginc_b[p] << 8);
-            for (int b = 0; b < 9; b++) in.roff[b] = 0;
+            in.la = la;
+            incs.push_back(in);
+            const long long ke = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof + (long long)(3 * la) * ti.ndof;
             for (int b = 0; b < ti.nb; b++) {
                 int a, grp; block_node(s, b, a, grp);
                 const int other = h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
-                // start of `other`'s run = free DOFs of the neighbours that precede it
-                const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
-                const int* pos = std::lower_bound(nb0, nb1, other);
-                int start = 0;
-                for (const int* q = nb0; q < pos; q++) start += __builtin_popcount(free_mask((size_t)*q));
-                in.roff[b] = (free_mask((size_t)other) << 28) | start;
+                const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
+                const long long off = ke + 3 * b;                 // first entry of the 3x3 block (row 3*la, column 3*b)
+                if (off % 3 != 0 || off / 3 >= (1LL << 30)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 30-bit block index of the slot map");
+                run_src[j].push_back((int)(off / 3) | (s << 30));
             }
-            incs.push_back(in);
         }
         if ((int)incs.size() == first_inc) continue;
         gn_list.push_back((int)gn);
@@ -714,7 +722,25 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             rec.gl[k] = g;
             rec.row[k] = g > 0 ? AA.rowptr[AA.row_local[g - 1]] : -1;
         }
-        rec.len = (int)L; rec.ib = first_inc; rec.ie = (int)incs.size();
+        rec.ib = first_inc; rec.ie = (int)incs.size(); rec.pad = 0;
+        rec.rb = (int)runs.size();
+        {
+            int col = 0;
+            for (int j = 0; j < n_runs; j++) {
+                const int fm = free_mask((size_t)nb0[j]);
+                const std::vector<int>& src = run_src[j];
+                if (fm && !src.empty()) {
+                    if (src.size() > 255 || col > 0xffff) return fail(GFA_EUNSUPPORTED, "group-node with more than 255 incident elements or 65535 columns");
+                    RunEnt r;
+                    r.head = (unsigned)col | ((unsigned)fm << 16) | ((unsigned)src.size() << 24);
+                    r.src0 = src[0]; r.src1 = src.size() > 1 ? src[1] : 0;
+                    if (src.size() > 2) { r.src0 = (int)ovf.size(); ovf.insert(ovf.end(), src.begin(), src.end()); }
+                    runs.push_back(r);
+                }
+                col += __builtin_popcount(fm);
+            }
+        }
+        rec.re = (int)runs.size();
         gn_recs.push_back(rec);
         gn_ready.push_back(ready);
         if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
@@ -745,6 +771,9 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
     CUDA_TRY(cudaMemset(h->d_arena.p, 0, (size_t)h->arena_size * sizeof(double)));
     CUDA_TRY(h->d_gn.upload(gn_recs));
+    CUDA_TRY(h->d_runs.upload(runs));
+    if (ovf.empty()) ovf.push_back(0);
+    CUDA_TRY(h->d_ovf.upload(ovf));
     CUDA_TRY(h->d_inc.upload(incs));
     CUDA_TRY(h->d_gseg.upload(gseg));
     CUDA_TRY(h->d_gsrc.upload(gsrc));
@@ -802,10 +831,9 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
     // (and reads element blocks that are still in L2).  With n_chunks == 1 this is the plain
     // evaluate-then-scatter sequence.
     ScatterArgs sa;
-    sa.gn = h->d_gn.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
+    sa.gn = h->d_gn.p; sa.runs = h->d_runs.p; sa.ovf = h->d_ovf.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
     sa.valAA = h->d_arena.p + h->arena_off[GFA_AA];
     sa.PA = h->d_arena.p + h->vec_off[GFA_P_A]; sa.IA = h->d_arena.p + h->vec_off[GFA_I_A]; sa.PB = h->d_arena.p + h->vec_off[GFA_P_B];
-    sa.max_row = h->max_row;
     const bool pipelined = h->n_chunks > 1;
     cudaStream_t s2 = pipelined ? h->stream2 : s;
     for (int slot = 0; slot < 3; slot++) {

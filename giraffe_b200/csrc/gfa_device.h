@@ -37,30 +37,41 @@ constexpr int BEAM_STATE = 15;         // Q_i(9) dz_i(3) kappa_i_ref(3)
 // "Group-node" = one 3-DOF group of a node (translations or rotations); every
 // in-scope element block is 3x3-structured over group-nodes in the
 // reference's own local DOF order (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444).
-struct Incidence {
-    long long ke_off;   // offset (doubles) of the element's K in the Ke arena
-    int pe_off;         // offset of the element's P in the Pe arena
-    int n_la;           // ndof | (local block index << 8)
-    int roff[9];        // per local block b: (free-mask(3 bits) << 28) | start of b's run in the AA row
+// All rows of a group-node share one column layout, made of "runs": the free
+// DOFs of one neighbouring group-node are consecutive columns.  The slot map is
+// therefore one entry per (group-node, neighbour) pair listing the element
+// blocks that contribute to that 3x3 patch of the CSR, in ascending element
+// order (the order the reference pushes and Eigen sums, Solution.cpp:327-328).
+struct RunEnt {
+    unsigned head;      // column offset of the run inside the row (bits 0-15) | free mask of the
+                        // neighbour's 3 DOFs (bits 16-18) | number of contributing blocks (bits 24-31)
+    int src0, src1;     // count <= 2: the sources themselves; count > 2: src0 = start in the overflow list
 };
-
+// source encoding: (offset of the 3x3 block's first entry in the Ke arena) / 3 in bits 0-29,
+// element type slot (row stride 27 / 18 / 24) in bits 30-31
+struct PInc {           // (element, local block) incidences of a group-node, for the residual vectors
+    int pe_off;         // offset of the element's P in the Pe arena
+    int la;             // local block index
+};
 // one record per group-node this rank's elements touch
 struct GnRec {
     long long row[3];   // start of each of the group's rows in valAA (-1: DOF not free)
     int gl[3];          // global DOF ids (Node::GLs) of the group's 3 DOFs
-    int len;            // length of the group's AA rows (identical for its 3 rows)
+    int rb, re;         // runs [rb, re)
     int ib, ie;         // incidences [ib, ie), element-ascending
+    int pad;
 };
 
 struct ScatterArgs {
     long long gn_begin, gn_end;  // range of group-node records handled by this launch
     const GnRec* gn;
-    const Incidence* inc;
+    const RunEnt* runs;
+    const int* ovf;              // overflow source lists (patches fed by more than two blocks)
+    const PInc* inc;
     const double* Ke;            // arena
     const double* Pe;            // arena
     double* valAA;
     double* PA; double* IA; double* PB;
-    int max_row;                 // longest AA row among this rank's group-nodes
 };
 
 // entries that involve a fixed DOF (AB, BA, BB): explicit gather lists

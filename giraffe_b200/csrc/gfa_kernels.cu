@@ -1113,56 +1113,49 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 // =========================================================================
 constexpr int SCATTER_WARPS = 4;
 
-// One warp per group-node.  (A persistent variant with an L2 prefetch pipeline and
-// variants with several incident elements in flight were measured slower on B200:
-// 4.1 ms and 4.8 ms against 3.15 ms for this plain form on the 1M-shell plate,
-// profiles/r01_notes.md -- the kernel is bound by issued instructions and sector
-// traffic, not by the depth of the dependent-load chain.)
+// One warp per group-node, one LANE per run (= per neighbouring group-node): the lane
+// gathers the 3x3 patch of every contributing element block straight from the Ke
+// arena (up to 9 independent 8-byte loads per block, element-ascending adds in
+// registers) and writes its <= 3 consecutive columns of the group's <= 3 rows.
+// Neighbouring lanes write neighbouring columns, so each CSR row is written once,
+// coalesced.  No shared memory, no warp synchronisation, ~5x fewer instructions than
+// the row-staging variants measured before it (profiles/r01_notes.md).
 __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs A) {
-    extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long gn = A.gn_begin + (long long)blockIdx.x * SCATTER_WARPS + warp;
     if (gn >= A.gn_end) return;
-    double* acc = smem + (size_t)warp * 3 * A.max_row;
-    const GnRec g = A.gn[gn];
-    const long long r0 = g.row[0], r1 = g.row[1], r2 = g.row[2];
-    const int ib = g.ib, ie = g.ie;
+    const GnRec* gp = A.gn + gn;
+    const long long r0 = gp->row[0], r1 = gp->row[1], r2 = gp->row[2];
+    const int rb = gp->rb, re = gp->re;
     if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
-        const int L = g.len;
-        double* acc1 = acc + A.max_row;
-        double* acc2 = acc1 + A.max_row;
-        for (int p = lane; p < L; p += 32) { acc[p] = 0.0; acc1[p] = 0.0; acc2[p] = 0.0; }
-        __syncwarp();
-        // incident elements in ascending order (the reference's triplet order)
-        const int lb = lane / 3, cbit = 1 << (lane % 3);
-        for (int k = ib; k < ie; k++) {
-            const Incidence& in = A.inc[k];
-            const int n = in.n_la & 0xff, la = in.n_la >> 8;
-            if (lane < n) {
-                const int r = in.roff[lb];
-                const int mask = (r >> 28) & 7;
-                if (mask & cbit) {
-                    const int pos = (r & 0x0fffffff) + __popc(mask & (cbit - 1));
-                    const double* row = A.Ke + in.ke_off + (size_t)(3 * la) * n + lane;
-                    if (r0 >= 0) acc[pos] += row[0];
-                    if (r1 >= 0) acc1[pos] += row[n];
-                    if (r2 >= 0) acc2[pos] += row[2 * n];
-                }
+        for (int j = rb + lane; j < re; j += 32) {
+            const RunEnt r = A.runs[j];
+            const int col = r.head & 0xffff, fm = (r.head >> 16) & 7, cnt = r.head >> 24;
+            double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
+            for (int k = 0; k < cnt; k++) {
+                const int src = cnt <= 2 ? (k == 0 ? r.src0 : r.src1) : __ldg(A.ovf + r.src0 + k);
+                const int ty = (unsigned)src >> 30;
+                const int n = ty == 0 ? 27 : ty == 1 ? 18 : 24;
+                const double* p = A.Ke + 3 * (size_t)(src & 0x3fffffff);
+                if (r0 >= 0) { a00 += p[0]; a01 += p[1]; a02 += p[2]; }
+                if (r1 >= 0) { a10 += p[n]; a11 += p[n + 1]; a12 += p[n + 2]; }
+                if (r2 >= 0) { a20 += p[2 * n]; a21 += p[2 * n + 1]; a22 += p[2 * n + 2]; }
             }
-            __syncwarp();
+            // columns of the run = the neighbour's free DOFs, in DOF order
+            const int c1 = col + (fm & 1), c2 = c1 + ((fm >> 1) & 1);
+            if (r0 >= 0) { double* o = A.valAA + r0; if (fm & 1) o[col] = a00; if (fm & 2) o[c1] = a01; if (fm & 4) o[c2] = a02; }
+            if (r1 >= 0) { double* o = A.valAA + r1; if (fm & 1) o[col] = a10; if (fm & 2) o[c1] = a11; if (fm & 4) o[c2] = a12; }
+            if (r2 >= 0) { double* o = A.valAA + r2; if (fm & 1) o[col] = a20; if (fm & 2) o[c1] = a21; if (fm & 4) o[c2] = a22; }
         }
-        if (r0 >= 0) { double* o = A.valAA + r0; for (int p = lane; p < L; p += 32) o[p] = acc[p]; }
-        if (r1 >= 0) { double* o = A.valAA + r1; for (int p = lane; p < L; p += 32) o[p] = acc1[p]; }
-        if (r2 >= 0) { double* o = A.valAA + r2; for (int p = lane; p < L; p += 32) o[p] = acc2[p]; }
     }
     // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
     if (lane < 3) {
-        const int gl = g.gl[lane];
+        const int gl = gp->gl[lane];
         if (gl != 0) {
             double s = 0.0;
-            for (int k = ib; k < ie; k++) {
-                const Incidence& in = A.inc[k];
-                s += A.Pe[in.pe_off + 3 * (in.n_la >> 8) + lane];
+            for (int k = gp->ib; k < gp->ie; k++) {
+                const PInc in = A.inc[k];
+                s += A.Pe[in.pe_off + 3 * in.la + lane];
             }
             if (gl > 0) { A.PA[gl - 1] = s; A.IA[gl - 1] = s; }
             else A.PB[-gl - 1] = s;
@@ -1217,7 +1210,6 @@ int configure_kernels() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(solid::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solid::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return (int)e;
 }
 
@@ -1278,9 +1270,8 @@ void launch_node_commit(int n_nodes, double* copy, double* disp, void* s) {
 void launch_scatter(const ScatterArgs& a, void* s) {
     const long long count = a.gn_end - a.gn_begin;
     if (count <= 0) return;
-    const size_t smem = (size_t)SCATTER_WARPS * 3 * a.max_row * sizeof(double);
     const long long blocks = (count + SCATTER_WARPS - 1) / SCATTER_WARPS;
-    scatter_kernel<<<(unsigned)blocks, 32 * SCATTER_WARPS, smem, (cudaStream_t)s>>>(a);
+    scatter_kernel<<<(unsigned)blocks, 32 * SCATTER_WARPS, 0, (cudaStream_t)s>>>(a);
 }
 void launch_gather(const GatherArgs& a, void* s) {
     if (a.n_dest <= 0) return;
