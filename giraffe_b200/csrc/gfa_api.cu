@@ -551,7 +551,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 Ent en;
                 en.mat = (g1 > 0) ? GFA_AB : (g2 > 0 ? GFA_BA : GFA_BB);
                 en.row = std::abs(g1) - 1; en.col = std::abs(g2) - 1;
-                en.src = mine ? base + (long long)i * ti.ndof + j : -1;
+                en.src = mine ? base + (long long)(((i / 3) * ti.nb + (j / 3)) * 9 + (i % 3) * 3 + (j % 3)) : -1;   // block-major
                 en.rank = h->world > 1 ? el_rank[e] : 0;
                 ents.push_back(en);
             }
@@ -704,14 +704,14 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             in.pe_off = h->tb[s].pe_base + h->el_local[e] * ti.ndof;
             in.la = la;
             incs.push_back(in);
-            const long long ke = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof + (long long)(3 * la) * ti.ndof;
+            const long long ke = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof + (long long)la * ti.nb * 9;
             for (int b = 0; b < ti.nb; b++) {
                 int a, grp; block_node(s, b, a, grp);
                 const int other = h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
                 const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
-                const long long off = ke + 3 * b;                 // first entry of the 3x3 block (row 3*la, column 3*b)
-                if (off % 3 != 0 || off / 3 >= (1LL << 30)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 30-bit block index of the slot map");
-                run_src[j].push_back((int)(off / 3) | (s << 30));
+                const long long off = ke + 9 * b;                 // contiguous 3x3 block (la, b) of the block-major element matrix
+                if (off % 9 != 0 || off / 9 >= (1LL << 32)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 32-bit block index of the slot map");
+                run_src[j].push_back((int)(unsigned)(off / 9));
             }
         }
         if ((int)incs.size() == first_inc) continue;
@@ -977,7 +977,13 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     if (s < 0) return fail(GFA_EINVAL, "element %d belongs to another rank's partition", e + 1);
     CUDA_TRY(cudaSetDevice(h->device));
     const int n = kTypes[s].ndof;
-    if (K) CUDA_TRY(cudaMemcpy(K, h->d_Ke.p + h->tb[s].ke_base + (size_t)h->el_local[e] * n * n, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+    if (K) {
+        std::vector<double> blk((size_t)n * n);
+        CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)h->el_local[e] * n * n, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+        const int nb = n / 3;     // device layout is block-major; hand back plain row-major
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) K[i * n + j] = blk[((i / 3) * nb + (j / 3)) * 9 + (i % 3) * 3 + (j % 3)];
+    }
     if (P) CUDA_TRY(cudaMemcpy(P, h->d_Pe.p + h->tb[s].pe_base + (size_t)h->el_local[e] * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return n;
 }

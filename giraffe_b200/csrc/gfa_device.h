@@ -21,7 +21,8 @@ struct EvalArgs {
     const double* geo;       // Shell_1 PreCalc: R(9), area per element (SoA)
     const double* shp;       // Shell_1 PreCalc: 21 shape values per Gauss point (SoA)
     double* state;           // committed Gauss-point state (read by eval, written by commit)
-    double* Ke;              // [n_el * ndof * ndof] row-major, reference local DOF order
+    double* Ke;              // [n_el * ndof * ndof] element blocks, stored block-major: the (ndof/3)^2 3x3 blocks
+                             // (row block, column block) are contiguous, each row-major; reference local DOF order
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
     double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
 };
@@ -47,8 +48,7 @@ struct RunEnt {
                         // neighbour's 3 DOFs (bits 16-18) | number of contributing blocks (bits 24-31)
     int src0, src1;     // count <= 2: the sources themselves; count > 2: src0 = start in the overflow list
 };
-// source encoding: (offset of the 3x3 block's first entry in the Ke arena) / 3 in bits 0-29,
-// element type slot (row stride 27 / 18 / 24) in bits 30-31
+// source encoding: (offset of the contiguous 3x3 block in the Ke arena) / 9
 struct PInc {           // (element, local block) incidences of a group-node, for the residual vectors
     int pe_off;         // offset of the element's P in the Pe arena
     int la;             // local block index

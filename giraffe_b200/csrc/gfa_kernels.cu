@@ -566,9 +566,10 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
 #undef GFA_S
     }
     const int col = ROT ? 18 + 3 * b + jj : 3 * b + jj;
-    double* Ke = A.Ke + (size_t)e * 729 + col;
+    // element block stored as 9x9 contiguous 3x3 blocks (block-major): block (a,cb), entry (ii,jj)
+    double* Ke = A.Ke + (size_t)e * 729 + (col / 3) * 9 + (col % 3);
 #pragma unroll
-    for (int r = 0; r < 27; r++) Ke[r * 27] = K[r];
+    for (int r = 0; r < 27; r++) Ke[(r / 3) * 81 + (r % 3) * 3] = K[r];
     // P = Fint - Fext; self-weight applied twice as in the reference (:1340-1375)
     double fe = 0.0;
     if (!ROT && (A.gx != 0.0 || A.gy != 0.0 || A.gz != 0.0)) {
@@ -867,9 +868,9 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         }
     }
     const int col = 6 * b + (ROT ? 3 : 0) + jj;
-    double* Ke = A.Ke + (size_t)e * 324 + col;
+    double* Ke = A.Ke + (size_t)e * 324 + (col / 3) * 9 + (col % 3);        // block-major 6x6 blocks of 3x3
 #pragma unroll
-    for (int r = 0; r < 18; r++) Ke[r * 18] = K[r];
+    for (int r = 0; r < 18; r++) Ke[(r / 3) * 54 + (r % 3) * 3] = K[r];
     A.Pe[(size_t)e * 18 + col] = F - fe;
 }
 
@@ -1062,9 +1063,9 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         fe += rec[W_OFF] * rec[N_OFF + b] * gk;
     }
     const int col = 3 * b + jj;
-    double* Ke = A.Ke + (size_t)e * 576 + col;
+    double* Ke = A.Ke + (size_t)e * 576 + (col / 3) * 9 + (col % 3);        // block-major 8x8 blocks of 3x3
 #pragma unroll
-    for (int r = 0; r < 24; r++) Ke[r * 24] = K[r];
+    for (int r = 0; r < 24; r++) Ke[(r / 3) * 72 + (r % 3) * 3] = K[r];
     A.Pe[(size_t)e * 24 + col] = F - fe;
 }
 
@@ -1134,12 +1135,10 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
             double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
             for (int k = 0; k < cnt; k++) {
                 const int src = cnt <= 2 ? (k == 0 ? r.src0 : r.src1) : __ldg(A.ovf + r.src0 + k);
-                const int ty = (unsigned)src >> 30;
-                const int n = ty == 0 ? 27 : ty == 1 ? 18 : 24;
-                const double* p = A.Ke + 3 * (size_t)(src & 0x3fffffff);
+                const double* p = A.Ke + 9 * (size_t)(unsigned)src;      // one contiguous 3x3 block (72 B)
                 if (r0 >= 0) { a00 += p[0]; a01 += p[1]; a02 += p[2]; }
-                if (r1 >= 0) { a10 += p[n]; a11 += p[n + 1]; a12 += p[n + 2]; }
-                if (r2 >= 0) { a20 += p[2 * n]; a21 += p[2 * n + 1]; a22 += p[2 * n + 2]; }
+                if (r1 >= 0) { a10 += p[3]; a11 += p[4]; a12 += p[5]; }
+                if (r2 >= 0) { a20 += p[6]; a21 += p[7]; a22 += p[8]; }
             }
             // columns of the run = the neighbour's free DOFs, in DOF order
             const int c1 = col + (fm & 1), c2 = c1 + ((fm >> 1) & 1);
