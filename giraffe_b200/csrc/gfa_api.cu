@@ -636,6 +636,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<std::vector<int> > run_src;   // scratch: sources per run of the current group-node
     std::vector<GnRec> gn_recs;
     std::vector<int> gn_ready;           // pipeline step after which all incident elements are evaluated
+    std::vector<int> gn_first;
     // chunked pipeline: every element type is evaluated in n_chunks launches; a group-node can be
     // scattered as soon as the launch holding its last incident element has finished
     {
@@ -743,6 +744,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         rec.re = (int)runs.size();
         gn_recs.push_back(rec);
         gn_ready.push_back(ready);
+        gn_first.push_back(incs[first_inc].pe_off);     // position of the first incident element (locality key)
         if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
     }
     if ((size_t)max_row * 3 * 4 * sizeof(double) > 200 * 1024)
@@ -756,9 +758,18 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         for (int r : gn_ready) cnt[(size_t)r + 1]++;
         for (int i = 0; i < n_seq; i++) cnt[i + 1] += cnt[i];
         h->gn_seq_ptr = cnt;
+        // inside a step, group-nodes are processed in the order of their first incident element, so
+        // that the (up to 9) group-nodes reading one element's blocks run close together and the
+        // sectors / blocks they share are served by L2 (node-id order would visit an element's
+        // corner and mid-side nodes millions of group-nodes apart)
+        std::vector<size_t> order(gn_recs.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+            if (gn_ready[x] != gn_ready[y]) return gn_ready[x] < gn_ready[y];
+            return gn_first[x] < gn_first[y];
+        });
         std::vector<GnRec> sorted(gn_recs.size());
-        std::vector<long long> fill(cnt.begin(), cnt.end() - 1);
-        for (size_t i = 0; i < gn_recs.size(); i++) sorted[(size_t)fill[gn_ready[i]]++] = gn_recs[i];
+        for (size_t i = 0; i < order.size(); i++) sorted[i] = gn_recs[order[i]];
         gn_recs.swap(sorted);
         while ((int)h->chunk_ev.size() < n_seq) {
             cudaEvent_t e;

@@ -1132,14 +1132,33 @@ __global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs
         for (int j = rb + lane; j < re; j += 32) {
             const RunEnt r = A.runs[j];
             const int col = r.head & 0xffff, fm = (r.head >> 16) & 7, cnt = r.head >> 24;
-            double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
-            for (int k = 0; k < cnt; k++) {
-                const int src = cnt <= 2 ? (k == 0 ? r.src0 : r.src1) : __ldg(A.ovf + r.src0 + k);
-                const double* p = A.Ke + 9 * (size_t)(unsigned)src;      // one contiguous 3x3 block (72 B)
-                if (r0 >= 0) { a00 += p[0]; a01 += p[1]; a02 += p[2]; }
-                if (r1 >= 0) { a10 += p[3]; a11 += p[4]; a12 += p[5]; }
-                if (r2 >= 0) { a20 += p[6]; a21 += p[7]; a22 += p[8]; }
+            double a[9];
+            {
+                // first two contributing blocks: all 18 loads are issued before the first add
+                const double* p0 = A.Ke + 9 * (size_t)(unsigned)(cnt <= 2 ? r.src0 : __ldg(A.ovf + r.src0));
+                const double* p1 = A.Ke + 9 * (size_t)(unsigned)(cnt <= 2 ? r.src1 : __ldg(A.ovf + r.src0 + 1));
+                double x[9], y[9];
+#pragma unroll
+                for (int i = 0; i < 9; i++) x[i] = p0[i];
+                if (cnt > 1) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) y[i] = p1[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) y[i] = 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 9; i++) a[i] = (0.0 + x[i]) + y[i];
             }
+            for (int k = 2; k < cnt; k++) {
+                const double* p = A.Ke + 9 * (size_t)(unsigned)__ldg(A.ovf + r.src0 + k);
+                double x[9];
+#pragma unroll
+                for (int i = 0; i < 9; i++) x[i] = p[i];
+#pragma unroll
+                for (int i = 0; i < 9; i++) a[i] += x[i];
+            }
+            const double a00 = a[0], a01 = a[1], a02 = a[2], a10 = a[3], a11 = a[4], a12 = a[5], a20 = a[6], a21 = a[7], a22 = a[8];
             // columns of the run = the neighbour's free DOFs, in DOF order
             const int c1 = col + (fm & 1), c2 = c1 + ((fm >> 1) & 1);
             if (r0 >= 0) { double* o = A.valAA + r0; if (fm & 1) o[col] = a00; if (fm & 2) o[c1] = a01; if (fm & 4) o[c2] = a02; }
