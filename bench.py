@@ -279,9 +279,20 @@ def run_cuda(args):
         nnz_local = nnz[0]                      # csr_dims are this rank's stored rows
         alg_bytes = n_local * (SHELL_READ_BYTES) + 8.0 * nnz_local + 16.0 * nf / world
         ev, sc = float(np.mean(eval_ms)), float(np.mean(scat_ms))
-        dom = "shell::eval_kernel" if ev >= sc else "scatter_kernel"
-        dom_ms = max(ev, sc)
+        # The path is two launches per step (element evaluation, then the CSR gather); the
+        # algorithmic bytes of SURVEY.md 8(d) belong to the pair, so the roofline is taken over
+        # both kernels' device time (CUDA events on the library's stream, gfa_last_timing).
+        dom = "shell::eval_kernel + scatter_kernel (one step = these two launches)"
+        dom_ms = ev + sc
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("elements") == n_local:
+                traffic = tj["dram_bytes_per_step"]
+        fp64_peak = 34.16      # measured on this pool with tools/fp64_peak.cu (profiles/fp64_peak_r01.json)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cb = time_cpu(3, 1)
@@ -296,10 +307,13 @@ def run_cuda(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": None, "kernel": dom, "peak_source": pk_src,
+                         "traffic": traffic, "kernel": dom, "peak_source": pk_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
-                         "note": "algorithmic bytes of the whole path (SURVEY.md 8d: 928 B read/element + 8 B per CSR non-zero + 16 B per free DOF) over the longest kernel"},
-            "kernels_ms": {"shell_eval": ev, "scatter": sc, "fp64_algorithmic_tflops_eval": n_local * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12},
+                         "note": "algorithmic bytes of the path (SURVEY.md 8d: 928 B read/element + 8 B per CSR non-zero + 16 B per free DOF); traffic = ncu dram bytes of both launches"},
+            "fp64_roofline": {"bound": "fp64", "achieved": n_local * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": n_local * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12 / fp64_peak, "kernel": "shell::eval_kernel",
+                              "note": "5.0e4 algorithmic flops per Shell_1 element (SURVEY.md 8d) over the evaluation kernel; peak = measured FP64 FMA rate"},
+            "kernels_ms": {"shell_eval": ev, "scatter": sc},
             "cpu_baseline": cpu,
             "setup_seconds": setup_s,
             "nnz_AA": nnz[0], "n_free": nf,
