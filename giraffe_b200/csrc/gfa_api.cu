@@ -67,6 +67,9 @@ const TypeInfo kTypes[3] = {
     { GFA_BEAM_1, 3, 6, 18, 2, BEAM_STATE },
     { GFA_SOLID_1, 8, 8, 24, 8, 0 },
 };
+// 3x3 blocks kept per element in the Ke arena: Shell_1 stores the upper triangle plus the
+// non-symmetric rotation corner (gfa_device.h: shell_block), the others every block
+inline int stored_blocks(int slot) { return slot == 0 ? SHELL_STORED : kTypes[slot].nb * kTypes[slot].nb; }
 inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : t == GFA_BEAM_1 ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
 // local 3-DOF block -> (local node, DOF group 0 = translations / 1 = rotations)
 // in the reference's local DOF order (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444)
@@ -100,13 +103,8 @@ struct HostCsr {
 
 struct gfa_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;        // evaluation stream (the one callers may time / order against)
-    cudaStream_t stream2 = nullptr;       // scatter stream of the chunked pipeline
+    cudaStream_t stream = nullptr;        // the stream every kernel of the path runs on (callers may time / order against it)
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-    std::vector<cudaEvent_t> chunk_ev;    // evaluation of pipeline step i finished
-    cudaEvent_t ev_scatter_done = nullptr;
-    int n_chunks = 1;                      // pipeline steps per element type
-    std::vector<long long> gn_seq_ptr;    // group-node records ready after pipeline step i: [ptr[i], ptr[i+1])
     int rank = 0, world = 1;
 
     int n_nodes = 0, n_el = 0;
@@ -130,9 +128,9 @@ struct gfa_handle {
     DevBuf<double> d_arena;
     DevBuf<GnRec> d_gn;
     DevBuf<RunEnt> d_runs;
-    DevBuf<int> d_ovf;
+    DevBuf<unsigned> d_ovf;
     DevBuf<PInc> d_inc;
-    int n_gn_local = 0, max_row = 0;
+    long long n_runs = 0, n_gn_local = 0;
     DevBuf<long long> d_gseg, d_gsrc, d_gdest;
     long long n_gdest = 0;
     // interface exchange
@@ -162,6 +160,14 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
     const double f = h->gravity_on ? gfac : 0.0;
     a.gx = h->grav[0] * f; a.gy = h->grav[1] * f; a.gz = h->grav[2] * f;
     return a;
+}
+
+// index (in 3x3 blocks) of block (la, b) of a local element in the Ke arena; `tr` = stored transposed
+inline long long arena_block(const gfa_t* h, int slot, int local, int la, int b, bool& tr) {
+    const long long base = h->tb[slot].ke_base / 9 + (long long)local * stored_blocks(slot);
+    tr = false;
+    if (slot == 0) return base + shell_block(la, b, tr);
+    return base + la * kTypes[slot].nb + b;
 }
 
 } // namespace
@@ -316,7 +322,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         for (int s = 0; s < 3 && e == cudaSuccess; s++) {
             TypeBlock& t = h->tb[s];
             t.ke_base = ke; t.pe_base = (int)pe;
-            ke += (long long)t.elems.size() * kTypes[s].ndof * kTypes[s].ndof;
+            ke += (long long)t.elems.size() * stored_blocks(s) * 9;
             pe += (long long)t.elems.size() * kTypes[s].ndof;
             e = t.d_conn.upload(t.conn);
             if (e == cudaSuccess) e = t.d_prop.upload(t.prop);
@@ -330,8 +336,6 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         if (e == cudaSuccess) e = h->tb[0].d_geo.alloc(10 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = h->tb[0].d_shp.alloc(21 * 3 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_scatter_done, cudaEventDisableTiming);
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
         if (e != cudaSuccess) FAIL_FREE(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "device set-up: %s", cudaGetErrorString(e));
     }
@@ -350,10 +354,7 @@ int gfa_destroy(gfa_t* h) {
     if (!h) return GFA_OK;
     cudaSetDevice(h->device);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    for (cudaEvent_t e : h->chunk_ev) cudaEventDestroy(e);
-    if (h->ev_scatter_done) cudaEventDestroy(h->ev_scatter_done);
     if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
     return GFA_OK;
 }
@@ -542,7 +543,6 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
         if (!any_fixed) continue;
         const bool mine = h->el_owner_slot[e] >= 0;
-        const long long base = mine ? h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof : -1;
         for (int i = 0; i < ti.ndof; i++)
             for (int j = 0; j < ti.ndof; j++) {
                 const int g1 = gl[i], g2 = gl[j];
@@ -551,7 +551,12 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 Ent en;
                 en.mat = (g1 > 0) ? GFA_AB : (g2 > 0 ? GFA_BA : GFA_BB);
                 en.row = std::abs(g1) - 1; en.col = std::abs(g2) - 1;
-                en.src = mine ? base + (long long)(((i / 3) * ti.nb + (j / 3)) * 9 + (i % 3) * 3 + (j % 3)) : -1;   // block-major
+                en.src = -1;
+                if (mine) {
+                    bool tr;
+                    const long long blk = arena_block(h, s, h->el_local[e], i / 3, j / 3, tr);
+                    en.src = blk * 9 + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3));
+                }
                 en.rank = h->world > 1 ? el_rank[e] : 0;
                 ents.push_back(en);
             }
@@ -628,36 +633,13 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             else send_small[owner].push_back(gdest[i]);
         }
 
-    // ---- scatter metadata for this rank's group-nodes -----------------------
-    std::vector<int> gn_list;            // group-nodes with at least one local incidence
-    std::vector<PInc> incs;
-    std::vector<RunEnt> runs;
-    std::vector<int> ovf;
-    std::vector<std::vector<int> > run_src;   // scratch: sources per run of the current group-node
-    std::vector<GnRec> gn_recs;
-    std::vector<int> gn_ready;           // pipeline step after which all incident elements are evaluated
-    std::vector<int> gn_first;
-    // chunked pipeline: every element type is evaluated in n_chunks launches; a group-node can be
-    // scattered as soon as the launch holding its last incident element has finished
-    {
-        const char* env = getenv("GFA_CHUNKS");
-        long long biggest = 0;
-        for (int s3 = 0; s3 < 3; s3++) biggest = std::max<long long>(biggest, (long long)h->tb[s3].elems.size());
-        // measured on B200 (profiles/r01_notes.md): overlapping the two kernels is work-conserving
-        // (7.10 ms with 16 steps vs 7.23 ms with 1 on the 1M-shell plate), so the default is 1
-        (void)biggest;
-        int nc = env ? atoi(env) : 1;
-        h->n_chunks = std::max(1, std::min(nc, 64));
-    }
-    auto seq_of = [&](int slot, int local) {
-        const long long n = (long long)h->tb[slot].elems.size();
-        const int c = n > 0 ? (int)(((long long)local * h->n_chunks) / n) : 0;
-        return slot * h->n_chunks + c;
-    };
-    int max_row = 1;
-    // interface ownership: owner = lowest rank with an incidence
+    // ---- interface ownership (owner = lowest rank with an incidence), ascending group-node
+    //      order on every rank so that the send and receive lists pair up ----------------------
     std::vector<std::vector<long long> > send_idx(h->world), recv_idx(h->world);
     h->owned_rows.clear();
+    std::vector<int> rowL(n_gn_all, 0);              // CSR row length of the group's rows
+    std::vector<int> touched_gn;                     // group-nodes with a local incidence
+    std::vector<long long> touched_key;              // position of the first local incident element (locality key)
     for (size_t gn = 0; gn < n_gn_all; gn++) {
         if (gptr[gn] == gptr[gn + 1]) continue;
         int owner = 0; bool touched = h->world == 1; unsigned long long rank_set = 0;
@@ -667,7 +649,9 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
         // AA row geometry shared by the group's rows
         long long L = 0;
-        for (long long q = nptr[gn]; q < nptr[gn + 1]; q++) L += __builtin_popcount(free_mask((size_t)nbr[q]));
+        if (need[gn]) for (long long q = nptr[gn]; q < nptr[gn + 1]; q++) L += __builtin_popcount(free_mask((size_t)nbr[q]));
+        if (L > 0xffff) return fail(GFA_EUNSUPPORTED, "a row of AA has %lld entries; the slot map holds 16-bit row strides", L);
+        rowL[gn] = (int)L;
         if (owner == h->rank || h->world == 1)
             for (int k = 0; k < 3; k++) if (gls[3 * gn + k] > 0) h->owned_rows.push_back(gls[3 * gn + k] - 1);
         if (h->world > 1 && touched && __builtin_popcountll(rank_set) > 1) {
@@ -686,97 +670,90 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             else list_for(send_idx[owner]);
         }
         if (!touched) continue;
-        // local incidences (elements of this rank), ascending element order; every block of an
-        // incident element feeds the run of the group-node that block belongs to
+        long long key = -1;
+        for (int p = gptr[gn]; p < gptr[gn + 1] && key < 0; p++) {
+            const int e = ginc_e[p];
+            if (h->el_owner_slot[e] >= 0) key = (long long)h->tb[h->el_owner_slot[e]].pe_base + (long long)h->el_local[e] * kTypes[h->el_owner_slot[e]].ndof;
+        }
+        if (key < 0) continue;
+        touched_gn.push_back((int)gn);
+        touched_key.push_back(key);
+    }
+    std::sort(h->owned_rows.begin(), h->owned_rows.end());
+    {   // patches are processed in the order of their group-node's first incident element, so that the
+        // blocks read next to each other were written next to each other (node-id order would visit an
+        // element's corner and mid-side nodes millions of group-nodes apart)
+        std::vector<size_t> order(touched_gn.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return touched_key[x] < touched_key[y]; });
+        std::vector<int> sorted(touched_gn.size());
+        for (size_t i = 0; i < order.size(); i++) sorted[i] = touched_gn[order[i]];
+        touched_gn.swap(sorted);
+    }
+
+    // ---- slot map of this rank's group-nodes ----------------------------------
+    // For every (group-node, neighbour) patch: the local element blocks feeding it, element-ascending.
+    std::vector<PInc> incs;
+    std::vector<RunEnt> runs;
+    std::vector<unsigned> ovf;
+    std::vector<std::vector<unsigned> > run_src;   // scratch: sources per patch of the current group-node
+    std::vector<GnRec> gn_recs;
+    for (size_t ti_ = 0; ti_ < touched_gn.size(); ti_++) {
+        const size_t gn = (size_t)touched_gn[ti_];
         const int first_inc = (int)incs.size();
         const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
         const int n_runs = (int)(nb1 - nb0);
         if ((int)run_src.size() < n_runs) run_src.resize(n_runs);
         for (int j = 0; j < n_runs; j++) run_src[j].clear();
-        int ready = 0;
         for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
             const int e = ginc_e[p];
             if (h->el_owner_slot[e] < 0) continue;
-            const int s = h->el_owner_slot[e];
-            ready = std::max(ready, seq_of(s, h->el_local[e]));
+            const int s = h->el_owner_slot[e], local = h->el_local[e];
             const TypeInfo& ti = kTypes[s];
             const int la = ginc_b[p];
             PInc in;
-            in.pe_off = h->tb[s].pe_base + h->el_local[e] * ti.ndof;
+            in.pe_off = h->tb[s].pe_base + local * ti.ndof;
             in.la = la;
             incs.push_back(in);
-            const long long ke = h->tb[s].ke_base + (long long)h->el_local[e] * ti.ndof * ti.ndof + (long long)la * ti.nb * 9;
             for (int b = 0; b < ti.nb; b++) {
                 int a, grp; block_node(s, b, a, grp);
                 const int other = h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
                 const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
-                const long long off = ke + 9 * b;                 // contiguous 3x3 block (la, b) of the block-major element matrix
-                if (off % 9 != 0 || off / 9 >= (1LL << 32)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 32-bit block index of the slot map");
-                run_src[j].push_back((int)(unsigned)(off / 9));
+                bool tr;
+                const long long blk = arena_block(h, s, local, la, b, tr);
+                if (blk >= (1LL << 31)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 31-bit block index of the slot map");
+                run_src[j].push_back((unsigned)blk | (tr ? SRC_T : 0u));
             }
         }
-        if ((int)incs.size() == first_inc) continue;
-        gn_list.push_back((int)gn);
         GnRec rec;
+        int rm = 0, first_row = -1;
         for (int k = 0; k < 3; k++) {
             const int g = gls[3 * gn + k];
             rec.gl[k] = g;
-            rec.row[k] = g > 0 ? AA.rowptr[AA.row_local[g - 1]] : -1;
+            if (g > 0) { rm |= 1 << k; if (first_row < 0) first_row = AA.row_local[g - 1]; }
         }
-        rec.ib = first_inc; rec.ie = (int)incs.size(); rec.pad = 0;
-        rec.rb = (int)runs.size();
-        {
-            int col = 0;
-            for (int j = 0; j < n_runs; j++) {
-                const int fm = free_mask((size_t)nb0[j]);
-                const std::vector<int>& src = run_src[j];
-                if (fm && !src.empty()) {
-                    if (src.size() > 255 || col > 0xffff) return fail(GFA_EUNSUPPORTED, "group-node with more than 255 incident elements or 65535 columns");
-                    RunEnt r;
-                    r.head = (unsigned)col | ((unsigned)fm << 16) | ((unsigned)src.size() << 24);
-                    r.src0 = src[0]; r.src1 = src.size() > 1 ? src[1] : 0;
-                    if (src.size() > 2) { r.src0 = (int)ovf.size(); ovf.insert(ovf.end(), src.begin(), src.end()); }
-                    runs.push_back(r);
-                }
-                col += __builtin_popcount(fm);
-            }
-        }
-        rec.re = (int)runs.size();
+        rec.ib = first_inc; rec.ie = (int)incs.size();
         gn_recs.push_back(rec);
-        gn_ready.push_back(ready);
-        gn_first.push_back(incs[first_inc].pe_off);     // position of the first incident element (locality key)
-        if (free_mask(gn)) max_row = std::max<long long>(max_row, L);
-    }
-    if ((size_t)max_row * 3 * 4 * sizeof(double) > 200 * 1024)
-        return fail(GFA_EUNSUPPORTED, "a row of AA has %d entries; the scatter kernel stages at most %d per row", max_row, (int)(200 * 1024 / (3 * 4 * sizeof(double))));
-    (void)fix_mask;
-    std::sort(h->owned_rows.begin(), h->owned_rows.end());
-
-    {   // order the records by pipeline step (stable: ascending group-node inside a step)
-        const int n_seq = 3 * h->n_chunks;
-        std::vector<long long> cnt((size_t)n_seq + 1, 0);
-        for (int r : gn_ready) cnt[(size_t)r + 1]++;
-        for (int i = 0; i < n_seq; i++) cnt[i + 1] += cnt[i];
-        h->gn_seq_ptr = cnt;
-        // inside a step, group-nodes are processed in the order of their first incident element, so
-        // that the (up to 9) group-nodes reading one element's blocks run close together and the
-        // sectors / blocks they share are served by L2 (node-id order would visit an element's
-        // corner and mid-side nodes millions of group-nodes apart)
-        std::vector<size_t> order(gn_recs.size());
-        for (size_t i = 0; i < order.size(); i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
-            if (gn_ready[x] != gn_ready[y]) return gn_ready[x] < gn_ready[y];
-            return gn_first[x] < gn_first[y];
-        });
-        std::vector<GnRec> sorted(gn_recs.size());
-        for (size_t i = 0; i < order.size(); i++) sorted[i] = gn_recs[order[i]];
-        gn_recs.swap(sorted);
-        while ((int)h->chunk_ev.size() < n_seq) {
-            cudaEvent_t e;
-            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            h->chunk_ev.push_back(e);
+        if (!rm) continue;
+        const long long row0 = AA.rowptr[first_row];
+        int col = 0;
+        for (int j = 0; j < n_runs; j++) {
+            const int fm = free_mask((size_t)nb0[j]);
+            const std::vector<unsigned>& src = run_src[j];
+            const long long dst = row0 + col;
+            col += __builtin_popcount(fm);
+            if (!fm) continue;
+            if (src.empty() && h->world == 1) continue;      // cannot happen: every stored patch has a local source
+            if (src.size() > 255) return fail(GFA_EUNSUPPORTED, "group-node with more than 255 incident elements");
+            RunEnt r;
+            r.dst = (int)dst;
+            r.info = (unsigned)rowL[gn] | ((unsigned)rm << 16) | ((unsigned)fm << 19) | ((unsigned)src.size() << 24);
+            r.src0 = src.size() > 0 ? src[0] : 0u; r.src1 = src.size() > 1 ? src[1] : 0u;
+            if (src.size() > 2) { r.src0 = (unsigned)ovf.size(); ovf.insert(ovf.end(), src.begin(), src.end()); }
+            runs.push_back(r);
         }
     }
+    (void)fix_mask;
 
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
@@ -786,11 +763,11 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     if (ovf.empty()) ovf.push_back(0);
     CUDA_TRY(h->d_ovf.upload(ovf));
     CUDA_TRY(h->d_inc.upload(incs));
+    h->n_runs = (long long)runs.size();
+    h->n_gn_local = (long long)gn_recs.size();
     CUDA_TRY(h->d_gseg.upload(gseg));
     CUDA_TRY(h->d_gsrc.upload(gsrc));
     CUDA_TRY(h->d_gdest.upload(gdest));
-    h->n_gn_local = (int)gn_list.size();
-    h->max_row = max_row;
     h->send_cnt.assign(h->world, 0); h->recv_cnt.assign(h->world, 0);
     {
         std::vector<long long> s_all, r_all;
@@ -837,46 +814,21 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
     CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
                              st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
-    // MountLocal + MountElementLoads on stream `s`, MountGlobal + MountSparse on stream2:
-    // the scatter of the group-nodes completed by evaluation step i overlaps evaluation step i+1
-    // (and reads element blocks that are still in L2).  With n_chunks == 1 this is the plain
-    // evaluate-then-scatter sequence.
+    // MountLocal + MountElementLoads: one evaluation launch per element type
+    for (int slot = 0; slot < 3; slot++) {
+        if (h->tb[slot].elems.empty()) continue;
+        const EvalArgs ea = eval_args(h, slot, st->gravity_factor);
+        if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
+        launches++;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[2], s));
+    // MountGlobal + MountSparse
     ScatterArgs sa;
-    sa.gn = h->d_gn.p; sa.runs = h->d_runs.p; sa.ovf = h->d_ovf.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
+    sa.n_runs = h->n_runs; sa.runs = h->d_runs.p; sa.ovf = h->d_ovf.p;
+    sa.n_gn = h->n_gn_local; sa.gn = h->d_gn.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
     sa.valAA = h->d_arena.p + h->arena_off[GFA_AA];
     sa.PA = h->d_arena.p + h->vec_off[GFA_P_A]; sa.IA = h->d_arena.p + h->vec_off[GFA_I_A]; sa.PB = h->d_arena.p + h->vec_off[GFA_P_B];
-    const bool pipelined = h->n_chunks > 1;
-    cudaStream_t s2 = pipelined ? h->stream2 : s;
-    for (int slot = 0; slot < 3; slot++) {
-        const long long n = (long long)h->tb[slot].elems.size();
-        for (int c = 0; c < h->n_chunks; c++) {
-            const int seq = slot * h->n_chunks + c;
-            // elements whose seq_of() is c: local in [ceil(c n / C), ceil((c+1) n / C))
-            const long long lo = (c * n + h->n_chunks - 1) / h->n_chunks, hi = ((c + 1) * n + h->n_chunks - 1) / h->n_chunks;
-            if (hi > lo) {
-                EvalArgs ea = eval_args(h, slot, st->gravity_factor);
-                ea.e_begin = (int)lo; ea.e_end = (int)hi;
-                if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
-                launches++;
-            }
-            sa.gn_begin = h->gn_seq_ptr[seq]; sa.gn_end = h->gn_seq_ptr[seq + 1];
-            if (pipelined && sa.gn_end > sa.gn_begin) {
-                CUDA_TRY(cudaEventRecord(h->chunk_ev[seq], s));
-                CUDA_TRY(cudaStreamWaitEvent(s2, h->chunk_ev[seq], 0));
-                launch_scatter(sa, s2); launches++;
-            }
-        }
-    }
-    if (!pipelined) {
-        CUDA_TRY(cudaEventRecord(h->ev[2], s));    // evaluation done; one scatter over every group-node
-        sa.gn_begin = h->gn_seq_ptr.front(); sa.gn_end = h->gn_seq_ptr.back();
-        if (sa.gn_end > sa.gn_begin) { launch_scatter(sa, s); launches++; }
-    }
-    if (pipelined) {
-        CUDA_TRY(cudaEventRecord(h->ev[2], s));    // end of the evaluation launches
-        CUDA_TRY(cudaEventRecord(h->ev_scatter_done, s2));
-        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_scatter_done, 0));
-    }
+    launches += launch_scatter(sa, s);
     if (h->n_gdest > 0) {
         GatherArgs g;
         g.n_dest = h->n_gdest; g.seg = h->d_gseg.p; g.src = h->d_gsrc.p; g.dest = h->d_gdest.p;
@@ -989,11 +941,16 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     CUDA_TRY(cudaSetDevice(h->device));
     const int n = kTypes[s].ndof;
     if (K) {
-        std::vector<double> blk((size_t)n * n);
-        CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)h->el_local[e] * n * n, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
-        const int nb = n / 3;     // device layout is block-major; hand back plain row-major
+        const int nb = n / 3, nsb = stored_blocks(s), local = h->el_local[e];
+        std::vector<double> blk((size_t)nsb * 9);
+        CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)local * nsb * 9, sizeof(double) * nsb * 9, cudaMemcpyDeviceToHost));
+        // device layout is block-major; hand back plain row-major
         for (int i = 0; i < n; i++)
-            for (int j = 0; j < n; j++) K[i * n + j] = blk[((i / 3) * nb + (j / 3)) * 9 + (i % 3) * 3 + (j % 3)];
+            for (int j = 0; j < n; j++) {
+                bool tr = false;
+                const int k = s == 0 ? shell_block(i / 3, j / 3, tr) : (i / 3) * nb + (j / 3);
+                K[i * n + j] = blk[(size_t)k * 9 + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3))];
+            }
     }
     if (P) CUDA_TRY(cudaMemcpy(P, h->d_Pe.p + h->tb[s].pe_base + (size_t)h->el_local[e] * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return n;

@@ -10,7 +10,7 @@ namespace gfa {
 // structure-of-arrays: state[k * n_gp + gp], gp = element * NGP + point.
 struct EvalArgs {
     int n_el;                // elements of this type on this rank (array extents)
-    int e_begin, e_end;      // range evaluated by this launch (chunked pipeline)
+    int e_begin, e_end;      // range evaluated by this launch
     const int* conn;
     const int* prop;         // per element index into props
     const double* props;     // per-type property rows (see *_PROP_STRIDE)
@@ -21,8 +21,9 @@ struct EvalArgs {
     const double* geo;       // Shell_1 PreCalc: R(9), area per element (SoA)
     const double* shp;       // Shell_1 PreCalc: 21 shape values per Gauss point (SoA)
     double* state;           // committed Gauss-point state (read by eval, written by commit)
-    double* Ke;              // [n_el * ndof * ndof] element blocks, stored block-major: the (ndof/3)^2 3x3 blocks
-                             // (row block, column block) are contiguous, each row-major; reference local DOF order
+    double* Ke;              // element arena of contiguous, row-major 3x3 blocks (reference local DOF order).
+                             // Beam_1 / Solid_1: all (ndof/3)^2 blocks, [row block][column block].
+                             // Shell_1: SHELL_STORED blocks per element (see shell_block()).
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
     double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
 };
@@ -34,6 +35,21 @@ constexpr int SOLID_PROP_STRIDE = 3;   // lambda, mu, rho
 constexpr int SHELL_STATE = 21;        // Q_i(9) z_x1_i(3) z_x2_i(3) kappa_r1_i(3) kappa_r2_i(3)
 constexpr int BEAM_STATE = 15;         // Q_i(9) dz_i(3) kappa_i_ref(3)
 
+// Shell_1 stored blocks over its 9 group-nodes (0-5: u of nodes 1-6, 6-8: alpha of nodes 4-6):
+// the 45 blocks (a <= b) of the upper triangle, then the 3 strictly-lower rotation-rotation
+// blocks (the only part of the tangent that is not symmetric, Shell_1.cpp:1277-1302).
+// Block (a > b) outside the rotation corner is the transpose of stored block (b, a).
+constexpr int SHELL_STORED = 48;
+__host__ __device__ constexpr int shell_upper(int a, int b) { return a * 9 - (a * (a - 1)) / 2 + (b - a); }
+// returns the stored index of block (a,b); `transposed` tells whether the stored block is (b,a)
+__host__ __device__ inline int shell_block(int a, int b, bool& transposed) {
+    transposed = false;
+    if (a <= b) return shell_upper(a, b);
+    if (b >= 6) return 45 + (a == 7 ? 0 : (b == 6 ? 1 : 2));     // (7,6) (8,6) (8,7)
+    transposed = true;
+    return shell_upper(b, a);
+}
+
 // ---- scatter ------------------------------------------------------------
 // "Group-node" = one 3-DOF group of a node (translations or rotations); every
 // in-scope element block is 3x3-structured over group-nodes in the
@@ -43,30 +59,30 @@ constexpr int BEAM_STATE = 15;         // Q_i(9) dz_i(3) kappa_i_ref(3)
 // therefore one entry per (group-node, neighbour) pair listing the element
 // blocks that contribute to that 3x3 patch of the CSR, in ascending element
 // order (the order the reference pushes and Eigen sums, Solution.cpp:327-328).
-struct RunEnt {
-    unsigned head;      // column offset of the run inside the row (bits 0-15) | free mask of the
-                        // neighbour's 3 DOFs (bits 16-18) | number of contributing blocks (bits 24-31)
-    int src0, src1;     // count <= 2: the sources themselves; count > 2: src0 = start in the overflow list
+struct RunEnt {         // 16 bytes, one per CSR patch that is summed by the scatter kernel
+    int dst;            // valAA offset of the patch's first entry (first free row, first free column)
+    unsigned info;      // row stride (bits 0-15) | free mask of the row group (16-18) | free mask of the
+                        // column group (19-21) | number of contributing blocks (24-31)
+    unsigned src0, src1;// count <= 2: the sources themselves; count > 2: src0 = start in the overflow list
 };
-// source encoding: (offset of the contiguous 3x3 block in the Ke arena) / 9
+// source encoding: index of the contiguous 3x3 block in the Ke arena (offset / 9); bit 31 = read transposed
+constexpr unsigned SRC_T = 0x80000000u;
 struct PInc {           // (element, local block) incidences of a group-node, for the residual vectors
     int pe_off;         // offset of the element's P in the Pe arena
     int la;             // local block index
 };
-// one record per group-node this rank's elements touch
+// one record per group-node this rank's elements touch (residual vectors)
 struct GnRec {
-    long long row[3];   // start of each of the group's rows in valAA (-1: DOF not free)
     int gl[3];          // global DOF ids (Node::GLs) of the group's 3 DOFs
-    int rb, re;         // runs [rb, re)
     int ib, ie;         // incidences [ib, ie), element-ascending
-    int pad;
 };
 
 struct ScatterArgs {
-    long long gn_begin, gn_end;  // range of group-node records handled by this launch
-    const GnRec* gn;
+    long long n_runs;
     const RunEnt* runs;
-    const int* ovf;              // overflow source lists (patches fed by more than two blocks)
+    const unsigned* ovf;         // overflow source lists (patches fed by more than two blocks)
+    long long n_gn;
+    const GnRec* gn;
     const PInc* inc;
     const double* Ke;            // arena
     const double* Pe;            // arena
@@ -78,7 +94,7 @@ struct ScatterArgs {
 struct GatherArgs {
     long long n_dest;
     const long long* seg;        // [n_dest+1]
-    const long long* src;        // Ke-arena offsets, element-ascending inside a segment
+    const long long* src;        // Ke-arena offsets (entry granularity), element-ascending inside a segment
     const long long* dest;       // index into `vals`
     const double* Ke;
     double* vals;                // AB | BA | BB value arrays, one arena
@@ -91,7 +107,7 @@ void launch_shell_precalc(const EvalArgs& a, double* geo, double* shp, void* str
 void launch_shell_commit(const EvalArgs& a, void* stream);
 void launch_beam_commit(const EvalArgs& a, void* stream);
 void launch_node_commit(int n_nodes, double* copy, double* disp, void* stream);
-void launch_scatter(const ScatterArgs& a, void* stream);
+int launch_scatter(const ScatterArgs& a, void* stream);      // returns the number of kernels launched
 void launch_gather(const GatherArgs& a, void* stream);
 void launch_add_slots(double* vals, const long long* slots, const double* add, long long n, void* stream);
 void launch_pack(const double* vals, const long long* idx, double* buf, long long n, void* stream);

@@ -33,6 +33,7 @@ constexpr int NGP = 3;                  // EPW (elements per warp batch) is a te
 constexpr int C_OFF = 0;                // 15 upper 3x3 blocks of C' (x weight)
 constexpr int F_OFF = 135;              // f (15)
 constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
+constexpr int X_OFF = 171;              // rho*thickness, area (self-weight)
 constexpr int REC = 175;                // odd (16 distinct bank pairs for per-lane stores) and 3*REC*2 mod 32 = 26:
                                         // the <=3 elements x 3 components a warp reads in phase B fall into distinct banks
 constexpr int smem_bytes(int epw) { return epw * NGP * REC * 8; }
@@ -378,6 +379,8 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
     const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
     const double w = fr.area / 3.0;                           // alpha1 (:2364)
+    rec[X_OFF] = __ldg(pr + 4) * thick;
+    rec[X_OFF + 1] = fr.area;
 
     double gg, Xi[9], Qt[9], z1[3], z2[3];
     Strains st;
@@ -517,11 +520,81 @@ GFA_DI double cowper_factor(int a, double area) {
     return s;
 }
 
-// Phase B work item: one column of K (and one entry of P) of one element.
-// U: translational column (node b in 0..5, component jj) -> gradient groups 0 (u,1) and 2 (u,2)
-// A: rotational column  (mid node b in 0..2)             -> groups 1 (a,1), 3 (a,2), 4 (a)
-template <bool ROT>
-__device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, int b, int jj, double rho_t) {
+// ---- Phase B: K = sum_g dN^T C' dN, upper blocks only ---------------------
+// A column of K is stored 3 values at a time (the rows of one group-node) into the
+// element's stored block k of the arena.
+GFA_DI void put_col(const EvalArgs& A, size_t blk0, int k, int jj, double v0, double v1, double v2) {
+    double* p = A.Ke + (blk0 + k) * 9 + jj;
+    p[0] = v0; p[3] = v1; p[6] = v2;
+}
+
+// self-weight entry of P for translational column (b, jj): applied twice, as the
+// reference does (Shell_1.cpp:1340-1375)
+GFA_DI double self_weight(const EvalArgs& A, const double* rec0, int b, int jj) {
+    if (A.gx == 0.0 && A.gy == 0.0 && A.gz == 0.0) return 0.0;
+    const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
+    const double one = cowper_factor(b, rec0[X_OFF + 1]) * (rec0[X_OFF] * gk);
+    return one + one;
+}
+
+// Translational columns B1 = KK and B2 = 5 - KK, component jj: rows u_0..u_B1 of the first and
+// u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7 blocks for every KK.
+template <int KK>
+__device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int jj) {
+    constexpr int B1 = KK, B2 = 5 - KK, N1 = B1 + 1, N2 = B2 + 1;
+    const size_t blk0 = (size_t)e * SHELL_STORED;
+    double K1[N1][3], K2[N2][3];
+#pragma unroll
+    for (int a = 0; a < N1; a++) { K1[a][0] = 0.0; K1[a][1] = 0.0; K1[a][2] = 0.0; }
+#pragma unroll
+    for (int a = 0; a < N2; a++) { K2[a][0] = 0.0; K2[a][1] = 0.0; K2[a][2] = 0.0; }
+    double F1 = 0.0, F2 = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++) {
+        const double* rec = rec0 + g * REC;
+        const double* recJ = rec + jj;
+        const double* rec3J = rec + 3 * jj;
+        const double* S = rec + S_OFF;
+        double c00[3], c02[3], c20[3], c22[3];
+        c00[0] = c_at<0, 0, 0>(recJ, rec3J); c00[1] = c_at<0, 1, 0>(recJ, rec3J); c00[2] = c_at<0, 2, 0>(recJ, rec3J);
+        c02[0] = c_at<0, 0, 2>(recJ, rec3J); c02[1] = c_at<0, 1, 2>(recJ, rec3J); c02[2] = c_at<0, 2, 2>(recJ, rec3J);
+        c20[0] = c_at<2, 0, 0>(recJ, rec3J); c20[1] = c_at<2, 1, 0>(recJ, rec3J); c20[2] = c_at<2, 2, 0>(recJ, rec3J);
+        c22[0] = c_at<2, 0, 2>(recJ, rec3J); c22[1] = c_at<2, 1, 2>(recJ, rec3J); c22[2] = c_at<2, 2, 2>(recJ, rec3J);
+        const double p1 = S[B1], q1 = S[6 + B1], p2 = S[B2], q2 = S[6 + B2];
+        double m10[3], m12[3], m20[3], m22[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            m10[i] = fma(q1, c02[i], p1 * c00[i]); m12[i] = fma(q1, c22[i], p1 * c20[i]);
+            m20[i] = fma(q2, c02[i], p2 * c00[i]); m22[i] = fma(q2, c22[i], p2 * c20[i]);
+        }
+        F1 = fma(q1, recJ[F_OFF + 6], fma(p1, recJ[F_OFF + 0], F1));
+        F2 = fma(q2, recJ[F_OFF + 6], fma(p2, recJ[F_OFF + 0], F2));
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const double n1 = S[a], n2 = S[6 + a];
+            if (a < N1) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) K1[a][i] = fma(n2, m12[i], fma(n1, m10[i], K1[a][i]));
+            }
+            if (a < N2) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) K2[a][i] = fma(n2, m22[i], fma(n1, m20[i], K2[a][i]));
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < N1; a++) put_col(A, blk0, shell_upper(a, B1), jj, K1[a][0], K1[a][1], K1[a][2]);
+#pragma unroll
+    for (int a = 0; a < N2; a++) put_col(A, blk0, shell_upper(a, B2), jj, K2[a][0], K2[a][1], K2[a][2]);
+    A.Pe[(size_t)e * 27 + 3 * B1 + jj] = F1 - self_weight(A, rec0, B1, jj);
+    A.Pe[(size_t)e * 27 + 3 * B2 + jj] = F2 - self_weight(A, rec0, B2, jj);
+}
+
+// Rotational column (mid-side node b in 0..2, component jj): all 27 rows -- the six u rows are the
+// upper u-alpha blocks (their transposes are the alpha-u blocks), the three alpha rows are the
+// non-symmetric alpha-alpha blocks, each stored on its own.
+__device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, int jj) {
+    const size_t blk0 = (size_t)e * SHELL_STORED;
     double K[27];
 #pragma unroll
     for (int i = 0; i < 27; i++) K[i] = 0.0;
@@ -532,56 +605,40 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         const double* recJ = rec + jj;
         const double* rec3J = rec + 3 * jj;
         const double* S = rec + S_OFF;
-#define GFA_S(k_) S[k_]
         double m[5][3];
-        if (!ROT) {
-            const double s0 = GFA_S(b), s2 = GFA_S(6 + b);
-#define GFA_ROW(P_, I_) m[P_][I_] = fma(s2, c_at<P_, I_, 2>(recJ, rec3J), s0 * c_at<P_, I_, 0>(recJ, rec3J));
-            GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
-            GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
-            GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
-#undef GFA_ROW
-            F = fma(s2, recJ[F_OFF + 6], fma(s0, recJ[F_OFF + 0], F));
-        } else {
-            const double s1 = GFA_S(12 + b), s3 = GFA_S(15 + b), s4 = GFA_S(18 + b);
+        const double s1 = S[12 + b], s3 = S[15 + b], s4 = S[18 + b];
 #define GFA_ROW(P_, I_) m[P_][I_] = fma(s4, c_at<P_, I_, 4>(recJ, rec3J), fma(s3, c_at<P_, I_, 3>(recJ, rec3J), s1 * c_at<P_, I_, 1>(recJ, rec3J)));
-            GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
-            GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
-            GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
+        GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
+        GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
+        GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
 #undef GFA_ROW
-            F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
-        }
+        F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-            const double n1 = GFA_S(a), n2 = GFA_S(6 + a);
+            const double n1 = S[a], n2 = S[6 + a];
 #pragma unroll
             for (int ii = 0; ii < 3; ii++) K[3 * a + ii] = fma(n2, m[2][ii], fma(n1, m[0][ii], K[3 * a + ii]));
         }
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const double a1 = GFA_S(12 + a), a2 = GFA_S(15 + a), a0 = GFA_S(18 + a);
+            const double a1 = S[12 + a], a2 = S[15 + a], a0 = S[18 + a];
 #pragma unroll
             for (int ii = 0; ii < 3; ii++) K[18 + 3 * a + ii] = fma(a0, m[4][ii], fma(a2, m[3][ii], fma(a1, m[1][ii], K[18 + 3 * a + ii])));
         }
-#undef GFA_S
     }
-    const int col = ROT ? 18 + 3 * b + jj : 3 * b + jj;
-    // element block stored as 9x9 contiguous 3x3 blocks (block-major): block (a,cb), entry (ii,jj)
-    double* Ke = A.Ke + (size_t)e * 729 + (col / 3) * 9 + (col % 3);
 #pragma unroll
-    for (int r = 0; r < 27; r++) Ke[(r / 3) * 81 + (r % 3) * 3] = K[r];
-    // P = Fint - Fext; self-weight applied twice as in the reference (:1340-1375)
-    double fe = 0.0;
-    if (!ROT && (A.gx != 0.0 || A.gy != 0.0 || A.gz != 0.0)) {
-        const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
-        const double one = cowper_factor(b, __ldg(A.geo + 9 * (size_t)A.n_el + e)) * (rho_t * gk);
-        fe = one + one;
+    for (int a = 0; a < 6; a++) put_col(A, blk0, shell_upper(a, 6) + b, jj, K[3 * a], K[3 * a + 1], K[3 * a + 2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        bool t;
+        put_col(A, blk0, shell_block(6 + a, 6 + b, t), jj, K[18 + 3 * a], K[19 + 3 * a], K[20 + 3 * a]);
     }
-    A.Pe[(size_t)e * 27 + col] = F - fe;
+    A.Pe[(size_t)e * 27 + 18 + 3 * b + jj] = F;
 }
 
 template <int EPW>
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
+    static_assert(EPW * 3 <= 32, "one lane per (element, component) item");
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
@@ -589,14 +646,16 @@ __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
         const int ne = min(EPW, A.e_end - e0);
         if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
         __syncwarp();
-        for (int it = lane; it < ne * 18; it += 32) {
-            const int el = it / 18, c = it % 18;
-            const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e0 + el);
-            congruence_item<false>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3, __ldg(pr + 4) * __ldg(pr + 2));
+        if (lane < ne * 3) {
+            const int el = lane / 3, jj = lane % 3;
+            const double* rec0 = smem + el * NGP * REC;
+            uu_item<0>(A, e0 + el, rec0, jj);
+            uu_item<1>(A, e0 + el, rec0, jj);
+            uu_item<2>(A, e0 + el, rec0, jj);
         }
         for (int it = lane; it < ne * 9; it += 32) {
             const int el = it / 9, c = it % 9;
-            congruence_item<true>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3, 0.0);
+            rot_item(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
         }
         __syncwarp();
     }
@@ -1110,75 +1169,85 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 
 // =========================================================================
 // Scatter: MountGlobal + MountSparse for the free x free matrix and the
-// residual vectors.  One warp per group-node.
+// residual vectors.
 // =========================================================================
-constexpr int SCATTER_WARPS = 4;
+constexpr int SCATTER_THREADS = 256;
 
-// One warp per group-node, one LANE per run (= per neighbouring group-node): the lane
-// gathers the 3x3 patch of every contributing element block straight from the Ke
-// arena (up to 9 independent 8-byte loads per block, element-ascending adds in
-// registers) and writes its <= 3 consecutive columns of the group's <= 3 rows.
-// Neighbouring lanes write neighbouring columns, so each CSR row is written once,
-// coalesced.  No shared memory, no warp synchronisation, ~5x fewer instructions than
-// the row-staging variants measured before it (profiles/r01_notes.md).
-__global__ void __launch_bounds__(32 * SCATTER_WARPS) scatter_kernel(ScatterArgs A) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long gn = A.gn_begin + (long long)blockIdx.x * SCATTER_WARPS + warp;
-    if (gn >= A.gn_end) return;
-    const GnRec* gp = A.gn + gn;
-    const long long r0 = gp->row[0], r1 = gp->row[1], r2 = gp->row[2];
-    const int rb = gp->rb, re = gp->re;
-    if (r0 >= 0 || r1 >= 0 || r2 >= 0) {
-        for (int j = rb + lane; j < re; j += 32) {
-            const RunEnt r = A.runs[j];
-            const int col = r.head & 0xffff, fm = (r.head >> 16) & 7, cnt = r.head >> 24;
-            double a[9];
-            {
-                // first two contributing blocks: all 18 loads are issued before the first add
-                const double* p0 = A.Ke + 9 * (size_t)(unsigned)(cnt <= 2 ? r.src0 : __ldg(A.ovf + r.src0));
-                const double* p1 = A.Ke + 9 * (size_t)(unsigned)(cnt <= 2 ? r.src1 : __ldg(A.ovf + r.src0 + 1));
-                double x[9], y[9];
+// load one 3x3 source block, transposing when the stored block is the twin
+GFA_DI void load_block(const double* Ke, unsigned src, double (&x)[9]) {
+    const double* p = Ke + 9 * (size_t)(src & ~SRC_T);
+    double t[9];
 #pragma unroll
-                for (int i = 0; i < 9; i++) x[i] = p0[i];
-                if (cnt > 1) {
+    for (int i = 0; i < 9; i++) t[i] = p[i];
+    const bool tr = (src & SRC_T) != 0;
+    x[0] = t[0]; x[4] = t[4]; x[8] = t[8];
+    x[1] = tr ? t[3] : t[1]; x[3] = tr ? t[1] : t[3];
+    x[2] = tr ? t[6] : t[2]; x[6] = tr ? t[2] : t[6];
+    x[5] = tr ? t[7] : t[5]; x[7] = tr ? t[5] : t[7];
+}
+
+// One THREAD per CSR patch (= one (group-node, neighbour) pair): it gathers the contributing 3x3 blocks straight from the arena --
+// all loads of the first two issued before the first add, element-ascending adds in registers
+// (the order the reference pushes and Eigen sums, Solution.cpp:327-328) -- and writes the patch's
+// <= 3 x 3 values into the CSR rows.  Consecutive threads own consecutive patches of the same rows,
+// so every row is written once, in whole sectors (partially written sectors cost a DRAM
+// read-modify-write each, profiles/r01_notes.md).  No shared memory, no atomics, no synchronisation.
+__global__ void __launch_bounds__(SCATTER_THREADS) scatter_kernel(ScatterArgs A) {
+    const long long j = (long long)blockIdx.x * SCATTER_THREADS + threadIdx.x;
+    if (j >= A.n_runs) return;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(A.runs) + j);
+    const unsigned info = q.y;
+    const int L = info & 0xffff, rm = (info >> 16) & 7, fm = (info >> 19) & 7, cnt = info >> 24;
+    double a[9];
+    {
+        unsigned s0 = q.z, s1 = q.w;
+        if (cnt > 2) { s0 = __ldg(A.ovf + q.z); s1 = __ldg(A.ovf + q.z + 1); }
+        double x[9], y[9];
+        load_block(A.Ke, s0, x);
+        if (cnt > 1) load_block(A.Ke, s1, y);
+        else {
 #pragma unroll
-                    for (int i = 0; i < 9; i++) y[i] = p1[i];
-                } else {
+            for (int i = 0; i < 9; i++) y[i] = 0.0;
+        }
 #pragma unroll
-                    for (int i = 0; i < 9; i++) y[i] = 0.0;
-                }
+        for (int i = 0; i < 9; i++) a[i] = cnt > 0 ? x[i] + y[i] : 0.0;     // count 0: a patch fed by other ranks only
+    }
+    for (int k = 2; k < cnt; k++) {
+        double x[9];
+        load_block(A.Ke, __ldg(A.ovf + q.z + k), x);
 #pragma unroll
-                for (int i = 0; i < 9; i++) a[i] = (0.0 + x[i]) + y[i];
-            }
-            for (int k = 2; k < cnt; k++) {
-                const double* p = A.Ke + 9 * (size_t)(unsigned)__ldg(A.ovf + r.src0 + k);
-                double x[9];
+        for (int i = 0; i < 9; i++) a[i] += x[i];
+    }
+    // rows = the group's free DOFs (consecutive CSR rows of equal length), columns = the neighbour's
+    double* o = A.valAA + (size_t)(int)q.x;
+    const int c1 = fm & 1, c2 = c1 + ((fm >> 1) & 1);
 #pragma unroll
-                for (int i = 0; i < 9; i++) x[i] = p[i];
-#pragma unroll
-                for (int i = 0; i < 9; i++) a[i] += x[i];
-            }
-            const double a00 = a[0], a01 = a[1], a02 = a[2], a10 = a[3], a11 = a[4], a12 = a[5], a20 = a[6], a21 = a[7], a22 = a[8];
-            // columns of the run = the neighbour's free DOFs, in DOF order
-            const int c1 = col + (fm & 1), c2 = c1 + ((fm >> 1) & 1);
-            if (r0 >= 0) { double* o = A.valAA + r0; if (fm & 1) o[col] = a00; if (fm & 2) o[c1] = a01; if (fm & 4) o[c2] = a02; }
-            if (r1 >= 0) { double* o = A.valAA + r1; if (fm & 1) o[col] = a10; if (fm & 2) o[c1] = a11; if (fm & 4) o[c2] = a12; }
-            if (r2 >= 0) { double* o = A.valAA + r2; if (fm & 1) o[col] = a20; if (fm & 2) o[c1] = a21; if (fm & 4) o[c2] = a22; }
+    for (int ii = 0; ii < 3; ii++) {
+        if (rm & (1 << ii)) {
+            if (fm & 1) o[0] = a[3 * ii];
+            if (fm & 2) o[c1] = a[3 * ii + 1];
+            if (fm & 4) o[c2] = a[3 * ii + 2];
+            o += L;
         }
     }
-    // residual: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums
-    if (lane < 3) {
-        const int gl = gp->gl[lane];
-        if (gl != 0) {
-            double s = 0.0;
-            for (int k = gp->ib; k < gp->ie; k++) {
-                const PInc in = A.inc[k];
-                s += A.Pe[in.pe_off + 3 * in.la + lane];
-            }
-            if (gl > 0) { A.PA[gl - 1] = s; A.IA[gl - 1] = s; }
-            else A.PB[-gl - 1] = s;
-        }
+}
+
+// residual vectors: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums;
+// one thread per (group-node, component)
+__global__ void vector_kernel(ScatterArgs A) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * A.n_gn) return;
+    const GnRec* gp = A.gn + t / 3;
+    const int k = (int)(t % 3);
+    const int gl = gp->gl[k];
+    if (gl == 0) return;
+    double s = 0.0;
+    for (int i = gp->ib; i < gp->ie; i++) {
+        const PInc in = A.inc[i];
+        s += A.Pe[in.pe_off + 3 * in.la + k];
     }
+    if (gl > 0) { A.PA[gl - 1] = s; A.IA[gl - 1] = s; }
+    else A.PB[-gl - 1] = s;
 }
 
 // AB / BA / BB entries: explicit element-ascending gather lists, one thread per slot.
@@ -1285,11 +1354,17 @@ void launch_node_commit(int n_nodes, double* copy, double* disp, void* s) {
     if (n_nodes <= 0) return;
     node_commit_kernel<<<(n_nodes + 255) / 256, 256, 0, (cudaStream_t)s>>>(n_nodes, copy, disp);
 }
-void launch_scatter(const ScatterArgs& a, void* s) {
-    const long long count = a.gn_end - a.gn_begin;
-    if (count <= 0) return;
-    const long long blocks = (count + SCATTER_WARPS - 1) / SCATTER_WARPS;
-    scatter_kernel<<<(unsigned)blocks, 32 * SCATTER_WARPS, 0, (cudaStream_t)s>>>(a);
+int launch_scatter(const ScatterArgs& a, void* s) {
+    int launches = 0;
+    if (a.n_runs > 0) {
+        scatter_kernel<<<(unsigned)((a.n_runs + SCATTER_THREADS - 1) / SCATTER_THREADS), SCATTER_THREADS, 0, (cudaStream_t)s>>>(a);
+        launches++;
+    }
+    if (a.n_gn > 0) {
+        vector_kernel<<<(unsigned)((3 * a.n_gn + 255) / 256), 256, 0, (cudaStream_t)s>>>(a);
+        launches++;
+    }
+    return launches;
 }
 void launch_gather(const GatherArgs& a, void* s) {
     if (a.n_dest <= 0) return;
