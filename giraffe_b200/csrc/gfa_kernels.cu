@@ -1173,63 +1173,54 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 // =========================================================================
 constexpr int SCATTER_THREADS = 256;
 
-// load one 3x3 source block, transposing when the stored block is the twin
-GFA_DI void load_block(const double* Ke, unsigned src, double (&x)[9]) {
-    const double* p = Ke + 9 * (size_t)(src & ~SRC_T);
-    double t[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) t[i] = p[i];
+// row ii of a 3x3 source block (column ii when the stored block is the transposed twin)
+GFA_DI void load_row(const double* Ke, unsigned src, int ii, double (&x)[3]) {
     const bool tr = (src & SRC_T) != 0;
-    x[0] = t[0]; x[4] = t[4]; x[8] = t[8];
-    x[1] = tr ? t[3] : t[1]; x[3] = tr ? t[1] : t[3];
-    x[2] = tr ? t[6] : t[2]; x[6] = tr ? t[2] : t[6];
-    x[5] = tr ? t[7] : t[5]; x[7] = tr ? t[5] : t[7];
+    const double* p = Ke + 9 * (size_t)(src & ~SRC_T) + (tr ? ii : 3 * ii);
+    const int st = tr ? 3 : 1;
+    x[0] = p[0]; x[1] = p[st]; x[2] = p[2 * st];
 }
 
-// One THREAD per CSR patch (= one (group-node, neighbour) pair): it gathers the contributing 3x3 blocks straight from the arena --
-// all loads of the first two issued before the first add, element-ascending adds in registers
-// (the order the reference pushes and Eigen sums, Solution.cpp:327-328) -- and writes the patch's
-// <= 3 x 3 values into the CSR rows.  Consecutive threads own consecutive patches of the same rows,
-// so every row is written once, in whole sectors (partially written sectors cost a DRAM
-// read-modify-write each, profiles/r01_notes.md).  No shared memory, no atomics, no synchronisation.
+// One THREAD per CSR patch row: thread t owns row ii = t % 3 of patch t / 3 (= one (group-node,
+// neighbour) pair).  It gathers that row of the contributing 3x3 blocks straight from the arena --
+// all loads of the first two issued before the first add, element-ascending adds in registers (the
+// order the reference pushes and Eigen sums, Solution.cpp:327-328) -- and writes <= 3 consecutive
+// values of one CSR row.  The three threads of a patch read one contiguous 72-byte block together and
+// consecutive patches of a group-node are consecutive in its rows, so loads arrive at the L1 a few
+// lines per request (one thread per whole patch: 32 lines per request, L1 wavefront pipe 75 % busy,
+// profiles/r01_notes.md) and every CSR row is written once, in whole sectors.
+// No shared memory, no atomics, no synchronisation.
 __global__ void __launch_bounds__(SCATTER_THREADS) scatter_kernel(ScatterArgs A) {
-    const long long j = (long long)blockIdx.x * SCATTER_THREADS + threadIdx.x;
+    const long long t = (long long)blockIdx.x * SCATTER_THREADS + threadIdx.x;
+    const long long j = t / 3;
     if (j >= A.n_runs) return;
+    const int ii = (int)(t - 3 * j);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(A.runs) + j);
     const unsigned info = q.y;
     const int L = info & 0xffff, rm = (info >> 16) & 7, fm = (info >> 19) & 7, cnt = info >> 24;
-    double a[9];
+    if (!((rm >> ii) & 1)) return;
+    double a[3];
     {
         unsigned s0 = q.z, s1 = q.w;
         if (cnt > 2) { s0 = __ldg(A.ovf + q.z); s1 = __ldg(A.ovf + q.z + 1); }
-        double x[9], y[9];
-        load_block(A.Ke, s0, x);
-        if (cnt > 1) load_block(A.Ke, s1, y);
-        else {
+        double x[3] = { 0.0, 0.0, 0.0 }, y[3] = { 0.0, 0.0, 0.0 };
+        if (cnt > 0) load_row(A.Ke, s0, ii, x);          // count 0: a patch fed by other ranks only
+        if (cnt > 1) load_row(A.Ke, s1, ii, y);
 #pragma unroll
-            for (int i = 0; i < 9; i++) y[i] = 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 9; i++) a[i] = cnt > 0 ? x[i] + y[i] : 0.0;     // count 0: a patch fed by other ranks only
+        for (int i = 0; i < 3; i++) a[i] = x[i] + y[i];
     }
     for (int k = 2; k < cnt; k++) {
-        double x[9];
-        load_block(A.Ke, __ldg(A.ovf + q.z + k), x);
+        double x[3];
+        load_row(A.Ke, __ldg(A.ovf + q.z + k), ii, x);
 #pragma unroll
-        for (int i = 0; i < 9; i++) a[i] += x[i];
+        for (int i = 0; i < 3; i++) a[i] += x[i];
     }
     // rows = the group's free DOFs (consecutive CSR rows of equal length), columns = the neighbour's
-    double* o = A.valAA + (size_t)(int)q.x;
+    double* o = A.valAA + (size_t)(int)q.x + (size_t)__popc(rm & ((1 << ii) - 1)) * L;
     const int c1 = fm & 1, c2 = c1 + ((fm >> 1) & 1);
-#pragma unroll
-    for (int ii = 0; ii < 3; ii++) {
-        if (rm & (1 << ii)) {
-            if (fm & 1) o[0] = a[3 * ii];
-            if (fm & 2) o[c1] = a[3 * ii + 1];
-            if (fm & 4) o[c2] = a[3 * ii + 2];
-            o += L;
-        }
-    }
+    if (fm & 1) o[0] = a[0];
+    if (fm & 2) o[c1] = a[1];
+    if (fm & 4) o[c2] = a[2];
 }
 
 // residual vectors: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums;
@@ -1357,7 +1348,7 @@ void launch_node_commit(int n_nodes, double* copy, double* disp, void* s) {
 int launch_scatter(const ScatterArgs& a, void* s) {
     int launches = 0;
     if (a.n_runs > 0) {
-        scatter_kernel<<<(unsigned)((a.n_runs + SCATTER_THREADS - 1) / SCATTER_THREADS), SCATTER_THREADS, 0, (cudaStream_t)s>>>(a);
+        scatter_kernel<<<(unsigned)((3 * a.n_runs + SCATTER_THREADS - 1) / SCATTER_THREADS), SCATTER_THREADS, 0, (cudaStream_t)s>>>(a);
         launches++;
     }
     if (a.n_gn > 0) {
