@@ -67,9 +67,9 @@ const TypeInfo kTypes[3] = {
     { GFA_BEAM_1, 3, 6, 18, 2, BEAM_STATE },
     { GFA_SOLID_1, 8, 8, 24, 8, 0 },
 };
-// 3x3 blocks kept per element in the Ke arena: Shell_1 stores the upper triangle plus the
-// non-symmetric rotation corner (gfa_device.h: shell_block), the others every block
-inline int stored_blocks(int slot) { return slot == 0 ? SHELL_STORED : kTypes[slot].nb * kTypes[slot].nb; }
+// doubles per element in the Ke arena: Shell_1 stores the upper triangle plus the non-symmetric
+// rotation corner in sector-padded groups (gfa_device.h: shell_stored_offset), the others every block
+inline int arena_doubles(int slot) { return slot == 0 ? SHELL_ARENA : kTypes[slot].ndof * kTypes[slot].ndof; }
 inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : t == GFA_BEAM_1 ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
 // local 3-DOF block -> (local node, DOF group 0 = translations / 1 = rotations)
 // in the reference's local DOF order (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444)
@@ -162,12 +162,12 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
     return a;
 }
 
-// index (in 3x3 blocks) of block (la, b) of a local element in the Ke arena; `tr` = stored transposed
+// offset (in doubles) of block (la, b) of a local element in the Ke arena; `tr` = stored transposed
 inline long long arena_block(const gfa_t* h, int slot, int local, int la, int b, bool& tr) {
-    const long long base = h->tb[slot].ke_base / 9 + (long long)local * stored_blocks(slot);
+    const long long base = h->tb[slot].ke_base + (long long)local * arena_doubles(slot);
     tr = false;
-    if (slot == 0) return base + shell_block(la, b, tr);
-    return base + la * kTypes[slot].nb + b;
+    if (slot == 0) return base + shell_block_offset(la, b, tr);
+    return base + (la * kTypes[slot].nb + b) * 9;
 }
 
 } // namespace
@@ -322,7 +322,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         for (int s = 0; s < 3 && e == cudaSuccess; s++) {
             TypeBlock& t = h->tb[s];
             t.ke_base = ke; t.pe_base = (int)pe;
-            ke += (long long)t.elems.size() * stored_blocks(s) * 9;
+            ke += (long long)t.elems.size() * arena_doubles(s);
             pe += (long long)t.elems.size() * kTypes[s].ndof;
             e = t.d_conn.upload(t.conn);
             if (e == cudaSuccess) e = t.d_prop.upload(t.prop);
@@ -555,7 +555,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 if (mine) {
                     bool tr;
                     const long long blk = arena_block(h, s, h->el_local[e], i / 3, j / 3, tr);
-                    en.src = blk * 9 + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3));
+                    en.src = blk + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3));
                 }
                 en.rank = h->world > 1 ? el_rank[e] : 0;
                 ents.push_back(en);
@@ -721,7 +721,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
                 bool tr;
                 const long long blk = arena_block(h, s, local, la, b, tr);
-                if (blk >= (1LL << 31)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 31-bit block index of the slot map");
+                if (blk >= (1LL << 31)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 31-bit block offsets of the slot map");
                 run_src[j].push_back((unsigned)blk | (tr ? SRC_T : 0u));
             }
         }
@@ -941,15 +941,15 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     CUDA_TRY(cudaSetDevice(h->device));
     const int n = kTypes[s].ndof;
     if (K) {
-        const int nb = n / 3, nsb = stored_blocks(s), local = h->el_local[e];
-        std::vector<double> blk((size_t)nsb * 9);
-        CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)local * nsb * 9, sizeof(double) * nsb * 9, cudaMemcpyDeviceToHost));
-        // device layout is block-major; hand back plain row-major
+        const int nb = n / 3, nd = arena_doubles(s), local = h->el_local[e];
+        std::vector<double> blk((size_t)nd);
+        CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)local * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+        // device layout is block-wise (and upper-triangular for Shell_1); hand back plain row-major
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 bool tr = false;
-                const int k = s == 0 ? shell_block(i / 3, j / 3, tr) : (i / 3) * nb + (j / 3);
-                K[i * n + j] = blk[(size_t)k * 9 + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3))];
+                const int off = s == 0 ? shell_block_offset(i / 3, j / 3, tr) : ((i / 3) * nb + (j / 3)) * 9;
+                K[i * n + j] = blk[(size_t)off + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3))];
             }
     }
     if (P) CUDA_TRY(cudaMemcpy(P, h->d_Pe.p + h->tb[s].pe_base + (size_t)h->el_local[e] * n, sizeof(double) * n, cudaMemcpyDeviceToHost));

@@ -23,7 +23,7 @@ struct EvalArgs {
     double* state;           // committed Gauss-point state (read by eval, written by commit)
     double* Ke;              // element arena of contiguous, row-major 3x3 blocks (reference local DOF order).
                              // Beam_1 / Solid_1: all (ndof/3)^2 blocks, [row block][column block].
-                             // Shell_1: SHELL_STORED blocks per element (see shell_block()).
+                             // Shell_1: SHELL_ARENA doubles per element (see shell_block_offset()).
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
     double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
 };
@@ -36,18 +36,25 @@ constexpr int SHELL_STATE = 21;        // Q_i(9) z_x1_i(3) z_x2_i(3) kappa_r1_i(
 constexpr int BEAM_STATE = 15;         // Q_i(9) dz_i(3) kappa_i_ref(3)
 
 // Shell_1 stored blocks over its 9 group-nodes (0-5: u of nodes 1-6, 6-8: alpha of nodes 4-6):
-// the 45 blocks (a <= b) of the upper triangle, then the 3 strictly-lower rotation-rotation
-// blocks (the only part of the tangent that is not symmetric, Shell_1.cpp:1277-1302).
-// Block (a > b) outside the rotation corner is the transpose of stored block (b, a).
+// the 45 blocks (a <= b) of the upper triangle plus the 3 strictly-lower rotation-rotation blocks
+// (the only part of the tangent that is not symmetric, Shell_1.cpp:1277-1302).  Block (a > b)
+// outside the rotation corner is the transpose of stored block (b, a).
+// Arena layout of one element (SHELL_ARENA doubles): the blocks are grouped by the evaluation
+// work item that produces them, each group padded to whole 32-byte sectors, so that every sector
+// is completed by one item within a few instructions (a sector left partially written is
+// evicted early and costs a DRAM read-modify-write, profiles/r01_notes.md):
+//   [64 K, 64 K + 63)       K = 0..2: translational columns K (rows u_0..u_K) then 5-K (rows u_0..u_{5-K})
+//   [192 + 84 c, .. + 81)   c = 0..2: rotational column c, rows u_0..u_5, alpha_0..alpha_2
 constexpr int SHELL_STORED = 48;
-__host__ __device__ constexpr int shell_upper(int a, int b) { return a * 9 - (a * (a - 1)) / 2 + (b - a); }
-// returns the stored index of block (a,b); `transposed` tells whether the stored block is (b,a)
-__host__ __device__ inline int shell_block(int a, int b, bool& transposed) {
-    transposed = false;
-    if (a <= b) return shell_upper(a, b);
-    if (b >= 6) return 45 + (a == 7 ? 0 : (b == 6 ? 1 : 2));     // (7,6) (8,6) (8,7)
-    transposed = true;
-    return shell_upper(b, a);
+constexpr int SHELL_ARENA = 444;
+// offset of stored block (a, b) inside the element's arena region
+__host__ __device__ constexpr int shell_stored_offset(int a, int b) {
+    return b < 6 ? (b < 3 ? 64 * b + 9 * a : 64 * (5 - b) + 9 * (6 - b + a)) : 192 + 84 * (b - 6) + 9 * a;
+}
+// offset of the stored block that holds block (a, b); `transposed` tells whether it holds (b, a)
+__host__ __device__ inline int shell_block_offset(int a, int b, bool& transposed) {
+    transposed = a > b && b < 6;
+    return transposed ? shell_stored_offset(b, a) : shell_stored_offset(a, b);
 }
 
 // ---- scatter ------------------------------------------------------------
@@ -65,7 +72,7 @@ struct RunEnt {         // 16 bytes, one per CSR patch that is summed by the sca
                         // column group (19-21) | number of contributing blocks (24-31)
     unsigned src0, src1;// count <= 2: the sources themselves; count > 2: src0 = start in the overflow list
 };
-// source encoding: index of the contiguous 3x3 block in the Ke arena (offset / 9); bit 31 = read transposed
+// source encoding: offset (in doubles) of the contiguous 3x3 block in the Ke arena; bit 31 = read transposed
 constexpr unsigned SRC_T = 0x80000000u;
 struct PInc {           // (element, local block) incidences of a group-node, for the residual vectors
     int pe_off;         // offset of the element's P in the Pe arena

@@ -36,7 +36,7 @@ constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
 constexpr int X_OFF = 171;              // rho*thickness, area (self-weight)
 constexpr int REC = 175;                // odd (16 distinct bank pairs for per-lane stores) and 3*REC*2 mod 32 = 26:
                                         // the <=3 elements x 3 components a warp reads in phase B fall into distinct banks
-constexpr int smem_bytes(int epw) { return epw * NGP * REC * 8; }
+constexpr int smem_bytes(int epw) { return epw * (NGP * REC + 27) * 8; }      // records, then the batch's P staging
 
 // upper-triangular block index of the 5x5 block matrix C'
 __host__ __device__ constexpr int blk(int p, int q) { return p * 5 - (p * (p - 1)) / 2 + (q - p); }
@@ -521,10 +521,10 @@ GFA_DI double cowper_factor(int a, double area) {
 }
 
 // ---- Phase B: K = sum_g dN^T C' dN, upper blocks only ---------------------
-// A column of K is stored 3 values at a time (the rows of one group-node) into the
-// element's stored block k of the arena.
-GFA_DI void put_col(const EvalArgs& A, size_t blk0, int k, int jj, double v0, double v1, double v2) {
-    double* p = A.Ke + (blk0 + k) * 9 + jj;
+// A column of K is stored 3 values at a time (the rows of one group-node) into the stored
+// block at `off` of the element's arena region (gfa_device.h: shell_stored_offset).
+GFA_DI void put_col(double* Ke_el, int off, int jj, double v0, double v1, double v2) {
+    double* p = Ke_el + off + jj;
     p[0] = v0; p[3] = v1; p[6] = v2;
 }
 
@@ -540,9 +540,9 @@ GFA_DI double self_weight(const EvalArgs& A, const double* rec0, int b, int jj) 
 // Translational columns B1 = KK and B2 = 5 - KK, component jj: rows u_0..u_B1 of the first and
 // u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7 blocks for every KK.
 template <int KK>
-__device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int jj) {
+__device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int jj, double* pe) {
     constexpr int B1 = KK, B2 = 5 - KK, N1 = B1 + 1, N2 = B2 + 1;
-    const size_t blk0 = (size_t)e * SHELL_STORED;
+    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA;
     double K1[N1][3], K2[N2][3];
 #pragma unroll
     for (int a = 0; a < N1; a++) { K1[a][0] = 0.0; K1[a][1] = 0.0; K1[a][2] = 0.0; }
@@ -583,18 +583,18 @@ __device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int jj) {
         }
     }
 #pragma unroll
-    for (int a = 0; a < N1; a++) put_col(A, blk0, shell_upper(a, B1), jj, K1[a][0], K1[a][1], K1[a][2]);
+    for (int a = 0; a < N1; a++) put_col(Ke_el, shell_stored_offset(a, B1), jj, K1[a][0], K1[a][1], K1[a][2]);
 #pragma unroll
-    for (int a = 0; a < N2; a++) put_col(A, blk0, shell_upper(a, B2), jj, K2[a][0], K2[a][1], K2[a][2]);
-    A.Pe[(size_t)e * 27 + 3 * B1 + jj] = F1 - self_weight(A, rec0, B1, jj);
-    A.Pe[(size_t)e * 27 + 3 * B2 + jj] = F2 - self_weight(A, rec0, B2, jj);
+    for (int a = 0; a < N2; a++) put_col(Ke_el, shell_stored_offset(a, B2), jj, K2[a][0], K2[a][1], K2[a][2]);
+    pe[3 * B1 + jj] = F1 - self_weight(A, rec0, B1, jj);
+    pe[3 * B2 + jj] = F2 - self_weight(A, rec0, B2, jj);
 }
 
 // Rotational column (mid-side node b in 0..2, component jj): all 27 rows -- the six u rows are the
 // upper u-alpha blocks (their transposes are the alpha-u blocks), the three alpha rows are the
 // non-symmetric alpha-alpha blocks, each stored on its own.
-__device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, int jj) {
-    const size_t blk0 = (size_t)e * SHELL_STORED;
+__device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, int jj, double* pe) {
+    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA + 192 + 84 * b;
     double K[27];
 #pragma unroll
     for (int i = 0; i < 27; i++) K[i] = 0.0;
@@ -627,13 +627,8 @@ __device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, in
         }
     }
 #pragma unroll
-    for (int a = 0; a < 6; a++) put_col(A, blk0, shell_upper(a, 6) + b, jj, K[3 * a], K[3 * a + 1], K[3 * a + 2]);
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        bool t;
-        put_col(A, blk0, shell_block(6 + a, 6 + b, t), jj, K[18 + 3 * a], K[19 + 3 * a], K[20 + 3 * a]);
-    }
-    A.Pe[(size_t)e * 27 + 18 + 3 * b + jj] = F;
+    for (int a = 0; a < 9; a++) put_col(Ke_el, 9 * a, jj, K[3 * a], K[3 * a + 1], K[3 * a + 2]);
+    pe[18 + 3 * b + jj] = F;
 }
 
 template <int EPW>
@@ -646,17 +641,20 @@ __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
         const int ne = min(EPW, A.e_end - e0);
         if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
         __syncwarp();
+        double* pe = smem + EPW * NGP * REC;      // the batch's P, written out in whole sectors below
         if (lane < ne * 3) {
             const int el = lane / 3, jj = lane % 3;
             const double* rec0 = smem + el * NGP * REC;
-            uu_item<0>(A, e0 + el, rec0, jj);
-            uu_item<1>(A, e0 + el, rec0, jj);
-            uu_item<2>(A, e0 + el, rec0, jj);
+            uu_item<0>(A, e0 + el, rec0, jj, pe + 27 * el);
+            uu_item<1>(A, e0 + el, rec0, jj, pe + 27 * el);
+            uu_item<2>(A, e0 + el, rec0, jj, pe + 27 * el);
         }
         for (int it = lane; it < ne * 9; it += 32) {
             const int el = it / 9, c = it % 9;
-            rot_item(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
+            rot_item(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3, pe + 27 * el);
         }
+        __syncwarp();
+        for (int i = lane; i < ne * 27; i += 32) A.Pe[(size_t)e0 * 27 + i] = pe[i];
         __syncwarp();
     }
 }
@@ -1176,7 +1174,7 @@ constexpr int SCATTER_THREADS = 256;
 // row ii of a 3x3 source block (column ii when the stored block is the transposed twin)
 GFA_DI void load_row(const double* Ke, unsigned src, int ii, double (&x)[3]) {
     const bool tr = (src & SRC_T) != 0;
-    const double* p = Ke + 9 * (size_t)(src & ~SRC_T) + (tr ? ii : 3 * ii);
+    const double* p = Ke + (size_t)(src & ~SRC_T) + (tr ? ii : 3 * ii);
     const int st = tr ? 3 : 1;
     x[0] = p[0]; x[1] = p[st]; x[2] = p[2 * st];
 }
@@ -1282,7 +1280,9 @@ int configure_kernels() {
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(shell::eval_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(6));
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(shell::eval_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(5));
+    e = cudaFuncSetAttribute(shell::eval_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(7));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(shell::eval_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(9));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(beam::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, beam::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -1299,7 +1299,7 @@ static int shell_epw() {
     if (!v) {
         const char* s = getenv("GFA_SHELL_EPW");
         v = s ? atoi(s) : 8;             // measured best on B200 (profiles/r01_notes.md)
-        if (v != 5 && v != 6 && v != 8 && v != 10) v = 8;
+        if (v < 6 || v > 10) v = 8;
     }
     return v;
 }
@@ -1310,7 +1310,8 @@ void launch_shell_eval(const EvalArgs& a, void* s) {
     const int grid = grid_for(a.e_end - a.e_begin, epw, cap);
     cudaStream_t st = (cudaStream_t)s;
     switch (epw) {
-    case 5: shell::eval_kernel<5><<<grid, 32, shell::smem_bytes(5), st>>>(a); break;
+    case 7: shell::eval_kernel<7><<<grid, 32, shell::smem_bytes(7), st>>>(a); break;
+    case 9: shell::eval_kernel<9><<<grid, 32, shell::smem_bytes(9), st>>>(a); break;
     case 6: shell::eval_kernel<6><<<grid, 32, shell::smem_bytes(6), st>>>(a); break;
     case 8: shell::eval_kernel<8><<<grid, 32, shell::smem_bytes(8), st>>>(a); break;
     default: shell::eval_kernel<10><<<grid, 32, shell::smem_bytes(10), st>>>(a); break;

@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""Print the handful of ncu metrics the notes quote from a .ncu-rep (raw page)."""
+import csv, subprocess, sys
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum',
+        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
+        'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum']
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units, vals = rows[0], rows[1], rows[2]
+print('metric,unit,value')
+for i, h in enumerate(hdr):
+    if h in KEYS or ('issue_stalled' in h and 'per_issue_active' in h and float(vals[i].replace(',', '') or 0) > 0.1):
+        print(f'{h},{units[i]},{vals[i]}')
