@@ -441,8 +441,22 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         mtv(t, PB, m2);
 #pragma unroll
         for (int i = 0; i < 3; i++) rec[F_OFF + 9 + i] = w * t[i];
-        direction_blocks(rec, P_Y0, P_Y1, P_G0, P_G1, G44, f4, kn.ga, kn.ga1, zg1, n1, m1, PA, Xig, gg, true);
-        direction_blocks(rec, P_Y2, P_Y3, P_G2, P_G3, G44, f4, kn.ga, kn.ga2, zg2, n2, m2, PA, Xig, gg, false);
+        // the two directions run through ONE copy of the code (rolled loop, inputs selected per
+        // pass): straight-line code is what this kernel is short of (instruction cache)
+#pragma unroll
+        for (int i = 0; i < 9; i++) G44[i] = 0.0;
+        f4[0] = 0.0; f4[1] = 0.0; f4[2] = 0.0;
+#pragma unroll 1
+        for (int beta = 0; beta < 2; beta++) {
+            double abg[3], zg[3], nb[3], mb[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                abg[i] = beta ? kn.ga2[i] : kn.ga1[i]; zg[i] = beta ? zg2[i] : zg1[i];
+                nb[i] = beta ? n2[i] : n1[i]; mb[i] = beta ? m2[i] : m1[i];
+            }
+            direction_blocks(rec, beta ? P_Y2 : P_Y0, beta ? P_Y3 : P_Y1, beta ? P_G2 : P_G0, beta ? P_G3 : P_G1,
+                             G44, f4, kn.ga, abg, zg, nb, mb, PA, Xig, gg, false);
+        }
 #pragma unroll
         for (int i = 0; i < 9; i++) rec[C_OFF + 9 * P_G4 + i] = G44[i];
 #pragma unroll
@@ -521,13 +535,6 @@ GFA_DI double cowper_factor(int a, double area) {
 }
 
 // ---- Phase B: K = sum_g dN^T C' dN, upper blocks only ---------------------
-// A column of K is stored 3 values at a time (the rows of one group-node) into the stored
-// block at `off` of the element's arena region (gfa_device.h: shell_stored_offset).
-GFA_DI void put_col(double* Ke_el, int off, int jj, double v0, double v1, double v2) {
-    double* p = Ke_el + off + jj;
-    p[0] = v0; p[3] = v1; p[6] = v2;
-}
-
 // self-weight entry of P for translational column (b, jj): applied twice, as the
 // reference does (Shell_1.cpp:1340-1375)
 GFA_DI double self_weight(const EvalArgs& A, const double* rec0, int b, int jj) {
@@ -537,55 +544,62 @@ GFA_DI double self_weight(const EvalArgs& A, const double* rec0, int b, int jj) 
     return one + one;
 }
 
-// Translational columns B1 = KK and B2 = 5 - KK, component jj: rows u_0..u_B1 of the first and
-// u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7 blocks for every KK.
-template <int KK>
-__device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int jj, double* pe) {
-    constexpr int B1 = KK, B2 = 5 - KK, N1 = B1 + 1, N2 = B2 + 1;
-    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA;
-    double K1[N1][3], K2[N2][3];
-#pragma unroll
-    for (int a = 0; a < N1; a++) { K1[a][0] = 0.0; K1[a][1] = 0.0; K1[a][2] = 0.0; }
-#pragma unroll
-    for (int a = 0; a < N2; a++) { K2[a][0] = 0.0; K2[a][1] = 0.0; K2[a][2] = 0.0; }
+// Phase B is written as short runtime loops on purpose: straight-line code beyond the ~32 KB the
+// SM's instruction cache holds is fetched at one instruction per ~3 cycles per warp
+// (tools/icache_probe.cu), which bounded this kernel (profiles/r01_notes.md).
+//
+// Translational columns B1 = kk and B2 = 5 - kk, component jj: rows u_0..u_B1 of the first and
+// u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7 blocks for every kk.
+__device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int kk, int jj, double* pe) {
+    const int B1 = kk, B2 = 5 - kk;
+    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA + 64 * kk + jj;
+    // m[g] = sum_q S_g[q, column] C'_g[(p, .), (q, jj)] for the two columns, p in {u,1 ; u,2}
+    double m10[NGP][3], m12[NGP][3], m20[NGP][3], m22[NGP][3];
     double F1 = 0.0, F2 = 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
         const double* recJ = rec + jj;
         const double* rec3J = rec + 3 * jj;
         const double* S = rec + S_OFF;
-        double c00[3], c02[3], c20[3], c22[3];
-        c00[0] = c_at<0, 0, 0>(recJ, rec3J); c00[1] = c_at<0, 1, 0>(recJ, rec3J); c00[2] = c_at<0, 2, 0>(recJ, rec3J);
-        c02[0] = c_at<0, 0, 2>(recJ, rec3J); c02[1] = c_at<0, 1, 2>(recJ, rec3J); c02[2] = c_at<0, 2, 2>(recJ, rec3J);
-        c20[0] = c_at<2, 0, 0>(recJ, rec3J); c20[1] = c_at<2, 1, 0>(recJ, rec3J); c20[2] = c_at<2, 2, 0>(recJ, rec3J);
-        c22[0] = c_at<2, 0, 2>(recJ, rec3J); c22[1] = c_at<2, 1, 2>(recJ, rec3J); c22[2] = c_at<2, 2, 2>(recJ, rec3J);
         const double p1 = S[B1], q1 = S[6 + B1], p2 = S[B2], q2 = S[6 + B2];
-        double m10[3], m12[3], m20[3], m22[3];
+        const double c00[3] = { c_at<0, 0, 0>(recJ, rec3J), c_at<0, 1, 0>(recJ, rec3J), c_at<0, 2, 0>(recJ, rec3J) };
+        const double c02[3] = { c_at<0, 0, 2>(recJ, rec3J), c_at<0, 1, 2>(recJ, rec3J), c_at<0, 2, 2>(recJ, rec3J) };
+        const double c20[3] = { c_at<2, 0, 0>(recJ, rec3J), c_at<2, 1, 0>(recJ, rec3J), c_at<2, 2, 0>(recJ, rec3J) };
+        const double c22[3] = { c_at<2, 0, 2>(recJ, rec3J), c_at<2, 1, 2>(recJ, rec3J), c_at<2, 2, 2>(recJ, rec3J) };
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            m10[i] = fma(q1, c02[i], p1 * c00[i]); m12[i] = fma(q1, c22[i], p1 * c20[i]);
-            m20[i] = fma(q2, c02[i], p2 * c00[i]); m22[i] = fma(q2, c22[i], p2 * c20[i]);
+            m10[g][i] = fma(q1, c02[i], p1 * c00[i]); m12[g][i] = fma(q1, c22[i], p1 * c20[i]);
+            m20[g][i] = fma(q2, c02[i], p2 * c00[i]); m22[g][i] = fma(q2, c22[i], p2 * c20[i]);
         }
         F1 = fma(q1, recJ[F_OFF + 6], fma(p1, recJ[F_OFF + 0], F1));
         F2 = fma(q2, recJ[F_OFF + 6], fma(p2, recJ[F_OFF + 0], F2));
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-            const double n1 = S[a], n2 = S[6 + a];
-            if (a < N1) {
-#pragma unroll
-                for (int i = 0; i < 3; i++) K1[a][i] = fma(n2, m12[i], fma(n1, m10[i], K1[a][i]));
-            }
-            if (a < N2) {
-#pragma unroll
-                for (int i = 0; i < 3; i++) K2[a][i] = fma(n2, m22[i], fma(n1, m20[i], K2[a][i]));
-            }
-        }
     }
+    const double* S0 = rec0 + S_OFF;
+#pragma unroll 1
+    for (int a = 0; a <= B1; a++) {            // block (u_a, u_B1) at 64 kk + 9 a
+        double k[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
-    for (int a = 0; a < N1; a++) put_col(Ke_el, shell_stored_offset(a, B1), jj, K1[a][0], K1[a][1], K1[a][2]);
+        for (int g = 0; g < NGP; g++) {
+            const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
 #pragma unroll
-    for (int a = 0; a < N2; a++) put_col(Ke_el, shell_stored_offset(a, B2), jj, K2[a][0], K2[a][1], K2[a][2]);
+            for (int i = 0; i < 3; i++) k[i] = fma(n2, m12[g][i], fma(n1, m10[g][i], k[i]));
+        }
+        double* o = Ke_el + 9 * a;
+        o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+    }
+#pragma unroll 1
+    for (int a = 0; a <= B2; a++) {            // block (u_a, u_B2) at 64 kk + 9 (kk + 1 + a)
+        double k[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+        for (int g = 0; g < NGP; g++) {
+            const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
+#pragma unroll
+            for (int i = 0; i < 3; i++) k[i] = fma(n2, m22[g][i], fma(n1, m20[g][i], k[i]));
+        }
+        double* o = Ke_el + 9 * (kk + 1 + a);
+        o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+    }
     pe[3 * B1 + jj] = F1 - self_weight(A, rec0, B1, jj);
     pe[3 * B2 + jj] = F2 - self_weight(A, rec0, B2, jj);
 }
@@ -594,40 +608,59 @@ __device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int jj, do
 // upper u-alpha blocks (their transposes are the alpha-u blocks), the three alpha rows are the
 // non-symmetric alpha-alpha blocks, each stored on its own.
 __device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, int jj, double* pe) {
-    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA + 192 + 84 * b;
-    double K[27];
-#pragma unroll
-    for (int i = 0; i < 27; i++) K[i] = 0.0;
+    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA + 192 + 84 * b + jj;
+    const double* S0 = rec0 + S_OFF;
     double F = 0.0;
-#pragma unroll 1
-    for (int g = 0; g < NGP; g++) {
-        const double* rec = rec0 + g * REC;
-        const double* recJ = rec + jj;
-        const double* rec3J = rec + 3 * jj;
-        const double* S = rec + S_OFF;
-        double m[5][3];
-        const double s1 = S[12 + b], s3 = S[15 + b], s4 = S[18 + b];
-#define GFA_ROW(P_, I_) m[P_][I_] = fma(s4, c_at<P_, I_, 4>(recJ, rec3J), fma(s3, c_at<P_, I_, 3>(recJ, rec3J), s1 * c_at<P_, I_, 1>(recJ, rec3J)));
-        GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2)
-        GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2) GFA_ROW(3, 0) GFA_ROW(3, 1) GFA_ROW(3, 2)
-        GFA_ROW(4, 0) GFA_ROW(4, 1) GFA_ROW(4, 2)
-#undef GFA_ROW
-        F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
+    {   // rows u_a: gradient groups {u,1 ; u,2} x {alpha,1 ; alpha,2 ; alpha}
+        double m0[NGP][3], m2[NGP][3];
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-            const double n1 = S[a], n2 = S[6 + a];
-#pragma unroll
-            for (int ii = 0; ii < 3; ii++) K[3 * a + ii] = fma(n2, m[2][ii], fma(n1, m[0][ii], K[3 * a + ii]));
+        for (int g = 0; g < NGP; g++) {
+            const double* rec = rec0 + g * REC;
+            const double* recJ = rec + jj;
+            const double* rec3J = rec + 3 * jj;
+            const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
+#define GFA_ROW(M_, P_, I_) M_[g][I_] = fma(s4, c_at<P_, I_, 4>(recJ, rec3J), fma(s3, c_at<P_, I_, 3>(recJ, rec3J), s1 * c_at<P_, I_, 1>(recJ, rec3J)));
+            GFA_ROW(m0, 0, 0) GFA_ROW(m0, 0, 1) GFA_ROW(m0, 0, 2) GFA_ROW(m2, 2, 0) GFA_ROW(m2, 2, 1) GFA_ROW(m2, 2, 2)
+            F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
         }
+#pragma unroll 1
+        for (int a = 0; a < 6; a++) {
+            double k[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            const double a1 = S[12 + a], a2 = S[15 + a], a0 = S[18 + a];
+            for (int g = 0; g < NGP; g++) {
+                const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
 #pragma unroll
-            for (int ii = 0; ii < 3; ii++) K[18 + 3 * a + ii] = fma(a0, m[4][ii], fma(a2, m[3][ii], fma(a1, m[1][ii], K[18 + 3 * a + ii])));
+                for (int i = 0; i < 3; i++) k[i] = fma(n2, m2[g][i], fma(n1, m0[g][i], k[i]));
+            }
+            double* o = Ke_el + 9 * a;
+            o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
         }
     }
+    {   // rows alpha_a: gradient groups {alpha,1 ; alpha,2 ; alpha} on both sides
+        double m1[NGP][3], m3[NGP][3], m4[NGP][3];
 #pragma unroll
-    for (int a = 0; a < 9; a++) put_col(Ke_el, 9 * a, jj, K[3 * a], K[3 * a + 1], K[3 * a + 2]);
+        for (int g = 0; g < NGP; g++) {
+            const double* rec = rec0 + g * REC;
+            const double* recJ = rec + jj;
+            const double* rec3J = rec + 3 * jj;
+            const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
+            GFA_ROW(m1, 1, 0) GFA_ROW(m1, 1, 1) GFA_ROW(m1, 1, 2) GFA_ROW(m3, 3, 0) GFA_ROW(m3, 3, 1) GFA_ROW(m3, 3, 2)
+            GFA_ROW(m4, 4, 0) GFA_ROW(m4, 4, 1) GFA_ROW(m4, 4, 2)
+#undef GFA_ROW
+        }
+#pragma unroll 1
+        for (int a = 0; a < 3; a++) {
+            double k[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+            for (int g = 0; g < NGP; g++) {
+                const double a1 = S0[g * REC + 12 + a], a2 = S0[g * REC + 15 + a], a0 = S0[g * REC + 18 + a];
+#pragma unroll
+                for (int i = 0; i < 3; i++) k[i] = fma(a0, m4[g][i], fma(a2, m3[g][i], fma(a1, m1[g][i], k[i])));
+            }
+            double* o = Ke_el + 9 * (6 + a);
+            o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+        }
+    }
     pe[18 + 3 * b + jj] = F;
 }
 
@@ -645,9 +678,8 @@ __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
         if (lane < ne * 3) {
             const int el = lane / 3, jj = lane % 3;
             const double* rec0 = smem + el * NGP * REC;
-            uu_item<0>(A, e0 + el, rec0, jj, pe + 27 * el);
-            uu_item<1>(A, e0 + el, rec0, jj, pe + 27 * el);
-            uu_item<2>(A, e0 + el, rec0, jj, pe + 27 * el);
+#pragma unroll 1
+            for (int kk = 0; kk < 3; kk++) uu_item(A, e0 + el, rec0, kk, jj, pe + 27 * el);
         }
         for (int it = lane; it < ne * 9; it += 32) {
             const int el = it / 9, c = it % 9;
