@@ -30,16 +30,23 @@ namespace gfa {
 namespace shell {
 
 constexpr int NGP = 3;                  // EPW (elements per warp batch) is a template parameter of eval_kernel
-constexpr int C_OFF = 0;                // 15 upper 3x3 blocks of C' (x weight)
-constexpr int F_OFF = 135;              // f (15)
-constexpr int S_OFF = 150;              // N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
-constexpr int X_OFF = 171;              // rho*thickness, area (self-weight)
-constexpr int REC = 175;                // odd (16 distinct bank pairs for per-lane stores) and 3*REC*2 mod 32 = 26:
-                                        // the <=3 elements x 3 components a warp reads in phase B fall into distinct banks
-constexpr int smem_bytes(int epw) { return epw * (NGP * REC + 27) * 8; }      // records, then the batch's P staging
+// Shared-memory record of one Gauss point (REC doubles):
+//   [0, 24)    the four symmetric diagonal blocks C'(R,R), R < 4, 6 values each (00 01 02 11 12 22)
+//   [24, 78)   the off-diagonal blocks (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), row-major 3x3
+//   [78, 123)  column 4: (0,4) (1,4) (2,4) (3,4) and the full, non-symmetric (4,4)
+//   [123, 138) f = Psi'^T sigma (15)
+//   [138, 159) S: N,1[6] N,2[6] Na,1[3] Na,2[3] Na[3]
+// While phase A runs, [0, 72) parks eight intermediate 3x3 blocks (Y0..Y3, G0..G3).
+constexpr int F_OFF = 123;
+constexpr int S_OFF = 138;
+constexpr int REC = 159;                // odd: the per-lane stores of phase A fall into 16 distinct bank pairs
+__host__ __device__ constexpr int smem_bytes(int epw) { return epw * (NGP * REC + 27) * 8; }      // records, then the batch's P staging
 
-// upper-triangular block index of the 5x5 block matrix C'
-__host__ __device__ constexpr int blk(int p, int q) { return p * 5 - (p * (p - 1)) / 2 + (q - p); }
+// offset of block (p, q), p <= q, of the 5x5 block matrix C' inside the record
+__host__ __device__ constexpr int boff(int p, int q) {
+    return q == 4 ? 78 + 9 * p : p == q ? 6 * p : 24 + 9 * (p == 0 ? q - 1 : p == 1 ? q + 1 : 5);
+}
+__host__ __device__ constexpr int park(int s) { return 9 * s; }      // parking slot s = 0..7
 
 struct DBlk { double d00, d01, d10, d11, d22; };
 
@@ -76,10 +83,17 @@ GFA_DI void dmul_acc(double* o, const DBlk& D, const double* P) {
         o[6 + j] += D.d22 * P[6 + j];
     }
 }
-// rec[blk(P,Q)] = w * (L^T M)  (+ w * R^T G R when G given)
-GFA_DI void put_block(double* rec, int b, double w, const double* LtM) {
+// rec[block (P,Q)] = w * M; a diagonal block of the first four groups is symmetric and keeps its
+// upper triangle only
+template <int P, int Q>
+GFA_DI void put_block(double* rec, double w, const double* M) {
+    if (P == Q && P < 4) {
+        rec[boff(P, Q) + 0] = w * M[0]; rec[boff(P, Q) + 1] = w * M[1]; rec[boff(P, Q) + 2] = w * M[2];
+        rec[boff(P, Q) + 3] = w * M[4]; rec[boff(P, Q) + 4] = w * M[5]; rec[boff(P, Q) + 5] = w * M[8];
+    } else {
 #pragma unroll
-    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * b + i] = w * LtM[i];
+        for (int i = 0; i < 9; i++) rec[boff(P, Q) + i] = w * M[i];
+    }
 }
 
 // Element frame and area-coordinate gradients (Shell_1::PreCalc, :1985-2060)
@@ -320,12 +334,12 @@ GFA_DI void direction_blocks(double* rec, int slotYn, int slotYm, int slotGn, in
     d_xi(Xib, ag, abg, gg, Xig);
     skew_mul(tmp, zg, Xig); mm(Y, PA, tmp);                    // Qt Z,b Xi R
 #pragma unroll
-    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotYn + i] = Y[i];
+    for (int i = 0; i < 9; i++) rec[9 * slotYn + i] = Y[i];
     mtv(t3, Y, nb);
     if (first) { f4[0] = t3[0]; f4[1] = t3[1]; f4[2] = t3[2]; } else { f4[0] += t3[0]; f4[1] += t3[1]; f4[2] += t3[2]; }
     mm(Y, PA, Xib);                                            // Qt Xi,b R
 #pragma unroll
-    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotYm + i] = Y[i];
+    for (int i = 0; i < 9; i++) rec[9 * slotYm + i] = Y[i];
     mtv(t3, Y, mb);
     f4[0] += t3[0]; f4[1] += t3[1]; f4[2] += t3[2];
 
@@ -333,12 +347,12 @@ GFA_DI void direction_blocks(double* rec, int slotYn, int slotYm, int slotGn, in
     mtv(sn, PA, nb); mtv(sm, PA, mb);                          // R^T Q n, R^T Q m
     skew_mul(SnXi, sn, Xig);                                   // skew(n) Xi
 #pragma unroll
-    for (int i = 0; i < 9; i++) rec[C_OFF + 9 * slotGn + i] = -SnXi[i];     // G(u,b ; alpha) = -skew(n) Xi
+    for (int i = 0; i < 9; i++) rec[9 * slotGn + i] = -SnXi[i];     // G(u,b ; alpha) = -skew(n) Xi
     v_op(V, ag, sm, gg);
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) rec[C_OFF + 9 * slotGm + 3 * i + j] = V[3 * j + i];   // G(alpha,b ; alpha) = V(alpha, m)^T
+        for (int j = 0; j < 3; j++) rec[9 * slotGm + 3 * i + j] = V[3 * j + i];   // G(alpha,b ; alpha) = V(alpha, m)^T
     // G(alpha;alpha) += Xi^T (Z,b skew(n)) Xi - V(alpha, Z,b n) + dV(alpha, alpha,b, m) - Xi,b^T (skew(m) Xi)
     skew_mul(tmp, zg, SnXi);
     if (first) mtm(G44, Xig, tmp); else mtm_acc(G44, Xig, tmp);
@@ -358,7 +372,7 @@ GFA_DI void direction_blocks(double* rec, int slotYn, int slotYm, int slotGn, in
 // Phase A for one Gauss point: fills its shared-memory record.
 __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     // parking slots inside the upper-triangle area (rewritten by the last step)
-    constexpr int P_Y0 = 0, P_Y1 = 1, P_Y2 = 2, P_Y3 = 3, P_G0 = 5, P_G1 = 6, P_G2 = 7, P_G3 = 9, P_G4 = 10;
+    constexpr int P_Y0 = 0, P_Y1 = 1, P_Y2 = 2, P_Y3 = 3, P_G0 = 4, P_G1 = 5, P_G2 = 6, P_G3 = 7;
     int nd[6];
 #pragma unroll
     for (int n = 0; n < 6; n++) nd[n] = __ldg(A.conn + 6 * (size_t)e + n);
@@ -379,8 +393,6 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
     const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
     const double w = fr.area / 3.0;                           // alpha1 (:2364)
-    rec[X_OFF] = __ldg(pr + 4) * thick;
-    rec[X_OFF + 1] = fr.area;
 
     double gg, Xi[9], Qt[9], z1[3], z2[3];
     Strains st;
@@ -458,7 +470,7 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
                              G44, f4, kn.ga, abg, zg, nb, mb, PA, Xig, gg, false);
         }
 #pragma unroll
-        for (int i = 0; i < 9; i++) rec[C_OFF + 9 * P_G4 + i] = G44[i];
+        for (int i = 0; i < 9; i++) rec[boff(4, 4) + i] = G44[i];       // parked in its final slot until column 4 is done
 #pragma unroll
         for (int i = 0; i < 3; i++) rec[F_OFF + 12 + i] = w * f4[i];  // f = Psi'^T sigma (:1324)
     }
@@ -472,25 +484,25 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     {
         double C44[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) C44[i] = rec[C_OFF + 9 * P_G4 + i];
+        for (int i = 0; i < 9; i++) C44[i] = rec[boff(4, 4) + i];
 #define GFA_COL4(R_, PG_, PY_)                                                        \
         { double H[9];                                                                \
-          { const DBlk d = getD<R_, 0>(X, smu, drill); dmul(H, d, rec + C_OFF + 9 * P_Y0); }     \
-          { const DBlk d = getD<R_, 1>(X, smu, drill); dmul_acc(H, d, rec + C_OFF + 9 * P_Y1); } \
-          { const DBlk d = getD<R_, 2>(X, smu, drill); dmul_acc(H, d, rec + C_OFF + 9 * P_Y2); } \
-          { const DBlk d = getD<R_, 3>(X, smu, drill); dmul_acc(H, d, rec + C_OFF + 9 * P_Y3); } \
+          { const DBlk d = getD<R_, 0>(X, smu, drill); dmul(H, d, rec + park(P_Y0)); }     \
+          { const DBlk d = getD<R_, 1>(X, smu, drill); dmul_acc(H, d, rec + park(P_Y1)); } \
+          { const DBlk d = getD<R_, 2>(X, smu, drill); dmul_acc(H, d, rec + park(P_Y2)); } \
+          { const DBlk d = getD<R_, 3>(X, smu, drill); dmul_acc(H, d, rec + park(P_Y3)); } \
           mtm(tmp2, GFA_PL(R_), H);                                                       \
-          _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += rec[C_OFF + 9 * PG_ + i];     \
-          put_block(rec, blk(R_, 4), w, tmp2);                                        \
-          mtm_acc(C44, rec + C_OFF + 9 * PY_, H); }
+          _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += rec[park(PG_) + i];     \
+          put_block<R_, 4>(rec, w, tmp2);                                             \
+          mtm_acc(C44, rec + park(PY_), H); }
         GFA_COL4(0, P_G0, P_Y0) GFA_COL4(1, P_G1, P_Y1) GFA_COL4(2, P_G2, P_Y2) GFA_COL4(3, P_G3, P_Y3)
 #undef GFA_COL4
-        put_block(rec, blk(4, 4), w, C44);
+        put_block<4, 4>(rec, w, C44);
     }
     // ... then the 10 upper blocks among the first four groups (overwrite the parking area)
 #define GFA_UPPER(R_, S_)                                                             \
     { const DBlk d = getD<R_, S_>(X, smu, drill); dmul(tmp, d, GFA_PL(S_));           \
-      mtm(tmp2, GFA_PL(R_), tmp); put_block(rec, blk(R_, S_), w, tmp2); }
+      mtm(tmp2, GFA_PL(R_), tmp); put_block<R_, S_>(rec, w, tmp2); }
     GFA_UPPER(0, 0) GFA_UPPER(0, 1) GFA_UPPER(0, 2) GFA_UPPER(0, 3)
     GFA_UPPER(1, 1) GFA_UPPER(1, 2) GFA_UPPER(1, 3)
     GFA_UPPER(2, 2) GFA_UPPER(2, 3)
@@ -499,12 +511,22 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
 #undef GFA_PL
 }
 
-// C'[(p,ii),(q,jj)] from the upper-triangular block storage.
-// recJ = rec + jj, rec3J = rec + 3*jj are precomputed by the caller.
+// C'[(p,ii),(q,jj)] from the record.  `c` carries the column: rec + jj, rec + 3 jj and the packed
+// index of (ii, jj) in a symmetric diagonal block for ii = 0, 1, 2.
+struct Col { const double* recJ; const double* rec3J; const double* sym[3]; };
+GFA_DI Col col_of(const double* rec, int jj) {
+    Col c;
+    c.recJ = rec + jj; c.rec3J = rec + 3 * jj;
+    c.sym[0] = rec + jj;                                  // (0,jj): 0 1 2
+    c.sym[1] = rec + (jj == 0 ? 1 : 2 + jj);              // (1,jj): 1 3 4
+    c.sym[2] = rec + (jj == 0 ? 2 : 3 + jj);              // (2,jj): 2 4 5
+    return c;
+}
 template <int P, int II, int Q>
-GFA_DI double c_at(const double* recJ, const double* rec3J) {
-    if (P <= Q) return recJ[C_OFF + 9 * blk(P, Q) + 3 * II];
-    else return rec3J[C_OFF + 9 * blk(Q, P) + II];
+GFA_DI double c_at(const Col& c) {
+    if (P == Q && P < 4) return c.sym[II][boff(P, P)];
+    if (P <= Q) return c.recJ[boff(P, Q) + 3 * II];
+    return c.rec3J[boff(Q, P) + II];
 }
 
 // 6-point Cowper rule factors sum_g w4[g] N_a(c_g) / area, a = 0..5 (:2185-2314)
@@ -537,10 +559,12 @@ GFA_DI double cowper_factor(int a, double area) {
 // ---- Phase B: K = sum_g dN^T C' dN, upper blocks only ---------------------
 // self-weight entry of P for translational column (b, jj): applied twice, as the
 // reference does (Shell_1.cpp:1340-1375)
-GFA_DI double self_weight(const EvalArgs& A, const double* rec0, int b, int jj) {
+GFA_DI double self_weight(const EvalArgs& A, int e, int b, int jj) {
     if (A.gx == 0.0 && A.gy == 0.0 && A.gz == 0.0) return 0.0;
     const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
-    const double one = cowper_factor(b, rec0[X_OFF + 1]) * (rec0[X_OFF] * gk);
+    const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    const double rho_t = __ldg(pr + 4) * __ldg(pr + 2);
+    const double one = cowper_factor(b, __ldg(A.geo + 9 * (size_t)A.n_el + e)) * (rho_t * gk);
     return one + one;
 }
 
@@ -560,13 +584,13 @@ __device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int kk, in
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
         const double* recJ = rec + jj;
-        const double* rec3J = rec + 3 * jj;
+        const Col cc = col_of(rec, jj);
         const double* S = rec + S_OFF;
         const double p1 = S[B1], q1 = S[6 + B1], p2 = S[B2], q2 = S[6 + B2];
-        const double c00[3] = { c_at<0, 0, 0>(recJ, rec3J), c_at<0, 1, 0>(recJ, rec3J), c_at<0, 2, 0>(recJ, rec3J) };
-        const double c02[3] = { c_at<0, 0, 2>(recJ, rec3J), c_at<0, 1, 2>(recJ, rec3J), c_at<0, 2, 2>(recJ, rec3J) };
-        const double c20[3] = { c_at<2, 0, 0>(recJ, rec3J), c_at<2, 1, 0>(recJ, rec3J), c_at<2, 2, 0>(recJ, rec3J) };
-        const double c22[3] = { c_at<2, 0, 2>(recJ, rec3J), c_at<2, 1, 2>(recJ, rec3J), c_at<2, 2, 2>(recJ, rec3J) };
+        const double c00[3] = { c_at<0, 0, 0>(cc), c_at<0, 1, 0>(cc), c_at<0, 2, 0>(cc) };
+        const double c02[3] = { c_at<0, 0, 2>(cc), c_at<0, 1, 2>(cc), c_at<0, 2, 2>(cc) };
+        const double c20[3] = { c_at<2, 0, 0>(cc), c_at<2, 1, 0>(cc), c_at<2, 2, 0>(cc) };
+        const double c22[3] = { c_at<2, 0, 2>(cc), c_at<2, 1, 2>(cc), c_at<2, 2, 2>(cc) };
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             m10[g][i] = fma(q1, c02[i], p1 * c00[i]); m12[g][i] = fma(q1, c22[i], p1 * c20[i]);
@@ -600,8 +624,8 @@ __device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int kk, in
         double* o = Ke_el + 9 * (kk + 1 + a);
         o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
     }
-    pe[3 * B1 + jj] = F1 - self_weight(A, rec0, B1, jj);
-    pe[3 * B2 + jj] = F2 - self_weight(A, rec0, B2, jj);
+    pe[3 * B1 + jj] = F1 - self_weight(A, e, B1, jj);
+    pe[3 * B2 + jj] = F2 - self_weight(A, e, B2, jj);
 }
 
 // Rotational column (mid-side node b in 0..2, component jj): all 27 rows -- the six u rows are the
@@ -617,9 +641,9 @@ __device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, in
         for (int g = 0; g < NGP; g++) {
             const double* rec = rec0 + g * REC;
             const double* recJ = rec + jj;
-            const double* rec3J = rec + 3 * jj;
+            const Col cc = col_of(rec, jj);
             const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
-#define GFA_ROW(M_, P_, I_) M_[g][I_] = fma(s4, c_at<P_, I_, 4>(recJ, rec3J), fma(s3, c_at<P_, I_, 3>(recJ, rec3J), s1 * c_at<P_, I_, 1>(recJ, rec3J)));
+#define GFA_ROW(M_, P_, I_) M_[g][I_] = fma(s4, c_at<P_, I_, 4>(cc), fma(s3, c_at<P_, I_, 3>(cc), s1 * c_at<P_, I_, 1>(cc)));
             GFA_ROW(m0, 0, 0) GFA_ROW(m0, 0, 1) GFA_ROW(m0, 0, 2) GFA_ROW(m2, 2, 0) GFA_ROW(m2, 2, 1) GFA_ROW(m2, 2, 2)
             F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
         }
@@ -641,8 +665,7 @@ __device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, in
 #pragma unroll
         for (int g = 0; g < NGP; g++) {
             const double* rec = rec0 + g * REC;
-            const double* recJ = rec + jj;
-            const double* rec3J = rec + 3 * jj;
+            const Col cc = col_of(rec, jj);
             const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
             GFA_ROW(m1, 1, 0) GFA_ROW(m1, 1, 1) GFA_ROW(m1, 1, 2) GFA_ROW(m3, 3, 0) GFA_ROW(m3, 3, 1) GFA_ROW(m3, 3, 2)
             GFA_ROW(m4, 4, 0) GFA_ROW(m4, 4, 1) GFA_ROW(m4, 4, 2)
