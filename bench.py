@@ -94,7 +94,7 @@ def workload(n_gpus: int, per_gpu_cells=(1000, 500)):
                                            "elements": 2 * nx * ny * n_gpus, "per_gpu_elements": 2 * nx * ny,
                                            "config": "BASELINE.json configs[2] (1M-element Shell_1 plate) per GPU",
                                            "partition": f"{n_gpus} strips by contiguous element range",
-                                           "l2": "inputs larger than L2 (element blocks 5.8 GB, CSR values 4.2 GB per GPU)"}
+                                           "l2": "inputs larger than L2 (element blocks 3.6 GB, CSR values 4.2 GB per GPU)"}
 
 
 # ---------------------------------------------------------------------------
