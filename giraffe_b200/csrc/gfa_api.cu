@@ -128,7 +128,7 @@ struct gfa_handle {
     DevBuf<double> d_arena;
     DevBuf<GnRec> d_gn;
     DevBuf<RunEnt> d_runs;
-    DevBuf<unsigned> d_ovf;
+    DevBuf<unsigned long long> d_ovf;
     DevBuf<PInc> d_inc;
     long long n_runs = 0, n_gn_local = 0;
     DevBuf<long long> d_gseg, d_gsrc, d_gdest;
@@ -695,8 +695,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     // For every (group-node, neighbour) patch: the local element blocks feeding it, element-ascending.
     std::vector<PInc> incs;
     std::vector<RunEnt> runs;
-    std::vector<unsigned> ovf;
-    std::vector<std::vector<unsigned> > run_src;   // scratch: sources per patch of the current group-node
+    std::vector<unsigned long long> ovf;
+    std::vector<std::vector<unsigned long long> > run_src;   // scratch: sources per patch of the current group-node
     std::vector<GnRec> gn_recs;
     for (size_t ti_ = 0; ti_ < touched_gn.size(); ti_++) {
         const size_t gn = (size_t)touched_gn[ti_];
@@ -721,8 +721,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
                 bool tr;
                 const long long blk = arena_block(h, s, local, la, b, tr);
-                if (blk >= (1LL << 31)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 31-bit block offsets of the slot map");
-                run_src[j].push_back((unsigned)blk | (tr ? SRC_T : 0u));
+                if (blk >= (1LL << 32)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 32-bit block offsets of the slot map");
+                run_src[j].push_back((unsigned long long)blk | (tr ? SRC_T : 0ULL));
             }
         }
         GnRec rec;
@@ -739,7 +739,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         int col = 0;
         for (int j = 0; j < n_runs; j++) {
             const int fm = free_mask((size_t)nb0[j]);
-            const std::vector<unsigned>& src = run_src[j];
+            const std::vector<unsigned long long>& src = run_src[j];
             const long long dst = row0 + col;
             col += __builtin_popcount(fm);
             if (!fm) continue;
@@ -748,8 +748,13 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             RunEnt r;
             r.dst = (int)dst;
             r.info = (unsigned)rowL[gn] | ((unsigned)rm << 16) | ((unsigned)fm << 19) | ((unsigned)src.size() << 24);
-            r.src0 = src.size() > 0 ? src[0] : 0u; r.src1 = src.size() > 1 ? src[1] : 0u;
-            if (src.size() > 2) { r.src0 = (unsigned)ovf.size(); ovf.insert(ovf.end(), src.begin(), src.end()); }
+            r.src0 = src.size() > 0 ? (unsigned)src[0] : 0u; r.src1 = src.size() > 1 ? (unsigned)src[1] : 0u;
+            if (src.size() > 0 && (src[0] & SRC_T)) r.info |= 1u << 22;
+            if (src.size() > 1 && (src[1] & SRC_T)) r.info |= 1u << 23;
+            if (src.size() > 2) {
+                if (ovf.size() >= (1ULL << 32)) return fail(GFA_EUNSUPPORTED, "overflow source list exceeds 2^32 entries");
+                r.src0 = (unsigned)ovf.size(); ovf.insert(ovf.end(), src.begin(), src.end());
+            }
             runs.push_back(r);
         }
     }

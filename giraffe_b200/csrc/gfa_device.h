@@ -69,11 +69,13 @@ __host__ __device__ inline int shell_block_offset(int a, int b, bool& transposed
 struct RunEnt {         // 16 bytes, one per CSR patch that is summed by the scatter kernel
     int dst;            // valAA offset of the patch's first entry (first free row, first free column)
     unsigned info;      // row stride (bits 0-15) | free mask of the row group (16-18) | free mask of the
-                        // column group (19-21) | number of contributing blocks (24-31)
+                        // column group (19-21) | src0 / src1 read transposed (22, 23) | number of
+                        // contributing blocks (24-31)
     unsigned src0, src1;// count <= 2: the sources themselves; count > 2: src0 = start in the overflow list
 };
-// source encoding: offset (in doubles) of the contiguous 3x3 block in the Ke arena; bit 31 = read transposed
-constexpr unsigned SRC_T = 0x80000000u;
+// source encoding: offset (in doubles, 32 bits) of the contiguous 3x3 block in the Ke arena; overflow
+// list entries are 64-bit, bit 63 = read transposed
+constexpr unsigned long long SRC_T = 1ULL << 63;
 struct PInc {           // (element, local block) incidences of a group-node, for the residual vectors
     int pe_off;         // offset of the element's P in the Pe arena
     int la;             // local block index
@@ -87,7 +89,7 @@ struct GnRec {
 struct ScatterArgs {
     long long n_runs;
     const RunEnt* runs;
-    const unsigned* ovf;         // overflow source lists (patches fed by more than two blocks)
+    const unsigned long long* ovf;   // overflow source lists (patches fed by more than two blocks)
     long long n_gn;
     const GnRec* gn;
     const PInc* inc;

@@ -1227,9 +1227,8 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 constexpr int SCATTER_THREADS = 256;
 
 // row ii of a 3x3 source block (column ii when the stored block is the transposed twin)
-GFA_DI void load_row(const double* Ke, unsigned src, int ii, double (&x)[3]) {
-    const bool tr = (src & SRC_T) != 0;
-    const double* p = Ke + (size_t)(src & ~SRC_T) + (tr ? ii : 3 * ii);
+GFA_DI void load_row(const double* Ke, unsigned off, bool tr, int ii, double (&x)[3]) {
+    const double* p = Ke + (size_t)off + (tr ? ii : 3 * ii);
     const int st = tr ? 3 : 1;
     x[0] = p[0]; x[1] = p[st]; x[2] = p[2 * st];
 }
@@ -1255,16 +1254,21 @@ __global__ void __launch_bounds__(SCATTER_THREADS) scatter_kernel(ScatterArgs A)
     double a[3];
     {
         unsigned s0 = q.z, s1 = q.w;
-        if (cnt > 2) { s0 = __ldg(A.ovf + q.z); s1 = __ldg(A.ovf + q.z + 1); }
+        bool t0 = (info >> 22) & 1, t1 = (info >> 23) & 1;
+        if (cnt > 2) {
+            const unsigned long long e0 = __ldg(A.ovf + q.z), e1 = __ldg(A.ovf + q.z + 1);
+            s0 = (unsigned)e0; t0 = (e0 & SRC_T) != 0; s1 = (unsigned)e1; t1 = (e1 & SRC_T) != 0;
+        }
         double x[3] = { 0.0, 0.0, 0.0 }, y[3] = { 0.0, 0.0, 0.0 };
-        if (cnt > 0) load_row(A.Ke, s0, ii, x);          // count 0: a patch fed by other ranks only
-        if (cnt > 1) load_row(A.Ke, s1, ii, y);
+        if (cnt > 0) load_row(A.Ke, s0, t0, ii, x);          // count 0: a patch fed by other ranks only
+        if (cnt > 1) load_row(A.Ke, s1, t1, ii, y);
 #pragma unroll
         for (int i = 0; i < 3; i++) a[i] = x[i] + y[i];
     }
     for (int k = 2; k < cnt; k++) {
         double x[3];
-        load_row(A.Ke, __ldg(A.ovf + q.z + k), ii, x);
+        const unsigned long long e = __ldg(A.ovf + q.z + k);
+        load_row(A.Ke, (unsigned)e, (e & SRC_T) != 0, ii, x);
 #pragma unroll
         for (int i = 0; i < 3; i++) a[i] += x[i];
     }
@@ -1361,7 +1365,29 @@ static int shell_epw() {
 void launch_shell_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
     const int epw = shell_epw();
-    const int cap = kSMs * 64;      // a multiple of the SM count; batches are strided over the grid
+    // persistent warps: exactly as many one-warp CTAs as are resident (7 per SM with 8-element
+    // batches), each striding over the batches -- 5 % faster than 64 CTAs per SM taking turns
+    // (profiles/r01_notes.md); GFA_SHELL_GRID overrides the CTAs per SM
+    static int per_sm = 0;
+    if (!per_sm) {
+        const char* e = getenv("GFA_SHELL_GRID");
+        per_sm = e ? atoi(e) : 0;
+        if (per_sm < 1) {
+            int n = 0;
+            cudaError_t err = cudaErrorUnknown;
+            switch (epw) {
+            case 7: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<7>, 32, shell::smem_bytes(7)); break;
+            case 9: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<9>, 32, shell::smem_bytes(9)); break;
+            case 6: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<6>, 32, shell::smem_bytes(6)); break;
+            case 8: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<8>, 32, shell::smem_bytes(8)); break;
+            default: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<10>, 32, shell::smem_bytes(10)); break;
+            }
+            per_sm = (err == cudaSuccess && n > 0) ? n : 8;
+        }
+    }
+    int n_sm = kSMs;
+    { static int sms = 0; if (!sms) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs; } n_sm = sms; }
+    const int cap = n_sm * per_sm;
     const int grid = grid_for(a.e_end - a.e_begin, epw, cap);
     cudaStream_t st = (cudaStream_t)s;
     switch (epw) {
@@ -1372,14 +1398,27 @@ void launch_shell_eval(const EvalArgs& a, void* s) {
     default: shell::eval_kernel<10><<<grid, 32, shell::smem_bytes(10), st>>>(a); break;
     }
 }
+// resident one-warp CTAs on the whole device for a kernel (persistent grid)
+template <class K>
+static int resident_ctas(K kernel, int smem) {
+    int n = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 32, smem) != cudaSuccess || n < 1) n = 8;
+    return sms * n;
+}
 void launch_beam_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
-    const int grid = grid_for(a.e_end - a.e_begin, beam::EPW, kSMs * 8 * 8);
+    static int cap = 0;
+    if (!cap) cap = resident_ctas(beam::eval_kernel, beam::SMEM_BYTES);
+    const int grid = grid_for(a.e_end - a.e_begin, beam::EPW, cap);
     beam::eval_kernel<<<grid, 32, beam::SMEM_BYTES, (cudaStream_t)s>>>(a);
 }
 void launch_solid_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
-    const int grid = grid_for(a.e_end - a.e_begin, solid::EPW, kSMs * 8 * 8);
+    static int cap = 0;
+    if (!cap) cap = resident_ctas(solid::eval_kernel, solid::SMEM_BYTES);
+    const int grid = grid_for(a.e_end - a.e_begin, solid::EPW, cap);
     solid::eval_kernel<<<grid, 32, solid::SMEM_BYTES, (cudaStream_t)s>>>(a);
 }
 void launch_shell_precalc(const EvalArgs& a, double* geo, double* shp, void* s) {

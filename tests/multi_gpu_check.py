@@ -47,6 +47,8 @@ def main():
         ex = InterfaceExchange(asm, world)
         asm.assemble(d)
         ex()
+        asm.assemble(d)      # a second Newton iteration on the same pattern: slots are rewritten, not accumulated
+        ex()
         lo, li, lv, _ = asm.csr("AA")
         rows = asm.local_rows()
         owned = asm.owned_rows()
