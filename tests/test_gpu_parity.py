@@ -248,13 +248,39 @@ def _full_size_checks(port, m, d, n_dof_el, what):
     interior = np.ones(nnz - 1, bool)
     interior[row_starts - 1] = False
     assert (dcol[interior] > 0).all(), f"{what}: AA columns not strictly ascending inside rows"
-    # (4) translation invariance: a rigid translation produces no internal force,
-    #     so K_AA t_A + K_AB t_B = 0 for t = unit translation of every node
-    #     (checked at zero increment where K is the tangent of Fint = 0)
+    # (4) translation invariance, the global check of the scatter: Fint(u + c) = Fint(u) for a rigid
+    #     translation c, so K c = 0 row by row -- K_AA c_A + K_AB c_B = 0 and K_BA c_A + K_BB c_B = 0 --
+    #     at ANY state (the shape-function derivatives sum to zero).  One misplaced, missing or doubled
+    #     element entry anywhere in the 5e8 slots breaks it.
+    _translation_invariance(asm, m, what)
+    # (5) nothing is assembled at rest
     asm.assemble(np.zeros_like(d))
     pa0, _, pb0 = asm.vectors()
     assert np.abs(pa0).max() <= 1e-9 * max(1.0, np.abs(asm.values("AA")).max() * 1e-6), f"{what}: residual at rest"
     return asm, total
+
+
+def _translation_invariance(asm, m, what, tol=1e-10):
+    import scipy.sparse as sp
+    gls, nf, nx = M.number_dofs(m)
+    mats = {}
+    for w in ("AA", "AB", "BA", "BB"):
+        outer, inner = asm.csr_pattern(w)
+        rows, cols, _ = asm.csr_dims(w)
+        mats[w] = sp.csr_matrix((asm.values(w), inner, outer), shape=(rows, cols))
+    for k in range(3):
+        g = gls[:, k]
+        cA = np.zeros(nf); cB = np.zeros(max(nx, 1))
+        cA[g[g > 0] - 1] = 1.0
+        cB[-g[g < 0] - 1] = 1.0
+        cB = cB[:nx]
+        for ra, rb in (("AA", "AB"), ("BA", "BB")):
+            if mats[ra].shape[0] == 0:
+                continue
+            r = mats[ra] @ cA + (mats[rb] @ cB if nx else 0.0)
+            scale = abs(mats[ra]) @ np.abs(cA) + (abs(mats[rb]) @ np.abs(cB) if nx else 0.0)
+            bad = np.abs(r) > tol * np.maximum(scale, scale.max() * 1e-6)
+            assert not bad.any(), f"{what}: K c != 0 for translation {k} in {int(bad.sum())} rows of {ra}|{rb} (worst {np.abs(r).max():.3e} vs {scale.max():.3e})"
 
 
 def test_full_size_beam_line(port):
@@ -273,3 +299,16 @@ def test_full_size_shell_plate(port):
     asm, _ = _full_size_checks(port, m, d, 27, "1M shells")
     nnz = asm.csr_dims("AA")[2]
     assert abs(nnz / m.n_elements - 517.5) < 2.0        # ~517 non-zeros per element
+
+
+def test_full_size_solid_block():
+    """BASELINE.json configs[3]: 4M Solid_1 block (builder-defined hexahedron, parity unpinned by the
+    reference).  The element arena passes 2^31 doubles here, so this also covers the 32-bit arena
+    offsets of the slot map; the check is the global translation invariance of the assembled tangent."""
+    m = M.solid_block(160, 160, 156)
+    assert m.n_elements * 576 > 2 ** 31
+    d = M.solid_block_displacements(m)
+    asm = capi.Assembler(m).set_dofs()
+    asm.assemble(d)
+    _translation_invariance(asm, m, "4M solids")
+    asm.close()
