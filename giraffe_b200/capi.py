@@ -26,7 +26,7 @@ EXPORTS = [
     "gfa_last_error", "gfa_device_count", "gfa_create", "gfa_destroy", "gfa_number_dofs", "gfa_set_dofs",
     "gfa_csr_dims", "gfa_csr_pattern", "gfa_assemble", "gfa_add_host_triplets", "gfa_add_host_vector",
     "gfa_csr_values", "gfa_csr_values_device", "gfa_vector", "gfa_vector_device", "gfa_element_block",
-    "gfa_commit_state", "gfa_element_state", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
+    "gfa_commit_state", "gfa_element_state", "gfa_results_stride", "gfa_gauss_point_results", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
 ]
 
@@ -83,6 +83,9 @@ def load_library() -> C.CDLL:
         lib.gfa_element_block.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.gfa_commit_state.argtypes = [C.c_void_p]
         lib.gfa_element_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        lib.gfa_results_stride.argtypes = [C.c_int]
+        lib.gfa_gauss_point_results.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        lib.gfa_gauss_point_results.restype = C.c_int64
         lib.gfa_copy_coordinates.argtypes = [C.c_void_p, C.c_void_p]
         lib.gfa_last_timing.argtypes = [C.c_void_p, C.c_void_p]
         lib.gfa_last_launch_count.argtypes = [C.c_void_p]
@@ -277,6 +280,19 @@ class Assembler:
         buf = np.zeros(64)
         n = self._check(self.lib.gfa_element_state(self._h, e, _ptr(buf)))
         return buf[:n].copy()
+
+    def gauss_point_results(self, element_type: int):
+        """Result read-back (gfa_gauss_point_results): array [n_elements_of_type, stride]; column 0 is
+        the strain energy, the rest the per-point strains / resultants (see include/gfa.h)."""
+        stride = self.lib.gfa_results_stride(int(element_type))
+        if stride == 0:
+            raise GfaError(-7, f"element type {element_type} keeps no Gauss-point results")
+        n = int(np.count_nonzero(self.model.elem_type == element_type))      # upper bound: this rank holds a part
+        buf = np.zeros((max(n, 1), stride))
+        got = self.lib.gfa_gauss_point_results(self._h, int(element_type), _ptr(buf), buf.size)
+        if got < 0:
+            raise GfaError(int(got), self.lib.gfa_last_error().decode())
+        return buf[:got]
 
     def copy_coordinates(self):
         c = np.zeros(self.model.n_nodes * 6)

@@ -989,6 +989,31 @@ int gfa_element_state(gfa_t* h, int32_t e, double* out) {
     return w;
 }
 
+int gfa_results_stride(int element_type) {
+    return element_type == GFA_SHELL_1 ? SHELL_RESULTS : element_type == GFA_BEAM_1 ? BEAM_RESULTS : 0;
+}
+
+int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* out, int64_t capacity) {
+    if (!h || !out) return fail(GFA_EINVAL, "gfa_gauss_point_results: null argument");
+    const int s = type_slot(element_type);
+    const int stride = gfa_results_stride(element_type);
+    if (s < 0 || stride == 0) return fail(GFA_EUNSUPPORTED, "element type %d keeps no Gauss-point results", element_type);
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_gauss_point_results before gfa_assemble");
+    const size_t n = h->tb[s].elems.size();
+    if ((int64_t)(n * stride) > capacity) return fail(GFA_EINVAL, "gfa_gauss_point_results: %zu records of %d doubles need capacity %zu, got %lld", n, stride, n * stride, (long long)capacity);
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    DevBuf<double> d;
+    cudaError_t e = d.alloc(n * stride);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "gfa_gauss_point_results: %s", cudaGetErrorString(e));
+    const EvalArgs ea = eval_args(h, s, 0.0);
+    if (s == 0) launch_shell_results(ea, d.p, h->stream); else launch_beam_results(ea, d.p, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d.p, n * stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return (int64_t)n;
+}
+
 int gfa_copy_coordinates(gfa_t* h, double* out) {
     if (!h || !out) return fail(GFA_EINVAL, "gfa_copy_coordinates: bad argument");
     CUDA_TRY(cudaSetDevice(h->device));

@@ -32,6 +32,8 @@ constexpr int SHELL_PROP_STRIDE = 5;   // lambda, mu, thickness, stiff_drill, rh
 constexpr int BEAM_PROP_STRIDE = 46;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A
 constexpr int SOLID_PROP_STRIDE = 3;   // lambda, mu, rho
 
+constexpr int SHELL_RESULTS = 73;      // strain_energy + 3 x (eta1 eta2 kappa1 kappa2 n1 n2 m1 m2)
+constexpr int BEAM_RESULTS = 25;       // strain_energy + 2 x (epsilon_r(6) sigma_r(6))
 constexpr int SHELL_STATE = 21;        // Q_i(9) z_x1_i(3) z_x2_i(3) kappa_r1_i(3) kappa_r2_i(3)
 constexpr int BEAM_STATE = 15;         // Q_i(9) dz_i(3) kappa_i_ref(3)
 
@@ -115,6 +117,8 @@ void launch_solid_eval(const EvalArgs& a, void* stream);
 void launch_shell_precalc(const EvalArgs& a, double* geo, double* shp, void* stream);
 void launch_shell_commit(const EvalArgs& a, void* stream);
 void launch_beam_commit(const EvalArgs& a, void* stream);
+void launch_shell_results(const EvalArgs& a, double* out, void* stream);     // out[n_el * GFA_SHELL_RESULTS]
+void launch_beam_results(const EvalArgs& a, double* out, void* stream);      // out[n_el * GFA_BEAM_RESULTS]
 void launch_node_commit(int n_nodes, double* copy, double* disp, void* stream);
 int launch_scatter(const ScatterArgs& a, void* stream);      // returns the number of kernels launched
 void launch_gather(const GatherArgs& a, void* stream);

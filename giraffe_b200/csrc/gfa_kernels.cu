@@ -746,6 +746,84 @@ __global__ void commit_kernel(EvalArgs A) {
     }
 }
 
+
+// Gauss-point results Mount keeps for WriteResults / WriteVTK / WriteMonitor (Shell_1.cpp:624-707,
+// Monitor.cpp:494): eta_r1, eta_r2, kappa_r1, kappa_r2, n_r1, n_r2, m_r1 (with the drilling term,
+// :1214-1217), m_r2 per point and the element's strain energy (:1150-1161, :1326).  Computed on demand
+// from the current increments and the committed state -- not on the per-iteration path.
+// out[e * 73]: strain_energy, then per point g: eta1 eta2 kappa1 kappa2 n1 n2 m1 m2 (3 each).
+__global__ void results_kernel(EvalArgs A, double* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.n_el) return;
+    int nd[6];
+#pragma unroll
+    for (int n = 0; n < 6; n++) nd[n] = __ldg(A.conn + 6 * (size_t)e + n);
+    const double* pr = A.props + SHELL_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    const double lam = __ldg(pr), mu = __ldg(pr + 1), thick = __ldg(pr + 2), drill = __ldg(pr + 3);
+    const size_t n_gp = (size_t)A.n_el * NGP;
+    double energy = 0.0;
+    double* o = out + (size_t)e * 73;
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++) {
+        const size_t gp = (size_t)e * NGP + g;
+        Frame fr; Shape sh; Kin kn;
+        load_precalc(A, e, g, fr, sh);
+        interpolate(A, nd, fr, sh, kn);
+        Strains st;
+        {
+            double gg, Xi[9], Qt[9], z1[3], z2[3], Qd[9], Qi[9], Q[9], t3[3];
+#pragma unroll
+            for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                z1[i] = s_add(kn.u1[i], A.state[(9 + i) * n_gp + gp]);
+                z2[i] = s_add(kn.u2[i], A.state[(12 + i) * n_gp + gp]);
+            }
+            s_rodrigues(kn.a, gg, Qd, Xi);
+            s_mm(Q, Qd, Qi);
+            m_transpose(Qt, Q);
+            s_mv(st.eta1, Qt, z1); st.eta1[0] = s_sub(st.eta1[0], 1.0);
+            s_mv(st.eta2, Qt, z2); st.eta2[1] = s_sub(st.eta2[1], 1.0);
+            s_mtv(t3, Xi, kn.a1); s_mtv(st.kap1, Qi, t3);
+            s_mtv(t3, Xi, kn.a2); s_mtv(st.kap2, Qi, t3);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                st.kap1[i] = s_add(st.kap1[i], A.state[(15 + i) * n_gp + gp]);
+                st.kap2[i] = s_add(st.kap2[i], A.state[(18 + i) * n_gp + gp]);
+            }
+        }
+        double X[3][3][4], smu = 0.0, n1[3], n2[3], m1[3], m2[3];
+        thickness<true>(st, lam, mu, thick, X, smu, n1, n2, m1, m2);
+        m1[2] = s_mul(drill, st.kap1[2]);
+        m2[2] = s_mul(drill, st.kap2[2]);
+        // specific strain energy through the thickness (:1150-1161)
+        double psi_t = 0.0;
+        const double jac = thick / 2.0;
+#pragma unroll 1
+        for (int q = 0; q < 3; q++) {
+            const double csi = (q == 0) ? -0.77459666924148337703585307995648 : (q == 1) ? 0.0 : 0.77459666924148337703585307995648;
+            const double al2 = (q == 1) ? 0.88888888888888888888888888888889 : 0.55555555555555555555555555555556;
+            const double zeta = thick * csi / 2.0;
+            const double g11 = st.eta1[0] + zeta * st.kap1[1], g12 = st.eta1[1] - zeta * st.kap1[0], g13 = st.eta1[2];
+            const double g21 = st.eta2[0] + zeta * st.kap2[1], g22 = st.eta2[1] - zeta * st.kap2[0], g23 = st.eta2[2];
+            const double jb = (1.0 + g11) * (1.0 + g22) - g12 * g21;
+            const double g33 = sqrt((lam + 2.0 * mu) / (lam * jb * jb + 2.0 * mu)) - 1.0;
+            const double jF = jb * (1.0 + g33);
+            const double I1 = (1.0 + g11) * (1.0 + g11) + g12 * g12 + g13 * g13 + g21 * g21 + (1.0 + g22) * (1.0 + g22) + g23 * g23 + (1.0 + g33) * (1.0 + g33);
+            const double psi = 0.5 * lam * (0.5 * (jF * jF - 1.0) - log(jF)) + 0.5 * mu * (I1 - 3.0 - 2.0 * log(jF));
+            psi_t += al2 * jac * psi;
+        }
+        energy += (fr.area / 3.0) * psi_t;                        // alpha1 (:2364), (:1326)
+        double* og = o + 1 + 24 * g;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            og[i] = st.eta1[i]; og[3 + i] = st.eta2[i]; og[6 + i] = st.kap1[i]; og[9 + i] = st.kap2[i];
+            og[12 + i] = n1[i]; og[15 + i] = n2[i]; og[18 + i] = m1[i]; og[21 + i] = m2[i];
+        }
+    }
+    o[0] = energy;
+}
+
 } // namespace shell
 
 // =========================================================================
@@ -1031,6 +1109,57 @@ __global__ void commit_kernel(EvalArgs A) {
     s_mm(Qn, Qd, Qi);
 #pragma unroll
     for (int i = 0; i < 9; i++) A.state[i * n_gp + gp] = Qn[i];
+}
+
+
+// Gauss-point results of Beam_1::Mount for WriteResults / WriteMonitor (Beam_1.cpp:444-497, :781-794,
+// :830): epsilon_r = [eta_r, kappa_r], sigma_r = D epsilon_r per point and the element's strain energy.
+// out[e * 25]: strain_energy, then per point g: epsilon_r(6) sigma_r(6).
+__global__ void results_kernel(EvalArgs A, double* out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.n_el) return;
+    int nd[3];
+#pragma unroll
+    for (int n = 0; n < 3; n++) nd[n] = __ldg(A.conn + 3 * (size_t)e + n);
+    const double* pr = A.props + BEAM_PROP_STRIDE * (size_t)__ldg(A.prop + e);
+    const size_t n_gp = (size_t)A.n_el * NGP;
+    double energy = 0.0;
+    double* o = out + (size_t)e * 25;
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++) {
+        const size_t gp = (size_t)e * NGP + g;
+        Geo go; geometry(A, e, g, nd, pr, go);
+        Kin kn; interpolate(A, nd, go, kn);
+        double Qi[9], dz[3], ki[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { dz[i] = s_add(kn.du[i], A.state[(9 + i) * n_gp + gp]); ki[i] = A.state[(12 + i) * n_gp + gp]; }
+        double gg, Qd[9], Xi[9], Q[9], Qt[9];
+        s_rodrigues(kn.a, gg, Qd, Xi);
+        s_mm(Q, Qd, Qi);
+        m_transpose(Qt, Q);
+        double eps[6], sig[6], t3[3];
+        s_mv(eps, Qt, dz);
+#pragma unroll
+        for (int i = 0; i < 3; i++) eps[i] = s_sub(eps[i], go.e3r[i]);
+        s_mtv(t3, Xi, kn.da); s_mtv(eps + 3, Qi, t3);
+#pragma unroll
+        for (int i = 0; i < 3; i++) eps[3 + i] = s_add(eps[3 + i], ki[i]);
+        double se = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            double sacc = s_mul(__ldg(pr + 6 * i), eps[0]);
+#pragma unroll
+            for (int j = 1; j < 6; j++) sacc = s_add(sacc, s_mul(__ldg(pr + 6 * i + j), eps[j]));
+            sig[i] = sacc;
+            se += sacc * eps[i];
+        }
+        energy += 0.5 * (1.0 * go.jac) * se;                      // (:830)
+#pragma unroll
+        for (int i = 0; i < 6; i++) { o[1 + 12 * g + i] = eps[i]; o[1 + 12 * g + 6 + i] = sig[i]; }
+    }
+    o[0] = energy;
 }
 
 } // namespace beam
@@ -1435,6 +1564,14 @@ void launch_beam_commit(const EvalArgs& a, void* s) {
     if (a.n_el <= 0) return;
     const long long n = (long long)a.n_el * beam::NGP;
     beam::commit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(a);
+}
+void launch_shell_results(const EvalArgs& a, double* out, void* s) {
+    if (a.n_el <= 0) return;
+    shell::results_kernel<<<(a.n_el + 127) / 128, 128, 0, (cudaStream_t)s>>>(a, out);
+}
+void launch_beam_results(const EvalArgs& a, double* out, void* s) {
+    if (a.n_el <= 0) return;
+    beam::results_kernel<<<(a.n_el + 127) / 128, 128, 0, (cudaStream_t)s>>>(a, out);
 }
 void launch_node_commit(int n_nodes, double* copy, double* disp, void* s) {
     if (n_nodes <= 0) return;

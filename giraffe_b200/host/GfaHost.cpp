@@ -372,6 +372,21 @@ bool GfaHost::GetCSR(int which, std::vector<int>& outer, std::vector<int>& inner
     return true;
 }
 
+// What WriteResults / WriteMonitor read from the elements after Mount (Shell_1.cpp:624-707,
+// Beam_1.cpp:444-497, Monitor.cpp:494): one record per element of the type, see include/gfa.h
+bool GfaHost::GetGaussPointResults(int element_type, std::vector<double>& out) {
+    const int stride = gfa_results_stride(element_type);
+    if (stride == 0) return fail("element type keeps no Gauss-point results");
+    size_t n = 0;
+    for (int t : elem_type) if (t == element_type) n++;
+    out.assign(n * stride, 0.0);
+    if (n == 0) return true;
+    const int64_t got = gfa_gauss_point_results(h, element_type, out.data(), (int64_t)out.size());
+    if (got < 0) return fail(gfa_last_error());
+    out.resize((size_t)got * stride);
+    return true;
+}
+
 bool GfaHost::GetVector(int which, std::vector<double>& v) {
     v.assign(which == GFA_P_B ? n_GL_fixed : n_GL_free, 0.0);
     if (gfa_vector(h, which, v.data()) != GFA_OK) return fail(gfa_last_error());

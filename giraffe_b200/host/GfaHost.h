@@ -16,6 +16,7 @@
 //   host.MountLoads()            Solution::MountLoads    (NodalLoad::Mount, NodalLoad.cpp:322-401, host side)
 //   host.UpdateDisps(x)          Solution::UpdateDisps   (Solution.cpp:390-402)
 //   host.SaveConfiguration()     Solution::SaveConfiguration (Solution.cpp:426-454) -> gfa_commit_state
+//   host.GetGaussPointResults()  what WriteResults / WriteMonitor read from the elements   -> gfa_gauss_point_results
 //
 // Errors follow the reference: Read* return false on a malformed block, the
 // rest report through last_error() and leave the state untouched.
@@ -81,6 +82,7 @@ public:
     // ---- global system -----------------------------------------------------------
     bool GetCSR(int which, std::vector<int>& outer, std::vector<int>& inner, std::vector<double>& values);
     bool GetVector(int which, std::vector<double>& v);
+    bool GetGaussPointResults(int element_type, std::vector<double>& out);   // strain energy + per-point strains / resultants
     double LoadFactor() const;                    // BoolTable::GetLinearFactorAtCurrentTime for a first step
     const std::string& last_error() const { return err; }
     gfa_t* handle() { return h; }

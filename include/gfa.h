@@ -165,6 +165,23 @@ int gfa_commit_state(gfa_t* h);
  *   Beam_1 : 2 x [Q_i(9) dz_i(3) kappa_i_ref(3)]                                     (src/LagrangeSave.h:11-17)
  * returns the number of doubles written. */
 int gfa_element_state(gfa_t* h, int32_t element, double* out);
+
+/* Result read-back (on demand, sampled steps only): the Gauss-point quantities
+ * Element::Mount leaves in its members for WriteResults / WriteVTK_XMLBase /
+ * WriteMonitor (src/Shell_1.cpp:624-707, src/Beam_1.cpp:444-497) and
+ * Element::strain_energy (src/Element.h:47, summed by src/Monitor.cpp:494),
+ * evaluated for the displacements of the LAST gfa_assemble call and the
+ * committed state.  One record per element of `element_type` in this rank's
+ * partition, ascending element order:
+ *   GFA_SHELL_1 (73): strain_energy, then per Gauss point g = 0..2
+ *                     eta_r1 eta_r2 kappa_r1 kappa_r2 n_r1 n_r2 m_r1 m_r2 (3 each; src/Shell_1.cpp:1017-1020,
+ *                     1146-1149, m_r*(2) = stiff_drill * kappa_r*(2) as at :1214-1217)
+ *   GFA_BEAM_1  (25): strain_energy, then per point g = 0..1 epsilon_r(6) sigma_r(6) (src/Beam_1.cpp:781-794, 830)
+ * gfa_results_stride returns the record length (0 for a type without results:
+ * Solid_1 keeps none in the reference).  `capacity` is the length of host_out
+ * in doubles; returns the number of records written or a negative error. */
+int gfa_results_stride(int element_type);
+int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* host_out, int64_t capacity);
 int gfa_copy_coordinates(gfa_t* h, double* host_out /* [n_nodes*6] */);
 
 /* Timing of the last gfa_assemble, milliseconds from CUDA events on the

@@ -105,6 +105,7 @@ struct ShellEl
 	// trial values kept by Mount for SaveLagrange (Shell_1.cpp:1650-1664)
 	M3 Q_d[3], Xi_d[3]; V3 a_x1[3], a_x2[3], u_x1[3], u_x2[3];
 	double K[27 * 27], Fint[27], P[27], energy;
+	double res[3][24];                        // eta_r1 eta_r2 kappa_r1 kappa_r2 n_r1 n_r2 m_r1 m_r2 per point (Shell_1.h:153-160)
 };
 struct BeamEl
 {
@@ -113,6 +114,7 @@ struct BeamEl
 	M3 Q_i[2]; V3 dz_i[2], k_i[2];
 	M3 Q_d[2]; V3 dz[2], kr[2];
 	double K[18 * 18], Fint[18], P[18], energy;
+	double res[2][12];                        // epsilon_r(6) sigma_r(6) per point (Beam_1.h:80-81)
 };
 struct SolidEl
 {
@@ -312,6 +314,10 @@ void shell_mount(ShellEl& s, const int* nd)
 		put(D, 9, 0, dm2e1); put(D, 9, 3, dm2k1); put(D, 9, 6, dm2e2); put(D, 9, 9, dm2k2);
 		D(5, 5) = s.stiff_drill; D(11, 11) = s.stiff_drill;
 		m1[2] = s.stiff_drill * kap1[2]; m2[2] = s.stiff_drill * kap2[2];
+		{
+			const V3* keep[8] = { &eta1, &eta2, &kap1, &kap2, &n1, &n2, &m1, &m2 };
+			for (int k = 0; k < 8; k++) for (int i = 0; i < 3; i++) s.res[g][3 * k + i] = (*keep[k])[i];
+		}
 		Mx<12, 1> sig;
 		for (int i = 0; i < 3; i++) { sig[i] = n1[i]; sig[3 + i] = m1[i]; sig[6 + i] = n2[i]; sig[9 + i] = m2[i]; }
 
@@ -472,6 +478,7 @@ void beam_mount(BeamEl& b, const int* nd)
 		K = K + (1.0 * b.jac) * (Kc + Kg);
 		F = F + (1.0 * b.jac) * ((tr(dN) * tr(B)) * sig);
 		b.energy += 0.5 * (1.0 * b.jac) * (tr(sig) * eps)[0];
+		for (int i = 0; i < 6; i++) { b.res[g][i] = eps[i]; b.res[g][6 + i] = sig[i]; }
 		b.Q_d[g] = Qd; b.dz[g] = dz; b.kr[g] = kap;
 	}
 	K = (tr(T) * K) * T;                                                     // :833-834
@@ -859,6 +866,26 @@ int gfo_get_state(int e, double* out)
 			for (int i = 0; i < 3; i++) out[w++] = b.dz_i[g][i];
 			for (int i = 0; i < 3; i++) out[w++] = b.k_i[g][i];
 		}
+	}
+	return w;
+}
+
+int gfo_get_results(int e, double* out)
+{
+	if (e < 0 || e >= (int)W.type.size()) return -1;
+	int w = 0;
+	const int ty = W.type[e];
+	if (ty == T_SHELL)
+	{
+		const ShellEl& s = W.shells[W.slot[e]];
+		out[w++] = s.energy;
+		for (int g = 0; g < 3; g++) for (int i = 0; i < 24; i++) out[w++] = s.res[g][i];
+	}
+	else if (ty == T_BEAM)
+	{
+		const BeamEl& b = W.beams[W.slot[e]];
+		out[w++] = b.energy;
+		for (int g = 0; g < 2; g++) for (int i = 0; i < 12; i++) out[w++] = b.res[g][i];
 	}
 	return w;
 }

@@ -54,6 +54,8 @@ int  gfo_csr_get(int which, int* outer, int* inner, double* val);
 int  gfo_get_vectors(double* PA, double* IA, double* PB);
 int  gfo_get_element(int e, double* K_rowmajor, double* P, double* energy);
 int  gfo_get_state(int e, double* out);
+/* Gauss-point results in the layout of gfa_gauss_point_results (include/gfa.h); returns doubles written */
+int  gfo_get_results(int e, double* out);
 int  gfo_commit(void);
 int  gfo_get_copy_coordinates(double* c6);
 

@@ -54,6 +54,7 @@ class PortOracle:
         L.gfo_get_vectors.argtypes = [_D, _D, _D]
         L.gfo_get_element.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gfo_get_state.argtypes = [C.c_int, _D]
+        L.gfo_get_results.argtypes = [C.c_int, _D]
         L.gfo_get_copy_coordinates.argtypes = [_D]
         if threads:
             L.gfo_set_threads(int(threads))
@@ -144,6 +145,13 @@ class PortOracle:
         en = C.c_double(0.0)
         self.lib.gfo_get_element(e, K.ctypes.data, P.ctypes.data, C.addressof(en))
         return K, P, en.value
+
+    def results(self, e: int) -> np.ndarray:
+        """Gauss-point results of element e after the last assemble, in the layout of
+        gfa_gauss_point_results: [strain_energy, per point strains / resultants]."""
+        buf = np.zeros(80)
+        n = self.lib.gfo_get_results(e, buf)
+        return buf[:n].copy()
 
     def state(self, e: int) -> np.ndarray:
         buf = np.zeros(64)

@@ -444,6 +444,35 @@ int ref_get_state(int e, double* out)
 	return w;
 }
 
+// Gauss-point results the elements keep after Mount for WriteResults / WriteMonitor, in the layout
+// of gfa_gauss_point_results (include/gfa.h):
+//  Shell_1 : strain_energy, 3 x [eta_r1 eta_r2 kappa_r1 kappa_r2 n_r1 n_r2 m_r1 m_r2]   (73)
+//  Beam_1  : strain_energy, 2 x [epsilon_r(6) sigma_r(6)]                                 (25)
+int ref_get_results(int e, double* out)
+{
+	Element* el = db.elements[e];
+	int w = 0;
+	if (Shell_1* s = dynamic_cast<Shell_1*>(el))
+	{
+		out[w++] = s->strain_energy;
+		for (int g = 0; g < 3; g++)
+		{
+			Matrix* v[8] = { s->eta_r1[g], s->eta_r2[g], s->kappa_r1[g], s->kappa_r2[g], s->n_r1[g], s->n_r2[g], s->m_r1[g], s->m_r2[g] };
+			for (int k = 0; k < 8; k++) for (int i = 0; i < 3; i++) out[w++] = (*v[k])(i, 0);
+		}
+	}
+	else if (Beam_1* b = dynamic_cast<Beam_1*>(el))
+	{
+		out[w++] = b->strain_energy;
+		for (int g = 0; g < 2; g++)
+		{
+			for (int i = 0; i < 6; i++) out[w++] = (*b->epsilon_r[g])(i, 0);
+			for (int i = 0; i < 6; i++) out[w++] = (*b->sigma_r[g])(i, 0);
+		}
+	}
+	return w;
+}
+
 // What Solution::SaveConfiguration does for nodes and elements
 // (reference Solution.cpp:426-454), followed by Zeros() of the increments
 // as the next time increment would (Static.cpp:191).

@@ -63,6 +63,7 @@ class RefOracle:
         L.ref_get_vectors.argtypes = [_D, _D, _D]
         L.ref_get_element.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_get_state.argtypes = [C.c_int, _D]
+        L.ref_get_results.argtypes = [C.c_int, _D]
         L.ref_set_threads.argtypes = [C.c_int]
         if threads:
             L.ref_set_threads(int(threads))
@@ -183,6 +184,13 @@ class RefOracle:
         en = C.c_double(0.0)
         self.lib.ref_get_element(e, K.ctypes.data, P.ctypes.data, C.addressof(en))
         return K, P, en.value
+
+    def results(self, e: int) -> np.ndarray:
+        """Gauss-point results of element e after the last assemble, in the layout of
+        gfa_gauss_point_results: [strain_energy, per point strains / resultants]."""
+        buf = np.zeros(80)
+        n = self.lib.ref_get_results(e, buf)
+        return buf[:n].copy()
 
     def state(self, e: int) -> np.ndarray:
         buf = np.zeros(64)

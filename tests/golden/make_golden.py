@@ -84,6 +84,8 @@ def sequence(R, m, disp_fn, name, scale2=0.6):
         z.update(util.capture(R, tag))
         K, P, en = R.element(1)
         z[f"{tag}_elem1_K"], z[f"{tag}_elem1_P"], z[f"{tag}_elem1_energy"] = K, P, np.array([en])
+        # Gauss-point results the elements keep for WriteResults / WriteMonitor (layout of gfa_gauss_point_results)
+        z[f"{tag}_results"] = np.array([R.results(e) for e in range(m.n_elements)])
         if commit_after:
             R.commit()
             z[f"{tag}_state1"] = R.state(1)

@@ -71,6 +71,9 @@ def test_sequence_against_reference_fixture(name):
         K, P = asm.element(1)
         util.assert_parity(z[f"{tag}_elem1_K"], K, f"{name} {tag} element K", util.block_scale(z[f"{tag}_elem1_K"]))
         util.assert_parity(z[f"{tag}_elem1_P"], P, f"{name} {tag} element P")
+        # result read-back: strains, stress resultants and strain energy of every element
+        etype = int(m.elem_type[0])
+        util.assert_results_parity(z[f"{tag}_results"], asm.gauss_point_results(etype), f"{name} {tag} results")
         if commit:
             asm.commit()
             util.assert_parity(z[f"{tag}_state1"], asm.state(1), f"{name} committed state")
@@ -312,3 +315,24 @@ def test_full_size_solid_block():
     asm.assemble(d)
     _translation_invariance(asm, m, "4M solids")
     asm.close()
+
+
+def test_gauss_point_results_against_oracle(port):
+    """gfa_gauss_point_results on a mixed model, before and after a state commit: the records come
+    back per element type in element order; Solid_1 keeps none (as in the reference)."""
+    m = M.concat_models([M.beam_line(37, pretension=1.0e4), M.shell_plate(7, 5, warp=0.005), M.solid_block(3, 3, 2)])
+    rng = np.random.default_rng(3)
+    asm = capi.Assembler(m).set_dofs()
+    port.load(m)
+    for it in range(2):
+        d = M.mask_displacements(m, rng.uniform(-2e-4, 2e-4, (m.n_nodes, 6)))
+        port.assemble(d)
+        asm.assemble(d)
+        for etype in (M.BEAM_1, M.SHELL_1):
+            ids = np.nonzero(m.elem_type == etype)[0]
+            ref = np.array([port.results(int(e)) for e in ids])
+            util.assert_results_parity(ref, asm.gauss_point_results(etype), f"iteration {it} type {etype}")
+        port.commit()
+        asm.commit()
+    with pytest.raises(capi.GfaError):
+        asm.gauss_point_results(M.SOLID_1)

@@ -59,6 +59,8 @@ def test_sequence_with_commit(port, name):
         util.assert_parity(z[f"{tag}_elem1_K"], K, f"{name} {tag} element K", util.block_scale(z[f"{tag}_elem1_K"]))
         util.assert_parity(z[f"{tag}_elem1_P"], P, f"{name} {tag} element P")
         assert abs(en - z[f"{tag}_elem1_energy"][0]) <= 1e-12 * abs(en) + 1e-300
+        # Gauss-point results kept for WriteResults / WriteMonitor (Shell_1.cpp:624-707, Beam_1.cpp:444-497)
+        util.assert_results_parity(z[f"{tag}_results"], np.array([port.results(e) for e in range(m.n_elements)]), f"{name} {tag} results")
         if commit:
             port.commit()
             util.assert_parity(z[f"{tag}_state1"], port.state(1), f"{name} committed state")
