@@ -49,6 +49,7 @@ class _ModelStruct(C.Structure):
         ("elem_nodes", C.c_void_p), ("beam_pretension", C.c_void_p),
         ("gravity_on", C.c_int32), ("gravity", C.c_double * 3),
         ("part_rank", C.c_int32), ("part_world", C.c_int32),
+        ("n_pipe_sections", C.c_int32), ("pipe_sections", C.c_void_p),
     ]
 
 
@@ -143,6 +144,8 @@ class Assembler:
         g = model.gravity if model.gravity is not None else (0.0, 0.0, 0.0)
         ms.gravity = (C.c_double * 3)(*[float(v) for v in g])
         ms.part_rank, ms.part_world = rank, world
+        pipes = arr(np.asarray(getattr(model, 'pipe_sections', np.zeros((0, 11))), float).reshape(-1, 11), np.float64)
+        ms.n_pipe_sections, ms.pipe_sections = len(pipes), _ptr(pipes) if len(pipes) else None
         self._check(self.lib.gfa_create(C.byref(ms), device, C.byref(self._h)))
         self.n_free = self.n_fixed = 0
         self.gravity_factor = 1.0

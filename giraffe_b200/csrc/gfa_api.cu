@@ -70,7 +70,9 @@ const TypeInfo kTypes[3] = {
 // doubles per element in the Ke arena: Shell_1 stores the upper triangle plus the non-symmetric
 // rotation corner in sector-padded groups (gfa_device.h: shell_stored_offset), the others every block
 inline int arena_doubles(int slot) { return slot == 0 ? SHELL_ARENA : kTypes[slot].ndof * kTypes[slot].ndof; }
-inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : t == GFA_BEAM_1 ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
+// Pipe_1 shares the Beam_1 block: same Mount / MountGlobal / SaveLagrange (Pipe_1.cpp:836-974, 1027-1104),
+// other constants (PreCalc, Pipe_1.cpp:1106-1146)
+inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : (t == GFA_BEAM_1 || t == GFA_PIPE_1) ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
 // local 3-DOF block -> (local node, DOF group 0 = translations / 1 = rotations)
 // in the reference's local DOF order (Shell_1.cpp:1523-1557, Beam_1.cpp:1439-1444)
 inline void block_node(int slot, int b, int& a, int& grp) {
@@ -214,14 +216,14 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
     }
     for (int e = 0; e < m->n_elements; e++) {
         int s = type_slot(h->el_type[e]);
-        if (s < 0) FAIL_FREE(GFA_EUNSUPPORTED, "element %d: type %d has no kernel (Beam_1=1, Shell_1=3, Solid_1=7)", e + 1, h->el_type[e]);
+        if (s < 0) FAIL_FREE(GFA_EUNSUPPORTED, "element %d: type %d has no kernel (Beam_1=1, Pipe_1=2, Shell_1=3, Solid_1=7)", e + 1, h->el_type[e]);
         if (h->el_ptr[e + 1] - h->el_ptr[e] != kTypes[s].nn) FAIL_FREE(GFA_EINVAL, "element %d: expected %d nodes", e + 1, kTypes[s].nn);
         const int* nd = &h->el_nodes[h->el_ptr[e]];
         for (int a = 0; a < kTypes[s].nn; a++)
             for (int b = a + 1; b < kTypes[s].nn; b++)
                 if (nd[a] == nd[b]) FAIL_FREE(GFA_EINVAL, "element %d repeats node %d", e + 1, nd[a] + 1);
         int mat = m->elem_material[e];
-        if (mat < 1 || mat > m->n_materials) FAIL_FREE(GFA_EINVAL, "element %d: material %d out of range", e + 1, mat);
+        if (h->el_type[e] != GFA_PIPE_1 && (mat < 1 || mat > m->n_materials)) FAIL_FREE(GFA_EINVAL, "element %d: material %d out of range", e + 1, mat);
         h->type_count[s]++;
     }
     // ---- partition: contiguous range of every type's elements ----------
@@ -258,6 +260,10 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
             if (s == 0) {
                 if (sec < 1 || sec > m->n_shell_sections) FAIL_FREE(GFA_EINVAL, "shell element %d: shell section %d out of range", e + 1, sec);
                 key = { mat, sec };
+            } else if (s == 1 && h->el_type[e] == GFA_PIPE_1) {
+                if (sec < 1 || sec > m->n_pipe_sections || !m->pipe_sections) FAIL_FREE(GFA_EINVAL, "pipe element %d: pipe section %d out of range", e + 1, sec);
+                if (cs < 1 || cs > m->n_cs) FAIL_FREE(GFA_EINVAL, "pipe element %d: CS %d out of range", e + 1, cs);
+                key = { -1, sec, cs };
             } else if (s == 1) {
                 if (sec < 1 || sec > m->n_sections) FAIL_FREE(GFA_EINVAL, "beam element %d: section %d out of range", e + 1, sec);
                 if (cs < 1 || cs > m->n_cs) FAIL_FREE(GFA_EINVAL, "beam element %d: CS %d out of range", e + 1, cs);
@@ -268,13 +274,23 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
             if (it == combos.end()) {
                 const int id = (int)combos.size();
                 combos[key] = id;
-                const double E = m->hooke[3 * (mat - 1)], nu = m->hooke[3 * (mat - 1) + 1], rho = m->hooke[3 * (mat - 1) + 2];
+                const bool pipe = h->el_type[e] == GFA_PIPE_1;
+                const double E = pipe ? 0.0 : m->hooke[3 * (mat - 1)], nu = pipe ? 0.0 : m->hooke[3 * (mat - 1) + 1], rho = pipe ? 0.0 : m->hooke[3 * (mat - 1) + 2];
                 if (s == 0) {           // Shell_1::PreCalc, Shell_1.cpp:2016-2021
                     const double th = m->shell_thickness[sec - 1];
                     const double mu = E / (2.0 * (1 + nu));
                     const double lambda = 2.0 * mu * nu / (1 - 2.0 * nu);
                     const double row[SHELL_PROP_STRIDE] = { lambda, mu, th, E * th * th * th, rho };
                     t.props.insert(t.props.end(), row, row + SHELL_PROP_STRIDE);
+                } else if (s == 1 && pipe) {   // Pipe_1::PreCalc, Pipe_1.cpp:1108-1114, 1130-1133
+                    const double* ps = m->pipe_sections + 11 * (size_t)(sec - 1);      // EA EI GJ GA Rho ...
+                    double row[BEAM_PROP_STRIDE];
+                    for (int i = 0; i < BEAM_PROP_STRIDE; i++) row[i] = 0.0;
+                    row[0] = ps[3]; row[7] = ps[3]; row[14] = ps[0]; row[21] = ps[1]; row[28] = ps[1]; row[35] = ps[2];
+                    for (int i = 0; i < 9; i++) row[36 + i] = m->cs[9 * (size_t)(cs - 1) + i];
+                    row[45] = ps[4];            // mass per unit length (gravity: Pipe_1.cpp:1311-1330 without ocean data)
+                    row[46] = 0.0;              // Pipe_1::Mount leaves strain_energy at zero
+                    t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
                 } else if (s == 1) {    // Beam_1::PreCalc, Beam_1.cpp:560-580
                     const double* sc = m->sections + 6 * (size_t)(sec - 1);
                     const double G = E / (2 * (1 + nu)), sf = 1.0;
@@ -284,6 +300,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
                     row[21] = E * sc[1]; row[28] = E * sc[2]; row[22] = E * sc[3]; row[27] = E * sc[3]; row[35] = G * sc[5];
                     for (int i = 0; i < 9; i++) row[36 + i] = m->cs[9 * (size_t)(cs - 1) + i];
                     row[45] = rho * sc[0];
+                    row[46] = 1.0;
                     t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
                 } else {                // builder-defined Solid_1: Lame constants of the Hooke material
                     const double mu = E / (2.0 * (1 + nu));
@@ -990,7 +1007,7 @@ int gfa_element_state(gfa_t* h, int32_t e, double* out) {
 }
 
 int gfa_results_stride(int element_type) {
-    return element_type == GFA_SHELL_1 ? SHELL_RESULTS : element_type == GFA_BEAM_1 ? BEAM_RESULTS : 0;
+    return element_type == GFA_SHELL_1 ? SHELL_RESULTS : (element_type == GFA_BEAM_1 || element_type == GFA_PIPE_1) ? BEAM_RESULTS : 0;
 }
 
 int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* out, int64_t capacity) {
@@ -1000,8 +1017,10 @@ int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* out, int64_t
     if (s < 0 || stride == 0) return fail(GFA_EUNSUPPORTED, "element type %d keeps no Gauss-point results", element_type);
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_gauss_point_results before gfa_assemble");
     const size_t n = h->tb[s].elems.size();
-    if ((int64_t)(n * stride) > capacity) return fail(GFA_EINVAL, "gfa_gauss_point_results: %zu records of %d doubles need capacity %zu, got %lld", n, stride, n * stride, (long long)capacity);
-    if (n == 0) return 0;
+    size_t n_out = 0;                      // Beam_1 and Pipe_1 share a block: hand back the asked type only
+    for (size_t k = 0; k < n; k++) if (h->el_type[h->tb[s].elems[k]] == element_type) n_out++;
+    if ((int64_t)(n_out * stride) > capacity) return fail(GFA_EINVAL, "gfa_gauss_point_results: %zu records of %d doubles need capacity %zu, got %lld", n_out, stride, n_out * stride, (long long)capacity);
+    if (n_out == 0) return 0;
     CUDA_TRY(cudaSetDevice(h->device));
     DevBuf<double> d;
     cudaError_t e = d.alloc(n * stride);
@@ -1009,9 +1028,18 @@ int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* out, int64_t
     const EvalArgs ea = eval_args(h, s, 0.0);
     if (s == 0) launch_shell_results(ea, d.p, h->stream); else launch_beam_results(ea, d.p, h->stream);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out, d.p, n * stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return (int64_t)n;
+    if (n_out == n) {
+        CUDA_TRY(cudaMemcpyAsync(out, d.p, n * stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+        std::vector<double> all(n * stride);
+        CUDA_TRY(cudaMemcpyAsync(all.data(), d.p, n * stride * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        size_t w = 0;
+        for (size_t k = 0; k < n; k++)
+            if (h->el_type[h->tb[s].elems[k]] == element_type) { std::memcpy(out + w * stride, all.data() + k * stride, stride * sizeof(double)); w++; }
+    }
+    return (int64_t)n_out;
 }
 
 int gfa_copy_coordinates(gfa_t* h, double* out) {

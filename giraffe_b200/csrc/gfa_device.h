@@ -29,7 +29,7 @@ struct EvalArgs {
 };
 
 constexpr int SHELL_PROP_STRIDE = 5;   // lambda, mu, thickness, stiff_drill, rho
-constexpr int BEAM_PROP_STRIDE = 46;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A
+constexpr int BEAM_PROP_STRIDE = 47;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A, strain-energy switch (1 Beam_1, 0 Pipe_1)
 constexpr int SOLID_PROP_STRIDE = 3;   // lambda, mu, rho
 
 constexpr int SHELL_RESULTS = 73;      // strain_energy + 3 x (eta1 eta2 kappa1 kappa2 n1 n2 m1 m2)

@@ -1155,7 +1155,7 @@ __global__ void results_kernel(EvalArgs A, double* out) {
             sig[i] = sacc;
             se += sacc * eps[i];
         }
-        energy += 0.5 * (1.0 * go.jac) * se;                      // (:830)
+        energy += __ldg(pr + 46) * (0.5 * (1.0 * go.jac) * se);   // (:830); Pipe_1::Mount has no such line
 #pragma unroll
         for (int i = 0; i < 6; i++) { o[1 + 12 * g + i] = eps[i]; o[1 + 12 * g + 6 + i] = sig[i]; }
     }

@@ -31,7 +31,7 @@ std::vector<std::string> tokenize(const std::string& text) {
 }
 
 bool is_top(const std::string& s) {
-    static const char* k[] = { "Nodes", "Elements", "Materials", "Sections", "ShellSections", "CoordinateSystems", "NodeSets",
+    static const char* k[] = { "Nodes", "Elements", "Materials", "Sections", "PipeSections", "ShellSections", "CoordinateSystems", "NodeSets",
         "Constraints", "Loads", "Environment", "SolutionSteps", "SolverOptions", "Monitor", "PostFiles",
         "ConvergenceCriteria", "ElementSets", "ExecutionData", "EOF" };
     for (const char* w : k) if (s == w) return true;
@@ -92,6 +92,16 @@ bool GfaHost::ReadFile(const char* path) {
                 i += 6;
                 if (i < tk.size() && tk[i] == "AD") i += 7;
             }
+        } else if (kw == "PipeSections") {     // IO::ReadPipeSections (IO.cpp:1282-1305), PipeSection::Read
+            const int n = integer(i + 1); i += 2;
+            static const char* names[11] = { "EA", "EI", "GJ", "GA", "Rho", "CDt", "CDn", "CAt", "CAn", "De", "Di" };
+            for (int r = 0; r < n; r++, i += 24) {
+                if (tk[i] != "PS") return fail("Error reading Pipe Section " + std::to_string(r + 1));
+                for (int k = 0; k < 11; k++) {
+                    if (tk[i + 2 + 2 * k] != names[k]) return fail("Error reading Pipe Section " + std::to_string(r + 1));
+                    pipe_sections.push_back(num(i + 3 + 2 * k));
+                }
+            }
         } else if (kw == "ShellSections") {
             const int n = integer(i + 1); i += 2;
             for (int r = 0; r < n; r++, i += 4) {
@@ -119,11 +129,14 @@ bool GfaHost::ReadFile(const char* path) {
             const int n = integer(i + 1); i += 2;
             for (int r = 0; r < n; r++) {
                 const std::string& ty = tk[i];
-                int type = 0, nn = 0, mat = integer(i + 3), sec = 0, c = 0;
+                int type = 0, nn = 0, mat = ty == "Pipe_1" ? 0 : integer(i + 3), sec = 0, c = 0;
                 double T0 = 0.0;
                 size_t nodes_at = 0;
                 if (ty == "Beam_1") { type = GFA_BEAM_1; nn = 3; sec = integer(i + 5); c = integer(i + 7); nodes_at = i + 9; i += 12;
                     if (i < tk.size() && tk[i] == "PreTension") { T0 = num(i + 1); i += 2; } }
+                else if (ty == "Pipe_1") {      // Pipe_1 id PipeSec s CS c Nodes a b c (Pipe_1.cpp:535-572)
+                    if (tk[i + 2] != "PipeSec" || tk[i + 4] != "CS" || tk[i + 6] != "Nodes") return fail("Error reading Pipe_1 element");
+                    type = GFA_PIPE_1; nn = 3; sec = integer(i + 3); c = integer(i + 5); nodes_at = i + 7; i += 10; }
                 else if (ty == "Shell_1") { type = GFA_SHELL_1; nn = 6; sec = integer(i + 5); i += 6;
                     if (tk[i] == "CS") { c = integer(i + 1); i += 2; }
                     nodes_at = i + 1; i += 7; }
@@ -236,6 +249,7 @@ bool GfaHost::PreCalc(int device) {
     m.gravity_on = g_exist ? 1 : 0;
     for (int k = 0; k < 3; k++) m.gravity[k] = G[k];
     m.part_rank = 0; m.part_world = 1;
+    m.n_pipe_sections = (int)(pipe_sections.size() / 11); m.pipe_sections = pipe_sections.empty() ? nullptr : pipe_sections.data();
     gfa_destroy(h); h = nullptr;
     if (gfa_create(&m, device, &h) != GFA_OK) return fail(gfa_last_error());
     return true;
@@ -252,7 +266,7 @@ void GfaHost::DOFsActive() {
         for (int a = 0; a < nn; a++) {
             const size_t nd = (size_t)(elem_nodes[elem_node_ptr[e] + a] - 1);
             for (int k = 0; k < 3; k++) active_GL[6 * nd + k] = 1;
-            const bool rot = elem_type[e] == GFA_BEAM_1 || (elem_type[e] == GFA_SHELL_1 && a > 2);   // Shell_1.cpp:51-68
+            const bool rot = elem_type[e] == GFA_BEAM_1 || elem_type[e] == GFA_PIPE_1 || (elem_type[e] == GFA_SHELL_1 && a > 2);   // Shell_1.cpp:51-68
             if (rot) for (int k = 3; k < 6; k++) active_GL[6 * nd + k] = 1;
         }
     }

@@ -45,6 +45,7 @@ public:
     std::vector<double> section_defs;             // [s][3]   kind(0 Rectangle,1 Tube) a b
     std::vector<double> sections;                 // [s][6]   A I11 I22 I12 I33 It (after PreCalc)
     std::vector<double> shell_thickness;
+    std::vector<double> pipe_sections;            // [p][11]  EA EI GJ GA Rho CDt CDn CAt CAn De Di (PipeSection.h:13-23)
     std::vector<double> cs_defs;                  // [c][6]   E1 E3 as read
     std::vector<double> cs;                       // [c][9]   E1 E2 E3 normalised
     std::vector<int> elem_type, elem_material, elem_section, elem_cs, elem_node_ptr, elem_nodes;

@@ -5,8 +5,8 @@ Tokens are whitespace separated; ``//`` and ``/* */`` comments may appear
 between records; a block is ``Keyword N`` followed by N records.  Blocks the
 assembly path does not consume (SolverOptions, Monitor, PostFiles,
 ConvergenceCriteria, ...) are skipped up to the next known keyword.
-Supported: Nodes, Elements (Beam_1 / Shell_1 / Solid_1), Materials (Hooke),
-Sections (Rectangle / Tube), ShellSections (Homogeneous), CoordinateSystems,
+Supported: Nodes, Elements (Beam_1 / Pipe_1 / Shell_1 / Solid_1), Materials (Hooke),
+Sections (Rectangle / Tube), PipeSections (PS), ShellSections (Homogeneous), CoordinateSystems,
 NodeSets (List / Sequence), Constraints (NodalConstraint), Loads (NodalLoad
 with a numeric table), Environment (GravityData), SolutionSteps (Static, for
 the time-stepping data only).
@@ -17,9 +17,9 @@ import re
 
 import numpy as np
 
-from .meshes import BEAM_1, SHELL_1, SOLID_1, Model, _finish
+from .meshes import BEAM_1, PIPE_1, SHELL_1, SOLID_1, Model, _finish
 
-_TOP = {"Nodes", "Elements", "Materials", "Sections", "ShellSections", "CoordinateSystems", "NodeSets",
+_TOP = {"Nodes", "Elements", "Materials", "Sections", "PipeSections", "ShellSections", "CoordinateSystems", "NodeSets",
         "Constraints", "Loads", "Environment", "SolutionSteps", "SolverOptions", "Monitor", "PostFiles",
         "ConvergenceCriteria", "ElementSets", "ExecutionData", "EOF"}
 
@@ -36,7 +36,7 @@ def read_inp(path: str):
     with open(path, "r", errors="replace") as f:
         tk = _tokens(f.read())
     i = 0
-    nodes, mats, secs, shsecs, csd = {}, {}, {}, {}, {}
+    nodes, mats, secs, shsecs, csd, pipes = {}, {}, {}, {}, {}, {}
     elems, nodesets, cons, loads = [], {}, [], []
     gravity = None
     info = {}
@@ -66,6 +66,13 @@ def read_inp(path: str):
                 secs[int(tk[i + 1])] = (kind, num(i + 3), num(i + 5)); i += 6
                 if i < len(tk) and tk[i] == "AD":
                     i += 7
+        elif kw == "PipeSections":          # PS id EA v EI v GJ v GA v Rho v CDt v CDn v CAt v CAn v De v Di v (PipeSection.cpp Read)
+            n = int(tk[i + 1]); i += 2
+            for _ in range(n):
+                assert tk[i] == "PS", f"unsupported pipe section record {tk[i]}"
+                names = [tk[i + 2 + 2 * k] for k in range(11)]
+                assert names == ["EA", "EI", "GJ", "GA", "Rho", "CDt", "CDn", "CAt", "CAn", "De", "Di"], names
+                pipes[int(tk[i + 1])] = tuple(num(i + 3 + 2 * k) for k in range(11)); i += 24
         elif kw == "ShellSections":
             n = int(tk[i + 1]); i += 2
             for _ in range(n):
@@ -96,6 +103,11 @@ def read_inp(path: str):
                     i += 12
                     if i < len(tk) and tk[i] == "PreTension":
                         e["T0"] = num(i + 1); i += 2
+                elif ty == "Pipe_1":        # Pipe_1 id PipeSec s CS c Nodes a b c (Pipe_1.cpp:535-572)
+                    assert tk[i + 2] == "PipeSec" and tk[i + 4] == "CS" and tk[i + 6] == "Nodes"
+                    e = dict(type=PIPE_1, mat=0, sec=int(tk[i + 3]), cs=int(tk[i + 5]),
+                             nodes=[int(t) for t in tk[i + 7:i + 10]], T0=0.0)
+                    i += 10
                 elif ty == "Shell_1":
                     e = dict(type=SHELL_1, mat=int(tk[i + 3]), sec=int(tk[i + 5]), cs=0, T0=0.0)
                     i += 6
@@ -154,7 +166,8 @@ def read_inp(path: str):
 
     nn = max(nodes)
     xyz = np.array([nodes[k] for k in range(1, nn + 1)], float)
-    m = Model(xyz=xyz, hooke=np.array([mats[k] for k in sorted(mats)], float), sections=np.zeros((0, 6)))
+    m = Model(xyz=xyz, hooke=np.array([mats[k] for k in sorted(mats)], float).reshape(-1, 3), sections=np.zeros((0, 6)))
+    m.pipe_sections = np.array([pipes[k] for k in sorted(pipes)], float).reshape(-1, 11)
     m.section_defs = [secs[k] for k in sorted(secs)]
     m.shell_thickness = np.array([shsecs[k] for k in sorted(shsecs)], float)
     m.cs_defs = [csd[k] for k in sorted(csd)]
@@ -198,13 +211,20 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
                 if m.pretension is not None and m.pretension[e] != 0.0:
                     f.write(f"\tPreTension\t{float(m.pretension[e])!r}")
                 f.write("\n")
+            elif t == PIPE_1:
+                f.write(f"Pipe_1\t{e + 1}\tPipeSec\t{m.elem_sec[e]}\tCS\t{m.elem_cs[e]}\tNodes\t{nd}\n")
             elif t == SHELL_1:
                 f.write(f"Shell_1\t{e + 1}\tMat\t{m.elem_mat[e]}\tSec\t{m.elem_sec[e]}\tNodes\t{nd}\n")
             else:
                 f.write(f"Solid_1\t{e + 1}\tMat\t{m.elem_mat[e]}\tCS\t{m.elem_cs[e]}\tNodes\t{nd}\n")
-        f.write(f"\nMaterials\t{len(m.hooke)}\n")
-        for k, (E, nu, rho) in enumerate(m.hooke):
-            f.write(f"Hooke\t{k + 1}\tE\t{float(E)!r}\tNu\t{float(nu)!r}\tRho\t{float(rho)!r}\n")
+        if len(m.hooke):
+            f.write(f"\nMaterials\t{len(m.hooke)}\n")
+            for k, (E, nu, rho) in enumerate(m.hooke):
+                f.write(f"Hooke\t{k + 1}\tE\t{float(E)!r}\tNu\t{float(nu)!r}\tRho\t{float(rho)!r}\n")
+        if len(m.pipe_sections):
+            f.write(f"\nPipeSections\t{len(m.pipe_sections)}\n")
+            for k, row in enumerate(np.asarray(m.pipe_sections, float).reshape(-1, 11)):
+                f.write(f"PS\t{k + 1}\t" + "\t".join(f"{nm}\t{_r(v)}" for nm, v in zip(("EA", "EI", "GJ", "GA", "Rho", "CDt", "CDn", "CAt", "CAn", "De", "Di"), row)) + "\n")
         if m.section_defs:
             f.write(f"\nSections\t{len(m.section_defs)}\n")
             for k, (kind, a, b) in enumerate(m.section_defs):

@@ -22,10 +22,11 @@ from dataclasses import dataclass, field
 import numpy as np
 
 BEAM_1 = 1
+PIPE_1 = 2       # evaluated by the Beam_1 kernel (Pipe_1::Mount is Beam_1::Mount, Pipe_1.cpp:836-974)
 SHELL_1 = 3
 SOLID_1 = 7
-NODES_PER_TYPE = {BEAM_1: 3, SHELL_1: 6, SOLID_1: 8}
-DOFS_PER_TYPE = {BEAM_1: 18, SHELL_1: 27, SOLID_1: 24}
+NODES_PER_TYPE = {BEAM_1: 3, PIPE_1: 3, SHELL_1: 6, SOLID_1: 8}
+DOFS_PER_TYPE = {BEAM_1: 18, PIPE_1: 18, SHELL_1: 27, SOLID_1: 24}
 
 
 @dataclass
@@ -47,6 +48,8 @@ class Model:
     constraints: list = field(default_factory=list)   # [(node ids 1-based, mask)]
     gravity: tuple | None = None
     nodal_loads: list = field(default_factory=list)   # [(node ids, cs id, table[n,7])]
+    # [n, 11] EA EI GJ GA Rho CDt CDn CAt CAn De Di (PipeSection.h:13-23); Pipe_1's elem_sec points here
+    pipe_sections: np.ndarray = field(default_factory=lambda: np.zeros((0, 11)))
 
     @property
     def n_nodes(self) -> int:
@@ -154,6 +157,21 @@ def beam_line_displacements(m: Model, seed: int = 20240001) -> np.ndarray:
     d[:, 3:] = rng.uniform(-1e-2, 1e-2, (m.n_nodes, 3))
     d[0, :] = 0.0  # clamped node
     return d
+
+
+def pipe_line(n_elements: int = 1000, spacing: float = 0.5,
+              pipe_section=(1.2e9, 6.0e7, 4.6e7, 4.6e8, 180.0, 0.1, 1.2, 0.0, 1.0, 0.65, 0.55), gravity=None) -> Model:
+    """A straight Pipe_1 riser segment on the Z axis (same topology as beam_line): PipeSection constants
+    EA EI GJ GA Rho CDt CDn CAt CAn De Di, no material (Pipe_1.cpp:535-572, PipeSection.cpp)."""
+    m = beam_line(n_elements, spacing)
+    m.hooke = np.zeros((0, 3))
+    m.section_defs = []
+    m.pipe_sections = np.array([pipe_section], float)
+    m.elem_type = np.full(n_elements, PIPE_1, np.int32)
+    m.elem_mat = np.zeros(n_elements, np.int32)
+    m.pretension = None
+    m.gravity = gravity
+    return _finish(m)
 
 
 # --------------------------------------------------------------------------
@@ -292,19 +310,22 @@ def solid_block_displacements(m: Model, seed: int = 20240003, amp: float = 1e-4)
 def concat_models(parts: list[Model]) -> Model:
     xyz, et, em, es, ec, en = [], [], [], [], [], []
     hooke, secdefs, thick, csdefs, cons = [], [], [], [], []
+    pipes = []
     pret = []
     node_off = 0
     for p in parts:
-        mo, so, to, co = len(hooke), len(secdefs), len(thick), len(csdefs)
+        mo, so, to, co, po = len(hooke), len(secdefs), len(thick), len(csdefs), len(pipes)
         xyz.append(p.xyz)
         hooke.extend(p.hooke.tolist())
         secdefs.extend(p.section_defs)
         thick.extend(p.shell_thickness.tolist())
         csdefs.extend(p.cs_defs)
+        pipes.extend(np.asarray(p.pipe_sections, float).reshape(-1, 11).tolist())
         et.append(p.elem_type)
-        em.append(p.elem_mat + mo)
+        em.append(np.where(p.elem_mat > 0, p.elem_mat + mo, 0))
         is_shell = p.elem_type == SHELL_1
-        es.append(np.where(is_shell, p.elem_sec + to, np.where(p.elem_sec > 0, p.elem_sec + so, 0)).astype(np.int32))
+        is_pipe = p.elem_type == PIPE_1
+        es.append(np.where(is_shell, p.elem_sec + to, np.where(is_pipe, p.elem_sec + po, np.where(p.elem_sec > 0, p.elem_sec + so, 0))).astype(np.int32))
         ec.append(np.where(p.elem_cs > 0, p.elem_cs + co, 0).astype(np.int32))
         en.append(p.elem_nodes + node_off)
         pret.append(p.pretension if p.pretension is not None else np.zeros(p.n_elements))
@@ -315,6 +336,7 @@ def concat_models(parts: list[Model]) -> Model:
     m.section_defs = secdefs
     m.shell_thickness = np.array(thick, float)
     m.cs_defs = csdefs
+    m.pipe_sections = np.array(pipes, float).reshape(-1, 11)
     m.elem_type = np.concatenate(et).astype(np.int32)
     m.elem_mat = np.concatenate(em).astype(np.int32)
     m.elem_sec = np.concatenate(es).astype(np.int32)
@@ -341,7 +363,7 @@ def number_dofs(m: Model):
     local = np.arange(m.elem_nodes.size) - np.repeat(m.elem_ptr[:-1], np.diff(m.elem_ptr))
     nodes0 = m.elem_nodes.astype(np.int64) - 1
     active[nodes0, 0:3] = True
-    rot = (conn_type == BEAM_1) | ((conn_type == SHELL_1) & (local >= 3))
+    rot = (conn_type == BEAM_1) | (conn_type == PIPE_1) | ((conn_type == SHELL_1) & (local >= 3))
     active[nodes0[rot], 3:6] = True
     mask = m.constraint_mask()
     fixed = ((mask[:, None] >> np.arange(6)[None, :]) & 1).astype(bool)

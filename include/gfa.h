@@ -31,6 +31,7 @@ extern "C" {
 
 /* element type ids = the reference's (src/Element.h:8-15) */
 #define GFA_BEAM_1  1
+#define GFA_PIPE_1  2   /* evaluated by the Beam_1 kernel: Pipe_1::Mount is Beam_1::Mount (src/Pipe_1.cpp:836-974) */
 #define GFA_SHELL_1 3
 #define GFA_SOLID_1 7
 
@@ -77,9 +78,9 @@ typedef struct gfa_model {
     const double* cs;                /* [n_cs*9] E1,E2,E3 normalised (src/CoordinateSystem.h:13-17) */
 
     int32_t n_elements;
-    const int32_t* elem_type;        /* [n_elements] GFA_BEAM_1 / GFA_SHELL_1 / GFA_SOLID_1 */
+    const int32_t* elem_type;        /* [n_elements] GFA_BEAM_1 / GFA_PIPE_1 / GFA_SHELL_1 / GFA_SOLID_1 */
     const int32_t* elem_material;    /* Element::material */
-    const int32_t* elem_section;     /* Element::section (beam: Sections id, shell: ShellSections id, solid: unused) */
+    const int32_t* elem_section;     /* Element::section (beam: Sections id, pipe: PipeSections id, shell: ShellSections id, solid: unused) */
     const int32_t* elem_cs;          /* Element::cs (beam; shells with homogeneous sections ignore it) */
     const int32_t* elem_node_ptr;    /* [n_elements+1] offsets into elem_nodes */
     const int32_t* elem_nodes;       /* Element::nodes, 1-based */
@@ -93,6 +94,10 @@ typedef struct gfa_model {
      * is derived from (rank, world); single-GPU callers pass 0 and 1. */
     int32_t part_rank;
     int32_t part_world;
+
+    int32_t n_pipe_sections;
+    const double* pipe_sections;     /* [n_pipe_sections*11] EA EI GJ GA Rho CDt CDn CAt CAn De Di (src/PipeSection.h:13-23);
+                                      * Pipe_1 has no material: elem_material is ignored for it */
 } gfa_model_t;
 
 /* Per-iteration inputs (src/Static.cpp:200-212; src/Solution.cpp:390-402). */
@@ -177,6 +182,7 @@ int gfa_element_state(gfa_t* h, int32_t element, double* out);
  *                     eta_r1 eta_r2 kappa_r1 kappa_r2 n_r1 n_r2 m_r1 m_r2 (3 each; src/Shell_1.cpp:1017-1020,
  *                     1146-1149, m_r*(2) = stiff_drill * kappa_r*(2) as at :1214-1217)
  *   GFA_BEAM_1  (25): strain_energy, then per point g = 0..1 epsilon_r(6) sigma_r(6) (src/Beam_1.cpp:781-794, 830)
+ *   GFA_PIPE_1  (25): the same record; strain_energy is 0 as in the reference (Pipe_1::Mount never adds to it)
  * gfa_results_stride returns the record length (0 for a type without results:
  * Solid_1 keeps none in the reference).  `capacity` is the length of host_out
  * in doubles; returns the number of records written or a negative error. */

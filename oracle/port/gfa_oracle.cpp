@@ -91,7 +91,7 @@ M3 dVop(const V3& x, const V3& dx, const V3& t, double alpha)
 // ------------------------------------------------------------------------
 // model tables
 // ------------------------------------------------------------------------
-enum { T_BEAM = 1, T_SHELL = 3, T_SOLID = 7 };
+enum { T_BEAM = 1, T_PIPE = 2, T_SHELL = 3, T_SOLID = 7 };    // Pipe_1 is held as a BeamEl: same Mount (Pipe_1.cpp:836-974)
 
 struct ShellEl
 {
@@ -114,6 +114,7 @@ struct BeamEl
 	M3 Q_i[2]; V3 dz_i[2], k_i[2];
 	M3 Q_d[2]; V3 dz[2], kr[2];
 	double K[18 * 18], Fint[18], P[18], energy;
+	bool energy_on;                           // Pipe_1::Mount never adds to strain_energy
 	double res[2][12];                        // epsilon_r(6) sigma_r(6) per point (Beam_1.h:80-81)
 };
 struct SolidEl
@@ -126,9 +127,10 @@ struct World
 {
 	int n_nodes = 0;
 	std::vector<double> ref, copy;            // [n][3], [n][6]
-	std::vector<double> hooke, sec, thick, cs;
+	std::vector<double> hooke, sec, thick, cs, pipe;
 	int n_el = 0;
 	std::vector<int> type, mat, secid, csid, nptr, nodes;
+	std::vector<char> is_pipe;
 	std::vector<double> pret;
 	int g_on = 0; double g[3] = { 0, 0, 0 };
 	std::vector<int> cmask, gls;
@@ -401,6 +403,7 @@ void beam_precalc(BeamEl& b, const int* nd, const double* hk, const double* sc, 
 	b.D(0, 0) = sf * G * A; b.D(1, 1) = sf * G * A; b.D(2, 2) = E * A;
 	b.D(3, 3) = E * I1; b.D(4, 4) = E * I2; b.D(3, 4) = E * I12; b.D(4, 3) = E * I12; b.D(5, 5) = G * It;
 	b.rhoA = rho * A;
+	b.energy_on = true;
 	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) b.T3(i, j) = cs[3 * i + j];
 	V3 e3 = Xv(nd[2]) - Xv(nd[0]);
 	e3 = (1.0 / norm(e3)) * e3;
@@ -417,6 +420,18 @@ void beam_precalc(BeamEl& b, const int* nd, const double* hk, const double* sc, 
 		b.dN[g][0] = (1.0 / b.jac) * (xi - 0.5); b.dN[g][1] = (1.0 / b.jac) * (-2.0 * xi); b.dN[g][2] = (1.0 / b.jac) * (0.5 + xi);
 		b.Q_i[g] = eye3(); b.dz_i[g] = vec(0, 0, 1.0 + du0); b.k_i[g] = V3();
 	}
+}
+
+// Pipe_1::PreCalc (Pipe_1.cpp:1106-1180): D = diag(GA, GA, EA, EI, EI, GJ) from the PipeSection, mass per
+// unit length Rho, plain chord length, no pre-tension; ps = EA EI GJ GA Rho CDt CDn CAt CAn De Di
+void pipe_precalc(BeamEl& b, const int* nd, const double* ps, const double* cs)
+{
+	const double unit_hooke[3] = { 1.0, 0.0, 0.0 }, no_section[6] = { 1.0, 0, 0, 0, 0, 0 };
+	beam_precalc(b, nd, unit_hooke, no_section, cs, 0.0);                    // frame, length, shape functions, state
+	b.D = Mx<6, 6>();
+	b.D(0, 0) = ps[3]; b.D(1, 1) = ps[3]; b.D(2, 2) = ps[0]; b.D(3, 3) = ps[1]; b.D(4, 4) = ps[1]; b.D(5, 5) = ps[2];
+	b.rhoA = ps[4];
+	b.energy_on = false;
 }
 
 // Beam_1.cpp:695-835
@@ -477,7 +492,7 @@ void beam_mount(BeamEl& b, const int* nd)
 		Mx<18, 18> Kg = tr(dN) * (G * dN);                                   // :824-828
 		K = K + (1.0 * b.jac) * (Kc + Kg);
 		F = F + (1.0 * b.jac) * ((tr(dN) * tr(B)) * sig);
-		b.energy += 0.5 * (1.0 * b.jac) * (tr(sig) * eps)[0];
+		if (b.energy_on) b.energy += 0.5 * (1.0 * b.jac) * (tr(sig) * eps)[0];
 		for (int i = 0; i < 6; i++) { b.res[g][i] = eps[i]; b.res[g][6 + i] = sig[i]; }
 		b.Q_d[g] = Qd; b.dz[g] = dz; b.kr[g] = kap;
 	}
@@ -678,15 +693,18 @@ int gfo_set_materials(int n, const double* h) { W.hooke.assign(h, h + 3 * (size_
 int gfo_set_sections(int n, const double* s) { W.sec.assign(s, s + 6 * (size_t)n); return 0; }
 int gfo_set_shell_sections(int n, const double* t) { W.thick.assign(t, t + n); return 0; }
 int gfo_set_cs(int n, const double* e) { W.cs.assign(e, e + 9 * (size_t)n); return 0; }
+int gfo_set_pipe_sections(int n, const double* p) { W.pipe.assign(p, p + 11 * (size_t)n); return 0; }
 int gfo_set_elements(int n, const int* type, const int* mat, const int* sec, const int* cs,
 	const int* node_ptr, const int* nodes, const double* pretension)
 {
 	W.n_el = n;
+	W.is_pipe.assign(n, 0);
 	W.type.assign(type, type + n); W.mat.assign(mat, mat + n); W.secid.assign(sec, sec + n); W.csid.assign(cs, cs + n);
 	W.nptr.assign(node_ptr, node_ptr + n + 1);
 	W.nodes.assign(nodes, nodes + node_ptr[n]);
 	W.pret.assign(n, 0.0);
 	if (pretension) W.pret.assign(pretension, pretension + n);
+	for (int e = 0; e < n; e++) if (W.type[e] == T_PIPE) { W.is_pipe[e] = 1; W.type[e] = T_BEAM; W.pret[e] = 0.0; }
 	return 0;
 }
 int gfo_set_gravity(int on, double gx, double gy, double gz) { W.g_on = on; W.g[0] = gx; W.g[1] = gy; W.g[2] = gz; return 0; }
@@ -709,8 +727,9 @@ int gfo_precalc(void)
 	for (int e = 0; e < W.n_el; e++)
 	{
 		const int* nd = &W.nodes[W.nptr[e]];
-		const double* hk = &W.hooke[3 * (size_t)(W.mat[e] - 1)];
-		if (W.type[e] == T_SHELL) shell_precalc(W.shells[W.slot[e]], nd, hk[0], hk[1], hk[2], W.thick[W.secid[e] - 1]);
+		const double* hk = W.is_pipe[e] ? nullptr : &W.hooke[3 * (size_t)(W.mat[e] - 1)];
+		if (W.is_pipe[e]) pipe_precalc(W.beams[W.slot[e]], nd, &W.pipe[11 * (size_t)(W.secid[e] - 1)], &W.cs[9 * (size_t)(W.csid[e] - 1)]);
+		else if (W.type[e] == T_SHELL) shell_precalc(W.shells[W.slot[e]], nd, hk[0], hk[1], hk[2], W.thick[W.secid[e] - 1]);
 		else if (W.type[e] == T_BEAM) beam_precalc(W.beams[W.slot[e]], nd, hk, &W.sec[6 * (size_t)(W.secid[e] - 1)], &W.cs[9 * (size_t)(W.csid[e] - 1)], W.pret[e]);
 		else
 		{

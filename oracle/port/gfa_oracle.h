@@ -27,6 +27,7 @@ int gfo_set_materials(int n, const double* hooke3);
 int gfo_set_sections(int n, const double* sec6);
 int gfo_set_shell_sections(int n, const double* thickness);
 int gfo_set_cs(int n, const double* e123);
+int gfo_set_pipe_sections(int n, const double* v11);   /* EA EI GJ GA Rho CDt CDn CAt CAn De Di; element type 2 = Pipe_1 */
 int gfo_set_elements(int n, const int* type, const int* mat, const int* sec, const int* cs,
                      const int* node_ptr, const int* nodes, const double* pretension);
 int gfo_set_gravity(int on, double gx, double gy, double gz);

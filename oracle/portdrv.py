@@ -41,6 +41,7 @@ class PortOracle:
         L.gfo_set_sections.argtypes = [C.c_int, C.c_void_p]
         L.gfo_set_shell_sections.argtypes = [C.c_int, C.c_void_p]
         L.gfo_set_cs.argtypes = [C.c_int, C.c_void_p]
+        L.gfo_set_pipe_sections.argtypes = [C.c_int, C.c_void_p]
         L.gfo_set_elements.argtypes = [C.c_int, _I, _I, _I, _I, _I, _I, C.c_void_p]
         L.gfo_set_gravity.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         L.gfo_set_constraint_mask.argtypes = [_I]
@@ -72,6 +73,8 @@ class PortOracle:
         L.gfo_set_shell_sections(len(th), th.ctypes.data)
         cs = np.ascontiguousarray(m.cs, np.float64).reshape(-1)
         L.gfo_set_cs(len(m.cs), cs.ctypes.data)
+        pipes = np.ascontiguousarray(np.asarray(getattr(m, 'pipe_sections', np.zeros((0, 11))), float).reshape(-1, 11))
+        L.gfo_set_pipe_sections(len(pipes), pipes.ctypes.data)
         pret = None
         if m.pretension is not None:
             self._pret = np.ascontiguousarray(m.pretension, np.float64)

@@ -22,6 +22,8 @@
 #include "Node.h"
 #include "Element.h"
 #include "Beam_1.h"
+#include "Pipe_1.h"
+#include "PipeSection.h"
 #include "Shell_1.h"
 #include "Solid_1.h"
 #include "Hooke.h"
@@ -96,6 +98,7 @@ int ref_reset()
 	db.number_materials = 0; db.materials = NULL;
 	db.number_sections = 0; db.sections = NULL;
 	db.number_shell_sections = 0; db.shell_sections = NULL;
+	db.number_pipe_sections = 0; db.pipe_sections = NULL; db.pipe_sections_exist = false;
 	db.number_CS = 0; db.CS = NULL;
 	db.number_node_sets = 0; db.node_sets = NULL;
 	db.number_constraints = 0; db.constraints = NULL;
@@ -169,6 +172,19 @@ int ref_get_section(int id, double* out6)
 	return 0;
 }
 
+// PipeSection constants EA EI GJ GA Rho CDt CDn CAt CAn De Di (reference PipeSection.h:13-23)
+int ref_add_pipe_section(const double* v11)
+{
+	PipeSection* s = new PipeSection();
+	s->number = db.number_pipe_sections + 1;
+	s->EA = v11[0]; s->EI = v11[1]; s->GJ = v11[2]; s->GA = v11[3]; s->Rho = v11[4];
+	s->CDt = v11[5]; s->CDn = v11[6]; s->CAt = v11[7]; s->CAn = v11[8]; s->De = v11[9]; s->Di = v11[10];
+	db.pipe_sections = grow(db.pipe_sections, db.number_pipe_sections);
+	db.pipe_sections[db.number_pipe_sections++] = s;
+	db.pipe_sections_exist = true;
+	return s->number;
+}
+
 int ref_add_shell_section(double thickness)
 {
 	ShellSectionHomogeneous* s = new ShellSectionHomogeneous();
@@ -202,7 +218,7 @@ int ref_get_cs(int id, double* e123)
 	return 0;
 }
 
-// type: 1 Beam_1 (3 nodes), 3 Shell_1 (6 nodes), 7 Solid_1 (8 nodes)
+// type: 1 Beam_1 (3 nodes), 2 Pipe_1 (3 nodes), 3 Shell_1 (6 nodes), 7 Solid_1 (8 nodes)
 // (ids as listed in reference Element.h:8-15).  conn is 1-based, packed.
 int ref_set_elements(int n, const int* type, const int* mat, const int* sec, const int* cs,
 	const int* conn, const double* pretension)
@@ -215,6 +231,7 @@ int ref_set_elements(int n, const int* type, const int* mat, const int* sec, con
 		Element* el = NULL;
 		int nn = 0;
 		if (type[e] == 1) { Beam_1* b = new Beam_1(); b->T0 = pretension ? pretension[e] : 0.0; el = b; nn = 3; }
+		else if (type[e] == 2) { el = new Pipe_1(); nn = 3; }
 		else if (type[e] == 3) { el = new Shell_1(); nn = 6; }
 		else if (type[e] == 7) { el = new Solid_1(); nn = 8; }
 		else return -1;
@@ -402,6 +419,7 @@ int ref_get_element(int e, double* K, double* P, double* energy)
 	Element* el = db.elements[e];
 	Matrix* k = NULL; Matrix* p = NULL;
 	if (Beam_1* b = dynamic_cast<Beam_1*>(el)) { k = b->stiffness; p = b->P_loading; }
+	else if (Pipe_1* q = dynamic_cast<Pipe_1*>(el)) { k = q->stiffness; p = q->P_loading; }
 	else if (Shell_1* s = dynamic_cast<Shell_1*>(el)) { k = s->stiffness; p = s->P_loading; }
 	else return el->nDOFs;
 	int n = el->nDOFs;
@@ -441,6 +459,15 @@ int ref_get_state(int e, double* out)
 			for (int i = 0; i < 3; i++) out[w++] = (*b->lag_save->kappa_i_ref[g])(i, 0);
 		}
 	}
+	else if (Pipe_1* q = dynamic_cast<Pipe_1*>(el))
+	{
+		for (int g = 0; g < 2; g++)
+		{
+			for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[w++] = (*q->lag_save->Q_i[g])(i, j);
+			for (int i = 0; i < 3; i++) out[w++] = (*q->lag_save->dz_i[g])(i, 0);
+			for (int i = 0; i < 3; i++) out[w++] = (*q->lag_save->kappa_i_ref[g])(i, 0);
+		}
+	}
 	return w;
 }
 
@@ -468,6 +495,15 @@ int ref_get_results(int e, double* out)
 		{
 			for (int i = 0; i < 6; i++) out[w++] = (*b->epsilon_r[g])(i, 0);
 			for (int i = 0; i < 6; i++) out[w++] = (*b->sigma_r[g])(i, 0);
+		}
+	}
+	else if (Pipe_1* q = dynamic_cast<Pipe_1*>(el))
+	{
+		out[w++] = q->strain_energy;
+		for (int g = 0; g < 2; g++)
+		{
+			for (int i = 0; i < 6; i++) out[w++] = (*q->epsilon_r[g])(i, 0);
+			for (int i = 0; i < 6; i++) out[w++] = (*q->sigma_r[g])(i, 0);
 		}
 	}
 	return w;

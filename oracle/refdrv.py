@@ -63,6 +63,7 @@ class RefOracle:
         L.ref_get_vectors.argtypes = [_D, _D, _D]
         L.ref_get_element.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_get_state.argtypes = [C.c_int, _D]
+        L.ref_add_pipe_section.argtypes = [_D]
         L.ref_get_results.argtypes = [C.c_int, _D]
         L.ref_set_threads.argtypes = [C.c_int]
         if threads:
@@ -80,6 +81,8 @@ class RefOracle:
             L.ref_add_section(int(kind), float(a), float(b))
         for t in m.shell_thickness:
             L.ref_add_shell_section(float(t))
+        for row in np.asarray(getattr(m, 'pipe_sections', np.zeros((0, 11))), float).reshape(-1, 11):
+            L.ref_add_pipe_section(np.ascontiguousarray(row, np.float64))
         for e1, e3 in m.cs_defs:
             r = L.ref_add_cs(np.asarray(e1, np.float64), np.asarray(e3, np.float64))
             if r < 0:

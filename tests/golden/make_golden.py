@@ -100,5 +100,7 @@ if __name__ == "__main__":
     mb = M.beam_line(24, pretension=2.0e5)
     mb.gravity = (0.4, -0.3, -9.81)
     sequence(R, mb, M.beam_line_displacements, "beam_line")
+    mp = M.pipe_line(16, gravity=(0.3, -0.2, -9.81))      # Pipe_1 riser segment
+    sequence(R, mp, M.beam_line_displacements, "pipe_line")
     ms = M.shell_plate(6, 4, warp=0.01, gravity=(0.0, 0.0, -9.81))
     sequence(R, ms, M.shell_plate_displacements, "shell_plate")

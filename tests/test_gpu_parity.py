@@ -56,7 +56,7 @@ def test_tutorial01_against_reference_fixture():
     util.assert_parity(z["elem0_K"], K, "tutorial01 element 1 K", util.block_scale(z["elem0_K"]))
 
 
-@pytest.mark.parametrize("name", ["beam_line", "shell_plate"])
+@pytest.mark.parametrize("name", ["beam_line", "pipe_line", "shell_plate"])
 def test_sequence_against_reference_fixture(name):
     z = _golden(name)
     m = util.model_from_dict(z)
@@ -87,10 +87,12 @@ def _seeded_cases():
     s = M.shell_plate(17, 9, warp=0.02, gravity=(0.0, 0.0, -9.81))
     flat = M.shell_plate(8, 8)
     v = M.solid_block(5, 4, 3, gravity=(0.0, 0.0, -9.81))
-    mixed = M.concat_models([M.beam_line(37), M.shell_plate(7, 5, warp=0.005), M.solid_block(3, 3, 2)])
+    mixed = M.concat_models([M.beam_line(37), M.pipe_line(21), M.shell_plate(7, 5, warp=0.005), M.solid_block(3, 3, 2)])
+    pipe = M.pipe_line(300, gravity=(0.1, 0.2, -9.81))
     rng = np.random.default_rng(11)
     return [
         ("beam", b, M.beam_line_displacements(b)),
+        ("pipe", pipe, M.beam_line_displacements(pipe)),
         ("shell_warped_gravity", s, M.shell_plate_displacements(s)),
         ("shell_flat", flat, M.shell_plate_displacements(flat, seed=5)),
         ("solid", v, M.solid_block_displacements(v)),
@@ -320,7 +322,7 @@ def test_full_size_solid_block():
 def test_gauss_point_results_against_oracle(port):
     """gfa_gauss_point_results on a mixed model, before and after a state commit: the records come
     back per element type in element order; Solid_1 keeps none (as in the reference)."""
-    m = M.concat_models([M.beam_line(37, pretension=1.0e4), M.shell_plate(7, 5, warp=0.005), M.solid_block(3, 3, 2)])
+    m = M.concat_models([M.beam_line(37, pretension=1.0e4), M.pipe_line(11), M.shell_plate(7, 5, warp=0.005), M.solid_block(3, 3, 2), M.pipe_line(5)])
     rng = np.random.default_rng(3)
     asm = capi.Assembler(m).set_dofs()
     port.load(m)
@@ -328,7 +330,7 @@ def test_gauss_point_results_against_oracle(port):
         d = M.mask_displacements(m, rng.uniform(-2e-4, 2e-4, (m.n_nodes, 6)))
         port.assemble(d)
         asm.assemble(d)
-        for etype in (M.BEAM_1, M.SHELL_1):
+        for etype in (M.BEAM_1, M.PIPE_1, M.SHELL_1):
             ids = np.nonzero(m.elem_type == etype)[0]
             ref = np.array([port.results(int(e)) for e in ids])
             util.assert_results_parity(ref, asm.gauss_point_results(etype), f"iteration {it} type {etype}")

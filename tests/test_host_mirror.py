@@ -19,7 +19,7 @@ EXE = os.path.join(ROOT, "giraffe_b200", "gfa_run")
 
 
 def _model():
-    m = M.concat_models([M.beam_line(6, pretension=1.0e4), M.shell_plate(3, 2, warp=0.01)])
+    m = M.concat_models([M.beam_line(6, pretension=1.0e4), M.shell_plate(3, 2, warp=0.01), M.pipe_line(4)])
     m.gravity = (0.0, 0.0, -9.81)
     m.nodal_loads = [(np.array([13], np.int32), 1, np.array([[0, 0, 0, 0, 0, 0, 0], [1, 100.0, 0, 50.0, 0, 3.0, 0]]))]
     return m
@@ -31,7 +31,7 @@ def test_inp_round_trip(tmp_path):
     write_inp(m, p, end_time=1.0, time_step=0.25)
     m2, info = read_inp(p)
     assert info["time_step"] == 0.25
-    for k in ("xyz", "hooke", "sections", "cs", "elem_type", "elem_mat", "elem_sec", "elem_cs", "elem_nodes", "shell_thickness"):
+    for k in ("xyz", "hooke", "sections", "cs", "elem_type", "elem_mat", "elem_sec", "elem_cs", "elem_nodes", "shell_thickness", "pipe_sections"):
         assert np.array_equal(getattr(m, k), getattr(m2, k)), k
     assert np.array_equal(m.pretension, m2.pretension)
     assert (M.number_dofs(m)[0] == M.number_dofs(m2)[0]).all()

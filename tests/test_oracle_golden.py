@@ -42,7 +42,7 @@ def test_tutorial01_structure_and_values(port):
     assert len(z["it1_AA_val"]) == 1296
 
 
-@pytest.mark.parametrize("name", ["beam_line", "shell_plate"])
+@pytest.mark.parametrize("name", ["beam_line", "pipe_line", "shell_plate"])
 def test_sequence_with_commit(port, name):
     """Two iterations, SaveLagrange/SaveConfiguration, one more iteration."""
     z = _load(name)

@@ -108,6 +108,7 @@ def model_to_dict(m: M.Model, prefix: str = "m_") -> dict:
         "gravity": np.array(m.gravity if m.gravity is not None else [], float),
         "n_constraints": np.array([len(m.constraints)]),
         "n_loads": np.array([len(m.nodal_loads)]),
+        "pipe_sections": np.asarray(m.pipe_sections, float).reshape(-1, 11),
     }
     for i, (nodes, mask) in enumerate(m.constraints):
         d[f"c{i}_nodes"] = np.asarray(nodes, np.int32)
@@ -134,6 +135,8 @@ def model_from_dict(z, prefix: str = "m_") -> M.Model:
     m.gravity = tuple(gr) if gr.size else None
     m.constraints = [(g(f"c{i}_nodes"), int(g(f"c{i}_mask")[0])) for i in range(int(g("n_constraints")[0]))]
     m.nodal_loads = [(g(f"l{i}_nodes"), int(g(f"l{i}_cs")[0]), g(f"l{i}_table")) for i in range(int(g("n_loads")[0]))]
+    if prefix + "pipe_sections" in getattr(z, "files", z):
+        m.pipe_sections = np.asarray(g("pipe_sections"), float).reshape(-1, 11)
     return m
 
 
