@@ -26,7 +26,8 @@ EXPORTS = [
     "gfa_last_error", "gfa_device_count", "gfa_create", "gfa_destroy", "gfa_number_dofs", "gfa_set_dofs",
     "gfa_csr_dims", "gfa_csr_pattern", "gfa_assemble", "gfa_add_host_triplets", "gfa_add_host_vector",
     "gfa_csr_values", "gfa_csr_values_device", "gfa_vector", "gfa_vector_device", "gfa_element_block",
-    "gfa_commit_state", "gfa_element_state", "gfa_results_stride", "gfa_gauss_point_results", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
+    "gfa_commit_state", "gfa_element_state", "gfa_results_stride", "gfa_gauss_point_results",
+    "gfa_residual", "gfa_update_displacements", "gfa_displacements", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
 ]
 
@@ -51,6 +52,14 @@ class _ModelStruct(C.Structure):
         ("part_rank", C.c_int32), ("part_world", C.c_int32),
         ("n_pipe_sections", C.c_int32), ("pipe_sections", C.c_void_p),
     ]
+
+
+class _NormsStruct(C.Structure):
+    _fields_ = [("max_force", C.c_double), ("max_moment", C.c_double), ("node_force", C.c_int32), ("node_moment", C.c_int32),
+                ("max_disp_value", C.c_double), ("max_rot_value", C.c_double), ("nan_detected", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class _StepStruct(C.Structure):
@@ -84,6 +93,9 @@ def load_library() -> C.CDLL:
         lib.gfa_element_block.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.gfa_commit_state.argtypes = [C.c_void_p]
         lib.gfa_element_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        lib.gfa_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gfa_update_displacements.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gfa_displacements.argtypes = [C.c_void_p, C.c_void_p]
         lib.gfa_results_stride.argtypes = [C.c_int]
         lib.gfa_gauss_point_results.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         lib.gfa_gauss_point_results.restype = C.c_int64
@@ -209,6 +221,8 @@ class Assembler:
         st = _StepStruct()
         if device_ptr is not None:
             st.displacements, st.displacements_on_device = device_ptr, 1
+        elif disp is None:           # keep the device copy (after update_displacements)
+            st.displacements, st.displacements_on_device = None, 0
         else:
             d = np.ascontiguousarray(disp, np.float64).reshape(-1)
             self._keep_disp = d
@@ -296,6 +310,26 @@ class Assembler:
         if got < 0:
             raise GfaError(int(got), self.lib.gfa_last_error().decode())
         return buf[:got]
+
+    # ---- Newton-loop vector steps on the device copies (include/gfa.h) ----
+    def residual(self, X_B=None) -> dict:
+        """P_A = -P_A (- K_AB X_B); returns the max-norms CheckResidualConvergence reads."""
+        n = _NormsStruct()
+        xb = np.ascontiguousarray(X_B, np.float64) if X_B is not None else None
+        self._check(self.lib.gfa_residual(self._h, _ptr(xb) if xb is not None else None, C.byref(n)))
+        return n.as_dict()
+
+    def update_displacements(self, x_A) -> dict:
+        """Solution::UpdateDisps on the device copy; returns the norms CheckGLConvergence reads."""
+        n = _NormsStruct()
+        x = np.ascontiguousarray(x_A, np.float64)
+        self._check(self.lib.gfa_update_displacements(self._h, _ptr(x), C.byref(n)))
+        return n.as_dict()
+
+    def displacements(self) -> np.ndarray:
+        d = np.zeros(self.model.n_nodes * 6)
+        self._check(self.lib.gfa_displacements(self._h, _ptr(d)))
+        return d.reshape(-1, 6)
 
     def copy_coordinates(self):
         c = np.zeros(self.model.n_nodes * 6)

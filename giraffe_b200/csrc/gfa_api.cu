@@ -131,6 +131,10 @@ struct gfa_handle {
     DevBuf<GnRec> d_gn;
     DevBuf<RunEnt> d_runs;
     DevBuf<unsigned long long> d_ovf;
+    // Newton-loop vector steps: DOF map and the non-empty rows of AB on the device
+    DevBuf<int> d_gls, d_ab_rows, d_ab_ptr, d_ab_inner;
+    DevBuf<NormAcc> d_norm;
+    int n_ab_rows = 0;
     DevBuf<PInc> d_inc;
     long long n_runs = 0, n_gn_local = 0;
     DevBuf<long long> d_gseg, d_gsrc, d_gdest;
@@ -803,6 +807,22 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         CUDA_TRY(h->d_send_idx.upload(s_all));
         CUDA_TRY(h->d_recv_idx.upload(r_all));
     }
+    {   // Newton-loop vector steps
+        CUDA_TRY(h->d_gls.upload(h->gls));
+        const HostCsr& AB = h->csr[GFA_AB];
+        // rows of AB that hold entries; CSR storage is contiguous, so row rows[k] spans [ptr[k], ptr[k+1]) of
+        // the value array when the empty rows in between are skipped
+        std::vector<int> rows, ptr, inner(AB.inner.begin(), AB.inner.end());
+        for (int r = 0; r < AB.rows; r++)
+            if (AB.rowptr[r + 1] > AB.rowptr[r]) { rows.push_back(r); ptr.push_back((int)AB.rowptr[r]); }
+        ptr.push_back((int)AB.inner.size());
+        h->n_ab_rows = (int)rows.size();
+        if (rows.empty()) { rows.push_back(0); inner.push_back(0); }
+        CUDA_TRY(h->d_ab_rows.upload(rows));
+        CUDA_TRY(h->d_ab_ptr.upload(ptr));
+        CUDA_TRY(h->d_ab_inner.upload(inner));
+        CUDA_TRY(h->d_norm.alloc(1));
+    }
     h->dofs_set = true;
     return GFA_OK;
 }
@@ -826,15 +846,16 @@ int gfa_csr_pattern(gfa_t* h, int which, int32_t* outer, int32_t* inner) {
 }
 
 int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
-    if (!h || !st || !st->displacements) return fail(GFA_EINVAL, "gfa_assemble: null argument");
+    if (!h || !st) return fail(GFA_EINVAL, "gfa_assemble: null argument");
     if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_assemble before gfa_set_dofs");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const size_t nd = 6 * (size_t)h->n_nodes * sizeof(double);
     int launches = 0;
     CUDA_TRY(cudaEventRecord(h->ev[0], s));
-    CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
-                             st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (st->displacements)       // NULL: keep the device copy (gfa_update_displacements)
+        CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
+                                 st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
     // MountLocal + MountElementLoads: one evaluation launch per element type
     for (int slot = 0; slot < 3; slot++) {
@@ -1040,6 +1061,78 @@ int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* out, int64_t
             if (h->el_type[h->tb[s].elems[k]] == element_type) { std::memcpy(out + w * stride, all.data() + k * stride, stride * sizeof(double)); w++; }
     }
     return (int64_t)n_out;
+}
+
+namespace {
+int read_norms(gfa_t* h, bool with_values, gfa_norms_t* out) {
+    NormAcc a;
+    CUDA_TRY(cudaMemcpyAsync(&a, h->d_norm.p, sizeof(a), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    auto dbl = [](unsigned long long b) { double d; std::memcpy(&d, &b, sizeof(d)); return d; };
+    std::memset(out, 0, sizeof(*out));
+    out->max_force = dbl(a.max_t); out->max_moment = dbl(a.max_r);
+    out->node_force = a.node_t == 0x7fffffff ? 0 : a.node_t + 1;
+    out->node_moment = a.node_r == 0x7fffffff ? 0 : a.node_r + 1;
+    if (with_values) { out->max_disp_value = dbl(a.max_dt); out->max_rot_value = dbl(a.max_dr); }
+    out->nan_detected = a.nan;
+    return GFA_OK;
+}
+int reset_norms(gfa_t* h) {
+    NormAcc z; std::memset(&z, 0, sizeof(z)); z.node_t = 0x7fffffff; z.node_r = 0x7fffffff;
+    CUDA_TRY(cudaMemcpyAsync(h->d_norm.p, &z, sizeof(z), cudaMemcpyHostToDevice, h->stream));
+    return GFA_OK;
+}
+} // namespace
+
+int gfa_residual(gfa_t* h, const double* X_B, gfa_norms_t* out) {
+    if (!h) return fail(GFA_EINVAL, "gfa_residual: null handle");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_residual before gfa_assemble");
+    if (h->world > 1) return fail(GFA_EUNSUPPORTED, "gfa_residual works on a single-rank system (the residual is row-distributed otherwise)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double* PA = h->d_arena.p + h->vec_off[GFA_P_A];
+    launch_negate(PA, h->n_free, h->stream);
+    if (X_B && h->n_fixed > 0 && h->n_ab_rows > 0) {
+        DevBuf<double> xb;
+        CUDA_TRY(xb.alloc((size_t)h->n_fixed));
+        CUDA_TRY(cudaMemcpyAsync(xb.p, X_B, (size_t)h->n_fixed * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_sub_ab_xb(PA, h->d_ab_rows.p, h->d_ab_ptr.p, h->d_ab_inner.p, h->d_arena.p + h->arena_off[GFA_AB], xb.p, h->n_ab_rows, h->stream);
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (out) {
+        if (int rc = reset_norms(h)) return rc;
+        launch_norms(h->d_gls.p, PA, nullptr, h->n_nodes, h->d_norm.p, h->stream);
+        CUDA_TRY(cudaGetLastError());
+        return read_norms(h, false, out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_update_displacements(gfa_t* h, const double* x_A, gfa_norms_t* out) {
+    if (!h || !x_A) return fail(GFA_EINVAL, "gfa_update_displacements: null argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_update_displacements before gfa_set_dofs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    DevBuf<double> x;
+    CUDA_TRY(x.alloc((size_t)std::max(h->n_free, 1)));
+    CUDA_TRY(cudaMemcpyAsync(x.p, x_A, (size_t)h->n_free * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_update_disps(h->d_gls.p, h->d_disp.p, x.p, h->n_nodes, h->stream);
+    if (out) {
+        if (int rc = reset_norms(h)) return rc;
+        launch_norms(h->d_gls.p, x.p, h->d_disp.p, h->n_nodes, h->d_norm.p, h->stream);
+        CUDA_TRY(cudaGetLastError());
+        return read_norms(h, true, out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_displacements(gfa_t* h, double* out) {
+    if (!h || !out) return fail(GFA_EINVAL, "gfa_displacements: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(out, h->d_disp.p, 6 * (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost));
+    return GFA_OK;
 }
 
 int gfa_copy_coordinates(gfa_t* h, double* out) {

@@ -111,6 +111,20 @@ struct GatherArgs {
     double* vals;                // AB | BA | BB value arrays, one arena
 };
 
+// ---- Newton-loop vector steps either side of the assembly (Static.cpp:210-217, Solution.cpp:390-402,
+//      ConvergenceCriteria.cpp:187-380, 460-598) -------------------------------------------------
+struct NormAcc {                    // filled by the norm kernels; doubles are >= 0 and compared as bit patterns
+    unsigned long long max_t, max_r;        // max |v(GL-1)| over free translational / rotational node DOFs
+    unsigned long long max_dt, max_dr;      // max |Node::displacements| over the same DOFs (update only)
+    int node_t, node_r;                     // 0-based node of the first maximum in node order (INT_MAX: none)
+    int nan;                                // NaN seen in v
+    int pad;
+};
+void launch_negate(double* v, long long n, void* stream);
+void launch_sub_ab_xb(double* PA, const int* rows, const int* ptr, const int* inner, const double* vals, const double* XB, int n_rows, void* stream);
+void launch_update_disps(const int* gls, double* disp, const double* x, int n_nodes, void* stream);
+void launch_norms(const int* gls, const double* v, const double* disp, int n_nodes, NormAcc* acc, void* stream);
+
 void launch_shell_eval(const EvalArgs& a, void* stream);
 void launch_beam_eval(const EvalArgs& a, void* stream);
 void launch_solid_eval(const EvalArgs& a, void* stream);

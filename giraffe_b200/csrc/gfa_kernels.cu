@@ -1450,6 +1450,86 @@ __global__ void unpack_add_kernel(double* vals, const long long* idx, const doub
 }
 
 // =========================================================================
+// Newton-loop vector steps either side of the assembly
+// =========================================================================
+// db.global_P_A = -1.0 * db.global_P_A (Static.cpp:210)
+__global__ void negate_kernel(double* v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = __dmul_rn(-1.0, v[i]);
+}
+// db.global_P_A = db.global_P_A - 1.0 * (db.global_stiffness_AB * db.global_X_B) (Static.cpp:216-217); the
+// product is the reference's own row loop, y_i += a * x in column order (SparseMatrix.cpp:186-190).
+// One thread per non-empty row of AB.
+__global__ void sub_ab_xb_kernel(double* PA, const int* rows, const int* ptr, const int* inner, const double* vals, const double* XB, int n_rows) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_rows) return;
+    double y = 0.0;
+    for (int p = ptr[k]; p < ptr[k + 1]; p++) y = __dadd_rn(y, __dmul_rn(vals[p], XB[inner[p]]));
+    const int r = rows[k];
+    PA[r] = __dsub_rn(PA[r], __dmul_rn(1.0, y));
+}
+// Solution::UpdateDisps (Solution.cpp:390-402): displacements[j] += x(GL-1) for free active DOFs
+__global__ void update_disps_kernel(const int* gls, double* disp, const double* x, int n_nodes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6LL * n_nodes) return;
+    const int g = gls[i];
+    if (g > 0) disp[i] = __dadd_rn(disp[i], x[g - 1]);
+}
+// The max-norms of EstablishResidualCriteria / CheckResidualConvergence / CheckGLConvergence
+// (ConvergenceCriteria.cpp:200-217, 474-505, 305-340): pass 1 the maxima, pass 2 the first node that
+// reaches them (the reference keeps the first, `value > max`).
+__global__ void norms_max_kernel(const int* gls, const double* v, const double* disp, int n_nodes, NormAcc* acc) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mt = 0, mr = 0, dt = 0, dr = 0;
+    int nan = 0;
+    if (node < n_nodes) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int g = gls[6 * (size_t)node + k];
+            if (g <= 0) continue;
+            const double a = fabs(v[g - 1]);
+            if (a != a) { nan = 1; continue; }
+            const unsigned long long b = (unsigned long long)__double_as_longlong(a);
+            if (k < 3) mt = max(mt, b); else mr = max(mr, b);
+            if (disp) {
+                const double d = fabs(disp[6 * (size_t)node + k]);
+                if (d == d) { const unsigned long long db = (unsigned long long)__double_as_longlong(d); if (k < 3) dt = max(dt, db); else dr = max(dr, db); }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mt = max(mt, __shfl_xor_sync(0xffffffffu, mt, o)); mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+        dt = max(dt, __shfl_xor_sync(0xffffffffu, dt, o)); dr = max(dr, __shfl_xor_sync(0xffffffffu, dr, o));
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mt) atomicMax(&acc->max_t, mt);
+        if (mr) atomicMax(&acc->max_r, mr);
+        if (dt) atomicMax(&acc->max_dt, dt);
+        if (dr) atomicMax(&acc->max_dr, dr);
+        if (nan) atomicOr(&acc->nan, 1);
+    }
+}
+__global__ void norms_node_kernel(const int* gls, const double* v, int n_nodes, NormAcc* acc) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n_nodes) return;
+    const unsigned long long mt = acc->max_t, mr = acc->max_r;
+    bool ht = false, hr = false;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int g = gls[6 * (size_t)node + k];
+        if (g <= 0) continue;
+        const double a = fabs(v[g - 1]);
+        if (a != a) continue;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(a);
+        if (k < 3) ht |= (b == mt && mt != 0); else hr |= (b == mr && mr != 0);
+    }
+    if (ht) atomicMin(&acc->node_t, node);
+    if (hr) atomicMin(&acc->node_r, node);
+}
+
+// =========================================================================
 // launchers
 // =========================================================================
 static int grid_for(long long items, int per_block, int cap) {
@@ -1564,6 +1644,20 @@ void launch_beam_commit(const EvalArgs& a, void* s) {
     if (a.n_el <= 0) return;
     const long long n = (long long)a.n_el * beam::NGP;
     beam::commit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)s>>>(a);
+}
+void launch_negate(double* v, long long n, void* s) {
+    if (n > 0) negate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(v, n);
+}
+void launch_sub_ab_xb(double* PA, const int* rows, const int* ptr, const int* inner, const double* vals, const double* XB, int n_rows, void* s) {
+    if (n_rows > 0) sub_ab_xb_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)s>>>(PA, rows, ptr, inner, vals, XB, n_rows);
+}
+void launch_update_disps(const int* gls, double* disp, const double* x, int n_nodes, void* s) {
+    if (n_nodes > 0) update_disps_kernel<<<(unsigned)((6LL * n_nodes + 255) / 256), 256, 0, (cudaStream_t)s>>>(gls, disp, x, n_nodes);
+}
+void launch_norms(const int* gls, const double* v, const double* disp, int n_nodes, NormAcc* acc, void* s) {
+    if (n_nodes <= 0) return;
+    norms_max_kernel<<<(n_nodes + 255) / 256, 256, 0, (cudaStream_t)s>>>(gls, v, disp, n_nodes, acc);
+    norms_node_kernel<<<(n_nodes + 255) / 256, 256, 0, (cudaStream_t)s>>>(gls, v, n_nodes, acc);
 }
 void launch_shell_results(const EvalArgs& a, double* out, void* s) {
     if (a.n_el <= 0) return;

@@ -102,7 +102,8 @@ typedef struct gfa_model {
 
 /* Per-iteration inputs (src/Static.cpp:200-212; src/Solution.cpp:390-402). */
 typedef struct gfa_step {
-    const double* displacements;     /* [n_nodes*6] Node::displacements of every node, node-major */
+    const double* displacements;     /* [n_nodes*6] Node::displacements of every node, node-major; NULL = keep the
+                                      * device copy (after gfa_update_displacements) */
     int32_t displacements_on_device; /* 0: host pointer (copied H2D inside the call); 1: device pointer */
     double  gravity_factor;          /* BoolTable::GetLinearFactorAtCurrentTime() of Environment::bool_g */
 } gfa_step_t;
@@ -189,6 +190,32 @@ int gfa_element_state(gfa_t* h, int32_t element, double* out);
 int gfa_results_stride(int element_type);
 int64_t gfa_gauss_point_results(gfa_t* h, int element_type, double* host_out, int64_t capacity);
 int gfa_copy_coordinates(gfa_t* h, double* host_out /* [n_nodes*6] */);
+
+/* ---- the Newton-loop vector steps either side of the assembly, on the device copies ----
+ * (they remove the per-iteration D2H of the residual). */
+typedef struct gfa_norms {
+    double  max_force, max_moment;   /* max |v(GL-1)| over free translational / rotational node DOFs:
+                                      * v = P_A in gfa_residual (ConvergenceCriteria.cpp:200-217, 474-505),
+                                      * v = the increment x_A in gfa_update_displacements (:305-340) */
+    int32_t node_force, node_moment; /* 1-based node of the first maximum in node order, 0 if none (node_force / node_moment,
+                                      * node_disp / node_rot of the reference) */
+    double  max_disp_value, max_rot_value; /* gfa_update_displacements only: max |Node::displacements| after the update */
+    int32_t nan_detected;            /* NaNDetector hit (the reference sets `diverged`) */
+} gfa_norms_t;
+
+/* Static.cpp:210-217: db.global_P_A = -1.0*db.global_P_A and, when X_B is given (first iteration of an
+ * increment), db.global_P_A -= 1.0*(db.global_stiffness_AB*db.global_X_B) with the reference's own row loop
+ * (SparseMatrix.cpp:186-190); then the max-norms EstablishResidualCriteria / CheckResidualConvergence read.
+ * Call after gfa_assemble and the host contributions; gfa_vector(GFA_P_A) afterwards returns the right-hand
+ * side handed to the solver. */
+int gfa_residual(gfa_t* h, const double* X_B /* [n_fixed] host, or NULL */, gfa_norms_t* out);
+
+/* Solution::UpdateDisps (src/Solution.cpp:390-402) for node DOFs on the device copy of Node::displacements
+ * (the array of the last gfa_assemble): displacements[j] += x_A(GL-1) where GL > 0, and the norms
+ * CheckGLConvergence reads.  A following gfa_assemble with step.displacements == NULL evaluates the updated
+ * device copy; gfa_displacements copies it back. */
+int gfa_update_displacements(gfa_t* h, const double* x_A /* [n_free] host */, gfa_norms_t* out);
+int gfa_displacements(gfa_t* h, double* host_out /* [n_nodes*6] */);
 
 /* Timing of the last gfa_assemble, milliseconds from CUDA events on the
  * library's stream: [0] H2D of displacements, [1] element evaluation

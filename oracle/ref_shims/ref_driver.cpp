@@ -37,6 +37,7 @@
 #include "Environment.h"
 #include "Solution.h"
 #include "LagrangeSave.h"
+#include "ConvergenceCriteria.h"
 
 extern Database db;
 
@@ -521,6 +522,37 @@ int ref_commit()
 		db.elements[i]->SaveLagrange();
 	for (int i = 0; i < db.number_nodes; i++)
 		for (int k = 0; k < 6; k++) db.nodes[i]->displacements[k] = 0.0;
+	return 0;
+}
+
+// The Newton-loop steps either side of the assembly, through the reference's own code:
+// Static.cpp:210-217 (sign flip, imposed displacements), ConvergenceCriteria::EstablishResidualCriteria /
+// CheckResidualConvergence (node_force, node_moment), Solution::UpdateDisps and CheckGLConvergence
+// (node_disp, node_rot).  out4 = node_force, node_moment (residual) or node_disp, node_rot (update), diverged, 0.
+int ref_residual(const double* XB, int* out4)
+{
+	db.global_P_A = -1.0*db.global_P_A;
+	if (XB)
+	{
+		for (int i = 0; i < db.n_GL_fixed; i++) db.global_X_B(i, 0) = XB[i];
+		db.global_P_A = db.global_P_A - 1.0*(db.global_stiffness_AB*db.global_X_B);
+	}
+	ConvergenceCriteria* c = db.conv_criteria;
+	c->diverged = false; c->node_force = 0; c->node_moment = 0;
+	c->EstablishResidualCriteria();
+	c->CheckResidualConvergence();
+	out4[0] = c->node_force; out4[1] = c->node_moment; out4[2] = c->diverged ? 1 : 0; out4[3] = 0;
+	return 0;
+}
+int ref_update_displacements(const double* xA, int* out4, double* disp_out)
+{
+	for (int i = 0; i < db.n_GL_free; i++) db.global_P_A(i, 0) = xA[i];
+	g_sol->UpdateDisps();
+	ConvergenceCriteria* c = db.conv_criteria;
+	c->diverged = false; c->node_disp = 0; c->node_rot = 0;
+	c->CheckGLConvergence();
+	out4[0] = c->node_disp; out4[1] = c->node_rot; out4[2] = c->diverged ? 1 : 0; out4[3] = 0;
+	for (int i = 0; i < db.number_nodes; i++) for (int k = 0; k < 6; k++) disp_out[6 * i + k] = db.nodes[i]->displacements[k];
 	return 0;
 }
 

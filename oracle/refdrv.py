@@ -64,6 +64,8 @@ class RefOracle:
         L.ref_get_element.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_get_state.argtypes = [C.c_int, _D]
         L.ref_add_pipe_section.argtypes = [_D]
+        L.ref_residual.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.int32, flags='C')]
+        L.ref_update_displacements.argtypes = [_D, np.ctypeslib.ndpointer(np.int32, flags='C'), _D]
         L.ref_get_results.argtypes = [C.c_int, _D]
         L.ref_set_threads.argtypes = [C.c_int]
         if threads:
@@ -187,6 +189,21 @@ class RefOracle:
         en = C.c_double(0.0)
         self.lib.ref_get_element(e, K.ctypes.data, P.ctypes.data, C.addressof(en))
         return K, P, en.value
+
+    def residual(self, X_B=None):
+        """Static.cpp:210-217 + EstablishResidualCriteria / CheckResidualConvergence through the reference's
+        own code; returns (node_force, node_moment, diverged); vectors() then holds the right-hand side."""
+        out = np.zeros(4, np.int32)
+        xb = np.ascontiguousarray(X_B, np.float64) if X_B is not None else None
+        self.lib.ref_residual(xb.ctypes.data if xb is not None else None, out)
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def update_displacements(self, x_A):
+        """Solution::UpdateDisps + CheckGLConvergence; returns (displacements[n,6], node_disp, node_rot, diverged)."""
+        out = np.zeros(4, np.int32)
+        d = np.zeros(self.model.n_nodes * 6)
+        self.lib.ref_update_displacements(np.ascontiguousarray(x_A, np.float64), out, d)
+        return d.reshape(-1, 6), int(out[0]), int(out[1]), int(out[2])
 
     def results(self, e: int) -> np.ndarray:
         """Gauss-point results of element e after the last assemble, in the layout of

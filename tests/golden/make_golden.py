@@ -94,8 +94,34 @@ def sequence(R, m, disp_fn, name, scale2=0.6):
     print(name, "n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
 
 
+def newton_steps(R):
+    """The vector steps either side of the assembly, through the reference's own code (Static.cpp:210-217,
+    ConvergenceCriteria.cpp, Solution::UpdateDisps): a beam + shell model with a prescribed-displacement set."""
+    m = M.concat_models([M.beam_line(12, pretension=1.0e4), M.shell_plate(5, 3, warp=0.01)])
+    m.constraints = m.constraints + [([7, 30], 0x07), ([40], 0x3F)]
+    rng = np.random.default_rng(20240005)
+    d = M.mask_displacements(m, rng.uniform(-1e-3, 1e-3, (m.n_nodes, 6)))
+    R.load(m)
+    R.set_time(0.0, 1.0)
+    R.assemble(d)
+    z = util.model_to_dict(m)
+    z["gls"] = R.gls()
+    z["disp"] = d
+    z["X_B"] = rng.uniform(-1e-3, 1e-3, R.n_fixed)
+    nf, nm, div = R.residual(z["X_B"])
+    z["rhs"] = R.vectors()[0]
+    z["residual_nodes"] = np.array([nf, nm, div])
+    z["x_A"] = rng.uniform(-1e-4, 1e-4, R.n_free)
+    d2, nd, nr, div = R.update_displacements(z["x_A"])
+    z["disp_after"] = d2
+    z["increment_nodes"] = np.array([nd, nr, div])
+    np.savez_compressed(os.path.join(OUT, "newton_steps.npz"), **z)
+    print("newton_steps: n_free", R.n_free, "n_fixed", R.n_fixed, "nodes", z["residual_nodes"], z["increment_nodes"])
+
+
 if __name__ == "__main__":
     R = RefOracle(threads=1)
+    newton_steps(R)
     tutorial01(R)
     mb = M.beam_line(24, pretension=2.0e5)
     mb.gravity = (0.4, -0.3, -9.81)

@@ -338,3 +338,40 @@ def test_gauss_point_results_against_oracle(port):
         asm.commit()
     with pytest.raises(capi.GfaError):
         asm.gauss_point_results(M.SOLID_1)
+
+
+def test_newton_vector_steps_on_device():
+    """gfa_residual / gfa_update_displacements / assemble-from-the-device-copy against the reference-generated
+    fixture: bit-exact right-hand side given the same P_A, first-node semantics of the max-norms, exact update."""
+    from oracle import newton_steps as ns
+    z = _golden("newton_steps")
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(0.0, 1.0)
+    assert (asm.gls == z["gls"]).all()
+    asm.assemble(z["disp"])
+    pa = asm.vectors()[0]
+    expect = ns.residual(pa, asm.csr("AB"), z["X_B"])          # same arithmetic on the device's own P_A
+    got = asm.residual(z["X_B"])
+    rhs = asm.vectors()[0]
+    assert np.array_equal(rhs, expect)
+    util.assert_parity(z["rhs"], rhs, "right-hand side vs reference")
+    n = ns.residual_norms(z["gls"], rhs)
+    assert (got["max_force"], got["max_moment"]) == (n["max_force"], n["max_moment"])
+    assert (got["node_force"], got["node_moment"], got["nan_detected"]) == (n["node_force"], n["node_moment"], 0)
+    assert (got["node_force"], got["node_moment"]) == tuple(int(v) for v in z["residual_nodes"][:2])
+    inc = asm.update_displacements(z["x_A"])
+    d2 = asm.displacements()
+    assert np.array_equal(d2, z["disp_after"])
+    ref_inc = ns.increment_norms(z["gls"], z["x_A"], z["disp_after"])
+    for k in ("max_force", "max_moment", "node_force", "node_moment", "max_disp_value", "max_rot_value", "nan_detected"):
+        assert inc[k] == ref_inc[k], k
+    assert (inc["node_force"], inc["node_moment"]) == tuple(int(v) for v in z["increment_nodes"][:2])
+    # the next iteration assembles the device copy: same system as handing the updated array over
+    asm.assemble(None)
+    v1 = asm.values("AA").copy(); p1 = asm.vectors()[0].copy()
+    asm.assemble(z["disp_after"])
+    assert np.array_equal(v1, asm.values("AA")) and np.array_equal(p1, asm.vectors()[0])
+    # NaN in the increment is flagged, not propagated into the maxima
+    x = z["x_A"].copy(); x[3] = np.nan
+    assert asm.update_displacements(x)["nan_detected"] == 1

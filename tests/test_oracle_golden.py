@@ -84,3 +84,25 @@ def test_shell_gravity_is_applied_twice(port):
     area = 3 * 2 * 0.0195 ** 2
     expect = 2.0 * 8000.0 * 0.002 * 9.81 * area      # P = Fint - Fext, Fext = 2 * weight (downwards)
     assert abs(total_z - expect) <= 1e-10 * expect
+
+
+def test_newton_steps_restatement_against_reference_fixture(port):
+    """oracle/newton_steps.py (sign flip, K_AB X_B, max-norms with first-node semantics, UpdateDisps) against
+    what the reference's own Static / ConvergenceCriteria / Solution code produced (make_golden.py)."""
+    from oracle import newton_steps as ns
+    z = _load("newton_steps")
+    m = util.model_from_dict(z)
+    port.load(m)
+    port.set_time(0.0, 1.0)
+    port.assemble(z["disp"])
+    assert (port.gls() == z["gls"]).all()
+    pa = port.vectors()[0]
+    rhs = ns.residual(pa, port.csr("AB"), z["X_B"])
+    util.assert_parity(z["rhs"], rhs, "right-hand side")
+    # the steps themselves are exact: replay them on the reference's own numbers
+    n = ns.residual_norms(z["gls"], z["rhs"])
+    assert (n["node_force"], n["node_moment"], n["nan_detected"]) == tuple(int(v) for v in z["residual_nodes"])
+    d2 = ns.update_displacements(z["gls"], z["disp"], z["x_A"])
+    assert np.array_equal(d2, z["disp_after"])
+    inc = ns.increment_norms(z["gls"], z["x_A"], d2)
+    assert (inc["node_force"], inc["node_moment"], inc["nan_detected"]) == tuple(int(v) for v in z["increment_nodes"])
