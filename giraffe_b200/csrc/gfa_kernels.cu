@@ -10,13 +10,17 @@
 //        K = sum_gp  (S (x) I3)^T C' (S (x) I3),   F = sum_gp (S (x) I3)^T f
 //   exploiting that every block of the reference's deltaN matrices is a
 //   scalar times I3 (Shell_1.cpp:2118-2180, Beam_1.cpp:641-669).  The element
-//   block is written row-major in the reference's local DOF order.
+//   block goes to the arena as contiguous 3x3 blocks in the reference's local
+//   DOF order (Shell_1: the 48 stored blocks of gfa_device.h only).
 //
-// Scatter (Element::MountGlobal + SparseMatrix::Mount): one warp per
-//   group-node (3-DOF group) accumulates the rows it owns in shared memory,
-//   visiting the incident elements in ascending order -- the order the
-//   reference pushes its triplets (Solution.cpp:327-328) -- and writes each
-//   CSR row once, coalesced.  No atomics; results are bitwise reproducible.
+// Scatter (Element::MountGlobal + SparseMatrix::Mount): one thread per row of a
+//   CSR patch (= one (group-node, neighbour) pair) sums the contributing element
+//   blocks in ascending element order -- the order the reference pushes its
+//   triplets (Solution.cpp:327-328) -- and writes each CSR row once, in whole
+//   sectors.  No atomics; results are bitwise reproducible.
+//
+// Also here: the on-demand Gauss-point result kernels, the state commit kernels and
+// the Newton-loop vector steps (sign flip, K_AB X_B, max-norms, UpdateDisps).
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "gfa_device.h"
