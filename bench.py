@@ -189,21 +189,22 @@ def run_cuda(args):
     recv_buf = torch.empty(int(recv_cnt.sum()), dtype=torch.float64, device="cuda") if world > 1 else None
 
     def exchange():
+        """pack -> NCCL send/recv -> unpack, stream-ordered on the library's stream (no host syncs)."""
         if world == 1:
             return
-        asm.interface_pack(send_buf.data_ptr())
-        ops, so, ro = [], 0, 0
-        for r in range(world):
-            if send_cnt[r]:
-                ops.append(dist.P2POp(dist.isend, send_buf[so:so + int(send_cnt[r])], r))
-            if recv_cnt[r]:
-                ops.append(dist.P2POp(dist.irecv, recv_buf[ro:ro + int(recv_cnt[r])], r))
-            so += int(send_cnt[r]); ro += int(recv_cnt[r])
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            torch.cuda.current_stream().synchronize()
-        asm.interface_unpack(recv_buf.data_ptr())
+        with torch.cuda.stream(lib_stream):
+            asm.interface_pack(send_buf.data_ptr())
+            ops, so, ro = [], 0, 0
+            for r in range(world):
+                if send_cnt[r]:
+                    ops.append(dist.P2POp(dist.isend, send_buf[so:so + int(send_cnt[r])], r))
+                if recv_cnt[r]:
+                    ops.append(dist.P2POp(dist.irecv, recv_buf[ro:ro + int(recv_cnt[r])], r))
+                so += int(send_cnt[r]); ro += int(recv_cnt[r])
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            asm.interface_unpack(recv_buf.data_ptr())
 
     def step_resident():
         asm.assemble(None, device_ptr=d_dev.data_ptr())

@@ -951,6 +951,7 @@ int gfa_csr_values(gfa_t* h, int which, double* out) {
     if (!h || which < 0 || which > 3 || !out) return fail(GFA_EINVAL, "gfa_csr_values: bad argument");
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_csr_values before gfa_assemble");
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
     const size_t n = h->csr[which].inner.size();
     if (n) CUDA_TRY(cudaMemcpy(out, h->d_arena.p + h->arena_off[which], n * sizeof(double), cudaMemcpyDeviceToHost));
     return GFA_OK;
@@ -965,6 +966,7 @@ int gfa_vector(gfa_t* h, int wv, double* out) {
     if (!h || wv < 0 || wv > 2 || !out) return fail(GFA_EINVAL, "gfa_vector: bad argument");
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_vector before gfa_assemble");
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
     const size_t n = wv == GFA_P_B ? h->n_fixed : h->n_free;
     if (n) CUDA_TRY(cudaMemcpy(out, h->d_arena.p + h->vec_off[wv], n * sizeof(double), cudaMemcpyDeviceToHost));
     return GFA_OK;
@@ -982,6 +984,7 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     const int s = h->el_owner_slot[e];
     if (s < 0) return fail(GFA_EINVAL, "element %d belongs to another rank's partition", e + 1);
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
     const int n = kTypes[s].ndof;
     if (K) {
         const int nb = n / 3, nd = arena_doubles(s), local = h->el_local[e];
@@ -1131,6 +1134,7 @@ int gfa_update_displacements(gfa_t* h, const double* x_A, gfa_norms_t* out) {
 int gfa_displacements(gfa_t* h, double* out) {
     if (!h || !out) return fail(GFA_EINVAL, "gfa_displacements: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
     CUDA_TRY(cudaMemcpy(out, h->d_disp.p, 6 * (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost));
     return GFA_OK;
 }
@@ -1161,8 +1165,7 @@ int gfa_interface_pack(gfa_t* h, double* buf) {
     CUDA_TRY(cudaSetDevice(h->device));
     launch_pack(h->d_arena.p, h->d_send_idx.p, buf, (long long)h->d_send_idx.n, h->stream);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return GFA_OK;
+    return GFA_OK;       // asynchronous: ordered on gfa_stream()
 }
 int gfa_interface_unpack(gfa_t* h, const double* buf) {
     if (!h) return fail(GFA_EINVAL, "gfa_interface_unpack: null handle");
@@ -1175,8 +1178,7 @@ int gfa_interface_unpack(gfa_t* h, const double* buf) {
         off += h->recv_cnt[r];
     }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return GFA_OK;
+    return GFA_OK;       // asynchronous: ordered on gfa_stream()
 }
 int gfa_local_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {
     if (!h) return fail(GFA_EINVAL, "gfa_local_rows: null handle");

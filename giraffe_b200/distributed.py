@@ -53,13 +53,19 @@ class InterfaceExchange:
         return 8 * int(self.send_counts.sum() + self.recv_counts.sum())
 
     def __call__(self):
+        """pack -> NCCL -> unpack, all ordered on the library's stream (gfa_stream): no host
+        synchronisation; the next read of the values waits for the stream."""
         if self.world == 1:
             return
-        self.asm.interface_pack(self.send_buf.data_ptr())
-        p2p_exchange(self.send_buf, self.send_counts, self.recv_buf, self.recv_counts)
         if self.recv_buf.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        self.asm.interface_unpack(self.recv_buf.data_ptr())
+            with torch.cuda.stream(torch.cuda.ExternalStream(self.asm.stream())):
+                self.asm.interface_pack(self.send_buf.data_ptr())
+                p2p_exchange(self.send_buf, self.send_counts, self.recv_buf, self.recv_counts)
+                self.asm.interface_unpack(self.recv_buf.data_ptr())
+        else:
+            self.asm.interface_pack(self.send_buf.data_ptr())
+            p2p_exchange(self.send_buf, self.send_counts, self.recv_buf, self.recv_counts)
+            self.asm.interface_unpack(self.recv_buf.data_ptr())
 
 
 def partition_ranges(type_counts, world: int):

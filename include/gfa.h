@@ -238,7 +238,9 @@ int gfa_last_launch_count(gfa_t* h);
  *   gfa_interface_unpack : adds received partials (device recv_buf, segments
  *                          ordered by peer rank, peers ascending => fixed
  *                          summation order) into the owned rows
- * The transport between pack and unpack is the caller's (NCCL send/recv). */
+ * The transport between pack and unpack is the caller's (NCCL send/recv).  Pack and unpack only ENQUEUE
+ * their kernels on gfa_stream(): the caller orders its transport after the pack and the unpack after its
+ * transport on that stream (or with events); gfa_csr_values / gfa_vector / the next gfa_assemble wait for it. */
 int gfa_interface_counts(gfa_t* h, int64_t* send_counts /* [world] */, int64_t* recv_counts /* [world] */);
 int gfa_interface_pack(gfa_t* h, double* send_buf_device);
 int gfa_interface_unpack(gfa_t* h, const double* recv_buf_device);
