@@ -105,6 +105,12 @@ struct ShellEl
 	// trial values kept by Mount for SaveLagrange (Shell_1.cpp:1650-1664)
 	M3 Q_d[3], Xi_d[3]; V3 a_x1[3], a_x2[3], u_x1[3], u_x2[3];
 	double K[27 * 27], Fint[27], P[27], energy;
+	// Newmark dynamics (Shell_1.cpp:2406-2547): committed Rodrigues vector, trial increments of Mount,
+	// 6-point rule data of MountMassModal, inertia constants (:2022-2024), stored Rayleigh matrix
+	V3 alpha_i[3], a_d[3], u_d[3];
+	double N4u[6][6], N4a[6][3], w4[6];
+	double coef1, coef2, coef3;
+	std::vector<double> CR;
 	double res[3][24];                        // eta_r1 eta_r2 kappa_r1 kappa_r2 n_r1 n_r2 m_r1 m_r2 per point (Shell_1.h:153-160)
 };
 struct BeamEl
@@ -114,6 +120,11 @@ struct BeamEl
 	M3 Q_i[2]; V3 dz_i[2], k_i[2];
 	M3 Q_d[2]; V3 dz[2], kr[2];
 	double K[18 * 18], Fint[18], P[18], energy;
+	// Newmark dynamics (Beam_1.cpp:1564-1673): committed Rodrigues vector, trial increments of Mount,
+	// section inertia (:582-596), stored Rayleigh matrix
+	V3 alpha_i[2], a_d[2], u_d[2];
+	M3 Mr, Jr; V3 br;
+	std::vector<double> CR;
 	bool energy_on;                           // Pipe_1::Mount never adds to strain_energy
 	double res[2][12];                        // epsilon_r(6) sigma_r(6) per point (Beam_1.h:80-81)
 };
@@ -144,6 +155,9 @@ struct World
 	std::vector<int> outer[4], inner[4]; std::vector<double> val[4];
 	int rows[4] = { 0, 0, 0, 0 }, cols[4] = { 0, 0, 0, 0 };
 	std::vector<double> PA, IA, PB;
+	// Newmark dynamics: Node::vel/accel/copy_vel/copy_accel, Dynamic::a1..a6, alpha, beta
+	std::vector<double> vel, accel, copy_vel, copy_accel;
+	double nm[6] = { 0, 0, 0, 0, 0, 0 }, ray_alpha = 0.0, ray_beta = 0.0;
 } W;
 
 const double* X(int node1) { return &W.ref[3 * (size_t)(node1 - 1)]; }
@@ -211,7 +225,15 @@ void shell_precalc(ShellEl& s, const int* nd, double E, double nu, double rho, d
 		double L1 = cw[g][0], L2 = cw[g][1], L3 = cw[g][2], w = A * cw[g][3];
 		double N4[6] = { (2 * L1 - 1) * L1, (2 * L2 - 1) * L2, (2 * L3 - 1) * L3, 4 * L1 * L2, 4 * L2 * L3, 4 * L3 * L1 };
 		for (int a = 0; a < 6; a++) s.grav[a] += w * N4[a];
+		for (int a = 0; a < 6; a++) s.N4u[g][a] = N4[a];                    // :2261-2269
+		s.N4a[g][0] = 1 - 2 * L3; s.N4a[g][1] = 1 - 2 * L1; s.N4a[g][2] = 1 - 2 * L2;
+		s.w4[g] = w;
 	}
+	s.coef1 = t * rho;                                                       // :2022-2024
+	s.coef2 = (1.0 / 12.0) * t * t * t * rho;
+	s.coef3 = rho * t * A / (3 * 3.1415926535897932384626433832795);
+	for (int g = 0; g < 3; g++) s.alpha_i[g] = V3();
+	s.CR.assign(27 * 27, 0.0);
 }
 
 // Shell_1.cpp:899-1332
@@ -260,6 +282,10 @@ void shell_mount(ShellEl& s, const int* nd)
 		V3 kap1 = tr(s.Q_i[g]) * (tr(Xi) * a_d1) + s.k1_i[g];
 		V3 kap2 = tr(s.Q_i[g]) * (tr(Xi) * a_d2) + s.k2_i[g];
 		s.Q_d[g] = Qd; s.Xi_d[g] = Xi; s.a_x1[g] = a_d1; s.a_x2[g] = a_d2; s.u_x1[g] = u_d1; s.u_x2[g] = u_d2;
+		V3 u_d;                                                              // :906-923, 993
+		for (int k = 0; k < 3; k++)
+			for (int a = 0; a < 6; a++) u_d[k] += W.disp[6 * (size_t)(nd[a] - 1) + k] * s.Nu[g][a];
+		s.u_d[g] = s.T3 * u_d; s.a_d[g] = a_d;
 
 		// thickness integration, Simo-Ciarlet plane-stress neo-Hookean (:1056-1163)
 		V3 n1, n2, m1, m2;
@@ -387,6 +413,7 @@ void shell_commit(ShellEl& s)
 		s.Q_i[g] = s.Q_d[g] * s.Q_i[g];
 		s.zx1_i[g] = s.u_x1[g] + s.zx1_i[g];
 		s.zx2_i[g] = s.u_x2[g] + s.zx2_i[g];
+		s.alpha_i[g] = (4.0 / (4.0 - dot(s.a_d[g], s.alpha_i[g]))) * (s.a_d[g] + s.alpha_i[g] + 0.5 * cross(s.a_d[g], s.alpha_i[g]));   // :1659-1660
 	}
 }
 
@@ -404,6 +431,11 @@ void beam_precalc(BeamEl& b, const int* nd, const double* hk, const double* sc, 
 	b.D(3, 3) = E * I1; b.D(4, 4) = E * I2; b.D(3, 4) = E * I12; b.D(4, 3) = E * I12; b.D(5, 5) = G * It;
 	b.rhoA = rho * A;
 	b.energy_on = true;
+	b.Mr = M3(); b.Jr = M3(); b.br = V3();                                   // :582-596
+	b.Mr(0, 0) = rho * A; b.Mr(1, 1) = rho * A; b.Mr(2, 2) = rho * A;
+	b.Jr(0, 0) = rho * I1; b.Jr(1, 1) = rho * I2; b.Jr(2, 2) = rho * sc[4]; b.Jr(0, 1) = rho * I12; b.Jr(1, 0) = rho * I12;
+	b.alpha_i[0] = V3(); b.alpha_i[1] = V3();
+	b.CR.assign(18 * 18, 0.0);
 	for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) b.T3(i, j) = cs[3 * i + j];
 	V3 e3 = Xv(nd[2]) - Xv(nd[0]);
 	e3 = (1.0 / norm(e3)) * e3;
@@ -495,6 +527,10 @@ void beam_mount(BeamEl& b, const int* nd)
 		if (b.energy_on) b.energy += 0.5 * (1.0 * b.jac) * (tr(sig) * eps)[0];
 		for (int i = 0; i < 6; i++) { b.res[g][i] = eps[i]; b.res[g][6 + i] = sig[i]; }
 		b.Q_d[g] = Qd; b.dz[g] = dz; b.kr[g] = kap;
+		V3 u_d;                                                              // :722-731, 743
+		for (int k = 0; k < 3; k++)
+			for (int a = 0; a < 3; a++) u_d[k] += W.disp[6 * (size_t)(nd[a] - 1) + k] * b.N[g][a];
+		b.u_d[g] = b.T3 * u_d; b.a_d[g] = a_d;
 	}
 	K = (tr(T) * K) * T;                                                     // :833-834
 	F = tr(T) * F;
@@ -524,6 +560,304 @@ void beam_commit(BeamEl& b)
 		b.Q_i[g] = b.Q_d[g] * b.Q_i[g];
 		b.k_i[g] = b.kr[g];
 		b.dz_i[g] = b.dz[g];
+		b.alpha_i[g] = (4.0 / (4.0 - dot(b.a_d[g], b.alpha_i[g]))) * (b.a_d[g] + b.alpha_i[g] + 0.5 * cross(b.a_d[g], b.alpha_i[g]));   // :1502-1503
+	}
+}
+
+
+// ------------------------------------------------------------------------
+// Newmark dynamics: MountMass / MountDamping / MountDyn of Beam_1 and Shell_1
+// (Beam_1.cpp:1537-1673, Shell_1.cpp:2367-2547).  The reference evaluates the
+// Gauss-point inertial pseudo-forces dT and their tangent DdT with AceGen-
+// generated code (Beam_1.cpp:1781-2361, Shell_1.cpp:2568-2890).  Restated here
+// from the formulation that code implements (Newmark in the tangent space of
+// the incremental rotation, Dynamic.cpp:480-556):
+//   Q = Q(alpha_d) Q(alpha_i),  Xi = Xi(alpha_d)
+//   omega  = Q(alpha_d) (a4 alpha_d + a5 omega_i + a6 domega_i)
+//   domega = Q(alpha_d) (a1 alpha_d - a2 omega_i - a3 domega_i)
+//   ddu    = a1 u_d - a2 du_i - a3 ddu_i
+//   Beam_1 : M = Q Mr Q^T, J = Q Jr Q^T, b = Q br
+//            f  = M (ddu + domega x b + omega x (omega x b))
+//            mu = M (b x ddu) + J domega + omega x (J omega)
+//   Shell_1: e3 = Q e3r,  f = coef1 ddu,  mu = coef2 e3 x (domega x e3 + omega x (omega x e3))
+//   dT = [f ; Xi^T mu],   DdT = d dT / d(u_d, alpha_d)
+// The tangent is obtained by forward-mode differentiation of dT (what AceGen
+// does symbolically), so DdT is the exact derivative of the same function.
+// ------------------------------------------------------------------------
+struct Du
+{
+	double v, d[6];
+	Du(double x = 0.0) : v(x) { for (int i = 0; i < 6; i++) d[i] = 0.0; }
+};
+Du operator+(Du a, const Du& b) { a.v += b.v; for (int i = 0; i < 6; i++) a.d[i] += b.d[i]; return a; }
+Du operator-(Du a, const Du& b) { a.v -= b.v; for (int i = 0; i < 6; i++) a.d[i] -= b.d[i]; return a; }
+Du operator-(Du a) { a.v = -a.v; for (int i = 0; i < 6; i++) a.d[i] = -a.d[i]; return a; }
+Du operator*(const Du& a, const Du& b) { Du o(a.v * b.v); for (int i = 0; i < 6; i++) o.d[i] = a.d[i] * b.v + a.v * b.d[i]; return o; }
+Du operator/(const Du& a, const Du& b) { Du o(a.v / b.v); for (int i = 0; i < 6; i++) o.d[i] = (a.d[i] - o.v * b.d[i]) / b.v; return o; }
+
+template <class T> void rot_Q(const T* a, T Q[3][3])             // I + g (A + A A / 2), g = 4 / (4 + |a|^2)
+{
+	T g = T(4.0) / (T(4.0) + a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+	T A[3][3] = { { T(0.0), -a[2], a[1] }, { a[2], T(0.0), -a[0] }, { -a[1], a[0], T(0.0) } };
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++)
+		{
+			T s2(0.0);
+			for (int k = 0; k < 3; k++) s2 = s2 + A[i][k] * A[k][j];
+			Q[i][j] = T(i == j ? 1.0 : 0.0) + g * (A[i][j] + T(0.5) * s2);
+		}
+}
+template <class T> void rot_Xi(const T* a, T X[3][3])            // g (I + A / 2)
+{
+	T g = T(4.0) / (T(4.0) + a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+	T A[3][3] = { { T(0.0), -a[2], a[1] }, { a[2], T(0.0), -a[0] }, { -a[1], a[0], T(0.0) } };
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) X[i][j] = g * (T(i == j ? 1.0 : 0.0) + T(0.5) * A[i][j]);
+}
+template <class T> void crossT(const T* a, const T* b, T* o)
+{ o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; }
+template <class T> void mulT(const T A[3][3], const T* x, T* o)
+{ for (int i = 0; i < 3; i++) o[i] = A[i][0] * x[0] + A[i][1] * x[1] + A[i][2] * x[2]; }
+
+// omega, domega, ddu, Q, Xi shared by both elements
+template <class T>
+void newmark_kinematics(const V3& alpha_i, const T* ad, const T* ud, const V3& om_i, const V3& dom_i, const V3& du_i,
+	const V3& ddu_i, T Q[3][3], T Xi[3][3], T* om, T* dom, T* ddu)
+{
+	const double a1 = W.nm[0], a2 = W.nm[1], a3 = W.nm[2], a4 = W.nm[3], a5 = W.nm[4], a6 = W.nm[5];
+	T Qd[3][3], Qi[3][3], ai[3] = { T(alpha_i[0]), T(alpha_i[1]), T(alpha_i[2]) };
+	rot_Q(ad, Qd); rot_Q(ai, Qi); rot_Xi(ad, Xi);
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) Q[i][j] = Qd[i][0] * Qi[0][j] + Qd[i][1] * Qi[1][j] + Qd[i][2] * Qi[2][j];
+	T wl[3], dwl[3];
+	for (int k = 0; k < 3; k++)
+	{
+		wl[k] = ad[k] * T(a4) + T(om_i[k] * a5) + T(dom_i[k] * a6);
+		dwl[k] = ad[k] * T(a1) - T(om_i[k] * a2) - T(dom_i[k] * a3);
+		ddu[k] = ud[k] * T(a1) - T(du_i[k] * a2) - T(ddu_i[k] * a3);
+	}
+	mulT(Qd, wl, om); mulT(Qd, dwl, dom);
+}
+
+template <class T>
+void beam_inertia(const V3& alpha_i, const T* ad, const T* ud, const V3& om_i, const V3& dom_i, const V3& du_i,
+	const V3& ddu_i, const M3& Jr, const M3& Mr, const V3& br, T* dT)
+{
+	T Q[3][3], Xi[3][3], w[3], dw[3], ddu[3];
+	newmark_kinematics(alpha_i, ad, ud, om_i, dom_i, du_i, ddu_i, Q, Xi, w, dw, ddu);
+	T M[3][3], J[3][3], b[3];
+	for (int i = 0; i < 3; i++)
+	{
+		b[i] = Q[i][0] * T(br[0]) + Q[i][1] * T(br[1]) + Q[i][2] * T(br[2]);
+		for (int j = 0; j < 3; j++)
+		{
+			T m(0.0), jj(0.0);
+			for (int k = 0; k < 3; k++)
+				for (int l = 0; l < 3; l++) { m = m + Q[i][k] * T(Mr(k, l)) * Q[j][l]; jj = jj + Q[i][k] * T(Jr(k, l)) * Q[j][l]; }
+			M[i][j] = m; J[i][j] = jj;
+		}
+	}
+	T wb[3], wwb[3], dwb[3], acc[3], f[3], bu[3], Mbu[3], Jdw[3], Jw[3], wJw[3], mu[3];
+	crossT(w, b, wb); crossT(w, wb, wwb); crossT(dw, b, dwb);
+	for (int k = 0; k < 3; k++) acc[k] = ddu[k] + dwb[k] + wwb[k];
+	mulT(M, acc, f);
+	crossT(b, ddu, bu); mulT(M, bu, Mbu); mulT(J, dw, Jdw); mulT(J, w, Jw); crossT(w, Jw, wJw);
+	for (int k = 0; k < 3; k++) mu[k] = Mbu[k] + Jdw[k] + wJw[k];
+	for (int k = 0; k < 3; k++)
+	{
+		dT[k] = f[k];
+		dT[3 + k] = Xi[0][k] * mu[0] + Xi[1][k] * mu[1] + Xi[2][k] * mu[2];
+	}
+}
+
+template <class T>
+void shell_inertia(const V3& alpha_i, const T* ad, const T* ud, const V3& om_i, const V3& dom_i, const V3& du_i,
+	const V3& ddu_i, const V3& e3r, double coef1, double coef2, T* dT)
+{
+	T Q[3][3], Xi[3][3], w[3], dw[3], ddu[3];
+	newmark_kinematics(alpha_i, ad, ud, om_i, dom_i, du_i, ddu_i, Q, Xi, w, dw, ddu);
+	T e3[3], we[3], wwe[3], dwe[3], acc[3], mu[3];
+	for (int i = 0; i < 3; i++) e3[i] = Q[i][0] * T(e3r[0]) + Q[i][1] * T(e3r[1]) + Q[i][2] * T(e3r[2]);
+	crossT(w, e3, we); crossT(w, we, wwe); crossT(dw, e3, dwe);
+	for (int k = 0; k < 3; k++) acc[k] = dwe[k] + wwe[k];
+	crossT(e3, acc, mu);
+	for (int k = 0; k < 3; k++)
+	{
+		dT[k] = T(coef1) * ddu[k];
+		dT[3 + k] = T(coef2) * (Xi[0][k] * mu[0] + Xi[1][k] * mu[1] + Xi[2][k] * mu[2]);
+	}
+}
+
+// seeds u_d (directions 0-2) and alpha_d (3-5), returns dT values and DdT
+template <class F>
+void with_tangent(const V3& a_d, const V3& u_d, F&& eval, Mx<6, 1>& dT, Mx<6, 6>& DdT)
+{
+	Du ad[3], ud[3], out[6];
+	for (int k = 0; k < 3; k++) { ud[k] = Du(u_d[k]); ud[k].d[k] = 1.0; ad[k] = Du(a_d[k]); ad[k].d[3 + k] = 1.0; }
+	eval(ad, ud, out);
+	for (int i = 0; i < 6; i++) { dT[i] = out[i].v; for (int j = 0; j < 6; j++) DdT(i, j) = out[i].d[j]; }
+}
+
+V3 nodal3(const std::vector<double>& arr, int node1, int off)
+{ const double* p = &arr[6 * (size_t)(node1 - 1) + off]; return vec(p[0], p[1], p[2]); }
+
+// Beam_1::MountMass (Beam_1.cpp:1564-1636), MountDamping (:1639-1664), MountDyn (:1667-1672)
+void beam_dynamics(BeamEl& b, const int* nd, bool update_rayleigh)
+{
+	Mx<18, 18> T; for (int k = 0; k < 6; k++) put(T, 3 * k, 3 * k, b.T3);
+	Mx<18, 18> mass; Mx<18, 1> inertial;
+	for (int g = 0; g < 2; g++)
+	{
+		V3 om, dom, du, ddu;
+		for (int a = 0; a < 3; a++)
+		{
+			om = om + b.N[g][a] * nodal3(W.copy_vel, nd[a], 3); dom = dom + b.N[g][a] * nodal3(W.copy_accel, nd[a], 3);
+			du = du + b.N[g][a] * nodal3(W.copy_vel, nd[a], 0); ddu = ddu + b.N[g][a] * nodal3(W.copy_accel, nd[a], 0);
+		}
+		om = b.T3 * om; dom = b.T3 * dom; du = b.T3 * du; ddu = b.T3 * ddu;     // :1618-1622
+		Mx<6, 1> dT; Mx<6, 6> DdT;
+		with_tangent(b.a_d[g], b.u_d[g], [&](const Du* ad, const Du* ud, Du* out)
+			{ beam_inertia(b.alpha_i[g], ad, ud, om, dom, du, ddu, b.Jr, b.Mr, b.br, out); }, dT, DdT);
+		Mx<6, 18> Nm;
+		for (int a = 0; a < 3; a++) for (int k = 0; k < 6; k++) Nm(k, 6 * a + k) = b.N[g][a];
+		inertial = inertial + (1.0 * b.jac) * (tr(Nm) * dT);
+		mass = mass + (1.0 * b.jac) * ((tr(Nm) * DdT) * Nm);
+	}
+	inertial = tr(T) * inertial;
+	mass = (tr(T) * mass) * T;
+	if (update_rayleigh)                                                         // MountMassModal :1537-1552
+	{
+		Mx<18, 18> mm;
+		for (int g = 0; g < 2; g++)
+		{
+			double ai[3] = { b.alpha_i[g][0], b.alpha_i[g][1], b.alpha_i[g][2] }, Qa[3][3];
+			rot_Q(ai, Qa);
+			M3 Q; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q(i, j) = Qa[i][j];
+			M3 M = (Q * b.Mr) * tr(Q), J = (Q * b.Jr) * tr(Q);
+			V3 bb = Q * b.br;
+			Mx<6, 6> MM;                                                         // EvaluateMassModal :1681-1777
+			put(MM, 0, 0, M); put(MM, 3, 3, J);
+			for (int i = 0; i < 3; i++)
+			{
+				V3 L = cross(vec(M(i, 0), M(i, 1), M(i, 2)), bb);
+				for (int j = 0; j < 3; j++) { MM(3 + i, j) = L[j]; MM(i, 3 + j) = -L[j]; }
+			}
+			Mx<6, 18> Nm;
+			for (int a = 0; a < 3; a++) for (int k = 0; k < 6; k++) Nm(k, 6 * a + k) = b.N[g][a];
+			mm = mm + (1.0 * b.jac) * ((tr(Nm) * MM) * Nm);
+		}
+		mm = (tr(T) * mm) * T;
+		for (int i = 0; i < 18 * 18; i++) b.CR[i] = W.ray_alpha * mm.a[i] + W.ray_beta * b.K[i];
+	}
+	double v[18], dl[18];
+	for (int a = 0; a < 3; a++) for (int k = 0; k < 6; k++) v[6 * a + k] = W.vel[6 * (size_t)(nd[a] - 1) + k];
+	for (int i = 0; i < 18; i++) { double sacc = 0.0; for (int j = 0; j < 18; j++) sacc += b.CR[i * 18 + j] * v[j]; dl[i] = sacc; }
+	for (int i = 0; i < 18; i++)
+	{
+		b.P[i] = b.P[i] + inertial[i] + dl[i];
+		for (int j = 0; j < 18; j++) b.K[i * 18 + j] = b.K[i * 18 + j] + mass(i, j) + W.nm[3] * b.CR[i * 18 + j];
+	}
+}
+
+// Shell_1::MountMass (Shell_1.cpp:2406-2498), MountDamping (:2501-2533), MountDyn (:2536-2541)
+void shell_dynamics(ShellEl& s, const int* nd, bool update_rayleigh)
+{
+	Mx<27, 27> T; for (int k = 0; k < 9; k++) put(T, 3 * k, 3 * k, s.T3);
+	Mx<27, 27> mass; Mx<27, 1> inertial;
+	const V3 e3r = vec(0, 0, 1);                                                 // e3rlocal :2006-2008
+	for (int g = 0; g < 3; g++)
+	{
+		V3 om, dom, du, ddu;
+		for (int a = 0; a < 3; a++)
+		{ om = om + s.Na[g][a] * nodal3(W.copy_vel, nd[3 + a], 3); dom = dom + s.Na[g][a] * nodal3(W.copy_accel, nd[3 + a], 3); }
+		for (int a = 0; a < 6; a++)
+		{ du = du + s.Nu[g][a] * nodal3(W.copy_vel, nd[a], 0); ddu = ddu + s.Nu[g][a] * nodal3(W.copy_accel, nd[a], 0); }
+		om = s.T3 * om; dom = s.T3 * dom; du = s.T3 * du; ddu = s.T3 * ddu;     // :2471-2474
+		Mx<6, 1> dT; Mx<6, 6> DdT;
+		with_tangent(s.a_d[g], s.u_d[g], [&](const Du* ad, const Du* ud, Du* out)
+			{ shell_inertia(s.alpha_i[g], ad, ud, om, dom, du, ddu, e3r, s.coef1, s.coef2, out); }, dT, DdT);
+		Mx<6, 27> Nm;
+		for (int k = 0; k < 3; k++)
+		{
+			for (int a = 0; a < 6; a++) Nm(k, 3 * a + k) = s.Nu[g][a];
+			for (int a = 0; a < 3; a++) Nm(3 + k, 18 + 3 * a + k) = s.Na[g][a];
+		}
+		inertial = inertial + s.alpha1 * (tr(Nm) * dT);
+		mass = mass + s.alpha1 * ((tr(Nm) * DdT) * Nm);
+	}
+	inertial = tr(T) * inertial;
+	mass = (tr(T) * mass) * T;
+	if (update_rayleigh)                                                         // MountMassModal :2367-2396
+	{
+		Mx<27, 27> mm;
+		for (int g = 0; g < 6; g++)
+		{
+			V3 ai;
+			for (int a = 0; a < 3; a++) ai = ai + s.N4a[g][a] * nodal3(W.copy, nd[3 + a], 3);
+			ai = s.T3 * ai;
+			double aa[3] = { ai[0], ai[1], ai[2] }, Qa[3][3];
+			rot_Q(aa, Qa);
+			double e3[3];
+			for (int i = 0; i < 3; i++) e3[i] = Qa[i][0] * e3r[0] + Qa[i][1] * e3r[1] + Qa[i][2] * e3r[2];
+			Mx<6, 6> MM;                                                         // EvaluateMassModal :3171-3221
+			for (int k = 0; k < 3; k++) MM(k, k) = s.coef1;
+			const double q0 = e3[0] * e3[0], q1 = e3[1] * e3[1], q2 = e3[2] * e3[2], dc = -s.coef2 + s.coef3;
+			MM(3, 3) = s.coef3 * q0 + s.coef2 * (q1 + q2); MM(4, 4) = s.coef3 * q1 + s.coef2 * (q0 + q2); MM(5, 5) = s.coef2 * (q1 + q0) + s.coef3 * q2;
+			MM(3, 4) = e3[0] * (e3[1] * dc); MM(3, 5) = e3[0] * e3[2] * dc; MM(4, 5) = e3[2] * (e3[1] * dc);
+			MM(4, 3) = MM(3, 4); MM(5, 3) = MM(3, 5); MM(5, 4) = MM(4, 5);
+			Mx<6, 27> Nm;
+			for (int k = 0; k < 3; k++)
+			{
+				for (int a = 0; a < 6; a++) Nm(k, 3 * a + k) = s.N4u[g][a];
+				for (int a = 0; a < 3; a++) Nm(3 + k, 18 + 3 * a + k) = s.N4a[g][a];
+			}
+			mm = mm + s.w4[g] * ((tr(Nm) * MM) * Nm);
+		}
+		mm = (tr(T) * mm) * T;
+		for (int i = 0; i < 27 * 27; i++) s.CR[i] = W.ray_alpha * mm.a[i] + W.ray_beta * s.K[i];
+	}
+	double v[27], dl[27];
+	for (int a = 0; a < 6; a++) for (int k = 0; k < 3; k++) v[3 * a + k] = W.vel[6 * (size_t)(nd[a] - 1) + k];
+	for (int a = 0; a < 3; a++) for (int k = 0; k < 3; k++) v[18 + 3 * a + k] = W.vel[6 * (size_t)(nd[3 + a] - 1) + 3 + k];
+	for (int i = 0; i < 27; i++) { double sacc = 0.0; for (int j = 0; j < 27; j++) sacc += s.CR[i * 27 + j] * v[j]; dl[i] = sacc; }
+	for (int i = 0; i < 27; i++)
+	{
+		s.P[i] = s.P[i] + inertial[i] + dl[i];
+		for (int j = 0; j < 27; j++) s.K[i * 27 + j] = s.K[i * 27 + j] + mass(i, j) + W.nm[3] * s.CR[i * 27 + j];
+	}
+}
+
+// Dynamic::UpdateDyn (Dynamic.cpp:480-556), node DOFs.  vel_aux / ace_aux live outside the node loop in
+// the reference: a rotational DOF that is not free keeps the value left by the previous node.
+void update_dyn()
+{
+	const double a1 = W.nm[0], a2 = W.nm[1], a3 = W.nm[2], a4 = W.nm[3], a5 = W.nm[4], a6 = W.nm[5];
+	V3 vel_aux, ace_aux;
+	for (int i = 0; i < W.n_nodes; i++)
+	{
+		const double* d = &W.disp[6 * (size_t)i]; const int* gl = &W.gls[6 * (size_t)i];
+		const double* cv = &W.copy_vel[6 * (size_t)i]; const double* ca = &W.copy_accel[6 * (size_t)i];
+		double* v = &W.vel[6 * (size_t)i]; double* ac = &W.accel[6 * (size_t)i];
+		for (int j = 0; j < 3; j++)
+			if (gl[j] > 0)
+			{
+				v[j] = d[j] * a4 + cv[j] * a5 + ca[j] * a6;
+				ac[j] = d[j] * a1 - cv[j] * a2 - ca[j] * a3;
+			}
+		V3 ad = vec(d[3], d[4], d[5]);
+		double al = norm(ad);
+		M3 A = skew(ad);
+		double g = 4.0 / (4.0 + al * al);
+		M3 Qd = eye3() + g * (A + 0.5 * (A * A));
+		for (int j = 3; j < 6; j++)
+			if (gl[j] > 0)
+			{
+				vel_aux[j - 3] = d[j] * a4 + cv[j] * a5 + ca[j] * a6;
+				ace_aux[j - 3] = d[j] * a1 - cv[j] * a2 - ca[j] * a3;
+			}
+		vel_aux = Qd * vel_aux; ace_aux = Qd * ace_aux;
+		for (int j = 3; j < 6; j++)
+			if (gl[j] > 0) { v[j] = vel_aux[j - 3]; ac[j] = ace_aux[j - 3]; }
 	}
 }
 
@@ -777,9 +1111,12 @@ int gfo_set_extra_triplets(int which, long n, const int* r, const int* c, const 
 	return 0;
 }
 
-int gfo_assemble(const double* disp6, double lfac, double* seconds)
+static int assemble(const double* disp6, double lfac, double* seconds, int dynamic, int update_rayleigh)
 {
 	W.disp.assign(disp6, disp6 + 6 * (size_t)W.n_nodes);
+	if (dynamic)
+		for (int e = 0; e < W.n_el; e++)
+			if (W.type[e] == T_SOLID || (W.type[e] == T_BEAM && W.is_pipe[e])) return -7;   // no dynamic path restated for them
 	double t0 = now_s();
 	for (int w = 0; w < 4; w++) W.trip[w] = W.extra[w];                      // Clear + MountLoads
 	W.PA.assign(W.n_free, 0.0); W.IA.assign(W.n_free, 0.0); W.PB.assign(W.n_fixed, 0.0);
@@ -798,6 +1135,16 @@ int gfo_assemble(const double* disp6, double lfac, double* seconds)
 	{
 		if (W.type[e] == T_SHELL) shell_loads(W.shells[W.slot[e]], lfac);
 		else if (W.type[e] == T_BEAM) beam_loads(W.beams[W.slot[e]], lfac);
+	}
+	if (dynamic)
+	{
+#pragma omp parallel for schedule(static)
+		for (int e = 0; e < W.n_el; e++)                                     // MountMass, MountDamping, MountDyn (Solution.cpp:711-759)
+		{
+			const int* nd = &W.nodes[W.nptr[e]];
+			if (W.type[e] == T_SHELL) shell_dynamics(W.shells[W.slot[e]], nd, update_rayleigh != 0);
+			else beam_dynamics(W.beams[W.slot[e]], nd, update_rayleigh != 0);
+		}
 	}
 	double t3 = now_s();
 	for (int e = 0; e < W.n_el; e++)                                         // MountGlobal, serial (:322-349)
@@ -829,6 +1176,60 @@ int gfo_assemble(const double* disp6, double lfac, double* seconds)
 	double t5 = now_s();
 	if (seconds) { seconds[0] = t2 - t1; seconds[1] = t3 - t2; seconds[2] = t4 - t3; seconds[3] = t5 - t4; seconds[4] = t1 - t0; }
 	return 0;
+}
+
+int gfo_assemble(const double* disp6, double lfac, double* seconds) { return assemble(disp6, lfac, seconds, 0, 0); }
+
+// ---- Newmark dynamics (Dynamic.cpp:303-340) ----
+int gfo_set_dynamic(const double* newmark6, double rayleigh_alpha, double rayleigh_beta)
+{
+	for (int i = 0; i < 6; i++) W.nm[i] = newmark6[i];
+	W.ray_alpha = rayleigh_alpha; W.ray_beta = rayleigh_beta;
+	return 0;
+}
+static void ensure_kinematics()
+{
+	const size_t n = 6 * (size_t)W.n_nodes;
+	if (W.vel.size() != n) { W.vel.assign(n, 0.0); W.accel.assign(n, 0.0); W.copy_vel.assign(n, 0.0); W.copy_accel.assign(n, 0.0); }
+}
+int gfo_set_kinematics(const double* vel, const double* accel, const double* copy_vel, const double* copy_accel)
+{
+	ensure_kinematics();
+	const size_t n = 6 * (size_t)W.n_nodes;
+	if (vel) W.vel.assign(vel, vel + n);
+	if (accel) W.accel.assign(accel, accel + n);
+	if (copy_vel) W.copy_vel.assign(copy_vel, copy_vel + n);
+	if (copy_accel) W.copy_accel.assign(copy_accel, copy_accel + n);
+	return 0;
+}
+int gfo_get_kinematics(double* vel, double* accel, double* copy_vel, double* copy_accel)
+{
+	ensure_kinematics();
+	const size_t n = sizeof(double) * 6 * (size_t)W.n_nodes;
+	if (vel) std::memcpy(vel, W.vel.data(), n);
+	if (accel) std::memcpy(accel, W.accel.data(), n);
+	if (copy_vel) std::memcpy(copy_vel, W.copy_vel.data(), n);
+	if (copy_accel) std::memcpy(copy_accel, W.copy_accel.data(), n);
+	return 0;
+}
+int gfo_update_dyn(const double* disp6)
+{
+	ensure_kinematics();
+	W.disp.assign(disp6, disp6 + 6 * (size_t)W.n_nodes);
+	update_dyn();
+	return 0;
+}
+int gfo_assemble_dynamic(const double* disp6, double lfac, int update_rayleigh)
+{
+	ensure_kinematics();
+	return assemble(disp6, lfac, NULL, 1, update_rayleigh);
+}
+int gfo_get_alpha_i(int e, double* out)
+{
+	int w = 0;
+	if (W.type[e] == T_SHELL) { const ShellEl& s = W.shells[W.slot[e]]; for (int g = 0; g < 3; g++) for (int i = 0; i < 3; i++) out[w++] = s.alpha_i[g][i]; }
+	else if (W.type[e] == T_BEAM) { const BeamEl& b = W.beams[W.slot[e]]; for (int g = 0; g < 2; g++) for (int i = 0; i < 3; i++) out[w++] = b.alpha_i[g][i]; }
+	return w;
 }
 
 long gfo_triplet_count(int w) { return (long)W.trip[w].size(); }
@@ -929,6 +1330,7 @@ int gfo_commit(void)
 		else if (W.type[e] == T_BEAM) beam_commit(W.beams[W.slot[e]]);
 	}
 	std::fill(W.disp.begin(), W.disp.end(), 0.0);
+	if (!W.vel.empty()) { W.copy_vel = W.vel; W.copy_accel = W.accel; }       // Node.cpp:375-380
 	return 0;
 }
 int gfo_get_copy_coordinates(double* c) { std::memcpy(c, W.copy.data(), sizeof(double) * W.copy.size()); return 0; }

@@ -60,6 +60,19 @@ int  gfo_get_results(int e, double* out);
 int  gfo_commit(void);
 int  gfo_get_copy_coordinates(double* c6);
 
+
+/* Newmark dynamics (Dynamic.cpp:303-340): Beam_1 and Shell_1 only (Pipe_1 / Solid_1 return -7).
+ * newmark6 = Dynamic::a1..a6; kinematics arrays are Node::vel / accel / copy_vel / copy_accel [n_nodes*6]
+ * (NULL = leave / skip).  gfo_assemble_dynamic = Clear, MountLocal, MountElementLoads, MountMass,
+ * MountDamping(update_rayleigh), MountDyn, MountGlobal, MountSparse.  gfo_commit also copies vel/accel
+ * (Node.cpp:375-380) and updates alpha_i. */
+int gfo_set_dynamic(const double* newmark6, double rayleigh_alpha, double rayleigh_beta);
+int gfo_set_kinematics(const double* vel, const double* accel, const double* copy_vel, const double* copy_accel);
+int gfo_get_kinematics(double* vel, double* accel, double* copy_vel, double* copy_accel);
+int gfo_update_dyn(const double* disp6);      /* Dynamic::UpdateDyn */
+int gfo_assemble_dynamic(const double* disp6, double gravity_factor, int update_rayleigh);
+int gfo_get_alpha_i(int e, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,12 @@ class PortOracle:
         L.gfo_get_state.argtypes = [C.c_int, _D]
         L.gfo_get_results.argtypes = [C.c_int, _D]
         L.gfo_get_copy_coordinates.argtypes = [_D]
+        L.gfo_set_dynamic.argtypes = [_D, C.c_double, C.c_double]
+        L.gfo_set_kinematics.argtypes = [C.c_void_p] * 4
+        L.gfo_get_kinematics.argtypes = [C.c_void_p] * 4
+        L.gfo_update_dyn.argtypes = [_D]
+        L.gfo_assemble_dynamic.argtypes = [_D, C.c_double, C.c_int]
+        L.gfo_get_alpha_i.argtypes = [C.c_int, _D]
         if threads:
             L.gfo_set_threads(int(threads))
         self.model = None
@@ -159,4 +165,38 @@ class PortOracle:
     def state(self, e: int) -> np.ndarray:
         buf = np.zeros(64)
         n = self.lib.gfo_get_state(e, buf)
+        return buf[:n].copy()
+
+    # ---- Newmark dynamics (Dynamic.cpp:303-340) -------------------------------
+    @staticmethod
+    def newmark_coefficients(time_step: float, beta_new: float = 0.3, gamma_new: float = 0.5) -> np.ndarray:
+        """Dynamic::CalculateNewmarkCoeff (Dynamic.cpp:582-590): a1..a6"""
+        dt, b, g = float(time_step), float(beta_new), float(gamma_new)
+        return np.array([1.0 / (dt * dt * b), 1.0 / (dt * b), 1.0 / (2.0 * b) - 1.0, g / (dt * b), 1.0 - g / b,
+                         dt * (1.0 - g / (2.0 * b))])
+
+    def set_dynamic(self, newmark6, rayleigh_alpha: float = 0.0, rayleigh_beta: float = 0.0):
+        self.lib.gfo_set_dynamic(np.ascontiguousarray(newmark6, np.float64), float(rayleigh_alpha), float(rayleigh_beta))
+
+    def set_kinematics(self, vel=None, accel=None, copy_vel=None, copy_accel=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64).reshape(-1) for a in (vel, accel, copy_vel, copy_accel)]
+        self.lib.gfo_set_kinematics(*[None if a is None else a.ctypes.data for a in arrs])
+
+    def kinematics(self):
+        out = [np.zeros(self.model.n_nodes * 6) for _ in range(4)]
+        self.lib.gfo_get_kinematics(*[a.ctypes.data for a in out])
+        return tuple(a.reshape(-1, 6) for a in out)
+
+    def update_dyn(self, disp):
+        self.lib.gfo_update_dyn(np.ascontiguousarray(disp, np.float64).reshape(-1))
+
+    def assemble_dynamic(self, disp, update_rayleigh: bool, with_loads: bool = False):
+        r = self.lib.gfo_assemble_dynamic(np.ascontiguousarray(disp, np.float64).reshape(-1), float(self.gravity_factor),
+                                          1 if update_rayleigh else 0)
+        if r != 0:
+            raise ValueError("dynamic assembly is restated for Beam_1 and Shell_1 only")
+
+    def alpha_i(self, e: int) -> np.ndarray:
+        buf = np.zeros(16)
+        n = self.lib.gfo_get_alpha_i(e, buf)
         return buf[:n].copy()

@@ -36,6 +36,7 @@
 #include "NodalLoad.h"
 #include "Environment.h"
 #include "Solution.h"
+#include "Dynamic.h"
 #include "LagrangeSave.h"
 #include "ConvergenceCriteria.h"
 
@@ -56,7 +57,8 @@ struct OracleSolution : public Solution
 	bool Solve() { return true; }
 };
 
-OracleSolution* g_sol = NULL;
+Solution* g_sol = NULL;          // OracleSolution (static steps) or the reference's own Dynamic
+Dynamic* g_dyn = NULL;
 
 template <class T> T** grow(T** arr, int n_old)
 {
@@ -106,7 +108,8 @@ int ref_reset()
 	db.number_loads = 0; db.loads = NULL;
 	db.environment = NULL; db.environment_exist = false;
 	db.n_GL_free = 0; db.n_GL_fixed = 0;
-	if (!g_sol)
+	g_dyn = NULL;
+	if (!g_sol || dynamic_cast<Dynamic*>(g_sol))
 	{
 		g_sol = new OracleSolution();
 		g_sol->solution_number = 1;
@@ -523,6 +526,88 @@ int ref_commit()
 	for (int i = 0; i < db.number_nodes; i++)
 		for (int k = 0; k < 6; k++) db.nodes[i]->displacements[k] = 0.0;
 	return 0;
+}
+
+// ---- Dynamic (Newmark) path: the steps Dynamic::Solve runs per time step and per Newton iteration
+// (reference Dynamic.cpp:303-340), on the reference's own Dynamic object so that the typeid checks in
+// Element::MountMass / MountDamping (Beam_1.cpp:1566, Shell_1.cpp:2478) see a Dynamic solution.
+int ref_dynamic_begin(double beta_new, double gamma_new, double rayleigh_alpha, double rayleigh_beta, int update)
+{
+	g_dyn = new Dynamic();
+	g_dyn->solution_number = 1;
+	g_dyn->start_time = 0.0;
+	g_dyn->end_time = 1.0;
+	g_dyn->beta_new = beta_new; g_dyn->gamma_new = gamma_new;
+	g_dyn->alpha = rayleigh_alpha; g_dyn->beta = rayleigh_beta; g_dyn->update = update;
+	db.solution[0] = g_dyn;
+	g_sol = g_dyn;
+	return 0;
+}
+// Dynamic::CalculateNewmarkCoeff (Dynamic.cpp:582-590); a6[0..5] = a1..a6
+int ref_newmark(double time_step, double* a6)
+{
+	if (!g_dyn) return -1;
+	g_dyn->CalculateNewmarkCoeff(time_step);
+	a6[0] = g_dyn->a1; a6[1] = g_dyn->a2; a6[2] = g_dyn->a3; a6[3] = g_dyn->a4; a6[4] = g_dyn->a5; a6[5] = g_dyn->a6;
+	return 0;
+}
+// Node::vel / accel / copy_vel / copy_accel, [n_nodes*6] each; NULL pointers are skipped
+int ref_set_kinematics(const double* vel, const double* accel, const double* copy_vel, const double* copy_accel)
+{
+	for (int i = 0; i < db.number_nodes; i++)
+		for (int k = 0; k < 6; k++)
+		{
+			if (vel) db.nodes[i]->vel[k] = vel[6 * i + k];
+			if (accel) db.nodes[i]->accel[k] = accel[6 * i + k];
+			if (copy_vel) db.nodes[i]->copy_vel[k] = copy_vel[6 * i + k];
+			if (copy_accel) db.nodes[i]->copy_accel[k] = copy_accel[6 * i + k];
+		}
+	return 0;
+}
+int ref_get_kinematics(double* vel, double* accel, double* copy_vel, double* copy_accel)
+{
+	for (int i = 0; i < db.number_nodes; i++)
+		for (int k = 0; k < 6; k++)
+		{
+			if (vel) vel[6 * i + k] = db.nodes[i]->vel[k];
+			if (accel) accel[6 * i + k] = db.nodes[i]->accel[k];
+			if (copy_vel) copy_vel[6 * i + k] = db.nodes[i]->copy_vel[k];
+			if (copy_accel) copy_accel[6 * i + k] = db.nodes[i]->copy_accel[k];
+		}
+	return 0;
+}
+// Dynamic::UpdateDyn (Dynamic.cpp:480-580)
+int ref_update_dyn()
+{
+	if (!g_dyn) return -1;
+	g_dyn->UpdateDyn();
+	return 0;
+}
+// One Newton iteration of Dynamic::Solve (Dynamic.cpp:323-340) up to MountSparse
+int ref_assemble_dynamic(int with_loads, int update_rayleigh)
+{
+	if (!g_dyn) return -1;
+	g_sol->Clear();
+	g_sol->MountLocal();
+	g_sol->MountElementLoads();
+	if (with_loads) g_sol->MountLoads();
+	g_sol->MountMass();
+	g_sol->MountDamping(update_rayleigh != 0);
+	g_sol->MountDyn();
+	g_sol->MountGlobal();
+	g_sol->MountSparse();
+	return 0;
+}
+// Committed Rodrigues vector alpha_i of every Gauss point (Shell_1: 3 x 3, Beam_1: 2 x 3)
+int ref_get_alpha_i(int e, double* out)
+{
+	Element* el = db.elements[e];
+	int w = 0;
+	if (Shell_1* s = dynamic_cast<Shell_1*>(el))
+		for (int g = 0; g < 3; g++) for (int i = 0; i < 3; i++) out[w++] = (*s->alpha_i[g])(i, 0);
+	else if (Beam_1* b = dynamic_cast<Beam_1*>(el))
+		for (int g = 0; g < 2; g++) for (int i = 0; i < 3; i++) out[w++] = (*b->lag_save->alpha_i[g])(i, 0);
+	return w;
 }
 
 // The Newton-loop steps either side of the assembly, through the reference's own code:

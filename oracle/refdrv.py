@@ -68,6 +68,12 @@ class RefOracle:
         L.ref_update_displacements.argtypes = [_D, np.ctypeslib.ndpointer(np.int32, flags='C'), _D]
         L.ref_get_results.argtypes = [C.c_int, _D]
         L.ref_set_threads.argtypes = [C.c_int]
+        L.ref_dynamic_begin.argtypes = [C.c_double] * 4 + [C.c_int]
+        L.ref_newmark.argtypes = [C.c_double, _D]
+        L.ref_set_kinematics.argtypes = [C.c_void_p] * 4
+        L.ref_get_kinematics.argtypes = [C.c_void_p] * 4
+        L.ref_assemble_dynamic.argtypes = [C.c_int, C.c_int]
+        L.ref_get_alpha_i.argtypes = [C.c_int, _D]
         if threads:
             L.ref_set_threads(int(threads))
         self.model = None
@@ -215,4 +221,41 @@ class RefOracle:
     def state(self, e: int) -> np.ndarray:
         buf = np.zeros(64)
         n = self.lib.ref_get_state(e, buf)
+        return buf[:n].copy()
+
+    # ---- Dynamic (Newmark) path: Dynamic.cpp:303-340 ----------------------
+    def dynamic_begin(self, beta_new=0.3, gamma_new=0.5, rayleigh_alpha=0.0, rayleigh_beta=0.0, update=0):
+        """Replace the solution object by the reference's own Dynamic (call after load())."""
+        self.lib.ref_dynamic_begin(float(beta_new), float(gamma_new), float(rayleigh_alpha), float(rayleigh_beta), int(update))
+
+    def newmark(self, time_step: float) -> np.ndarray:
+        a = np.zeros(6)
+        if self.lib.ref_newmark(float(time_step), a) < 0:
+            raise RuntimeError("dynamic_begin() first")
+        return a
+
+    def set_kinematics(self, vel=None, accel=None, copy_vel=None, copy_accel=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64).reshape(-1) for a in (vel, accel, copy_vel, copy_accel)]
+        self.lib.ref_set_kinematics(*[None if a is None else a.ctypes.data for a in arrs])
+
+    def kinematics(self):
+        """(vel, accel, copy_vel, copy_accel), each [n_nodes, 6]"""
+        out = [np.zeros(self.model.n_nodes * 6) for _ in range(4)]
+        self.lib.ref_get_kinematics(*[a.ctypes.data for a in out])
+        return tuple(a.reshape(-1, 6) for a in out)
+
+    def update_dyn(self, disp):
+        """Dynamic::UpdateDyn for the given Node::displacements"""
+        self.lib.ref_set_displacements(np.ascontiguousarray(disp, np.float64).reshape(-1))
+        if self.lib.ref_update_dyn() < 0:
+            raise RuntimeError("dynamic_begin() first")
+
+    def assemble_dynamic(self, disp, update_rayleigh: bool, with_loads: bool = False):
+        self.lib.ref_set_displacements(np.ascontiguousarray(disp, np.float64).reshape(-1))
+        if self.lib.ref_assemble_dynamic(1 if with_loads else 0, 1 if update_rayleigh else 0) < 0:
+            raise RuntimeError("dynamic_begin() first")
+
+    def alpha_i(self, e: int) -> np.ndarray:
+        buf = np.zeros(16)
+        n = self.lib.ref_get_alpha_i(e, buf)
         return buf[:n].copy()
