@@ -29,6 +29,7 @@ EXPORTS = [
     "gfa_commit_state", "gfa_element_state", "gfa_results_stride", "gfa_gauss_point_results",
     "gfa_residual", "gfa_update_displacements", "gfa_displacements", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
+    "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i",
 ]
 
 
@@ -64,6 +65,12 @@ class _NormsStruct(C.Structure):
 
 class _StepStruct(C.Structure):
     _fields_ = [("displacements", C.c_void_p), ("displacements_on_device", C.c_int32), ("gravity_factor", C.c_double)]
+
+
+class _DynamicStruct(C.Structure):
+    """gfa_dynamic_t: Dynamic::a1..a6, alpha, beta and the MountDamping(update_rayleigh) flag"""
+    _fields_ = [("a1", C.c_double), ("a2", C.c_double), ("a3", C.c_double), ("a4", C.c_double), ("a5", C.c_double),
+                ("a6", C.c_double), ("rayleigh_alpha", C.c_double), ("rayleigh_beta", C.c_double), ("update_rayleigh", C.c_int32)]
 
 
 _lib = None
@@ -108,6 +115,11 @@ def load_library() -> C.CDLL:
         lib.gfa_owned_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
         lib.gfa_local_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
         lib.gfa_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.gfa_set_kinematics.argtypes = [C.c_void_p] * 5
+        lib.gfa_kinematics.argtypes = [C.c_void_p] * 5
+        lib.gfa_update_dyn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DynamicStruct)]
+        lib.gfa_assemble_dynamic.argtypes = [C.c_void_p, C.POINTER(_StepStruct), C.POINTER(_DynamicStruct)]
+        lib.gfa_element_alpha_i.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -230,6 +242,48 @@ class Assembler:
         st.gravity_factor = float(self.gravity_factor)
         self._check(self.lib.gfa_assemble(self._h, C.byref(st)))
         return self
+
+    # ---- Newmark dynamics (Dynamic.cpp:303-340) ------------------------------
+    def set_dynamic(self, newmark6, rayleigh_alpha: float = 0.0, rayleigh_beta: float = 0.0):
+        """Dynamic::a1..a6 of the time step (Dynamic.cpp:582-590) and the Rayleigh coefficients."""
+        d = _DynamicStruct()
+        d.a1, d.a2, d.a3, d.a4, d.a5, d.a6 = [float(v) for v in newmark6]
+        d.rayleigh_alpha, d.rayleigh_beta, d.update_rayleigh = float(rayleigh_alpha), float(rayleigh_beta), 0
+        self._dyn = d
+        return self
+
+    def set_kinematics(self, vel=None, accel=None, copy_vel=None, copy_accel=None):
+        arrs = [None if a is None else np.ascontiguousarray(a, np.float64).reshape(-1) for a in (vel, accel, copy_vel, copy_accel)]
+        self._check(self.lib.gfa_set_kinematics(self._h, *[None if a is None else a.ctypes.data for a in arrs]))
+
+    def kinematics(self):
+        """(vel, accel, copy_vel, copy_accel), each [n_nodes, 6]"""
+        out = [np.zeros(self.model.n_nodes * 6) for _ in range(4)]
+        self._check(self.lib.gfa_kinematics(self._h, *[a.ctypes.data for a in out]))
+        return tuple(a.reshape(-1, 6) for a in out)
+
+    def update_dyn(self, disp=None):
+        """Dynamic::UpdateDyn; disp None = the device copy of Node::displacements"""
+        d = None if disp is None else np.ascontiguousarray(disp, np.float64).reshape(-1)
+        self._check(self.lib.gfa_update_dyn(self._h, None if d is None else d.ctypes.data, C.byref(self._dyn)))
+
+    def assemble_dynamic(self, disp, update_rayleigh: bool):
+        st = _StepStruct()
+        if disp is None:
+            st.displacements, st.displacements_on_device = None, 0
+        else:
+            d = np.ascontiguousarray(disp, np.float64).reshape(-1)
+            self._keep_disp = d
+            st.displacements, st.displacements_on_device = d.ctypes.data, 0
+        st.gravity_factor = float(self.gravity_factor)
+        self._dyn.update_rayleigh = 1 if update_rayleigh else 0
+        self._check(self.lib.gfa_assemble_dynamic(self._h, C.byref(st), C.byref(self._dyn)))
+        return self
+
+    def alpha_i(self, e: int):
+        buf = np.zeros(16)
+        n = self._check(self.lib.gfa_element_alpha_i(self._h, e, _ptr(buf)))
+        return buf[:n].copy()
 
     def assemble_raw(self, host_ptr: int):
         """Host pointer (e.g. pinned memory) without numpy marshalling."""

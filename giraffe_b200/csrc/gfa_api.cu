@@ -90,6 +90,9 @@ struct TypeBlock {
     int pe_base = 0;
     DevBuf<int> d_conn, d_prop;
     DevBuf<double> d_props, d_pret, d_state, d_geo, d_shp;
+    // Newmark dynamics: committed Rodrigues vector per Gauss point (always kept: SaveLagrange updates it in
+    // static steps too), per-element record and Element::rayleigh_damping (allocated on first use)
+    DevBuf<double> d_alpha_i, d_dynrec, d_CR;
 };
 
 struct HostCsr {
@@ -118,6 +121,11 @@ struct gfa_handle {
     double grav[3] = { 0, 0, 0 };
 
     DevBuf<double> d_xyz, d_copy, d_disp, d_Ke, d_Pe;
+    // Newmark dynamics: Node::vel / accel / copy_vel / copy_accel (allocated on first use), nodes whose
+    // rotational DOFs are partly free (Dynamic::UpdateDyn replay) and where each replay starts
+    DevBuf<double> d_vel, d_accel, d_cvel, d_caccel;
+    DevBuf<int> d_mixed, d_mixed_start;
+    int n_mixed = 0;
 
     // DOF map / pattern
     bool dofs_set = false;
@@ -199,6 +207,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         return fail(GFA_EINVAL, "gfa_create: bad partition rank %d of %d", m->part_rank, m->part_world);
     CUDA_TRY(cudaSetDevice(device));
     int cfg = configure_kernels();
+    if (cfg == 0) cfg = configure_dynamics();
     if (cfg != 0) return fail(GFA_ECUDA, "kernel configuration: %s", cudaGetErrorString((cudaError_t)cfg));
 
     gfa_t* h = new gfa_handle();
@@ -294,6 +303,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
                     for (int i = 0; i < 9; i++) row[36 + i] = m->cs[9 * (size_t)(cs - 1) + i];
                     row[45] = ps[4];            // mass per unit length (gravity: Pipe_1.cpp:1311-1330 without ocean data)
                     row[46] = 0.0;              // Pipe_1::Mount leaves strain_energy at zero
+                                                // row[47..50]: no dynamic path for Pipe_1 (added mass needs ocean data)
                     t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
                 } else if (s == 1) {    // Beam_1::PreCalc, Beam_1.cpp:560-580
                     const double* sc = m->sections + 6 * (size_t)(sec - 1);
@@ -305,6 +315,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
                     for (int i = 0; i < 9; i++) row[36 + i] = m->cs[9 * (size_t)(cs - 1) + i];
                     row[45] = rho * sc[0];
                     row[46] = 1.0;
+                    row[47] = rho * sc[1]; row[48] = rho * sc[2]; row[49] = rho * sc[4]; row[50] = rho * sc[3];   // Jr, Beam_1.cpp:587-591
                     t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
                 } else {                // builder-defined Solid_1: Lame constants of the Hooke material
                     const double mu = E / (2.0 * (1 + nu));
@@ -350,6 +361,10 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
             if (e == cudaSuccess) e = t.d_props.upload(t.props);
             if (e == cudaSuccess && t.any_pret) e = t.d_pret.upload(t.pret);
             if (e == cudaSuccess) e = t.d_state.upload(state_init[s]);
+            if (e == cudaSuccess && kTypes[s].nstate) {                    // alpha_i = 0 (LagrangeSave.cpp:16-18, Shell_1.cpp:163)
+                e = t.d_alpha_i.alloc(3 * t.elems.size() * kTypes[s].ngp);
+                if (e == cudaSuccess && t.d_alpha_i.n) e = cudaMemset(t.d_alpha_i.p, 0, t.d_alpha_i.n * sizeof(double));
+            }
         }
         if (pe > 0x7fffffffLL) FAIL_FREE(GFA_EUNSUPPORTED, "element force arena exceeds 2^31 entries");
         if (e == cudaSuccess) e = h->d_Ke.alloc((size_t)ke);
@@ -823,6 +838,19 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         CUDA_TRY(h->d_ab_inner.upload(inner));
         CUDA_TRY(h->d_norm.alloc(1));
     }
+    {   // Dynamic::UpdateDyn (Dynamic.cpp:493-556): nodes whose rotational DOFs are partly free see the values
+        // earlier nodes left in vel_aux / ace_aux; each replay starts at the last node that overwrote all three
+        std::vector<int> mixed, start;
+        int last_full = 0;
+        for (int i = 0; i < h->n_nodes; i++) {
+            const int* g = &gls[6 * (size_t)i];
+            const int nf = (g[3] > 0) + (g[4] > 0) + (g[5] > 0);
+            if (nf == 3) last_full = i;
+            else if (nf > 0) { mixed.push_back(i); start.push_back(last_full); }
+        }
+        h->n_mixed = (int)mixed.size();
+        if (h->n_mixed) { CUDA_TRY(h->d_mixed.upload(mixed)); CUDA_TRY(h->d_mixed_start.upload(start)); }
+    }
     h->dofs_set = true;
     return GFA_OK;
 }
@@ -845,10 +873,57 @@ int gfa_csr_pattern(gfa_t* h, int which, int32_t* outer, int32_t* inner) {
     return GFA_OK;
 }
 
-int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
+} // extern "C"
+
+namespace {
+
+int ensure_kinematics(gfa_t* h) {
+    const size_t n = 6 * (size_t)h->n_nodes;
+    if (h->d_vel.n == n) return GFA_OK;
+    DevBuf<double>* bufs[4] = { &h->d_vel, &h->d_accel, &h->d_cvel, &h->d_caccel };
+    for (DevBuf<double>* b : bufs) {
+        CUDA_TRY(b->alloc(n));
+        CUDA_TRY(cudaMemset(b->p, 0, n * sizeof(double)));
+    }
+    return GFA_OK;
+}
+
+DynArgs dyn_args(gfa_t* h, int slot, const gfa_dynamic_t* d) {
+    DynArgs a;
+    a.a1 = d->a1; a.a2 = d->a2; a.a3 = d->a3; a.a4 = d->a4; a.a5 = d->a5; a.a6 = d->a6;
+    a.ray_alpha = d->rayleigh_alpha; a.ray_beta = d->rayleigh_beta; a.update = d->update_rayleigh != 0;
+    a.vel = h->d_vel.p; a.copy_vel = h->d_cvel.p; a.copy_accel = h->d_caccel.p;
+    a.alpha_i = slot >= 0 ? h->tb[slot].d_alpha_i.p : nullptr;
+    a.rec = slot >= 0 ? h->tb[slot].d_dynrec.p : nullptr;
+    a.CR = slot >= 0 ? h->tb[slot].d_CR.p : nullptr;
+    return a;
+}
+
+int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
     if (!h || !st) return fail(GFA_EINVAL, "gfa_assemble: null argument");
     if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_assemble before gfa_set_dofs");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (dyn) {
+        // MountMass / MountDamping exist on the device for Beam_1 and Shell_1; Pipe_1's added mass needs ocean
+        // data (Pipe_1.cpp:1560-1583) and Solid_1 has no arithmetic in the reference
+        if (!h->tb[2].elems.empty()) return fail(GFA_EUNSUPPORTED, "gfa_assemble_dynamic: Solid_1 has no dynamic contributions");
+        for (int e : h->tb[1].elems)
+            if (h->el_type[e] == GFA_PIPE_1) return fail(GFA_EUNSUPPORTED, "gfa_assemble_dynamic: Pipe_1 dynamic contributions stay on the host");
+        int rc = ensure_kinematics(h);
+        if (rc != GFA_OK) return rc;
+        for (int slot = 0; slot < 2; slot++) {
+            TypeBlock& t = h->tb[slot];
+            if (t.elems.empty()) continue;
+            const size_t rec = (slot == 0 ? SHELL_DYN_REC : BEAM_DYN_REC) * t.elems.size();
+            if (t.d_dynrec.n != rec) CUDA_TRY(t.d_dynrec.alloc(rec));
+            const bool rayleigh = dyn->update_rayleigh && (dyn->rayleigh_alpha != 0.0 || dyn->rayleigh_beta != 0.0);
+            const size_t cr = (size_t)arena_doubles(slot) * t.elems.size();
+            if (rayleigh && t.d_CR.n != cr) {           // Element::rayleigh_damping, zero until the first update
+                CUDA_TRY(t.d_CR.alloc(cr));
+                CUDA_TRY(cudaMemset(t.d_CR.p, 0, cr * sizeof(double)));
+            }
+        }
+    }
     cudaStream_t s = h->stream;
     const size_t nd = 6 * (size_t)h->n_nodes * sizeof(double);
     int launches = 0;
@@ -863,6 +938,11 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
         const EvalArgs ea = eval_args(h, slot, st->gravity_factor);
         if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
         launches++;
+        if (dyn) {      // MountMass + MountDamping + MountDyn folded into the element blocks before the scatter
+            const DynArgs da = dyn_args(h, slot, dyn);
+            if (slot == 0) launch_shell_dynamics(ea, da, s); else launch_beam_dynamics(ea, da, s);
+            launches += 2;
+        }
     }
     CUDA_TRY(cudaEventRecord(h->ev[2], s));
     // MountGlobal + MountSparse
@@ -888,6 +968,77 @@ int gfa_assemble(gfa_t* h, const gfa_step_t* st) {
     h->last_launches = launches;
     h->assembled = true;
     return GFA_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int gfa_assemble(gfa_t* h, const gfa_step_t* st) { return assemble_impl(h, st, nullptr); }
+
+int gfa_assemble_dynamic(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
+    if (!dyn) return fail(GFA_EINVAL, "gfa_assemble_dynamic: null argument");
+    return assemble_impl(h, st, dyn);
+}
+
+int gfa_set_kinematics(gfa_t* h, const double* vel, const double* accel, const double* copy_vel, const double* copy_accel) {
+    if (!h) return fail(GFA_EINVAL, "gfa_set_kinematics: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_kinematics(h);
+    if (rc != GFA_OK) return rc;
+    const size_t nb = 6 * (size_t)h->n_nodes * sizeof(double);
+    const double* src[4] = { vel, accel, copy_vel, copy_accel };
+    double* dst[4] = { h->d_vel.p, h->d_accel.p, h->d_cvel.p, h->d_caccel.p };
+    for (int k = 0; k < 4; k++)
+        if (src[k]) CUDA_TRY(cudaMemcpyAsync(dst[k], src[k], nb, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_kinematics(gfa_t* h, double* vel, double* accel, double* copy_vel, double* copy_accel) {
+    if (!h) return fail(GFA_EINVAL, "gfa_kinematics: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_kinematics(h);
+    if (rc != GFA_OK) return rc;
+    const size_t nb = 6 * (size_t)h->n_nodes * sizeof(double);
+    double* dst[4] = { vel, accel, copy_vel, copy_accel };
+    const double* src[4] = { h->d_vel.p, h->d_accel.p, h->d_cvel.p, h->d_caccel.p };
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; k++)
+        if (dst[k]) CUDA_TRY(cudaMemcpy(dst[k], src[k], nb, cudaMemcpyDeviceToHost));
+    return GFA_OK;
+}
+
+int gfa_update_dyn(gfa_t* h, const double* displacements, const gfa_dynamic_t* dyn) {
+    if (!h || !dyn) return fail(GFA_EINVAL, "gfa_update_dyn: null argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_update_dyn before gfa_set_dofs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_kinematics(h);
+    if (rc != GFA_OK) return rc;
+    if (displacements)
+        CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, displacements, 6 * (size_t)h->n_nodes * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_update_dyn(dyn_args(h, -1, dyn), h->d_gls.p, h->d_disp.p, h->d_vel.p, h->d_accel.p, h->n_nodes,
+                      h->d_mixed.p, h->d_mixed_start.p, h->n_mixed, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GFA_OK;
+}
+
+int gfa_element_alpha_i(gfa_t* h, int32_t e, double* out) {
+    if (!h || e < 0 || e >= h->n_el || !out) return fail(GFA_EINVAL, "gfa_element_alpha_i: bad argument");
+    const int s = h->el_owner_slot[e];
+    if (s < 0) return fail(GFA_EINVAL, "element %d belongs to another rank's partition", e + 1);
+    if (kTypes[s].nstate == 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const size_t ngp = h->tb[s].elems.size() * kTypes[s].ngp;
+    int w = 0;
+    for (int g = 0; g < kTypes[s].ngp; g++)
+        for (int k = 0; k < 3; k++) {
+            CUDA_TRY(cudaMemcpy(out + w, h->tb[s].d_alpha_i.p + (size_t)k * ngp + (size_t)h->el_local[e] * kTypes[s].ngp + g, sizeof(double), cudaMemcpyDeviceToHost));
+            w++;
+        }
+    return w;
 }
 
 int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, const int32_t* cols, const double* vals) {
@@ -1008,7 +1159,14 @@ int gfa_commit_state(gfa_t* h) {
     CUDA_TRY(cudaSetDevice(h->device));
     launch_shell_commit(eval_args(h, 0, 0.0), h->stream);
     launch_beam_commit(eval_args(h, 1, 0.0), h->stream);
+    launch_shell_alpha_commit(eval_args(h, 0, 0.0), h->tb[0].d_alpha_i.p, h->stream);      // alpha_i (Shell_1.cpp:1659, Beam_1.cpp:1502)
+    launch_beam_alpha_commit(eval_args(h, 1, 0.0), h->tb[1].d_alpha_i.p, h->stream);
     launch_node_commit(h->n_nodes, h->d_copy.p, h->d_disp.p, h->stream);
+    if (h->d_vel.n) {       // copy_vel = vel, copy_accel = accel (Node.cpp:375-380)
+        const size_t nb = h->d_vel.n * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(h->d_cvel.p, h->d_vel.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_caccel.p, h->d_accel.p, nb, cudaMemcpyDeviceToDevice, h->stream));
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return GFA_OK;

@@ -29,7 +29,8 @@ struct EvalArgs {
 };
 
 constexpr int SHELL_PROP_STRIDE = 5;   // lambda, mu, thickness, stiff_drill, rho
-constexpr int BEAM_PROP_STRIDE = 47;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A, strain-energy switch (1 Beam_1, 0 Pipe_1)
+constexpr int BEAM_PROP_STRIDE = 51;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A, strain-energy switch (1 Beam_1, 0 Pipe_1),
+                                       // Jr = rho*(I11, I22, I33, I12) (Beam_1.cpp:587-591; zero for Pipe_1: no dynamic path)
 constexpr int SOLID_PROP_STRIDE = 3;   // lambda, mu, rho
 
 constexpr int SHELL_RESULTS = 73;      // strain_energy + 3 x (eta1 eta2 kappa1 kappa2 n1 n2 m1 m2)
@@ -120,6 +121,37 @@ struct NormAcc {                    // filled by the norm kernels; doubles are >
     int nan;                                // NaN seen in v
     int pad;
 };
+// ---- Newmark dynamics: MountMass + MountDamping + MountDyn (Beam_1.cpp:1564-1673, Shell_1.cpp:2406-2541),
+//      Dynamic::UpdateDyn (Dynamic.cpp:480-556) ------------------------------------------------------
+// Phase 1 (one thread per element) writes a small record per element; phase 2 (one warp per element) folds
+// it and the stored Rayleigh matrix into the element arena in place, coalesced.
+//   record = [uu NU*NU | aa 3*3*9 | P ndof | modal uu NU*NU | modal aa 3*3*9]
+//   uu(a,b): scalar s of the translation-translation block s*I3 of nodes (a,b); aa(a,b): 3x3 rotation-rotation
+//   block of the rotational nodes (Shell_1: nodes 4-6), global axes; P: inertial_loading in local DOF order.
+constexpr int BEAM_DYN_REC = 9 + 81 + 18 + 9 + 81;
+constexpr int SHELL_DYN_REC = 36 + 81 + 27 + 36 + 81;
+struct DynArgs {
+    double a1, a2, a3, a4, a5, a6;      // Dynamic::a1..a6
+    double ray_alpha, ray_beta;         // Dynamic::alpha, beta
+    int update;                         // MountDamping(update_rayleigh)
+    const double* vel;                  // [n_nodes*6] Node::vel
+    const double* copy_vel;             // Node::copy_vel
+    const double* copy_accel;           // Node::copy_accel
+    double* alpha_i;                    // committed Rodrigues vector per Gauss point, SoA [3][n_gp], element frame
+    double* rec;                        // [n_el * *_DYN_REC]
+    double* CR;                         // Element::rayleigh_damping in the layout of the Ke arena, or nullptr (= zero)
+};
+void launch_shell_dynamics(const EvalArgs& a, const DynArgs& d, void* stream);   // 2 launches
+void launch_beam_dynamics(const EvalArgs& a, const DynArgs& d, void* stream);    // 2 launches
+void launch_shell_alpha_commit(const EvalArgs& a, double* alpha_i, void* stream);
+void launch_beam_alpha_commit(const EvalArgs& a, double* alpha_i, void* stream);
+// vel/accel of every node from the displacement increments; `mixed` lists the nodes whose rotational DOFs are
+// partly free (they see the values the reference's loop leaves from earlier nodes), `start` the node each
+// replay begins at
+void launch_update_dyn(const DynArgs& d, const int* gls, const double* disp, double* vel, double* accel, int n_nodes,
+                       const int* mixed, const int* start, int n_mixed, void* stream);
+int configure_dynamics();   // constant tables; returns cudaError_t as int
+
 void launch_negate(double* v, long long n, void* stream);
 void launch_sub_ab_xb(double* PA, const int* rows, const int* ptr, const int* inner, const double* vals, const double* XB, int n_rows, void* stream);
 void launch_update_disps(const int* gls, double* disp, const double* x, int n_nodes, void* stream);

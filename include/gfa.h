@@ -217,6 +217,44 @@ int gfa_residual(gfa_t* h, const double* X_B /* [n_fixed] host, or NULL */, gfa_
 int gfa_update_displacements(gfa_t* h, const double* x_A /* [n_free] host */, gfa_norms_t* out);
 int gfa_displacements(gfa_t* h, double* host_out /* [n_nodes*6] */);
 
+/* ---- Newmark dynamics: the element contributions Dynamic::Solve adds per Newton iteration -------------
+ * (SURVEY.md 8f rank 1).  Beam_1 and Shell_1; a model that holds Pipe_1 (added mass needs ocean data,
+ * src/Pipe_1.cpp:1560-1583) or Solid_1 elements gets GFA_EUNSUPPORTED from gfa_assemble_dynamic. */
+typedef struct gfa_dynamic {
+    double a1, a2, a3, a4, a5, a6;   /* Dynamic::a1..a6 of the current time step (src/Dynamic.cpp:582-590) */
+    double rayleigh_alpha;           /* Dynamic::alpha (mass-proportional)       (src/Dynamic.h:26-27) */
+    double rayleigh_beta;            /* Dynamic::beta  (stiffness-proportional) */
+    int32_t update_rayleigh;         /* the argument of Solution::MountDamping: recompute Element::rayleigh_damping =
+                                      * alpha*mass_modal + beta*stiffness from this iteration's stiffness
+                                      * (first iteration of the solution step, or every iteration when Dynamic::update == 1;
+                                      * src/Dynamic.cpp:329-335); otherwise the stored matrix is used */
+} gfa_dynamic_t;
+
+/* Node::vel / accel / copy_vel / copy_accel, [n_nodes*6] host arrays each (src/Node.h); NULL = leave the
+ * device copy as it is (all four start at zero).  InitialCondition / prescribed motions write them on the
+ * host and push them here; gfa_update_dyn and gfa_commit_state maintain them afterwards. */
+int gfa_set_kinematics(gfa_t* h, const double* vel, const double* accel, const double* copy_vel, const double* copy_accel);
+int gfa_kinematics(gfa_t* h, double* vel, double* accel, double* copy_vel, double* copy_accel);
+
+/* Dynamic::UpdateDyn for node DOFs (src/Dynamic.cpp:480-556): vel / accel of every free DOF from the
+ * displacement increments (`displacements` host [n_nodes*6], or NULL = the device copy left by
+ * gfa_assemble / gfa_update_displacements), rotations rotated by Q(alpha_delta) as the reference does.
+ * A rotational DOF that is not free keeps, in the reference's loop, the value the previous node left in
+ * vel_aux / ace_aux; nodes with partly-free rotations reproduce that by replaying the loop. */
+int gfa_update_dyn(gfa_t* h, const double* displacements, const gfa_dynamic_t* dyn);
+
+/* One Newton iteration of Dynamic::Solve up to MountSparse (src/Dynamic.cpp:323-340): gfa_assemble plus
+ * Element::MountMass (src/Beam_1.cpp:1564-1636, src/Shell_1.cpp:2406-2498), MountDamping
+ * (src/Beam_1.cpp:1639-1664, src/Shell_1.cpp:2501-2533) and MountDyn (src/Beam_1.cpp:1667-1672,
+ * src/Shell_1.cpp:2536-2541) folded into the element blocks before the scatter: the CSR values hold
+ * stiffness + mass + a4*rayleigh_damping, the vectors P_loading + inertial_loading + damping_loading.
+ * gfa_commit_state afterwards also saves alpha_i and copies vel/accel (src/Node.cpp:375-380). */
+int gfa_assemble_dynamic(gfa_t* h, const gfa_step_t* step, const gfa_dynamic_t* dyn);
+
+/* Committed Rodrigues rotation vector alpha_i of every Gauss point of one element, element frame
+ * (src/Shell_1.h:121, src/LagrangeSave.h:12): 3 per point; returns the number of doubles written. */
+int gfa_element_alpha_i(gfa_t* h, int32_t element, double* out);
+
 /* Timing of the last gfa_assemble, milliseconds from CUDA events on the
  * library's stream: [0] H2D of displacements, [1] element evaluation
  * (MountLocal+MountElementLoads), [2] scatter (MountGlobal+MountSparse),

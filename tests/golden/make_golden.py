@@ -20,6 +20,10 @@ Newton iteration and the reference's CSR matrices (AA/AB/BA/BB) and vectors
                    iterations, a commit (SaveLagrange) and one more iteration.
   shell_plate.npz  6x4-cell warped Shell_1 plate with gravity (doubled
                    self-weight quirk), same sequence.
+  dynamic_beam.npz, dynamic_shell.npz
+                   Newmark path (Dynamic.cpp:303-340): UpdateDyn, MountMass,
+                   MountDamping (Rayleigh update on the first iteration), MountDyn
+                   over two iterations, a commit and a third iteration.
 """
 import os
 import sys
@@ -119,8 +123,42 @@ def newton_steps(R):
     print("newton_steps: n_free", R.n_free, "n_fixed", R.n_fixed, "nodes", z["residual_nodes"], z["increment_nodes"])
 
 
+def dynamic_models():
+    """Beam_1 line and warped Shell_1 plate for the Newmark path; each has a node whose rotational DOFs are
+    only partly free (UpdateDyn's vel_aux / ace_aux carry-over, Dynamic.cpp:493-556)."""
+    mb = M.beam_line(14, pretension=2.0e5)
+    mb.gravity = (0.4, -0.3, -9.81)
+    mb.constraints = mb.constraints + [([9], 0x08), ([10], 0x38), ([16], 0x30)]
+    ms = M.shell_plate(5, 3, warp=0.01, gravity=(0.0, 0.0, -9.81))
+    mids = sorted(set(int(n) for n in ms.elem_nodes.reshape(-1, 6)[:, 3:].reshape(-1)))
+    ms.constraints = ms.constraints + [([mids[7]], 0x10), ([mids[20]], 0x28)]
+    db = M.mask_displacements(mb, M.beam_line_displacements(mb))
+    db[8, 3] = 2.0e-3; db[9, 3:6] = (1.0e-3, -2.0e-3, 1.5e-3); db[15, 4:6] = (-1.0e-3, 0.5e-3)      # prescribed rotations
+    ds = M.mask_displacements(ms, M.shell_plate_displacements(ms))
+    ds[mids[7] - 1, 4] = 1.0e-3; ds[mids[20] - 1, 3] = -1.0e-3; ds[mids[20] - 1, 5] = 2.0e-3
+    return (("dynamic_beam", mb, db, 20240011), ("dynamic_shell", ms, ds, 20240012))
+
+
+def dynamic(R):
+    """Newmark path through the reference's own Dynamic / MountMass / MountDamping / MountDyn / UpdateDyn."""
+    for name, m, d, seed in dynamic_models():
+        R.load(m)
+        R.set_time(0.0, 0.7)
+        z = util.model_to_dict(m)
+        z["time"] = np.array([0.0, 0.7])
+        z["gls"] = R.gls()
+        z.update(util.dynamic_scenario(m, d, seed))
+        util.run_dynamic(R, m, z, util.capture_dynamic(z, (1, m.n_elements - 1)))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **z)
+        print(name, "n_free", R.n_free, "nnz_AA", len(z["s1_AA_val"]))
+
+
 if __name__ == "__main__":
     R = RefOracle(threads=1)
+    if sys.argv[1:] == ["dynamic"]:          # only the fixtures of the Newmark path
+        dynamic(R)
+        sys.exit(0)
+    dynamic(R)
     newton_steps(R)
     tutorial01(R)
     mb = M.beam_line(24, pretension=2.0e5)

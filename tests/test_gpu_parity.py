@@ -375,3 +375,56 @@ def test_newton_vector_steps_on_device():
     # NaN in the increment is flagged, not propagated into the maxima
     x = z["x_A"].copy(); x[3] = np.nan
     assert asm.update_displacements(x)["nan_detected"] == 1
+
+
+# ---- Newmark dynamics -----------------------------------------------------
+@pytest.mark.parametrize("name", ["dynamic_beam", "dynamic_shell"])
+def test_newmark_dynamics_against_reference_fixture(name):
+    """gfa_update_dyn + gfa_assemble_dynamic + gfa_commit_state against what the reference's own Dynamic /
+    MountMass / MountDamping / MountDyn / UpdateDyn produced (tests/golden/make_golden.py): CSR values,
+    vectors, vel/accel (incl. nodes with partly-free rotations), alpha_i after the commit."""
+    z = _golden(name)
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(*z["time"])
+    assert (asm.gls == z["gls"]).all()
+    util.run_dynamic(asm, m, z, util.check_dynamic(z, (1, m.n_elements - 1), name))
+
+
+def test_newmark_dynamics_against_oracle(port):
+    """Mixed Beam_1 + Shell_1 model, larger than the fixtures, with and without Rayleigh damping; the stored
+    rayleigh_damping must survive iterations that do not update it."""
+    m = M.concat_models([M.beam_line(70, pretension=3.0e4), M.shell_plate(9, 7, warp=0.015, gravity=(0.0, 0.0, -9.81))])
+    d = M.mask_displacements(m, np.random.default_rng(11).uniform(-1e-3, 1e-3, (m.n_nodes, 6)))
+    for k, rayleigh in enumerate([(0.0, 0.0), (0.5, 3.0e-4)]):
+        scen = util.dynamic_scenario(m, d, 500 + k, time_step=0.002, rayleigh=rayleigh)
+        port.load(m)
+        port.set_time(0.0, 0.4)
+        z = dict(scen)
+        els = (0, 69, 70, m.n_elements - 1)
+        util.run_dynamic(port, m, scen, util.capture_dynamic(z, els))
+        asm = capi.Assembler(m).set_dofs()
+        asm.set_time(0.0, 0.4)
+        util.run_dynamic(asm, m, scen, util.check_dynamic(z, els, f"dynamic mixed rayleigh={rayleigh}"))
+        asm.close()
+
+
+def test_static_steps_keep_alpha_i_and_dynamic_rejects_unsupported_types(port):
+    """SaveLagrange updates alpha_i in static steps too (Shell_1.cpp:1659, Beam_1.cpp:1502); Pipe_1 / Solid_1
+    have no dynamic path on the device."""
+    m = M.concat_models([M.beam_line(6), M.shell_plate(3, 2, warp=0.01)])
+    d = M.mask_displacements(m, np.random.default_rng(2).uniform(-2e-3, 2e-3, (m.n_nodes, 6)))
+    port.load(m)
+    asm = capi.Assembler(m).set_dofs()
+    for _ in range(2):
+        port.assemble(d); asm.assemble(d)
+        port.commit(); asm.commit()
+    for e in (0, 5, 6, m.n_elements - 1):
+        util.assert_parity(port.alpha_i(e), asm.alpha_i(e), f"alpha_i of element {e} after two static commits")
+    asm.close()
+    ms = M.solid_block(2, 2, 2)
+    a2 = capi.Assembler(ms).set_dofs()
+    a2.set_dynamic(util.newmark_coefficients(0.01))
+    with pytest.raises(capi.GfaError):
+        a2.assemble_dynamic(np.zeros((ms.n_nodes, 6)), True)
+    a2.close()

@@ -106,3 +106,15 @@ def test_newton_steps_restatement_against_reference_fixture(port):
     assert np.array_equal(d2, z["disp_after"])
     inc = ns.increment_norms(z["gls"], z["x_A"], d2)
     assert (inc["node_force"], inc["node_moment"], inc["nan_detected"]) == tuple(int(v) for v in z["increment_nodes"])
+
+
+@pytest.mark.parametrize("name", ["dynamic_beam", "dynamic_shell"])
+def test_newmark_dynamics(port, name):
+    """Dynamic::Solve's element contributions (MountMass, MountDamping with a Rayleigh update, MountDyn) and
+    UpdateDyn, incl. nodes with partly-free rotations, against what the reference's own Dynamic produced."""
+    z = _load(name)
+    m = util.model_from_dict(z)
+    port.load(m)
+    port.set_time(*z["time"])
+    assert (port.gls() == z["gls"]).all()
+    util.run_dynamic(port, m, z, util.check_dynamic(z, (1, m.n_elements - 1), name))

@@ -59,3 +59,26 @@ def test_section_and_cs_constants(ref):
     for k in (1, 2):
         assert np.array_equal(ref.section(k), m.sections[k - 1])
         assert np.array_equal(ref.cs(k), m.cs[k - 1])
+
+
+@pytest.mark.parametrize("rayleigh", [(0.0, 0.0), (0.35, 2.0e-4)], ids=["undamped", "rayleigh"])
+def test_port_newmark_dynamics_match_reference_sources(ref, port, rayleigh):
+    """Seeded models other than the fixtures: the port's formulation-level restatement of the AceGen inertia
+    code (forward-mode tangent) against the reference's own MountMass / MountDamping / MountDyn / UpdateDyn."""
+    b = M.beam_line(30, pretension=5.0e4)
+    b.gravity = (0.1, 0.2, -9.81)
+    b.constraints = b.constraints + [([21], 0x20), ([22], 0x18)]
+    s = M.shell_plate(4, 5, warp=0.02, gravity=(0.0, 0.0, -9.81))
+    mixed = M.concat_models([M.beam_line(8), M.shell_plate(3, 3, warp=0.005)])
+    cases = [("beam", b, M.beam_line_displacements(b)), ("shell", s, M.shell_plate_displacements(s)),
+             ("mixed", mixed, np.random.default_rng(3).uniform(-1e-3, 1e-3, (mixed.n_nodes, 6)))]
+    for k, (name, m, d) in enumerate(cases):
+        scen = util.dynamic_scenario(m, M.mask_displacements(m, d), 77 + k, time_step=0.004, rayleigh=rayleigh)
+        ref.load(m)
+        ref.set_time(0.0, 0.5)
+        z = dict(scen)
+        els = (0, m.n_elements - 1)
+        util.run_dynamic(ref, m, scen, util.capture_dynamic(z, els))
+        port.load(m)
+        port.set_time(0.0, 0.5)
+        util.run_dynamic(port, m, scen, util.check_dynamic(z, els, name))

@@ -226,3 +226,90 @@ def assert_results_parity(ref, got, what):
     for k in range(per_point):
         scale = float(np.abs(body_r[:, :, k]).max())
         assert_parity(body_r[:, :, k].ravel(), body_g[:, :, k].ravel(), f"{what} group {k}", max(scale, 1e-300))
+
+
+# ---- Newmark dynamics: one scenario driven identically on every backend -------------------------
+# (RefOracle = the reference's own Dynamic object, PortOracle = the CPU restatement, Assembler = the
+# C-ABI library).  Sequence of Dynamic::Solve (Dynamic.cpp:303-340, Solution.cpp:426-454):
+#   time step 1: UpdateDyn, assembly with MountDamping(true); UpdateDyn, assembly with MountDamping(false);
+#                SaveConfiguration (alpha_i, copy_vel/copy_accel)
+#   time step 2: UpdateDyn, assembly with MountDamping(false)  -> non-zero alpha_i, stored rayleigh_damping
+def newmark_coefficients(time_step: float, beta_new: float = 0.3, gamma_new: float = 0.5) -> np.ndarray:
+    """Dynamic::CalculateNewmarkCoeff (Dynamic.cpp:582-590): a1..a6"""
+    dt, b, g = float(time_step), float(beta_new), float(gamma_new)
+    return np.array([1.0 / (dt * dt * b), 1.0 / (dt * b), 1.0 / (2.0 * b) - 1.0, g / (dt * b), 1.0 - g / b,
+                     dt * (1.0 - g / (2.0 * b))])
+
+
+def dynamic_scenario(m: M.Model, disp: np.ndarray, seed: int, time_step=0.01, rayleigh=(0.7, 1.0e-4)) -> dict:
+    rng = np.random.default_rng(seed)
+    n = m.n_nodes
+    return {
+        "dyn_dt": np.array([time_step]), "dyn_rayleigh": np.array(rayleigh, float),
+        "dyn_copy_vel": rng.uniform(-1.0, 1.0, (n, 6)) * np.array([1, 1, 1, 0.5, 0.5, 0.5]),
+        "dyn_copy_accel": rng.uniform(-10.0, 10.0, (n, 6)),
+        "dyn_disp": np.stack([disp, 0.6 * disp, -0.4 * disp]),
+    }
+
+
+DYN_STEPS = (("s1", 0, True, False), ("s2", 1, False, True), ("s3", 2, False, False))   # tag, disp index, update_rayleigh, commit after
+
+
+def run_dynamic(backend, m: M.Model, scen: dict, on_step):
+    """Drives `backend` through the scenario; on_step(tag, backend) is called after every assembly and
+    on_step(tag + '_commit', backend) after the commit."""
+    dt = float(scen["dyn_dt"][0])
+    ra, rb = [float(v) for v in scen["dyn_rayleigh"]]
+    if hasattr(backend, "dynamic_begin"):         # the reference computes its own coefficients
+        backend.dynamic_begin(0.3, 0.5, ra, rb, 0)
+        a = backend.newmark(dt)
+        assert np.array_equal(a, newmark_coefficients(dt))
+    else:
+        backend.set_dynamic(newmark_coefficients(dt), ra, rb)
+    zeros = np.zeros((m.n_nodes, 6))
+    backend.set_kinematics(zeros, zeros, scen["dyn_copy_vel"], scen["dyn_copy_accel"])
+    for tag, k, update, commit in DYN_STEPS:
+        d = scen["dyn_disp"][k]
+        backend.update_dyn(d)
+        backend.assemble_dynamic(d, update)
+        on_step(tag, backend)
+        if commit:
+            backend.commit()
+            on_step(tag + "_commit", backend)
+
+
+def capture_dynamic(z: dict, elements):
+    """on_step callback that records everything into z (fixture generation)."""
+    def cb(tag, b):
+        if tag.endswith("_commit"):
+            for e in elements:
+                z[f"{tag}_alpha_i{e}"] = b.alpha_i(e)
+            z[f"{tag}_kin"] = np.stack(b.kinematics())
+            return
+        z.update(capture(b, tag))
+        z[f"{tag}_kin"] = np.stack(b.kinematics())
+        for e in elements:
+            K, P = b.element(e)[:2]
+            z[f"{tag}_elem{e}_K"], z[f"{tag}_elem{e}_P"] = K, P
+    return cb
+
+
+def check_dynamic(z, elements, what: str):
+    """on_step callback that compares a backend with a recorded fixture / another capture."""
+    def cb(tag, b):
+        if tag.endswith("_commit"):
+            for e in elements:
+                assert_parity(z[f"{tag}_alpha_i{e}"], b.alpha_i(e), f"{what} {tag} alpha_i of element {e}")
+            for r, g, key in zip(z[f"{tag}_kin"], b.kinematics(), ("vel", "accel", "copy_vel", "copy_accel")):
+                assert_parity(r, g, f"{what} {tag} {key}")
+            return
+        assert_system_parity(lambda w: captured_csr(z, tag, w), b.csr, f"{what} {tag}")
+        for v, key in zip(b.vectors(), ("PA", "IA", "PB")):
+            assert_parity(z[f"{tag}_{key}"], v, f"{what} {tag} {key}")
+        for r, g, key in zip(z[f"{tag}_kin"], b.kinematics(), ("vel", "accel", "copy_vel", "copy_accel")):
+            assert_parity(r, g, f"{what} {tag} {key}")
+        for e in elements:
+            K, P = b.element(e)[:2]
+            assert_parity(z[f"{tag}_elem{e}_K"], K, f"{what} {tag} element {e} K", block_scale(z[f"{tag}_elem{e}_K"]))
+            assert_parity(z[f"{tag}_elem{e}_P"], P, f"{what} {tag} element {e} P")
+    return cb
