@@ -1359,31 +1359,30 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 // =========================================================================
 constexpr int SCATTER_THREADS = 256;
 
-// row ii of a 3x3 source block (column ii when the stored block is the transposed twin)
-GFA_DI void load_row(const double* Ke, unsigned off, bool tr, int ii, double (&x)[3]) {
-    const double* p = Ke + (size_t)off + (tr ? ii : 3 * ii);
-    const int st = tr ? 3 : 1;
+// column c of the 3x3 destination patch: D(i,c) = S(i,c), or S(c,i) when the stored block is the transposed twin
+GFA_DI void load_col(const double* Ke, unsigned off, bool tr, int c, double (&x)[3]) {
+    const double* p = Ke + (size_t)off + (tr ? 3 * c : c);
+    const int st = tr ? 1 : 3;
     x[0] = p[0]; x[1] = p[st]; x[2] = p[2 * st];
 }
 
-// One THREAD per CSR patch row: thread t owns row ii = t % 3 of patch t / 3 (= one (group-node,
-// neighbour) pair).  It gathers that row of the contributing 3x3 blocks straight from the arena --
+// One THREAD per CSR patch column: thread t owns column c = t % 3 of patch t / 3 (= one (group-node,
+// neighbour) pair).  It gathers that column of the contributing 3x3 blocks straight from the arena --
 // all loads of the first two issued before the first add, element-ascending adds in registers (the
-// order the reference pushes and Eigen sums, Solution.cpp:327-328) -- and writes <= 3 consecutive
-// values of one CSR row.  The three threads of a patch read one contiguous 72-byte block together and
-// consecutive patches of a group-node are consecutive in its rows, so loads arrive at the L1 a few
-// lines per request (one thread per whole patch: 32 lines per request, L1 wavefront pipe 75 % busy,
-// profiles/r01_notes.md) and every CSR row is written once, in whole sectors.
-// No shared memory, no atomics, no synchronisation.
+// order the reference pushes and Eigen sums, Solution.cpp:327-328) -- and writes one value into each of
+// the patch's <= 3 CSR rows.  The three threads of a patch read one contiguous 72-byte block together
+// (24 contiguous bytes per load when the block is stored as is) and write 24 contiguous bytes of one
+// CSR row per store; consecutive patches of a group-node are consecutive in its rows, so every CSR row
+// is written once, in whole sectors.  No shared memory, no atomics, no synchronisation.
 __global__ void __launch_bounds__(SCATTER_THREADS) scatter_kernel(ScatterArgs A) {
     const long long t = (long long)blockIdx.x * SCATTER_THREADS + threadIdx.x;
     const long long j = t / 3;
     if (j >= A.n_runs) return;
-    const int ii = (int)(t - 3 * j);
+    const int c = (int)(t - 3 * j);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(A.runs) + j);
     const unsigned info = q.y;
     const int L = info & 0xffff, rm = (info >> 16) & 7, fm = (info >> 19) & 7, cnt = info >> 24;
-    if (!((rm >> ii) & 1)) return;
+    if (!((fm >> c) & 1)) return;
     double a[3];
     {
         unsigned s0 = q.z, s1 = q.w;
@@ -1393,24 +1392,24 @@ __global__ void __launch_bounds__(SCATTER_THREADS) scatter_kernel(ScatterArgs A)
             s0 = (unsigned)e0; t0 = (e0 & SRC_T) != 0; s1 = (unsigned)e1; t1 = (e1 & SRC_T) != 0;
         }
         double x[3] = { 0.0, 0.0, 0.0 }, y[3] = { 0.0, 0.0, 0.0 };
-        if (cnt > 0) load_row(A.Ke, s0, t0, ii, x);          // count 0: a patch fed by other ranks only
-        if (cnt > 1) load_row(A.Ke, s1, t1, ii, y);
+        if (cnt > 0) load_col(A.Ke, s0, t0, c, x);           // count 0: a patch fed by other ranks only
+        if (cnt > 1) load_col(A.Ke, s1, t1, c, y);
 #pragma unroll
         for (int i = 0; i < 3; i++) a[i] = x[i] + y[i];
     }
     for (int k = 2; k < cnt; k++) {
         double x[3];
         const unsigned long long e = __ldg(A.ovf + q.z + k);
-        load_row(A.Ke, (unsigned)e, (e & SRC_T) != 0, ii, x);
+        load_col(A.Ke, (unsigned)e, (e & SRC_T) != 0, c, x);
 #pragma unroll
         for (int i = 0; i < 3; i++) a[i] += x[i];
     }
-    // rows = the group's free DOFs (consecutive CSR rows of equal length), columns = the neighbour's
-    double* o = A.valAA + (size_t)(int)q.x + (size_t)__popc(rm & ((1 << ii) - 1)) * L;
-    const int c1 = fm & 1, c2 = c1 + ((fm >> 1) & 1);
-    if (fm & 1) o[0] = a[0];
-    if (fm & 2) o[c1] = a[1];
-    if (fm & 4) o[c2] = a[2];
+    // rows = the group's free DOFs (consecutive CSR rows of equal length L), columns = the neighbour's free DOFs
+    double* o = A.valAA + (size_t)(int)q.x + __popc(fm & ((1 << c) - 1));
+    const int r1 = rm & 1, r2 = r1 + ((rm >> 1) & 1);
+    if (rm & 1) o[0] = a[0];
+    if (rm & 2) o[(size_t)r1 * L] = a[1];
+    if (rm & 4) o[(size_t)r2 * L] = a[2];
 }
 
 // residual vectors: global_P_A / global_I_A (free) or global_P_B (fixed), element-ascending sums;
