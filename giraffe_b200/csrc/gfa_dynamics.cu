@@ -471,15 +471,17 @@ __global__ void alpha_commit_kernel(EvalArgs A, double* alpha_i) {
 // =========================================================================
 // apply: MountDamping + MountDyn on the element arena, one warp per element
 // =========================================================================
-// arena offset -> (row group a, column group b, i, j) packed a | b<<4 | i<<8 | j<<10; 0xFFFF = padding
-__constant__ unsigned short c_shell_decode[SHELL_ARENA];
+// arena offset -> (row group a, column group b, i, j) packed a | b<<4 | i<<8 | j<<10; 0xFFFF = padding.
+// Lanes look up different offsets, so the table is staged in shared memory (constant memory would
+// serialise the divergent reads).
+__device__ unsigned short g_shell_decode[SHELL_ARENA];
 
 template <bool SHELL> struct Lay;
 template <> struct Lay<true> {
     static constexpr int ARENA = SHELL_ARENA, NDOF = 27, REC = SHELL_DYN_REC, NN = 6;
     static constexpr int UU = shell::UU, AA = shell::AA, PP = shell::PP, MUU = shell::MUU, MAA = shell::MAA, NUU = 6;
-    GFA_DI static bool decode(int off, int& a, int& b, int& i, int& j) {
-        const unsigned v = c_shell_decode[off];
+    GFA_DI static bool decode(const unsigned short* tab, int off, int& a, int& b, int& i, int& j) {
+        const unsigned v = tab[off];
         if (v == 0xFFFFu) return false;
         a = v & 15; b = (v >> 4) & 15; i = (v >> 8) & 3; j = (v >> 10) & 3;
         return true;
@@ -496,7 +498,7 @@ template <> struct Lay<true> {
 template <> struct Lay<false> {
     static constexpr int ARENA = 324, NDOF = 18, REC = BEAM_DYN_REC, NN = 3;
     static constexpr int UU = beam::UU, AA = beam::AA, PP = beam::PP, MUU = beam::MUU, MAA = beam::MAA, NUU = 3;
-    GFA_DI static bool decode(int off, int& a, int& b, int& i, int& j) {
+    GFA_DI static bool decode(const unsigned short*, int off, int& a, int& b, int& i, int& j) {
         const int blk = off / 9, r = off % 9;
         a = blk / 6; b = blk % 6; i = r / 3; j = r % 3;
         return true;
@@ -509,42 +511,77 @@ template <> struct Lay<false> {
 template <bool SHELL>
 __global__ void __launch_bounds__(128) apply_kernel(EvalArgs A, DynArgs D) {
     using L = Lay<SHELL>;
+    __shared__ unsigned short tab[SHELL ? SHELL_ARENA : 1];
+    __shared__ unsigned short ent[SHELL ? 81 : 1];      // block (ra, cb) -> offset | transposed << 15
+    if (SHELL) {
+        for (int i = threadIdx.x; i < SHELL_ARENA; i += blockDim.x) tab[i] = g_shell_decode[i];
+        for (int i = threadIdx.x; i < 81; i += blockDim.x) {
+            bool tr;
+            const int o = shell_block_offset(i / 9, i % 9, tr);
+            ent[i] = (unsigned short)(o | (tr ? 0x8000 : 0));
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    // what this lane adds at each of its arena offsets does not depend on the element: record index of the
+    // mass term (-1: none, -2: padding / beyond the region) and of the modal-mass term
+    constexpr int NIT = (L::ARENA + 31) / 32;
+    int aidx[NIT], midx[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int off = lane + 32 * it;
+        int a, b, i, j;
+        aidx[it] = -2; midx[it] = -1;
+        if (off < L::ARENA && L::decode(tab, off, a, b, i, j)) {
+            int na, nb; bool ra, rb;
+            L::group(a, na, ra); L::group(b, nb, rb);
+            aidx[it] = -1;
+            if (!ra && !rb) { if (i == j) { aidx[it] = L::UU + L::NUU * na + nb; midx[it] = L::MUU + L::NUU * na + nb; } }
+            else if (ra && rb) { aidx[it] = L::AA + 9 * (3 * na + nb) + 3 * i + j; midx[it] = L::MAA + 9 * (3 * na + nb) + 3 * i + j; }
+        }
+    }
     for (long long e = warp; e < A.n_el; e += n_warps) {
         double* Ke = A.Ke + (size_t)e * L::ARENA;
         double* CR = D.CR ? D.CR + (size_t)e * L::ARENA : nullptr;
         const double* rec = D.rec + (size_t)e * L::REC;
-        for (int off = lane; off < L::ARENA; off += 32) {
-            int a, b, i, j;
-            if (!L::decode(off, a, b, i, j)) continue;
-            int na, nb; bool ra, rb;
-            L::group(a, na, ra); L::group(b, nb, rb);
-            double add = 0.0, modal = 0.0;
-            if (!ra && !rb) {
-                if (i == j) { add = rec[L::UU + L::NUU * na + nb]; if (D.update) modal = rec[L::MUU + L::NUU * na + nb]; }
-            } else if (ra && rb) {
-                add = rec[L::AA + 9 * (3 * na + nb) + 3 * i + j];
-                if (D.update) modal = rec[L::MAA + 9 * (3 * na + nb) + 3 * i + j];
+        double k[NIT], cr[NIT], add[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {          // all loads of the element first
+            const int off = lane + 32 * it;
+            k[it] = 0.0; cr[it] = 0.0; add[it] = 0.0;
+            if (aidx[it] != -2) {
+                k[it] = Ke[off];
+                if (aidx[it] >= 0) add[it] = rec[aidx[it]];
+                if (CR) cr[it] = D.update ? (midx[it] >= 0 ? rec[midx[it]] : 0.0) : CR[off];
             }
-            double k = Ke[off], cr = 0.0;
-            if (CR) {
-                if (D.update) { cr = D.ray_alpha * modal + D.ray_beta * k; CR[off] = cr; }   // rayleigh_damping (:1649, :2510)
-                else cr = CR[off];
-            }
-            Ke[off] = k + add + D.a4 * cr;                                                   // MountDyn (:1672, :2540)
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int off = lane + 32 * it;
+            if (aidx[it] == -2) continue;
+            double c = cr[it];
+            if (CR && D.update) { c = D.ray_alpha * c + D.ray_beta * k[it]; CR[off] = c; }   // rayleigh_damping (:1649, :2510)
+            Ke[off] = k[it] + add[it] + D.a4 * c;                                            // MountDyn (:1672, :2540)
         }
         __syncwarp();
         if (lane < L::NDOF) {
             int nd[L::NN];
 #pragma unroll
             for (int n = 0; n < L::NN; n++) nd[n] = __ldg(A.conn + L::NN * (size_t)e + n);
-            double dl = 0.0;
+            double dl = 0.0, dl0 = 0.0, dl1 = 0.0, dl2 = 0.0;
             if (CR) {
                 const int ra = lane / 3, i = lane % 3;
-                for (int c = 0; c < L::NDOF; c++)                                            // rayleigh_damping * v_ipp (:1663, :2531)
-                    dl += CR[L::entry(ra, i, c / 3, c % 3)] * __ldg(D.vel + L::vel_index(nd, c / 3, c % 3));
+                for (int cb = 0; cb < L::NDOF / 3; cb++) {                                   // rayleigh_damping * v_ipp (:1663, :2531)
+                    int o0, st;
+                    if (SHELL) { const unsigned v = ent[9 * ra + cb]; o0 = (v & 0x7fff) + ((v & 0x8000) ? i : 3 * i); st = (v & 0x8000) ? 3 : 1; }
+                    else { o0 = L::entry(ra, i, cb, 0); st = 1; }
+                    dl0 = fma(CR[o0], __ldg(D.vel + L::vel_index(nd, cb, 0)), dl0);
+                    dl1 = fma(CR[o0 + st], __ldg(D.vel + L::vel_index(nd, cb, 1)), dl1);
+                    dl2 = fma(CR[o0 + 2 * st], __ldg(D.vel + L::vel_index(nd, cb, 2)), dl2);
+                }
+                dl = dl0 + dl1 + dl2;
             }
             double* P = A.Pe + (size_t)e * L::NDOF + lane;
             *P = *P + rec[L::PP + lane] + dl;                                                // MountDyn (:1670, :2538)
@@ -661,7 +698,7 @@ int configure_dynamics() {
             for (int i = 0; i < 3; i++)
                 for (int j = 0; j < 3; j++) tab[o + 3 * i + j] = (unsigned short)(a | (b << 4) | (i << 8) | (j << 10));
         }
-    return (int)cudaMemcpyToSymbol(c_shell_decode, tab, sizeof(tab));
+    return (int)cudaMemcpyToSymbol(g_shell_decode, tab, sizeof(tab));
 }
 
 } // namespace gfa
