@@ -189,6 +189,18 @@ bool GfaHost::ReadFile(const char* path) {
                     if (tk[j] == "TimeStep") time_step = num(j + 1);
                 }
                 i += 20;
+            } else if (i < tk.size() && tk[i] == "Dynamic") {      // Dynamic::Read (Dynamic.cpp:65-222)
+                dynamic = true;
+                size_t j = i + 2;
+                for (; j + 1 < tk.size() && j < i + 20; j += 2) {
+                    if (tk[j] == "EndTime") end_time = num(j + 1);
+                    if (tk[j] == "TimeStep") time_step = num(j + 1);
+                }
+                if (j + 6 < tk.size() && tk[j] == "RayleighDamping") { alpha = num(j + 2); beta = num(j + 4); update = integer(j + 6); j += 7; }
+                else return fail("Error reading Dynamic solution step: RayleighDamping expected");
+                if (j + 4 < tk.size() && tk[j] == "NewmarkCoefficients") { beta_new = num(j + 2); gamma_new = num(j + 4); j += 5; }
+                else return fail("Error reading Dynamic solution step: NewmarkCoefficients expected");
+                i = j;
             }
         } else {
             i++;
@@ -315,6 +327,44 @@ bool GfaHost::MountLocal() {
     st.displacements = displacements.data(); st.displacements_on_device = 0;
     st.gravity_factor = g_exist ? LoadFactor() : 0.0;
     if (gfa_assemble(h, &st) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+// Dynamic::CalculateNewmarkCoeff (Dynamic.cpp:582-590)
+void GfaHost::CalculateNewmarkCoeff(double dt) {
+    a1 = 1.0 / (dt * dt * beta_new);
+    a2 = 1.0 / (dt * beta_new);
+    a3 = 1.0 / (2.0 * beta_new) - 1.0;
+    a4 = gamma_new / (dt * beta_new);
+    a5 = 1.0 - gamma_new / beta_new;
+    a6 = dt * (1.0 - gamma_new / (2.0 * beta_new));
+}
+
+bool GfaHost::SetKinematics(const double* vel, const double* accel, const double* copy_vel, const double* copy_accel) {
+    if (gfa_set_kinematics(h, vel, accel, copy_vel, copy_accel) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+// Dynamic::UpdateDyn (Dynamic.cpp:480-556) on the device copy of the nodal arrays
+bool GfaHost::UpdateDyn() {
+    const gfa_dynamic_t d = { a1, a2, a3, a4, a5, a6, alpha, beta, 0 };
+    if (gfa_update_dyn(h, displacements.data(), &d) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+// One Newton iteration of Dynamic::Solve up to MountSparse (Dynamic.cpp:323-340)
+bool GfaHost::MountLocalDynamic(bool update_rayleigh) {
+    gfa_step_t st;
+    st.displacements = displacements.data(); st.displacements_on_device = 0;
+    st.gravity_factor = g_exist ? LoadFactor() : 0.0;
+    const gfa_dynamic_t d = { a1, a2, a3, a4, a5, a6, alpha, beta, update_rayleigh ? 1 : 0 };
+    if (gfa_assemble_dynamic(h, &st, &d) != GFA_OK) return fail(gfa_last_error());
+    return true;
+}
+
+bool GfaHost::GetKinematics(std::vector<double>& vel, std::vector<double>& accel) {
+    vel.assign(6 * (size_t)number_nodes(), 0.0); accel.assign(6 * (size_t)number_nodes(), 0.0);
+    if (gfa_kinematics(h, vel.data(), accel.data(), nullptr, nullptr) != GFA_OK) return fail(gfa_last_error());
     return true;
 }
 

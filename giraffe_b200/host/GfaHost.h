@@ -17,6 +17,11 @@
 //   host.UpdateDisps(x)          Solution::UpdateDisps   (Solution.cpp:390-402)
 //   host.SaveConfiguration()     Solution::SaveConfiguration (Solution.cpp:426-454) -> gfa_commit_state
 //   host.GetGaussPointResults()  what WriteResults / WriteMonitor read from the elements   -> gfa_gauss_point_results
+// Dynamic::Solve (src/Dynamic.cpp:255-340), when the first solution step of the input is `Dynamic`:
+//   host.CalculateNewmarkCoeff(dt)  Dynamic::CalculateNewmarkCoeff (Dynamic.cpp:582-590)
+//   host.UpdateDyn()                Dynamic::UpdateDyn            (Dynamic.cpp:480-556)   -> gfa_update_dyn
+//   host.MountLocalDynamic(update)  MountLocal + MountElementLoads + MountMass + MountDamping(update) + MountDyn
+//                                   + MountGlobal + MountSparse                            -> gfa_assemble_dynamic
 //
 // Errors follow the reference: Read* return false on a malformed block, the
 // rest report through last_error() and leave the state untouched.
@@ -56,7 +61,12 @@ public:
     std::vector<GfaNodalLoad> loads;
     bool g_exist = false;
     double G[3] = { 0, 0, 0 };
-    double end_time = 1.0, time_step = 1.0;       // first Static step (Static.cpp:43-130)
+    double end_time = 1.0, time_step = 1.0;       // first solution step (Static.cpp:43-130, Dynamic.cpp:65-222)
+    bool dynamic = false;                         // the first solution step is `Dynamic`
+    double alpha = 0.0, beta = 0.0;               // Dynamic::alpha, beta (RayleighDamping)
+    int update = 0;                               // Dynamic::update
+    double beta_new = 0.3, gamma_new = 0.5;       // NewmarkCoefficients (defaults of Dynamic::Dynamic, Dynamic.cpp:40-41)
+    double a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0;
     int n_GL_free = 0, n_GL_fixed = 0;
     double last_converged_time = 0.0, current_time_step = 0.0;
 
@@ -79,6 +89,15 @@ public:
     bool MountLoads();                            // host NodalLoad -> gfa_add_host_triplets / gfa_add_host_vector
     void UpdateDisps(const double* x_A);          // displacements[j] += x(GL-1) for free active DOFs
     bool SaveConfiguration();
+    // Dynamic::Solve
+    void CalculateNewmarkCoeff(double dt);
+    bool SetKinematics(const double* vel, const double* accel, const double* copy_vel, const double* copy_accel);   // InitialCondition
+    bool UpdateDyn();                             // device: vel / accel of every free DOF from `displacements`
+    bool MountLocalDynamic(bool update_rayleigh); // device: MountLocal .. MountMass, MountDamping(update_rayleigh), MountDyn .. MountSparse
+    void MountMass() {}                           // folded into MountLocalDynamic()
+    void MountDamping(bool) {}
+    void MountDyn() {}
+    bool GetKinematics(std::vector<double>& vel, std::vector<double>& accel);
 
     // ---- global system -----------------------------------------------------------
     bool GetCSR(int which, std::vector<int>& outer, std::vector<int>& inner, std::vector<double>& values);

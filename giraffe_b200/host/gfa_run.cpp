@@ -22,21 +22,36 @@ int main(int argc, char** argv) {
     host.DOFsActive();
     host.SetGlobalDOFs();
     if (parse_only) {
-        printf("{\"nodes\": %d, \"elements\": %d, \"n_GL_free\": %d, \"n_GL_fixed\": %d, \"loads\": %zu, \"node_sets\": %zu, \"time_step\": %.17g, \"end_time\": %.17g}\n",
-               host.number_nodes(), host.number_elements(), host.n_GL_free, host.n_GL_fixed, host.loads.size(), host.node_sets.size(), host.time_step, host.end_time);
+        printf("{\"nodes\": %d, \"elements\": %d, \"n_GL_free\": %d, \"n_GL_fixed\": %d, \"loads\": %zu, \"node_sets\": %zu, \"time_step\": %.17g, \"end_time\": %.17g, "
+               "\"dynamic\": %d, \"alpha\": %.17g, \"beta\": %.17g, \"update\": %d, \"beta_new\": %.17g, \"gamma_new\": %.17g}\n",
+               host.number_nodes(), host.number_elements(), host.n_GL_free, host.n_GL_fixed, host.loads.size(), host.node_sets.size(), host.time_step, host.end_time,
+               host.dynamic ? 1 : 0, host.alpha, host.beta, host.update, host.beta_new, host.gamma_new);
         return 0;
     }
     if (!host.PreCalc(0)) { fprintf(stderr, "PreCalc: %s\n", host.last_error().c_str()); return 1; }
     if (!host.SetGlobalSize()) { fprintf(stderr, "SetGlobalSize: %s\n", host.last_error().c_str()); return 1; }
     host.last_converged_time = 0.0;
     host.current_time_step = host.time_step;
-    // one Newton iteration of Static::Solve (Static.cpp:203-212)
-    host.Clear();
-    if (!host.MountLocal()) { fprintf(stderr, "MountLocal: %s\n", host.last_error().c_str()); return 1; }
-    host.MountElementLoads();
-    if (!host.MountLoads()) { fprintf(stderr, "MountLoads: %s\n", host.last_error().c_str()); return 1; }
-    host.MountGlobal();
-    host.MountSparse();
+    if (host.dynamic) {
+        // first Newton iteration of Dynamic::Solve (Dynamic.cpp:303-340) from rest
+        host.CalculateNewmarkCoeff(host.time_step);
+        host.Clear();
+        if (!host.UpdateDyn()) { fprintf(stderr, "UpdateDyn: %s\n", host.last_error().c_str()); return 1; }
+        if (!host.MountLocalDynamic(true)) { fprintf(stderr, "MountLocalDynamic: %s\n", host.last_error().c_str()); return 1; }
+        host.MountElementLoads();
+        if (!host.MountLoads()) { fprintf(stderr, "MountLoads: %s\n", host.last_error().c_str()); return 1; }
+        host.MountMass(); host.MountDamping(true); host.MountDyn();
+        host.MountGlobal();
+        host.MountSparse();
+    } else {
+        // one Newton iteration of Static::Solve (Static.cpp:203-212)
+        host.Clear();
+        if (!host.MountLocal()) { fprintf(stderr, "MountLocal: %s\n", host.last_error().c_str()); return 1; }
+        host.MountElementLoads();
+        if (!host.MountLoads()) { fprintf(stderr, "MountLoads: %s\n", host.last_error().c_str()); return 1; }
+        host.MountGlobal();
+        host.MountSparse();
+    }
     std::vector<int> outer, inner;
     std::vector<double> val, pa;
     if (!host.GetCSR(GFA_AA, outer, inner, val) || !host.GetVector(GFA_P_A, pa)) { fprintf(stderr, "%s\n", host.last_error().c_str()); return 1; }

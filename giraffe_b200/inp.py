@@ -8,8 +8,8 @@ ConvergenceCriteria, ...) are skipped up to the next known keyword.
 Supported: Nodes, Elements (Beam_1 / Pipe_1 / Shell_1 / Solid_1), Materials (Hooke),
 Sections (Rectangle / Tube), PipeSections (PS), ShellSections (Homogeneous), CoordinateSystems,
 NodeSets (List / Sequence), Constraints (NodalConstraint), Loads (NodalLoad
-with a numeric table), Environment (GravityData), SolutionSteps (Static, for
-the time-stepping data only).
+with a numeric table), Environment (GravityData), SolutionSteps (Static / Dynamic, for the
+time-stepping data, Rayleigh and Newmark coefficients only).
 """
 from __future__ import annotations
 
@@ -159,6 +159,14 @@ def read_inp(path: str):
                 vals = {tk[j]: tk[j + 1] for j in range(i + 2, i + 20, 2)}
                 info["end_time"] = float(vals["EndTime"]); info["time_step"] = float(vals["TimeStep"])
                 i += 20
+            elif tk[i] == "Dynamic":        # Dynamic::Read (Dynamic.cpp:65-222)
+                vals = {tk[j]: tk[j + 1] for j in range(i + 2, i + 20, 2)}
+                info["end_time"] = float(vals["EndTime"]); info["time_step"] = float(vals["TimeStep"])
+                j = i + 20
+                assert tk[j] == "RayleighDamping" and tk[j + 7] == "NewmarkCoefficients", "Dynamic step: RayleighDamping / NewmarkCoefficients expected"
+                info["dynamic"] = {"alpha": float(tk[j + 2]), "beta": float(tk[j + 4]), "update": int(tk[j + 6]),
+                                   "beta_new": float(tk[j + 9]), "gamma_new": float(tk[j + 11])}
+                i = j + 12
         else:
             i += 1
             while i < len(tk) and tk[i] not in _TOP:
@@ -189,9 +197,10 @@ def _r(v) -> str:
     return repr(float(v))
 
 
-def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0) -> None:
+def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0, dynamic: dict | None = None) -> None:
     """Write a Model in the reference's ``.inp`` syntax, e.g. to
-    hand a synthetic mesh to a GIRAFFE build or to the C++ host mirror."""
+    hand a synthetic mesh to a GIRAFFE build or to the C++ host mirror.  `dynamic` =
+    {alpha, beta, update, beta_new, gamma_new} writes a Dynamic solution step (Dynamic.cpp:65-222)."""
     names = ["UX", "UY", "UZ", "ROTX", "ROTY", "ROTZ"]
     with open(path, "w") as f:
         f.write(f"Nodes\t{m.n_nodes}\n")
@@ -237,8 +246,11 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
             f.write(f"\nCoordinateSystems\t{len(m.cs_defs)}\n")
             for k, (e1, e3) in enumerate(m.cs_defs):
                 f.write(f"CS\t{k + 1}\tE1\t{_r(e1[0])}\t{_r(e1[1])}\t{_r(e1[2])}\tE3\t{_r(e3[0])}\t{_r(e3[1])}\t{_r(e3[2])}\n")
-        f.write(f"\nSolutionSteps\t1\nStatic\t1\nEndTime\t{_r(end_time)}\nTimeStep\t{_r(time_step)}\nMaxTimeStep\t{_r(time_step)}\n"
+        f.write(f"\nSolutionSteps\t1\n{'Dynamic' if dynamic else 'Static'}\t1\nEndTime\t{_r(end_time)}\nTimeStep\t{_r(time_step)}\nMaxTimeStep\t{_r(time_step)}\n"
                 "MinTimeStep\t0.001\nMaxIt\t20\nMinIt\t3\nConvIncrease\t4\nIncFactor\t1.0\nSample\t1\n")
+        if dynamic:
+            f.write(f"RayleighDamping\tAlpha\t{_r(dynamic['alpha'])}\tBeta\t{_r(dynamic['beta'])}\tUpdate\t{int(dynamic['update'])}\n"
+                    f"NewmarkCoefficients\tBeta\t{_r(dynamic['beta_new'])}\tGamma\t{_r(dynamic['gamma_new'])}\n")
         if m.nodal_loads:
             f.write(f"\nLoads\t{len(m.nodal_loads)}\n")
             for k, (nodes, cs, table) in enumerate(m.nodal_loads):
