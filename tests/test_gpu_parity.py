@@ -428,3 +428,49 @@ def test_static_steps_keep_alpha_i_and_dynamic_rejects_unsupported_types(port):
     with pytest.raises(capi.GfaError):
         a2.assemble_dynamic(np.zeros((ms.n_nodes, 6)), True)
     a2.close()
+
+
+def test_full_size_shell_plate_dynamics_conserve_mass():
+    """BASELINE.json configs[2] through gfa_assemble_dynamic: size-independent properties of the Newmark path.
+    For a rigid translation c_k the stiffness gives K c = 0, the consistent mass a1 * integral(rho t N_a) and the
+    mass-proportional Rayleigh term a4 * alpha * (the same with the 6-point rule), so the sum over ALL rows of
+    direction k of (K + M + a4 C) c_k is (a1 + a4 alpha) * rho * t * Area; a uniform previous acceleration g0
+    gives inertial forces that sum to -a3 * rho * t * Area * g0.  One misplaced or doubled mass entry breaks it."""
+    import scipy.sparse as sp
+    m = M.shell_plate(1000, 500)
+    asm = capi.Assembler(m).set_dofs()
+    a = util.newmark_coefficients(1.0e-3)
+    ray_alpha, g0 = 0.3, 2.5
+    asm.set_dynamic(a, ray_alpha, 0.0)
+    zeros = np.zeros((m.n_nodes, 6))
+    acc = zeros.copy(); acc[:, 2] = g0
+    asm.set_kinematics(zeros, zeros, zeros, acc)
+    asm.assemble_dynamic(zeros, True)
+    E, nu, rho = m.hooke[0]
+    t = float(m.shell_thickness[0])
+    area = 1000 * 500 * 0.0195 ** 2
+    mass = rho * t * area
+    gls, nf, nx = M.number_dofs(m)
+    mats = {}
+    for w in ("AA", "AB", "BA", "BB"):
+        outer, inner = asm.csr_pattern(w)
+        rows, cols, _ = asm.csr_dims(w)
+        mats[w] = sp.csr_matrix((asm.values(w), inner, outer), shape=(rows, cols))
+    for k in range(3):
+        g = gls[:, k]
+        cA = np.zeros(nf); cB = np.zeros(nx)
+        cA[g[g > 0] - 1] = 1.0
+        cB[-g[g < 0] - 1] = 1.0
+        rA = mats["AA"] @ cA + mats["AB"] @ cB
+        rB = mats["BA"] @ cA + mats["BB"] @ cB
+        total = rA[g[g > 0] - 1].sum() + rB[-g[g < 0] - 1].sum()
+        expect = (a[0] + a[3] * ray_alpha) * mass
+        assert abs(total - expect) <= 1e-9 * expect, f"direction {k}: sum of (K+M+a4 C) c = {total!r}, expected {expect!r}"
+        # no coupling into the other directions or the rotations
+        others = np.abs(rA).sum() + np.abs(rB).sum() - np.abs(rA[g[g > 0] - 1]).sum() - np.abs(rB[-g[g < 0] - 1]).sum()
+        assert others <= 1e-8 * expect
+    pa, _, pb = asm.vectors()
+    gz = gls[:, 2]
+    fz = pa[gz[gz > 0] - 1].sum() + pb[-gz[gz < 0] - 1].sum()
+    assert abs(fz - (-a[2] * mass * g0)) <= 1e-9 * abs(a[2] * mass * g0), f"inertial force sum {fz!r}"
+    asm.close()
