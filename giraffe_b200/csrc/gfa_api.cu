@@ -303,7 +303,9 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
                     for (int i = 0; i < 9; i++) row[36 + i] = m->cs[9 * (size_t)(cs - 1) + i];
                     row[45] = ps[4];            // mass per unit length (gravity: Pipe_1.cpp:1311-1330 without ocean data)
                     row[46] = 0.0;              // Pipe_1::Mount leaves strain_energy at zero
-                                                // row[47..50]: no dynamic path for Pipe_1 (added mass needs ocean data)
+                    // Jr as written in Pipe_1.cpp:1137-1139 (the squared radii are subtracted); Mr = Rho I without ocean data
+                    const double rr = (ps[9] / 2.0) * (ps[9] / 2.0) - (ps[10] / 2.0) * (ps[10] / 2.0);
+                    row[47] = (ps[4] * rr / 4.0); row[48] = (ps[4] * rr / 4.0); row[49] = (ps[4] * rr / 2.0); row[50] = 0.0;
                     t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
                 } else if (s == 1) {    // Beam_1::PreCalc, Beam_1.cpp:560-580
                     const double* sc = m->sections + 6 * (size_t)(sec - 1);
@@ -904,11 +906,10 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
     if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_assemble before gfa_set_dofs");
     CUDA_TRY(cudaSetDevice(h->device));
     if (dyn) {
-        // MountMass / MountDamping exist on the device for Beam_1 and Shell_1; Pipe_1's added mass needs ocean
-        // data (Pipe_1.cpp:1560-1583) and Solid_1 has no arithmetic in the reference
+        // MountMass / MountDamping exist on the device for Beam_1, Shell_1 and Pipe_1 (structural mass Rho only:
+        // the model tables carry no ocean data, so the added-mass branch of Pipe_1.cpp:1758-1795 is never taken);
+        // Solid_1 has no arithmetic in the reference
         if (!h->tb[2].elems.empty()) return fail(GFA_EUNSUPPORTED, "gfa_assemble_dynamic: Solid_1 has no dynamic contributions");
-        for (int e : h->tb[1].elems)
-            if (h->el_type[e] == GFA_PIPE_1) return fail(GFA_EUNSUPPORTED, "gfa_assemble_dynamic: Pipe_1 dynamic contributions stay on the host");
         int rc = ensure_kinematics(h);
         if (rc != GFA_OK) return rc;
         for (int slot = 0; slot < 2; slot++) {

@@ -218,8 +218,9 @@ int gfa_update_displacements(gfa_t* h, const double* x_A /* [n_free] host */, gf
 int gfa_displacements(gfa_t* h, double* host_out /* [n_nodes*6] */);
 
 /* ---- Newmark dynamics: the element contributions Dynamic::Solve adds per Newton iteration -------------
- * (SURVEY.md 8f rank 1).  Beam_1 and Shell_1; a model that holds Pipe_1 (added mass needs ocean data,
- * src/Pipe_1.cpp:1560-1583) or Solid_1 elements gets GFA_EUNSUPPORTED from gfa_assemble_dynamic. */
+ * (SURVEY.md 8f rank 1).  Beam_1, Shell_1 and Pipe_1 with its structural mass (src/Pipe_1.cpp:1131-1144; the
+ * model tables carry no ocean data, so the added-mass branch of src/Pipe_1.cpp:1758-1795 stays on the host);
+ * a model that holds Solid_1 elements gets GFA_EUNSUPPORTED from gfa_assemble_dynamic. */
 typedef struct gfa_dynamic {
     double a1, a2, a3, a4, a5, a6;   /* Dynamic::a1..a6 of the current time step (src/Dynamic.cpp:582-590) */
     double rayleigh_alpha;           /* Dynamic::alpha (mass-proportional)       (src/Dynamic.h:26-27) */

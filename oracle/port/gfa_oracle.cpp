@@ -464,6 +464,12 @@ void pipe_precalc(BeamEl& b, const int* nd, const double* ps, const double* cs)
 	b.D(0, 0) = ps[3]; b.D(1, 1) = ps[3]; b.D(2, 2) = ps[0]; b.D(3, 3) = ps[1]; b.D(4, 4) = ps[1]; b.D(5, 5) = ps[2];
 	b.rhoA = ps[4];
 	b.energy_on = false;
+	// inertia per unit length (Pipe_1.cpp:1131-1144, as written: radii squared are SUBTRACTED), no ocean data:
+	// Mr = Rho I in MountMass / MountMassModal (Pipe_1.cpp:1580-1583, 1799-1803)
+	const double rr = (ps[9] / 2.0) * (ps[9] / 2.0) - (ps[10] / 2.0) * (ps[10] / 2.0);
+	b.Mr = M3(); b.Jr = M3(); b.br = V3();
+	b.Mr(0, 0) = ps[4]; b.Mr(1, 1) = ps[4]; b.Mr(2, 2) = ps[4];
+	b.Jr(0, 0) = (ps[4] * rr / 4.0); b.Jr(1, 1) = (ps[4] * rr / 4.0); b.Jr(2, 2) = (ps[4] * rr / 2.0);
 }
 
 // Beam_1.cpp:695-835
@@ -1116,7 +1122,7 @@ static int assemble(const double* disp6, double lfac, double* seconds, int dynam
 	W.disp.assign(disp6, disp6 + 6 * (size_t)W.n_nodes);
 	if (dynamic)
 		for (int e = 0; e < W.n_el; e++)
-			if (W.type[e] == T_SOLID || (W.type[e] == T_BEAM && W.is_pipe[e])) return -7;   // no dynamic path restated for them
+			if (W.type[e] == T_SOLID) return -7;   // no arithmetic in the reference (Pipe_1: restated without ocean data)
 	double t0 = now_s();
 	for (int w = 0; w < 4; w++) W.trip[w] = W.extra[w];                      // Clear + MountLoads
 	W.PA.assign(W.n_free, 0.0); W.IA.assign(W.n_free, 0.0); W.PB.assign(W.n_fixed, 0.0);

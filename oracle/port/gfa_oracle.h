@@ -61,7 +61,7 @@ int  gfo_commit(void);
 int  gfo_get_copy_coordinates(double* c6);
 
 
-/* Newmark dynamics (Dynamic.cpp:303-340): Beam_1 and Shell_1 only (Pipe_1 / Solid_1 return -7).
+/* Newmark dynamics (Dynamic.cpp:303-340): Beam_1, Shell_1 and Pipe_1 without ocean data (Solid_1 returns -7).
  * newmark6 = Dynamic::a1..a6; kinematics arrays are Node::vel / accel / copy_vel / copy_accel [n_nodes*6]
  * (NULL = leave / skip).  gfo_assemble_dynamic = Clear, MountLocal, MountElementLoads, MountMass,
  * MountDamping(update_rayleigh), MountDyn, MountGlobal, MountSparse.  gfo_commit also copies vel/accel

@@ -194,7 +194,7 @@ class PortOracle:
         r = self.lib.gfo_assemble_dynamic(np.ascontiguousarray(disp, np.float64).reshape(-1), float(self.gravity_factor),
                                           1 if update_rayleigh else 0)
         if r != 0:
-            raise ValueError("dynamic assembly is restated for Beam_1 and Shell_1 only")
+            raise ValueError("dynamic assembly is restated for Beam_1, Pipe_1 and Shell_1 only")
 
     def alpha_i(self, e: int) -> np.ndarray:
         buf = np.zeros(16)

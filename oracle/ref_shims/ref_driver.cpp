@@ -607,6 +607,8 @@ int ref_get_alpha_i(int e, double* out)
 		for (int g = 0; g < 3; g++) for (int i = 0; i < 3; i++) out[w++] = (*s->alpha_i[g])(i, 0);
 	else if (Beam_1* b = dynamic_cast<Beam_1*>(el))
 		for (int g = 0; g < 2; g++) for (int i = 0; i < 3; i++) out[w++] = (*b->lag_save->alpha_i[g])(i, 0);
+	else if (Pipe_1* q = dynamic_cast<Pipe_1*>(el))
+		for (int g = 0; g < 2; g++) for (int i = 0; i < 3; i++) out[w++] = (*q->lag_save->alpha_i[g])(i, 0);
 	return w;
 }
 

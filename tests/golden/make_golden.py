@@ -20,7 +20,7 @@ Newton iteration and the reference's CSR matrices (AA/AB/BA/BB) and vectors
                    iterations, a commit (SaveLagrange) and one more iteration.
   shell_plate.npz  6x4-cell warped Shell_1 plate with gravity (doubled
                    self-weight quirk), same sequence.
-  dynamic_beam.npz, dynamic_shell.npz
+  dynamic_beam.npz, dynamic_shell.npz, dynamic_pipe.npz
                    Newmark path (Dynamic.cpp:303-340): UpdateDyn, MountMass,
                    MountDamping (Rayleigh update on the first iteration), MountDyn
                    over two iterations, a commit and a third iteration.
@@ -136,7 +136,11 @@ def dynamic_models():
     db[8, 3] = 2.0e-3; db[9, 3:6] = (1.0e-3, -2.0e-3, 1.5e-3); db[15, 4:6] = (-1.0e-3, 0.5e-3)      # prescribed rotations
     ds = M.mask_displacements(ms, M.shell_plate_displacements(ms))
     ds[mids[7] - 1, 4] = 1.0e-3; ds[mids[20] - 1, 3] = -1.0e-3; ds[mids[20] - 1, 5] = 2.0e-3
-    return (("dynamic_beam", mb, db, 20240011), ("dynamic_shell", ms, ds, 20240012))
+    mp = M.pipe_line(10, gravity=(0.3, -0.2, -9.81))          # Pipe_1 with its structural mass (no ocean data)
+    mp.constraints = mp.constraints + [([8], 0x10)]
+    dp = M.mask_displacements(mp, M.beam_line_displacements(mp))
+    dp[7, 4] = -1.5e-3
+    return (("dynamic_beam", mb, db, 20240011), ("dynamic_shell", ms, ds, 20240012), ("dynamic_pipe", mp, dp, 20240013))
 
 
 def dynamic(R):

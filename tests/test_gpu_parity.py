@@ -378,7 +378,7 @@ def test_newton_vector_steps_on_device():
 
 
 # ---- Newmark dynamics -----------------------------------------------------
-@pytest.mark.parametrize("name", ["dynamic_beam", "dynamic_shell"])
+@pytest.mark.parametrize("name", ["dynamic_beam", "dynamic_shell", "dynamic_pipe"])
 def test_newmark_dynamics_against_reference_fixture(name):
     """gfa_update_dyn + gfa_assemble_dynamic + gfa_commit_state against what the reference's own Dynamic /
     MountMass / MountDamping / MountDyn / UpdateDyn produced (tests/golden/make_golden.py): CSR values,
@@ -410,8 +410,8 @@ def test_newmark_dynamics_against_oracle(port):
 
 
 def test_static_steps_keep_alpha_i_and_dynamic_rejects_unsupported_types(port):
-    """SaveLagrange updates alpha_i in static steps too (Shell_1.cpp:1659, Beam_1.cpp:1502); Pipe_1 / Solid_1
-    have no dynamic path on the device."""
+    """SaveLagrange updates alpha_i in static steps too (Shell_1.cpp:1659, Beam_1.cpp:1502); Solid_1 has no
+    dynamic path (the reference has no arithmetic for it)."""
     m = M.concat_models([M.beam_line(6), M.shell_plate(3, 2, warp=0.01)])
     d = M.mask_displacements(m, np.random.default_rng(2).uniform(-2e-3, 2e-3, (m.n_nodes, 6)))
     port.load(m)

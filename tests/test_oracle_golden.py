@@ -108,7 +108,7 @@ def test_newton_steps_restatement_against_reference_fixture(port):
     assert (inc["node_force"], inc["node_moment"], inc["nan_detected"]) == tuple(int(v) for v in z["increment_nodes"])
 
 
-@pytest.mark.parametrize("name", ["dynamic_beam", "dynamic_shell"])
+@pytest.mark.parametrize("name", ["dynamic_beam", "dynamic_shell", "dynamic_pipe"])
 def test_newmark_dynamics(port, name):
     """Dynamic::Solve's element contributions (MountMass, MountDamping with a Rayleigh update, MountDyn) and
     UpdateDyn, incl. nodes with partly-free rotations, against what the reference's own Dynamic produced."""
