@@ -60,6 +60,13 @@ __host__ __device__ inline int shell_block_offset(int a, int b, bool& transposed
     return transposed ? shell_stored_offset(b, a) : shell_stored_offset(a, b);
 }
 
+// Beam_1 / Pipe_1 arena of one element (BEAM_ARENA doubles): all 36 blocks over the 6 group-nodes (2 node + rot),
+// [row block][column block].  (Grouping the blocks by column block and padding each group to whole sectors,
+// as the Shell_1 arena does, was measured: no change -- the beam kernel is latency-bound in its Gauss-point
+// phase, profiles/r01_notes.md.)
+constexpr int BEAM_ARENA = 324;
+__host__ __device__ constexpr int beam_block_offset(int rb, int cb) { return 9 * (6 * rb + cb); }
+
 // ---- scatter ------------------------------------------------------------
 // "Group-node" = one 3-DOF group of a node (translations or rotations); every
 // in-scope element block is 3x3-structured over group-nodes in the

@@ -496,7 +496,7 @@ template <> struct Lay<true> {
     }
 };
 template <> struct Lay<false> {
-    static constexpr int ARENA = 324, NDOF = 18, REC = BEAM_DYN_REC, NN = 3;
+    static constexpr int ARENA = BEAM_ARENA, NDOF = 18, REC = BEAM_DYN_REC, NN = 3;
     static constexpr int UU = beam::UU, AA = beam::AA, PP = beam::PP, MUU = beam::MUU, MAA = beam::MAA, NUU = 3;
     GFA_DI static bool decode(const unsigned short*, int off, int& a, int& b, int& i, int& j) {
         const int blk = off / 9, r = off % 9;
@@ -505,7 +505,7 @@ template <> struct Lay<false> {
     }
     GFA_DI static void group(int grp, int& node, bool& rot) { rot = grp & 1; node = grp >> 1; }
     GFA_DI static int vel_index(const int* nd, int grp, int comp) { return 6 * nd[grp >> 1] + ((grp & 1) ? 3 : 0) + comp; }
-    GFA_DI static int entry(int ra, int i, int cb, int j) { return (ra * 6 + cb) * 9 + 3 * i + j; }
+    GFA_DI static int entry(int ra, int i, int cb, int j) { return beam_block_offset(ra, cb) + 3 * i + j; }
 };
 
 template <bool SHELL>

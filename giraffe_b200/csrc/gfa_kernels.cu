@@ -884,15 +884,30 @@ GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Geo& go, Kin& k)
     s_mv(k.a, go.R, ga); s_mv(k.da, go.R, gda); s_mv(k.du, go.R, gdu);   // :743-746
 }
 
-// y(3x3) = D_rs (3x3 block of the 6x6 section matrix) * P
-GFA_DI void dblock_mul(double* o, const double* D6, int r, int s, const double* P, bool acc) {
+// Section matrix of the in-scope sections: D = blockdiag(diag(d0), [[a, c, 0], [c, b, 0], [0, 0, t]])
+// (Beam_1.cpp:560-580: GA, GA, EA | EI1, EI2, EI12, GIt; Pipe_1.cpp:1108-1114: diagonal); the property rows
+// are built by gfa_create with exactly these non-zeros.
+struct DSec { double d0[3], a, b, c, t; };
+GFA_DI DSec load_dsec(const double* pr) {
+    DSec D;
+    D.d0[0] = __ldg(pr + 0); D.d0[1] = __ldg(pr + 7); D.d0[2] = __ldg(pr + 14);
+    D.a = __ldg(pr + 21); D.c = __ldg(pr + 22); D.b = __ldg(pr + 28); D.t = __ldg(pr + 35);
+    return D;
+}
+// o = D(0,0) P  and  o = D(1,1) P  (3x3 blocks of the 6x6 section matrix; D(0,1) = D(1,0) = 0)
+GFA_DI void d00_mul(double* o, const DSec& D, const double* P) {
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const double v = D6[6 * (3 * r + i) + 3 * s] * P[j] + D6[6 * (3 * r + i) + 3 * s + 1] * P[3 + j] + D6[6 * (3 * r + i) + 3 * s + 2] * P[6 + j];
-            if (acc) o[3 * i + j] += v; else o[3 * i + j] = v;
-        }
+        for (int j = 0; j < 3; j++) o[3 * i + j] = D.d0[i] * P[3 * i + j];
+}
+GFA_DI void d11_mul(double* o, const DSec& D, const double* P) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        o[j] = D.a * P[j] + D.c * P[3 + j];
+        o[3 + j] = D.c * P[j] + D.b * P[3 + j];
+        o[6 + j] = D.t * P[6 + j];
+    }
 }
 GFA_DI void store9(double* rec, int p, int q, double w, const double* M) {
 #pragma unroll
@@ -909,9 +924,7 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     const double* pr = A.props + BEAM_PROP_STRIDE * (size_t)__ldg(A.prop + e);
     Geo go; geometry(A, e, g, nd, pr, go);
     Kin kn; interpolate(A, nd, go, kn);
-    double D6[36];
-#pragma unroll
-    for (int i = 0; i < 36; i++) D6[i] = __ldg(pr + i);
+    const DSec D = load_dsec(pr);
     const size_t n_gp = (size_t)A.n_el * NGP, gp = (size_t)e * NGP + g;
     double Qi[9], dz[3], ki[3];
 #pragma unroll
@@ -931,13 +944,12 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     s_mtv(t3, Xi, kn.da); s_mtv(eps + 3, Qi, t3);
 #pragma unroll
     for (int i = 0; i < 3; i++) eps[3 + i] = s_add(eps[3 + i], ki[i]);   // kappa_r (:779)
+    // sigma_r = D eps (:788), strict; the zero entries of D add exact zeros in the reference's full sum
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double sacc = s_mul(D6[6 * i], eps[0]);
-#pragma unroll
-        for (int j = 1; j < 6; j++) sacc = s_add(sacc, s_mul(D6[6 * i + j], eps[j]));
-        sig[i] = sacc;                                            // sigma_r = D eps (:788)
-    }
+    for (int i = 0; i < 3; i++) sig[i] = s_mul(D.d0[i], eps[i]);
+    sig[3] = s_add(s_mul(D.a, eps[3]), s_mul(D.c, eps[4]));
+    sig[4] = s_add(s_mul(D.c, eps[3]), s_mul(D.b, eps[4]));
+    sig[5] = s_mul(D.t, eps[5]);
     double n[3], m[3];
     mv(n, Q, sig); mv(m, Q, sig + 3);                            // spatial resultants (:796-797)
 
@@ -990,27 +1002,25 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         mm(tmp, G12, go.R); mtm(G12, go.R, tmp);
         mm(tmp, G21, go.R); mtm(G21, go.R, tmp);
     }
-    // C' = B'^T D B' + G'  (:776, :824-826)
-    double DB0[9], DB1[9];     // D(0,.)B(.,c), D(1,.)B(.,c) for one column block c
+    // C' = B'^T D B' + G'  (:776, :824-826) with D = blockdiag(D00, D11): the blocks (1,0) and (0,1) of C' vanish
+    // identically (they are neither stored nor read: congruence_item skips them)
+    double DB0[9], DB1[9];
     // column 0: B(.,0) = [B00; 0]
-    dblock_mul(DB0, D6, 0, 0, B00, false); dblock_mul(DB1, D6, 1, 0, B00, false);
+    d00_mul(DB0, D, B00);
     mtm(tmp, B00, DB0); store9(rec, 0, 0, w, tmp);
-    mtm(tmp, B11, DB1); store9(rec, 1, 0, w, tmp);
-    mtm(tmp, B02, DB0); mtm_acc(tmp, B12, DB1);
+    mtm(tmp, B02, DB0);
 #pragma unroll
     for (int i = 0; i < 9; i++) tmp[i] += G20[i];
     store9(rec, 2, 0, w, tmp);
     // column 1: B(.,1) = [0; B11]
-    dblock_mul(DB0, D6, 0, 1, B11, false); dblock_mul(DB1, D6, 1, 1, B11, false);
-    mtm(tmp, B00, DB0); store9(rec, 0, 1, w, tmp);
+    d11_mul(DB1, D, B11);
     mtm(tmp, B11, DB1); store9(rec, 1, 1, w, tmp);
-    mtm(tmp, B02, DB0); mtm_acc(tmp, B12, DB1);
+    mtm(tmp, B12, DB1);
 #pragma unroll
     for (int i = 0; i < 9; i++) tmp[i] += G21[i];
     store9(rec, 2, 1, w, tmp);
     // column 2: B(.,2) = [B02; B12]
-    dblock_mul(DB0, D6, 0, 0, B02, false); dblock_mul(DB0, D6, 0, 1, B12, true);
-    dblock_mul(DB1, D6, 1, 0, B02, false); dblock_mul(DB1, D6, 1, 1, B12, true);
+    d00_mul(DB0, D, B02); d11_mul(DB1, D, B12);
     mtm(tmp, B00, DB0);
 #pragma unroll
     for (int i = 0; i < 9; i++) tmp[i] += G02[i];
@@ -1040,21 +1050,30 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
         const double* S = rec + S_OFF;
-        double m[3][3];
+        // gradient groups 0: u', 1: alpha', 2: alpha; the blocks (1,0) and (0,1) of C' are identically zero
+        double m0[3], m1[3], m2[3];
 #pragma unroll
-        for (int p = 0; p < 3; p++)
-#pragma unroll
-            for (int ii = 0; ii < 3; ii++) {
-                const double* row = rec + C_OFF + 9 * (3 * p + ii) + jj;
-                m[p][ii] = ROT ? S[b] * row[3] + S[3 + b] * row[6] : S[b] * row[0];
+        for (int ii = 0; ii < 3; ii++) {
+            const double* r0 = rec + C_OFF + 9 * ii + jj;
+            const double* r1 = rec + C_OFF + 9 * (3 + ii) + jj;
+            const double* r2 = rec + C_OFF + 9 * (6 + ii) + jj;
+            if (ROT) {
+                m0[ii] = S[3 + b] * r0[6];
+                m1[ii] = S[b] * r1[3] + S[3 + b] * r1[6];
+                m2[ii] = S[b] * r2[3] + S[3 + b] * r2[6];
+            } else {
+                m0[ii] = S[b] * r0[0];
+                m1[ii] = 0.0;
+                m2[ii] = S[b] * r2[0];
             }
+        }
         F += ROT ? S[b] * rec[F_OFF + 3 + jj] + S[3 + b] * rec[F_OFF + 6 + jj] : S[b] * rec[F_OFF + jj];
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int ii = 0; ii < 3; ii++) {
-                K[6 * a + ii] += S[a] * m[0][ii];
-                K[6 * a + 3 + ii] += S[a] * m[1][ii] + S[3 + a] * m[2][ii];
+                K[6 * a + ii] += S[a] * m0[ii];
+                K[6 * a + 3 + ii] += ROT ? S[a] * m1[ii] + S[3 + a] * m2[ii] : S[3 + a] * m2[ii];
             }
         if (!ROT) {
             const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
@@ -1062,7 +1081,7 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         }
     }
     const int col = 6 * b + (ROT ? 3 : 0) + jj;
-    double* Ke = A.Ke + (size_t)e * 324 + (col / 3) * 9 + (col % 3);        // block-major 6x6 blocks of 3x3
+    double* Ke = A.Ke + (size_t)e * BEAM_ARENA + beam_block_offset(0, col / 3) + (col % 3);   // block-major 6x6 blocks of 3x3
 #pragma unroll
     for (int r = 0; r < 18; r++) Ke[(r / 3) * 54 + (r % 3) * 3] = K[r];
     A.Pe[(size_t)e * 18 + col] = F - fe;
