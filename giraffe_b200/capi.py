@@ -29,7 +29,7 @@ EXPORTS = [
     "gfa_commit_state", "gfa_element_state", "gfa_results_stride", "gfa_gauss_point_results",
     "gfa_residual", "gfa_update_displacements", "gfa_displacements", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
-    "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i",
+    "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library() -> C.CDLL:
         lib.gfa_csr_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
         lib.gfa_csr_pattern.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.gfa_assemble.argtypes = [C.c_void_p, C.POINTER(_StepStruct)]
+        lib.gfa_assemble_enqueue.argtypes = [C.c_void_p, C.POINTER(_StepStruct)]
         lib.gfa_add_host_triplets.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.gfa_add_host_vector.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         lib.gfa_csr_values.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -284,6 +285,15 @@ class Assembler:
         buf = np.zeros(16)
         n = self._check(self.lib.gfa_element_alpha_i(self._h, e, _ptr(buf)))
         return buf[:n].copy()
+
+    def assemble_enqueue(self, device_ptr: int | None = None):
+        """gfa_assemble_enqueue: queue the assembly on the library's stream and return (device displacements or
+        the device copy); reads wait for the stream."""
+        st = _StepStruct()
+        st.displacements, st.displacements_on_device = device_ptr, 1 if device_ptr is not None else 0
+        st.gravity_factor = float(self.gravity_factor)
+        self._check(self.lib.gfa_assemble_enqueue(self._h, C.byref(st)))
+        return self
 
     def assemble_raw(self, host_ptr: int):
         """Host pointer (e.g. pinned memory) without numpy marshalling."""

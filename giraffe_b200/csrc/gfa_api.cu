@@ -153,6 +153,7 @@ struct gfa_handle {
     std::vector<int> owned_rows;
 
     bool assembled = false;
+    bool timing_pending = false;          // events of the last assembly not read yet (gfa_assemble_enqueue)
     float last_ms[4] = { 0, 0, 0, 0 };
     int last_launches = 0;
 };
@@ -880,6 +881,16 @@ int gfa_csr_pattern(gfa_t* h, int which, int32_t* outer, int32_t* inner) {
 
 namespace {
 
+void resolve_timing(gfa_t* h) {
+    if (!h->timing_pending) return;
+    cudaEventSynchronize(h->ev[3]);
+    cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
+    cudaEventElapsedTime(&h->last_ms[3], h->ev[0], h->ev[3]);
+    h->timing_pending = false;
+}
+
 int ensure_kinematics(gfa_t* h) {
     const size_t n = 6 * (size_t)h->n_nodes;
     if (h->d_vel.n == n) return GFA_OK;
@@ -902,7 +913,7 @@ DynArgs dyn_args(gfa_t* h, int slot, const gfa_dynamic_t* d) {
     return a;
 }
 
-int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
+int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool wait = true) {
     if (!h || !st) return fail(GFA_EINVAL, "gfa_assemble: null argument");
     if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_assemble before gfa_set_dofs");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -962,13 +973,13 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
     }
     CUDA_TRY(cudaEventRecord(h->ev[3], s));
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s));
-    cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
-    cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
-    cudaEventElapsedTime(&h->last_ms[3], h->ev[0], h->ev[3]);
     h->last_launches = launches;
     h->assembled = true;
+    h->timing_pending = true;
+    if (wait) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        resolve_timing(h);
+    }
     return GFA_OK;
 }
 
@@ -977,6 +988,12 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
 extern "C" {
 
 int gfa_assemble(gfa_t* h, const gfa_step_t* st) { return assemble_impl(h, st, nullptr); }
+
+int gfa_assemble_enqueue(gfa_t* h, const gfa_step_t* st) {
+    if (st && st->displacements && !st->displacements_on_device)
+        return fail(GFA_EINVAL, "gfa_assemble_enqueue: displacements must be a device pointer or NULL (the call returns before they are read)");
+    return assemble_impl(h, st, nullptr, false);
+}
 
 int gfa_assemble_dynamic(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn) {
     if (!dyn) return fail(GFA_EINVAL, "gfa_assemble_dynamic: null argument");
@@ -1308,6 +1325,7 @@ int gfa_copy_coordinates(gfa_t* h, double* out) {
 
 int gfa_last_timing(gfa_t* h, double* ms4) {
     if (!h || !ms4) return fail(GFA_EINVAL, "gfa_last_timing: bad argument");
+    resolve_timing(h);
     for (int i = 0; i < 4; i++) ms4[i] = h->last_ms[i];
     return GFA_OK;
 }

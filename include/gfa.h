@@ -141,6 +141,11 @@ int gfa_csr_pattern(gfa_t* h, int which, int32_t* outer, int32_t* inner);
  * MountGlobal + MountSparse for the supported element types.  Returns after
  * the results are complete on the device (stream-synchronised). */
 int gfa_assemble(gfa_t* h, const gfa_step_t* step);
+/* The same work, only ENQUEUED on gfa_stream(): returns at once so that the caller can queue what follows
+ * (interface pack / NCCL / unpack in a multi-GPU run, its own consumers) behind it without leaving the GPU idle
+ * while the host catches up.  step->displacements must be a device pointer or NULL.  Every read entry point
+ * (gfa_csr_values, gfa_vector, gfa_element_block, gfa_last_timing ...) waits for the stream. */
+int gfa_assemble_enqueue(gfa_t* h, const gfa_step_t* step);
 
 /* Contributions of host-side contributors (loads, joints, contacts, element
  * types without a kernel), summed into existing slots AFTER the elements.

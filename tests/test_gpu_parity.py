@@ -192,6 +192,17 @@ def test_assembly_is_bitwise_reproducible_and_reentrant():
     asm.assemble(d)
     assert asm.values("AA").tobytes() == v1.tobytes()
     assert asm.vectors()[0].tobytes() == p1.tobytes()
+    # gfa_assemble_enqueue: same work, not waited for; the reads wait for the stream
+    asm.assemble(7.0 * d)
+    asm.assemble(d)                # leaves d as the device copy of the displacements
+    asm.assemble_enqueue(None)
+    assert asm.values("AA").tobytes() == v1.tobytes()
+    assert asm.vectors()[0].tobytes() == p1.tobytes()
+    assert asm.timing()["total_ms"] > 0.0
+    import ctypes
+    st = capi._StepStruct()
+    st.displacements, st.displacements_on_device = d.ctypes.data, 0
+    assert asm.lib.gfa_assemble_enqueue(asm._h, ctypes.byref(st)) == -1      # host pointers are refused
 
 
 def test_host_triplets_outside_pattern_are_rejected():
