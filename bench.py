@@ -182,6 +182,7 @@ def run_cuda(args):
     pinned.numpy()[:] = d_host.reshape(-1)
     d_dev = pinned.cuda(non_blocking=False)
     lib_stream = torch.cuda.ExternalStream(asm.stream())
+    if_stream = torch.cuda.ExternalStream(asm.interface_stream())
 
     # interface exchange buffers (N > 1)
     send_cnt, recv_cnt = asm.interface_counts(world)
@@ -189,10 +190,11 @@ def run_cuda(args):
     recv_buf = torch.empty(int(recv_cnt.sum()), dtype=torch.float64, device="cuda") if world > 1 else None
 
     def exchange():
-        """pack -> NCCL send/recv -> unpack, stream-ordered on the library's stream (no host syncs)."""
+        """pack -> NCCL send/recv -> unpack, stream-ordered on the library's interface stream (no host syncs);
+        the library scatters the interface rows first, so the exchange overlaps the interior rows' scatter."""
         if world == 1:
             return
-        with torch.cuda.stream(lib_stream):
+        with torch.cuda.stream(if_stream):
             asm.interface_pack(send_buf.data_ptr())
             ops, so, ro = [], 0, 0
             for r in range(world):

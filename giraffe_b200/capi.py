@@ -29,7 +29,7 @@ EXPORTS = [
     "gfa_commit_state", "gfa_element_state", "gfa_results_stride", "gfa_gauss_point_results",
     "gfa_residual", "gfa_update_displacements", "gfa_displacements", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
-    "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue",
+    "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue", "gfa_interface_stream",
 ]
 
 
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
         lib.gfa_owned_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
         lib.gfa_local_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
         lib.gfa_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.gfa_interface_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.gfa_set_kinematics.argtypes = [C.c_void_p] * 5
         lib.gfa_kinematics.argtypes = [C.c_void_p] * 5
         lib.gfa_update_dyn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DynamicStruct)]
@@ -437,4 +438,11 @@ class Assembler:
     def stream(self) -> int:
         p = C.c_void_p()
         self._check(self.lib.gfa_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def interface_stream(self) -> int:
+        """cudaStream_t of the interface exchange: pack / unpack are enqueued there, the caller's transport goes
+        between them on the same stream"""
+        p = C.c_void_p()
+        self._check(self.lib.gfa_interface_stream(self._h, C.byref(p)))
         return p.value or 0

@@ -110,6 +110,11 @@ struct gfa_handle {
     int device = 0;
     cudaStream_t stream = nullptr;        // the stream every kernel of the path runs on (callers may time / order against it)
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    // multi-GPU: the rows of partition interfaces are scattered first; pack / transport / unpack run on their own
+    // stream behind ev_iface while the interior rows are still being scattered on `stream`
+    cudaStream_t stream_if = nullptr;
+    cudaEvent_t ev_iface = nullptr, ev_unpacked = nullptr;
+    long long n_iface_runs = 0, n_iface_gn = 0;
     int rank = 0, world = 1;
 
     int n_nodes = 0, n_el = 0;
@@ -376,6 +381,9 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         if (e == cudaSuccess) e = h->tb[0].d_geo.alloc(10 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = h->tb[0].d_shp.alloc(21 * 3 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream_if, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_iface, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_unpacked, cudaEventDisableTiming);
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
         if (e != cudaSuccess) FAIL_FREE(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "device set-up: %s", cudaGetErrorString(e));
     }
@@ -393,8 +401,13 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
 int gfa_destroy(gfa_t* h) {
     if (!h) return GFA_OK;
     cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream_if) cudaStreamSynchronize(h->stream_if);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->ev_iface) cudaEventDestroy(h->ev_iface);
+    if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_if) cudaStreamDestroy(h->stream_if);
     delete h;
     return GFA_OK;
 }
@@ -680,6 +693,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<int> rowL(n_gn_all, 0);              // CSR row length of the group's rows
     std::vector<int> touched_gn;                     // group-nodes with a local incidence
     std::vector<long long> touched_key;              // position of the first local incident element (locality key)
+    std::vector<char> touched_iface;                 // shared with another rank: scattered first (see gfa_assemble)
     for (size_t gn = 0; gn < n_gn_all; gn++) {
         if (gptr[gn] == gptr[gn + 1]) continue;
         int owner = 0; bool touched = h->world == 1; unsigned long long rank_set = 0;
@@ -718,6 +732,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         if (key < 0) continue;
         touched_gn.push_back((int)gn);
         touched_key.push_back(key);
+        touched_iface.push_back(h->world > 1 && __builtin_popcountll(rank_set) > 1 ? 1 : 0);
     }
     std::sort(h->owned_rows.begin(), h->owned_rows.end());
     {   // patches are processed in the order of their group-node's first incident element, so that the
@@ -725,11 +740,18 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         // element's corner and mid-side nodes millions of group-nodes apart)
         std::vector<size_t> order(touched_gn.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return touched_key[x] < touched_key[y]; });
+        // group-nodes on a partition interface come first: their rows are complete (and can be packed and sent)
+        // while the interior rows are still being scattered
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+            if (touched_iface[x] != touched_iface[y]) return touched_iface[x] > touched_iface[y];
+            return touched_key[x] < touched_key[y];
+        });
         std::vector<int> sorted(touched_gn.size());
         for (size_t i = 0; i < order.size(); i++) sorted[i] = touched_gn[order[i]];
         touched_gn.swap(sorted);
     }
+    size_t n_iface_touched = 0;
+    for (char c : touched_iface) n_iface_touched += c ? 1 : 0;
 
     // ---- slot map of this rank's group-nodes ----------------------------------
     // For every (group-node, neighbour) patch: the local element blocks feeding it, element-ascending.
@@ -738,7 +760,9 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<unsigned long long> ovf;
     std::vector<std::vector<unsigned long long> > run_src;   // scratch: sources per patch of the current group-node
     std::vector<GnRec> gn_recs;
+    h->n_iface_runs = 0; h->n_iface_gn = 0;
     for (size_t ti_ = 0; ti_ < touched_gn.size(); ti_++) {
+        if (ti_ == n_iface_touched) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)gn_recs.size(); }
         const size_t gn = (size_t)touched_gn[ti_];
         const int first_inc = (int)incs.size();
         const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
@@ -799,6 +823,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
     }
     (void)fix_mask;
+    if (n_iface_touched == touched_gn.size()) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)gn_recs.size(); }
 
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
@@ -964,13 +989,21 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
     sa.n_gn = h->n_gn_local; sa.gn = h->d_gn.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
     sa.valAA = h->d_arena.p + h->arena_off[GFA_AA];
     sa.PA = h->d_arena.p + h->vec_off[GFA_P_A]; sa.IA = h->d_arena.p + h->vec_off[GFA_I_A]; sa.PB = h->d_arena.p + h->vec_off[GFA_P_B];
-    launches += launch_scatter(sa, s);
+    // rows of partition interfaces first (n_iface_* are zero with one rank), then the fixed-DOF entries: after
+    // ev_iface everything the interface exchange packs is final, and the interior rows follow behind it
+    ScatterArgs si = sa;
+    si.n_runs = h->n_iface_runs; si.n_gn = h->n_iface_gn;
+    launches += launch_scatter(si, s);
     if (h->n_gdest > 0) {
         GatherArgs g;
         g.n_dest = h->n_gdest; g.seg = h->d_gseg.p; g.src = h->d_gsrc.p; g.dest = h->d_gdest.p;
         g.Ke = h->d_Ke.p; g.vals = h->d_arena.p;
         launch_gather(g, s); launches++;
     }
+    CUDA_TRY(cudaEventRecord(h->ev_iface, s));
+    sa.runs += h->n_iface_runs; sa.n_runs -= h->n_iface_runs;
+    sa.gn += h->n_iface_gn; sa.n_gn -= h->n_iface_gn;
+    launches += launch_scatter(sa, s);
     CUDA_TRY(cudaEventRecord(h->ev[3], s));
     CUDA_TRY(cudaGetLastError());
     h->last_launches = launches;
@@ -1341,9 +1374,10 @@ int gfa_interface_pack(gfa_t* h, double* buf) {
     if (!h) return fail(GFA_EINVAL, "gfa_interface_pack: null handle");
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_interface_pack before gfa_assemble");
     CUDA_TRY(cudaSetDevice(h->device));
-    launch_pack(h->d_arena.p, h->d_send_idx.p, buf, (long long)h->d_send_idx.n, h->stream);
+    CUDA_TRY(cudaStreamWaitEvent(h->stream_if, h->ev_iface, 0));      // interface rows and fixed-DOF entries are final
+    launch_pack(h->d_arena.p, h->d_send_idx.p, buf, (long long)h->d_send_idx.n, h->stream_if);
     CUDA_TRY(cudaGetLastError());
-    return GFA_OK;       // asynchronous: ordered on gfa_stream()
+    return GFA_OK;       // asynchronous: ordered on gfa_interface_stream()
 }
 int gfa_interface_unpack(gfa_t* h, const double* buf) {
     if (!h) return fail(GFA_EINVAL, "gfa_interface_unpack: null handle");
@@ -1352,11 +1386,14 @@ int gfa_interface_unpack(gfa_t* h, const double* buf) {
     // peers ascending, one launch per peer segment => fixed summation order
     long long off = 0;
     for (int r = 0; r < h->world; r++) {
-        launch_unpack_add(h->d_arena.p, h->d_recv_idx.p + off, buf + off, h->recv_cnt[r], h->stream);
+        launch_unpack_add(h->d_arena.p, h->d_recv_idx.p + off, buf + off, h->recv_cnt[r], h->stream_if);
         off += h->recv_cnt[r];
     }
     CUDA_TRY(cudaGetLastError());
-    return GFA_OK;       // asynchronous: ordered on gfa_stream()
+    // everything that follows on gfa_stream() -- reads, host additions, the next assembly -- waits for the exchange
+    CUDA_TRY(cudaEventRecord(h->ev_unpacked, h->stream_if));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_unpacked, 0));
+    return GFA_OK;       // asynchronous: ordered on gfa_interface_stream()
 }
 int gfa_local_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {
     if (!h) return fail(GFA_EINVAL, "gfa_local_rows: null handle");
@@ -1373,6 +1410,12 @@ int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {
     if (rows_out && !h->owned_rows.empty()) std::memcpy(rows_out, h->owned_rows.data(), h->owned_rows.size() * sizeof(int));
     return GFA_OK;
 }
+int gfa_interface_stream(gfa_t* h, void** out) {
+    if (!h || !out) return fail(GFA_EINVAL, "gfa_interface_stream: bad argument");
+    *out = (void*)h->stream_if;
+    return GFA_OK;
+}
+
 int gfa_stream(gfa_t* h, void** out) {
     if (!h || !out) return fail(GFA_EINVAL, "gfa_stream: bad argument");
     *out = (void*)h->stream;

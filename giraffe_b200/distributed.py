@@ -53,12 +53,13 @@ class InterfaceExchange:
         return 8 * int(self.send_counts.sum() + self.recv_counts.sum())
 
     def __call__(self):
-        """pack -> NCCL -> unpack, all ordered on the library's stream (gfa_stream): no host
-        synchronisation; the next read of the values waits for the stream."""
+        """pack -> NCCL -> unpack, all ordered on the library's interface stream (gfa_interface_stream): no host
+        synchronisation.  The library scatters the interface rows first, so after gfa_assemble_enqueue the
+        exchange overlaps the scatter of the interior rows; unpack makes the library's main stream wait."""
         if self.world == 1:
             return
         if self.recv_buf.is_cuda:
-            with torch.cuda.stream(torch.cuda.ExternalStream(self.asm.stream())):
+            with torch.cuda.stream(torch.cuda.ExternalStream(self.asm.interface_stream())):
                 self.asm.interface_pack(self.send_buf.data_ptr())
                 p2p_exchange(self.send_buf, self.send_counts, self.recv_buf, self.recv_counts)
                 self.asm.interface_unpack(self.recv_buf.data_ptr())

@@ -282,9 +282,12 @@ int gfa_last_launch_count(gfa_t* h);
  *   gfa_interface_unpack : adds received partials (device recv_buf, segments
  *                          ordered by peer rank, peers ascending => fixed
  *                          summation order) into the owned rows
- * The transport between pack and unpack is the caller's (NCCL send/recv).  Pack and unpack only ENQUEUE
- * their kernels on gfa_stream(): the caller orders its transport after the pack and the unpack after its
- * transport on that stream (or with events); gfa_csr_values / gfa_vector / the next gfa_assemble wait for it. */
+ * The transport between pack and unpack is the caller's (NCCL send/recv).  gfa_assemble scatters the rows of
+ * partition interfaces FIRST and records an event; pack and unpack only ENQUEUE their kernels on
+ * gfa_interface_stream() -- pack behind that event, so with gfa_assemble_enqueue the exchange runs while the interior
+ * rows are still being scattered on gfa_stream().  The caller issues its transport on gfa_interface_stream() between
+ * the two calls.  gfa_interface_unpack makes gfa_stream() wait for the exchange, so gfa_csr_values / gfa_vector / the
+ * next gfa_assemble see the summed rows. */
 int gfa_interface_counts(gfa_t* h, int64_t* send_counts /* [world] */, int64_t* recv_counts /* [world] */);
 int gfa_interface_pack(gfa_t* h, double* send_buf_device);
 int gfa_interface_unpack(gfa_t* h, const double* recv_buf_device);
@@ -298,6 +301,8 @@ int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out /* may be NULL *
 /* Raw stream the library launches on (cudaStream_t), for callers that time
  * or order their own work against it. */
 int gfa_stream(gfa_t* h, void** stream_out);
+/* Stream of the interface exchange (pack, the caller's transport, unpack). */
+int gfa_interface_stream(gfa_t* h, void** stream_out);
 
 #ifdef __cplusplus
 }

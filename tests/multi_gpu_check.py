@@ -49,6 +49,9 @@ def main():
         ex()
         asm.assemble(d)      # a second Newton iteration on the same pattern: slots are rewritten, not accumulated
         ex()
+        for _ in range(3):   # and queued ones: the exchange overlaps the scatter of the interior rows
+            asm.assemble_enqueue(None)
+            ex()
         lo, li, lv, _ = asm.csr("AA")
         rows = asm.local_rows()
         owned = asm.owned_rows()
