@@ -32,6 +32,7 @@ def main():
     cases = [
         ("shell", M.shell_plate(24, 16, warp=0.01, gravity=(0.0, 0.0, -9.81))),
         ("beam", M.beam_line(101)),
+        ("shell-large", M.shell_plate(160, 96, warp=0.01)),      # 30k shells: thousands of scatter blocks around the exchange
         ("mixed", M.concat_models([M.beam_line(40), M.shell_plate(9, 8), M.solid_block(4, 4, 3)])),
     ]
     ok = True
