@@ -35,24 +35,43 @@ def main():
         ("shell-large", M.shell_plate(160, 96, warp=0.01)),      # 30k shells: thousands of scatter blocks around the exchange
         ("mixed", M.concat_models([M.beam_line(40), M.shell_plate(9, 8), M.solid_block(4, 4, 3)])),
     ]
+    cases.append(("dynamic", M.concat_models([M.beam_line(30), M.shell_plate(12, 9, warp=0.01, gravity=(0.0, 0.0, -9.81))])))
     ok = True
     for name, m in cases:
         d = M.mask_displacements(m, np.random.default_rng(7).uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
         port = PortOracle(threads=2).load(m)
         port.set_time(0.0, 1.0)
-        port.assemble(d)
+        dynamic = name == "dynamic"
+        if dynamic:      # Newmark path: UpdateDyn + MountMass / MountDamping(true) / MountDyn, partitioned like the rest
+            rng = np.random.default_rng(11)
+            cv, ca = rng.uniform(-1, 1, (m.n_nodes, 6)), rng.uniform(-10, 10, (m.n_nodes, 6))
+            zeros = np.zeros((m.n_nodes, 6))
+            a = util.newmark_coefficients(0.005)
+            port.set_dynamic(a, 0.4, 2.0e-4)
+            port.set_kinematics(zeros, zeros, cv, ca)
+            port.update_dyn(d)
+            port.assemble_dynamic(d, True)
+        else:
+            port.assemble(d)
         ro, ri, rv, _ = port.csr("AA")
         rpa, ria, rpb = port.vectors()
         asm = capi.Assembler(m, device=local, rank=rank, world=world).set_dofs()
         asm.set_time(0.0, 1.0)
         ex = InterfaceExchange(asm, world)
-        asm.assemble(d)
-        ex()
-        asm.assemble(d)      # a second Newton iteration on the same pattern: slots are rewritten, not accumulated
-        ex()
-        for _ in range(3):   # and queued ones: the exchange overlaps the scatter of the interior rows
-            asm.assemble_enqueue(None)
+        if dynamic:
+            asm.set_dynamic(a, 0.4, 2.0e-4)
+            asm.set_kinematics(zeros, zeros, cv, ca)
+            asm.update_dyn(d)
+            asm.assemble_dynamic(d, True)
             ex()
+        else:
+            asm.assemble(d)
+            ex()
+            asm.assemble(d)      # a second Newton iteration on the same pattern: slots are rewritten, not accumulated
+            ex()
+            for _ in range(3):   # and queued ones: the exchange overlaps the scatter of the interior rows
+                asm.assemble_enqueue(None)
+                ex()
         lo, li, lv, _ = asm.csr("AA")
         rows = asm.local_rows()
         owned = asm.owned_rows()
