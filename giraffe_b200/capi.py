@@ -15,7 +15,7 @@ import numpy as np
 from .meshes import Model
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgfa.so")
+LIB_PATH = os.environ.get("GFA_LIB") or os.path.join(_HERE, "libgfa.so")      # GFA_LIB: another build of the same library (experiments)
 
 AA, AB, BA, BB = 0, 1, 2, 3
 P_A, I_A, P_B = 0, 1, 2
