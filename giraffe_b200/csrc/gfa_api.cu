@@ -187,7 +187,7 @@ inline long long arena_block(const gfa_t* h, int slot, int local, int la, int b,
     const long long base = h->tb[slot].ke_base + (long long)local * arena_doubles(slot);
     tr = false;
     if (slot == 0) return base + shell_block_offset(la, b, tr);
-    if (slot == 1) return base + beam_block_offset(la, b);
+    if (slot == 1) return base + beam_block_offset(la, b, tr);
     return base + (la * kTypes[slot].nb + b) * 9;
 }
 
@@ -1197,7 +1197,7 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 bool tr = false;
-                const int off = s == 0 ? shell_block_offset(i / 3, j / 3, tr) : s == 1 ? beam_block_offset(i / 3, j / 3) : ((i / 3) * nb + (j / 3)) * 9;
+                const int off = s == 0 ? shell_block_offset(i / 3, j / 3, tr) : s == 1 ? beam_block_offset(i / 3, j / 3, tr) : ((i / 3) * nb + (j / 3)) * 9;
                 K[i * n + j] = blk[(size_t)off + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3))];
             }
     }

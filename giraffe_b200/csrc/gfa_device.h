@@ -22,7 +22,8 @@ struct EvalArgs {
     const double* shp;       // Shell_1 PreCalc: 21 shape values per Gauss point (SoA)
     double* state;           // committed Gauss-point state (read by eval, written by commit)
     double* Ke;              // element arena of contiguous, row-major 3x3 blocks (reference local DOF order).
-                             // Beam_1 / Solid_1: all (ndof/3)^2 blocks, [row block][column block].
+                             // Solid_1: all 64 blocks, [row block][column block].
+                             // Beam_1: BEAM_ARENA doubles per element (see beam_block_offset()).
                              // Shell_1: SHELL_ARENA doubles per element (see shell_block_offset()).
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
     double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
@@ -60,12 +61,24 @@ __host__ __device__ inline int shell_block_offset(int a, int b, bool& transposed
     return transposed ? shell_stored_offset(b, a) : shell_stored_offset(a, b);
 }
 
-// Beam_1 / Pipe_1 arena of one element (BEAM_ARENA doubles): all 36 blocks over the 6 group-nodes (2 node + rot),
-// [row block][column block].  (Grouping the blocks by column block and padding each group to whole sectors,
-// as the Shell_1 arena does, was measured: no change -- the beam kernel is latency-bound in its Gauss-point
-// phase, profiles/r01_notes.md.)
-constexpr int BEAM_ARENA = 324;
-__host__ __device__ constexpr int beam_block_offset(int rb, int cb) { return 9 * (6 * rb + cb); }
+// Beam_1 / Pipe_1 stored blocks over the 6 group-nodes (2 * node + rot): the 21 blocks (a <= b) of the upper
+// triangle plus the 3 strictly-lower rotation-rotation blocks (3,1), (5,1), (5,3) -- as for Shell_1 the
+// rotation-rotation part is the only non-symmetric one (Beam_1.cpp:799-822); block (a > b) elsewhere is the
+// transpose of stored block (b, a).  Column block b holds its rows a = 0..b and then, for a rotational
+// column, the rotational rows below it: 1, 4, 3, 5, 5, 6 blocks = 24 blocks, BEAM_ARENA doubles per element.
+constexpr int BEAM_STORED = 24;
+constexpr int BEAM_ARENA = 216;
+__host__ __device__ constexpr int beam_col_base(int b) { return b == 0 ? 0 : b == 1 ? 1 : b == 2 ? 5 : b == 3 ? 8 : b == 4 ? 13 : 18; }
+__host__ __device__ constexpr bool beam_is_stored(int a, int b) { return a <= b || ((a & 1) && (b & 1)); }
+// offset of stored block (a, b) inside the element's arena region (beam_is_stored(a, b) must hold)
+__host__ __device__ constexpr int beam_stored_offset(int a, int b) {
+    return 9 * (beam_col_base(b) + (a <= b ? a : b + 1 + (a - b - 2) / 2));
+}
+// offset of the stored block that holds block (a, b); `transposed` tells whether it holds (b, a)
+__host__ __device__ inline int beam_block_offset(int a, int b, bool& transposed) {
+    transposed = !beam_is_stored(a, b);
+    return transposed ? beam_stored_offset(b, a) : beam_stored_offset(a, b);
+}
 
 // ---- scatter ------------------------------------------------------------
 // "Group-node" = one 3-DOF group of a node (translations or rotations); every

@@ -475,53 +475,46 @@ __global__ void alpha_commit_kernel(EvalArgs A, double* alpha_i) {
 // Lanes look up different offsets, so the table is staged in shared memory (constant memory would
 // serialise the divergent reads).
 __device__ unsigned short g_shell_decode[SHELL_ARENA];
+__device__ unsigned short g_beam_decode[BEAM_ARENA];
 
 template <bool SHELL> struct Lay;
 template <> struct Lay<true> {
-    static constexpr int ARENA = SHELL_ARENA, NDOF = 27, REC = SHELL_DYN_REC, NN = 6;
+    static constexpr int ARENA = SHELL_ARENA, NDOF = 27, REC = SHELL_DYN_REC, NN = 6, NG = 9;
     static constexpr int UU = shell::UU, AA = shell::AA, PP = shell::PP, MUU = shell::MUU, MAA = shell::MAA, NUU = 6;
-    GFA_DI static bool decode(const unsigned short* tab, int off, int& a, int& b, int& i, int& j) {
-        const unsigned v = tab[off];
-        if (v == 0xFFFFu) return false;
-        a = v & 15; b = (v >> 4) & 15; i = (v >> 8) & 3; j = (v >> 10) & 3;
-        return true;
-    }
+    GFA_DI static const unsigned short* decode_table() { return g_shell_decode; }
+    GFA_DI static int block_offset(int a, int b, bool& tr) { return shell_block_offset(a, b, tr); }
     // group -> (translation node | rotation node, is rotation)
     GFA_DI static void group(int grp, int& node, bool& rot) { rot = grp >= 6; node = rot ? grp - 6 : grp; }
     GFA_DI static int vel_index(const int* nd, int grp, int comp) { return grp < 6 ? 6 * nd[grp] + comp : 6 * nd[3 + grp - 6] + 3 + comp; }
-    GFA_DI static int entry(int ra, int i, int cb, int j) {
-        bool tr;
-        const int o = shell_block_offset(ra, cb, tr);
-        return o + (tr ? 3 * j + i : 3 * i + j);
-    }
 };
 template <> struct Lay<false> {
-    static constexpr int ARENA = BEAM_ARENA, NDOF = 18, REC = BEAM_DYN_REC, NN = 3;
+    static constexpr int ARENA = BEAM_ARENA, NDOF = 18, REC = BEAM_DYN_REC, NN = 3, NG = 6;
     static constexpr int UU = beam::UU, AA = beam::AA, PP = beam::PP, MUU = beam::MUU, MAA = beam::MAA, NUU = 3;
-    GFA_DI static bool decode(const unsigned short*, int off, int& a, int& b, int& i, int& j) {
-        const int blk = off / 9, r = off % 9;
-        a = blk / 6; b = blk % 6; i = r / 3; j = r % 3;
-        return true;
-    }
+    GFA_DI static const unsigned short* decode_table() { return g_beam_decode; }
+    GFA_DI static int block_offset(int a, int b, bool& tr) { return beam_block_offset(a, b, tr); }
     GFA_DI static void group(int grp, int& node, bool& rot) { rot = grp & 1; node = grp >> 1; }
     GFA_DI static int vel_index(const int* nd, int grp, int comp) { return 6 * nd[grp >> 1] + ((grp & 1) ? 3 : 0) + comp; }
-    GFA_DI static int entry(int ra, int i, int cb, int j) { return beam_block_offset(ra, cb) + 3 * i + j; }
 };
+// packed table entry -> (row group a, column group b, i, j); false for padding
+GFA_DI bool decode_entry(const unsigned short* tab, int off, int& a, int& b, int& i, int& j) {
+    const unsigned v = tab[off];
+    if (v == 0xFFFFu) return false;
+    a = v & 15; b = (v >> 4) & 15; i = (v >> 8) & 3; j = (v >> 10) & 3;
+    return true;
+}
 
 template <bool SHELL>
 __global__ void __launch_bounds__(128) apply_kernel(EvalArgs A, DynArgs D) {
     using L = Lay<SHELL>;
-    __shared__ unsigned short tab[SHELL ? SHELL_ARENA : 1];
-    __shared__ unsigned short ent[SHELL ? 81 : 1];      // block (ra, cb) -> offset | transposed << 15
-    if (SHELL) {
-        for (int i = threadIdx.x; i < SHELL_ARENA; i += blockDim.x) tab[i] = g_shell_decode[i];
-        for (int i = threadIdx.x; i < 81; i += blockDim.x) {
-            bool tr;
-            const int o = shell_block_offset(i / 9, i % 9, tr);
-            ent[i] = (unsigned short)(o | (tr ? 0x8000 : 0));
-        }
-        __syncthreads();
+    __shared__ unsigned short tab[L::ARENA];
+    __shared__ unsigned short ent[L::NG * L::NG];       // block (ra, cb) -> offset | transposed << 15
+    for (int i = threadIdx.x; i < L::ARENA; i += blockDim.x) tab[i] = L::decode_table()[i];
+    for (int i = threadIdx.x; i < L::NG * L::NG; i += blockDim.x) {
+        bool tr;
+        const int o = L::block_offset(i / L::NG, i % L::NG, tr);
+        ent[i] = (unsigned short)(o | (tr ? 0x8000 : 0));
     }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -534,7 +527,7 @@ __global__ void __launch_bounds__(128) apply_kernel(EvalArgs A, DynArgs D) {
         const int off = lane + 32 * it;
         int a, b, i, j;
         aidx[it] = -2; midx[it] = -1;
-        if (off < L::ARENA && L::decode(tab, off, a, b, i, j)) {
+        if (off < L::ARENA && decode_entry(tab, off, a, b, i, j)) {
             int na, nb; bool ra, rb;
             L::group(a, na, ra); L::group(b, nb, rb);
             aidx[it] = -1;
@@ -574,9 +567,8 @@ __global__ void __launch_bounds__(128) apply_kernel(EvalArgs A, DynArgs D) {
             if (CR) {
                 const int ra = lane / 3, i = lane % 3;
                 for (int cb = 0; cb < L::NDOF / 3; cb++) {                                   // rayleigh_damping * v_ipp (:1663, :2531)
-                    int o0, st;
-                    if (SHELL) { const unsigned v = ent[9 * ra + cb]; o0 = (v & 0x7fff) + ((v & 0x8000) ? i : 3 * i); st = (v & 0x8000) ? 3 : 1; }
-                    else { o0 = L::entry(ra, i, cb, 0); st = 1; }
+                    const unsigned v = ent[L::NG * ra + cb];
+                    const int o0 = (v & 0x7fff) + ((v & 0x8000) ? i : 3 * i), st = (v & 0x8000) ? 3 : 1;
                     dl0 = fma(CR[o0], __ldg(D.vel + L::vel_index(nd, cb, 0)), dl0);
                     dl1 = fma(CR[o0 + st], __ldg(D.vel + L::vel_index(nd, cb, 1)), dl1);
                     dl2 = fma(CR[o0 + 2 * st], __ldg(D.vel + L::vel_index(nd, cb, 2)), dl2);
@@ -698,7 +690,18 @@ int configure_dynamics() {
             for (int i = 0; i < 3; i++)
                 for (int j = 0; j < 3; j++) tab[o + 3 * i + j] = (unsigned short)(a | (b << 4) | (i << 8) | (j << 10));
         }
-    return (int)cudaMemcpyToSymbol(g_shell_decode, tab, sizeof(tab));
+    cudaError_t e = cudaMemcpyToSymbol(g_shell_decode, tab, sizeof(tab));
+    if (e != cudaSuccess) return (int)e;
+    unsigned short tb[BEAM_ARENA];
+    for (int i = 0; i < BEAM_ARENA; i++) tb[i] = 0xFFFF;
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+            if (!beam_is_stored(a, b)) continue;         // held as the transpose of (b, a)
+            const int o = beam_stored_offset(a, b);
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) tb[o + 3 * i + j] = (unsigned short)(a | (b << 4) | (i << 8) | (j << 10));
+        }
+    return (int)cudaMemcpyToSymbol(g_beam_decode, tb, sizeof(tb));
 }
 
 } // namespace gfa

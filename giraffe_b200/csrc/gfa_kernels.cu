@@ -1081,9 +1081,15 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         }
     }
     const int col = 6 * b + (ROT ? 3 : 0) + jj;
-    double* Ke = A.Ke + (size_t)e * BEAM_ARENA + beam_block_offset(0, col / 3) + (col % 3);   // block-major 6x6 blocks of 3x3
+    // stored blocks of this column block: rows 0..cb and, for a rotational column, the rotational rows below
+    const int cb = col / 3;
+    double* Ke = A.Ke + (size_t)e * BEAM_ARENA + (col % 3);
 #pragma unroll
-    for (int r = 0; r < 18; r++) Ke[(r / 3) * 54 + (r % 3) * 3] = K[r];
+    for (int rb = 0; rb < 6; rb++)
+        if (beam_is_stored(rb, cb)) {
+            double* o = Ke + beam_stored_offset(rb, cb);
+            o[0] = K[3 * rb]; o[3] = K[3 * rb + 1]; o[6] = K[3 * rb + 2];
+        }
     A.Pe[(size_t)e * 18 + col] = F - fe;
 }
 
