@@ -69,7 +69,7 @@ const TypeInfo kTypes[3] = {
 };
 // doubles per element in the Ke arena: Shell_1 stores the upper triangle plus the non-symmetric
 // rotation corner in sector-padded groups (gfa_device.h: shell_stored_offset), the others every block
-inline int arena_doubles(int slot) { return slot == 0 ? SHELL_ARENA : slot == 1 ? BEAM_ARENA : kTypes[slot].ndof * kTypes[slot].ndof; }
+inline int arena_doubles(int slot) { return slot == 0 ? SHELL_ARENA : slot == 1 ? BEAM_ARENA : SOLID_ARENA; }
 // Pipe_1 shares the Beam_1 block: same Mount / MountGlobal / SaveLagrange (Pipe_1.cpp:836-974, 1027-1104),
 // other constants (PreCalc, Pipe_1.cpp:1106-1146)
 inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : (t == GFA_BEAM_1 || t == GFA_PIPE_1) ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
@@ -188,7 +188,7 @@ inline long long arena_block(const gfa_t* h, int slot, int local, int la, int b,
     tr = false;
     if (slot == 0) return base + shell_block_offset(la, b, tr);
     if (slot == 1) return base + beam_block_offset(la, b, tr);
-    return base + (la * kTypes[slot].nb + b) * 9;
+    return base + solid_block_offset(la, b, tr);
 }
 
 } // namespace
@@ -1190,14 +1190,14 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
     const int n = kTypes[s].ndof;
     if (K) {
-        const int nb = n / 3, nd = arena_doubles(s), local = h->el_local[e];
+        const int nd = arena_doubles(s), local = h->el_local[e];
         std::vector<double> blk((size_t)nd);
         CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)local * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost));
         // device layout is block-wise (and upper-triangular for Shell_1); hand back plain row-major
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 bool tr = false;
-                const int off = s == 0 ? shell_block_offset(i / 3, j / 3, tr) : s == 1 ? beam_block_offset(i / 3, j / 3, tr) : ((i / 3) * nb + (j / 3)) * 9;
+                const int off = s == 0 ? shell_block_offset(i / 3, j / 3, tr) : s == 1 ? beam_block_offset(i / 3, j / 3, tr) : solid_block_offset(i / 3, j / 3, tr);
                 K[i * n + j] = blk[(size_t)off + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3))];
             }
     }

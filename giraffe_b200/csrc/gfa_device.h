@@ -22,8 +22,8 @@ struct EvalArgs {
     const double* shp;       // Shell_1 PreCalc: 21 shape values per Gauss point (SoA)
     double* state;           // committed Gauss-point state (read by eval, written by commit)
     double* Ke;              // element arena of contiguous, row-major 3x3 blocks (reference local DOF order).
-                             // Solid_1: all 64 blocks, [row block][column block].
-                             // Beam_1: BEAM_ARENA doubles per element (see beam_block_offset()).
+                             // Beam_1: BEAM_ARENA, Solid_1: SOLID_ARENA doubles per element
+                             // (see beam_block_offset(), solid_block_offset()).
                              // Shell_1: SHELL_ARENA doubles per element (see shell_block_offset()).
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
     double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
@@ -78,6 +78,15 @@ __host__ __device__ constexpr int beam_stored_offset(int a, int b) {
 __host__ __device__ inline int beam_block_offset(int a, int b, bool& transposed) {
     transposed = !beam_is_stored(a, b);
     return transposed ? beam_stored_offset(b, a) : beam_stored_offset(a, b);
+}
+
+// Solid_1 (builder-defined hexahedron): the tangent is symmetric, so only the 36 blocks (a <= b) over the 8 nodes
+// are stored, column block b holding its rows a = 0..b; block (a > b) is the transpose of stored block (b, a).
+constexpr int SOLID_ARENA = 324;
+__host__ __device__ constexpr int solid_stored_offset(int a, int b) { return 9 * (b * (b + 1) / 2 + a); }
+__host__ __device__ inline int solid_block_offset(int a, int b, bool& transposed) {
+    transposed = a > b;
+    return transposed ? solid_stored_offset(b, a) : solid_stored_offset(a, b);
 }
 
 // ---- scatter ------------------------------------------------------------

@@ -1333,9 +1333,11 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
         fe += rec[W_OFF] * rec[N_OFF + b] * gk;
     }
     const int col = 3 * b + jj;
-    double* Ke = A.Ke + (size_t)e * 576 + (col / 3) * 9 + (col % 3);        // block-major 8x8 blocks of 3x3
+    // stored blocks of this column block: rows 0..b (the tangent is symmetric)
+    double* Ke = A.Ke + (size_t)e * SOLID_ARENA + solid_stored_offset(0, b) + jj;
 #pragma unroll
-    for (int r = 0; r < 24; r++) Ke[(r / 3) * 72 + (r % 3) * 3] = K[r];
+    for (int rb = 0; rb < 8; rb++)
+        if (rb <= b) { Ke[9 * rb] = K[3 * rb]; Ke[9 * rb + 3] = K[3 * rb + 1]; Ke[9 * rb + 6] = K[3 * rb + 2]; }
     A.Pe[(size_t)e * 24 + col] = F - fe;
 }
 
