@@ -17,6 +17,7 @@
 // derivative of Xi^T mu with respect to alpha_d (three directions), i.e. the exact derivative AceGen
 // generates symbolically; the translational tangent is a1 m I.
 //
+// Pipe_1 rides on the beam kernels with its own Mr = Rho I and Jr (Pipe_1.cpp:1131-1144, structural mass only).
 // Two launches per element type:
 //   gp kernel    one thread per element: Gauss-point quantities -> a small record per element
 //                (node-pair scalars of the u-u blocks, 3x3 alpha-alpha blocks in global axes,

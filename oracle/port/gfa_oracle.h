@@ -6,6 +6,10 @@
  *   the reference's own sources compiled here (oracle/_ref, see
  *   oracle/Makefile) by tests/test_oracle_vs_ref.py, and against the committed
  *   fixtures under tests/golden/ that the same build generated.
+ *   Newmark dynamics (MountMass / MountDamping / MountDyn / UpdateDyn of Beam_1, Pipe_1, Shell_1): the
+ *   AceGen-generated inertia code of the reference is restated from its formulation with a forward-mode
+ *   tangent; pinned against the reference's own Dynamic object the same two ways
+ *   (tests/test_oracle_vs_ref.py, tests/golden/dynamic_*.npz), agreement 2e-15.
  *   Solid_1: PARITY UNPINNED -- the reference's Solid_1::Mount/MountGlobal are
  *   empty bodies (reference Solid_1.cpp:148-176); the formulation restated
  *   here is builder-defined (8-node trilinear hexahedron, total-Lagrangian
