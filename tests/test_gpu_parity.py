@@ -487,3 +487,26 @@ def test_full_size_shell_plate_dynamics_conserve_mass():
     fz = pa[gz[gz > 0] - 1].sum() + pb[-gz[gz < 0] - 1].sum()
     assert abs(fz - (-a[2] * mass * g0)) <= 1e-9 * abs(a[2] * mass * g0), f"inertial force sum {fz!r}"
     asm.close()
+
+
+def test_newmark_dynamics_large_rotations(port):
+    """Rotation increments of ~0.5 rad and angular velocities of ~3 rad/s over three committed time steps
+    (the oracle is pinned to the reference in this regime by tests/test_oracle_vs_ref.py)."""
+    m = M.concat_models([M.beam_line(6), M.shell_plate(3, 2, warp=0.02)])
+    rng = np.random.default_rng(4242)
+    d = M.mask_displacements(m, rng.uniform(-1.0, 1.0, (m.n_nodes, 6)) * np.array([2e-3, 2e-3, 2e-3, 0.5, 0.5, 0.5]))
+    scen = util.dynamic_scenario(m, d, 99, time_step=0.02, rayleigh=(0.2, 5.0e-5))
+    scen["dyn_copy_vel"] = scen["dyn_copy_vel"] * np.array([1, 1, 1, 6.0, 6.0, 6.0])
+    els = (0, 5, 6, m.n_elements - 1)
+    z = dict(scen)
+    old = util.DYN_STEPS
+    util.DYN_STEPS = (("s1", 0, True, True), ("s2", 1, False, True), ("s3", 2, False, True))
+    try:
+        port.load(m); port.set_time(0.0, 0.5)
+        util.run_dynamic(port, m, scen, util.capture_dynamic(z, els))
+        asm = capi.Assembler(m).set_dofs()
+        asm.set_time(0.0, 0.5)
+        util.run_dynamic(asm, m, scen, util.check_dynamic(z, els, "large rotations"))
+        asm.close()
+    finally:
+        util.DYN_STEPS = old

@@ -82,3 +82,31 @@ def test_port_newmark_dynamics_match_reference_sources(ref, port, rayleigh):
         port.load(m)
         port.set_time(0.0, 0.5)
         util.run_dynamic(port, m, scen, util.check_dynamic(z, els, name))
+
+
+def _large_rotation_dynamic_case():
+    """Rotation increments of ~0.5 rad over three committed time steps: the committed Rodrigues vector alpha_i,
+    the gyroscopic terms and the forward-mode tangent far from the linear regime."""
+    m = M.concat_models([M.beam_line(6), M.shell_plate(3, 2, warp=0.02)])
+    rng = np.random.default_rng(4242)
+    d = rng.uniform(-1.0, 1.0, (m.n_nodes, 6)) * np.array([2e-3, 2e-3, 2e-3, 0.5, 0.5, 0.5])
+    return m, M.mask_displacements(m, d)
+
+
+def test_port_newmark_dynamics_large_rotations(ref, port):
+    m, d = _large_rotation_dynamic_case()
+    scen = util.dynamic_scenario(m, d, 99, time_step=0.02, rayleigh=(0.2, 5.0e-5))
+    scen["dyn_copy_vel"] = scen["dyn_copy_vel"] * np.array([1, 1, 1, 6.0, 6.0, 6.0])      # angular velocities of ~3 rad/s
+    els = (0, 5, 6, m.n_elements - 1)
+    z = dict(scen)
+    ref.load(m); ref.set_time(0.0, 0.5)
+    port.load(m); port.set_time(0.0, 0.5)
+    # three time steps, each with a commit: run the 3-assembly scenario and commit after every assembly
+    steps = (("s1", 0, True, True), ("s2", 1, False, True), ("s3", 2, False, True))
+    old = util.DYN_STEPS
+    util.DYN_STEPS = steps
+    try:
+        util.run_dynamic(ref, m, scen, util.capture_dynamic(z, els))
+        util.run_dynamic(port, m, scen, util.check_dynamic(z, els, "large rotations"))
+    finally:
+        util.DYN_STEPS = old
