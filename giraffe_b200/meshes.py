@@ -50,6 +50,9 @@ class Model:
     nodal_loads: list = field(default_factory=list)   # [(node ids, cs id, table[n,7])]
     # [n, 11] EA EI GJ GA Rho CDt CDn CAt CAn De Di (PipeSection.h:13-23); Pipe_1's elem_sec points here
     pipe_sections: np.ndarray = field(default_factory=lambda: np.zeros((0, 11)))
+    # ShellLoad (ShellLoad.h): [(element ids 1-based, area_update, table[n,2] = time, pressure)] -- a host-side
+    # contributor (Load), not part of the device path
+    shell_loads: list = field(default_factory=list)
 
     @property
     def n_nodes(self) -> int:

@@ -34,6 +34,8 @@
 #include "NodeSet.h"
 #include "NodalConstraint.h"
 #include "NodalLoad.h"
+#include "ShellLoad.h"
+#include "ElementSet.h"
 #include "Environment.h"
 #include "Solution.h"
 #include "Dynamic.h"
@@ -106,6 +108,7 @@ int ref_reset()
 	db.number_node_sets = 0; db.node_sets = NULL;
 	db.number_constraints = 0; db.constraints = NULL;
 	db.number_loads = 0; db.loads = NULL;
+	db.number_element_sets = 0; db.element_sets = NULL;
 	db.environment = NULL; db.environment_exist = false;
 	db.n_GL_free = 0; db.n_GL_fixed = 0;
 	g_dyn = NULL;
@@ -301,6 +304,33 @@ int ref_add_nodal_load(int n, const int* nodes, int cs, int n_times, const doubl
 	}
 	FILE* f = text_stream(buf.data());
 	NodalLoad* l = new NodalLoad();
+	bool ok = l->Read(f);
+	fclose(f);
+	if (!ok) return -1;
+	db.loads = grow(db.loads, db.number_loads);
+	db.loads[db.number_loads++] = l;
+	return l->number;
+}
+
+// ShellLoad over an ElementSet (reference ShellLoad.cpp:28-87 format): follower pressure on Shell_1 elements,
+// table rows: time pressure.  Goes through the reference's own reader; Shell_1::MountShellSpecialLoads
+// (Shell_1.cpp:1392-1467) then folds it into the element block during MountLoads.
+int ref_add_shell_load(int n_el, const int* elements, int area_update, int n_times, const double* table2)
+{
+	ElementSet* es = new ElementSet();
+	es->number = db.number_element_sets + 1;
+	es->n_el = n_el;
+	es->list = true;
+	es->el_list = new int[n_el];
+	for (int i = 0; i < n_el; i++) es->el_list[i] = elements[i];
+	db.element_sets = grow(db.element_sets, db.number_element_sets);
+	db.element_sets[db.number_element_sets++] = es;
+	std::vector<char> buf(256 + 100 * (size_t)n_times);
+	int w = snprintf(buf.data(), buf.size(), "%d ElementSet %d AreaUpdate %d NTimes %d\n", db.number_loads + 1, es->number, area_update ? 1 : 0, n_times);
+	for (int r = 0; r < n_times; r++)
+		w += snprintf(buf.data() + w, buf.size() - w, "%.17g %.17g\n", table2[2 * r], table2[2 * r + 1]);
+	FILE* f = text_stream(buf.data());
+	ShellLoad* l = new ShellLoad();
 	bool ok = l->Read(f);
 	fclose(f);
 	if (!ok) return -1;

@@ -20,6 +20,8 @@ Newton iteration and the reference's CSR matrices (AA/AB/BA/BB) and vectors
                    iterations, a commit (SaveLagrange) and one more iteration.
   shell_plate.npz  6x4-cell warped Shell_1 plate with gravity (doubled
                    self-weight quirk), same sequence.
+  shell_load.npz   ShellLoad follower pressure (AreaUpdate 0 and 1) folded into the shell blocks
+                   by MountLoads: the host-contributor seam of gfa_add_host_triplets.
   dynamic_beam.npz, dynamic_shell.npz, dynamic_pipe.npz
                    Newmark path (Dynamic.cpp:303-340): UpdateDyn, MountMass,
                    MountDamping (Rayleigh update on the first iteration), MountDyn
@@ -157,11 +159,40 @@ def dynamic(R):
         print(name, "n_free", R.n_free, "nnz_AA", len(z["s1_AA_val"]))
 
 
+def shell_load(R):
+    """ShellLoad follower pressure (ShellLoad.cpp:133-148 -> Shell_1::MountShellSpecialLoads, Shell_1.cpp:1392-1467),
+    one load with AreaUpdate 0 and one with AreaUpdate 1 on different element sets of a warped plate: two
+    iterations, a commit (so that copy_coordinates differ from the reference ones) and a third iteration."""
+    m = M.shell_plate(5, 4, warp=0.02, gravity=(0.0, 0.0, -9.81))
+    m.shell_loads = [(np.array([2, 5, 6, 11, 17, 30], np.int32), False, np.array([[0.0, 0.0], [1.0, 6.0e7]])),
+                     (np.array([9, 10, 23, 38], np.int32), True, np.array([[0.0, 1.0e7], [1.0, -4.0e7]]))]
+    R.load(m)
+    R.set_time(0.0, 0.7)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([0.0, 0.7])
+    z["gls"] = R.gls()
+    rng = np.random.default_rng(20240021)
+    d1 = M.mask_displacements(m, rng.uniform(-2e-3, 2e-3, (m.n_nodes, 6)))
+    for tag, d, commit_after in (("it1", d1, False), ("it2", 0.6 * d1, True), ("it3", -0.35 * d1, False)):
+        z[f"{tag}_copy_before"] = R.copy_coordinates()
+        R.assemble(d, with_loads=True)
+        z[f"{tag}_disp"] = d.copy()
+        z.update(util.capture(R, tag))
+        if commit_after:
+            R.commit()
+    np.savez_compressed(os.path.join(OUT, "shell_load.npz"), **z)
+    print("shell_load: n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
+
+
 if __name__ == "__main__":
     R = RefOracle(threads=1)
     if sys.argv[1:] == ["dynamic"]:          # only the fixtures of the Newmark path
         dynamic(R)
         sys.exit(0)
+    if sys.argv[1:] == ["shell_load"]:
+        shell_load(R)
+        sys.exit(0)
+    shell_load(R)
     dynamic(R)
     newton_steps(R)
     tutorial01(R)

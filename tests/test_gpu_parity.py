@@ -510,3 +510,32 @@ def test_newmark_dynamics_large_rotations(port):
         asm.close()
     finally:
         util.DYN_STEPS = old
+
+
+def test_shell_load_host_contributor_through_the_c_abi():
+    """ShellLoad follower pressure (a Load: host side) pushed with gfa_add_host_triplets / gfa_add_host_vector on top
+    of the device assembly, against what the reference's MountLoads + MountGlobal produced (AreaUpdate 0 and 1,
+    before and after a commit).  Its non-symmetric u-u blocks land in existing slots of the element pattern."""
+    z = _golden("shell_load")
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(*z["time"])
+    assert (asm.gls == z["gls"]).all()
+    t = float(z["time"][0] + z["time"][1])
+    for tag, commit in (("it1", False), ("it2", True), ("it3", False)):
+        disp = z[f"{tag}_disp"]
+        asm.assemble(disp)
+        trip, pa_add, pb_add = util.shell_load_contribution(m, asm.gls, disp, asm.copy_coordinates(), t)
+        for w in ("AA", "AB", "BA", "BB"):
+            if trip[w][0]:
+                asm.add_host_triplets(w, *trip[w])
+        asm.add_host_vector(capi.P_A, *pa_add)
+        asm.add_host_vector(capi.I_A, *pa_add)
+        if pb_add[0]:
+            asm.add_host_vector(capi.P_B, *pb_add)
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), asm.csr, f"shell_load {tag}")
+        for v, key in zip(asm.vectors(), ("PA", "IA", "PB")):
+            util.assert_parity(z[f"{tag}_{key}"], v, f"shell_load {tag} {key}")
+        if commit:
+            asm.commit()
+    asm.close()

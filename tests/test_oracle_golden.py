@@ -118,3 +118,44 @@ def test_newmark_dynamics(port, name):
     port.set_time(*z["time"])
     assert (port.gls() == z["gls"]).all()
     util.run_dynamic(port, m, z, util.check_dynamic(z, (1, m.n_elements - 1), name))
+
+
+def test_shell_load_host_contributor(port):
+    """ShellLoad follower pressure stays on the host (it is a Load): the restatement in tests/util.py added to the
+    oracle's element assembly reproduces what the reference's MountLoads + MountGlobal produced."""
+    import scipy.sparse as sp
+    z = _load("shell_load")
+    m = util.model_from_dict(z)
+    assert len(m.shell_loads) == 2
+    port.load(m)
+    port.set_time(*z["time"])
+    assert (port.gls() == z["gls"]).all()
+    t = float(z["time"][0] + z["time"][1])
+    for tag, commit in (("it1", False), ("it2", True), ("it3", False)):
+        disp = z[f"{tag}_disp"]
+        util.assert_parity(z[f"{tag}_copy_before"], port.copy_coordinates(), f"shell_load {tag} copy coordinates")
+        port.assemble(disp)
+        trip, pa_add, pb_add = util.shell_load_contribution(m, port.gls(), disp, port.copy_coordinates(), t)
+
+        def with_load(w):
+            o, i, v, s = port.csr(w)
+            if len(trip[w][0]) == 0:
+                return o, i, v, s
+            # the load only adds into positions of the element pattern: look each one up in it
+            base = sp.csr_matrix((np.arange(1, len(v) + 1, dtype=float), i, o), shape=s)
+            out = v.copy()
+            add = sp.coo_matrix((trip[w][2], (trip[w][0], trip[w][1])), shape=s).tocsr()
+            add.sum_duplicates()
+            rows = np.repeat(np.arange(s[0]), np.diff(add.indptr))
+            pos = np.asarray(base[rows, add.indices]).reshape(-1).astype(np.int64) - 1
+            assert (pos >= 0).all(), "ShellLoad position outside the element pattern"
+            out[pos] += add.data
+            return o, i, out, s
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), with_load, f"shell_load {tag}")
+        pa, ia, pb = port.vectors()
+        np.add.at(pa, pa_add[0], pa_add[1]); np.add.at(ia, pa_add[0], pa_add[1]); np.add.at(pb, pb_add[0], pb_add[1])
+        util.assert_parity(z[f"{tag}_PA"], pa, f"shell_load {tag} P_A")
+        util.assert_parity(z[f"{tag}_IA"], ia, f"shell_load {tag} I_A")
+        util.assert_parity(z[f"{tag}_PB"], pb, f"shell_load {tag} P_B")
+        if commit:
+            port.commit()

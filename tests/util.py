@@ -109,7 +109,12 @@ def model_to_dict(m: M.Model, prefix: str = "m_") -> dict:
         "n_constraints": np.array([len(m.constraints)]),
         "n_loads": np.array([len(m.nodal_loads)]),
         "pipe_sections": np.asarray(m.pipe_sections, float).reshape(-1, 11),
+        "n_shell_loads": np.array([len(m.shell_loads)]),
     }
+    for i, (elements, area_update, table) in enumerate(m.shell_loads):
+        d[f"s{i}_elements"] = np.asarray(elements, np.int32)
+        d[f"s{i}_area_update"] = np.array([1 if area_update else 0])
+        d[f"s{i}_table"] = np.asarray(table, float)
     for i, (nodes, mask) in enumerate(m.constraints):
         d[f"c{i}_nodes"] = np.asarray(nodes, np.int32)
         d[f"c{i}_mask"] = np.array([mask])
@@ -137,6 +142,8 @@ def model_from_dict(z, prefix: str = "m_") -> M.Model:
     m.nodal_loads = [(g(f"l{i}_nodes"), int(g(f"l{i}_cs")[0]), g(f"l{i}_table")) for i in range(int(g("n_loads")[0]))]
     if prefix + "pipe_sections" in getattr(z, "files", z):
         m.pipe_sections = np.asarray(g("pipe_sections"), float).reshape(-1, 11)
+    if prefix + "n_shell_loads" in getattr(z, "files", z):
+        m.shell_loads = [(g(f"s{i}_elements"), bool(g(f"s{i}_area_update")[0]), g(f"s{i}_table")) for i in range(int(g("n_shell_loads")[0]))]
     return m
 
 
@@ -313,3 +320,98 @@ def check_dynamic(z, elements, what: str):
             assert_parity(z[f"{tag}_elem{e}_K"], K, f"{what} {tag} element {e} K", block_scale(z[f"{tag}_elem{e}_K"]))
             assert_parity(z[f"{tag}_elem{e}_P"], P, f"{what} {tag} element {e} P")
     return cb
+
+
+# ---- ShellLoad: follower pressure on Shell_1 elements, a coexisting HOST contributor ------------------
+_COWPER = np.array([
+    [0.816847572980459, 0.091576213509771, 0.091576213509771, 0.109951743655322],
+    [0.091576213509771, 0.816847572980459, 0.091576213509771, 0.109951743655322],
+    [0.091576213509771, 0.091576213509771, 0.816847572980459, 0.109951743655322],
+    [0.108103018168070, 0.445948490915965, 0.445948490915965, 0.223381589678011],
+    [0.445948490915965, 0.108103018168070, 0.445948490915965, 0.223381589678011],
+    [0.445948490915965, 0.445948490915965, 0.108103018168070, 0.223381589678011]])
+
+
+def _skew(v):
+    return np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def shell_load_contribution(m: M.Model, gls: np.ndarray, disp: np.ndarray, copy: np.ndarray, time: float):
+    """Host restatement of ShellLoad::Mount -> Shell_1::MountShellSpecialLoads (reference ShellLoad.cpp:133-148,
+    Shell_1.cpp:1392-1467): follower pressure integrated with the 6-point rule on the current configuration
+    (copy_coordinates + displacements), its non-symmetric load stiffness on the u-u blocks and its force on
+    P_loading.  Returns (triplets per matrix, additions to P_A and I_A (the same), additions to P_B): what the
+    host pushes through gfa_add_host_triplets / gfa_add_host_vector after gfa_assemble.  `copy` is
+    Node::copy_coordinates [n,6] (gfa_copy_coordinates)."""
+    trip = {w: ([], [], []) for w in ("AA", "AB", "BA", "BB")}
+    pa, pb = ([], []), ([], [])
+    conn = m.elem_nodes
+    for elements, area_update, table in m.shell_loads:
+        table = np.asarray(table, float)
+        pressure = float(np.interp(time, table[:, 0], table[:, 1]))
+        for e1 in np.asarray(elements, int):
+            e = e1 - 1
+            nd = conn[m.elem_ptr[e]:m.elem_ptr[e + 1]].astype(int) - 1
+            x = m.xyz[nd]
+            nvec = np.cross(x[1] - x[0], x[2] - x[0])
+            A = 0.5 * np.linalg.norm(nvec)
+            e3 = nvec / np.linalg.norm(nvec)
+            eg = np.array([1.0, 0.0, 0.0])
+            if abs(eg @ e3) >= 1.0 - 1e-4:
+                eg = np.array([0.0, 1.0, 0.0])
+            e1r = eg - (eg @ e3) * e3
+            e1r = e1r / np.linalg.norm(e1r)
+            e2r = np.cross(e3, e1r)
+            Lx = 0.5 * np.array([(x[1] - x[2]) @ e2r, (x[2] - x[0]) @ e2r, (x[0] - x[1]) @ e2r]) / A
+            Ly = 0.5 * np.array([(x[2] - x[1]) @ e1r, (x[0] - x[2]) @ e1r, (x[1] - x[0]) @ e1r]) / A
+            u = copy[nd, :3] - x + disp[nd, :3]                       # pu_ip, global axes
+            K = np.zeros((18, 18))
+            P = np.zeros(18)
+            for L1, L2, L3, wq in _COWPER:
+                L = np.array([L1, L2, L3])
+                w4 = A * wq
+                N = np.array([(2 * L1 - 1) * L1, (2 * L2 - 1) * L2, (2 * L3 - 1) * L3, 4 * L1 * L2, 4 * L2 * L3, 4 * L3 * L1])
+
+                def grad(D):
+                    return np.array([4 * D[0] * L[0] - D[0], 4 * D[1] * L[1] - D[1], 4 * D[2] * L[2] - D[2],
+                                     4 * D[0] * L[1] + 4 * L[0] * D[1], 4 * D[1] * L[2] + 4 * L[1] * D[2],
+                                     4 * D[2] * L[0] + 4 * L[2] * D[0]])
+                N1, N2 = grad(Lx), grad(Ly)
+                t1 = e1r + N1 @ u
+                t2 = e2r + N2 @ u
+                c = np.cross(t1, t2)
+                jac = np.linalg.norm(c)
+                n = c / jac
+                q = -1.0 * pressure * n
+                if not area_update:
+                    proj = (1.0 / jac) * (np.eye(3) - np.outer(n, n))
+                    scale = w4
+                else:
+                    proj = np.eye(3)
+                    scale = w4 * jac
+                for a in range(6):
+                    P[3 * a:3 * a + 3] -= scale * N[a] * q
+                    for b in range(6):
+                        Kp = proj @ (_skew(t1) * N2[b] - _skew(t2) * N1[b])
+                        K[3 * a:3 * a + 3, 3 * b:3 * b + 3] += w4 * 1.0 * pressure * N[a] * Kp
+            g = gls[nd, :3].reshape(-1)
+            for i in range(18):
+                gi = g[i]
+                if gi > 0:
+                    pa[0].append(gi - 1); pa[1].append(P[i])
+                elif gi < 0:
+                    pb[0].append(-gi - 1); pb[1].append(P[i])
+                for j in range(18):
+                    gj = g[j]
+                    if gi > 0 and gj > 0:
+                        w, r, cc = "AA", gi - 1, gj - 1
+                    elif gi < 0 and gj < 0:
+                        w, r, cc = "BB", -gi - 1, -gj - 1
+                    elif gi > 0 and gj < 0:
+                        w, r, cc = "AB", gi - 1, -gj - 1
+                    elif gi < 0 and gj > 0:
+                        w, r, cc = "BA", -gi - 1, gj - 1
+                    else:
+                        continue
+                    trip[w][0].append(r); trip[w][1].append(cc); trip[w][2].append(K[i, j])
+    return trip, pa, pb
