@@ -13,7 +13,8 @@
 //   host.Clear()                 Solution::Clear         (Solution.cpp:833-848)
 //   host.MountLocal()            Solution::MountLocal + MountElementLoads + MountGlobal + MountSparse
 //                                for the device element types                    -> gfa_assemble
-//   host.MountLoads()            Solution::MountLoads    (NodalLoad::Mount, NodalLoad.cpp:322-401, host side)
+//   host.MountLoads()            Solution::MountLoads    (NodalLoad::Mount, NodalLoad.cpp:322-401; ShellLoad::Mount ->
+//                                Shell_1::MountShellSpecialLoads, Shell_1.cpp:1392-1467; host side)
 //   host.UpdateDisps(x)          Solution::UpdateDisps   (Solution.cpp:390-402)
 //   host.SaveConfiguration()     Solution::SaveConfiguration (Solution.cpp:426-454) -> gfa_commit_state
 //   host.GetGaussPointResults()  what WriteResults / WriteMonitor read from the elements   -> gfa_gauss_point_results
@@ -35,6 +36,13 @@ struct GfaNodalLoad {              // NodalLoad with a numeric table (NodalLoad.
     int node_set = 0, cs = 0;
     std::vector<double> table;     // rows: time FX FY FZ MX MY MZ
     double GetValueAt(double t, int column) const;   // Table::GetValueAt, linear interpolation
+};
+
+struct GfaShellLoad {              // ShellLoad with a numeric table (ShellLoad.h): follower pressure on an ElementSet
+    int element_set = 0;
+    bool area_update = false;
+    std::vector<double> table;     // rows: time pressure
+    double GetValueAt(double t) const;
 };
 
 class GfaHost {
@@ -59,6 +67,8 @@ public:
     struct NodalConstraint { int node_set; int mask; };
     std::vector<NodalConstraint> nodal_constraints;
     std::vector<GfaNodalLoad> loads;
+    std::vector<std::vector<int> > element_sets;  // ElementSet::el_list, 1-based (ElementSet.h)
+    std::vector<GfaShellLoad> shell_loads;        // ShellLoad (host contributor: Shell_1::MountShellSpecialLoads)
     bool g_exist = false;
     double G[3] = { 0, 0, 0 };
     double end_time = 1.0, time_step = 1.0;       // first solution step (Static.cpp:43-130, Dynamic.cpp:65-222)
@@ -86,7 +96,7 @@ public:
     void MountElementLoads() {}                   // folded into MountLocal()
     void MountGlobal() {}                         // folded into MountLocal()
     void MountSparse() {}                         // folded into MountLocal()
-    bool MountLoads();                            // host NodalLoad -> gfa_add_host_triplets / gfa_add_host_vector
+    bool MountLoads();                            // host NodalLoad / ShellLoad -> gfa_add_host_triplets / gfa_add_host_vector
     void UpdateDisps(const double* x_A);          // displacements[j] += x(GL-1) for free active DOFs
     bool SaveConfiguration();
     // Dynamic::Solve

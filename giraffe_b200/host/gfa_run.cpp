@@ -23,9 +23,9 @@ int main(int argc, char** argv) {
     host.SetGlobalDOFs();
     if (parse_only) {
         printf("{\"nodes\": %d, \"elements\": %d, \"n_GL_free\": %d, \"n_GL_fixed\": %d, \"loads\": %zu, \"node_sets\": %zu, \"time_step\": %.17g, \"end_time\": %.17g, "
-               "\"dynamic\": %d, \"alpha\": %.17g, \"beta\": %.17g, \"update\": %d, \"beta_new\": %.17g, \"gamma_new\": %.17g}\n",
+               "\"dynamic\": %d, \"alpha\": %.17g, \"beta\": %.17g, \"update\": %d, \"beta_new\": %.17g, \"gamma_new\": %.17g, \"shell_loads\": %zu, \"element_sets\": %zu}\n",
                host.number_nodes(), host.number_elements(), host.n_GL_free, host.n_GL_fixed, host.loads.size(), host.node_sets.size(), host.time_step, host.end_time,
-               host.dynamic ? 1 : 0, host.alpha, host.beta, host.update, host.beta_new, host.gamma_new);
+               host.dynamic ? 1 : 0, host.alpha, host.beta, host.update, host.beta_new, host.gamma_new, host.shell_loads.size(), host.element_sets.size());
         return 0;
     }
     if (!host.PreCalc(0)) { fprintf(stderr, "PreCalc: %s\n", host.last_error().c_str()); return 1; }

@@ -7,8 +7,8 @@ assembly path does not consume (SolverOptions, Monitor, PostFiles,
 ConvergenceCriteria, ...) are skipped up to the next known keyword.
 Supported: Nodes, Elements (Beam_1 / Pipe_1 / Shell_1 / Solid_1), Materials (Hooke),
 Sections (Rectangle / Tube), PipeSections (PS), ShellSections (Homogeneous), CoordinateSystems,
-NodeSets (List / Sequence), Constraints (NodalConstraint), Loads (NodalLoad
-with a numeric table), Environment (GravityData), SolutionSteps (Static / Dynamic, for the
+NodeSets / ElementSets (List / Sequence), Constraints (NodalConstraint), Loads (NodalLoad,
+ShellLoad with a numeric table), Environment (GravityData), SolutionSteps (Static / Dynamic, for the
 time-stepping data, Rayleigh and Newmark coefficients only).
 """
 from __future__ import annotations
@@ -38,6 +38,7 @@ def read_inp(path: str):
     i = 0
     nodes, mats, secs, shsecs, csd, pipes = {}, {}, {}, {}, {}, {}
     elems, nodesets, cons, loads = [], {}, [], []
+    elemsets, shloads = {}, []
     gravity = None
     info = {}
 
@@ -141,10 +142,25 @@ def read_inp(path: str):
         elif kw == "Loads":
             n = int(tk[i + 1]); i += 2
             for _ in range(n):
+                if tk[i] == "ShellLoad":      # ShellLoad id ElementSet s AreaUpdate b NTimes n (ShellLoad.cpp:28-87)
+                    es, au, nt = int(tk[i + 3]), int(tk[i + 5]), int(tk[i + 7]); i += 8
+                    table = np.array([float(t) for t in tk[i:i + 2 * nt]]).reshape(nt, 2); i += 2 * nt
+                    shloads.append((es, bool(au), table))
+                    continue
                 assert tk[i] == "NodalLoad", f"load {tk[i]} stays on the host"
                 sid, cs, nt = int(tk[i + 3]), int(tk[i + 5]), int(tk[i + 7]); i += 8
                 table = np.array([float(t) for t in tk[i:i + 7 * nt]]).reshape(nt, 7); i += 7 * nt
                 loads.append((sid, cs, table))
+        elif kw == "ElementSets":        # ElementSet id Elements n List ... | Sequence Initial a Increment k (ElementSet.cpp:27-95)
+            n = int(tk[i + 1]); i += 2
+            for _ in range(n):
+                assert tk[i] == "ElementSet"
+                sid, cnt = int(tk[i + 1]), int(tk[i + 3])
+                if tk[i + 4] == "List":
+                    elemsets[sid] = [int(t) for t in tk[i + 5:i + 5 + cnt]]; i += 5 + cnt
+                else:
+                    a, inc = int(tk[i + 6]), int(tk[i + 8])
+                    elemsets[sid] = [a + k * inc for k in range(cnt)]; i += 9
         elif kw == "Environment":
             i += 1
             if tk[i] == "GravityData":
@@ -189,6 +205,7 @@ def read_inp(path: str):
     m.constraints = [(np.array(nodesets[s], np.int32), mask) for s, mask in cons]
     m.nodal_loads = [(np.array(nodesets[s], np.int32), cs, t) for s, cs, t in loads]
     m.gravity = gravity
+    m.shell_loads = [(np.array(elemsets[es], np.int32), au, t) for es, au, t in shloads]
     info["node_sets"] = nodesets
     return _finish(m), info
 
@@ -251,11 +268,20 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
         if dynamic:
             f.write(f"RayleighDamping\tAlpha\t{_r(dynamic['alpha'])}\tBeta\t{_r(dynamic['beta'])}\tUpdate\t{int(dynamic['update'])}\n"
                     f"NewmarkCoefficients\tBeta\t{_r(dynamic['beta_new'])}\tGamma\t{_r(dynamic['gamma_new'])}\n")
-        if m.nodal_loads:
-            f.write(f"\nLoads\t{len(m.nodal_loads)}\n")
+        if m.shell_loads:
+            f.write(f"\nElementSets\t{len(m.shell_loads)}\n")
+            for k, (elements, _, _) in enumerate(m.shell_loads):
+                f.write(f"ElementSet\t{k + 1}\tElements\t{len(elements)}\tList\t" + "\t".join(str(int(e)) for e in elements) + "\n")
+        if m.nodal_loads or m.shell_loads:
+            f.write(f"\nLoads\t{len(m.nodal_loads) + len(m.shell_loads)}\n")
             for k, (nodes, cs, table) in enumerate(m.nodal_loads):
                 table = np.asarray(table, float)
                 f.write(f"NodalLoad\t{k + 1}\tNodeSet\t{len(m.constraints) + k + 1}\tCS\t{cs}\tNTimes\t{len(table)}\n")
+                for row in table:
+                    f.write("\t".join(repr(float(v)) for v in row) + "\n")
+            for k, (elements, area_update, table) in enumerate(m.shell_loads):
+                table = np.asarray(table, float)
+                f.write(f"ShellLoad\t{len(m.nodal_loads) + k + 1}\tElementSet\t{k + 1}\tAreaUpdate\t{1 if area_update else 0}\tNTimes\t{len(table)}\n")
                 for row in table:
                     f.write("\t".join(repr(float(v)) for v in row) + "\n")
         if m.constraints:

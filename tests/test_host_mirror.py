@@ -121,3 +121,50 @@ def test_cpp_host_dynamic_sequence_matches_python_binding(tmp_path):
     assert abs(out["sum_AA"] - val.sum()) <= 1e-9 * np.abs(val).sum()
     assert abs(out["max_AA"] - np.abs(val).max()) <= 1e-12 * np.abs(val).max()
     assert abs(out["max_P_A"] - np.abs(pa).max()) <= 1e-12 * np.abs(pa).max()
+
+
+def _pressure_model():
+    m = M.concat_models([M.beam_line(4), M.shell_plate(4, 3, warp=0.02)])
+    m.gravity = (0.0, 0.0, -9.81)
+    m.shell_loads = [(np.array([6, 9, 10, 20], np.int32), False, np.array([[0.0, 0.0], [1.0, 4.0e7]])),
+                     (np.array([13, 14], np.int32), True, np.array([[0.0, 0.0], [1.0, -2.0e7]]))]
+    return m
+
+
+def test_shell_load_inp_round_trip(tmp_path):
+    m = _pressure_model()
+    p = str(tmp_path / "pressure.inp")
+    write_inp(m, p, time_step=0.5)
+    m2, _ = read_inp(p)
+    assert len(m2.shell_loads) == 2
+    for (e1, a1, t1), (e2, a2, t2) in zip(m.shell_loads, m2.shell_loads):
+        assert np.array_equal(e1, e2) and a1 == a2 and np.array_equal(t1, t2)
+    if os.path.exists(EXE):
+        out = json.loads(subprocess.check_output([EXE, "--parse-only", p]))
+        assert out["shell_loads"] == 2 and out["element_sets"] == 2
+
+
+@pytest.mark.gpu
+def test_cpp_host_shell_load_matches_python_host_step(tmp_path):
+    """GfaHost::MountLoads with ShellLoad (C++) against the Python restatement of the same host step
+    (tests/util.py, pinned to the reference by tests/golden/shell_load.npz), both over the C-ABI."""
+    from giraffe_b200 import capi
+    m = _pressure_model()
+    p = str(tmp_path / "pressure.inp")
+    write_inp(m, p, time_step=0.5)
+    out = json.loads(subprocess.check_output([EXE, p]))
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(0.0, 0.5)
+    d = np.zeros((m.n_nodes, 6))
+    asm.assemble(d)
+    trip, pa_add, pb_add = util.shell_load_contribution(m, asm.gls, d, asm.copy_coordinates(), 0.5)
+    for w in ("AA", "AB", "BA", "BB"):
+        if trip[w][0]:
+            asm.add_host_triplets(w, *trip[w])
+    asm.add_host_vector(capi.P_A, *pa_add)
+    val = asm.values("AA")
+    pa = asm.vectors()[0]
+    assert out["nnz_AA"] == len(val)
+    assert abs(out["sum_AA"] - val.sum()) <= 1e-9 * np.abs(val).sum()
+    assert abs(out["max_AA"] - np.abs(val).max()) <= 1e-12 * np.abs(val).max()
+    assert abs(out["max_P_A"] - np.abs(pa).max()) <= 1e-12 * np.abs(pa).max()
