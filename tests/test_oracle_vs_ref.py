@@ -110,3 +110,38 @@ def test_port_newmark_dynamics_large_rotations(ref, port):
         util.run_dynamic(port, m, scen, util.check_dynamic(z, els, "large rotations"))
     finally:
         util.DYN_STEPS = old
+
+
+def test_port_matches_reference_on_random_models(ref, port):
+    """Seeded random variations the fixed cases do not reach: random constraint masks on random nodes (partly
+    constrained translations and rotations, fully fixed and free-floating nodes), random plate / line sizes and
+    warps, gravity on or off, displacement amplitudes from 1e-6 to 1e-2, with a commit between iterations."""
+    rng = np.random.default_rng(20240031)
+    for trial in range(12):
+        nb = int(rng.integers(2, 9)); nx = int(rng.integers(1, 5)); ny = int(rng.integers(1, 4))
+        parts = []
+        if trial % 3 != 1:
+            parts.append(M.beam_line(nb, pretension=float(rng.choice([0.0, 3.0e4]))))
+        if trial % 3 != 2:
+            parts.append(M.shell_plate(nx, ny, warp=float(rng.choice([0.0, 0.01, 0.05]))))
+        if trial % 4 == 0:
+            parts.append(M.pipe_line(int(rng.integers(2, 6))))
+        m = M.concat_models(parts)
+        m.gravity = None if trial % 2 else (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), -9.81)
+        extra = []
+        for _ in range(int(rng.integers(1, 5))):
+            node = int(rng.integers(1, m.n_nodes + 1))
+            extra.append(([node], int(rng.integers(1, 64))))
+        m.constraints = m.constraints + extra
+        amp = 10.0 ** rng.uniform(-6, -2)
+        d = M.mask_displacements(m, rng.uniform(-amp, amp, (m.n_nodes, 6)))
+        ref.load(m); port.load(m)
+        ref.set_time(0.0, 0.3); port.set_time(0.0, 0.3)
+        assert (ref.gls() == port.gls()).all(), f"trial {trial}: DOF numbering"
+        for it in range(2):
+            ref.assemble(d); port.assemble(d)
+            util.assert_system_parity(ref.csr, port.csr, f"random trial {trial} it{it}")
+            for a, b, key in zip(ref.vectors(), port.vectors(), ("PA", "IA", "PB")):
+                util.assert_parity(a, b, f"random trial {trial} it{it} {key}")
+            ref.commit(); port.commit()
+            d = -0.7 * d
