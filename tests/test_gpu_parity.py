@@ -539,3 +539,39 @@ def test_shell_load_host_contributor_through_the_c_abi():
         if commit:
             asm.commit()
     asm.close()
+
+
+def test_random_models_against_oracle(port):
+    """Seeded random variations (the oracle is pinned to the reference on the same generator by
+    tests/test_oracle_vs_ref.py): random constraint masks on random nodes, sizes, warps, gravity, displacement
+    amplitudes from 1e-6 to 1e-2, with a commit between iterations."""
+    rng = np.random.default_rng(20240031)
+    for trial in range(12):
+        nb = int(rng.integers(2, 9)); nx = int(rng.integers(1, 5)); ny = int(rng.integers(1, 4))
+        parts = []
+        if trial % 3 != 1:
+            parts.append(M.beam_line(nb, pretension=float(rng.choice([0.0, 3.0e4]))))
+        if trial % 3 != 2:
+            parts.append(M.shell_plate(nx, ny, warp=float(rng.choice([0.0, 0.01, 0.05]))))
+        if trial % 4 == 0:
+            parts.append(M.pipe_line(int(rng.integers(2, 6))))
+        m = M.concat_models(parts)
+        m.gravity = None if trial % 2 else (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), -9.81)
+        extra = []
+        for _ in range(int(rng.integers(1, 5))):
+            node = int(rng.integers(1, m.n_nodes + 1))
+            extra.append(([node], int(rng.integers(1, 64))))
+        m.constraints = m.constraints + extra
+        amp = 10.0 ** rng.uniform(-6, -2)
+        d = M.mask_displacements(m, rng.uniform(-amp, amp, (m.n_nodes, 6)))
+        port.load(m)
+        port.set_time(0.0, 0.3)
+        asm = capi.Assembler(m).set_dofs()
+        asm.set_time(0.0, 0.3)
+        assert (asm.gls == port.gls()).all(), f"trial {trial}: DOF numbering"
+        for it in range(2):
+            port.assemble(d); asm.assemble(d)
+            _compare_system(port, asm, f"random trial {trial} it{it}")
+            port.commit(); asm.commit()
+            d = -0.7 * d
+        asm.close()
