@@ -30,6 +30,7 @@ EXPORTS = [
     "gfa_residual", "gfa_update_displacements", "gfa_displacements", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
     "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue", "gfa_interface_stream",
+    "gfa_pipeline_info",
 ]
 
 
@@ -122,6 +123,7 @@ def load_library() -> C.CDLL:
         lib.gfa_update_dyn.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DynamicStruct)]
         lib.gfa_assemble_dynamic.argtypes = [C.c_void_p, C.POINTER(_StepStruct), C.POINTER(_DynamicStruct)]
         lib.gfa_element_alpha_i.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        lib.gfa_pipeline_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
         _lib = lib
     return _lib
 
@@ -408,6 +410,12 @@ class Assembler:
 
     def launch_count(self) -> int:
         return self.lib.gfa_last_launch_count(self._h)
+
+    def pipeline_info(self):
+        """(ring, description): which pipeline gfa_set_dofs chose (fused ring kernel or classic two kernels)"""
+        buf = C.create_string_buffer(512)
+        rc = self._check(self.lib.gfa_pipeline_info(self._h, buf, 512))
+        return bool(rc), buf.value.decode()
 
     # ---- multi-GPU interface rows -----------------------------------------
     def interface_counts(self, world: int):

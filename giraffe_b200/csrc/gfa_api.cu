@@ -86,8 +86,15 @@ struct TypeBlock {
     std::vector<int> conn, prop;
     std::vector<double> props, pret;
     bool any_pret = false;
-    long long ke_base = 0;
+    long long ke_base = 0;           // classic arena: first double of this type's block
     int pe_base = 0;
+    // arena placement of every local element (offset of its first double in d_Ke), set by gfa_set_dofs
+    std::vector<long long> ke_off;
+    // ring pipeline: elements evaluated into the ring (ascending) and the pinned ones (own regions behind it)
+    std::vector<int> ring_list, pin_list;
+    int chunk_el = 0, chunk0 = 0, n_chunks = 0;
+    long long pin_base = 0;          // first double of this type's pinned regions in d_Ke
+    DevBuf<int> d_ring_list, d_pin_list;
     DevBuf<int> d_conn, d_prop;
     DevBuf<double> d_props, d_pret, d_state, d_geo, d_shp;
     // Newmark dynamics: committed Rodrigues vector per Gauss point (always kept: SaveLagrange updates it in
@@ -157,6 +164,32 @@ struct gfa_handle {
     DevBuf<long long> d_send_idx, d_recv_idx;
     std::vector<int> owned_rows;
 
+    // ring pipeline (fused evaluation + scatter, FusedArgs in gfa_device.h); `ring` false = classic two-kernel path
+    bool ring = false, force_classic = false;
+    int ring_chunks = 0, ring_span = 0, total_chunks = 0;
+    long long chunk_doubles = 0, ring_doubles = 0;
+    long long n_pre_runs = 0;             // runs fed by pinned elements only: scattered by the classic kernel before the fused launches
+    DevBuf<long long> d_chunk_run_ptr;
+    DevBuf<int> d_chunk_tile_ptr, d_chunk_batches;
+    cudaStream_t stream_sc = nullptr;     // the scatter kernel of the ring pipeline runs here, beside the evaluation kernels on `stream`
+    cudaEvent_t ev_ctl = nullptr, ev_scattered = nullptr;
+    DevBuf<unsigned> d_ctl;
+    DevBuf<double> d_scratch_ke;          // one element's blocks, for gfa_element_block in ring mode
+    DevBuf<int> d_one;
+    std::string ring_note;                // why the classic path was chosen, or the ring geometry
+    // arguments of the last gfa_set_dofs (replayed when a handle has to leave ring mode)
+    std::vector<int> ex_mat, ex_rows, ex_cols;
+    long long n_vec_untouched = 0;        // vector entries no element of this rank writes (zeroed per assembly)
+    // persistent staging of gfa_add_host_*
+    DevBuf<long long> d_stage_slots; DevBuf<double> d_stage_vals;
+    std::vector<long long> stage_slots; std::vector<double> stage_vals;
+
+    int fused_eval_warps[3] = { 0, 0, 0 };
+    int fused_tile_group = 8, fused_scatter_ctas = 1;
+    unsigned long long fused_timeout_ns = 4000000000ULL;
+    bool abort_check_pending = false;     // the watchdog flag of the last fused launches has not been read yet
+    double last_gfac = 0.0;
+
     bool assembled = false;
     bool timing_pending = false;          // events of the last assembly not read yet (gfa_assemble_enqueue)
     float last_ms[4] = { 0, 0, 0, 0 };
@@ -165,11 +198,14 @@ struct gfa_handle {
 
 namespace {
 
-EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
+enum EvalPass { PASS_ALL, PASS_PINNED, PASS_RING };
+
+EvalArgs eval_args(gfa_t* h, int slot, double gfac, EvalPass pass = PASS_ALL) {
     TypeBlock& t = h->tb[slot];
     EvalArgs a;
     a.n_el = (int)t.elems.size();
     a.e_begin = 0; a.e_end = a.n_el;
+    a.elist = nullptr; a.ring_chunks = 0; a.chunk_el = 1; a.chunk0 = 0; a.chunk_doubles = 0;
     a.conn = t.d_conn.p; a.prop = t.d_prop.p; a.props = t.d_props.p;
     a.pret = t.any_pret ? t.d_pret.p : nullptr;
     a.xyz = h->d_xyz.p; a.copy = h->d_copy.p; a.disp = h->d_disp.p;
@@ -179,12 +215,20 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac) {
     a.Pe = h->d_Pe.p + t.pe_base;
     const double f = h->gravity_on ? gfac : 0.0;
     a.gx = h->grav[0] * f; a.gy = h->grav[1] * f; a.gz = h->grav[2] * f;
+    if (pass == PASS_PINNED) {          // ring mode: the pinned elements, each into its own region behind the ring
+        a.elist = t.d_pin_list.p; a.e_end = (int)t.pin_list.size();
+        a.Ke = h->d_Ke.p + t.pin_base;
+    } else if (pass == PASS_RING) {
+        a.elist = t.pin_list.empty() ? nullptr : t.d_ring_list.p; a.e_end = (int)t.ring_list.size();
+        a.Ke = h->d_Ke.p;
+        a.ring_chunks = h->ring_chunks; a.chunk_el = t.chunk_el; a.chunk0 = t.chunk0; a.chunk_doubles = h->chunk_doubles;
+    }
     return a;
 }
 
 // offset (in doubles) of block (la, b) of a local element in the Ke arena; `tr` = stored transposed
 inline long long arena_block(const gfa_t* h, int slot, int local, int la, int b, bool& tr) {
-    const long long base = h->tb[slot].ke_base + (long long)local * arena_doubles(slot);
+    const long long base = h->tb[slot].ke_off[local];
     tr = false;
     if (slot == 0) return base + shell_block_offset(la, b, tr);
     if (slot == 1) return base + beam_block_offset(la, b, tr);
@@ -212,6 +256,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
     if (m->n_nodes <= 0 || m->n_elements < 0 || !m->ref_coordinates) return fail(GFA_EINVAL, "gfa_create: empty model");
     if (m->part_world < 1 || m->part_rank < 0 || m->part_rank >= m->part_world)
         return fail(GFA_EINVAL, "gfa_create: bad partition rank %d of %d", m->part_rank, m->part_world);
+    if (m->part_world > 64) return fail(GFA_EUNSUPPORTED, "gfa_create: %d ranks; the interface bookkeeping holds rank sets in 64 bits", m->part_world);
     CUDA_TRY(cudaSetDevice(device));
     int cfg = configure_kernels();
     if (cfg == 0) cfg = configure_dynamics();
@@ -376,12 +421,15 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
             }
         }
         if (pe > 0x7fffffffLL) FAIL_FREE(GFA_EUNSUPPORTED, "element force arena exceeds 2^31 entries");
-        if (e == cudaSuccess) e = h->d_Ke.alloc((size_t)ke);
+        // the element arena is sized by gfa_set_dofs (classic: every element; ring: ring slots + pinned elements)
         if (e == cudaSuccess) e = h->d_Pe.alloc((size_t)pe);
         if (e == cudaSuccess) e = h->tb[0].d_geo.alloc(10 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = h->tb[0].d_shp.alloc(21 * 3 * h->tb[0].elems.size());
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream_if, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream_sc, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_ctl, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_scattered, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_iface, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_unpacked, cudaEventDisableTiming);
         for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&h->ev[i]);
@@ -403,6 +451,9 @@ int gfa_destroy(gfa_t* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream_if) cudaStreamSynchronize(h->stream_if);
+    if (h->stream_sc) { cudaStreamSynchronize(h->stream_sc); cudaStreamDestroy(h->stream_sc); }
+    if (h->ev_ctl) cudaEventDestroy(h->ev_ctl);
+    if (h->ev_scattered) cudaEventDestroy(h->ev_scattered);
     for (int i = 0; i < 4; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_iface) cudaEventDestroy(h->ev_iface);
     if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
@@ -446,6 +497,30 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     const std::vector<int>& gls = h->gls;
     for (size_t i = 0; i < gls.size(); i++)
         if (gls[i] > n_free || -gls[i] > n_fixed) return fail(GFA_EINVAL, "GLs[%zu] = %d outside [-%d, %d]", i, gls[i], n_fixed, n_free);
+    {   // The pattern builder and the slot map rely on the reference's node-major numbering (Solution.cpp:53-72): free ids
+        // ascend with (node, DOF) and the free DOFs of one 3-DOF group are consecutive ids, so that a group's rows are
+        // consecutive CSR rows and columns ascend with the group-node id.  Anything else is refused, not mis-assembled.
+        int last = 0;
+        std::vector<unsigned char> seen_fixed((size_t)n_fixed, 0);
+        for (size_t gn = 0; gn < gls.size() / 3; gn++) {
+            int prev = 0;
+            for (int k = 0; k < 3; k++) {
+                const int g = gls[3 * gn + k];
+                if (g > 0) {
+                    if (g <= last) return fail(GFA_EUNSUPPORTED, "GLs are not in the reference's node-major ascending order at node %zu (free id %d after %d)", gn / 2 + 1, g, last);
+                    if (prev && g != prev + 1) return fail(GFA_EUNSUPPORTED, "free ids %d and %d of node %zu are not consecutive (another DOF is numbered in between)", prev, g, gn / 2 + 1);
+                    last = g; prev = g;
+                } else if (g < 0) {
+                    if (seen_fixed[(size_t)(-g - 1)]) return fail(GFA_EINVAL, "fixed id %d appears twice in GLs", g);
+                    seen_fixed[(size_t)(-g - 1)] = 1;
+                }
+            }
+        }
+    }
+    // keep the arguments: a handle that has to leave ring mode replays the call (from copies, see leave_ring_mode)
+    h->ex_mat.assign(ex_mat, ex_mat + (n_extra > 0 ? n_extra : 0));
+    h->ex_rows.assign(ex_rows, ex_rows + (n_extra > 0 ? n_extra : 0));
+    h->ex_cols.assign(ex_cols, ex_cols + (n_extra > 0 ? n_extra : 0));
 
     // ---- group-node adjacency over ALL elements (every rank builds the same pattern)
     const size_t n_gn_all = (size_t)h->n_nodes * 2;
@@ -495,6 +570,144 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         if (h->world == 1) { need[gn] = 1; continue; }
         for (int p = gptr[gn]; p < gptr[gn + 1]; p++) if (el_rank[ginc_e[p]] == h->rank) { need[gn] = 1; break; }
     }
+
+    // ---- arena placement -------------------------------------------------------------------------
+    // classic: every local element owns a region of one big arena (written by the evaluation kernel, read back
+    // by the scatter kernel through DRAM).  ring: elements are evaluated chunk by chunk into an L2-resident ring
+    // that the scatter role of the fused kernel drains behind the evaluation (gfa_device.h: FusedArgs).  Elements
+    // whose blocks must outlive their chunk are PINNED to regions of their own behind the ring and evaluated
+    // first: those that touch a fixed DOF (explicit AB/BA/BB gather lists), a partition interface (their rows
+    // are scattered, packed and sent first) or a group-node whose incident elements lie more than the ring's
+    // reach apart in evaluation order.
+    std::vector<unsigned char> gn_iface(n_gn_all, 0);
+    if (h->world > 1)
+        for (size_t gn = 0; gn < n_gn_all; gn++) {
+            unsigned long long rs = 0;
+            for (int p = gptr[gn]; p < gptr[gn + 1]; p++) rs |= 1ULL << el_rank[ginc_e[p]];
+            gn_iface[gn] = __builtin_popcountll(rs) > 1;
+        }
+    long long classic_doubles = 0;
+    for (int s = 0; s < 3; s++) classic_doubles += (long long)h->tb[s].elems.size() * arena_doubles(s);
+    {
+        const char* env = getenv("GFA_RING");
+        const char* ekb = getenv("GFA_RING_CHUNK_KB");
+        const char* ek = getenv("GFA_RING_CHUNKS");
+        const long long chunk_bytes = (ekb && atoll(ekb) > 0 ? atoll(ekb) : 7168) * 1024LL;
+        int K = ek && atoi(ek) >= 3 ? atoi(ek) : 9;
+        // 1: ring pipeline, 2: ring pipeline when the arena exceeds the ring; default 0 -- measured on B200 the thin
+        // scatter kernel cannot keep up beside the register-hungry evaluation kernel (profiles/r02_notes.md), so the
+        // classic two-kernel path stays the default until the evaluation kernel leaves more of the SM free
+        const int mode = env ? atoi(env) : 0;
+        bool ring = !h->force_classic && mode != 0 && (mode == 1 || classic_doubles * 8 > (long long)K * chunk_bytes);
+        h->ring_note = h->force_classic ? "classic: dynamics / explicit request" : mode == 0 ? "classic (GFA_RING=1 selects the ring pipeline)" : "classic: the element arena fits the ring";
+        std::vector<std::vector<unsigned char> > pinned(3);
+        int ce[3] = { 1, 1, 1 };
+        for (int s = 0; s < 3; s++) {
+            const int epw = s == 0 ? 8 : s == 1 ? 16 : 4;          // batch sizes of the evaluation kernels
+            long long n = chunk_bytes / (8LL * arena_doubles(s)) / epw * epw;
+            ce[s] = (int)std::max<long long>(n, epw);
+            pinned[s].assign(h->tb[s].elems.size(), 0);
+        }
+        auto chunk_of = [&](const int* c0, int s, long long pos) { return c0[s] + (int)(pos / ce[s]); };
+        if (ring) {
+            int c0p[3]; long long acc = 0;                          // provisional chunks over all local elements
+            for (int s = 0; s < 3; s++) { c0p[s] = (int)acc; acc += ((long long)h->tb[s].elems.size() + ce[s] - 1) / ce[s]; }
+            const int reach = std::max(1, K / 3);
+            for (size_t gn = 0; gn < n_gn_all; gn++) {
+                int lo = 0x7fffffff, hi = -1; bool fixed = false;
+                for (int k = 0; k < 3; k++) fixed |= gls[3 * gn + k] < 0;
+                for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                    const int e = ginc_e[p], s = h->el_owner_slot[e];
+                    if (s < 0) continue;
+                    const int c = chunk_of(c0p, s, h->el_local[e]);
+                    lo = std::min(lo, c); hi = std::max(hi, c);
+                }
+                if (hi < 0) continue;
+                if (fixed || gn_iface[gn] || hi - lo > reach)
+                    for (int p = gptr[gn]; p < gptr[gn + 1]; p++) { const int e = ginc_e[p], s = h->el_owner_slot[e]; if (s >= 0) pinned[s][h->el_local[e]] = 1; }
+            }
+        }
+        // lists, chunks, per-element offsets
+        int c0[3] = { 0, 0, 0 }; long long tot_chunks = 0, chunk_doubles = 0, n_pinned = 0, n_ring = 0;
+        for (int s = 0; s < 3; s++) {
+            TypeBlock& t = h->tb[s];
+            t.ring_list.clear(); t.pin_list.clear();
+            for (size_t l = 0; l < t.elems.size(); l++) (ring && !pinned[s][l] ? t.ring_list : t.pin_list).push_back((int)l);
+            if (!ring) t.pin_list.clear();
+            t.chunk_el = ce[s]; t.chunk0 = c0[s] = (int)tot_chunks;
+            t.n_chunks = (int)(((long long)t.ring_list.size() + ce[s] - 1) / ce[s]);
+            tot_chunks += t.n_chunks;
+            if (!t.ring_list.empty()) chunk_doubles = std::max(chunk_doubles, (long long)ce[s] * arena_doubles(s));
+            n_pinned += (long long)t.pin_list.size(); n_ring += (long long)t.ring_list.size();
+        }
+        int span = 0;
+        if (ring) {
+            std::vector<int> fc[3];                                  // final chunk of a local element, -1 = pinned
+            for (int s = 0; s < 3; s++) {
+                fc[s].assign(h->tb[s].elems.size(), -1);
+                for (size_t k = 0; k < h->tb[s].ring_list.size(); k++) fc[s][h->tb[s].ring_list[k]] = chunk_of(c0, s, (long long)k);
+            }
+            for (size_t gn = 0; gn < n_gn_all; gn++) {
+                int lo = 0x7fffffff, hi = -1;
+                for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                    const int e = ginc_e[p], s = h->el_owner_slot[e];
+                    if (s < 0 || fc[s][h->el_local[e]] < 0) continue;
+                    lo = std::min(lo, fc[s][h->el_local[e]]); hi = std::max(hi, fc[s][h->el_local[e]]);
+                }
+                if (hi >= 0) span = std::max(span, hi - lo);
+            }
+            if (n_ring == 0) { ring = false; h->ring_note = "classic: every element is pinned (fixed DOFs / interfaces / numbering without locality)"; }
+            else if (span > K - 2) { ring = false; h->ring_note = "classic: patches reach further than the ring"; }
+        }
+        h->ring = ring;
+        long long total = 0;
+        if (ring) {
+            h->ring_chunks = K; h->ring_span = span; h->total_chunks = (int)tot_chunks; h->chunk_doubles = chunk_doubles;
+            h->ring_doubles = (long long)K * chunk_doubles;
+            total = h->ring_doubles;
+            for (int s = 0; s < 3; s++) {
+                TypeBlock& t = h->tb[s];
+                t.pin_base = total; total += (long long)t.pin_list.size() * arena_doubles(s);
+                t.ke_off.assign(t.elems.size(), 0);
+                for (size_t k = 0; k < t.ring_list.size(); k++)
+                    t.ke_off[t.ring_list[k]] = (long long)((c0[s] + (int)(k / ce[s])) % K) * chunk_doubles + (long long)(k % ce[s]) * arena_doubles(s);
+                for (size_t k = 0; k < t.pin_list.size(); k++) t.ke_off[t.pin_list[k]] = t.pin_base + (long long)k * arena_doubles(s);
+            }
+            char buf[256];
+            snprintf(buf, sizeof(buf), "ring: %d chunks of %.1f MB (%lld total), span %d, %lld elements through the ring, %lld pinned",
+                     K, chunk_doubles * 8 / 1048576.0, tot_chunks, span, n_ring, n_pinned);
+            h->ring_note = buf;
+        } else {
+            h->ring_chunks = 0; h->ring_span = 0; h->total_chunks = 0; h->chunk_doubles = 0; h->ring_doubles = 0;
+            for (int s = 0; s < 3; s++) {
+                TypeBlock& t = h->tb[s];
+                t.ring_list.clear(); t.pin_list.clear(); t.n_chunks = 0; t.pin_base = 0;
+                t.ke_off.resize(t.elems.size());
+                for (size_t l = 0; l < t.elems.size(); l++) t.ke_off[l] = t.ke_base + (long long)l * arena_doubles(s);
+            }
+            total = classic_doubles;
+        }
+        if (total >= (1LL << 32)) return fail(GFA_EUNSUPPORTED, "element arena of %lld doubles is too large for the 32-bit block offsets of the slot map%s", total, ring ? "" : " (classic path)");
+        if (h->d_Ke.n != (size_t)total + 2) {
+            cudaError_t e = h->d_Ke.alloc((size_t)total + 2);      // the scatter kernel stages whole 16-byte pieces: one past the last block
+            if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? GFA_ENOMEM : GFA_ECUDA, "element arena: %s", cudaGetErrorString(e));
+        }
+    }
+    // ready chunk of a group-node: the last chunk that holds one of its incident ring elements (-1: pinned sources only)
+    auto ready_chunk = [&](size_t gn) {
+        int rc = -1;
+        if (!h->ring) return rc;
+        for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+            const int e = ginc_e[p], s = h->el_owner_slot[e];
+            if (s < 0) continue;
+            const TypeBlock& t = h->tb[s];
+            const long long off = t.ke_off[h->el_local[e]];
+            if (off >= h->ring_doubles) continue;            // pinned
+            const int* pos = std::lower_bound(t.ring_list.data(), t.ring_list.data() + t.ring_list.size(), h->el_local[e]);
+            rc = std::max(rc, t.chunk0 + (int)((pos - t.ring_list.data()) / t.chunk_el));
+        }
+        return rc;
+    };
 
     // ---- neighbour lists (sorted group-node ids), over ALL incident elements so
     //      that a stored row carries its complete global column set ------------
@@ -694,6 +907,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<int> touched_gn;                     // group-nodes with a local incidence
     std::vector<long long> touched_key;              // position of the first local incident element (locality key)
     std::vector<char> touched_iface;                 // shared with another rank: scattered first (see gfa_assemble)
+    std::vector<int> touched_rc;                     // ring mode: chunk after which the group-node's patches are complete
     for (size_t gn = 0; gn < n_gn_all; gn++) {
         if (gptr[gn] == gptr[gn + 1]) continue;
         int owner = 0; bool touched = h->world == 1; unsigned long long rank_set = 0;
@@ -733,6 +947,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         touched_gn.push_back((int)gn);
         touched_key.push_back(key);
         touched_iface.push_back(h->world > 1 && __builtin_popcountll(rank_set) > 1 ? 1 : 0);
+        touched_rc.push_back(ready_chunk(gn));
     }
     std::sort(h->owned_rows.begin(), h->owned_rows.end());
     {   // patches are processed in the order of their group-node's first incident element, so that the
@@ -742,13 +957,15 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         for (size_t i = 0; i < order.size(); i++) order[i] = i;
         // group-nodes on a partition interface come first: their rows are complete (and can be packed and sent)
         // while the interior rows are still being scattered
+        // (ring mode: then by ready chunk -- the fused kernel scatters a chunk's group-nodes as soon as it is evaluated)
         std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
             if (touched_iface[x] != touched_iface[y]) return touched_iface[x] > touched_iface[y];
+            if (touched_rc[x] != touched_rc[y]) return touched_rc[x] < touched_rc[y];
             return touched_key[x] < touched_key[y];
         });
-        std::vector<int> sorted(touched_gn.size());
-        for (size_t i = 0; i < order.size(); i++) sorted[i] = touched_gn[order[i]];
-        touched_gn.swap(sorted);
+        std::vector<int> sorted(touched_gn.size()), sorted_rc(touched_gn.size());
+        for (size_t i = 0; i < order.size(); i++) { sorted[i] = touched_gn[order[i]]; sorted_rc[i] = touched_rc[order[i]]; }
+        touched_gn.swap(sorted); touched_rc.swap(sorted_rc);
     }
     size_t n_iface_touched = 0;
     for (char c : touched_iface) n_iface_touched += c ? 1 : 0;
@@ -761,9 +978,12 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<std::vector<unsigned long long> > run_src;   // scratch: sources per patch of the current group-node
     std::vector<GnRec> gn_recs;
     h->n_iface_runs = 0; h->n_iface_gn = 0;
+    std::vector<long long> chunk_run_ptr((size_t)h->total_chunks + 1, 0);
+    int crp_filled = 0;                              // chunk_run_ptr[0 .. crp_filled) are final
     for (size_t ti_ = 0; ti_ < touched_gn.size(); ti_++) {
         if (ti_ == n_iface_touched) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)gn_recs.size(); }
         const size_t gn = (size_t)touched_gn[ti_];
+        if (h->ring) for (; crp_filled <= touched_rc[ti_]; crp_filled++) chunk_run_ptr[crp_filled] = (long long)runs.size();
         const int first_inc = (int)incs.size();
         const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
         const int n_runs = (int)(nb1 - nb0);
@@ -824,6 +1044,76 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     }
     (void)fix_mask;
     if (n_iface_touched == touched_gn.size()) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)gn_recs.size(); }
+    for (; crp_filled <= h->total_chunks; crp_filled++) chunk_run_ptr[crp_filled] = (long long)runs.size();
+    {   // Solution::Clear zeroes the whole vectors (Solution.cpp:833-848); entries no local element writes -- DOFs beyond
+        // the node table, rows of other ranks -- are zeroed at the head of every assembly when there are any
+        long long covered = 0;
+        for (const GnRec& r : gn_recs) for (int k = 0; k < 3; k++) covered += r.gl[k] != 0;
+        h->n_vec_untouched = (long long)n_free + n_fixed - covered;
+    }
+    h->n_pre_runs = h->ring ? chunk_run_ptr[0] : (long long)runs.size();
+    if (h->ring) {
+        std::vector<int> chunk_tile_ptr((size_t)h->total_chunks + 1, 0);
+        for (int c = 0; c < h->total_chunks; c++) {
+            const long long tiles = (chunk_run_ptr[c + 1] - chunk_run_ptr[c] + FUSED_TILE_PATCHES - 1) / FUSED_TILE_PATCHES;
+            if (chunk_tile_ptr[c] + tiles > 0x7fffffffLL) return fail(GFA_EUNSUPPORTED, "too many scatter tiles");
+            chunk_tile_ptr[c + 1] = chunk_tile_ptr[c] + (int)tiles;
+        }
+        CUDA_TRY(h->d_chunk_run_ptr.upload(chunk_run_ptr));
+        CUDA_TRY(h->d_chunk_tile_ptr.upload(chunk_tile_ptr));
+        std::vector<int> chunk_batches((size_t)h->total_chunks, 0);
+        for (int sl = 0; sl < 3; sl++) {
+            const TypeBlock& t = h->tb[sl];
+            const int epw = sl == 0 ? 8 : sl == 1 ? 16 : 4;
+            for (int c = 0; c < t.n_chunks; c++) {
+                const long long el = std::min<long long>(t.chunk_el, (long long)t.ring_list.size() - (long long)c * t.chunk_el);
+                chunk_batches[(size_t)t.chunk0 + c] = (int)((el + epw - 1) / epw);
+            }
+        }
+        CUDA_TRY(h->d_chunk_batches.upload(chunk_batches));
+        CUDA_TRY(h->d_ctl.alloc((size_t)CTL_HDR + 3 * (size_t)h->total_chunks + 8));
+        for (int sl = 0; sl < 3; sl++) {
+            CUDA_TRY(h->tb[sl].d_ring_list.upload(h->tb[sl].ring_list));
+            CUDA_TRY(h->tb[sl].d_pin_list.upload(h->tb[sl].pin_list));
+        }
+        if (h->d_scratch_ke.n == 0) { CUDA_TRY(h->d_scratch_ke.alloc(SHELL_ARENA)); CUDA_TRY(h->d_one.alloc(1)); }
+        for (int sl = 0; sl < 3; sl++) {
+            const char* ew = getenv("GFA_FUSED_EVAL_WARPS");
+            int nb = fused_buffers(sl);
+            if (ew && atoi(ew) >= 1 && atoi(ew) <= fused_buffers(sl)) nb = atoi(ew);
+            h->fused_eval_warps[sl] = nb;
+        }
+        if (const char* tg = getenv("GFA_FUSED_TILE_GROUP")) if (atoi(tg) >= 1 && atoi(tg) <= 64) h->fused_tile_group = atoi(tg);
+        if (const char* sc = getenv("GFA_FUSED_SCATTER_CTAS")) if (atoi(sc) >= 1 && atoi(sc) <= 8) h->fused_scatter_ctas = atoi(sc);
+        if (const char* tm = getenv("GFA_FUSED_TIMEOUT_MS")) if (atoll(tm) > 0) h->fused_timeout_ns = 1000000ULL * (unsigned long long)atoll(tm);
+        // keep the ring in L2: persisting access-policy window over it on the library's stream
+        const char* pe = getenv("GFA_RING_PERSIST");
+        if (!pe || atoi(pe) != 0) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+            const size_t ring_bytes = (size_t)h->ring_doubles * sizeof(double);
+            if (max_persist > 0 && max_window > 0) {
+                const size_t carve = std::min(ring_bytes, (size_t)max_persist);
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+                cudaStreamAttrValue av;
+                std::memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = h->d_Ke.p;
+                av.accessPolicyWindow.num_bytes = std::min(ring_bytes, (size_t)max_window);
+                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+                char buf[96];
+                snprintf(buf, sizeof(buf), "; L2 window %.0f MB persisting (carve-out %.0f MB)", av.accessPolicyWindow.num_bytes / 1048576.0, carve / 1048576.0);
+                h->ring_note += buf;
+            }
+        }
+    } else {
+        cudaStreamAttrValue av;
+        std::memset(&av, 0, sizeof(av));
+        if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
 
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
@@ -938,6 +1228,37 @@ DynArgs dyn_args(gfa_t* h, int slot, const gfa_dynamic_t* d) {
     return a;
 }
 
+// A handle in ring mode keeps no complete element arena; paths that need one (the Newmark kernels work on it in
+// place) rebuild the slot map for the classic two-kernel path, once.
+int leave_ring_mode(gfa_t* h) {
+    if (!h->ring) return GFA_OK;
+    h->force_classic = true;
+    const std::vector<int> gl = h->gls, em = h->ex_mat, er = h->ex_rows, ec = h->ex_cols;
+    return gfa_set_dofs(h, gl.data(), h->n_free, h->n_fixed, (int64_t)em.size(), em.data(), er.data(), ec.data());
+}
+
+// the fused kernel's watchdog: a warp that waited longer than the time-out raised CTL_ABORT and every warp left
+int check_abort(gfa_t* h) {
+    if (!h->abort_check_pending) return GFA_OK;
+    h->abort_check_pending = false;
+    unsigned flag = 0;
+    CUDA_TRY(cudaMemcpy(&flag, h->d_ctl.p + CTL_ABORT, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag && getenv("GFA_FUSED_DEBUG")) {
+        std::vector<unsigned> c(h->d_ctl.n);
+        cudaMemcpy(c.data(), h->d_ctl.p, c.size() * sizeof(unsigned), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[gfa] watchdog: batches claimed %u %u %u, chunks %d; first to give up: %s waiting on chunk %u after %u us\n", c[CTL_BATCH], c[CTL_BATCH + 1], c[CTL_BATCH + 2], h->total_chunks, (c[0] & 15) == 1 ? "evaluation warp" : "scatter warp", c[0] >> 4, c[5]);
+        { const unsigned* g = c.data() + CTL_HDR + 3 * h->total_chunks;
+          fprintf(stderr, "[gfa]  giving-up evaluation warp: saw %u, wanted %u, s_upto %u, need %u, batch %u, chunk0 %u, ring_chunks %u\n", g[1], g[2], g[3], g[4], g[5], g[6], g[7]); }
+        std::vector<int> tp(h->d_chunk_tile_ptr.n), cb(h->d_chunk_batches.n);
+        cudaMemcpy(tp.data(), h->d_chunk_tile_ptr.p, tp.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(cb.data(), h->d_chunk_batches.p, cb.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        for (int k = 0; k < h->total_chunks && k < 14; k++)
+            fprintf(stderr, "[gfa]  chunk %d: evaluated %u of %d, scattered %u of %d, tiles claimed %u\n", k, c[CTL_HDR + k], cb[k], c[CTL_HDR + h->total_chunks + k], tp[k + 1] - tp[k], c[CTL_HDR + 2 * h->total_chunks + k]);
+    }
+    if (flag) { h->assembled = false; return fail(GFA_ECUDA, "fused assembly kernel gave up after waiting %.1f s for a chunk (watchdog); results are incomplete", h->fused_timeout_ns * 1e-9); }
+    return GFA_OK;
+}
+
 int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool wait = true) {
     if (!h || !st) return fail(GFA_EINVAL, "gfa_assemble: null argument");
     if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_assemble before gfa_set_dofs");
@@ -962,48 +1283,110 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
             }
         }
     }
+    if (dyn && h->ring) {       // the mass / damping kernels fold their terms into a complete arena in place
+        int rc = leave_ring_mode(h);
+        if (rc != GFA_OK) return rc;
+    }
     cudaStream_t s = h->stream;
     const size_t nd = 6 * (size_t)h->n_nodes * sizeof(double);
     int launches = 0;
+    h->last_gfac = st->gravity_factor;
     CUDA_TRY(cudaEventRecord(h->ev[0], s));
     if (st->displacements)       // NULL: keep the device copy (gfa_update_displacements)
         CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
                                  st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (h->n_vec_untouched > 0)  // Solution::Clear for the vector entries no element writes
+        CUDA_TRY(cudaMemsetAsync(h->d_arena.p + h->vec_off[GFA_P_A], 0, (size_t)(h->arena_size - h->vec_off[GFA_P_A]) * sizeof(double), s));
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
-    // MountLocal + MountElementLoads: one evaluation launch per element type
-    for (int slot = 0; slot < 3; slot++) {
-        if (h->tb[slot].elems.empty()) continue;
-        const EvalArgs ea = eval_args(h, slot, st->gravity_factor);
-        if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
-        launches++;
-        if (dyn) {      // MountMass + MountDamping + MountDyn folded into the element blocks before the scatter
-            const DynArgs da = dyn_args(h, slot, dyn);
-            if (slot == 0) launch_shell_dynamics(ea, da, s); else launch_beam_dynamics(ea, da, s);
-            launches += 2;
-        }
-    }
-    CUDA_TRY(cudaEventRecord(h->ev[2], s));
-    // MountGlobal + MountSparse
     ScatterArgs sa;
     sa.n_runs = h->n_runs; sa.runs = h->d_runs.p; sa.ovf = h->d_ovf.p;
     sa.n_gn = h->n_gn_local; sa.gn = h->d_gn.p; sa.inc = h->d_inc.p; sa.Ke = h->d_Ke.p; sa.Pe = h->d_Pe.p;
     sa.valAA = h->d_arena.p + h->arena_off[GFA_AA];
     sa.PA = h->d_arena.p + h->vec_off[GFA_P_A]; sa.IA = h->d_arena.p + h->vec_off[GFA_I_A]; sa.PB = h->d_arena.p + h->vec_off[GFA_P_B];
-    // rows of partition interfaces first (n_iface_* are zero with one rank), then the fixed-DOF entries: after
-    // ev_iface everything the interface exchange packs is final, and the interior rows follow behind it
-    ScatterArgs si = sa;
-    si.n_runs = h->n_iface_runs; si.n_gn = h->n_iface_gn;
-    launches += launch_scatter(si, s);
-    if (h->n_gdest > 0) {
-        GatherArgs g;
-        g.n_dest = h->n_gdest; g.seg = h->d_gseg.p; g.src = h->d_gsrc.p; g.dest = h->d_gdest.p;
-        g.Ke = h->d_Ke.p; g.vals = h->d_arena.p;
-        launch_gather(g, s); launches++;
+    GatherArgs g;
+    g.n_dest = h->n_gdest; g.seg = h->d_gseg.p; g.src = h->d_gsrc.p; g.dest = h->d_gdest.p;
+    g.Ke = h->d_Ke.p; g.vals = h->d_arena.p;
+    if (!h->ring) {
+        // MountLocal + MountElementLoads: one evaluation launch per element type
+        for (int slot = 0; slot < 3; slot++) {
+            if (h->tb[slot].elems.empty()) continue;
+            const EvalArgs ea = eval_args(h, slot, st->gravity_factor);
+            if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
+            launches++;
+            if (dyn) {      // MountMass + MountDamping + MountDyn folded into the element blocks before the scatter
+                const DynArgs da = dyn_args(h, slot, dyn);
+                if (slot == 0) launch_shell_dynamics(ea, da, s); else launch_beam_dynamics(ea, da, s);
+                launches += 2;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(h->ev[2], s));
+        // MountGlobal + MountSparse: rows of partition interfaces first (n_iface_* are zero with one rank), then the
+        // fixed-DOF entries: after ev_iface everything the interface exchange packs is final, and the interior rows
+        // follow behind it
+        ScatterArgs si = sa;
+        si.n_runs = h->n_iface_runs; si.n_gn = h->n_iface_gn;
+        launches += launch_scatter(si, s);
+        if (h->n_gdest > 0) { launch_gather(g, s); launches++; }
+        CUDA_TRY(cudaEventRecord(h->ev_iface, s));
+        sa.runs += h->n_iface_runs; sa.n_runs -= h->n_iface_runs;
+        sa.gn += h->n_iface_gn; sa.n_gn -= h->n_iface_gn;
+        launches += launch_scatter(sa, s);
+    } else {
+        // ---- ring pipeline.  Pre-pass: the pinned elements (fixed DOFs, partition interfaces, far-reaching
+        // group-nodes) into their own regions, then everything only they feed -- interface rows and vectors
+        // first, the AB / BA / BB entries, ev_iface, the remaining pinned-only patches.
+        for (int slot = 0; slot < 3; slot++) {
+            if (h->tb[slot].pin_list.empty()) continue;
+            const EvalArgs ea = eval_args(h, slot, st->gravity_factor, PASS_PINNED);
+            if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
+            launches++;
+        }
+        ScatterArgs si = sa;
+        si.n_runs = h->n_iface_runs; si.n_gn = h->n_iface_gn;
+        launches += launch_scatter(si, s);
+        if (h->n_gdest > 0) { launch_gather(g, s); launches++; }
+        CUDA_TRY(cudaEventRecord(h->ev_iface, s));
+        ScatterArgs sp = sa;
+        sp.runs += h->n_iface_runs; sp.n_runs = h->n_pre_runs - h->n_iface_runs; sp.n_gn = 0;
+        launches += launch_scatter(sp, s);
+        CUDA_TRY(cudaEventRecord(h->ev[2], s));
+        // ---- ring pipeline: the scatter kernel on its own stream, the evaluation kernels (one per element type)
+        // beside it; the two talk through the control block
+        CUDA_TRY(cudaMemsetAsync(h->d_ctl.p, 0, h->d_ctl.n * sizeof(unsigned), s));
+        CUDA_TRY(cudaEventRecord(h->ev_ctl, s));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream_sc, h->ev_ctl, 0));
+        FusedArgs f;
+        f.total_chunks = h->total_chunks; f.span = h->ring_span; f.tile_group = h->fused_tile_group; f.scatter_ctas = h->fused_scatter_ctas;
+        f.sc = sa;
+        f.chunk_run_ptr = h->d_chunk_run_ptr.p; f.chunk_tile_ptr = h->d_chunk_tile_ptr.p; f.chunk_batches = h->d_chunk_batches.p;
+        f.ctl = h->d_ctl.p; f.timeout_ns = h->fused_timeout_ns;
+        // the evaluation kernel goes first: it configures every SM for the large shared-memory carve-out, under
+        // which the scatter CTA (no shared memory, 32 registers a thread) still fits beside it -- an SM that
+        // started with the scatter kernel's small carve-out could not take the evaluation CTA until it drained
+        bool scatter_launched = false;
+        for (int slot = 0; slot < 3; slot++) {
+            const TypeBlock& t = h->tb[slot];
+            if (t.ring_list.empty()) continue;
+            f.ev = eval_args(h, slot, st->gravity_factor, PASS_RING);
+            f.n_buf = h->fused_eval_warps[slot]; f.type_slot = slot;
+            int e = launch_fused_eval(f, s);
+            if (e != 0) return fail(GFA_ECUDA, "evaluation kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+            launches++;
+            if (!scatter_launched) {
+                e = launch_fused_scatter(f, h->stream_sc);
+                if (e != 0) return fail(GFA_ECUDA, "scatter kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+                launches++;
+                CUDA_TRY(cudaEventRecord(h->ev_scattered, h->stream_sc));
+                scatter_launched = true;
+            }
+        }
+        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_scattered, 0));
+        // residual vectors of the remaining group-nodes (the element force arena holds every element)
+        ScatterArgs sv = sa;
+        sv.gn += h->n_iface_gn; sv.n_gn -= h->n_iface_gn;
+        if (sv.n_gn > 0) { launch_vectors(sv, s); launches++; }
+        h->abort_check_pending = true;
     }
-    CUDA_TRY(cudaEventRecord(h->ev_iface, s));
-    sa.runs += h->n_iface_runs; sa.n_runs -= h->n_iface_runs;
-    sa.gn += h->n_iface_gn; sa.n_gn -= h->n_iface_gn;
-    launches += launch_scatter(sa, s);
     CUDA_TRY(cudaEventRecord(h->ev[3], s));
     CUDA_TRY(cudaGetLastError());
     h->last_launches = launches;
@@ -1012,6 +1395,7 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
     if (wait) {
         CUDA_TRY(cudaStreamSynchronize(s));
         resolve_timing(h);
+        return check_abort(h);
     }
     return GFA_OK;
 }
@@ -1155,6 +1539,7 @@ int gfa_csr_values(gfa_t* h, int which, double* out) {
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_csr_values before gfa_assemble");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
+    if (int rc = check_abort(h)) return rc;
     const size_t n = h->csr[which].inner.size();
     if (n) CUDA_TRY(cudaMemcpy(out, h->d_arena.p + h->arena_off[which], n * sizeof(double), cudaMemcpyDeviceToHost));
     return GFA_OK;
@@ -1170,6 +1555,7 @@ int gfa_vector(gfa_t* h, int wv, double* out) {
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_vector before gfa_assemble");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
+    if (int rc = check_abort(h)) return rc;
     const size_t n = wv == GFA_P_B ? h->n_fixed : h->n_free;
     if (n) CUDA_TRY(cudaMemcpy(out, h->d_arena.p + h->vec_off[wv], n * sizeof(double), cudaMemcpyDeviceToHost));
     return GFA_OK;
@@ -1192,7 +1578,18 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     if (K) {
         const int nd = arena_doubles(s), local = h->el_local[e];
         std::vector<double> blk((size_t)nd);
-        CUDA_TRY(cudaMemcpy(blk.data(), h->d_Ke.p + h->tb[s].ke_base + (size_t)local * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+        const double* src = h->d_Ke.p + h->tb[s].ke_off[local];
+        if (h->ring) {
+            // the ring keeps only the last chunks: evaluate this one element again, into a scratch region
+            CUDA_TRY(cudaMemcpyAsync(h->d_one.p, &local, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            EvalArgs ea = eval_args(h, s, h->last_gfac);
+            ea.elist = h->d_one.p; ea.e_begin = 0; ea.e_end = 1; ea.Ke = h->d_scratch_ke.p;
+            if (s == 0) launch_shell_eval(ea, h->stream); else if (s == 1) launch_beam_eval(ea, h->stream); else launch_solid_eval(ea, h->stream);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            src = h->d_scratch_ke.p;
+        }
+        CUDA_TRY(cudaMemcpy(blk.data(), src, sizeof(double) * nd, cudaMemcpyDeviceToHost));
         // device layout is block-wise (and upper-triangular for Shell_1); hand back plain row-major
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
@@ -1360,7 +1757,13 @@ int gfa_last_timing(gfa_t* h, double* ms4) {
     if (!h || !ms4) return fail(GFA_EINVAL, "gfa_last_timing: bad argument");
     resolve_timing(h);
     for (int i = 0; i < 4; i++) ms4[i] = h->last_ms[i];
-    return GFA_OK;
+    return check_abort(h);
+}
+int gfa_pipeline_info(gfa_t* h, char* buf, int32_t capacity) {
+    if (!h || !buf || capacity < 1) return fail(GFA_EINVAL, "gfa_pipeline_info: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_pipeline_info before gfa_set_dofs");
+    snprintf(buf, (size_t)capacity, "%s", h->ring_note.c_str());
+    return h->ring ? 1 : 0;
 }
 int gfa_last_launch_count(gfa_t* h) { return h ? h->last_launches : 0; }
 

@@ -2,6 +2,12 @@
 #pragma once
 #include <cstdint>
 
+#if defined(__CUDACC__)
+#define GFA_HD_INLINE __host__ __device__ __forceinline__
+#else
+#define GFA_HD_INLINE inline
+#endif
+
 namespace gfa {
 
 // ---- element evaluation -------------------------------------------------
@@ -27,7 +33,24 @@ struct EvalArgs {
                              // Shell_1: SHELL_ARENA doubles per element (see shell_block_offset()).
     double* Pe;              // [n_el * ndof]  P_loading = Fint - Fext
     double gx, gy, gz;       // Environment::G * l_factor (zero when no gravity)
+    // Evaluation order and arena placement.  The launch evaluates list positions k in [e_begin, e_end);
+    // position k is element elist[k] (identity when elist == nullptr).  Its blocks go to arena slot k
+    // (classic: the arena holds every element) or, in ring mode (ring_chunks > 0), into the slot of its
+    // chunk inside an L2-resident ring of ring_chunks x chunk_doubles doubles that the scatter role of the
+    // fused kernel drains behind the evaluation (see FusedArgs).
+    const int* elist;
+    int ring_chunks;         // 0: classic arena
+    int chunk_el;            // elements per chunk (multiple of the type's batch size)
+    int chunk0;              // global index of this type's first chunk (ring slot = (chunk0 + k / chunk_el) % ring_chunks)
+    long long chunk_doubles; // doubles per ring slot
 };
+GFA_HD_INLINE int eval_element(const EvalArgs& A, int k) { return A.elist ? A.elist[k] : k; }
+// first arena double of list position k; `arena` = doubles per element of the type
+GFA_HD_INLINE double* eval_ke(const EvalArgs& A, int k, int arena) {
+    if (A.ring_chunks == 0) return A.Ke + (size_t)k * arena;
+    const int c = k / A.chunk_el;
+    return A.Ke + (size_t)((A.chunk0 + c) % A.ring_chunks) * (size_t)A.chunk_doubles + (size_t)(k - c * A.chunk_el) * arena;
+}
 
 constexpr int SHELL_PROP_STRIDE = 5;   // lambda, mu, thickness, stiff_drill, rho
 constexpr int BEAM_PROP_STRIDE = 51;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A, strain-energy switch (1 Beam_1, 0 Pipe_1),
@@ -131,6 +154,38 @@ struct ScatterArgs {
     double* PA; double* IA; double* PB;
 };
 
+// ---- ring pipeline: two co-resident persistent kernels -----------------------------------------------
+// Evaluation: one CTA per SM, FUSED_WARPS (or as many as record buffers fit) independent warps at the full
+// register budget; each claims element batches in order from a counter and evaluates them into an L2-resident
+// RING of arena slots.  Scatter: one thin CTA per SM (FUSED_SCATTER_WARPS warps, 32 registers a thread -- the two
+// kernels split an SM's register file exactly), running beside it on a second stream: the slot map is sorted by the
+// chunk after which a group-node's patches are complete ("ready chunk") and cut into tiles of FUSED_TILE_COLS
+// patch columns; a warp claims tiles of a chunk as soon as the evaluation of it (and of all earlier chunks) has
+// finished.  A batch of chunk c may overwrite its ring slot once every tile that reads chunk c - ring_chunks has
+// been scattered.  Completion is published through the control block with release / acquire counters; no atomics
+// touch the results and the sums keep the reference's element-ascending order, so the output is bitwise that of
+// the two-kernel classic path.  A watchdog (globaltimer) turns a wait that never ends into an error code.
+constexpr int FUSED_WARPS = 7;                        // evaluation warps per CTA at most (7 x 255 registers leave exactly the scatter CTA's share)
+constexpr int FUSED_SCATTER_WARPS = 6;
+constexpr int FUSED_EVAL_REGS = 224;                  // registers per evaluation thread (see fused::eval_kernel)
+constexpr int FUSED_TILE_PATCHES = 32;                 // patches per tile: one per lane, staged through shared memory together
+constexpr int CTL_ABORT = 0, CTL_BATCH = 2 /* + type slot */, CTL_HDR = 8;
+struct FusedArgs {
+    EvalArgs ev;                     // ring-mode evaluation arguments (e_begin = 0, e_end = list length)
+    int total_chunks;                // chunks of the whole step (all types)
+    int span;                        // a patch whose ready chunk is r reads chunks [r - span, r]
+    int n_buf;                       // evaluation warps (record buffers) per CTA
+    int tile_group;                  // tiles claimed per atomic
+    int scatter_ctas;                // scatter CTAs per SM
+    int type_slot;
+    ScatterArgs sc;                  // ring slot map
+    const long long* chunk_run_ptr;  // [total_chunks + 1] first run (patch) whose ready chunk is c
+    const int* chunk_tile_ptr;       // [total_chunks + 1] first tile of ready chunk c
+    const int* chunk_batches;        // [total_chunks] evaluation batches of chunk c
+    unsigned* ctl;                   // [CTL_HDR + 3 * total_chunks]: header, edone[], sdone[], tnext[]; zeroed per step
+    unsigned long long timeout_ns;   // watchdog: a warp that waits longer sets CTL_ABORT and everyone leaves
+};
+
 // entries that involve a fixed DOF (AB, BA, BB): explicit gather lists
 struct GatherArgs {
     long long n_dest;
@@ -196,6 +251,10 @@ void launch_shell_results(const EvalArgs& a, double* out, void* stream);     // 
 void launch_beam_results(const EvalArgs& a, double* out, void* stream);      // out[n_el * GFA_BEAM_RESULTS]
 void launch_node_commit(int n_nodes, double* copy, double* disp, void* stream);
 int launch_scatter(const ScatterArgs& a, void* stream);      // returns the number of kernels launched
+void launch_vectors(const ScatterArgs& a, void* stream);
+int launch_fused_eval(const FusedArgs& f, void* stream);     // returns cudaError_t as int
+int launch_fused_scatter(const FusedArgs& f, void* stream);
+int fused_buffers(int type_slot);                            // record buffers (evaluating warps) per CTA of the fused kernel
 void launch_gather(const GatherArgs& a, void* stream);
 void launch_add_slots(double* vals, const long long* slots, const double* add, long long n, void* stream);
 void launch_pack(const double* vals, const long long* idx, double* buf, long long n, void* stream);

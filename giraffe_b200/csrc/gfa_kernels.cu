@@ -578,9 +578,9 @@ GFA_DI double self_weight(const EvalArgs& A, int e, int b, int jj) {
 //
 // Translational columns B1 = kk and B2 = 5 - kk, component jj: rows u_0..u_B1 of the first and
 // u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7 blocks for every kk.
-__device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int kk, int jj, double* pe) {
+__device__ void uu_item(const EvalArgs& A, int e, double* ke, const double* rec0, int kk, int jj, double* pe) {
     const int B1 = kk, B2 = 5 - kk;
-    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA + 64 * kk + jj;
+    double* Ke_el = ke + 64 * kk + jj;
     // m[g] = sum_q S_g[q, column] C'_g[(p, .), (q, jj)] for the two columns, p in {u,1 ; u,2}
     double m10[NGP][3], m12[NGP][3], m20[NGP][3], m22[NGP][3];
     double F1 = 0.0, F2 = 0.0;
@@ -635,8 +635,9 @@ __device__ void uu_item(const EvalArgs& A, int e, const double* rec0, int kk, in
 // Rotational column (mid-side node b in 0..2, component jj): all 27 rows -- the six u rows are the
 // upper u-alpha blocks (their transposes are the alpha-u blocks), the three alpha rows are the
 // non-symmetric alpha-alpha blocks, each stored on its own.
-__device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, int jj, double* pe) {
-    double* Ke_el = A.Ke + (size_t)e * SHELL_ARENA + 192 + 84 * b + jj;
+__device__ void rot_item(const EvalArgs& A, int e, double* ke, const double* rec0, int b, int jj, double* pe) {
+    (void)A; (void)e;
+    double* Ke_el = ke + 192 + 84 * b + jj;
     const double* S0 = rec0 + S_OFF;
     double F = 0.0;
     {   // rows u_a: gradient groups {u,1 ; u,2} x {alpha,1 ; alpha,2 ; alpha}
@@ -691,30 +692,39 @@ __device__ void rot_item(const EvalArgs& A, int e, const double* rec0, int b, in
     pe[18 + 3 * b + jj] = F;
 }
 
+// One batch of `ne` <= EPW elements at list positions k0 .. k0 + ne - 1, evaluated by one warp; `smem` is the
+// warp's own smem_bytes(EPW) region.  Shared by the classic evaluation kernel and the fused ring kernel.
+template <int EPW>
+__device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, double* smem, int lane) {
+    static_assert(EPW * 3 <= 32, "one lane per (element, component) item");
+    if (lane < ne * NGP) physics(A, eval_element(A, k0 + lane / NGP), lane % NGP, smem + lane * REC);
+    __syncwarp();
+    double* pe = smem + EPW * NGP * REC;      // the batch's P, written out in whole sectors below
+    if (lane < ne * 3) {
+        const int el = lane / 3, jj = lane % 3;
+        const double* rec0 = smem + el * NGP * REC;
+        const int e = eval_element(A, k0 + el);
+        double* ke = eval_ke(A, k0 + el, SHELL_ARENA);
+#pragma unroll 1
+        for (int kk = 0; kk < 3; kk++) uu_item(A, e, ke, rec0, kk, jj, pe + 27 * el);
+    }
+    for (int it = lane; it < ne * 9; it += 32) {
+        const int el = it / 9, c = it % 9;
+        rot_item(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, SHELL_ARENA), smem + el * NGP * REC, c / 3, c % 3, pe + 27 * el);
+    }
+    __syncwarp();
+    if (!A.elist) { for (int i = lane; i < ne * 27; i += 32) A.Pe[(size_t)k0 * 27 + i] = pe[i]; }
+    else { for (int i = lane; i < ne * 27; i += 32) A.Pe[(size_t)A.elist[k0 + i / 27] * 27 + i % 27] = pe[i]; }
+    __syncwarp();
+}
+
 template <int EPW>
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
-    static_assert(EPW * 3 <= 32, "one lane per (element, component) item");
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
-        const int e0 = A.e_begin + (int)(batch * EPW);
-        const int ne = min(EPW, A.e_end - e0);
-        if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
-        __syncwarp();
-        double* pe = smem + EPW * NGP * REC;      // the batch's P, written out in whole sectors below
-        if (lane < ne * 3) {
-            const int el = lane / 3, jj = lane % 3;
-            const double* rec0 = smem + el * NGP * REC;
-#pragma unroll 1
-            for (int kk = 0; kk < 3; kk++) uu_item(A, e0 + el, rec0, kk, jj, pe + 27 * el);
-        }
-        for (int it = lane; it < ne * 9; it += 32) {
-            const int el = it / 9, c = it % 9;
-            rot_item(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3, pe + 27 * el);
-        }
-        __syncwarp();
-        for (int i = lane; i < ne * 27; i += 32) A.Pe[(size_t)e0 * 27 + i] = pe[i];
-        __syncwarp();
+        const int k0 = A.e_begin + (int)(batch * EPW);
+        eval_batch<EPW>(A, k0, min(EPW, A.e_end - k0), smem, lane);
     }
 }
 
@@ -1041,7 +1051,7 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
 
 // local DOF order: node-major [u_a(3), alpha_a(3)] (Beam_1.cpp:1439-1444)
 template <bool ROT>
-__device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, int b, int jj) {
+__device__ void congruence_item(const EvalArgs& A, int e, double* ke, const double* rec0, int b, int jj) {
     double K[18];
 #pragma unroll
     for (int i = 0; i < 18; i++) K[i] = 0.0;
@@ -1083,7 +1093,7 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     const int col = 6 * b + (ROT ? 3 : 0) + jj;
     // stored blocks of this column block: rows 0..cb and, for a rotational column, the rotational rows below
     const int cb = col / 3;
-    double* Ke = A.Ke + (size_t)e * BEAM_ARENA + (col % 3);
+    double* Ke = ke + (col % 3);
 #pragma unroll
     for (int rb = 0; rb < 6; rb++)
         if (beam_is_stored(rb, cb)) {
@@ -1093,23 +1103,26 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     A.Pe[(size_t)e * 18 + col] = F - fe;
 }
 
+// one batch of `ne` <= EPW beams at list positions k0 .. (see shell::eval_batch)
+__device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, double* smem, int lane) {
+    if (lane < ne * NGP) physics(A, eval_element(A, k0 + lane / NGP), lane % NGP, smem + lane * REC);
+    __syncwarp();
+    for (int it = lane; it < ne * 9; it += 32) {
+        const int el = it / 9, c = it % 9;
+        congruence_item<false>(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, BEAM_ARENA), smem + el * NGP * REC, c / 3, c % 3);
+    }
+    for (int it = lane; it < ne * 9; it += 32) {
+        const int el = it / 9, c = it % 9;
+        congruence_item<true>(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, BEAM_ARENA), smem + el * NGP * REC, c / 3, c % 3);
+    }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
-        const int e0 = A.e_begin + (int)(batch * EPW);
-        const int ne = min(EPW, A.e_end - e0);
-        if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
-        __syncwarp();
-        for (int it = lane; it < ne * 9; it += 32) {
-            const int el = it / 9, c = it % 9;
-            congruence_item<false>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
-        }
-        for (int it = lane; it < ne * 9; it += 32) {
-            const int el = it / 9, c = it % 9;
-            congruence_item<true>(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
-        }
-        __syncwarp();
+        const int k0 = A.e_begin + (int)(batch * EPW);
+        eval_batch(A, k0, min(EPW, A.e_end - k0), smem, lane);
     }
 }
 
@@ -1307,7 +1320,7 @@ GFA_DI double c_at(const double* recJ, const double* rec3J) {
     else return rec3J[C_OFF + 9 * blk(Q, P) + II];
 }
 
-__device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, int b, int jj) {
+__device__ void congruence_item(const EvalArgs& A, int e, double* ke, const double* rec0, int b, int jj) {
     double K[24];
 #pragma unroll
     for (int i = 0; i < 24; i++) K[i] = 0.0;
@@ -1334,26 +1347,29 @@ __device__ void congruence_item(const EvalArgs& A, int e, const double* rec0, in
     }
     const int col = 3 * b + jj;
     // stored blocks of this column block: rows 0..b (the tangent is symmetric)
-    double* Ke = A.Ke + (size_t)e * SOLID_ARENA + solid_stored_offset(0, b) + jj;
+    double* Ke = ke + solid_stored_offset(0, b) + jj;
 #pragma unroll
     for (int rb = 0; rb < 8; rb++)
         if (rb <= b) { Ke[9 * rb] = K[3 * rb]; Ke[9 * rb + 3] = K[3 * rb + 1]; Ke[9 * rb + 6] = K[3 * rb + 2]; }
     A.Pe[(size_t)e * 24 + col] = F - fe;
 }
 
+// one batch of `ne` <= EPW solids at list positions k0 .. (see shell::eval_batch)
+__device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, double* smem, int lane) {
+    if (lane < ne * NGP) physics(A, eval_element(A, k0 + lane / NGP), lane % NGP, smem + lane * REC);
+    __syncwarp();
+    for (int it = lane; it < ne * 24; it += 32) {
+        const int el = it / 24, c = it % 24;
+        congruence_item(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, SOLID_ARENA), smem + el * NGP * REC, c / 3, c % 3);
+    }
+    __syncwarp();
+}
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
-        const int e0 = A.e_begin + (int)(batch * EPW);
-        const int ne = min(EPW, A.e_end - e0);
-        if (lane < ne * NGP) physics(A, e0 + lane / NGP, lane % NGP, smem + lane * REC);
-        __syncwarp();
-        for (int it = lane; it < ne * 24; it += 32) {
-            const int el = it / 24, c = it % 24;
-            congruence_item(A, e0 + el, smem + el * NGP * REC, c / 3, c % 3);
-        }
-        __syncwarp();
+        const int k0 = A.e_begin + (int)(batch * EPW);
+        eval_batch(A, k0, min(EPW, A.e_end - k0), smem, lane);
     }
 }
 
@@ -1480,6 +1496,234 @@ __global__ void unpack_add_kernel(double* vals, const long long* idx, const doub
 }
 
 // =========================================================================
+// Fused ring pipeline: evaluation + scatter in one persistent kernel (FusedArgs, gfa_device.h)
+// =========================================================================
+namespace fused {
+
+GFA_DI unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+GFA_DI unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+GFA_DI void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+GFA_DI unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// column c of a contributing block, read from L2 (the ring is rewritten while the kernel runs: L1 must not serve it)
+GFA_DI void load_col_cg(const double* Ke, unsigned off, bool tr, int c, double (&x)[3]) {
+    const double* p = Ke + (size_t)off + (tr ? 3 * c : c);
+    const int st = tr ? 1 : 3;
+    x[0] = __ldcg(p); x[1] = __ldcg(p + st); x[2] = __ldcg(p + 2 * st);
+}
+
+struct ShellT {
+    static constexpr int EPW = 8, SMEM = shell::smem_bytes(8);
+    static GFA_DI void batch(const EvalArgs& A, int k0, int ne, double* sm, int lane) { shell::eval_batch<8>(A, k0, ne, sm, lane); }
+};
+struct BeamT {
+    static constexpr int EPW = beam::EPW, SMEM = beam::SMEM_BYTES;
+    static GFA_DI void batch(const EvalArgs& A, int k0, int ne, double* sm, int lane) { beam::eval_batch(A, k0, ne, sm, lane); }
+};
+struct SolidT {
+    static constexpr int EPW = solid::EPW, SMEM = solid::SMEM_BYTES;
+    static GFA_DI void batch(const EvalArgs& A, int k0, int ne, double* sm, int lane) { solid::eval_batch(A, k0, ne, sm, lane); }
+};
+
+// a wait that gives up: returns true when the kernel has to leave (abort raised by anyone, or this warp waited too long)
+GFA_DI bool backoff(unsigned* ctl, unsigned long long& t_wait, unsigned long long timeout_ns, unsigned who) {
+    if (ld_relaxed(ctl + CTL_ABORT)) return true;
+    const unsigned long long now = global_ns();
+    if (!t_wait) t_wait = now;
+    else if (now > t_wait && now - t_wait > timeout_ns) {
+        if (atomicExch(ctl + CTL_ABORT, who) == 0u) ctl[5] = (unsigned)((now - t_wait) >> 10);     // who gave up first, after how many microseconds
+        return true;
+    }
+    __nanosleep(128);
+    return false;
+}
+
+// ---- evaluation kernel: one CTA per SM, every warp owns a record buffer and evaluates batches claimed in order ----
+// Register budget: an SM's register file is four banks of 16 K, one per scheduler, and a CTA's warps are dealt
+// round-robin to them.  Seven evaluation warps put two on three of the schedulers; the scatter CTA's eight warps
+// need two slots of 32 registers on EVERY scheduler, so an evaluation thread may hold at most 256 - 32 = 224
+// (tools/coresidency_probe.cu: at 254 registers the thin kernel never becomes resident beside five or more warps).
+template <class T>
+__global__ void __maxnreg__(FUSED_EVAL_REGS) eval_kernel(FusedArgs F) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* buf = smem + (size_t)warp * (T::SMEM / 8);
+    unsigned* ctl = F.ctl;
+    unsigned* edone = ctl + CTL_HDR;                         // batches evaluated, per chunk
+    const unsigned* sdone = edone + F.total_chunks;          // tiles scattered, per ready chunk
+    const EvalArgs& A = F.ev;
+    const int n_list = A.e_end;
+    const int n_batches = (n_list + T::EPW - 1) / T::EPW;
+    // lane 0: chunks known to be scattered completely.  The scatter kernel runs on its own: it may still be draining the
+    // last chunks of the previous element type's launch, but everything a full ring before this launch's first chunk
+    // had to be scattered for that launch to get as far as it did
+    int s_upto = max(0, A.chunk0 - A.ring_chunks);
+    unsigned long long t_wait = 0;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = (int)atomicAdd(ctl + CTL_BATCH + F.type_slot, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_batches) break;
+        const int k0 = b * T::EPW;
+        const int c = A.chunk0 + k0 / A.chunk_el;
+        // the ring slot of chunk c held chunk c - ring_chunks: everything that read it must have been scattered
+        const int need = c - A.ring_chunks + F.span + 1;
+        int stop = 0;
+        if (lane == 0) {
+            t_wait = 0;
+            while (s_upto < need) {
+                const unsigned have = ld_acquire(sdone + s_upto), want = (unsigned)(F.chunk_tile_ptr[s_upto + 1] - F.chunk_tile_ptr[s_upto]);
+                if (have == want) { s_upto++; continue; }
+                if (backoff(ctl, t_wait, F.timeout_ns, 1u + (unsigned)c * 16u)) {
+                    unsigned* dbg = ctl + CTL_HDR + 3 * F.total_chunks;
+                    if (atomicExch(dbg, 1u) == 0u) { dbg[1] = have; dbg[2] = want; dbg[3] = (unsigned)s_upto; dbg[4] = (unsigned)need; dbg[5] = (unsigned)b; dbg[6] = (unsigned)A.chunk0; dbg[7] = (unsigned)A.ring_chunks; }
+                    stop = 1; break;
+                }
+            }
+        }
+        if (__shfl_sync(0xffffffffu, stop, 0)) break;
+        T::batch(A, k0, min(T::EPW, n_list - k0), buf, lane);
+        __syncwarp();               // the warp's arena stores are ordered before lane 0's release (cumulativity)
+        if (lane == 0) { fence_acq_rel(); atomicAdd(edone + c, 1u); }
+    }
+}
+
+// ---- scatter kernel: thin persistent warps beside the evaluation CTA of every SM ------------------------------
+// Registers are what the evaluation kernel leaves least of (32 a thread here), and a gather that has to cover
+// ~1 us of L2 latency with loads held in registers needs thousands of them per SM.  So the blocks do not pass
+// through registers: a warp claims tiles of FUSED_TILE_PATCHES patches of one ready chunk (atomicAdd on that
+// chunk's cursor, once the chunk and all earlier ones are evaluated), and for every tile
+//   1. issues, for both possible sources of each patch, the five aligned 16-byte pieces that cover the 72-byte
+//      block as cp.async.cg copies into its own staging buffer (L2 -> shared memory, no register, no L1: the ring
+//      is rewritten while the kernel runs);
+//   2. waits for the group, then sums each patch column from shared memory in element-ascending order and writes
+//      the CSR rows with streaming stores -- the arithmetic of scatter_kernel, bit for bit.
+// Patches fed by more than two blocks take their sources straight from L2 (overflow list).
+constexpr int STAGE_BLOCK = 80;                                          // bytes staged per source block
+constexpr int STAGE_BYTES = FUSED_TILE_PATCHES * 2 * STAGE_BLOCK;       // per warp
+GFA_DI void cp_async16(unsigned dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst_smem), "l"(src) : "memory");
+}
+__global__ void __maxnreg__(32) scatter_kernel(FusedArgs F) {
+    extern __shared__ __align__(16) unsigned char stage_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* stage = stage_all + warp * STAGE_BYTES;
+    const unsigned stage_s = (unsigned)__cvta_generic_to_shared(stage);
+    unsigned* ctl = F.ctl;
+    const unsigned* edone = ctl + CTL_HDR;
+    unsigned* sdone = ctl + CTL_HDR + F.total_chunks;
+    unsigned* tnext = sdone + F.total_chunks;
+    const ScatterArgs& A = F.sc;
+    const int chunk_end = F.total_chunks;
+    int e_upto = 0, r_cur = 0;      // lane 0: evaluated prefix, first chunk that may hold unclaimed tiles
+    unsigned long long t_wait = 0;
+    for (;;) {
+        int t0 = -1, nt = 0;
+        if (lane == 0) {
+            for (;;) {
+                if (r_cur >= chunk_end) break;
+                const int tiles = F.chunk_tile_ptr[r_cur + 1] - F.chunk_tile_ptr[r_cur];
+                if (tiles == 0 || (int)ld_relaxed(tnext + r_cur) >= tiles) { r_cur++; continue; }
+                while (e_upto <= r_cur && ld_acquire(edone + e_upto) == (unsigned)F.chunk_batches[e_upto]) e_upto++;
+                if (e_upto <= r_cur) {                                    // not evaluated yet
+                    if (backoff(ctl, t_wait, F.timeout_ns, 2u + (unsigned)r_cur * 16u)) break;
+                    continue;
+                }
+                const int t = (int)atomicAdd(tnext + r_cur, (unsigned)F.tile_group);
+                if (t >= tiles) { r_cur++; continue; }
+                t0 = t; nt = min(F.tile_group, tiles - t); t_wait = 0;
+                break;
+            }
+        }
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if (t0 < 0) break;                                                // every tile is claimed, or the watchdog fired
+        nt = __shfl_sync(0xffffffffu, nt, 0);
+        const int r = __shfl_sync(0xffffffffu, r_cur, 0);
+        const long long run0 = F.chunk_run_ptr[r] + (long long)t0 * FUSED_TILE_PATCHES;
+        const long long run1 = min(F.chunk_run_ptr[r + 1], run0 + (long long)nt * FUSED_TILE_PATCHES);
+        // the slot-map entries of the claim come from DRAM: start them all now (128-byte lines)
+        for (long long j = run0 + 8 * lane; j < run1; j += 256) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.runs + j));
+        uint4 qn = run0 + lane < run1 ? __ldcs(reinterpret_cast<const uint4*>(A.runs) + run0 + lane) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+        for (long long p0 = run0; p0 < run1; p0 += FUSED_TILE_PATCHES) {
+            const uint4 q = qn;             // this lane's patch of the tile (info == 0 past the end)
+            qn = p0 + FUSED_TILE_PATCHES + lane < run1 ? __ldcs(reinterpret_cast<const uint4*>(A.runs) + p0 + FUSED_TILE_PATCHES + lane) : make_uint4(0u, 0u, 0u, 0u);
+            const unsigned info = q.y;
+            const int cnt = info >> 24;
+            // ---- 1. stage this lane's (at most two) source blocks: the five aligned 16-byte pieces around each
+            if (cnt >= 1 && cnt <= 2) {
+                const unsigned long long g = reinterpret_cast<unsigned long long>(A.Ke + q.z) & ~15ULL;
+                const unsigned d = stage_s + lane * STAGE_BLOCK;
+#pragma unroll
+                for (int k = 0; k < 5; k++) cp_async16(d + 16 * k, reinterpret_cast<const void*>(g + 16 * k));
+            }
+            if (cnt == 2) {
+                const unsigned long long g = reinterpret_cast<unsigned long long>(A.Ke + q.w) & ~15ULL;
+                const unsigned d = stage_s + (32 + lane) * STAGE_BLOCK;
+#pragma unroll
+                for (int k = 0; k < 5; k++) cp_async16(d + 16 * k, reinterpret_cast<const void*>(g + 16 * k));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            // ---- 2. sum and store the patch's columns (a lane reads only what it staged itself)
+            const int L = info & 0xffff, rm = (info >> 16) & 7, fm = (info >> 19) & 7;
+            const int r1 = rm & 1, r2 = r1 + ((rm >> 1) & 1);
+            const double* b0 = reinterpret_cast<const double*>(stage + lane * STAGE_BLOCK) + (q.z & 1u);
+            const double* b1 = reinterpret_cast<const double*>(stage + (32 + lane) * STAGE_BLOCK) + (q.w & 1u);
+            const bool tr0 = (info >> 22) & 1, tr1 = (info >> 23) & 1;
+            double* o = A.valAA + (size_t)(int)q.x;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (!((fm >> c) & 1)) continue;
+                double a[3];
+                if (cnt <= 2) {
+                    const int o0 = tr0 ? 3 * c : c, st0 = tr0 ? 1 : 3, o1 = tr1 ? 3 * c : c, st1 = tr1 ? 1 : 3;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const double x = cnt > 0 ? b0[o0 + i * st0] : 0.0, y = cnt > 1 ? b1[o1 + i * st1] : 0.0;
+                        a[i] = x + y;
+                    }
+                } else {
+                    const unsigned long long e0 = __ldg(A.ovf + q.z), e1 = __ldg(A.ovf + q.z + 1);
+                    double v0[3], v1[3];
+                    load_col_cg(A.Ke, (unsigned)e0, (e0 & SRC_T) != 0, c, v0);
+                    load_col_cg(A.Ke, (unsigned)e1, (e1 & SRC_T) != 0, c, v1);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) a[i] = v0[i] + v1[i];
+#pragma unroll 1
+                    for (int k = 2; k < cnt; k++) {
+                        const unsigned long long e = __ldg(A.ovf + q.z + k);
+                        load_col_cg(A.Ke, (unsigned)e, (e & SRC_T) != 0, c, v0);
+#pragma unroll
+                        for (int i = 0; i < 3; i++) a[i] += v0[i];
+                    }
+                }
+                if (rm & 1) __stcs(o, a[0]);
+                if (rm & 2) __stcs(o + (size_t)r1 * L, a[1]);
+                if (rm & 4) __stcs(o + (size_t)r2 * L, a[2]);
+                o++;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { fence_acq_rel(); atomicAdd(sdone + r, (unsigned)nt); }
+    }
+}
+
+} // namespace fused
+
+// =========================================================================
 // Newton-loop vector steps either side of the assembly
 // =========================================================================
 // db.global_P_A = -1.0 * db.global_P_A (Static.cpp:210)
@@ -1585,6 +1829,24 @@ int configure_kernels() {
     e = cudaFuncSetAttribute(beam::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, beam::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(solid::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, solid::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::eval_kernel<fused::ShellT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_buffers(0) * fused::ShellT::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::eval_kernel<fused::BeamT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_buffers(1) * fused::BeamT::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::eval_kernel<fused::SolidT>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused_buffers(2) * fused::SolidT::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    // the scatter kernel has to be resident BESIDE the evaluation CTA of every SM: an SM runs with one shared-memory
+    // carve-out at a time, so the kernel without shared memory asks for the same (maximal) split
+    e = cudaFuncSetAttribute(fused::scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SCATTER_WARPS * fused::STAGE_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::eval_kernel<fused::ShellT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::eval_kernel<fused::BeamT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fused::eval_kernel<fused::SolidT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     return (int)e;
 }
@@ -1712,6 +1974,33 @@ int launch_scatter(const ScatterArgs& a, void* s) {
         launches++;
     }
     return launches;
+}
+void launch_vectors(const ScatterArgs& a, void* s) {
+    if (a.n_gn > 0) vector_kernel<<<(unsigned)((3 * a.n_gn + 255) / 256), 256, 0, (cudaStream_t)s>>>(a);
+}
+int fused_buffers(int slot) {
+    const int per = slot == 0 ? fused::ShellT::SMEM : slot == 1 ? fused::BeamT::SMEM : fused::SolidT::SMEM;
+    // what the scatter CTA's staging buffers and the two reserved kilobytes leave of an SM's 228 KB
+    const int n = (226 * 1024 - FUSED_SCATTER_WARPS * fused::STAGE_BYTES) / per;
+    return n < FUSED_WARPS ? n : FUSED_WARPS;
+}
+static int sm_count() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs;
+    return sms;
+}
+int launch_fused_eval(const FusedArgs& f, void* s) {
+    const int nb = f.n_buf, sms = sm_count();
+    cudaStream_t st = (cudaStream_t)s;
+    if (f.type_slot == 0) fused::eval_kernel<fused::ShellT><<<sms, 32 * nb, nb * fused::ShellT::SMEM, st>>>(f);
+    else if (f.type_slot == 1) fused::eval_kernel<fused::BeamT><<<sms, 32 * nb, nb * fused::BeamT::SMEM, st>>>(f);
+    else fused::eval_kernel<fused::SolidT><<<sms, 32 * nb, nb * fused::SolidT::SMEM, st>>>(f);
+    return (int)cudaGetLastError();
+}
+int launch_fused_scatter(const FusedArgs& f, void* s) {
+    fused::scatter_kernel<<<sm_count() * f.scatter_ctas, 32 * FUSED_SCATTER_WARPS, FUSED_SCATTER_WARPS * fused::STAGE_BYTES, (cudaStream_t)s>>>(f);
+    return (int)cudaGetLastError();
 }
 void launch_gather(const GatherArgs& a, void* s) {
     if (a.n_dest <= 0) return;

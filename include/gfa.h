@@ -268,6 +268,16 @@ int gfa_element_alpha_i(gfa_t* h, int32_t element, double* out);
 int gfa_last_timing(gfa_t* h, double* ms4);
 /* Number of kernels the last gfa_assemble launched. */
 int gfa_last_launch_count(gfa_t* h);
+/* Which pipeline gfa_set_dofs chose for this DOF map: returns 0 for the classic evaluation + scatter kernels (the
+ * default), 1 for the ring pipeline, negative on error; `buf` receives a one-line description.  In the ring
+ * pipeline the element blocks go through an L2-resident ring of arena slots: persistent evaluation kernels (one
+ * per element type) fill it chunk by chunk and a persistent scatter kernel, co-resident on every SM, drains it
+ * behind them (release / acquire counters per chunk, a watchdog instead of a hang).  It halves the DRAM traffic
+ * of a step and gives bitwise the classic results, but is slower on B200 today (profiles/r02_notes.md), hence
+ * opt-in: GFA_RING=1 (always) or 2 (when the arena is larger than the ring); GFA_RING_CHUNK_KB and
+ * GFA_RING_CHUNKS size the ring (default 9 x 7 MB).  gfa_last_timing then reports [1] = pre-pass of the pinned
+ * elements, [2] = ring kernels + vectors. */
+int gfa_pipeline_info(gfa_t* h, char* buf, int32_t capacity);
 
 /* ---- multi-GPU (mesh partition by element range) ----------------------
  * Every rank holds the full DOF map but evaluates only its element partition

@@ -1,0 +1,176 @@
+"""GPU: the fused ring pipeline (one persistent kernel per element type: evaluation into an L2-resident ring
+of arena slots, the scatter role draining it behind the evaluation) against the oracle and, bit for bit,
+against the classic evaluation + scatter kernels.  Small meshes are pushed through the ring with chunks of a
+few elements (GFA_RING_CHUNK_KB) so that chunk boundaries, ring wrap-around, pinned elements (fixed DOFs,
+far-reaching group-nodes) and the tile tables are all exercised at sizes the oracle finishes in seconds; the
+>= 50k-element cases run the default ring geometry and compare the FULL CSR and the vectors with the oracle
+(VERDICT r1 "harden parity where the code runs hot")."""
+import numpy as np
+import pytest
+
+import util
+from giraffe_b200 import capi, meshes as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _assembler(monkeypatch, m, ring, chunk_kb=None, chunks=None):
+    monkeypatch.setenv("GFA_RING", "1" if ring else "0")
+    if chunk_kb is not None:
+        monkeypatch.setenv("GFA_RING_CHUNK_KB", str(chunk_kb))
+    else:
+        monkeypatch.delenv("GFA_RING_CHUNK_KB", raising=False)
+    if chunks is not None:
+        monkeypatch.setenv("GFA_RING_CHUNKS", str(chunks))
+    else:
+        monkeypatch.delenv("GFA_RING_CHUNKS", raising=False)
+    asm = capi.Assembler(m).set_dofs()
+    is_ring, note = asm.pipeline_info()
+    return asm, is_ring, note
+
+
+def _compare(port, asm, what):
+    worst = util.assert_system_parity(port.csr, asm.csr, what)
+    for a, b, key in zip(port.vectors(), asm.vectors(), ("P_A", "I_A", "P_B")):
+        util.assert_parity(a, b, f"{what} {key}")
+    return worst
+
+
+def _cases():
+    rng = np.random.default_rng(21)
+    shell = M.shell_plate(40, 25, warp=0.01, gravity=(0.0, 0.0, -9.81))
+    beam = M.beam_line(3000, pretension=2.0e4)
+    beam.gravity = (0.1, 0.2, -9.81)
+    solid = M.solid_block(12, 10, 8, gravity=(0.0, 0.0, -9.81))
+    mixed = M.concat_models([M.beam_line(700), M.pipe_line(300), M.shell_plate(30, 14, warp=0.005), M.solid_block(8, 7, 6)])
+    free = M.shell_plate(24, 18)
+    free.constraints = []
+    return [
+        # (name, model, displacements, chunk KB, ring chunks): a group-node of the 40 x 25 plate touches elements up to
+        # 160 positions apart, so 72-element chunks (256 KB) keep most of them within the reach of a 9-chunk ring and
+        # pin the rest; 184-element chunks with a 3-chunk ring wrap the ring every third chunk
+        ("shell", shell, M.shell_plate_displacements(shell), 256, 9),
+        ("shell_k3", shell, M.shell_plate_displacements(shell, seed=3), 640, 3),
+        ("beam", beam, M.beam_line_displacements(beam), 32, 5),
+        ("solid", solid, M.solid_block_displacements(solid), 256, 9),
+        ("mixed", mixed, M.mask_displacements(mixed, rng.uniform(-1e-4, 1e-4, (mixed.n_nodes, 6))), 256, 6),
+        ("unconstrained", free, M.mask_displacements(free, rng.uniform(-1e-4, 1e-4, (free.n_nodes, 6))), 128, 9),
+    ]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
+def test_ring_pipeline_against_oracle_and_classic(monkeypatch, port, case):
+    name, m, d, chunk_kb, chunks = case
+    port.load(m)
+    port.set_time(0.0, 0.5)
+    ring, is_ring, note = _assembler(monkeypatch, m, True, chunk_kb, chunks)
+    assert is_ring, f"{name}: expected the ring pipeline, got: {note}"
+    classic, is_ring_c, _ = _assembler(monkeypatch, m, False)
+    assert not is_ring_c
+    ring.set_time(0.0, 0.5)
+    classic.set_time(0.0, 0.5)
+    for it in range(2):
+        port.assemble(d)
+        ring.assemble(d)
+        classic.assemble(d)
+        _compare(port, ring, f"ring {name} it{it}")
+        for w in ("AA", "AB", "BA", "BB"):
+            assert ring.values(w).tobytes() == classic.values(w).tobytes(), f"{name}: ring and classic {w} differ bitwise ({note})"
+        for a, b in zip(ring.vectors(), classic.vectors()):
+            assert a.tobytes() == b.tobytes(), f"{name}: ring and classic vectors differ bitwise"
+        for e in sorted({0, m.n_elements // 3, m.n_elements - 1}):      # the ring keeps no element: re-evaluated on demand
+            Kp, Pp, _ = port.element(e)
+            Kg, Pg = ring.element(e)
+            util.assert_parity(Kp, Kg, f"ring {name} element {e} K", util.block_scale(Kp))
+            util.assert_parity(Pp, Pg, f"ring {name} element {e} P")
+        port.commit(); ring.commit(); classic.commit()
+        d = -0.6 * d
+    # repeated assemblies are bit-identical (no atomics touch the results; chunk completion order does not matter)
+    ring.assemble(d)
+    v1 = ring.values("AA").copy()
+    ring.assemble(3.0 * d)
+    ring.assemble(d)
+    assert ring.values("AA").tobytes() == v1.tobytes()
+
+
+def test_ring_with_scrambled_element_numbering(monkeypatch, port):
+    """Element numbering without locality: group-nodes whose elements lie further apart than the ring reaches
+    are served from pinned regions (or the whole model falls back to the classic kernels) -- same results."""
+    m = M.shell_plate(30, 20, warp=0.01)
+    rng = np.random.default_rng(8)
+    perm = rng.permutation(m.n_elements)
+    nn = 6
+    m.elem_nodes = m.elem_nodes.reshape(-1, nn)[perm].reshape(-1).copy()
+    d = M.shell_plate_displacements(m)
+    port.load(m)
+    port.set_time(0.0, 1.0)
+    port.assemble(d)
+    asm, is_ring, note = _assembler(monkeypatch, m, True, 256, 9)
+    asm.assemble(d)
+    _compare(port, asm, f"scrambled plate ({note})")
+    # partly scrambled: only a band of elements is permuted, the rest keeps its locality and goes through the ring
+    m2 = M.shell_plate(40, 30, warp=0.01)
+    conn = m2.elem_nodes.reshape(-1, nn).copy()
+    band = np.arange(700, 900)
+    conn[band] = conn[rng.permutation(band)]
+    far = np.array([5, 2300])                       # two elements swapped across the whole mesh
+    conn[far] = conn[far[::-1]]
+    m2.elem_nodes = conn.reshape(-1).copy()
+    d2 = M.shell_plate_displacements(m2)
+    port.load(m2)
+    port.assemble(d2)
+    asm2, is_ring2, note2 = _assembler(monkeypatch, m2, True, 256, 9)
+    assert is_ring2 and "pinned" in note2, note2
+    asm2.assemble(d2)
+    _compare(port, asm2, f"partly scrambled plate ({note2})")
+
+
+def test_ring_leaves_for_dynamics(monkeypatch, port):
+    """The Newmark kernels work on a complete arena in place: a ring-mode handle rebuilds its slot map for the
+    classic kernels at the first dynamic assembly and gives the classic handle's results."""
+    m = M.shell_plate(20, 12, warp=0.01)
+    d = M.shell_plate_displacements(m)
+    ring, is_ring, _ = _assembler(monkeypatch, m, True, 128, 9)
+    assert is_ring
+    classic, _, _ = _assembler(monkeypatch, m, False)
+    nm = (4.0e4, 4.0e2, 1.0, 2.0e2, 1.0, 0.0)
+    for a in (ring, classic):
+        a.set_dynamic(nm, 0.1, 1e-4)
+        a.assemble(d)
+        a.assemble_dynamic(d, True)
+    assert not ring.pipeline_info()[0]
+    assert ring.values("AA").tobytes() == classic.values("AA").tobytes()
+    for a, b in zip(ring.vectors(), classic.vectors()):
+        assert a.tobytes() == b.tobytes()
+
+
+# ---- >= 50k elements: default ring geometry, FULL CSR + vectors against the oracle --------------------
+@pytest.mark.parametrize("kind", ["shell", "beam", "solid", "mixed"])
+def test_full_csr_parity_at_scale(monkeypatch, port, kind):
+    monkeypatch.setenv("GFA_RING", "2")
+    monkeypatch.delenv("GFA_RING_CHUNK_KB", raising=False)
+    monkeypatch.delenv("GFA_RING_CHUNKS", raising=False)
+    rng = np.random.default_rng(77)
+    if kind == "shell":
+        m = M.shell_plate(250, 120, warp=0.01, gravity=(0.0, 0.0, -9.81))           # 60 000 shells
+        d = M.shell_plate_displacements(m)
+    elif kind == "beam":
+        m = M.beam_line(60_000, pretension=1.0e4)
+        m.gravity = (0.0, 0.3, -9.81)
+        d = M.beam_line_displacements(m)
+    elif kind == "solid":
+        m = M.solid_block(40, 30, 25, gravity=(0.0, 0.0, -9.81))                      # 30 000 solids
+        d = M.solid_block_displacements(m)
+    else:
+        m = M.concat_models([M.beam_line(10_000), M.shell_plate(150, 100, warp=0.005), M.solid_block(25, 20, 20)])   # 50 000
+        d = M.mask_displacements(m, rng.uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
+    port.load(m)
+    port.set_time(0.0, 1.0)
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(0.0, 1.0)
+    is_ring, note = asm.pipeline_info()
+    assert is_ring, f"{kind}: {note}"
+    port.assemble(d)
+    asm.assemble(d)
+    worst = _compare(port, asm, f"{kind} at scale ({note})")
+    print(f"{kind}: {m.n_elements} elements, nnz_AA {asm.csr_dims('AA')[2]}, worst {worst:.2e}; {note}")
