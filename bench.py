@@ -6,10 +6,16 @@ elements assembled/sec, Kt+Fint -> CSR, FP64).
     python bench.py --impl reference --gpus N --steps K ...   # reference CPU path
 
 A "step" is one pass of the hot path (Clear + MountLocal + MountElementLoads +
-MountGlobal + MountSparse) over one synthetic batch: the 1M-element Shell_1
-plate of BASELINE.json configs[2] per GPU (weak scaling: N GPUs assemble an
-N-times larger plate, partitioned by contiguous element ranges; interface rows
-are exchanged with NCCL send/recv).  Prints ONE JSON line on rank 0.
+MountGlobal + MountSparse) over one synthetic batch.  The headline line is the
+1M-element Shell_1 plate of BASELINE.json configs[2] per GPU (weak scaling: N GPUs
+assemble an N-times larger plate, partitioned by contiguous element ranges, the
+interface rows exchanged with NCCL send/recv).  The same JSON line carries
+`side_configs`: the other BASELINE configs (100k Beam_1 line, 4M Solid_1 block, the
+mixed Beam_1 + Shell_1 + Solid_1 model of configs[4] at 1M elements per GPU) and,
+for N > 1, the STRONG-scaling number of the fixed 1M-shell plate -- each with the
+parity probe of the headline (`parity_ok`): rows of sampled nodes, partition
+interfaces included, against a single-GPU assembly of the elements around them.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -32,15 +38,23 @@ METRIC = "elements assembled/sec (Kt+Fint->CSR, FP64)"
 UNIT = "elements/s"
 # compulsory HBM traffic and structure-exploiting flop count
 SHELL_ALG_FLOPS = 5.0e4
-SHELL_READ_BYTES = 928.0
+READ_BYTES = {"shell": 928.0, "beam": 524.0, "solid": 8 * (8 * 9 + 8) + 36.0}      # per element (Solid_1: builder-defined)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0}, "fallback"
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def profile_file(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
 
 
 class ClockSampler:
@@ -86,25 +100,49 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(n_gpus: int, per_gpu_cells=(1000, 500)):
-    """N x (1000 x 500 cells x 2 triangles): the plate grows along y so that
-    contiguous element ranges are strips with one interface line each."""
-    nx, ny = per_gpu_cells
-    return M.shell_plate(nx, ny * n_gpus), {"workload": f"shell_plate_{nx}x{ny * n_gpus}cells_Shell_1",
-                                           "elements": 2 * nx * ny * n_gpus, "per_gpu_elements": 2 * nx * ny,
-                                           "config": "BASELINE.json configs[2] (1M-element Shell_1 plate) per GPU",
-                                           "partition": f"{n_gpus} strips by contiguous element range",
-                                           "l2": "inputs larger than L2 (element blocks 3.6 GB, CSR values 4.2 GB per GPU)"}
+# ---------------------------------------------------------------------------
+# workloads = BASELINE.json configs
+# ---------------------------------------------------------------------------
+def workload(kind: str, n_gpus: int, scaling: str = "weak", cells=(1000, 500)):
+    """(model, displacements, config dict).  Weak scaling multiplies the per-GPU size by N along the direction
+    the element numbering runs last, so that contiguous element ranges are strips with one interface each."""
+    f = n_gpus if scaling == "weak" else 1
+    if kind == "shell":
+        nx, ny = cells
+        m = M.shell_plate(nx, ny * f)
+        d = M.shell_plate_displacements(m)
+        cfg = {"workload": f"shell_plate_{nx}x{ny * f}cells_Shell_1", "config": "BASELINE.json configs[2] (1M-element Shell_1 plate)" + (" per GPU" if scaling == "weak" else ", fixed size")}
+    elif kind == "beam":
+        m = M.beam_line(100_000 * f)
+        d = M.beam_line_displacements(m)
+        cfg = {"workload": f"beam_line_{100_000 * f}_Beam_1", "config": "BASELINE.json configs[1] (100k-element Beam_1 line)" + (" per GPU" if scaling == "weak" else "")}
+    elif kind == "solid":
+        m = M.solid_block(160, 160, 156 * f)
+        d = M.solid_block_displacements(m)
+        cfg = {"workload": f"solid_block_160x160x{156 * f}_Solid_1", "config": "BASELINE.json configs[3] (4M-element Solid_1 block; builder-defined hexahedron, reference bodies are empty)" + (" per GPU" if scaling == "weak" else "")}
+    elif kind == "mixed":
+        # configs[4]: 8M elements on 8 GPUs = 1M per GPU: 125k Beam_1 + 375k Shell_1 + 500k Solid_1 per GPU
+        m = M.concat_models([M.beam_line(125_000 * f), M.shell_plate(750, 250 * f), M.solid_block(100, 100, 50 * f)])
+        d = M.mask_displacements(m, np.random.default_rng(20240005).uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
+        cfg = {"workload": f"mixed_{125_000 * f}beams+{375_000 * f}shells+{500_000 * f}solids",
+               "config": "BASELINE.json configs[4] (mixed Beam_1 + Shell_1 + Solid_1, 1M elements per GPU: 8M on 8 GPUs)", "mix": "12.5 % Beam_1, 37.5 % Shell_1, 50 % Solid_1"}
+    else:
+        raise SystemExit(f"unknown workload {kind}")
+    cfg.update({"elements": int(m.n_elements), "per_gpu_elements": int(m.n_elements // n_gpus), "scaling": scaling,
+                "partition": f"{n_gpus} contiguous element ranges per type", "l2": "inputs and outputs far larger than L2 (no flush needed between steps)"})
+    return m, d, cfg
+
+
+def algorithmic_bytes(m, nnz_local, n_free_local, world):
+    """compulsory reads per element + 8 B per CSR non-zero + 16 B per free DOF (P_A, I_A)."""
+    t = m.elem_type
+    n = {"beam": int(np.count_nonzero((t == M.BEAM_1) | (t == M.PIPE_1))), "shell": int(np.count_nonzero(t == M.SHELL_1)), "solid": int(np.count_nonzero(t == M.SOLID_1))}
+    return sum(READ_BYTES[k] * n[k] for k in n) / world + 8.0 * nnz_local + 16.0 * n_free_local
 
 
 # ---------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path
 # ---------------------------------------------------------------------------
-def cpu_sample(cells=(100, 50)):
-    m = M.shell_plate(*cells)
-    return m, M.shell_plate_displacements(m), f"Shell_1 plate {cells[0]}x{cells[1]} cells = {m.n_elements} elements of the same mesh family"
-
-
 def cpu_oracle(threads: int):
     from oracle import refdrv
     if refdrv.available():
@@ -116,19 +154,21 @@ def cpu_oracle(threads: int):
 def time_cpu(steps: int, warmup: int, cells=(100, 50)):
     threads = os.cpu_count() or 1
     orc, kind = cpu_oracle(threads)
-    m, d, sample = cpu_sample(cells)
+    m = M.shell_plate(*cells)
+    d = M.shell_plate_displacements(m)
     orc.load(m)
     for _ in range(warmup):
         orc.assemble(d)
-    t = []
-    local = []
+    t, local = [], []
     for _ in range(steps):
         s = orc.assemble(d)
         t.append(float(s[:4].sum()))       # MountLocal + MountElementLoads + MountGlobal + MountSparse
         local.append(float(s[0]))
     med = float(np.median(t))
-    return {"value": m.n_elements / med, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-            "ms_per_step": med * 1e3, "mount_local_only_elements_per_s": m.n_elements / float(np.median(local)),
+    return {"value": m.n_elements / med, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"Shell_1 plate {cells[0]}x{cells[1]} cells = {m.n_elements} elements (the headline mesh family at a size the CPU finishes in seconds), median of {steps} steps",
+            "sample_elements": int(m.n_elements), "ms_per_step": med * 1e3,
+            "mount_local_only_elements_per_s": m.n_elements / float(np.median(local)),
             "note": "OpenMP MountLocal/MountElementLoads, serial MountGlobal + setFromTriplets as in the reference; "
                     "GEMM and setFromTriplets are restatements (no MKL/Eigen on the box)"}
 
@@ -137,23 +177,260 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = time_cpu(max(args.steps, 1), max(args.warmup, 1))
-    _, cfg = workload(args.gpus)
+    cells = tuple(int(c) for c in args.cpu_cells.split("x"))
+    cb = time_cpu(max(args.steps, 1), max(args.warmup, 1), cells)
+    _, _, cfg = workload("shell", args.gpus)
+    cfg = dict(cfg)
+    # what is timed is the SAMPLE, not the 1M plate of the CUDA arm: say so in config itself
+    cfg.update({"workload": f"shell_plate_{cells[0]}x{cells[1]}cells_Shell_1 (bounded CPU sample of the {cfg['workload']} family)",
+                "elements": cb["sample_elements"], "per_gpu_elements": cb["sample_elements"],
+                "same_config_as_cuda_arm": False, "extrapolates_to": "elements/s of the full plate (see full_size_step for one measured step at 1M elements)"})
+    full = None
+    if not args.no_full_size_step:
+        # one real step of the reference at the CUDA arm's single-GPU size (1M shells fit in host memory)
+        try:
+            t0 = time.time()
+            threads = os.cpu_count() or 1
+            orc, kind = cpu_oracle(threads)
+            m = M.shell_plate(1000, 500)
+            d = M.shell_plate_displacements(m)
+            orc.load(m)
+            s = orc.assemble(d)
+            sec = float(s[:4].sum())
+            full = {"elements": int(m.n_elements), "seconds": sec, "value": m.n_elements / sec, "unit": UNIT, "steps": 1, "kind": kind,
+                    "phases_s": {"MountLocal": float(s[0]), "MountElementLoads": float(s[1]), "MountGlobal": float(s[2]), "MountSparse": float(s[3])},
+                    "wall_s_with_setup": time.time() - t0}
+        except Exception as e:      # noqa: BLE001  (host memory, 32-bit triplet counters of the reference ...)
+            full = {"error": repr(e)[:300]}
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": cb["note"] + "; each step is a bounded sample of the workload (throughput is size-independent: the path is O(elements))"}
+            "full_size_step": full,
+            "note": cb["note"] + "; value = the bounded sample; full_size_step = one measured step of the same code at the 1M-element plate"}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------
+class Runner:
+    """One workload on this rank's GPU: set-up, exchange buffers, timed loops."""
+
+    def __init__(self, m, d_host, rank, world, local_rank, dist):
+        import torch
+        from giraffe_b200 import capi
+        self.torch, self.capi, self.dist = torch, capi, dist
+        self.m, self.rank, self.world = m, rank, world
+        t0 = time.time()
+        self.asm = asm = capi.Assembler(m, device=local_rank, rank=rank, world=world)
+        self.gls, self.nf, self.nx = M.number_dofs(m)
+        asm.set_dofs(self.gls, self.nf, self.nx)
+        self.setup_s = time.time() - t0
+        self.d_host = d_host
+        self.d_dev = torch.from_numpy(np.ascontiguousarray(d_host).reshape(-1)).cuda()
+        self.lib_stream = torch.cuda.ExternalStream(asm.stream())
+        self.if_stream = torch.cuda.ExternalStream(asm.interface_stream())
+        self.send_cnt, self.recv_cnt = asm.interface_counts(world)
+        self.send_buf = torch.empty(int(self.send_cnt.sum()), dtype=torch.float64, device="cuda") if world > 1 else None
+        self.recv_buf = torch.empty(int(self.recv_cnt.sum()), dtype=torch.float64, device="cuda") if world > 1 else None
+        self.nnz = [asm.csr_dims(w)[2] for w in ("AA", "AB", "BA", "BB")]
+        self.eval_ms, self.scat_ms = [], []
+
+    def close(self):
+        self.asm.close()
+        self.d_dev = self.send_buf = self.recv_buf = None
+        self.torch.cuda.empty_cache()
+
+    def exchange(self):
+        """pack -> NCCL send/recv -> unpack, stream-ordered on the library's interface stream (no host syncs);
+        the library scatters the interface rows first, so the exchange overlaps the interior rows' scatter."""
+        if self.world == 1:
+            return
+        torch, dist = self.torch, self.dist
+        with torch.cuda.stream(self.if_stream):
+            self.asm.interface_pack(self.send_buf.data_ptr())
+            ops, so, ro = [], 0, 0
+            for r in range(self.world):
+                if self.send_cnt[r]:
+                    ops.append(dist.P2POp(dist.isend, self.send_buf[so:so + int(self.send_cnt[r])], r))
+                if self.recv_cnt[r]:
+                    ops.append(dist.P2POp(dist.irecv, self.recv_buf[ro:ro + int(self.recv_cnt[r])], r))
+                so += int(self.send_cnt[r]); ro += int(self.recv_cnt[r])
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            self.asm.interface_unpack(self.recv_buf.data_ptr())
+
+    def step_resident(self):
+        if self.world > 1:
+            # enqueue only: the host queues pack / NCCL / unpack behind the assembly instead of leaving the
+            # GPU idle while it catches up; reads of the results wait for the stream
+            self.asm.assemble_enqueue(self.d_dev.data_ptr())
+        else:
+            self.asm.assemble(None, device_ptr=self.d_dev.data_ptr())
+        self.exchange()
+
+    def step_resident_logged(self):
+        self.step_resident()
+        if self.world == 1:
+            t = self.asm.timing()
+            self.eval_ms.append(t["eval_ms"]); self.scat_ms.append(t["scatter_ms"])
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, host_side=False):
+        """Device time of `steps` calls: CUDA events on the library's stream, bracketed by barrier + synchronize;
+        max over ranks.  Paths with host-side pieces (exchange waits, D2H) take the larger of device and wall time."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.lib_stream)
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        e1.record(self.lib_stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        ms = max(ms, wall * 1e3) if (self.world > 1 or host_side) else ms
+        if self.dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def resident(self, steps, warmup):
+        for _ in range(max(warmup, 3)):
+            self.step_resident()
+        ms = self.timed(self.step_resident_logged, steps)
+        if self.world > 1:      # the timed loop of N > 1 does not read per-kernel times (that would wait for every step)
+            for _ in range(3):
+                self.step_resident()
+                t = self.asm.timing()
+                self.eval_ms.append(t["eval_ms"]); self.scat_ms.append(t["scatter_ms"])
+        return ms / steps
+
+    # ---- end to end through the C-ABI with HOST buffers ------------------------------------------------
+    def e2e(self, steps):
+        """Every step: H2D of the displacements of the nodes this rank's elements reference (pinned, packed),
+        the assembly, the interface exchange, D2H of this rank's CSR values (AA, AB, BA, BB) and of its owned
+        rows of P_A / I_A (+ P_B) into pinned host buffers -- what a host-side solver consumes."""
+        torch, asm, capi = self.torch, self.asm, self.capi
+        nodes = asm.touched_nodes()
+        packed = torch.empty(len(nodes) * 6, dtype=torch.float64).pin_memory()
+        packed.numpy()[:] = self.d_host.reshape(-1, 6)[nodes].reshape(-1)
+        owned = len(asm.owned_rows()) if self.world > 1 else self.nf
+        out_vals = [torch.empty(max(n, 1), dtype=torch.float64).pin_memory() for n in self.nnz]
+        out_vecs = [torch.empty(max(n, 1), dtype=torch.float64).pin_memory() for n in (owned, owned, self.nx)]
+
+        def step():
+            asm.set_displacements_packed(packed.data_ptr())
+            if self.world > 1:
+                asm.assemble_enqueue(None)
+            else:
+                asm.assemble(None)
+            self.exchange()
+            for w, buf, n in zip(("AA", "AB", "BA", "BB"), out_vals, self.nnz):
+                asm.values(w, out=buf.numpy()[:n])
+            for w, buf, n in zip((capi.P_A, capi.I_A, capi.P_B), out_vecs, (owned, owned, self.nx)):
+                asm.vector_owned(w, buf.numpy()[:n])
+
+        step()
+        ms = self.timed(step, steps, host_side=True) / steps
+        h2d = len(nodes) * 48
+        d2h = 8 * (sum(self.nnz) + 2 * owned + self.nx)
+        if self.dist is not None:      # whole-job bytes per step
+            t = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
+        return ms, h2d, d2h
+
+    # ---- parity probe ---------------------------------------------------------------------------------
+    def parity(self, n_nodes=24):
+        """Rows of sampled nodes -- those of this rank's first and last elements (the partition interfaces when
+        N > 1) and a few interior ones -- against a single-GPU assembly of all elements around them."""
+        from giraffe_b200 import capi
+        torch, asm, m = self.torch, self.asm, self.m
+        ptr, en = m.elem_ptr, m.elem_nodes
+        touched = asm.touched_nodes() + 1                       # 1-based ids of this rank's nodes
+        owned = set(int(r) for r in (asm.owned_rows() if self.world > 1 else []))
+        rng = np.random.default_rng(1000 + self.rank)
+        # candidates: nodes of the partition's boundary elements first, then random ones
+        first_last = np.concatenate([touched[:n_nodes], touched[-n_nodes:], rng.choice(touched, size=min(n_nodes, len(touched)), replace=False)])
+        sample = []
+        for nd in first_last:
+            g = self.gls[nd - 1]
+            free = g[g > 0]
+            if len(free) == 0:
+                continue
+            if self.world > 1 and not all(int(r - 1) in owned for r in free):
+                continue                                         # completed on another rank
+            sample.append(int(nd))
+            if len(sample) >= n_nodes:
+                break
+        ok, worst = True, 0.0
+        if sample:
+            elem_of_entry = np.repeat(np.arange(m.n_elements), np.diff(ptr))
+            elems = np.unique(elem_of_entry[np.isin(en, np.array(sample, np.int32))])
+            sub, nodes = M.submodel(m, elems)             # no constraints: every DOF of the sample is a free row there
+            dev = torch.cuda.current_device()
+            ref = capi.Assembler(sub, device=dev).set_dofs()
+            ref.gravity_factor = asm.gravity_factor
+            ref.assemble(self.d_host.reshape(-1, 6)[nodes - 1])
+            so, si, sv, _ = ref.csr("AA")
+            sgl = ref.gls
+            inv = {}                                             # sub free id -> (parent node, dof)
+            for i, nd in enumerate(nodes):
+                for k in range(6):
+                    if sgl[i, k] > 0:
+                        inv[int(sgl[i, k]) - 1] = (int(nd), k)
+            lo, li = asm.csr_pattern("AA")
+            lv = asm.values("AA")
+            rows = asm.local_rows() if self.world > 1 else None
+            pos = {int(r): i for i, r in enumerate(rows)} if rows is not None else None
+            sub_index = {int(nd): i for i, nd in enumerate(nodes)}
+            for nd in sample:
+                for k in range(6):
+                    g = int(self.gls[nd - 1, k])
+                    if g <= 0:
+                        continue
+                    i = pos[g - 1] if pos is not None else g - 1
+                    cols, vals = li[lo[i]:lo[i + 1]], lv[lo[i]:lo[i + 1]]
+                    got = dict(zip(cols.tolist(), vals.tolist()))
+                    srow = int(sgl[sub_index[nd], k]) - 1
+                    diag_r = abs(sv[so[srow]:so[srow + 1]][si[so[srow]:so[srow + 1]] == srow][0])
+                    for c, v in zip(si[so[srow]:so[srow + 1]].tolist(), sv[so[srow]:so[srow + 1]].tolist()):
+                        pn, pk = inv[c]
+                        gc = int(self.gls[pn - 1, pk])
+                        if gc <= 0:
+                            continue                             # fixed in the full model: lives in AB
+                        w = got.get(gc - 1)
+                        if w is None:
+                            ok = False
+                            continue
+                        dd = sv[so[c]:so[c + 1]][si[so[c]:so[c + 1]] == c]
+                        scale = 0.1 * float(np.sqrt(diag_r * abs(dd[0]))) if len(dd) else 0.0
+                        err = abs(v - w) / max(abs(v), abs(w), scale, 1e-300)
+                        worst = max(worst, err)
+            ref.close()
+            ok = ok and worst <= 1e-12
+        if self.dist is not None:
+            t = torch.tensor([0.0 if ok else 1.0, worst, float(len(sample))], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ok, worst = t[0].item() == 0.0, float(t[1].item())
+        return {"parity_ok": bool(ok), "worst_relative_error": worst, "sampled_nodes_per_rank": len(sample),
+                "what": "CSR rows of sampled nodes (first / last nodes of every rank's partition = its interfaces, plus random ones) vs a single-GPU assembly of the elements around them, tolerance 1e-12"}
+
+
 def run_cuda(args):
     import torch
-    from giraffe_b200 import capi
+    from giraffe_b200 import capi  # noqa: F401
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,170 +446,98 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cells = tuple(int(c) for c in args.cells.split("x"))
-    m, cfg = workload(world, cells)
-    d_host = M.shell_plate_displacements(m)
-    t0 = time.time()
-    asm = capi.Assembler(m, device=local_rank, rank=rank, world=world)
-    gls, nf, nx = M.number_dofs(m)
-    asm.set_dofs(gls, nf, nx)
-    setup_s = time.time() - t0
+    m, d_host, cfg = workload(args.workload, world, args.scaling, cells)
+    run = Runner(m, d_host, rank, world, local_rank, dist)
     n_el_total = m.n_elements
-
-    pinned = torch.empty(d_host.size, dtype=torch.float64).pin_memory()
-    pinned.numpy()[:] = d_host.reshape(-1)
-    d_dev = pinned.cuda(non_blocking=False)
-    lib_stream = torch.cuda.ExternalStream(asm.stream())
-    if_stream = torch.cuda.ExternalStream(asm.interface_stream())
-
-    # interface exchange buffers (N > 1)
-    send_cnt, recv_cnt = asm.interface_counts(world)
-    send_buf = torch.empty(int(send_cnt.sum()), dtype=torch.float64, device="cuda") if world > 1 else None
-    recv_buf = torch.empty(int(recv_cnt.sum()), dtype=torch.float64, device="cuda") if world > 1 else None
-
-    def exchange():
-        """pack -> NCCL send/recv -> unpack, stream-ordered on the library's interface stream (no host syncs);
-        the library scatters the interface rows first, so the exchange overlaps the interior rows' scatter."""
-        if world == 1:
-            return
-        with torch.cuda.stream(if_stream):
-            asm.interface_pack(send_buf.data_ptr())
-            ops, so, ro = [], 0, 0
-            for r in range(world):
-                if send_cnt[r]:
-                    ops.append(dist.P2POp(dist.isend, send_buf[so:so + int(send_cnt[r])], r))
-                if recv_cnt[r]:
-                    ops.append(dist.P2POp(dist.irecv, recv_buf[ro:ro + int(recv_cnt[r])], r))
-                so += int(send_cnt[r]); ro += int(recv_cnt[r])
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            asm.interface_unpack(recv_buf.data_ptr())
-
-    def step_resident():
-        if world > 1:
-            # enqueue only: the host queues pack / NCCL / unpack behind the assembly instead of leaving the
-            # GPU idle while it catches up; reads of the results wait for the stream
-            asm.assemble_enqueue(d_dev.data_ptr())
-        else:
-            asm.assemble(None, device_ptr=d_dev.data_ptr())
-        exchange()
-
-    # results land here in the end-to-end leg (what the host-side solver consumes)
-    nnz = [asm.csr_dims(w)[2] for w in ("AA", "AB", "BA", "BB")]
-    out_vals = [torch.empty(max(n, 1), dtype=torch.float64).pin_memory() for n in nnz]
-    out_vecs = [torch.empty(max(n, 1), dtype=torch.float64).pin_memory() for n in (nf, nf, nx)]
-
-    def step_e2e():
-        asm.assemble_raw(pinned.data_ptr())          # H2D of the displacements inside the call
-        exchange()
-        for w, buf in zip(("AA", "AB", "BA", "BB"), out_vals):
-            asm.values(w, out=buf.numpy()[:asm.csr_dims(w)[2]])
-        for w, buf, n in zip((capi.P_A, capi.I_A, capi.P_B), out_vecs, (nf, nf, nx)):
-            asm.vector(w, buf.numpy()[:n])
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        """Device time of `steps` calls: CUDA events on the library's stream,
-        bracketed by barrier + synchronize; max over ranks."""
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(lib_stream)
-        w0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        e1.record(lib_stream)
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - w0
-        barrier()
-        ms = e0.elapsed_time(e1)
-        # host-side pieces (exchange waits, D2H) are not on the library stream: take the larger
-        ms = max(ms, wall * 1e3) if (world > 1 or fn is step_e2e) else ms
-        if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    eval_ms, scat_ms = [], []
-
-    def step_resident_logged():
-        step_resident()
-        if world == 1:
-            t = asm.timing()
-            eval_ms.append(t["eval_ms"]); scat_ms.append(t["scatter_ms"])
-
-    def sample_kernel_times():
-        """N > 1: the timed loop does not read per-kernel times (that would wait for every step)."""
-        for _ in range(3):
-            step_resident()
-            t = asm.timing()
-            eval_ms.append(t["eval_ms"]); scat_ms.append(t["scatter_ms"])
-
-    ms = timed(step_resident_logged, args.steps)
+    ms_per_step = run.resident(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        sample_kernel_times()
-    launches = asm.launch_count() * args.steps + (2 * args.steps if world > 1 else 0)
-    ms_per_step = ms / args.steps
+    launches = run.asm.launch_count() * args.steps + (2 * args.steps if world > 1 else 0)
     value = n_el_total / (ms_per_step * 1e-3)
-
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    step_e2e()
-    e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
-    h2d = d_host.size * 8
-    d2h = 8 * (sum(nnz) + 2 * nf + nx)
+    e2e_ms, h2d, d2h = run.e2e(e2e_steps)
+    par = run.parity()
+    ring, pipeline = run.asm.pipeline_info()
+    nnz, nf, nx = run.nnz, run.nf, run.nx
+    ev, sc = float(np.mean(run.eval_ms)), float(np.mean(run.scat_ms))
+    owned_free = len(run.asm.owned_rows()) if world > 1 else nf
+    alg_bytes = algorithmic_bytes(m, nnz[0], owned_free, world)
+    setup_s = run.setup_s
+    run.close()
+
+    # ---- the other BASELINE configs, same protocol, fewer steps ------------------------------------------
+    side = []
+    if not args.no_side_configs and args.workload == "shell" and args.scaling == "weak":
+        plan = [("beam", "weak"), ("solid", "weak"), ("mixed", "weak")] if world == 1 else [("shell", "strong"), ("mixed", "weak")]
+        for kind, scaling in plan:
+            try:
+                sm, sd, scfg = workload(kind, world, scaling, cells)
+                r2 = Runner(sm, sd, rank, world, local_rank, dist)
+                steps2 = max(3, min(args.steps, 20))
+                ms2 = r2.resident(steps2, 3)
+                p2 = r2.parity(12)
+                e2, s2 = float(np.mean(r2.eval_ms)), float(np.mean(r2.scat_ms))
+                ofree = len(r2.asm.owned_rows()) if world > 1 else r2.nf
+                ab = algorithmic_bytes(sm, r2.nnz[0], ofree, world)
+                entry = {"config": scfg, "value": sm.n_elements / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": steps2,
+                         "kernels_ms_rank0": {"evaluation": e2, "scatter": s2}, "nnz_AA_rank0": r2.nnz[0], "setup_seconds": r2.setup_s,
+                         "gpu_launches_per_step": r2.asm.launch_count(),
+                         "hbm_roofline": {"achieved_gbs": ab / ((e2 + s2) * 1e-3) / 1e9, "algorithmic_bytes_per_step_rank0": ab},
+                         "parity_ok": p2["parity_ok"], "parity_worst": p2["worst_relative_error"]}
+                r2.close()
+                side.append(entry)
+            except Exception as e:      # noqa: BLE001  (a side config must not take the headline down)
+                side.append({"config": {"workload": kind, "scaling": scaling}, "error": repr(e)[:300]})
 
     if rank == 0:
         pk, pk_src = peaks()
-        n_local = n_el_total // world
-        nnz_local = nnz[0]                      # csr_dims are this rank's stored rows
-        alg_bytes = n_local * (SHELL_READ_BYTES) + 8.0 * nnz_local + 16.0 * nf / world
-        ev, sc = float(np.mean(eval_ms)), float(np.mean(scat_ms))
-        # The path is two launches per step (element evaluation, then the CSR gather); the
-        # algorithmic bytes of SURVEY.md 8(d) belong to the pair, so the roofline is taken over
-        # both kernels' device time (CUDA events on the library's stream, gfa_last_timing).
-        dom = "shell::eval_kernel + scatter_kernel (one step = these two launches)"
+        # One step is two launches (element evaluation, then the CSR scatter); the algorithmic bytes of SURVEY.md 8(d)
+        # belong to the pair, so the roofline is taken over both kernels' device time (CUDA events on the library's
+        # stream, gfa_last_timing).
+        dom = "shell::eval_kernel + scatter_kernel (one step = these two launches)" if not ring else "ring pipeline (evaluation + scatter kernels, co-resident)"
         dom_ms = ev + sc
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj.get("elements") == n_local:
-                traffic = tj["dram_bytes_per_step"]
-        fp64_peak = 34.16      # measured on this pool with tools/fp64_peak.cu (profiles/fp64_peak_r01.json)
+        tj = profile_file("traffic_r02.json") or profile_file("traffic_r01.json")
+        traffic, traffic_src = None, None
+        if tj and tj.get("elements") == n_el_total // world and tj.get("pipeline", "classic") == ("ring" if ring else "classic"):
+            traffic = tj["dram_bytes_per_step"]
+            traffic_src = tj.get("source", "profiles/traffic_r01.json") + " (ncu capture of this command, not re-measured in this run)"
+        fpk = profile_file("fp64_peak_r01.json") or {}
+        fp64_peak = float(fpk.get("fp64_fma_tflops", fpk.get("tflops", 34.16)))
+        evp = profile_file("eval_pipe_r02.json") or {}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cb = time_cpu(3, 1)
+            cb = time_cpu(3, 1, tuple(int(c) for c in args.cpu_cells.split("x")))
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             cpu["mount_local_only_elements_per_s"] = cb["mount_local_only_elements_per_s"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg,
             "e2e": {"value": n_el_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "what": "gfa_assemble from pinned host displacements + D2H of all CSR values (AA,AB,BA,BB) and P_A,I_A,P_B"},
+                    "ms_per_step": e2e_ms,
+                    "what": "per rank: pinned H2D of the displacements of the nodes its elements reference, gfa_assemble, interface exchange, "
+                            "D2H of its CSR values (AA,AB,BA,BB) and its owned rows of P_A, I_A (+P_B); bytes are whole-job sums"},
             "gpu_launches": launches,
             "clocks": clocks,
+            "parity_ok": par["parity_ok"], "parity": par,
+            "pipeline": pipeline,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": traffic, "kernel": dom, "peak_source": pk_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": dom, "peak_source": pk_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
-                         "note": "algorithmic bytes of the path (SURVEY.md 8d: 928 B read/element + 8 B per CSR non-zero + 16 B per free DOF); traffic = ncu dram bytes of both launches"},
-            "fp64_roofline": {"bound": "fp64", "achieved": n_local * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                              "frac": n_local * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12 / fp64_peak, "kernel": "shell::eval_kernel",
-                              "note": "5.0e4 algorithmic flops per Shell_1 element (SURVEY.md 8d) over the evaluation kernel; peak = measured FP64 FMA rate"},
-            "kernels_ms": {"shell_eval": ev, "scatter": sc},
+                         "note": "algorithmic bytes of the path on rank 0 (SURVEY.md 8d: compulsory reads per element + 8 B per CSR non-zero + 16 B per owned free DOF) "
+                                 "over the device time of the step's kernels"},
+            "fp64_roofline": {"bound": "fp64", "achieved": (n_el_total // world) * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": (n_el_total // world) * SHELL_ALG_FLOPS / (ev * 1e-3) / 1e12 / fp64_peak, "kernel": "shell::eval_kernel",
+                              "peak_source": "tools/fp64_peak.cu on this pool (profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry",
+                              "ncu_fp64_pipe_busy_pct": evp.get("fp64_pipe_busy_pct"), "ncu_executed_fp64_thread_instructions_per_element": evp.get("fp64_thread_inst_per_element"),
+                              "note": "numerator = 5.0e4 ALGORITHMIC flops per Shell_1 element (SURVEY.md 8d), more than the kernel executes: the structure-exploiting "
+                                      "kernel issues fewer, so this fraction overstates pipe use -- ncu's pipe-busy figure beside it is the utilisation"} if args.workload == "shell" else None,
+            "kernels_ms": {"evaluation": ev, "scatter": sc},
             "cpu_baseline": cpu,
+            "side_configs": side,
             "setup_seconds": setup_s,
             "nnz_AA": nnz[0], "n_free": nf,
         }
@@ -347,9 +552,14 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="shell", choices=["shell", "beam", "solid", "mixed"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cells", default="1000x500", help="per-GPU plate size in cells (2 Shell_1 per cell)")
+    ap.add_argument("--cpu-cells", default="100x50", help="plate of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true")
+    ap.add_argument("--no-full-size-step", action="store_true", help="reference arm: skip the one 1M-element step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

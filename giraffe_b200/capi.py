@@ -30,7 +30,7 @@ EXPORTS = [
     "gfa_residual", "gfa_update_displacements", "gfa_displacements", "gfa_copy_coordinates", "gfa_last_timing", "gfa_last_launch_count",
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
     "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue", "gfa_interface_stream",
-    "gfa_pipeline_info",
+    "gfa_pipeline_info", "gfa_touched_nodes", "gfa_set_displacements_packed", "gfa_vector_owned",
 ]
 
 
@@ -124,6 +124,9 @@ def load_library() -> C.CDLL:
         lib.gfa_assemble_dynamic.argtypes = [C.c_void_p, C.POINTER(_StepStruct), C.POINTER(_DynamicStruct)]
         lib.gfa_element_alpha_i.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.gfa_pipeline_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+        lib.gfa_touched_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+        lib.gfa_set_displacements_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        lib.gfa_vector_owned.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -442,6 +445,24 @@ class Assembler:
         rows = np.zeros(n.value, np.int32)
         self._check(self.lib.gfa_owned_rows(self._h, C.byref(n), _ptr(rows)))
         return rows
+
+    # ---- partition-local transfers -----------------------------------------
+    def touched_nodes(self):
+        """0-based indices of the nodes this rank's elements reference (ascending)"""
+        n = C.c_int64()
+        self._check(self.lib.gfa_touched_nodes(self._h, C.byref(n), None))
+        nodes = np.zeros(n.value, np.int32)
+        self._check(self.lib.gfa_touched_nodes(self._h, C.byref(n), _ptr(nodes)))
+        return nodes
+
+    def set_displacements_packed(self, ptr: int, on_device: bool = False):
+        """Node::displacements of the touched nodes only, [n_touched*6], raw host (e.g. pinned) or device pointer"""
+        self._check(self.lib.gfa_set_displacements_packed(self._h, ptr, 1 if on_device else 0))
+
+    def vector_owned(self, which_vector, out):
+        """P_A / I_A entries of the rows this rank owns (order of owned_rows()); P_B whole"""
+        self._check(self.lib.gfa_vector_owned(self._h, which_vector, _ptr(out)))
+        return out
 
     def stream(self) -> int:
         p = C.c_void_p()

@@ -163,6 +163,11 @@ struct gfa_handle {
     std::vector<long long> send_cnt, recv_cnt;
     DevBuf<long long> d_send_idx, d_recv_idx;
     std::vector<int> owned_rows;
+    // partition-local transfers: nodes this rank's elements reference, staging for the packed upload, owned-row gather
+    std::vector<int> touched_nodes;
+    DevBuf<int> d_touched_nodes;
+    DevBuf<double> d_packed;
+    DevBuf<long long> d_owned_idx;
 
     // ring pipeline (fused evaluation + scatter, FusedArgs in gfa_device.h); `ring` false = classic two-kernel path
     bool ring = false, force_classic = false;
@@ -306,6 +311,13 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
                 h->tb[s].elems.push_back(e);
             }
         }
+    }
+    {   // nodes referenced by this rank's elements (gfa_touched_nodes)
+        std::vector<unsigned char> used((size_t)m->n_nodes, 0);
+        for (int sl = 0; sl < 3; sl++)
+            for (int e : h->tb[sl].elems)
+                for (int k = h->el_ptr[e]; k < h->el_ptr[e + 1]; k++) used[(size_t)h->el_nodes[k]] = 1;
+        for (int i = 0; i < m->n_nodes; i++) if (used[i] || h->world == 1) h->touched_nodes.push_back(i);
     }
     // ---- per-type tables and property rows -------------------------------
     std::vector<double> state_init[3];
@@ -492,6 +504,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     if (!h || !GLs) return fail(GFA_EINVAL, "gfa_set_dofs: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     h->dofs_set = false; h->assembled = false;
+    h->d_owned_idx.release();
     h->n_free = n_free; h->n_fixed = n_fixed;
     h->gls.assign(GLs, GLs + 6 * (size_t)h->n_nodes);
     const std::vector<int>& gls = h->gls;
@@ -1812,6 +1825,46 @@ int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out) {
     if (n_rows) *n_rows = (int64_t)h->owned_rows.size();
     if (rows_out && !h->owned_rows.empty()) std::memcpy(rows_out, h->owned_rows.data(), h->owned_rows.size() * sizeof(int));
     return GFA_OK;
+}
+int gfa_touched_nodes(gfa_t* h, int64_t* n_nodes, int32_t* nodes_out) {
+    if (!h) return fail(GFA_EINVAL, "gfa_touched_nodes: null handle");
+    if (n_nodes) *n_nodes = (int64_t)h->touched_nodes.size();
+    if (nodes_out && !h->touched_nodes.empty()) std::memcpy(nodes_out, h->touched_nodes.data(), h->touched_nodes.size() * sizeof(int));
+    return GFA_OK;
+}
+int gfa_set_displacements_packed(gfa_t* h, const double* packed, int32_t on_device) {
+    if (!h || !packed) return fail(GFA_EINVAL, "gfa_set_displacements_packed: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = h->touched_nodes.size();
+    if (h->d_touched_nodes.n != n) CUDA_TRY(h->d_touched_nodes.upload(h->touched_nodes));
+    const double* src = packed;
+    if (!on_device) {
+        if (h->d_packed.n != 6 * n) CUDA_TRY(h->d_packed.alloc(6 * n));
+        CUDA_TRY(cudaMemcpyAsync(h->d_packed.p, packed, 6 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        src = h->d_packed.p;
+    }
+    launch_unpack_nodes(h->d_disp.p, h->d_touched_nodes.p, src, (long long)n, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    return GFA_OK;       // stream-ordered: the next gfa_assemble (displacements == NULL) runs behind it
+}
+int gfa_vector_owned(gfa_t* h, int wv, double* out) {
+    if (!h || wv < 0 || wv > 2 || !out) return fail(GFA_EINVAL, "gfa_vector_owned: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_vector_owned before gfa_assemble");
+    if (wv == GFA_P_B || h->world == 1) return gfa_vector(h, wv, out);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = h->owned_rows.size();
+    if (n == 0) return GFA_OK;
+    if (h->d_owned_idx.n != n) {
+        std::vector<long long> idx(n);
+        for (size_t i = 0; i < n; i++) idx[i] = (long long)h->owned_rows[i];
+        CUDA_TRY(h->d_owned_idx.upload(idx));
+    }
+    if (h->d_packed.n < n) CUDA_TRY(h->d_packed.alloc(std::max(n, 6 * h->touched_nodes.size())));
+    launch_pack(h->d_arena.p + h->vec_off[wv], h->d_owned_idx.p, h->d_packed.p, (long long)n, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_packed.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return check_abort(h);
 }
 int gfa_interface_stream(gfa_t* h, void** out) {
     if (!h || !out) return fail(GFA_EINVAL, "gfa_interface_stream: bad argument");

@@ -258,6 +258,7 @@ int fused_buffers(int type_slot);                            // record buffers (
 void launch_gather(const GatherArgs& a, void* stream);
 void launch_add_slots(double* vals, const long long* slots, const double* add, long long n, void* stream);
 void launch_pack(const double* vals, const long long* idx, double* buf, long long n, void* stream);
+void launch_unpack_nodes(double* disp, const int* nodes, const double* packed, long long n_nodes, void* stream);   // disp[nodes[i]*6 + k] = packed[i*6 + k]
 void launch_unpack_add(double* vals, const long long* idx, const double* buf, long long n, void* stream);
 int configure_kernels();   // opt-in shared memory sizes; returns cudaError_t as int
 

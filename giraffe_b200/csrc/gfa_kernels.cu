@@ -175,17 +175,22 @@ GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Frame& fr, const
     double gu1[3], gu2[3], ga[3], ga1[3], ga2[3];
 #pragma unroll
     for (int n = 0; n < 6; n++) {
-        const double* d = A.disp + 6 * (size_t)nd[n];
+        // a node's six increments are one 48-byte record, 16-byte aligned: three (corner nodes: two) vector loads
+        const double2* d = reinterpret_cast<const double2*>(A.disp + 6 * (size_t)nd[n]);
+        const double2 u01 = __ldg(d), u2r0 = __ldg(d + 1);
+        const double u[3] = { u01.x, u01.y, u2r0.x };
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double v = __ldg(d + c);
+            const double v = u[c];
             gu1[c] = n == 0 ? s_mul(v, s.N1[0]) : s_add(gu1[c], s_mul(v, s.N1[n]));
             gu2[c] = n == 0 ? s_mul(v, s.N2[0]) : s_add(gu2[c], s_mul(v, s.N2[n]));
         }
         if (n >= 3) {
+            const double2 r12 = __ldg(d + 2);
+            const double rr[3] = { u2r0.y, r12.x, r12.y };
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const double r = __ldg(d + 3 + c);
+                const double r = rr[c];
                 ga[c] = n == 3 ? s_mul(r, s.A0[0]) : s_add(ga[c], s_mul(r, s.A0[n - 3]));
                 ga1[c] = n == 3 ? s_mul(r, s.A1[0]) : s_add(ga1[c], s_mul(r, s.A1[n - 3]));
                 ga2[c] = n == 3 ? s_mul(r, s.A2[0]) : s_add(ga2[c], s_mul(r, s.A2[n - 3]));
@@ -882,10 +887,13 @@ GFA_DI void interpolate(const EvalArgs& A, const int* nd, const Geo& go, Kin& k)
     double ga[3], gda[3], gdu[3];
 #pragma unroll
     for (int n = 0; n < 3; n++) {
-        const double* d = A.disp + 6 * (size_t)nd[n];
+        // one 48-byte record per node, 16-byte aligned: three vector loads
+        const double2* d = reinterpret_cast<const double2*>(A.disp + 6 * (size_t)nd[n]);
+        const double2 u01 = __ldg(d), u2r0 = __ldg(d + 1), r12 = __ldg(d + 2);
+        const double uu[3] = { u01.x, u01.y, u2r0.x }, rr[3] = { u2r0.y, r12.x, r12.y };
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const double r = __ldg(d + 3 + c), u = __ldg(d + c);
+            const double r = rr[c], u = uu[c];
             ga[c] = n == 0 ? s_mul(r, go.N[0]) : s_add(ga[c], s_mul(r, go.N[n]));
             gda[c] = n == 0 ? s_mul(r, go.dN[0]) : s_add(gda[c], s_mul(r, go.dN[n]));
             gdu[c] = n == 0 ? s_mul(u, go.dN[0]) : s_add(gdu[c], s_mul(u, go.dN[n]));
@@ -1490,6 +1498,10 @@ __global__ void pack_kernel(const double* vals, const long long* idx, double* bu
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) buf[i] = vals[idx[i]];
 }
+__global__ void unpack_nodes_kernel(double* disp, const int* nodes, const double* packed, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6 * n) disp[6 * (size_t)nodes[i / 6] + i % 6] = packed[i];
+}
 __global__ void unpack_add_kernel(double* vals, const long long* idx, const double* buf, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) vals[idx[i]] += buf[i];
@@ -2013,6 +2025,10 @@ void launch_add_slots(double* vals, const long long* slots, const double* add, l
 void launch_pack(const double* vals, const long long* idx, double* buf, long long n, void* s) {
     if (n <= 0) return;
     pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(vals, idx, buf, n);
+}
+void launch_unpack_nodes(double* disp, const int* nodes, const double* packed, long long n, void* s) {
+    if (n <= 0) return;
+    unpack_nodes_kernel<<<(unsigned)((6 * n + 255) / 256), 256, 0, (cudaStream_t)s>>>(disp, nodes, packed, n);
 }
 void launch_unpack_add(double* vals, const long long* idx, const double* buf, long long n, void* s) {
     if (n <= 0) return;

@@ -351,6 +351,25 @@ def concat_models(parts: list[Model]) -> Model:
     return _finish(m)
 
 
+def submodel(m: Model, elems) -> tuple[Model, np.ndarray]:
+    """Sub-model made of the listed elements only (0-based indices; same node coordinates, no constraints);
+    returns it with the 1-based ids of its nodes in the parent model."""
+    ptr = m.elem_ptr
+    elems = np.asarray(elems, np.int64)
+    nodes = np.unique(np.concatenate([m.elem_nodes[ptr[e]:ptr[e + 1]] for e in elems]))
+    remap = np.zeros(m.n_nodes + 1, np.int32)
+    remap[nodes] = np.arange(1, len(nodes) + 1, dtype=np.int32)
+    sub = Model(xyz=m.xyz[nodes - 1], hooke=m.hooke, sections=m.sections)
+    sub.section_defs, sub.shell_thickness, sub.cs_defs = m.section_defs, m.shell_thickness, m.cs_defs
+    sub.pipe_sections = getattr(m, "pipe_sections", np.zeros((0, 11)))
+    sub.elem_type, sub.elem_mat = m.elem_type[elems], m.elem_mat[elems]
+    sub.elem_sec, sub.elem_cs = m.elem_sec[elems], m.elem_cs[elems]
+    sub.elem_nodes = np.concatenate([remap[m.elem_nodes[ptr[e]:ptr[e + 1]]] for e in elems]).astype(np.int32)
+    sub.pretension = None if m.pretension is None else np.asarray(m.pretension)[elems]
+    sub.gravity = m.gravity
+    return _finish(sub), nodes
+
+
 def mixed_model(n_beam: int, shell_nx: int, shell_ny: int, solid_n: tuple) -> Model:
     return concat_models([beam_line(n_beam), shell_plate(shell_nx, shell_ny), solid_block(*solid_n)])
 

@@ -308,6 +308,17 @@ int gfa_local_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out /* may be NULL *
  * rank after the exchange; every row is owned by exactly one rank */
 int gfa_owned_rows(gfa_t* h, int64_t* n_rows, int32_t* rows_out /* may be NULL */);
 
+/* ---- partition-local transfers: what one rank of a partitioned run has to move per iteration ----------
+ * gfa_touched_nodes: the nodes this rank's elements reference (0-based indices into the displacement array,
+ * ascending; every node with one rank).  gfa_set_displacements_packed uploads Node::displacements of exactly those
+ * nodes ([n_touched*6], host or device pointer) into the device copy -- a following gfa_assemble with
+ * step.displacements == NULL evaluates them -- so that the host-to-device bytes of an iteration do not grow with the
+ * number of ranks.  gfa_vector_owned returns the entries of P_A / I_A for the rows this rank owns (order of
+ * gfa_owned_rows; with GFA_P_B: the whole vector, it is small): the residual is row-distributed like the matrix. */
+int gfa_touched_nodes(gfa_t* h, int64_t* n_nodes, int32_t* nodes_out /* may be NULL */);
+int gfa_set_displacements_packed(gfa_t* h, const double* packed, int32_t on_device);
+int gfa_vector_owned(gfa_t* h, int which_vector, double* host_out);
+
 /* Raw stream the library launches on (cudaStream_t), for callers that time
  * or order their own work against it. */
 int gfa_stream(gfa_t* h, void** stream_out);

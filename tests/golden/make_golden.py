@@ -100,6 +100,48 @@ def sequence(R, m, disp_fn, name, scale2=0.6):
     print(name, "n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
 
 
+def shipped_shell_mesh(R, name):
+    """A shell mesh the reference ships (inputs/tutorial05: 400 Shell_1, SURVEY.md 7's minimum slice;
+    inputs/tutorial02: 3036 Shell_1), read with giraffe_b200/inp.py and assembled by the reference's own sources at
+    seeded nodal increments: an iteration, a commit, a second iteration.  tutorial05 keeps every CSR value;
+    tutorial02 (1.6 M non-zeros per capture) keeps the pattern digest, the vectors, the row sums of AA (one
+    misplaced, missing or doubled value changes one of them) and 20 000 sampled values."""
+    import hashlib
+    m, info = read_inp(f"/root/reference/inputs/{name}/{name}.inp")
+    R.load(m)
+    R.set_time(0.0, 0.5)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([0.0, 0.5])
+    z["gls"] = R.gls()
+    rng = np.random.default_rng(20240031)
+    d1 = M.mask_displacements(m, np.concatenate([rng.uniform(-2e-4, 2e-4, (m.n_nodes, 3)), rng.uniform(-5e-3, 5e-3, (m.n_nodes, 3))], axis=1))
+    full = m.n_elements <= 500
+    for tag, d, commit_after in (("it1", d1, True), ("it2", -0.4 * d1, False)):
+        R.assemble(d)
+        z[f"{tag}_disp"] = d.copy()
+        if full:
+            z.update(util.capture(R, tag))
+        else:
+            o, i, v, s = R.csr("AA")
+            z[f"{tag}_AA_shape"] = np.array(s)
+            z[f"{tag}_AA_pattern_sha256"] = np.frombuffer(hashlib.sha256(o.tobytes() + i.tobytes()).digest(), np.uint8)
+            rows = np.repeat(np.arange(s[0]), np.diff(o))
+            z[f"{tag}_AA_rowsum"] = np.bincount(rows, weights=v, minlength=s[0])
+            z[f"{tag}_AA_rowabs"] = np.bincount(rows, weights=np.abs(v), minlength=s[0])
+            z[f"{tag}_AA_diag"] = util.csr_diag((o, i, v, s))
+            pick = np.sort(rng.choice(len(v), size=20000, replace=False))
+            z[f"{tag}_AA_sample_idx"], z[f"{tag}_AA_sample_val"] = pick, v[pick]
+            z[f"{tag}_nnz"] = np.array([len(R.csr(w)[2]) for w in ("AA", "AB", "BA", "BB")])
+            pa, ia, pb = R.vectors()
+            z[f"{tag}_PA"], z[f"{tag}_IA"], z[f"{tag}_PB"] = pa, ia, pb
+        K, P, en = R.element(m.n_elements // 2)
+        z[f"{tag}_elem_K"], z[f"{tag}_elem_P"] = K, P
+        if commit_after:
+            R.commit()
+    np.savez_compressed(os.path.join(OUT, name + "_shells.npz"), **z)
+    print(name, "elements", m.n_elements, "n_free", R.n_free, "nnz_AA", len(R.csr("AA")[2]))
+
+
 def newton_steps(R):
     """The vector steps either side of the assembly, through the reference's own code (Static.cpp:210-217,
     ConvergenceCriteria.cpp, Solution::UpdateDisps): a beam + shell model with a prescribed-displacement set."""
@@ -192,10 +234,16 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["shell_load"]:
         shell_load(R)
         sys.exit(0)
+    if sys.argv[1:] == ["shipped"]:
+        shipped_shell_mesh(R, "tutorial05")
+        shipped_shell_mesh(R, "tutorial02")
+        sys.exit(0)
     shell_load(R)
     dynamic(R)
     newton_steps(R)
     tutorial01(R)
+    shipped_shell_mesh(R, "tutorial05")
+    shipped_shell_mesh(R, "tutorial02")
     mb = M.beam_line(24, pretension=2.0e5)
     mb.gravity = (0.4, -0.3, -9.81)
     sequence(R, mb, M.beam_line_displacements, "beam_line")

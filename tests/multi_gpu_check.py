@@ -36,6 +36,9 @@ def main():
         ("mixed", M.concat_models([M.beam_line(40), M.shell_plate(9, 8), M.solid_block(4, 4, 3)])),
     ]
     cases.append(("dynamic", M.concat_models([M.beam_line(30), M.shell_plate(12, 9, warp=0.01, gravity=(0.0, 0.0, -9.81))])))
+    # the ring pipeline on a partitioned model: elements that touch a partition interface are pinned and evaluated
+    # first, so that their rows are scattered, packed and sent before the ring kernels start
+    cases.append(("shell-ring", M.shell_plate(60, 40, warp=0.01, gravity=(0.0, 0.0, -9.81))))
     ok = True
     for name, m in cases:
         d = M.mask_displacements(m, np.random.default_rng(7).uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
@@ -55,7 +58,13 @@ def main():
             port.assemble(d)
         ro, ri, rv, _ = port.csr("AA")
         rpa, ria, rpb = port.vectors()
+        if name == "shell-ring":
+            os.environ.update(GFA_RING="1", GFA_RING_CHUNK_KB="512")
+        else:
+            os.environ.pop("GFA_RING", None)
         asm = capi.Assembler(m, device=local, rank=rank, world=world).set_dofs()
+        if name == "shell-ring":
+            assert asm.pipeline_info()[0], asm.pipeline_info()[1]
         asm.set_time(0.0, 1.0)
         ex = InterfaceExchange(asm, world)
         if dynamic:

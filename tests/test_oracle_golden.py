@@ -159,3 +159,15 @@ def test_shell_load_host_contributor(port):
         util.assert_parity(z[f"{tag}_PB"], pb, f"shell_load {tag} P_B")
         if commit:
             port.commit()
+
+
+@pytest.mark.parametrize("name", ["tutorial05", "tutorial02"])
+def test_shipped_shell_meshes(port, name):
+    """inputs/tutorial05 (400 Shell_1) and inputs/tutorial02 (3036 Shell_1) as the reference ships them, assembled by
+    the reference's own sources (fixture) and by the oracle port: pattern, values, vectors, a commit in between."""
+    z = np.load(os.path.join(util.GOLDEN_DIR, name + "_shells.npz"))
+    m = util.model_from_dict(z)
+    port.load(m)
+    assert (port.gls() == z["gls"]).all()
+    port.set_time(*z["time"])
+    util.check_shipped_shell_mesh(z, port, f"{name} (port)")

@@ -415,3 +415,36 @@ def shell_load_contribution(m: M.Model, gls: np.ndarray, disp: np.ndarray, copy:
                         continue
                     trip[w][0].append(r); trip[w][1].append(cc); trip[w][2].append(K[i, j])
     return trip, pa, pb
+
+
+# ---- shell meshes the reference ships (tests/golden/tutorial05_shells.npz, tutorial02_shells.npz) ----------
+def check_shipped_shell_mesh(z, backend, what: str):
+    """Replay the fixture's two iterations (with the commit in between) on `backend` (the oracle port or the CUDA
+    Assembler) and compare with what the reference's own sources produced: every CSR value when the fixture
+    holds them (tutorial05), otherwise the pattern digest, the vectors, AA's row sums, diagonal and 20 000
+    sampled values (tutorial02)."""
+    import hashlib
+    full = "it1_AA_val" in z
+    for tag, commit_after in (("it1", True), ("it2", False)):
+        backend.assemble(z[f"{tag}_disp"])
+        if full:
+            assert_system_parity(lambda w: captured_csr(z, tag, w), backend.csr, f"{what} {tag}")
+        else:
+            o, i, v, s = backend.csr("AA")
+            assert tuple(s) == tuple(z[f"{tag}_AA_shape"])
+            digest = np.frombuffer(hashlib.sha256(o.tobytes() + i.tobytes()).digest(), np.uint8)
+            assert (digest == z[f"{tag}_AA_pattern_sha256"]).all(), f"{what} {tag}: AA pattern differs from the reference's"
+            assert [len(backend.csr(w)[2]) for w in ("AA", "AB", "BA", "BB")] == list(z[f"{tag}_nnz"])
+            diag = z[f"{tag}_AA_diag"]
+            rows = np.repeat(np.arange(s[0]), np.diff(o))
+            pick = z[f"{tag}_AA_sample_idx"]
+            scale = np.sqrt(diag[rows[pick]] * diag[i[pick]])
+            assert_parity(z[f"{tag}_AA_sample_val"], v[pick], f"{what} {tag} sampled AA values", scale)
+            # row sums: every value of a row enters; errors of 1e-12 relative to the row's absolute sum
+            rs = np.bincount(rows, weights=v, minlength=s[0])
+            assert_parity(z[f"{tag}_AA_rowsum"], rs, f"{what} {tag} AA row sums", 10.0 * z[f"{tag}_AA_rowabs"])
+            assert_parity(diag, csr_diag((o, i, v, s)), f"{what} {tag} AA diagonal")
+        for v, key in zip(backend.vectors(), ("PA", "IA", "PB")):
+            assert_parity(z[f"{tag}_{key}"], v, f"{what} {tag} {key}")
+        if commit_after:
+            backend.commit()
