@@ -361,8 +361,18 @@ class Runner:
         touched = asm.touched_nodes() + 1                       # 1-based ids of this rank's nodes
         owned = set(int(r) for r in (asm.owned_rows() if self.world > 1 else []))
         rng = np.random.default_rng(1000 + self.rank)
-        # candidates: nodes of the partition's boundary elements first, then random ones
-        first_last = np.concatenate([touched[:n_nodes], touched[-n_nodes:], rng.choice(touched, size=min(n_nodes, len(touched)), replace=False)])
+        # candidates: the nodes of the first and last elements of this rank's range of every element type (the library
+        # partitions each type by contiguous ranges, gfa_create) -- the partition interfaces when N > 1 -- then random ones
+        cand = []
+        slot = np.where((m.elem_type == M.BEAM_1) | (m.elem_type == M.PIPE_1), 1, np.where(m.elem_type == M.SHELL_1, 0, 2))
+        for sl in range(3):
+            idx = np.nonzero(slot == sl)[0]
+            if len(idx) == 0:
+                continue
+            lo, hi = len(idx) * self.rank // self.world, len(idx) * (self.rank + 1) // self.world
+            for e in list(idx[hi - 3:hi][::-1]) + list(idx[lo:lo + 3]):
+                cand.extend(int(x) for x in en[ptr[e]:ptr[e + 1]])
+        first_last = np.concatenate([np.array(cand, np.int64), rng.choice(touched, size=min(n_nodes, len(touched)), replace=False)])
         sample = []
         for nd in first_last:
             g = self.gls[nd - 1]
@@ -371,7 +381,8 @@ class Runner:
                 continue
             if self.world > 1 and not all(int(r - 1) in owned for r in free):
                 continue                                         # completed on another rank
-            sample.append(int(nd))
+            if int(nd) not in sample:
+                sample.append(int(nd))
             if len(sample) >= n_nodes:
                 break
         ok, worst = True, 0.0

@@ -188,6 +188,9 @@ struct gfa_handle {
     // persistent staging of gfa_add_host_*
     DevBuf<long long> d_stage_slots; DevBuf<double> d_stage_vals;
     std::vector<long long> stage_slots; std::vector<double> stage_vals;
+    std::vector<std::pair<long long, double> > stage_items;
+    DevBuf<double> d_xb, d_xa;            // X_B / x_A of the Newton-loop vector steps
+    DevBuf<int> d_gls_owned;              // DOF map with the free ids of rows other ranks own removed (norms of a partitioned run)
 
     int fused_eval_warps[3] = { 0, 0, 0 };
     int fused_tile_group = 8, fused_scatter_ctas = 1;
@@ -584,6 +587,79 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         for (int p = gptr[gn]; p < gptr[gn + 1]; p++) if (el_rank[ginc_e[p]] == h->rank) { need[gn] = 1; break; }
     }
 
+    // ---- neighbour lists (sorted group-node ids), over ALL incident elements so
+    //      that a stored row carries its complete global column set ------------
+    std::vector<long long> nptr(n_gn_all + 1, 0);
+    {
+        std::vector<int> cnt(n_gn_all, 0);
+#pragma omp parallel
+        {
+            std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 4096)
+            for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
+                if (!need[gn]) continue;
+                tmp.clear();
+                for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                    const int e = ginc_e[p], s = type_slot(h->el_type[e]);
+                    for (int b = 0; b < kTypes[s].nb; b++) {
+                        int a, grp; block_node(s, b, a, grp);
+                        tmp.push_back(h->el_nodes[h->el_ptr[e] + a] * 2 + grp);
+                    }
+                }
+                std::sort(tmp.begin(), tmp.end());
+                cnt[gn] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+            }
+        }
+        for (size_t i = 0; i < n_gn_all; i++) nptr[i + 1] = nptr[i] + cnt[i];
+    }
+    std::vector<int> nbr((size_t)nptr[n_gn_all]);
+#pragma omp parallel
+    {
+        std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 4096)
+        for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
+            if (!need[gn]) continue;
+            tmp.clear();
+            for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                const int e = ginc_e[p], s = type_slot(h->el_type[e]);
+                for (int b = 0; b < kTypes[s].nb; b++) {
+                    int a, grp; block_node(s, b, a, grp);
+                    tmp.push_back(h->el_nodes[h->el_ptr[e] + a] * 2 + grp);
+                }
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            std::copy(tmp.begin(), tmp.end(), nbr.begin() + nptr[gn]);
+        }
+    }
+
+    // ---- host positions outside the element pattern (Solution.cpp:268-281, 322-349: joints, contacts and other
+    //      contributors push arbitrary triplets into the same lists).  An extra AA position whose column group is not a
+    //      neighbour of its row group -- or that involves a DOF beyond the node table (Lagrange multipliers, super
+    //      nodes) -- lengthens that row only.  Group-nodes with such rows are "irregular": their rows no longer share
+    //      one layout, so they leave the patch slot map and are filled through explicit per-slot source lists (the
+    //      mechanism of AB / BA / BB); every other group-node is untouched.
+    std::vector<int> dof_gn((size_t)n_free, -1);             // free id -> group-node (-1: not a node DOF)
+    for (size_t gn = 0; gn < n_gn_all; gn++)
+        for (int k = 0; k < 3; k++) if (gls[3 * gn + k] > 0) dof_gn[(size_t)gls[3 * gn + k] - 1] = (int)gn;
+    std::vector<std::pair<int, int> > xtra;                  // (row, column) pairs outside the element pattern, sorted, unique
+    std::vector<unsigned char> irregular(n_gn_all, 0);
+    for (int64_t i = 0; i < n_extra; i++) {
+        if (ex_mat[i] != GFA_AA) continue;
+        const int r = ex_rows[i], c = ex_cols[i];
+        if (r < 0 || r >= n_free || c < 0 || c >= n_free) return fail(GFA_EINVAL, "extra pattern entry %lld out of range", (long long)i);
+        const int gr = dof_gn[(size_t)r], gc = dof_gn[(size_t)c];
+        bool inside = false;
+        if (gr >= 0 && gc >= 0 && need[(size_t)gr]) inside = std::binary_search(nbr.begin() + nptr[gr], nbr.begin() + nptr[gr + 1], gc);
+        if (!inside) xtra.emplace_back(r, c);
+    }
+    std::sort(xtra.begin(), xtra.end());
+    xtra.erase(std::unique(xtra.begin(), xtra.end()), xtra.end());
+    for (const std::pair<int, int>& rc : xtra) if (dof_gn[(size_t)rc.first] >= 0) irregular[(size_t)dof_gn[(size_t)rc.first]] = 1;
+    // extra columns of a row that are not in its group's element columns
+    auto row_extras = [&](int r) { return std::equal_range(xtra.begin(), xtra.end(), std::make_pair(r, 0), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; }); };
+
+
     // ---- arena placement -------------------------------------------------------------------------
     // classic: every local element owns a region of one big arena (written by the evaluation kernel, read back
     // by the scatter kernel through DRAM).  ring: elements are evaluated chunk by chunk into an L2-resident ring
@@ -636,7 +712,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                     lo = std::min(lo, c); hi = std::max(hi, c);
                 }
                 if (hi < 0) continue;
-                if (fixed || gn_iface[gn] || hi - lo > reach)
+                if (fixed || gn_iface[gn] || irregular[gn] || hi - lo > reach)
                     for (int p = gptr[gn]; p < gptr[gn + 1]; p++) { const int e = ginc_e[p], s = h->el_owner_slot[e]; if (s >= 0) pinned[s][h->el_local[e]] = 1; }
             }
         }
@@ -722,52 +798,6 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         return rc;
     };
 
-    // ---- neighbour lists (sorted group-node ids), over ALL incident elements so
-    //      that a stored row carries its complete global column set ------------
-    std::vector<long long> nptr(n_gn_all + 1, 0);
-    {
-        std::vector<int> cnt(n_gn_all, 0);
-#pragma omp parallel
-        {
-            std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 4096)
-            for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
-                if (!need[gn]) continue;
-                tmp.clear();
-                for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
-                    const int e = ginc_e[p], s = type_slot(h->el_type[e]);
-                    for (int b = 0; b < kTypes[s].nb; b++) {
-                        int a, grp; block_node(s, b, a, grp);
-                        tmp.push_back(h->el_nodes[h->el_ptr[e] + a] * 2 + grp);
-                    }
-                }
-                std::sort(tmp.begin(), tmp.end());
-                cnt[gn] = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
-            }
-        }
-        for (size_t i = 0; i < n_gn_all; i++) nptr[i + 1] = nptr[i] + cnt[i];
-    }
-    std::vector<int> nbr((size_t)nptr[n_gn_all]);
-#pragma omp parallel
-    {
-        std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 4096)
-        for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
-            if (!need[gn]) continue;
-            tmp.clear();
-            for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
-                const int e = ginc_e[p], s = type_slot(h->el_type[e]);
-                for (int b = 0; b < kTypes[s].nb; b++) {
-                    int a, grp; block_node(s, b, a, grp);
-                    tmp.push_back(h->el_nodes[h->el_ptr[e] + a] * 2 + grp);
-                }
-            }
-            std::sort(tmp.begin(), tmp.end());
-            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-            std::copy(tmp.begin(), tmp.end(), nbr.begin() + nptr[gn]);
-        }
-    }
-
     // ---- AA pattern: rows of a group-node share one column layout.  Stored
     //      rows are numbered in ascending global order (all rows when world == 1,
     //      so the single-GPU CSR is exactly the reference's). ------------------
@@ -781,6 +811,9 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     } else {
         for (size_t gn = 0; gn < n_gn_all; gn++)
             if (need[gn]) for (int k = 0; k < 3; k++) { const int g = gls[3 * gn + k]; if (g > 0) AA.row_ids.push_back(g - 1); }
+        if (h->rank == 0)       // rows of DOFs beyond the node table exist through host positions only: rank 0 keeps them
+            for (size_t i = 0; i < xtra.size(); i++)
+                if (dof_gn[(size_t)xtra[i].first] < 0 && (i == 0 || xtra[i - 1].first != xtra[i].first)) AA.row_ids.push_back(xtra[i].first);
         std::sort(AA.row_ids.begin(), AA.row_ids.end());
         for (size_t i = 0; i < AA.row_ids.size(); i++) AA.row_local[AA.row_ids[i]] = (int)i;
     }
@@ -792,6 +825,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         for (long long q = nptr[gn]; q < nptr[gn + 1]; q++) L += __builtin_popcount(free_mask((size_t)nbr[q]));
         for (int k = 0; k < 3; k++) { const int g = gls[3 * gn + k]; if (g > 0) AA.rowptr[AA.row_local[g - 1] + 1] = L; }
     }
+    for (const std::pair<int, int>& rc : xtra) { const int lr = AA.row_local[(size_t)rc.first]; if (lr >= 0) AA.rowptr[(size_t)lr + 1]++; }
     for (int r = 0; r < AA.rows; r++) AA.rowptr[r + 1] += AA.rowptr[r];
     const long long nnzAA = AA.rowptr[AA.rows];
     if (nnzAA > 0x7fffffffLL) return fail(GFA_EUNSUPPORTED, "AA has %lld non-zeros on this rank; 32-bit CSR (PARDISO/Eigen int) cannot hold it", nnzAA);
@@ -803,14 +837,33 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             const int g = gls[3 * gn + k];
             if (g <= 0) continue;
             int* out = AA.inner.data() + AA.rowptr[AA.row_local[g - 1]];
-            for (long long q = nptr[gn]; q < nptr[gn + 1]; q++)
-                for (int c = 0; c < 3; c++) { const int gc = gls[3 * (size_t)nbr[q] + c]; if (gc > 0) *out++ = gc - 1; }
+            if (!irregular[gn]) {
+                for (long long q = nptr[gn]; q < nptr[gn + 1]; q++)
+                    for (int c = 0; c < 3; c++) { const int gc = gls[3 * (size_t)nbr[q] + c]; if (gc > 0) *out++ = gc - 1; }
+            } else {            // element columns merged with the row's host positions, ascending
+                std::vector<int> cols;
+                for (long long q = nptr[gn]; q < nptr[gn + 1]; q++)
+                    for (int c = 0; c < 3; c++) { const int gc = gls[3 * (size_t)nbr[q] + c]; if (gc > 0) cols.push_back(gc - 1); }
+                const auto ex = row_extras(g - 1);
+                auto a = cols.begin(); auto b = ex.first;
+                while (a != cols.end() || b != ex.second) {
+                    if (b == ex.second || (a != cols.end() && *a < b->second)) *out++ = *a++;
+                    else *out++ = (b++)->second;
+                }
+            }
         }
+    }
+    for (size_t i = 0; i < xtra.size(); i++) {      // rows of DOFs beyond the node table
+        const int r = xtra[i].first, lr = AA.row_local[(size_t)r];
+        if (dof_gn[(size_t)r] >= 0 || lr < 0 || (i > 0 && xtra[i - 1].first == r)) continue;
+        int* out = AA.inner.data() + AA.rowptr[lr];
+        for (size_t j = i; j < xtra.size() && xtra[j].first == r; j++) *out++ = xtra[j].second;
     }
 
     // ---- AB / BA / BB: explicit entry lists of elements that touch a fixed DOF
     struct Ent { int mat, row, col; long long src; int rank; };
     std::vector<Ent> ents;      // pattern from all elements; src = -1 when the element is not this rank's
+    std::vector<Ent> aa_ents;   // AA slots of rows that carry host positions: element sources, element-ascending
     for (int e = 0; e < h->n_el; e++) {
         const int s = type_slot(h->el_type[e]);
         const TypeInfo& ti = kTypes[s];
@@ -820,12 +873,24 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             const size_t gn = (size_t)h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
             for (int k = 0; k < 3; k++) { gl[3 * b + k] = gls[3 * gn + k]; any_fixed |= gl[3 * b + k] < 0; }
         }
-        if (!any_fixed) continue;
+        bool any_irregular = false;
+        for (int b = 0; b < ti.nb; b++) {
+            int a, grp; block_node(s, b, a, grp);
+            any_irregular |= irregular[(size_t)h->el_nodes[h->el_ptr[e] + a] * 2 + grp] != 0;
+        }
+        if (!any_fixed && !any_irregular) continue;
         const bool mine = h->el_owner_slot[e] >= 0;
         for (int i = 0; i < ti.ndof; i++)
             for (int j = 0; j < ti.ndof; j++) {
                 const int g1 = gl[i], g2 = gl[j];
-                if (g1 > 0 && g2 > 0) continue;
+                if (g1 > 0 && g2 > 0) {
+                    // free x free: only the rows of irregular group-nodes are filled through explicit lists
+                    if (!mine || !irregular[(size_t)dof_gn[(size_t)g1 - 1]] || AA.row_local[(size_t)g1 - 1] < 0) continue;
+                    bool tr;
+                    const long long blk = arena_block(h, s, h->el_local[e], i / 3, j / 3, tr);
+                    aa_ents.push_back({ GFA_AA, g1 - 1, g2 - 1, blk + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3)), -1 });
+                    continue;
+                }
                 if (g1 == 0 || g2 == 0) continue;
                 Ent en;
                 en.mat = (g1 > 0) ? GFA_AB : (g2 > 0 ? GFA_BA : GFA_BB);
@@ -840,19 +905,14 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 ents.push_back(en);
             }
     }
-    // extra host positions: AA ones must already be in the element pattern; the small matrices take them as they come
+    // extra host positions of the small matrices are taken as they come (AA: see the pattern above)
     for (int64_t i = 0; i < n_extra; i++) {
         const int w = ex_mat[i], r = ex_rows[i], c = ex_cols[i];
         if (w < 0 || w > 3) return fail(GFA_EINVAL, "extra pattern entry %lld: matrix %d", (long long)i, w);
         const int nr = (w == GFA_AA || w == GFA_AB) ? n_free : n_fixed, nc = (w == GFA_AA || w == GFA_BA) ? n_free : n_fixed;
         if (r < 0 || r >= nr || c < 0 || c >= nc) return fail(GFA_EINVAL, "extra pattern entry %lld out of range", (long long)i);
-        if (w == GFA_AA) {
-            const int lr = AA.row_local[r];
-            if (lr < 0) continue;           // row stored on other ranks only
-            const int* b = AA.inner.data() + AA.rowptr[lr]; const int* e2 = AA.inner.data() + AA.rowptr[lr + 1];
-            if (!std::binary_search(b, e2, c))
-                return fail(GFA_EUNSUPPORTED, "extra AA position (%d,%d) lies outside the element pattern; host contributors that couple otherwise unconnected DOFs are not supported yet", r, c);
-        } else { Ent en; en.mat = w; en.row = r; en.col = c; en.src = -1; en.rank = -1; ents.push_back(en); }
+        if (w == GFA_AA) continue;           // in the element pattern already, or added to its row above
+        { Ent en; en.mat = w; en.row = r; en.col = c; en.src = -1; en.rank = -1; ents.push_back(en); }
     }
     std::stable_sort(ents.begin(), ents.end(), [](const Ent& x, const Ent& y) {
         if (x.mat != y.mat) return x.mat < y.mat;
@@ -884,6 +944,33 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             }
             granks.push_back(rs);
             i = j;
+        }
+        // AA rows that carry host positions: every slot of the row is rewritten per assembly (zero when no element feeds it)
+        for (size_t gn = 0; gn < n_gn_all; gn++) {
+            if (!irregular[gn]) continue;
+            for (int k = 0; k < 3; k++) {
+                const int g = gls[3 * gn + k];
+                if (g <= 0 || AA.row_local[(size_t)g - 1] < 0) continue;
+                const int lr = AA.row_local[(size_t)g - 1];
+                for (long long q = AA.rowptr[lr]; q < AA.rowptr[lr + 1]; q++) aa_ents.push_back({ GFA_AA, g - 1, AA.inner[(size_t)q], -1, -1 });
+            }
+        }
+        for (size_t i = 0; i < xtra.size(); i++) {
+            const int r = xtra[i].first;
+            if (dof_gn[(size_t)r] < 0 && AA.row_local[(size_t)r] >= 0) aa_ents.push_back({ GFA_AA, r, xtra[i].second, -1, -1 });
+        }
+        std::stable_sort(aa_ents.begin(), aa_ents.end(), [](const Ent& x, const Ent& y) { return x.row != y.row ? x.row < y.row : x.col < y.col; });
+        for (size_t a = 0; a < aa_ents.size();) {
+            size_t b = a;
+            const int lr = AA.row_local[(size_t)aa_ents[a].row];
+            const int* c0 = AA.inner.data() + AA.rowptr[lr]; const int* c1 = AA.inner.data() + AA.rowptr[lr + 1];
+            const long long slot = AA.rowptr[lr] + (std::lower_bound(c0, c1, aa_ents[a].col) - c0);
+            gseg.push_back((long long)gsrc.size());
+            gdest.push_back(slot);                            // matrix 0: the AA values start the arena
+            granks.push_back(0ULL);
+            for (; b < aa_ents.size() && aa_ents[b].row == aa_ents[a].row && aa_ents[b].col == aa_ents[a].col; b++)
+                if (aa_ents[b].src >= 0) gsrc.push_back(aa_ents[b].src);
+            a = b;
         }
         gseg.push_back((long long)gsrc.size());
     }
@@ -941,7 +1028,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 for (int k = 0; k < 3; k++) {
                     const int g = gls[3 * gn + k];
                     if (g > 0) {
-                        for (long long p = 0; p < L; p++) dst.push_back(h->arena_off[GFA_AA] + AA.rowptr[AA.row_local[g - 1]] + p);
+                        const int lr = AA.row_local[g - 1];
+                        for (long long p = AA.rowptr[lr]; p < AA.rowptr[lr + 1]; p++) dst.push_back(h->arena_off[GFA_AA] + p);
                         dst.push_back(h->vec_off[GFA_P_A] + g - 1);
                         dst.push_back(h->vec_off[GFA_I_A] + g - 1);
                     } else if (g < 0) dst.push_back(h->vec_off[GFA_P_B] + (-g - 1));
@@ -962,6 +1050,9 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         touched_iface.push_back(h->world > 1 && __builtin_popcountll(rank_set) > 1 ? 1 : 0);
         touched_rc.push_back(ready_chunk(gn));
     }
+    if (h->rank == 0)
+        for (size_t i = 0; i < xtra.size(); i++)
+            if (dof_gn[(size_t)xtra[i].first] < 0 && (i == 0 || xtra[i - 1].first != xtra[i].first)) h->owned_rows.push_back(xtra[i].first);
     std::sort(h->owned_rows.begin(), h->owned_rows.end());
     {   // patches are processed in the order of their group-node's first incident element, so that the
         // blocks read next to each other were written next to each other (node-id order would visit an
@@ -1031,7 +1122,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
         rec.ib = first_inc; rec.ie = (int)incs.size();
         gn_recs.push_back(rec);
-        if (!rm) continue;
+        if (!rm || irregular[gn]) continue;      // rows with host positions are filled through the explicit lists
         const long long row0 = AA.rowptr[first_row];
         int col = 0;
         for (int j = 0; j < n_runs; j++) {
@@ -1156,6 +1247,13 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     }
     {   // Newton-loop vector steps
         CUDA_TRY(h->d_gls.upload(h->gls));
+        if (h->world > 1) {
+            std::vector<unsigned char> own((size_t)n_free, 0);
+            for (int r : h->owned_rows) own[(size_t)r] = 1;
+            std::vector<int> g2(h->gls);
+            for (size_t i = 0; i < g2.size(); i++) if (g2[i] > 0 && !own[(size_t)g2[i] - 1]) g2[i] = 0;
+            CUDA_TRY(h->d_gls_owned.upload(g2));
+        }
         const HostCsr& AB = h->csr[GFA_AB];
         // rows of AB that hold entries; CSR storage is contiguous, so row rows[k] spans [ptr[k], ptr[k+1]) of
         // the value array when the empty rows in between are skipped
@@ -1490,18 +1588,44 @@ int gfa_element_alpha_i(gfa_t* h, int32_t e, double* out) {
     return w;
 }
 
+namespace {
+// Sum duplicates in push order (what Eigen's setFromTriplets does with repeated positions) and add the result
+// into the value arena: slots sorted with a stable sort, staging buffers kept in the handle -- nothing is
+// allocated on the per-iteration path once they have grown to the largest call.
+int add_staged(gfa_t* h, std::vector<std::pair<long long, double> >& items) {
+    std::stable_sort(items.begin(), items.end(), [](const std::pair<long long, double>& x, const std::pair<long long, double>& y) { return x.first < y.first; });
+    h->stage_slots.clear(); h->stage_vals.clear();
+    for (size_t i = 0; i < items.size();) {
+        size_t j = i; double acc = items[i].second;
+        for (j = i + 1; j < items.size() && items[j].first == items[i].first; j++) acc += items[j].second;
+        h->stage_slots.push_back(items[i].first); h->stage_vals.push_back(acc);
+        i = j;
+    }
+    const size_t n = h->stage_slots.size();
+    if (h->d_stage_slots.n < n) {
+        const size_t cap = std::max(n, 2 * h->d_stage_slots.n + 1024);
+        CUDA_TRY(h->d_stage_slots.alloc(cap)); CUDA_TRY(h->d_stage_vals.alloc(cap));
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->d_stage_slots.p, h->stage_slots.data(), n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_stage_vals.p, h->stage_vals.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_add_slots(h->d_arena.p, h->d_stage_slots.p, h->d_stage_vals.p, (long long)n, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // the host staging vectors are reused by the next call
+    return GFA_OK;
+}
+} // namespace
+
 int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, const int32_t* cols, const double* vals) {
     if (!h || which < 0 || which > 3 || (n > 0 && (!rows || !cols || !vals))) return fail(GFA_EINVAL, "gfa_add_host_triplets: bad argument");
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_add_host_triplets before gfa_assemble");
     if (n <= 0) return GFA_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     const HostCsr& M = h->csr[which];
-    // pre-sum duplicates in push order so that the device add touches every slot once
-    std::map<long long, double> acc;
-    std::vector<long long> order;
+    std::vector<std::pair<long long, double> >& items = h->stage_items;
+    items.clear();
+    const int n_rows_global = (which == GFA_AA || which == GFA_AB) ? h->n_free : h->n_fixed;
     for (int64_t i = 0; i < n; i++) {
         const int r = rows[i], c = cols[i];
-        const int n_rows_global = (which == GFA_AA || which == GFA_AB) ? h->n_free : h->n_fixed;
         if (r < 0 || r >= n_rows_global) return fail(GFA_EPATTERN, "host triplet %lld: row %d outside the matrix", (long long)i, r);
         int lr = r;
         if (which == GFA_AA) {
@@ -1511,17 +1635,9 @@ int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, c
         const int* b = M.inner.data() + M.rowptr[lr]; const int* e = M.inner.data() + M.rowptr[lr + 1];
         const int* p = std::lower_bound(b, e, c);
         if (p == e || *p != c) return fail(GFA_EPATTERN, "host triplet (%d,%d) is not in the registered pattern of matrix %d; list it in gfa_set_dofs", r, c, which);
-        const long long slot = h->arena_off[which] + M.rowptr[lr] + (p - b);
-        auto it = acc.find(slot);
-        if (it == acc.end()) { acc[slot] = vals[i]; order.push_back(slot); } else it->second += vals[i];
+        items.emplace_back(h->arena_off[which] + M.rowptr[lr] + (p - b), vals[i]);
     }
-    std::vector<double> v(order.size());
-    for (size_t i = 0; i < order.size(); i++) v[i] = acc[order[i]];
-    DevBuf<long long> ds; DevBuf<double> dv;
-    CUDA_TRY(ds.upload(order)); CUDA_TRY(dv.upload(v));
-    launch_add_slots(h->d_arena.p, ds.p, dv.p, (long long)order.size(), h->stream);
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return GFA_OK;
+    return add_staged(h, items);
 }
 
 int gfa_add_host_vector(gfa_t* h, int wv, int64_t n, const int32_t* index, const double* vals) {
@@ -1530,21 +1646,13 @@ int gfa_add_host_vector(gfa_t* h, int wv, int64_t n, const int32_t* index, const
     if (n <= 0) return GFA_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     const int len = wv == GFA_P_B ? h->n_fixed : h->n_free;
-    std::map<long long, double> acc;
-    std::vector<long long> order;
+    std::vector<std::pair<long long, double> >& items = h->stage_items;
+    items.clear();
     for (int64_t i = 0; i < n; i++) {
         if (index[i] < 0 || index[i] >= len) return fail(GFA_EINVAL, "host vector entry %lld: index %d out of range", (long long)i, index[i]);
-        const long long slot = h->vec_off[wv] + index[i];
-        auto it = acc.find(slot);
-        if (it == acc.end()) { acc[slot] = vals[i]; order.push_back(slot); } else it->second += vals[i];
+        items.emplace_back(h->vec_off[wv] + index[i], vals[i]);
     }
-    std::vector<double> v(order.size());
-    for (size_t i = 0; i < order.size(); i++) v[i] = acc[order[i]];
-    DevBuf<long long> ds; DevBuf<double> dv;
-    CUDA_TRY(ds.upload(order)); CUDA_TRY(dv.upload(v));
-    launch_add_slots(h->d_arena.p, ds.p, dv.p, (long long)order.size(), h->stream);
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return GFA_OK;
+    return add_staged(h, items);
 }
 
 int gfa_csr_values(gfa_t* h, int which, double* out) {
@@ -1710,20 +1818,18 @@ int reset_norms(gfa_t* h) {
 int gfa_residual(gfa_t* h, const double* X_B, gfa_norms_t* out) {
     if (!h) return fail(GFA_EINVAL, "gfa_residual: null handle");
     if (!h->assembled) return fail(GFA_ESTATE, "gfa_residual before gfa_assemble");
-    if (h->world > 1) return fail(GFA_EUNSUPPORTED, "gfa_residual works on a single-rank system (the residual is row-distributed otherwise)");
     CUDA_TRY(cudaSetDevice(h->device));
     double* PA = h->d_arena.p + h->vec_off[GFA_P_A];
     launch_negate(PA, h->n_free, h->stream);
     if (X_B && h->n_fixed > 0 && h->n_ab_rows > 0) {
-        DevBuf<double> xb;
-        CUDA_TRY(xb.alloc((size_t)h->n_fixed));
-        CUDA_TRY(cudaMemcpyAsync(xb.p, X_B, (size_t)h->n_fixed * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        launch_sub_ab_xb(PA, h->d_ab_rows.p, h->d_ab_ptr.p, h->d_ab_inner.p, h->d_arena.p + h->arena_off[GFA_AB], xb.p, h->n_ab_rows, h->stream);
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (h->d_xb.n < (size_t)h->n_fixed) CUDA_TRY(h->d_xb.alloc((size_t)h->n_fixed));
+        CUDA_TRY(cudaMemcpyAsync(h->d_xb.p, X_B, (size_t)h->n_fixed * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        launch_sub_ab_xb(PA, h->d_ab_rows.p, h->d_ab_ptr.p, h->d_ab_inner.p, h->d_arena.p + h->arena_off[GFA_AB], h->d_xb.p, h->n_ab_rows, h->stream);
     }
     if (out) {
         if (int rc = reset_norms(h)) return rc;
-        launch_norms(h->d_gls.p, PA, nullptr, h->n_nodes, h->d_norm.p, h->stream);
+        // a partitioned run: this rank's norms cover the rows it owns (complete after the interface exchange)
+        launch_norms(h->world > 1 ? h->d_gls_owned.p : h->d_gls.p, PA, nullptr, h->n_nodes, h->d_norm.p, h->stream);
         CUDA_TRY(cudaGetLastError());
         return read_norms(h, false, out);
     }
@@ -1736,13 +1842,12 @@ int gfa_update_displacements(gfa_t* h, const double* x_A, gfa_norms_t* out) {
     if (!h || !x_A) return fail(GFA_EINVAL, "gfa_update_displacements: null argument");
     if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_update_displacements before gfa_set_dofs");
     CUDA_TRY(cudaSetDevice(h->device));
-    DevBuf<double> x;
-    CUDA_TRY(x.alloc((size_t)std::max(h->n_free, 1)));
-    CUDA_TRY(cudaMemcpyAsync(x.p, x_A, (size_t)h->n_free * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    launch_update_disps(h->d_gls.p, h->d_disp.p, x.p, h->n_nodes, h->stream);
+    if (h->d_xa.n < (size_t)std::max(h->n_free, 1)) CUDA_TRY(h->d_xa.alloc((size_t)std::max(h->n_free, 1)));
+    CUDA_TRY(cudaMemcpyAsync(h->d_xa.p, x_A, (size_t)h->n_free * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_update_disps(h->d_gls.p, h->d_disp.p, h->d_xa.p, h->n_nodes, h->stream);
     if (out) {
         if (int rc = reset_norms(h)) return rc;
-        launch_norms(h->d_gls.p, x.p, h->d_disp.p, h->n_nodes, h->d_norm.p, h->stream);
+        launch_norms(h->world > 1 ? h->d_gls_owned.p : h->d_gls.p, h->d_xa.p, h->d_disp.p, h->n_nodes, h->d_norm.p, h->stream);
         CUDA_TRY(cudaGetLastError());
         return read_norms(h, true, out);
     }

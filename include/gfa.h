@@ -212,7 +212,9 @@ typedef struct gfa_norms {
  * increment), db.global_P_A -= 1.0*(db.global_stiffness_AB*db.global_X_B) with the reference's own row loop
  * (SparseMatrix.cpp:186-190); then the max-norms EstablishResidualCriteria / CheckResidualConvergence read.
  * Call after gfa_assemble and the host contributions; gfa_vector(GFA_P_A) afterwards returns the right-hand
- * side handed to the solver. */
+ * side handed to the solver.  In a partitioned run (after the interface exchange) the vector steps act on the
+ * entries this rank stores and the norms cover the rows it OWNS: the caller takes the maximum over ranks (and
+ * the smallest node among equal maxima), one tiny all-reduce, where the reference has one loop. */
 int gfa_residual(gfa_t* h, const double* X_B /* [n_fixed] host, or NULL */, gfa_norms_t* out);
 
 /* Solution::UpdateDisps (src/Solution.cpp:390-402) for node DOFs on the device copy of Node::displacements

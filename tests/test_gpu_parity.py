@@ -230,6 +230,89 @@ def test_host_triplets_outside_pattern_are_rejected():
     assert ei.value.code == -5
 
 
+def test_host_positions_outside_the_element_pattern(port):
+    """contributors that stay on the host (joints, contacts, loads) push triplets into the same lists
+    as the elements (Solution.cpp:268-281, 322-349) -- also at positions no element touches.  gfa_set_dofs takes
+    them into the pattern (byte-equal to what setFromTriplets yields for elements + extras), gfa_add_host_triplets
+    sums into them, and every assembly starts those slots from zero again."""
+    m = M.concat_models([M.beam_line(12), M.shell_plate(5, 4, warp=0.01)])
+    gls, nf, nx = M.number_dofs(m)
+    rng = np.random.default_rng(31)
+    d = M.mask_displacements(m, rng.uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
+    # a "joint" between a beam node and two shell nodes that share no element with it: every free-free pair, both ways
+    a = 9                                                    # beam node (1-based)
+    shell_nodes = np.unique(m.elem_nodes[m.elem_ptr[12 + 7]:m.elem_ptr[12 + 8]])
+    b, c = int(shell_nodes[0]), int(shell_nodes[-1])
+    rows, cols = [], []
+    for n1, n2 in ((a, b), (b, a), (a, c), (c, a), (b, c)):     # (b, c) lies inside the shell pattern already
+        for g1 in gls[n1 - 1][gls[n1 - 1] > 0]:
+            for g2 in gls[n2 - 1][gls[n2 - 1] > 0]:
+                rows.append(int(g1) - 1); cols.append(int(g2) - 1)
+    rows.append(3); cols.append(nf - 1)                       # and one lone position far off the diagonal
+    rows, cols = np.array(rows, np.int32), np.array(cols, np.int32)
+    vals = rng.uniform(-1e6, 1e6, len(rows))
+    port.load(m)
+    port.set_time(0.0, 1.0)
+    port.set_extra_triplets("AA", rows, cols, vals)
+    asm = capi.Assembler(m).set_dofs(gls, nf, nx, extra=(np.zeros(len(rows), np.int32), rows, cols))
+    asm.set_time(0.0, 1.0)
+    for it in range(2):                                      # the second pass: slots are rewritten, not accumulated
+        port.assemble(d)
+        asm.assemble(d)
+        asm.add_host_triplets("AA", rows, cols, vals)
+        _compare_system(port, asm, f"joint positions outside the element pattern, pass {it}")
+    port.set_extra_triplets("AA", np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    # DOFs beyond the node table (Lagrange multipliers of a joint, Solution.cpp:73-107): rows that exist through host
+    # positions only, and vector entries no element writes -- zeroed by every assembly like Solution::Clear does
+    n_lag = 3
+    lr, lc, lv = [], [], []
+    for k in range(n_lag):
+        g = gls[a - 1][gls[a - 1] > 0][k] - 1
+        lr += [nf + k, int(g), nf + k]; lc += [int(g), nf + k, nf + k]; lv += [1.0 + k, 1.0 + k, 0.5]
+    lr, lc, lv = np.array(lr, np.int32), np.array(lc, np.int32), np.array(lv)
+    asm2 = capi.Assembler(m).set_dofs(gls, nf + n_lag, nx, extra=(np.zeros(len(lr), np.int32), lr, lc))
+    base = capi.Assembler(m).set_dofs(gls, nf, nx)
+    base.assemble(d)
+    bo, bi, bv, _ = base.csr("AA")
+    for it in range(2):
+        asm2.assemble(d)
+        asm2.add_host_triplets("AA", lr, lc, lv)
+        asm2.add_host_vector(capi.P_A, np.array([nf, nf + 2], np.int32), np.array([7.0, -3.0]))
+        o, i, v, shape = asm2.csr("AA")
+        assert shape == (nf + n_lag, nf + n_lag)
+        for k in range(n_lag):
+            g = int(gls[a - 1][gls[a - 1] > 0][k] - 1)
+            r0, r1 = o[nf + k], o[nf + k + 1]
+            assert list(i[r0:r1]) == [g, nf + k] and list(v[r0:r1]) == [1.0 + k, 0.5]
+            row = dict(zip(i[o[g]:o[g + 1]].tolist(), v[o[g]:o[g + 1]].tolist()))
+            assert row[nf + k] == 1.0 + k
+            ref_row = dict(zip(bi[bo[g]:bo[g + 1]].tolist(), bv[bo[g]:bo[g + 1]].tolist()))
+            assert {c: x for c, x in row.items() if c < nf} == ref_row        # the element part of the row is untouched
+        pa = asm2.vectors()[0]
+        assert pa[nf] == 7.0 and pa[nf + 1] == 0.0 and pa[nf + 2] == -3.0
+        np.testing.assert_array_equal(pa[:nf], base.vectors()[0])
+
+
+def test_set_dofs_refuses_numberings_it_cannot_assemble():
+    """The pattern builder relies on the reference's node-major ascending numbering (Solution.cpp:53-72); a permuted
+    or interleaved map is refused instead of being mis-assembled."""
+    m = M.beam_line(6)
+    gls, nf, nx = M.number_dofs(m)
+    asm = capi.Assembler(m)
+    g2 = gls.copy()
+    i, j = np.argwhere(g2 == 7)[0], np.argwhere(g2 == 20)[0]
+    g2[tuple(i)], g2[tuple(j)] = 20, 7
+    with pytest.raises(capi.GfaError) as ei:
+        asm.set_dofs(g2, nf, nx)
+    assert ei.value.code == -7
+    g3 = gls.copy()
+    g3[g3 > 8] += 1                                          # a foreign DOF numbered inside a node's translation group
+    with pytest.raises(capi.GfaError) as ei:
+        asm.set_dofs(g3, nf + 1, nx)
+    assert ei.value.code == -7
+    asm.set_dofs(gls, nf, nx)                                # the reference's own numbering still goes through
+
+
 def test_call_order_errors():
     m = M.beam_line(3)
     asm = capi.Assembler(m)
