@@ -31,6 +31,7 @@ EXPORTS = [
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
     "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue", "gfa_interface_stream",
     "gfa_pipeline_info", "gfa_touched_nodes", "gfa_set_displacements_packed", "gfa_vector_owned",
+    "gfa_set_shell_loads", "gfa_apply_shell_loads",
 ]
 
 
@@ -127,6 +128,8 @@ def load_library() -> C.CDLL:
         lib.gfa_touched_nodes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
         lib.gfa_set_displacements_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         lib.gfa_vector_owned.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.gfa_set_shell_loads.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gfa_apply_shell_loads.argtypes = [C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -316,6 +319,22 @@ class Assembler:
     def add_host_vector(self, which_vector, index, vals):
         index, vals = np.ascontiguousarray(index, np.int32), np.ascontiguousarray(vals, np.float64)
         self._check(self.lib.gfa_add_host_vector(self._h, which_vector, len(vals), _ptr(index), _ptr(vals)))
+
+    # ---- ShellLoad follower pressure on the device ----------------------------
+    def set_shell_loads(self, loads):
+        """loads: [(element ids 1-based, area_update, table)] as in Model.shell_loads; call after set_dofs"""
+        ptr = np.zeros(len(loads) + 1, np.int32)
+        for k, (els, _, _) in enumerate(loads):
+            ptr[k + 1] = ptr[k] + len(els)
+        elems = np.concatenate([np.asarray(els, np.int32) - 1 for els, _, _ in loads]).astype(np.int32) if loads else np.zeros(0, np.int32)
+        area = np.array([1 if au else 0 for _, au, _ in loads], np.int32)
+        self._shell_load_tables = [np.asarray(t, float) for _, _, t in loads]
+        self._check(self.lib.gfa_set_shell_loads(self._h, len(loads), _ptr(ptr), _ptr(elems), _ptr(area)))
+
+    def apply_shell_loads(self, time: float):
+        """ShellLoad::GetValueAt(time) of every registered load (linear table), then gfa_apply_shell_loads"""
+        p = np.array([float(np.interp(time, t[:, 0], t[:, 1])) for t in self._shell_load_tables])
+        self._check(self.lib.gfa_apply_shell_loads(self._h, _ptr(p)))
 
     def commit(self):
         self._check(self.lib.gfa_commit_state(self._h))

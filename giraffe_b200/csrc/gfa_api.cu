@@ -198,6 +198,13 @@ struct gfa_handle {
     bool abort_check_pending = false;     // the watchdog flag of the last fused launches has not been read yet
     double last_gfac = 0.0;
 
+    // ShellLoad follower pressure on the device (gfa_set_shell_loads / gfa_apply_shell_loads)
+    int n_shell_loads = 0, n_load_entries = 0;
+    long long n_load_dest = 0;
+    DevBuf<int> d_load_elem, d_load_of, d_load_area;
+    DevBuf<double> d_load_pressure, d_load_out;
+    DevBuf<long long> d_load_seg, d_load_src, d_load_dest;
+
     bool assembled = false;
     bool timing_pending = false;          // events of the last assembly not read yet (gfa_assemble_enqueue)
     float last_ms[4] = { 0, 0, 0, 0 };
@@ -508,6 +515,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     CUDA_TRY(cudaSetDevice(h->device));
     h->dofs_set = false; h->assembled = false;
     h->d_owned_idx.release();
+    h->n_shell_loads = 0; h->n_load_entries = 0; h->n_load_dest = 0;      // registered against the old DOF map
     h->n_free = n_free; h->n_fixed = n_fixed;
     h->gls.assign(GLs, GLs + 6 * (size_t)h->n_nodes);
     const std::vector<int>& gls = h->gls;
@@ -1653,6 +1661,77 @@ int gfa_add_host_vector(gfa_t* h, int wv, int64_t n, const int32_t* index, const
         items.emplace_back(h->vec_off[wv] + index[i], vals[i]);
     }
     return add_staged(h, items);
+}
+
+int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements, const int32_t* area_update) {
+    if (!h || n_loads < 0 || (n_loads > 0 && (!load_ptr || !load_elements || !area_update))) return fail(GFA_EINVAL, "gfa_set_shell_loads: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_set_shell_loads before gfa_set_dofs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<int> elem, load, area(area_update, area_update + n_loads);
+    struct Slot { long long dest, src; };
+    std::vector<Slot> slots;
+    for (int l = 0; l < n_loads; l++)
+        for (int k = load_ptr[l]; k < load_ptr[l + 1]; k++) {
+            const int e = load_elements[k];
+            if (e < 0 || e >= h->n_el || h->el_type[e] != GFA_SHELL_1) return fail(GFA_EINVAL, "shell load %d: element %d is not a Shell_1 element", l + 1, e + 1);
+            if (h->el_owner_slot[e] != 0) continue;              // another rank's partition
+            const long long entry = (long long)elem.size();
+            elem.push_back(h->el_local[e]); load.push_back(l);
+            int gl[18];
+            for (int a = 0; a < 6; a++)
+                for (int c = 0; c < 3; c++) gl[3 * a + c] = h->gls[6 * (size_t)h->el_nodes[h->el_ptr[e] + a] + c];
+            for (int i = 0; i < 18; i++) {
+                const int g1 = gl[i];
+                if (g1 == 0) continue;
+                slots.push_back({ (g1 > 0 ? h->vec_off[GFA_P_A] + g1 - 1 : h->vec_off[GFA_P_B] + (-g1 - 1)), entry * SHELL_LOAD_REC + 324 + i });
+                if (g1 > 0) slots.push_back({ h->vec_off[GFA_I_A] + g1 - 1, entry * SHELL_LOAD_REC + 324 + i });
+                for (int j = 0; j < 18; j++) {
+                    const int g2 = gl[j];
+                    if (g2 == 0) continue;
+                    const int w = g1 > 0 ? (g2 > 0 ? GFA_AA : GFA_AB) : (g2 > 0 ? GFA_BA : GFA_BB);
+                    const HostCsr& M = h->csr[w];
+                    int lr = std::abs(g1) - 1;
+                    if (w == GFA_AA) lr = M.row_local[(size_t)lr];
+                    const int col = std::abs(g2) - 1;
+                    const int* b = M.inner.data() + M.rowptr[lr]; const int* en = M.inner.data() + M.rowptr[lr + 1];
+                    const int* p = std::lower_bound(b, en, col);
+                    if (p == en || *p != col) return fail(GFA_EPATTERN, "shell load position (%d,%d) of matrix %d is not in the pattern", lr, col, w);
+                    slots.push_back({ h->arena_off[w] + M.rowptr[lr] + (p - b), entry * SHELL_LOAD_REC + i * 18 + j });
+                }
+            }
+        }
+    // one destination per slot, its sources in registration order (stable sort)
+    std::stable_sort(slots.begin(), slots.end(), [](const Slot& x, const Slot& y) { return x.dest < y.dest; });
+    std::vector<long long> seg, src, dest;
+    for (size_t i = 0; i < slots.size();) {
+        size_t j = i;
+        seg.push_back((long long)src.size()); dest.push_back(slots[i].dest);
+        for (; j < slots.size() && slots[j].dest == slots[i].dest; j++) src.push_back(slots[j].src);
+        i = j;
+    }
+    seg.push_back((long long)src.size());
+    h->n_shell_loads = n_loads; h->n_load_entries = (int)elem.size(); h->n_load_dest = (long long)dest.size();
+    CUDA_TRY(h->d_load_elem.upload(elem)); CUDA_TRY(h->d_load_of.upload(load)); CUDA_TRY(h->d_load_area.upload(area));
+    CUDA_TRY(h->d_load_pressure.alloc((size_t)std::max(n_loads, 1)));
+    CUDA_TRY(h->d_load_out.alloc((size_t)std::max<size_t>(elem.size(), 1) * SHELL_LOAD_REC));
+    CUDA_TRY(h->d_load_seg.upload(seg)); CUDA_TRY(h->d_load_src.upload(src)); CUDA_TRY(h->d_load_dest.upload(dest));
+    return GFA_OK;
+}
+
+int gfa_apply_shell_loads(gfa_t* h, const double* pressures) {
+    if (!h || (h->n_shell_loads > 0 && !pressures)) return fail(GFA_EINVAL, "gfa_apply_shell_loads: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_apply_shell_loads before gfa_assemble");
+    if (h->n_load_entries == 0) return GFA_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->d_load_pressure.p, pressures, (size_t)h->n_shell_loads * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ShellLoadArgs la;
+    la.n_entries = h->n_load_entries; la.elem = h->d_load_elem.p; la.load = h->d_load_of.p;
+    la.pressure = h->d_load_pressure.p; la.area_update = h->d_load_area.p; la.out = h->d_load_out.p;
+    launch_shell_loads(eval_args(h, 0, 0.0), la, h->stream);
+    launch_gather_add(h->d_arena.p, h->d_load_seg.p, h->d_load_src.p, h->d_load_dest.p, h->d_load_out.p, h->n_load_dest, h->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // `pressures` is the caller's
+    return GFA_OK;
 }
 
 int gfa_csr_values(gfa_t* h, int which, double* out) {

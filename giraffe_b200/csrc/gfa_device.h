@@ -186,6 +186,22 @@ struct FusedArgs {
     unsigned long long timeout_ns;   // watchdog: a warp that waits longer sets CTL_ABORT and everyone leaves
 };
 
+// ---- ShellLoad follower pressure (ShellLoad.cpp:133-148 -> Shell_1::MountShellSpecialLoads, Shell_1.cpp:1392-1467) ----
+// one entry per (load, Shell_1 element of its set): the 18 x 18 load stiffness on the element's u DOFs (not symmetric)
+// and the 18 load-vector entries, SHELL_LOAD_REC doubles: K row-major, then P
+constexpr int SHELL_LOAD_REC = 324 + 18;
+struct ShellLoadArgs {
+    int n_entries;
+    const int* elem;             // [n_entries] local index of the Shell_1 element
+    const int* load;             // [n_entries] index of the load
+    const double* pressure;      // [n_loads] ShellLoad::GetValueAt(time) of every load
+    const int* area_update;      // [n_loads] ShellLoad::area_update
+    double* out;                 // [n_entries * SHELL_LOAD_REC]
+};
+void launch_shell_loads(const EvalArgs& a, const ShellLoadArgs& l, void* stream);
+// vals[dest[i]] += sum of src[seg[i] .. seg[i+1]) in list order (one thread per destination: fixed summation order)
+void launch_gather_add(double* vals, const long long* seg, const long long* src, const long long* dest, const double* from, long long n_dest, void* stream);
+
 // entries that involve a fixed DOF (AB, BA, BB): explicit gather lists
 struct GatherArgs {
     long long n_dest;

@@ -733,6 +733,93 @@ __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     }
 }
 
+// ShellLoad follower pressure on the current configuration (Shell_1::MountShellSpecialLoads, :1392-1467): 6-point
+// Cowper rule (the w4 / N4 tables of PreCalc, :2185-2314), t_b = e_br + N,b u with u = copy - ref + displacements,
+// n = t1 x t2 / |t1 x t2|, q = -p n; AreaUpdate 0: P -= w4 N^T q, K += w4 p N^T (I - n n^T)/|t1 x t2| (skew(t1) N,2 -
+// skew(t2) N,1); AreaUpdate 1: the same with the Jacobian |t1 x t2| kept in the force and no projector.
+// One thread per (entry, node pair a, b): the 3 x 3 block (a, b) of the load stiffness, thread b = 0 also the force.
+__global__ void load_kernel(EvalArgs A, ShellLoadArgs Ld) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 36LL * Ld.n_entries) return;
+    const int entry = (int)(t / 36), pair = (int)(t % 36), a = pair / 6, b = pair % 6;
+    const int e = Ld.elem[entry], ld = Ld.load[entry];
+    const double pressure = Ld.pressure[ld];
+    const bool area_update = Ld.area_update[ld] != 0;
+    int nd[6];
+    double x[6][3], u[6][3];
+    load_nodes(A, e, nd, x);
+#pragma unroll
+    for (int n = 0; n < 6; n++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) u[n][c] = A.copy[6 * (size_t)nd[n] + c] - x[n][c] + A.disp[6 * (size_t)nd[n] + c];
+    Frame fr; frame_of(x, fr);
+    const double cw[6][4] = {
+        { 0.816847572980459, 0.091576213509771, 0.091576213509771, 0.109951743655322 },
+        { 0.091576213509771, 0.816847572980459, 0.091576213509771, 0.109951743655322 },
+        { 0.091576213509771, 0.091576213509771, 0.816847572980459, 0.109951743655322 },
+        { 0.108103018168070, 0.445948490915965, 0.445948490915965, 0.223381589678011 },
+        { 0.445948490915965, 0.108103018168070, 0.445948490915965, 0.223381589678011 },
+        { 0.445948490915965, 0.445948490915965, 0.108103018168070, 0.223381589678011 } };
+    double K[9], P[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+    for (int i = 0; i < 9; i++) K[i] = 0.0;
+    for (int g = 0; g < 6; g++) {
+        const double L[3] = { cw[g][0], cw[g][1], cw[g][2] };
+        const double w4 = fr.area * cw[g][3];
+        double N[6], N1[6], N2[6];
+        N[0] = (2 * L[0] - 1) * L[0]; N[1] = (2 * L[1] - 1) * L[1]; N[2] = (2 * L[2] - 1) * L[2];
+        N[3] = 4 * L[0] * L[1]; N[4] = 4 * L[1] * L[2]; N[5] = 4 * L[2] * L[0];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { N1[k] = 4 * fr.Lx[k] * L[k] - fr.Lx[k]; N2[k] = 4 * fr.Ly[k] * L[k] - fr.Ly[k]; }
+        N1[3] = 4 * fr.Lx[0] * L[1] + 4 * L[0] * fr.Lx[1]; N1[4] = 4 * fr.Lx[1] * L[2] + 4 * L[1] * fr.Lx[2]; N1[5] = 4 * fr.Lx[2] * L[0] + 4 * L[2] * fr.Lx[0];
+        N2[3] = 4 * fr.Ly[0] * L[1] + 4 * L[0] * fr.Ly[1]; N2[4] = 4 * fr.Ly[1] * L[2] + 4 * L[1] * fr.Ly[2]; N2[5] = 4 * fr.Ly[2] * L[0] + 4 * L[2] * fr.Ly[0];
+        double t1[3], t2[3], c[3], n[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            double s1 = fr.R[k], s2 = fr.R[3 + k];
+#pragma unroll
+            for (int m = 0; m < 6; m++) { s1 += N1[m] * u[m][k]; s2 += N2[m] * u[m][k]; }
+            t1[k] = s1; t2[k] = s2;
+        }
+        cross3(c, t1, t2);
+        const double jac = norm3(c);
+#pragma unroll
+        for (int k = 0; k < 3; k++) n[k] = c[k] / jac;
+        // M = skew(t1) N2[b] - skew(t2) N1[b]
+        double S1[9], S2[9], Mx[9];
+        skew3(S1, t1); skew3(S2, t2);
+#pragma unroll
+        for (int i = 0; i < 9; i++) Mx[i] = S1[i] * N2[b] - S2[i] * N1[b];
+        const double scale = area_update ? w4 * jac : w4;
+        if (!area_update) {
+            double Pm[9];                      // (I - n n^T) / jac * M
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) v += ((i == k ? 1.0 : 0.0) - n[i] * n[k]) * Mx[3 * k + j];
+                    Pm[3 * i + j] = v / jac;
+                }
+#pragma unroll
+            for (int i = 0; i < 9; i++) K[i] += w4 * pressure * N[a] * Pm[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; i++) K[i] += w4 * pressure * N[a] * Mx[i];
+        }
+        if (b == 0)
+#pragma unroll
+            for (int k = 0; k < 3; k++) P[k] -= scale * N[a] * (-pressure * n[k]);
+    }
+    double* o = Ld.out + (size_t)entry * SHELL_LOAD_REC;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[(3 * a + i) * 18 + 3 * b + j] = K[3 * i + j];
+    if (b == 0) { o[324 + 3 * a] = P[0]; o[324 + 3 * a + 1] = P[1]; o[324 + 3 * a + 2] = P[2]; }
+}
+
 // Shell_1::SaveLagrange (:1650-1664): one thread per Gauss point.
 __global__ void commit_kernel(EvalArgs A) {
     const size_t n_gp = (size_t)A.n_el * NGP;
@@ -1490,6 +1577,13 @@ __global__ void gather_kernel(GatherArgs A) {
     A.vals[A.dest[i]] = s;
 }
 
+__global__ void gather_add_kernel(double* vals, const long long* seg, const long long* src, const long long* dest, const double* from, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (long long k = seg[i]; k < seg[i + 1]; k++) s += from[src[k]];
+    vals[dest[i]] += s;
+}
 __global__ void add_slots_kernel(double* vals, const long long* slots, const double* add, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) vals[slots[i]] += add[i];
@@ -2017,6 +2111,14 @@ int launch_fused_scatter(const FusedArgs& f, void* s) {
 void launch_gather(const GatherArgs& a, void* s) {
     if (a.n_dest <= 0) return;
     gather_kernel<<<(unsigned)((a.n_dest + 255) / 256), 256, 0, (cudaStream_t)s>>>(a);
+}
+void launch_shell_loads(const EvalArgs& a, const ShellLoadArgs& l, void* s) {
+    if (l.n_entries <= 0) return;
+    shell::load_kernel<<<(unsigned)((36LL * l.n_entries + 127) / 128), 128, 0, (cudaStream_t)s>>>(a, l);
+}
+void launch_gather_add(double* vals, const long long* seg, const long long* src, const long long* dest, const double* from, long long n, void* s) {
+    if (n <= 0) return;
+    gather_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)s>>>(vals, seg, src, dest, from, n);
 }
 void launch_add_slots(double* vals, const long long* slots, const double* add, long long n, void* s) {
     if (n <= 0) return;

@@ -153,6 +153,18 @@ int gfa_assemble_enqueue(gfa_t* h, const gfa_step_t* step);
 int gfa_add_host_triplets(gfa_t* h, int which, int64_t n, const int32_t* rows, const int32_t* cols, const double* vals);
 int gfa_add_host_vector(gfa_t* h, int which_vector, int64_t n, const int32_t* index, const double* vals);
 
+/* ShellLoad follower pressure on the device (src/ShellLoad.cpp:133-148 -> Shell_1::MountShellSpecialLoads,
+ * src/Shell_1.cpp:1392-1467): the one Load of the reference that is element arithmetic -- a 6-point integration
+ * over the current configuration of every shell of an element set, with a non-symmetric load stiffness on the u-u
+ * blocks.  gfa_set_shell_loads registers the loads after gfa_set_dofs (a new gfa_set_dofs drops them): load l
+ * applies to the Shell_1 elements load_elements[load_ptr[l] .. load_ptr[l+1]) (0-based element ids; elements of
+ * other ranks' partitions are skipped), area_update[l] = ShellLoad::area_update.  gfa_apply_shell_loads, called
+ * after gfa_assemble (MountLoads runs after the elements are mounted), evaluates them for the displacements of that
+ * assembly and the committed configuration with pressures[l] = ShellLoad::GetValueAt(time) and adds stiffness and
+ * load vector into the CSR values and P_A / I_A / P_B, contributions summed in registration order. */
+int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements, const int32_t* area_update);
+int gfa_apply_shell_loads(gfa_t* h, const double* pressures /* [n_loads] */);
+
 /* Results.  Device pointers stay valid until the next gfa_set_dofs/destroy. */
 int gfa_csr_values(gfa_t* h, int which, double* host_out /* [nnz] */);
 int gfa_csr_values_device(gfa_t* h, int which, double** dev_ptr);

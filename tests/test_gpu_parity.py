@@ -648,6 +648,26 @@ def test_shell_load_host_contributor_through_the_c_abi():
     asm.close()
 
 
+def test_shell_load_on_the_device():
+    """The same fixture with the follower pressure evaluated by the library's own kernel (gfa_set_shell_loads /
+    gfa_apply_shell_loads): AreaUpdate 0 and 1 on different element sets, before and after a commit."""
+    z = _golden("shell_load")
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(*z["time"])
+    asm.set_shell_loads(m.shell_loads)
+    t = float(z["time"][0] + z["time"][1])
+    for tag, commit in (("it1", False), ("it2", True), ("it3", False)):
+        asm.assemble(z[f"{tag}_disp"])
+        asm.apply_shell_loads(t)
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), asm.csr, f"device shell_load {tag}")
+        for v, key in zip(asm.vectors(), ("PA", "IA", "PB")):
+            util.assert_parity(z[f"{tag}_{key}"], v, f"device shell_load {tag} {key}")
+        if commit:
+            asm.commit()
+    asm.close()
+
+
 def test_random_models_against_oracle(port):
     """Seeded random variations (the oracle is pinned to the reference on the same generator by
     tests/test_oracle_vs_ref.py): random constraint masks on random nodes, sizes, warps, gravity, displacement
