@@ -408,11 +408,11 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
     {
         double Qd[9], Qi[9], Q[9], t3[3];
 #pragma unroll
-        for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+        for (int i = 0; i < 9; i++) Qi[i] = __ldg(A.state + i * n_gp + gp);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            z1[i] = s_add(kn.u1[i], A.state[(9 + i) * n_gp + gp]);      // z,1 = u_delta,1 + z,1^i  (:1010)
-            z2[i] = s_add(kn.u2[i], A.state[(12 + i) * n_gp + gp]);
+            z1[i] = s_add(kn.u1[i], __ldg(A.state + (9 + i) * n_gp + gp));      // z,1 = u_delta,1 + z,1^i  (:1010)
+            z2[i] = s_add(kn.u2[i], __ldg(A.state + (12 + i) * n_gp + gp));
         }
         s_rodrigues(kn.a, gg, Qd, Xi);
         s_mm(Q, Qd, Qi);
@@ -424,8 +424,8 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         s_mtv(t3, Xi, kn.a2); s_mtv(st.kap2, Qi, t3);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            st.kap1[i] = s_add(st.kap1[i], A.state[(15 + i) * n_gp + gp]);
-            st.kap2[i] = s_add(st.kap2[i], A.state[(18 + i) * n_gp + gp]);
+            st.kap1[i] = s_add(st.kap1[i], __ldg(A.state + (15 + i) * n_gp + gp));
+            st.kap2[i] = s_add(st.kap2[i], __ldg(A.state + (18 + i) * n_gp + gp));
         }
     }
     double X[3][3][4], smu = 0.0;

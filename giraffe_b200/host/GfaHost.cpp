@@ -346,6 +346,18 @@ bool GfaHost::SetGlobalSize() {
     std::vector<int> m, r, c;
     CollectLoadPattern(m, r, c);
     if (gfa_set_dofs(h, GLs.data(), n_GL_free, n_GL_fixed, (int64_t)m.size(), m.data(), r.data(), c.data()) != GFA_OK) return fail(gfa_last_error());
+    // ShellLoad element sets (the reference ignores elements of other types in the set, Shell_1-only virtual)
+    if (!shell_loads.empty()) {
+        std::vector<int> ptr(1, 0), elems, area;
+        for (const GfaShellLoad& l : shell_loads) {
+            if (l.element_set < 1 || l.element_set > (int)element_sets.size()) return fail("ShellLoad refers to an ElementSet that does not exist");
+            for (int el1 : element_sets[l.element_set - 1])
+                if (el1 >= 1 && el1 <= number_elements() && elem_type[el1 - 1] == GFA_SHELL_1) elems.push_back(el1 - 1);
+            ptr.push_back((int)elems.size());
+            area.push_back(l.area_update ? 1 : 0);
+        }
+        if (gfa_set_shell_loads(h, (int32_t)shell_loads.size(), ptr.data(), elems.data(), area.data()) != GFA_OK) return fail(gfa_last_error());
+    }
     return true;
 }
 
@@ -439,112 +451,16 @@ bool GfaHost::MountLoads() {
                 }
         }
     }
-    // ShellLoad::Mount -> Shell_1::MountShellSpecialLoads (ShellLoad.cpp:133-148, Shell_1.cpp:1392-1467): follower
-    // pressure over the 6-point rule on copy_coordinates + displacements; the element adds it to its P_loading
-    // (which MountGlobal puts into global_P_A AND global_I_A) and to the u-u blocks of its stiffness
-    std::vector<int> is; std::vector<double> vs;            // additions that go to both P_A and I_A
+    // ShellLoad::Mount -> Shell_1::MountShellSpecialLoads (ShellLoad.cpp:133-148, Shell_1.cpp:1392-1467): the follower
+    // pressure is element arithmetic and runs on the device (registered in SetGlobalSize); the host only evaluates
+    // the load's time table, as ShellLoad::GetValueAt does
     if (!shell_loads.empty()) {
-        std::vector<double> copy(6 * (size_t)number_nodes());
-        if (gfa_copy_coordinates(h, copy.data()) != GFA_OK) return fail(gfa_last_error());
-        static const double cw[6][4] = {
-            { 0.816847572980459, 0.091576213509771, 0.091576213509771, 0.109951743655322 },
-            { 0.091576213509771, 0.816847572980459, 0.091576213509771, 0.109951743655322 },
-            { 0.091576213509771, 0.091576213509771, 0.816847572980459, 0.109951743655322 },
-            { 0.108103018168070, 0.445948490915965, 0.445948490915965, 0.223381589678011 },
-            { 0.445948490915965, 0.108103018168070, 0.445948490915965, 0.223381589678011 },
-            { 0.445948490915965, 0.445948490915965, 0.108103018168070, 0.223381589678011 } };
-        auto cross = [](const double* a, const double* b, double* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
-        auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
-        for (const GfaShellLoad& l : shell_loads) {
-            if (l.element_set < 1 || l.element_set > (int)element_sets.size()) return fail("ShellLoad refers to an ElementSet that does not exist");
-            const double pressure = l.GetValueAt(t);
-            for (int el1 : element_sets[l.element_set - 1]) {
-                const int e = el1 - 1;
-                if (e < 0 || e >= number_elements() || elem_type[e] != GFA_SHELL_1) continue;      // the reference ignores other types
-                const int* nd = &elem_nodes[elem_node_ptr[e]];
-                double x[6][3], u[6][3];
-                for (int a = 0; a < 6; a++)
-                    for (int k = 0; k < 3; k++) {
-                        x[a][k] = ref_coordinates[3 * (size_t)(nd[a] - 1) + k];
-                        u[a][k] = copy[6 * (size_t)(nd[a] - 1) + k] - x[a][k] + displacements[6 * (size_t)(nd[a] - 1) + k];
-                    }
-                double d21[3], d31[3], nv[3], e3[3], e1r[3], e2r[3];
-                for (int k = 0; k < 3; k++) { d21[k] = x[1][k] - x[0][k]; d31[k] = x[2][k] - x[0][k]; }
-                cross(d21, d31, nv);
-                const double nn = sqrt(dot(nv, nv)), A = 0.5 * nn;
-                for (int k = 0; k < 3; k++) e3[k] = nv[k] / nn;
-                double eg[3] = { 1.0, 0.0, 0.0 };
-                if (fabs(e3[0]) >= 1.0 - 1e-4) { eg[0] = 0.0; eg[1] = 1.0; }
-                const double ege3 = dot(eg, e3);
-                for (int k = 0; k < 3; k++) e1r[k] = eg[k] - ege3 * e3[k];
-                const double n1 = sqrt(dot(e1r, e1r));
-                for (int k = 0; k < 3; k++) e1r[k] /= n1;
-                cross(e3, e1r, e2r);
-                double Lx[3], Ly[3], d[3];
-                for (int k = 0; k < 3; k++) d[k] = x[1][k] - x[2][k]; Lx[0] = 0.5 * dot(d, e2r) / A;
-                for (int k = 0; k < 3; k++) d[k] = x[2][k] - x[0][k]; Lx[1] = 0.5 * dot(d, e2r) / A;
-                for (int k = 0; k < 3; k++) d[k] = x[0][k] - x[1][k]; Lx[2] = 0.5 * dot(d, e2r) / A;
-                for (int k = 0; k < 3; k++) d[k] = x[2][k] - x[1][k]; Ly[0] = 0.5 * dot(d, e1r) / A;
-                for (int k = 0; k < 3; k++) d[k] = x[0][k] - x[2][k]; Ly[1] = 0.5 * dot(d, e1r) / A;
-                for (int k = 0; k < 3; k++) d[k] = x[1][k] - x[0][k]; Ly[2] = 0.5 * dot(d, e1r) / A;
-                double K[18][18], P[18];
-                for (int i = 0; i < 18; i++) { P[i] = 0.0; for (int j = 0; j < 18; j++) K[i][j] = 0.0; }
-                for (int g = 0; g < 6; g++) {
-                    const double L[3] = { cw[g][0], cw[g][1], cw[g][2] }, w4 = A * cw[g][3];
-                    const double N[6] = { (2 * L[0] - 1) * L[0], (2 * L[1] - 1) * L[1], (2 * L[2] - 1) * L[2], 4 * L[0] * L[1], 4 * L[1] * L[2], 4 * L[2] * L[0] };
-                    double N1[6], N2[6];
-                    for (int k = 0; k < 3; k++) { N1[k] = 4 * Lx[k] * L[k] - Lx[k]; N2[k] = 4 * Ly[k] * L[k] - Ly[k]; }
-                    for (int k = 0; k < 3; k++) {
-                        const int k2 = (k + 1) % 3;
-                        N1[3 + k] = 4 * Lx[k] * L[k2] + 4 * L[k] * Lx[k2];
-                        N2[3 + k] = 4 * Ly[k] * L[k2] + 4 * L[k] * Ly[k2];
-                    }
-                    double t1[3], t2[3], c[3], n[3];
-                    for (int k = 0; k < 3; k++) {
-                        t1[k] = e1r[k]; t2[k] = e2r[k];
-                        for (int a = 0; a < 6; a++) { t1[k] += N1[a] * u[a][k]; t2[k] += N2[a] * u[a][k]; }
-                    }
-                    cross(t1, t2, c);
-                    const double jac = sqrt(dot(c, c));
-                    for (int k = 0; k < 3; k++) n[k] = c[k] / jac;
-                    const double scale = l.area_update ? w4 * jac : w4;
-                    for (int a = 0; a < 6; a++)
-                        for (int k = 0; k < 3; k++) P[3 * a + k] -= scale * N[a] * (-1.0 * pressure * n[k]);
-                    const double S1[9] = { 0, -t1[2], t1[1], t1[2], 0, -t1[0], -t1[1], t1[0], 0 };
-                    const double S2[9] = { 0, -t2[2], t2[1], t2[2], 0, -t2[0], -t2[1], t2[0], 0 };
-                    for (int b = 0; b < 6; b++) {
-                        double M[9], Kp[9];
-                        for (int q = 0; q < 9; q++) M[q] = S1[q] * N2[b] - S2[q] * N1[b];
-                        if (l.area_update) for (int q = 0; q < 9; q++) Kp[q] = M[q];
-                        else
-                            for (int i = 0; i < 3; i++)
-                                for (int j = 0; j < 3; j++) {
-                                    double sacc = 0.0;
-                                    for (int k = 0; k < 3; k++) sacc += ((i == k ? 1.0 : 0.0) - n[i] * n[k]) * M[3 * k + j];
-                                    Kp[3 * i + j] = sacc / jac;
-                                }
-                        for (int a = 0; a < 6; a++)
-                            for (int i = 0; i < 3; i++)
-                                for (int j = 0; j < 3; j++) K[3 * a + i][3 * b + j] += w4 * 1.0 * pressure * N[a] * Kp[3 * i + j];
-                    }
-                }
-                for (int i = 0; i < 18; i++) {
-                    const int g1 = GLs[6 * (size_t)(nd[i / 3] - 1) + i % 3];
-                    if (g1 > 0) { is.push_back(g1 - 1); vs.push_back(P[i]); } else if (g1 < 0) { ib.push_back(-g1 - 1); vb.push_back(P[i]); }
-                    for (int j = 0; j < 18; j++) {
-                        const int g2 = GLs[6 * (size_t)(nd[j / 3] - 1) + j % 3];
-                        if (g1 == 0 || g2 == 0) continue;
-                        const int w = g1 > 0 ? (g2 > 0 ? GFA_AA : GFA_AB) : (g2 > 0 ? GFA_BA : GFA_BB);
-                        tr[w].push_back(abs(g1) - 1); tc[w].push_back(abs(g2) - 1); tv[w].push_back(K[i][j]);
-                    }
-                }
-            }
-        }
+        std::vector<double> pressures;
+        for (const GfaShellLoad& l : shell_loads) pressures.push_back(l.GetValueAt(t));
+        if (gfa_apply_shell_loads(h, pressures.data()) != GFA_OK) return fail(gfa_last_error());
     }
     for (int w = 0; w < 4; w++)
         if (!tv[w].empty() && gfa_add_host_triplets(h, w, (int64_t)tv[w].size(), tr[w].data(), tc[w].data(), tv[w].data()) != GFA_OK) return fail(gfa_last_error());
-    if (!vs.empty() && gfa_add_host_vector(h, GFA_P_A, (int64_t)vs.size(), is.data(), vs.data()) != GFA_OK) return fail(gfa_last_error());
-    if (!vs.empty() && gfa_add_host_vector(h, GFA_I_A, (int64_t)vs.size(), is.data(), vs.data()) != GFA_OK) return fail(gfa_last_error());
     if (!va.empty() && gfa_add_host_vector(h, GFA_P_A, (int64_t)va.size(), ia.data(), va.data()) != GFA_OK) return fail(gfa_last_error());
     if (!vb.empty() && gfa_add_host_vector(h, GFA_P_B, (int64_t)vb.size(), ib.data(), vb.data()) != GFA_OK) return fail(gfa_last_error());
     return true;
