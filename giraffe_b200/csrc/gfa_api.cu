@@ -171,6 +171,9 @@ struct gfa_handle {
 
     // ring pipeline (fused evaluation + scatter, FusedArgs in gfa_device.h); `ring` false = classic two-kernel path
     bool ring = false, force_classic = false;
+    bool ring_serial = false;             // ring placement, but classic kernels launched group by group (GFA_RING=3)
+    int ring_group = 4;                   // chunks per group of the serial variant
+    std::vector<long long> chunk_run_ptr_h;
     int ring_chunks = 0, ring_span = 0, total_chunks = 0;
     long long chunk_doubles = 0, ring_doubles = 0;
     long long n_pre_runs = 0;             // runs fed by pinned elements only: scattered by the classic kernel before the fused launches
@@ -695,7 +698,10 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         // scatter kernel cannot keep up beside the register-hungry evaluation kernel (profiles/r02_notes.md), so the
         // classic two-kernel path stays the default until the evaluation kernel leaves more of the SM free
         const int mode = env ? atoi(env) : 0;
-        bool ring = !h->force_classic && mode != 0 && (mode == 1 || classic_doubles * 8 > (long long)K * chunk_bytes);
+        h->ring_serial = mode == 3 || mode == 4;             // 3: serial ring always, 4: when the arena exceeds the ring
+        if (const char* eg = getenv("GFA_RING_GROUP")) if (atoi(eg) >= 1) h->ring_group = atoi(eg);
+        if (h->ring_serial && K < h->ring_group + 2) K = h->ring_group + 2;
+        bool ring = !h->force_classic && mode != 0 && (mode == 1 || mode == 3 || classic_doubles * 8 > (long long)K * chunk_bytes);
         h->ring_note = h->force_classic ? "classic: dynamics / explicit request" : mode == 0 ? "classic (GFA_RING=1 selects the ring pipeline)" : "classic: the element arena fits the ring";
         std::vector<std::vector<unsigned char> > pinned(3);
         int ce[3] = { 1, 1, 1 };
@@ -771,8 +777,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                 for (size_t k = 0; k < t.pin_list.size(); k++) t.ke_off[t.pin_list[k]] = t.pin_base + (long long)k * arena_doubles(s);
             }
             char buf[256];
-            snprintf(buf, sizeof(buf), "ring: %d chunks of %.1f MB (%lld total), span %d, %lld elements through the ring, %lld pinned",
-                     K, chunk_doubles * 8 / 1048576.0, tot_chunks, span, n_ring, n_pinned);
+            snprintf(buf, sizeof(buf), "%s: %d chunks of %.1f MB (%lld total), span %d, %lld elements through the ring, %lld pinned",
+                     h->ring_serial ? "serial ring" : "ring", K, chunk_doubles * 8 / 1048576.0, tot_chunks, span, n_ring, n_pinned);
             h->ring_note = buf;
         } else {
             h->ring_chunks = 0; h->ring_span = 0; h->total_chunks = 0; h->chunk_doubles = 0; h->ring_doubles = 0;
@@ -1172,6 +1178,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             chunk_tile_ptr[c + 1] = chunk_tile_ptr[c] + (int)tiles;
         }
         CUDA_TRY(h->d_chunk_run_ptr.upload(chunk_run_ptr));
+        h->chunk_run_ptr_h = chunk_run_ptr;
         CUDA_TRY(h->d_chunk_tile_ptr.upload(chunk_tile_ptr));
         std::vector<int> chunk_batches((size_t)h->total_chunks, 0);
         for (int sl = 0; sl < 3; sl++) {
@@ -1469,6 +1476,27 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
         sp.runs += h->n_iface_runs; sp.n_runs = h->n_pre_runs - h->n_iface_runs; sp.n_gn = 0;
         launches += launch_scatter(sp, s);
         CUDA_TRY(cudaEventRecord(h->ev[2], s));
+        if (h->ring_serial) {
+            // ---- serial ring: the classic kernels, launched group by group.  A group of chunks is evaluated into the
+            // ring and the group-nodes it completes are scattered right behind it, while their blocks are still in L2;
+            // stream order is the only synchronisation (a slot is rewritten ring_chunks chunks later, after every
+            // scatter launch that read it)
+            for (int slot = 0; slot < 3; slot++) {
+                const TypeBlock& t = h->tb[slot];
+                if (t.ring_list.empty()) continue;
+                EvalArgs ea = eval_args(h, slot, st->gravity_factor, PASS_RING);
+                for (int c0 = 0; c0 < t.n_chunks; c0 += h->ring_group) {
+                    const int c1 = std::min(t.n_chunks, c0 + h->ring_group);
+                    ea.e_begin = c0 * t.chunk_el; ea.e_end = (int)std::min<long long>((long long)c1 * t.chunk_el, (long long)t.ring_list.size());
+                    if (slot == 0) launch_shell_eval(ea, s); else if (slot == 1) launch_beam_eval(ea, s); else launch_solid_eval(ea, s);
+                    ScatterArgs sg = sa;
+                    sg.runs += h->chunk_run_ptr_h[(size_t)t.chunk0 + c0];
+                    sg.n_runs = h->chunk_run_ptr_h[(size_t)t.chunk0 + c1] - h->chunk_run_ptr_h[(size_t)t.chunk0 + c0];
+                    sg.n_gn = 0;
+                    launches += 1 + launch_scatter(sg, s);
+                }
+            }
+        } else {
         // ---- ring pipeline: the scatter kernel on its own stream, the evaluation kernels (one per element type)
         // beside it; the two talk through the control block
         CUDA_TRY(cudaMemsetAsync(h->d_ctl.p, 0, h->d_ctl.n * sizeof(unsigned), s));
@@ -1500,11 +1528,12 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
             }
         }
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_scattered, 0));
+        h->abort_check_pending = true;
+        }
         // residual vectors of the remaining group-nodes (the element force arena holds every element)
         ScatterArgs sv = sa;
         sv.gn += h->n_iface_gn; sv.n_gn -= h->n_iface_gn;
         if (sv.n_gn > 0) { launch_vectors(sv, s); launches++; }
-        h->abort_check_pending = true;
     }
     CUDA_TRY(cudaEventRecord(h->ev[3], s));
     CUDA_TRY(cudaGetLastError());

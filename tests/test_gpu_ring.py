@@ -93,6 +93,34 @@ def test_ring_pipeline_against_oracle_and_classic(monkeypatch, port, case):
     assert ring.values("AA").tobytes() == v1.tobytes()
 
 
+@pytest.mark.parametrize("group", [1, 3])
+def test_serial_ring_matches_classic_bitwise(monkeypatch, port, group):
+    """GFA_RING=3: the ring placement with the classic kernels launched group by group (evaluate a few chunks,
+    scatter what they complete while the blocks are still in L2); stream order is the only synchronisation."""
+    rng = np.random.default_rng(5)
+    for name, m, chunk_kb in (("shell", M.shell_plate(40, 25, warp=0.01, gravity=(0.0, 0.0, -9.81)), 256),
+                              ("mixed", M.concat_models([M.beam_line(700), M.pipe_line(300), M.shell_plate(30, 14, warp=0.005), M.solid_block(8, 7, 6)]), 256)):
+        d = M.mask_displacements(m, rng.uniform(-1e-4, 1e-4, (m.n_nodes, 6)))
+        monkeypatch.setenv("GFA_RING_GROUP", str(group))
+        ring, is_ring, note = _assembler(monkeypatch, m, True, chunk_kb, 9)
+        monkeypatch.setenv("GFA_RING", "3")
+        serial = capi.Assembler(m).set_dofs()
+        assert serial.pipeline_info()[0] and "serial" in serial.pipeline_info()[1], serial.pipeline_info()
+        classic, _, _ = _assembler(monkeypatch, m, False)
+        port.load(m)
+        port.set_time(0.0, 1.0)
+        port.assemble(d)
+        for a in (serial, classic):
+            a.set_time(0.0, 1.0)
+            a.assemble(d)
+            a.assemble(d)
+        _compare(port, serial, f"serial ring {name}")
+        for w in ("AA", "AB", "BA", "BB"):
+            assert serial.values(w).tobytes() == classic.values(w).tobytes(), f"{name}: serial ring and classic {w} differ"
+        for x, y in zip(serial.vectors(), classic.vectors()):
+            assert x.tobytes() == y.tobytes()
+
+
 def test_ring_with_scrambled_element_numbering(monkeypatch, port):
     """Element numbering without locality: group-nodes whose elements lie further apart than the ring reaches
     are served from pinned regions (or the whole model falls back to the classic kernels) -- same results."""
