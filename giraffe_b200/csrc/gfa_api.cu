@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gfa.h"
@@ -549,6 +550,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     h->ex_rows.assign(ex_rows, ex_rows + (n_extra > 0 ? n_extra : 0));
     h->ex_cols.assign(ex_cols, ex_cols + (n_extra > 0 ? n_extra : 0));
 
+    // launchers such as torchrun pin OMP_NUM_THREADS to 1 per process: take this rank's share of the host cores instead
+    const int host_threads = std::max(1, (int)std::thread::hardware_concurrency() / std::max(1, h->world));
     // ---- group-node adjacency over ALL elements (every rank builds the same pattern)
     const size_t n_gn_all = (size_t)h->n_nodes * 2;
     std::vector<int> gptr(n_gn_all + 1, 0);
@@ -603,7 +606,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     std::vector<long long> nptr(n_gn_all + 1, 0);
     {
         std::vector<int> cnt(n_gn_all, 0);
-#pragma omp parallel
+#pragma omp parallel num_threads(host_threads)
         {
             std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
@@ -624,7 +627,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         for (size_t i = 0; i < n_gn_all; i++) nptr[i + 1] = nptr[i] + cnt[i];
     }
     std::vector<int> nbr((size_t)nptr[n_gn_all]);
-#pragma omp parallel
+#pragma omp parallel num_threads(host_threads)
     {
         std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
@@ -844,7 +847,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     const long long nnzAA = AA.rowptr[AA.rows];
     if (nnzAA > 0x7fffffffLL) return fail(GFA_EUNSUPPORTED, "AA has %lld non-zeros on this rank; 32-bit CSR (PARDISO/Eigen int) cannot hold it", nnzAA);
     AA.inner.resize((size_t)nnzAA);
-#pragma omp parallel for schedule(dynamic, 4096)
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(host_threads)
     for (long long gn = 0; gn < (long long)n_gn_all; gn++) {
         if (!need[gn]) continue;
         for (int k = 0; k < 3; k++) {

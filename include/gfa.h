@@ -18,6 +18,17 @@
  * There is no CPU fallback: without a CUDA device gfa_create fails with
  * GFA_ENODEVICE.
  */
+/* Limits of the slot map (gfa_set_dofs refuses what exceeds them with GFA_EUNSUPPORTED; none is reached by the
+ * BASELINE configs):
+ *   - DOF numbering: the reference's own (src/Solution.cpp:53-72) -- free ids ascending with (node, DOF), the free
+ *     DOFs of one node's translations (rotations) consecutive; DOFs beyond the node table (Lagrange multipliers,
+ *     super nodes) may take any ids that leave those groups intact and enter through gfa_set_dofs' extra positions;
+ *   - AA non-zeros per rank < 2^31 (Eigen / PARDISO 32-bit indices; the reference's own `int size_AA` overflows
+ *     at ~2.9 M shells, src/Solution.cpp:579);
+ *   - a CSR row of an element-only group-node holds at most 65 535 entries (16-bit row stride of a patch);
+ *   - at most 255 elements of one rank share a pair of 3-DOF groups (8-bit source count of a patch);
+ *   - element arena of one rank < 2^32 doubles (32-bit block offsets: 34 GB, ~9.6 M shells or 13 M solids);
+ *   - at most 64 ranks (interface bookkeeping keeps rank sets in 64 bits). */
 #ifndef GFA_H
 #define GFA_H
 
