@@ -1,5 +1,2 @@
-export GFA_FUSED_TIMEOUT_MS=2000
-timeout 900 python -m pytest tests/test_gpu_ring.py -q -x -k "serial" 2>&1 | tail -4
-for cfg in "GFA_RING=3 GFA_RING_CHUNK_KB=7188 GFA_RING_GROUP=4" "GFA_RING=3 GFA_RING_CHUNK_KB=7188 GFA_RING_GROUP=8" "GFA_RING=3 GFA_RING_CHUNK_KB=7188 GFA_RING_GROUP=12" "GFA_RING=3 GFA_RING_CHUNK_KB=7188 GFA_RING_GROUP=8 GFA_RING_PERSIST=0" "GFA_RING=3 GFA_RING_CHUNK_KB=7188 GFA_RING_GROUP=2" "GFA_RING=3 GFA_RING_CHUNK_KB=14376 GFA_RING_GROUP=4"; do
-timeout 300 python tools/ring_probe.py steps=20 $cfg 2>&1 | grep -E "RESULT|rror|abort" | head -3 | cut -c1-330
-done
+export GFA_SHELL_PAIR=1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:eval_pair -s 3 -c 1 -f -o gpurun_out/prof_eval_pair_a python tools/ring_probe.py steps=1 2>&1 | grep -E "rror" | tail -3
