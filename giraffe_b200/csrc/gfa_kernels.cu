@@ -1969,32 +1969,43 @@ static int shell_epw() {
     }
     return v;
 }
+// Persistent grids are sized by what is resident on the CURRENT device (occupancy query x SM count), cached per
+// device: handles on different GPUs of one process each get their own figure.
+constexpr int kMaxDevices = 64;
+static int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= kMaxDevices ? 0 : d; }
+static int sm_count() {
+    static int sms[kMaxDevices] = { 0 };
+    const int d = current_device();
+    if (!sms[d] && (cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d) != cudaSuccess || sms[d] < 1)) sms[d] = kSMs;
+    return sms[d];
+}
+// resident one-warp CTAs on the whole device for a kernel (persistent grid)
+template <class K>
+static int resident_ctas(K kernel, int smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 32, smem) != cudaSuccess || n < 1) n = 8;
+    return sm_count() * n;
+}
 void launch_shell_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
     const int epw = shell_epw();
     // persistent warps: exactly as many one-warp CTAs as are resident (7 per SM with 8-element
     // batches), each striding over the batches -- 5 % faster than 64 CTAs per SM taking turns
     // (profiles/r01_notes.md); GFA_SHELL_GRID overrides the CTAs per SM
-    static int per_sm = 0;
-    if (!per_sm) {
+    static int caps[kMaxDevices] = { 0 };
+    int& cap = caps[current_device()];
+    if (!cap) {
         const char* e = getenv("GFA_SHELL_GRID");
-        per_sm = e ? atoi(e) : 0;
-        if (per_sm < 1) {
-            int n = 0;
-            cudaError_t err = cudaErrorUnknown;
-            switch (epw) {
-            case 7: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<7>, 32, shell::smem_bytes(7)); break;
-            case 9: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<9>, 32, shell::smem_bytes(9)); break;
-            case 6: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<6>, 32, shell::smem_bytes(6)); break;
-            case 8: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<8>, 32, shell::smem_bytes(8)); break;
-            default: err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shell::eval_kernel<10>, 32, shell::smem_bytes(10)); break;
-            }
-            per_sm = (err == cudaSuccess && n > 0) ? n : 8;
+        const int forced = e ? atoi(e) : 0;
+        if (forced >= 1) cap = sm_count() * forced;
+        else switch (epw) {
+            case 7: cap = resident_ctas(shell::eval_kernel<7>, shell::smem_bytes(7)); break;
+            case 9: cap = resident_ctas(shell::eval_kernel<9>, shell::smem_bytes(9)); break;
+            case 6: cap = resident_ctas(shell::eval_kernel<6>, shell::smem_bytes(6)); break;
+            case 8: cap = resident_ctas(shell::eval_kernel<8>, shell::smem_bytes(8)); break;
+            default: cap = resident_ctas(shell::eval_kernel<10>, shell::smem_bytes(10)); break;
         }
     }
-    int n_sm = kSMs;
-    { static int sms = 0; if (!sms) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs; } n_sm = sms; }
-    const int cap = n_sm * per_sm;
     const int grid = grid_for(a.e_end - a.e_begin, epw, cap);
     cudaStream_t st = (cudaStream_t)s;
     switch (epw) {
@@ -2005,25 +2016,18 @@ void launch_shell_eval(const EvalArgs& a, void* s) {
     default: shell::eval_kernel<10><<<grid, 32, shell::smem_bytes(10), st>>>(a); break;
     }
 }
-// resident one-warp CTAs on the whole device for a kernel (persistent grid)
-template <class K>
-static int resident_ctas(K kernel, int smem) {
-    int n = 0, dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 32, smem) != cudaSuccess || n < 1) n = 8;
-    return sms * n;
-}
 void launch_beam_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
-    static int cap = 0;
+    static int caps[kMaxDevices] = { 0 };
+    int& cap = caps[current_device()];
     if (!cap) cap = resident_ctas(beam::eval_kernel, beam::SMEM_BYTES);
     const int grid = grid_for(a.e_end - a.e_begin, beam::EPW, cap);
     beam::eval_kernel<<<grid, 32, beam::SMEM_BYTES, (cudaStream_t)s>>>(a);
 }
 void launch_solid_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
-    static int cap = 0;
+    static int caps[kMaxDevices] = { 0 };
+    int& cap = caps[current_device()];
     if (!cap) cap = resident_ctas(solid::eval_kernel, solid::SMEM_BYTES);
     const int grid = grid_for(a.e_end - a.e_begin, solid::EPW, cap);
     solid::eval_kernel<<<grid, 32, solid::SMEM_BYTES, (cudaStream_t)s>>>(a);
@@ -2089,12 +2093,6 @@ int fused_buffers(int slot) {
     // what the scatter CTA's staging buffers and the two reserved kilobytes leave of an SM's 228 KB
     const int n = (226 * 1024 - FUSED_SCATTER_WARPS * fused::STAGE_BYTES) / per;
     return n < FUSED_WARPS ? n : FUSED_WARPS;
-}
-static int sm_count() {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = kSMs;
-    return sms;
 }
 int launch_fused_eval(const FusedArgs& f, void* s) {
     const int nb = f.n_buf, sms = sm_count();

@@ -76,7 +76,13 @@ def main():
         else:
             asm.assemble(d)
             ex()
-            asm.assemble(d)      # a second Newton iteration on the same pattern: slots are rewritten, not accumulated
+            # a second Newton iteration on the same pattern (slots are rewritten, not accumulated), this time with the
+            # partition-local upload: only the nodes this rank's elements reference travel
+            nodes = asm.touched_nodes()
+            packed = np.ascontiguousarray(d.reshape(-1, 6)[nodes]).reshape(-1)
+            asm.assemble(np.full_like(d, 123.0))        # poison the device copy first
+            asm.set_displacements_packed(packed.ctypes.data)
+            asm.assemble(None)
             ex()
             for _ in range(3):   # and queued ones: the exchange overlaps the scatter of the interior rows
                 asm.assemble_enqueue(None)
@@ -96,6 +102,8 @@ def main():
             worst = max(worst, util.parity_error(rv[ra:rb], lv[a:b], scale))
         pa, ia, pb = asm.vectors()
         e_pa = util.parity_error(rpa[owned], pa[owned], float(np.abs(rpa).max()))
+        po = asm.vector_owned(capi.P_A, np.zeros(len(owned)))
+        assert po.tobytes() == np.ascontiguousarray(pa[owned]).tobytes(), f"{name}: gfa_vector_owned differs from the owned entries of gfa_vector"
         counts = torch.tensor([len(owned)], device="cuda")
         dist.all_reduce(counts)
         good = worst <= util.TOL and e_pa <= util.TOL and int(counts.item()) == asm.n_free

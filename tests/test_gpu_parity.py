@@ -56,6 +56,62 @@ def test_tutorial01_against_reference_fixture():
     util.assert_parity(z["elem0_K"], K, "tutorial01 element 1 K", util.block_scale(z["elem0_K"]))
 
 
+def test_tutorial01_static_solution_in_lockstep_with_the_reference(ref):
+    """inputs/tutorial01 solved to the end -- ten increments of Static::Solve's Newton loop (Static.cpp:161-236) --
+    twice: through the reference's own sources (assembly, MountLoads, sign flip, UpdateDisps, SaveConfiguration)
+    and through the library (gfa_assemble, the host NodalLoad pushed with gfa_add_host_*, gfa_residual,
+    gfa_update_displacements on the device copy, gfa_commit_state), the same sparse solve in between.  The
+    configurations must stay together increment by increment."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    z = _golden("tutorial01")
+    m = util.model_from_dict(z)
+    dt = float(z["time"][1])
+    ref.load(m)
+    asm = capi.Assembler(m)
+    gls, nf, nx = asm.number_dofs()
+    asm.set_dofs(gls, nf, nx)
+    t = 0.0
+    for inc in range(10):
+        ref.set_time(t, dt)
+        asm.set_time(t, dt)
+        d_ref = np.zeros((m.n_nodes, 6))
+        asm.assemble(np.zeros((m.n_nodes, 6)))              # start of the increment: zero increments on the device
+        first = True
+        for it in range(8):
+            # the reference's own loop
+            ref.assemble(d_ref, with_loads=True)
+            ref.residual(None)
+            o, i, v, shape = ref.csr("AA")
+            x = spla.spsolve(sp.csr_matrix((v, i, o), shape=shape).tocsc(), ref.vectors()[0])
+            d_ref = ref.update_displacements(x)[0]
+            # the library's
+            if not first:
+                asm.assemble(None)                              # the device copy left by gfa_update_displacements
+            first = False
+            d_dev = asm.displacements()
+            trip, pa_add, pb_add = util.nodal_load_contribution(m, gls, d_dev, t + dt)
+            for w in ("AA", "AB", "BA", "BB"):
+                if trip[w][0]:
+                    asm.add_host_triplets(w, *trip[w])
+            asm.add_host_vector(capi.P_A, *pa_add)
+            if pb_add[0]:
+                asm.add_host_vector(capi.P_B, *pb_add)
+            norms = asm.residual(None)
+            o2, i2, v2, shape2 = asm.csr("AA")
+            x2 = spla.spsolve(sp.csr_matrix((v2, i2, o2), shape=shape2).tocsc(), asm.vectors()[0])
+            inc_norms = asm.update_displacements(x2)
+            assert not norms["nan_detected"] and not inc_norms["nan_detected"]
+        assert np.abs(x2).max() <= 1e-9 * max(np.abs(asm.displacements()).max(), 1e-30), "Newton did not converge in 8 iterations"
+        util.assert_parity(d_ref, asm.displacements(), f"tutorial01 increment {inc + 1}: converged increments", tol=1e-9)
+        ref.commit()
+        asm.commit()
+        util.assert_parity(ref.copy_coordinates(), asm.copy_coordinates(), f"tutorial01 increment {inc + 1}: configuration", tol=1e-10)
+        t += dt
+    tip = asm.copy_coordinates()[-1, :3] - m.xyz[-1]
+    assert np.abs(tip).max() > 1e-6, "the load did not move the structure"
+
+
 @pytest.mark.parametrize("name", ["beam_line", "pipe_line", "shell_plate"])
 def test_sequence_against_reference_fixture(name):
     z = _golden(name)
