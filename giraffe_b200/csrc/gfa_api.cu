@@ -188,7 +188,8 @@ struct gfa_handle {
     std::string ring_note;                // why the classic path was chosen, or the ring geometry
     // arguments of the last gfa_set_dofs (replayed when a handle has to leave ring mode)
     std::vector<int> ex_mat, ex_rows, ex_cols;
-    long long n_vec_untouched = 0;        // vector entries no element of this rank writes (zeroed per assembly)
+    long long n_vec_untouched = 0;        // vector entries no element of this rank writes (zeroed per assembly ...
+    bool vec_dirty = false;               // ... when something has been added to the vectors since they were last zero)
     // persistent staging of gfa_add_host_*
     DevBuf<long long> d_stage_slots; DevBuf<double> d_stage_vals;
     std::vector<long long> stage_slots; std::vector<double> stage_vals;
@@ -517,7 +518,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                  int64_t n_extra, const int32_t* ex_mat, const int32_t* ex_rows, const int32_t* ex_cols) {
     if (!h || !GLs) return fail(GFA_EINVAL, "gfa_set_dofs: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    h->dofs_set = false; h->assembled = false;
+    h->dofs_set = false; h->assembled = false; h->vec_dirty = false;
     h->d_owned_idx.release();
     h->n_shell_loads = 0; h->n_load_entries = 0; h->n_load_dest = 0;      // registered against the old DOF map
     h->n_free = n_free; h->n_fixed = n_fixed;
@@ -1424,8 +1425,12 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
     if (st->displacements)       // NULL: keep the device copy (gfa_update_displacements)
         CUDA_TRY(cudaMemcpyAsync(h->d_disp.p, st->displacements, nd,
                                  st->displacements_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-    if (h->n_vec_untouched > 0)  // Solution::Clear for the vector entries no element writes
+    if (h->n_vec_untouched > 0 && h->vec_dirty) {   // Solution::Clear for the vector entries no element writes: they start at
+        // zero (gfa_set_dofs) and only gfa_add_host_vector can have changed them (shell loads, the interface unpack and
+        // K_AB X_B add into rows that elements write; negating a zero leaves a zero)
         CUDA_TRY(cudaMemsetAsync(h->d_arena.p + h->vec_off[GFA_P_A], 0, (size_t)(h->arena_size - h->vec_off[GFA_P_A]) * sizeof(double), s));
+        h->vec_dirty = false;
+    }
     CUDA_TRY(cudaEventRecord(h->ev[1], s));
     ScatterArgs sa;
     sa.n_runs = h->n_runs; sa.runs = h->d_runs.p; sa.ovf = h->d_ovf.p;
@@ -1686,6 +1691,7 @@ int gfa_add_host_vector(gfa_t* h, int wv, int64_t n, const int32_t* index, const
     if (n <= 0) return GFA_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     const int len = wv == GFA_P_B ? h->n_fixed : h->n_free;
+    h->vec_dirty = true;
     std::vector<std::pair<long long, double> >& items = h->stage_items;
     items.clear();
     for (int64_t i = 0; i < n; i++) {
