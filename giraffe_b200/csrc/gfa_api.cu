@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -103,9 +104,19 @@ struct TypeBlock {
     DevBuf<double> d_alpha_i, d_dynrec, d_CR;
 };
 
+// std::vector whose resize() leaves new elements uninitialised: the 2 GB column array of a 1M-shell AA is written
+// once, in parallel, right after it is sized -- zero-filling it first costs half a second of one core
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U, class... Args> void construct(U* p, Args&&... args) {
+        if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<Args>(args)...);
+    }
+};
+
 struct HostCsr {
     std::vector<long long> rowptr;
-    std::vector<int> inner;
+    std::vector<int, NoInitAlloc<int> > inner;
     int rows = 0, cols = 0;
     // AA only: rows stored on this rank (all rows when world == 1) and the
     // inverse map global row -> local row (-1 = row lives on other ranks only)
@@ -551,6 +562,14 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     h->ex_rows.assign(ex_rows, ex_rows + (n_extra > 0 ? n_extra : 0));
     h->ex_cols.assign(ex_cols, ex_cols + (n_extra > 0 ? n_extra : 0));
 
+    const bool timing = getenv("GFA_SETUP_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gfa] set_dofs %-28s %7.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     // launchers such as torchrun pin OMP_NUM_THREADS to 1 per process: take this rank's share of the host cores instead
     const int host_threads = std::max(1, (int)std::thread::hardware_concurrency() / std::max(1, h->world));
     // ---- group-node adjacency over ALL elements (every rank builds the same pattern)
@@ -580,6 +599,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     auto fix_mask = [&](size_t gn) { int mk = 0; for (int k = 0; k < 3; k++) if (gls[3 * gn + k] < 0) mk |= 1 << k; return mk; };
     // note: gls is [node][6] = [group-node][3] with gn = node*2 + grp
 
+    lap("adjacency");
     // ---- which rank evaluates which element (same rule as gfa_create) -----
     std::vector<int> el_rank;
     if (h->world > 1) {
@@ -648,6 +668,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         }
     }
 
+    lap("neighbour lists");
     // ---- host positions outside the element pattern (Solution.cpp:268-281, 322-349: joints, contacts and other
     //      contributors push arbitrary triplets into the same lists).  An extra AA position whose column group is not a
     //      neighbour of its row group -- or that involves a DOF beyond the node table (Lagrange multipliers, super
@@ -675,6 +696,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     auto row_extras = [&](int r) { return std::equal_range(xtra.begin(), xtra.end(), std::make_pair(r, 0), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first < y.first; }); };
 
 
+    lap("extras");
     // ---- arena placement -------------------------------------------------------------------------
     // classic: every local element owns a region of one big arena (written by the evaluation kernel, read back
     // by the scatter kernel through DRAM).  ring: elements are evaluated chunk by chunk into an L2-resident ring
@@ -816,6 +838,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         return rc;
     };
 
+    lap("placement");
     // ---- AA pattern: rows of a group-node share one column layout.  Stored
     //      rows are numbered in ascending global order (all rows when world == 1,
     //      so the single-GPU CSR is exactly the reference's). ------------------
@@ -878,6 +901,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         for (size_t j = i; j < xtra.size() && xtra[j].first == r; j++) *out++ = xtra[j].second;
     }
 
+    lap("AA pattern");
     // ---- AB / BA / BB: explicit entry lists of elements that touch a fixed DOF
     struct Ent { int mat, row, col; long long src; int rank; };
     std::vector<Ent> ents;      // pattern from all elements; src = -1 when the element is not this rank's
@@ -994,6 +1018,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     }
     for (int w = 1; w < 4; w++) { HostCsr& M = h->csr[w]; for (int r = 0; r < M.rows; r++) M.rowptr[r + 1] += M.rowptr[r]; }
 
+    lap("fixed-DOF entries");
     // ---- value arena: [AA | AB | BA | BB | P_A | I_A | P_B] ----------------
     long long off = 0;
     for (int w = 0; w < 4; w++) { h->arena_off[w] = off; off += (long long)h->csr[w].inner.size(); }
@@ -1017,6 +1042,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             else send_small[owner].push_back(gdest[i]);
         }
 
+    lap("arena offsets");
     // ---- interface ownership (owner = lowest rank with an incidence), ascending group-node
     //      order on every rank so that the send and receive lists pair up ----------------------
     std::vector<std::vector<long long> > send_idx(h->world), recv_idx(h->world);
@@ -1092,81 +1118,127 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     size_t n_iface_touched = 0;
     for (char c : touched_iface) n_iface_touched += c ? 1 : 0;
 
+    lap("ownership + ordering");
     // ---- slot map of this rank's group-nodes ----------------------------------
-    // For every (group-node, neighbour) patch: the local element blocks feeding it, element-ascending.
+    // For every (group-node, neighbour) patch: the local element blocks feeding it, element-ascending.  Built in
+    // parallel: contiguous pieces of the (ordered) group-node list go to per-piece buffers that are concatenated in
+    // order afterwards, indices shifted by the pieces' offsets.
     std::vector<PInc> incs;
     std::vector<RunEnt> runs;
     std::vector<unsigned long long> ovf;
-    std::vector<std::vector<unsigned long long> > run_src;   // scratch: sources per patch of the current group-node
-    std::vector<GnRec> gn_recs;
+    std::vector<GnRec> gn_recs(touched_gn.size());
+    std::vector<int> run_count(touched_gn.size(), 0);        // patches emitted per group-node
     h->n_iface_runs = 0; h->n_iface_gn = 0;
     std::vector<long long> chunk_run_ptr((size_t)h->total_chunks + 1, 0);
-    int crp_filled = 0;                              // chunk_run_ptr[0 .. crp_filled) are final
-    for (size_t ti_ = 0; ti_ < touched_gn.size(); ti_++) {
-        if (ti_ == n_iface_touched) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)gn_recs.size(); }
-        const size_t gn = (size_t)touched_gn[ti_];
-        if (h->ring) for (; crp_filled <= touched_rc[ti_]; crp_filled++) chunk_run_ptr[crp_filled] = (long long)runs.size();
-        const int first_inc = (int)incs.size();
-        const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
-        const int n_runs = (int)(nb1 - nb0);
-        if ((int)run_src.size() < n_runs) run_src.resize(n_runs);
-        for (int j = 0; j < n_runs; j++) run_src[j].clear();
-        for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
-            const int e = ginc_e[p];
-            if (h->el_owner_slot[e] < 0) continue;
-            const int s = h->el_owner_slot[e], local = h->el_local[e];
-            const TypeInfo& ti = kTypes[s];
-            const int la = ginc_b[p];
-            PInc in;
-            in.pe_off = h->tb[s].pe_base + local * ti.ndof;
-            in.la = la;
-            incs.push_back(in);
-            for (int b = 0; b < ti.nb; b++) {
-                int a, grp; block_node(s, b, a, grp);
-                const int other = h->el_nodes[h->el_ptr[e] + a] * 2 + grp;
-                const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
-                bool tr;
-                const long long blk = arena_block(h, s, local, la, b, tr);
-                if (blk >= (1LL << 32)) return fail(GFA_EUNSUPPORTED, "element arena too large for the 32-bit block offsets of the slot map");
-                run_src[j].push_back((unsigned long long)blk | (tr ? SRC_T : 0ULL));
+    {
+        const size_t T = touched_gn.size();
+        const int n_pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads * 8, (T + 4095) / 4096));
+        struct Piece { std::vector<PInc> incs; std::vector<RunEnt> runs; std::vector<unsigned long long> ovf; std::vector<size_t> ovf_runs; int err = 0; };
+        std::vector<Piece> pieces((size_t)n_pieces);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads)
+        for (int pc = 0; pc < n_pieces; pc++) {
+            Piece& P = pieces[(size_t)pc];
+            std::vector<std::vector<unsigned long long> > run_src;   // scratch: sources per patch of the current group-node
+            const size_t t0 = T * (size_t)pc / (size_t)n_pieces, t1 = T * (size_t)(pc + 1) / (size_t)n_pieces;
+            for (size_t ti_ = t0; ti_ < t1 && !P.err; ti_++) {
+                const size_t gn = (size_t)touched_gn[ti_];
+                const int first_inc = (int)P.incs.size();
+                const int* nb0 = nbr.data() + nptr[gn]; const int* nb1 = nbr.data() + nptr[gn + 1];
+                const int n_runs = (int)(nb1 - nb0);
+                if ((int)run_src.size() < n_runs) run_src.resize(n_runs);
+                for (int j = 0; j < n_runs; j++) run_src[j].clear();
+                for (int p = gptr[gn]; p < gptr[gn + 1]; p++) {
+                    const int e = ginc_e[p];
+                    if (h->el_owner_slot[e] < 0) continue;
+                    const int sl = h->el_owner_slot[e], local = h->el_local[e];
+                    const TypeInfo& ti = kTypes[sl];
+                    const int la = ginc_b[p];
+                    PInc in;
+                    in.pe_off = h->tb[sl].pe_base + local * ti.ndof;
+                    in.la = la;
+                    P.incs.push_back(in);
+                    for (int bb = 0; bb < ti.nb; bb++) {
+                        int an, grp; block_node(sl, bb, an, grp);
+                        const int other = h->el_nodes[h->el_ptr[e] + an] * 2 + grp;
+                        const int j = (int)(std::lower_bound(nb0, nb1, other) - nb0);
+                        bool tr;
+                        const long long blk = arena_block(h, sl, local, la, bb, tr);
+                        if (blk >= (1LL << 32)) { P.err = 1; break; }
+                        run_src[j].push_back((unsigned long long)blk | (tr ? SRC_T : 0ULL));
+                    }
+                }
+                GnRec rec;
+                int rm = 0, first_row = -1;
+                for (int k = 0; k < 3; k++) {
+                    const int g = gls[3 * gn + k];
+                    rec.gl[k] = g;
+                    if (g > 0) { rm |= 1 << k; if (first_row < 0) first_row = AA.row_local[g - 1]; }
+                }
+                rec.ib = first_inc; rec.ie = (int)P.incs.size();      // piece-local: shifted below
+                gn_recs[ti_] = rec;
+                if (!rm || irregular[gn]) continue;      // rows with host positions are filled through the explicit lists
+                const long long row0 = AA.rowptr[first_row];
+                int col = 0;
+                const size_t runs_before = P.runs.size();
+                for (int j = 0; j < n_runs; j++) {
+                    const int fm = free_mask((size_t)nb0[j]);
+                    const std::vector<unsigned long long>& src = run_src[j];
+                    const long long dst = row0 + col;
+                    col += __builtin_popcount(fm);
+                    if (!fm) continue;
+                    if (src.empty() && h->world == 1) continue;      // cannot happen: every stored patch has a local source
+                    if (src.size() > 255) { P.err = 2; break; }
+                    RunEnt r;
+                    r.dst = (int)dst;
+                    r.info = (unsigned)rowL[gn] | ((unsigned)rm << 16) | ((unsigned)fm << 19) | ((unsigned)src.size() << 24);
+                    r.src0 = src.size() > 0 ? (unsigned)src[0] : 0u; r.src1 = src.size() > 1 ? (unsigned)src[1] : 0u;
+                    if (src.size() > 0 && (src[0] & SRC_T)) r.info |= 1u << 22;
+                    if (src.size() > 1 && (src[1] & SRC_T)) r.info |= 1u << 23;
+                    if (src.size() > 2) {
+                        r.src0 = (unsigned)P.ovf.size();                  // piece-local: shifted below
+                        P.ovf_runs.push_back(P.runs.size());
+                        P.ovf.insert(P.ovf.end(), src.begin(), src.end());
+                    }
+                    P.runs.push_back(r);
+                }
+                run_count[ti_] = (int)(P.runs.size() - runs_before);
             }
         }
-        GnRec rec;
-        int rm = 0, first_row = -1;
-        for (int k = 0; k < 3; k++) {
-            const int g = gls[3 * gn + k];
-            rec.gl[k] = g;
-            if (g > 0) { rm |= 1 << k; if (first_row < 0) first_row = AA.row_local[g - 1]; }
+        for (const Piece& P : pieces) {
+            if (P.err == 1) return fail(GFA_EUNSUPPORTED, "element arena too large for the 32-bit block offsets of the slot map");
+            if (P.err == 2) return fail(GFA_EUNSUPPORTED, "group-node with more than 255 incident elements");
         }
-        rec.ib = first_inc; rec.ie = (int)incs.size();
-        gn_recs.push_back(rec);
-        if (!rm || irregular[gn]) continue;      // rows with host positions are filled through the explicit lists
-        const long long row0 = AA.rowptr[first_row];
-        int col = 0;
-        for (int j = 0; j < n_runs; j++) {
-            const int fm = free_mask((size_t)nb0[j]);
-            const std::vector<unsigned long long>& src = run_src[j];
-            const long long dst = row0 + col;
-            col += __builtin_popcount(fm);
-            if (!fm) continue;
-            if (src.empty() && h->world == 1) continue;      // cannot happen: every stored patch has a local source
-            if (src.size() > 255) return fail(GFA_EUNSUPPORTED, "group-node with more than 255 incident elements");
-            RunEnt r;
-            r.dst = (int)dst;
-            r.info = (unsigned)rowL[gn] | ((unsigned)rm << 16) | ((unsigned)fm << 19) | ((unsigned)src.size() << 24);
-            r.src0 = src.size() > 0 ? (unsigned)src[0] : 0u; r.src1 = src.size() > 1 ? (unsigned)src[1] : 0u;
-            if (src.size() > 0 && (src[0] & SRC_T)) r.info |= 1u << 22;
-            if (src.size() > 1 && (src[1] & SRC_T)) r.info |= 1u << 23;
-            if (src.size() > 2) {
-                if (ovf.size() >= (1ULL << 32)) return fail(GFA_EUNSUPPORTED, "overflow source list exceeds 2^32 entries");
-                r.src0 = (unsigned)ovf.size(); ovf.insert(ovf.end(), src.begin(), src.end());
-            }
-            runs.push_back(r);
+        std::vector<size_t> inc_off((size_t)n_pieces + 1, 0), run_off((size_t)n_pieces + 1, 0), ovf_off((size_t)n_pieces + 1, 0);
+        for (int pc = 0; pc < n_pieces; pc++) {
+            inc_off[(size_t)pc + 1] = inc_off[(size_t)pc] + pieces[(size_t)pc].incs.size();
+            run_off[(size_t)pc + 1] = run_off[(size_t)pc] + pieces[(size_t)pc].runs.size();
+            ovf_off[(size_t)pc + 1] = ovf_off[(size_t)pc] + pieces[(size_t)pc].ovf.size();
         }
+        if (inc_off[(size_t)n_pieces] > 0x7fffffffULL) return fail(GFA_EUNSUPPORTED, "more than 2^31 (group-node, element) incidences on one rank");
+        if (ovf_off[(size_t)n_pieces] >= (1ULL << 32)) return fail(GFA_EUNSUPPORTED, "overflow source list exceeds 2^32 entries");
+        incs.resize(inc_off[(size_t)n_pieces]); runs.resize(run_off[(size_t)n_pieces]); ovf.resize(ovf_off[(size_t)n_pieces]);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(host_threads)
+        for (int pc = 0; pc < n_pieces; pc++) {
+            Piece& P = pieces[(size_t)pc];
+            for (size_t r : P.ovf_runs) P.runs[r].src0 += (unsigned)ovf_off[(size_t)pc];
+            std::copy(P.incs.begin(), P.incs.end(), incs.begin() + inc_off[(size_t)pc]);
+            std::copy(P.runs.begin(), P.runs.end(), runs.begin() + run_off[(size_t)pc]);
+            std::copy(P.ovf.begin(), P.ovf.end(), ovf.begin() + ovf_off[(size_t)pc]);
+            const size_t t0 = T * (size_t)pc / (size_t)n_pieces, t1 = T * (size_t)(pc + 1) / (size_t)n_pieces;
+            for (size_t ti_ = t0; ti_ < t1; ti_++) { gn_recs[ti_].ib += (int)inc_off[(size_t)pc]; gn_recs[ti_].ie += (int)inc_off[(size_t)pc]; }
+        }
+        // interface prefix and, in ring mode, the first run of every ready chunk
+        long long run_prefix = 0;
+        int crp_filled = 0;                              // chunk_run_ptr[0 .. crp_filled) are final
+        for (size_t ti_ = 0; ti_ < T; ti_++) {
+            if (ti_ == n_iface_touched) { h->n_iface_runs = run_prefix; h->n_iface_gn = (long long)ti_; }
+            if (h->ring) for (; crp_filled <= touched_rc[ti_]; crp_filled++) chunk_run_ptr[crp_filled] = run_prefix;
+            run_prefix += run_count[ti_];
+        }
+        if (n_iface_touched == T) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)T; }
+        for (; crp_filled <= h->total_chunks; crp_filled++) chunk_run_ptr[crp_filled] = (long long)runs.size();
     }
     (void)fix_mask;
-    if (n_iface_touched == touched_gn.size()) { h->n_iface_runs = (long long)runs.size(); h->n_iface_gn = (long long)gn_recs.size(); }
-    for (; crp_filled <= h->total_chunks; crp_filled++) chunk_run_ptr[crp_filled] = (long long)runs.size();
     {   // Solution::Clear zeroes the whole vectors (Solution.cpp:833-848); entries no local element writes -- DOFs beyond
         // the node table, rows of other ranks -- are zeroed at the head of every assembly when there are any
         long long covered = 0;
@@ -1238,6 +1310,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
     }
 
+    lap("slot map");
     // ---- uploads ----------------------------------------------------------
     CUDA_TRY(h->d_arena.alloc((size_t)h->arena_size));
     CUDA_TRY(cudaMemset(h->d_arena.p, 0, (size_t)h->arena_size * sizeof(double)));
@@ -1300,6 +1373,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         h->n_mixed = (int)mixed.size();
         if (h->n_mixed) { CUDA_TRY(h->d_mixed.upload(mixed)); CUDA_TRY(h->d_mixed_start.upload(start)); }
     }
+    lap("uploads");
     h->dofs_set = true;
     return GFA_OK;
 }
