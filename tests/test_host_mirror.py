@@ -168,3 +168,35 @@ def test_cpp_host_shell_load_matches_python_host_step(tmp_path):
     assert abs(out["sum_AA"] - val.sum()) <= 1e-9 * np.abs(val).sum()
     assert abs(out["max_AA"] - np.abs(val).max()) <= 1e-12 * np.abs(val).max()
     assert abs(out["max_P_A"] - np.abs(pa).max()) <= 1e-12 * np.abs(pa).max()
+
+
+@pytest.mark.gpu
+def test_cpp_static_solve_matches_the_reference_newton_loop(tmp_path, ref):
+    """`gfa_run --solve`: Static::Solve's loop in C++ over the host mirror -- device assembly, MountLoads, gfa_residual,
+    a host solve, UpdateDisps, SaveConfiguration, ten increments of the shipped tutorial01 -- against the same loop
+    through the reference's own sources (RefOracle)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    z = np.load(os.path.join(util.GOLDEN_DIR, "tutorial01.npz"))
+    m = util.model_from_dict(z)
+    dt = float(z["time"][1])
+    p = str(tmp_path / "tutorial01.inp")
+    write_inp(m, p, end_time=1.0, time_step=dt)
+    out = json.loads(subprocess.check_output([EXE, "--solve", p]))
+    assert out["increments"] == 10
+    got = np.array(out["copy_coordinates"]).reshape(-1, 6)
+    ref.load(m)
+    t = 0.0
+    for inc in range(10):
+        ref.set_time(t, dt)
+        d = np.zeros((m.n_nodes, 6))
+        for it in range(8):
+            ref.assemble(d, with_loads=True)
+            ref.residual(None)
+            o, i, v, shape = ref.csr("AA")
+            x = spla.spsolve(sp.csr_matrix((v, i, o), shape=shape).tocsc(), ref.vectors()[0])
+            d = ref.update_displacements(x)[0]
+        ref.commit()
+        t += dt
+    util.assert_parity(ref.copy_coordinates(), got, "tutorial01 solved by gfa_run --solve", tol=1e-9)
+    assert out["last_max_dx"] < 1e-9
