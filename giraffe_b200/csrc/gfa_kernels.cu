@@ -579,122 +579,165 @@ GFA_DI double self_weight(const EvalArgs& A, int e, int b, int jj) {
 
 // Phase B is written as short runtime loops on purpose: straight-line code beyond the ~32 KB the
 // SM's instruction cache holds is fetched at one instruction per ~3 cycles per warp
-// (tools/icache_probe.cu), which bounded this kernel (profiles/r01_notes.md).
+// (tools/icache_probe.cu), which bounded this kernel (profiles/r01_notes.md).  Its other budget is the
+// L1 data pipe: shared-memory loads were 41 % of that pipe's cycles (63 % with the arena stores, ncu
+// round 2), so every record value is read ONCE per lane -- the C' entries of a column depend on the
+// component jj only, not on the node, and are kept in registers across the nodes of the column.
 //
-// Translational columns B1 = kk and B2 = 5 - kk, component jj: rows u_0..u_B1 of the first and
-// u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7 blocks for every kk.
-__device__ void uu_item(const EvalArgs& A, int e, double* ke, const double* rec0, int kk, int jj, double* pe) {
-    const int B1 = kk, B2 = 5 - kk;
-    double* Ke_el = ke + 64 * kk + jj;
-    // m[g] = sum_q S_g[q, column] C'_g[(p, .), (q, jj)] for the two columns, p in {u,1 ; u,2}
-    double m10[NGP][3], m12[NGP][3], m20[NGP][3], m22[NGP][3];
-    double F1 = 0.0, F2 = 0.0;
+// Translational columns, component jj, of ALL six nodes: pass kk takes B1 = kk and B2 = 5 - kk, rows
+// u_0..u_B1 of the first and u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7
+// blocks for every kk; the rows both columns have share their shape-function loads.
+__device__ void uu_items(const EvalArgs& A, int e, double* ke, const double* rec0, int jj, double* pe) {
+    const double* S0 = rec0 + S_OFF;
+    double c00[NGP][3], c02[NGP][3], c20[NGP][3], c22[NGP][3], f0[NGP], f2[NGP];
 #pragma unroll
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
-        const double* recJ = rec + jj;
         const Col cc = col_of(rec, jj);
-        const double* S = rec + S_OFF;
-        const double p1 = S[B1], q1 = S[6 + B1], p2 = S[B2], q2 = S[6 + B2];
-        const double c00[3] = { c_at<0, 0, 0>(cc), c_at<0, 1, 0>(cc), c_at<0, 2, 0>(cc) };
-        const double c02[3] = { c_at<0, 0, 2>(cc), c_at<0, 1, 2>(cc), c_at<0, 2, 2>(cc) };
-        const double c20[3] = { c_at<2, 0, 0>(cc), c_at<2, 1, 0>(cc), c_at<2, 2, 0>(cc) };
-        const double c22[3] = { c_at<2, 0, 2>(cc), c_at<2, 1, 2>(cc), c_at<2, 2, 2>(cc) };
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            m10[g][i] = fma(q1, c02[i], p1 * c00[i]); m12[g][i] = fma(q1, c22[i], p1 * c20[i]);
-            m20[g][i] = fma(q2, c02[i], p2 * c00[i]); m22[g][i] = fma(q2, c22[i], p2 * c20[i]);
-        }
-        F1 = fma(q1, recJ[F_OFF + 6], fma(p1, recJ[F_OFF + 0], F1));
-        F2 = fma(q2, recJ[F_OFF + 6], fma(p2, recJ[F_OFF + 0], F2));
-    }
-    const double* S0 = rec0 + S_OFF;
-#pragma unroll 1
-    for (int a = 0; a <= B1; a++) {            // block (u_a, u_B1) at 64 kk + 9 a
-        double k[3] = { 0.0, 0.0, 0.0 };
-#pragma unroll
-        for (int g = 0; g < NGP; g++) {
-            const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
-#pragma unroll
-            for (int i = 0; i < 3; i++) k[i] = fma(n2, m12[g][i], fma(n1, m10[g][i], k[i]));
-        }
-        double* o = Ke_el + 9 * a;
-        o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+        c00[g][0] = c_at<0, 0, 0>(cc); c00[g][1] = c_at<0, 1, 0>(cc); c00[g][2] = c_at<0, 2, 0>(cc);
+        c02[g][0] = c_at<0, 0, 2>(cc); c02[g][1] = c_at<0, 1, 2>(cc); c02[g][2] = c_at<0, 2, 2>(cc);
+        c20[g][0] = c_at<2, 0, 0>(cc); c20[g][1] = c_at<2, 1, 0>(cc); c20[g][2] = c_at<2, 2, 0>(cc);
+        c22[g][0] = c_at<2, 0, 2>(cc); c22[g][1] = c_at<2, 1, 2>(cc); c22[g][2] = c_at<2, 2, 2>(cc);
+        f0[g] = rec[jj + F_OFF + 0]; f2[g] = rec[jj + F_OFF + 6];
     }
 #pragma unroll 1
-    for (int a = 0; a <= B2; a++) {            // block (u_a, u_B2) at 64 kk + 9 (kk + 1 + a)
-        double k[3] = { 0.0, 0.0, 0.0 };
+    for (int kk = 0; kk < 3; kk++) {
+        const int B1 = kk, B2 = 5 - kk;
+        double* Ke_el = ke + 64 * kk + jj;
+        // m[g] = sum_q S_g[q, column] C'_g[(p, .), (q, jj)] for the two columns, p in {u,1 ; u,2}
+        double m10[NGP][3], m12[NGP][3], m20[NGP][3], m22[NGP][3];
+        double F1 = 0.0, F2 = 0.0;
 #pragma unroll
         for (int g = 0; g < NGP; g++) {
-            const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
+            const double p1 = S0[g * REC + B1], q1 = S0[g * REC + 6 + B1], p2 = S0[g * REC + B2], q2 = S0[g * REC + 6 + B2];
 #pragma unroll
-            for (int i = 0; i < 3; i++) k[i] = fma(n2, m22[g][i], fma(n1, m20[g][i], k[i]));
+            for (int i = 0; i < 3; i++) {
+                m10[g][i] = fma(q1, c02[g][i], p1 * c00[g][i]); m12[g][i] = fma(q1, c22[g][i], p1 * c20[g][i]);
+                m20[g][i] = fma(q2, c02[g][i], p2 * c00[g][i]); m22[g][i] = fma(q2, c22[g][i], p2 * c20[g][i]);
+            }
+            F1 = fma(q1, f2[g], fma(p1, f0[g], F1));
+            F2 = fma(q2, f2[g], fma(p2, f0[g], F2));
         }
-        double* o = Ke_el + 9 * (kk + 1 + a);
-        o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+#pragma unroll 1
+        for (int a = 0; a <= B2; a++) {            // block (u_a, u_B1) at 64 kk + 9 a, block (u_a, u_B2) at 64 kk + 9 (kk + 1 + a)
+            double n1[NGP], n2[NGP];
+#pragma unroll
+            for (int g = 0; g < NGP; g++) { n1[g] = S0[g * REC + a]; n2[g] = S0[g * REC + 6 + a]; }
+            if (a <= B1) {
+                double k[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+                for (int g = 0; g < NGP; g++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) k[i] = fma(n2[g], m12[g][i], fma(n1[g], m10[g][i], k[i]));
+                double* o = Ke_el + 9 * a;
+                o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+            }
+            double k[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+            for (int g = 0; g < NGP; g++)
+#pragma unroll
+                for (int i = 0; i < 3; i++) k[i] = fma(n2[g], m22[g][i], fma(n1[g], m20[g][i], k[i]));
+            double* o = Ke_el + 9 * (kk + 1 + a);
+            o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
+        }
+        pe[3 * B1 + jj] = F1 - self_weight(A, e, B1, jj);
+        pe[3 * B2 + jj] = F2 - self_weight(A, e, B2, jj);
     }
-    pe[3 * B1 + jj] = F1 - self_weight(A, e, B1, jj);
-    pe[3 * B2 + jj] = F2 - self_weight(A, e, B2, jj);
 }
 
-// Rotational column (mid-side node b in 0..2, component jj): all 27 rows -- the six u rows are the
+// Rotational columns, component jj, of ALL three mid-side nodes b: all 27 rows -- the six u rows are the
 // upper u-alpha blocks (their transposes are the alpha-u blocks), the three alpha rows are the
-// non-symmetric alpha-alpha blocks, each stored on its own.
-__device__ void rot_item(const EvalArgs& A, int e, double* ke, const double* rec0, int b, int jj, double* pe) {
+// non-symmetric alpha-alpha blocks, each stored on its own.  Column (b, jj) starts at 192 + 84 b + jj.
+__device__ void rot_items(const EvalArgs& A, int e, double* ke, const double* rec0, int jj, double* pe) {
     (void)A; (void)e;
-    double* Ke_el = ke + 192 + 84 * b + jj;
+    double* Ke_el = ke + 192 + jj;
     const double* S0 = rec0 + S_OFF;
-    double F = 0.0;
     {   // rows u_a: gradient groups {u,1 ; u,2} x {alpha,1 ; alpha,2 ; alpha}
-        double m0[NGP][3], m2[NGP][3];
+        double m0[3][NGP][3], m2[3][NGP][3], F[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
         for (int g = 0; g < NGP; g++) {
             const double* rec = rec0 + g * REC;
             const double* recJ = rec + jj;
             const Col cc = col_of(rec, jj);
-            const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
-#define GFA_ROW(M_, P_, I_) M_[g][I_] = fma(s4, c_at<P_, I_, 4>(cc), fma(s3, c_at<P_, I_, 3>(cc), s1 * c_at<P_, I_, 1>(cc)));
-            GFA_ROW(m0, 0, 0) GFA_ROW(m0, 0, 1) GFA_ROW(m0, 0, 2) GFA_ROW(m2, 2, 0) GFA_ROW(m2, 2, 1) GFA_ROW(m2, 2, 2)
-            F = fma(s4, recJ[F_OFF + 12], fma(s3, recJ[F_OFF + 9], fma(s1, recJ[F_OFF + 3], F)));
+            const double c01[3] = { c_at<0, 0, 1>(cc), c_at<0, 1, 1>(cc), c_at<0, 2, 1>(cc) };
+            const double c03[3] = { c_at<0, 0, 3>(cc), c_at<0, 1, 3>(cc), c_at<0, 2, 3>(cc) };
+            const double c04[3] = { c_at<0, 0, 4>(cc), c_at<0, 1, 4>(cc), c_at<0, 2, 4>(cc) };
+            const double c21[3] = { c_at<2, 0, 1>(cc), c_at<2, 1, 1>(cc), c_at<2, 2, 1>(cc) };
+            const double c23[3] = { c_at<2, 0, 3>(cc), c_at<2, 1, 3>(cc), c_at<2, 2, 3>(cc) };
+            const double c24[3] = { c_at<2, 0, 4>(cc), c_at<2, 1, 4>(cc), c_at<2, 2, 4>(cc) };
+            const double f1 = recJ[F_OFF + 3], f3 = recJ[F_OFF + 9], f4 = recJ[F_OFF + 12];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    m0[b][g][i] = fma(s4, c04[i], fma(s3, c03[i], s1 * c01[i]));
+                    m2[b][g][i] = fma(s4, c24[i], fma(s3, c23[i], s1 * c21[i]));
+                }
+                F[b] = fma(s4, f4, fma(s3, f3, fma(s1, f1, F[b])));
+            }
         }
 #pragma unroll 1
         for (int a = 0; a < 6; a++) {
-            double k[3] = { 0.0, 0.0, 0.0 };
+            double n1[NGP], n2[NGP];
 #pragma unroll
-            for (int g = 0; g < NGP; g++) {
-                const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
+            for (int g = 0; g < NGP; g++) { n1[g] = S0[g * REC + a]; n2[g] = S0[g * REC + 6 + a]; }
 #pragma unroll
-                for (int i = 0; i < 3; i++) k[i] = fma(n2, m2[g][i], fma(n1, m0[g][i], k[i]));
+            for (int b = 0; b < 3; b++) {
+                double k[3] = { 0.0, 0.0, 0.0 };
+#pragma unroll
+                for (int g = 0; g < NGP; g++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) k[i] = fma(n2[g], m2[b][g][i], fma(n1[g], m0[b][g][i], k[i]));
+                double* o = Ke_el + 84 * b + 9 * a;
+                o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
             }
-            double* o = Ke_el + 9 * a;
-            o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
         }
-    }
-    {   // rows alpha_a: gradient groups {alpha,1 ; alpha,2 ; alpha} on both sides
-        double m1[NGP][3], m3[NGP][3], m4[NGP][3];
 #pragma unroll
+        for (int b = 0; b < 3; b++) pe[18 + 3 * b + jj] = F[b];
+    }
+    {   // rows alpha_a: gradient groups {alpha,1 ; alpha,2 ; alpha} on both sides; one Gauss point at a time, the 27
+        // sums (row node a, column node b, component i) stay in registers -- same order of additions as a loop
+        // over the points inside each sum
+        double k[3][3][3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int i = 0; i < 3; i++) k[a][b][i] = 0.0;
+#pragma unroll 1
         for (int g = 0; g < NGP; g++) {
             const double* rec = rec0 + g * REC;
             const Col cc = col_of(rec, jj);
-            const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
-            GFA_ROW(m1, 1, 0) GFA_ROW(m1, 1, 1) GFA_ROW(m1, 1, 2) GFA_ROW(m3, 3, 0) GFA_ROW(m3, 3, 1) GFA_ROW(m3, 3, 2)
-            GFA_ROW(m4, 4, 0) GFA_ROW(m4, 4, 1) GFA_ROW(m4, 4, 2)
-#undef GFA_ROW
-        }
-#pragma unroll 1
-        for (int a = 0; a < 3; a++) {
-            double k[3] = { 0.0, 0.0, 0.0 };
+            const double* Sg = S0 + g * REC;
+            double m1[3][3], m3[3][3], m4[3][3];
+#define GFA_MROW(M_, P_)                                                                                              \
+            { const double x1[3] = { c_at<P_, 0, 1>(cc), c_at<P_, 1, 1>(cc), c_at<P_, 2, 1>(cc) };                    \
+              const double x3[3] = { c_at<P_, 0, 3>(cc), c_at<P_, 1, 3>(cc), c_at<P_, 2, 3>(cc) };                    \
+              const double x4[3] = { c_at<P_, 0, 4>(cc), c_at<P_, 1, 4>(cc), c_at<P_, 2, 4>(cc) };                    \
+              _Pragma("unroll") for (int b = 0; b < 3; b++) {                                                         \
+                  const double s1 = Sg[12 + b], s3 = Sg[15 + b], s4 = Sg[18 + b];                                     \
+                  _Pragma("unroll") for (int i = 0; i < 3; i++) M_[b][i] = fma(s4, x4[i], fma(s3, x3[i], s1 * x1[i])); } }
+            GFA_MROW(m1, 1) GFA_MROW(m3, 3) GFA_MROW(m4, 4)
+#undef GFA_MROW
 #pragma unroll
-            for (int g = 0; g < NGP; g++) {
-                const double a1 = S0[g * REC + 12 + a], a2 = S0[g * REC + 15 + a], a0 = S0[g * REC + 18 + a];
+            for (int a = 0; a < 3; a++) {
+                const double a1 = Sg[12 + a], a2 = Sg[15 + a], a0 = Sg[18 + a];
 #pragma unroll
-                for (int i = 0; i < 3; i++) k[i] = fma(a0, m4[g][i], fma(a2, m3[g][i], fma(a1, m1[g][i], k[i])));
+                for (int b = 0; b < 3; b++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) k[a][b][i] = fma(a0, m4[b][i], fma(a2, m3[b][i], fma(a1, m1[b][i], k[a][b][i])));
             }
-            double* o = Ke_el + 9 * (6 + a);
-            o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
         }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                double* o = Ke_el + 84 * b + 9 * (6 + a);
+                o[0] = k[a][b][0]; o[3] = k[a][b][1]; o[6] = k[a][b][2];
+            }
     }
-    pe[18 + 3 * b + jj] = F;
 }
 
 // One batch of `ne` <= EPW elements at list positions k0 .. k0 + ne - 1, evaluated by one warp; `smem` is the
@@ -710,12 +753,8 @@ __device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, do
         const double* rec0 = smem + el * NGP * REC;
         const int e = eval_element(A, k0 + el);
         double* ke = eval_ke(A, k0 + el, SHELL_ARENA);
-#pragma unroll 1
-        for (int kk = 0; kk < 3; kk++) uu_item(A, e, ke, rec0, kk, jj, pe + 27 * el);
-    }
-    for (int it = lane; it < ne * 9; it += 32) {
-        const int el = it / 9, c = it % 9;
-        rot_item(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, SHELL_ARENA), smem + el * NGP * REC, c / 3, c % 3, pe + 27 * el);
+        uu_items(A, e, ke, rec0, jj, pe + 27 * el);
+        rot_items(A, e, ke, rec0, jj, pe + 27 * el);
     }
     __syncwarp();
     if (!A.elist) { for (int i = lane; i < ne * 27; i += 32) A.Pe[(size_t)k0 * 27 + i] = pe[i]; }
