@@ -494,16 +494,21 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         double C44[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) C44[i] = rec[boff(4, 4) + i];
+        // H_R = sum_s D(R,s) Y_s for the four row groups at once: every parked Y block is read once
+        double H[4][9];
+#define GFA_HCOL(S_, PY_, OP_)                                                        \
+        { const double* Ys = rec + park(PY_);                                         \
+          { const DBlk d = getD<0, S_>(X, smu, drill); OP_(H[0], d, Ys); }            \
+          { const DBlk d = getD<1, S_>(X, smu, drill); OP_(H[1], d, Ys); }            \
+          { const DBlk d = getD<2, S_>(X, smu, drill); OP_(H[2], d, Ys); }            \
+          { const DBlk d = getD<3, S_>(X, smu, drill); OP_(H[3], d, Ys); } }
+        GFA_HCOL(0, P_Y0, dmul) GFA_HCOL(1, P_Y1, dmul_acc) GFA_HCOL(2, P_Y2, dmul_acc) GFA_HCOL(3, P_Y3, dmul_acc)
+#undef GFA_HCOL
 #define GFA_COL4(R_, PG_, PY_)                                                        \
-        { double H[9];                                                                \
-          { const DBlk d = getD<R_, 0>(X, smu, drill); dmul(H, d, rec + park(P_Y0)); }     \
-          { const DBlk d = getD<R_, 1>(X, smu, drill); dmul_acc(H, d, rec + park(P_Y1)); } \
-          { const DBlk d = getD<R_, 2>(X, smu, drill); dmul_acc(H, d, rec + park(P_Y2)); } \
-          { const DBlk d = getD<R_, 3>(X, smu, drill); dmul_acc(H, d, rec + park(P_Y3)); } \
-          mtm(tmp2, GFA_PL(R_), H);                                                       \
-          _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += rec[park(PG_) + i];     \
-          put_block<R_, 4>(rec, w, tmp2);                                             \
-          mtm_acc(C44, rec + park(PY_), H); }
+        { mtm(tmp2, GFA_PL(R_), H[R_]);                                               \
+          _Pragma("unroll") for (int i = 0; i < 9; i++) tmp2[i] += rec[park(PG_) + i]; \
+          mtm_acc(C44, rec + park(PY_), H[R_]);                                       \
+          put_block<R_, 4>(rec, w, tmp2); }
         GFA_COL4(0, P_G0, P_Y0) GFA_COL4(1, P_G1, P_Y1) GFA_COL4(2, P_G2, P_Y2) GFA_COL4(3, P_G3, P_Y3)
 #undef GFA_COL4
         put_block<4, 4>(rec, w, C44);
