@@ -31,7 +31,7 @@ EXPORTS = [
     "gfa_interface_counts", "gfa_interface_pack", "gfa_interface_unpack", "gfa_local_rows", "gfa_owned_rows", "gfa_stream",
     "gfa_set_kinematics", "gfa_kinematics", "gfa_update_dyn", "gfa_assemble_dynamic", "gfa_element_alpha_i", "gfa_assemble_enqueue", "gfa_interface_stream",
     "gfa_pipeline_info", "gfa_touched_nodes", "gfa_set_displacements_packed", "gfa_vector_owned",
-    "gfa_set_shell_loads", "gfa_apply_shell_loads",
+    "gfa_set_shell_loads", "gfa_apply_shell_loads", "gfa_set_pipe_loads", "gfa_apply_pipe_loads",
 ]
 
 
@@ -130,6 +130,8 @@ def load_library() -> C.CDLL:
         lib.gfa_vector_owned.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.gfa_set_shell_loads.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.gfa_apply_shell_loads.argtypes = [C.c_void_p, C.c_void_p]
+        lib.gfa_set_pipe_loads.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.gfa_apply_pipe_loads.argtypes = [C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -330,6 +332,21 @@ class Assembler:
         area = np.array([1 if au else 0 for _, au, _ in loads], np.int32)
         self._shell_load_tables = [np.asarray(t, float) for _, _, t in loads]
         self._check(self.lib.gfa_set_shell_loads(self._h, len(loads), _ptr(ptr), _ptr(elems), _ptr(area)))
+
+    # ---- PipeLoad internal pressure on the device --------------------------------
+    def set_pipe_loads(self, loads):
+        """loads: [(element ids 1-based, table[n,5] = time P0I P0E RhoI RhoE)] as in Model.pipe_loads; call after set_dofs"""
+        ptr = np.zeros(len(loads) + 1, np.int32)
+        for k, (elements, _) in enumerate(loads):
+            ptr[k + 1] = ptr[k] + len(elements)
+        elems = np.concatenate([np.asarray(e, np.int32) - 1 for e, _ in loads]).astype(np.int32) if loads else np.zeros(1, np.int32)
+        self._pipe_load_tables = [np.asarray(t, float) for _, t in loads]
+        self._check(self.lib.gfa_set_pipe_loads(self._h, len(loads), _ptr(ptr), _ptr(elems)))
+
+    def apply_pipe_loads(self, time: float):
+        """Load::GetValueAt(time, 0) of every registered PipeLoad (linear table), then gfa_apply_pipe_loads"""
+        p = np.array([float(np.interp(time, t[:, 0], t[:, 1])) for t in self._pipe_load_tables] or [0.0])
+        self._check(self.lib.gfa_apply_pipe_loads(self._h, _ptr(p)))
 
     def apply_shell_loads(self, time: float):
         """ShellLoad::GetValueAt(time) of every registered load (linear table), then gfa_apply_shell_loads"""

@@ -214,12 +214,15 @@ struct gfa_handle {
     bool abort_check_pending = false;     // the watchdog flag of the last fused launches has not been read yet
     double last_gfac = 0.0;
 
-    // ShellLoad follower pressure on the device (gfa_set_shell_loads / gfa_apply_shell_loads)
-    int n_shell_loads = 0, n_load_entries = 0;
-    long long n_load_dest = 0;
-    DevBuf<int> d_load_elem, d_load_of, d_load_area;
-    DevBuf<double> d_load_pressure, d_load_out;
-    DevBuf<long long> d_load_seg, d_load_src, d_load_dest;
+    // element loads evaluated on the device: ShellLoad follower pressure (gfa_set_shell_loads / gfa_apply_shell_loads)
+    // and PipeLoad internal pressure (gfa_set_pipe_loads / gfa_apply_pipe_loads)
+    struct LoadSet {
+        int n_loads = 0, n_entries = 0;
+        long long n_dest = 0;
+        DevBuf<int> d_elem, d_of, d_flag;
+        DevBuf<double> d_value, d_out;
+        DevBuf<long long> d_seg, d_src, d_dest;
+    } shell_loads, pipe_loads;
 
     bool assembled = false;
     bool timing_pending = false;          // events of the last assembly not read yet (gfa_assemble_enqueue)
@@ -396,6 +399,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
                     // Jr as written in Pipe_1.cpp:1137-1139 (the squared radii are subtracted); Mr = Rho I without ocean data
                     const double rr = (ps[9] / 2.0) * (ps[9] / 2.0) - (ps[10] / 2.0) * (ps[10] / 2.0);
                     row[47] = (ps[4] * rr / 4.0); row[48] = (ps[4] * rr / 4.0); row[49] = (ps[4] * rr / 2.0); row[50] = 0.0;
+                    row[51] = 3.1415926535897932384626433832795 * ps[10] * ps[10] / 4.0;   // Aint (Pipe_1.cpp:1151), for the PipeLoad pressure
                     t.props.insert(t.props.end(), row, row + BEAM_PROP_STRIDE);
                 } else if (s == 1) {    // Beam_1::PreCalc, Beam_1.cpp:560-580
                     const double* sc = m->sections + 6 * (size_t)(sec - 1);
@@ -531,7 +535,8 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     CUDA_TRY(cudaSetDevice(h->device));
     h->dofs_set = false; h->assembled = false; h->vec_dirty = false;
     h->d_owned_idx.release();
-    h->n_shell_loads = 0; h->n_load_entries = 0; h->n_load_dest = 0;      // registered against the old DOF map
+    h->shell_loads.n_loads = h->shell_loads.n_entries = 0; h->shell_loads.n_dest = 0;      // registered against the old DOF map
+    h->pipe_loads.n_loads = h->pipe_loads.n_entries = 0; h->pipe_loads.n_dest = 0;
     h->n_free = n_free; h->n_fixed = n_fixed;
     h->gls.assign(GLs, GLs + 6 * (size_t)h->n_nodes);
     const std::vector<int>& gls = h->gls;
@@ -1775,23 +1780,28 @@ int gfa_add_host_vector(gfa_t* h, int wv, int64_t n, const int32_t* index, const
     return add_staged(h, items);
 }
 
-int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements, const int32_t* area_update) {
-    if (!h || n_loads < 0 || (n_loads > 0 && (!load_ptr || !load_elements || !area_update))) return fail(GFA_EINVAL, "gfa_set_shell_loads: bad argument");
-    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_set_shell_loads before gfa_set_dofs");
-    CUDA_TRY(cudaSetDevice(h->device));
-    std::vector<int> elem, load, area(area_update, area_update + n_loads);
+// Shared by the two element-load families: for every (load, element) entry a record of 18 x 18 + 18 doubles
+// (LOAD_REC) is written by the load kernel; `slots` routes every record entry to its CSR value / vector position,
+// sources of a destination in registration order.  `shell`: local DOFs are the translations of the six nodes;
+// otherwise (Pipe_1) the six DOFs of the three nodes.
+static int build_load_set(gfa_t* h, gfa_t::LoadSet& L, bool shell, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements,
+                          const int32_t* flags, const char* what) {
+    std::vector<int> elem, load, flag;
+    if (flags) flag.assign(flags, flags + n_loads); else flag.assign((size_t)std::max(n_loads, 1), 0);
     struct Slot { long long dest, src; };
     std::vector<Slot> slots;
+    const int slot_of_type = shell ? 0 : 1, nn = shell ? 6 : 3, per = shell ? 3 : 6;
     for (int l = 0; l < n_loads; l++)
         for (int k = load_ptr[l]; k < load_ptr[l + 1]; k++) {
             const int e = load_elements[k];
-            if (e < 0 || e >= h->n_el || h->el_type[e] != GFA_SHELL_1) return fail(GFA_EINVAL, "shell load %d: element %d is not a Shell_1 element", l + 1, e + 1);
-            if (h->el_owner_slot[e] != 0) continue;              // another rank's partition
+            const bool ok = e >= 0 && e < h->n_el && (shell ? h->el_type[e] == GFA_SHELL_1 : h->el_type[e] == GFA_PIPE_1);
+            if (!ok) return fail(GFA_EINVAL, "%s %d: element %d is not a %s element", what, l + 1, e + 1, shell ? "Shell_1" : "Pipe_1");
+            if (h->el_owner_slot[e] != slot_of_type) continue;              // another rank's partition
             const long long entry = (long long)elem.size();
             elem.push_back(h->el_local[e]); load.push_back(l);
             int gl[18];
-            for (int a = 0; a < 6; a++)
-                for (int c = 0; c < 3; c++) gl[3 * a + c] = h->gls[6 * (size_t)h->el_nodes[h->el_ptr[e] + a] + c];
+            for (int a = 0; a < nn; a++)
+                for (int c = 0; c < per; c++) gl[per * a + c] = h->gls[6 * (size_t)h->el_nodes[h->el_ptr[e] + a] + c];
             for (int i = 0; i < 18; i++) {
                 const int g1 = gl[i];
                 if (g1 == 0) continue;
@@ -1807,7 +1817,7 @@ int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, cons
                     const int col = std::abs(g2) - 1;
                     const int* b = M.inner.data() + M.rowptr[lr]; const int* en = M.inner.data() + M.rowptr[lr + 1];
                     const int* p = std::lower_bound(b, en, col);
-                    if (p == en || *p != col) return fail(GFA_EPATTERN, "shell load position (%d,%d) of matrix %d is not in the pattern", lr, col, w);
+                    if (p == en || *p != col) return fail(GFA_EPATTERN, "%s position (%d,%d) of matrix %d is not in the pattern", what, lr, col, w);
                     slots.push_back({ h->arena_off[w] + M.rowptr[lr] + (p - b), entry * SHELL_LOAD_REC + i * 18 + j });
                 }
             }
@@ -1822,28 +1832,53 @@ int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, cons
         i = j;
     }
     seg.push_back((long long)src.size());
-    h->n_shell_loads = n_loads; h->n_load_entries = (int)elem.size(); h->n_load_dest = (long long)dest.size();
-    CUDA_TRY(h->d_load_elem.upload(elem)); CUDA_TRY(h->d_load_of.upload(load)); CUDA_TRY(h->d_load_area.upload(area));
-    CUDA_TRY(h->d_load_pressure.alloc((size_t)std::max(n_loads, 1)));
-    CUDA_TRY(h->d_load_out.alloc((size_t)std::max<size_t>(elem.size(), 1) * SHELL_LOAD_REC));
-    CUDA_TRY(h->d_load_seg.upload(seg)); CUDA_TRY(h->d_load_src.upload(src)); CUDA_TRY(h->d_load_dest.upload(dest));
+    L.n_loads = n_loads; L.n_entries = (int)elem.size(); L.n_dest = (long long)dest.size();
+    CUDA_TRY(L.d_elem.upload(elem)); CUDA_TRY(L.d_of.upload(load)); CUDA_TRY(L.d_flag.upload(flag));
+    CUDA_TRY(L.d_value.alloc((size_t)std::max(n_loads, 1)));
+    CUDA_TRY(L.d_out.alloc((size_t)std::max<size_t>(elem.size(), 1) * SHELL_LOAD_REC));
+    CUDA_TRY(L.d_seg.upload(seg)); CUDA_TRY(L.d_src.upload(src)); CUDA_TRY(L.d_dest.upload(dest));
     return GFA_OK;
 }
 
-int gfa_apply_shell_loads(gfa_t* h, const double* pressures) {
-    if (!h || (h->n_shell_loads > 0 && !pressures)) return fail(GFA_EINVAL, "gfa_apply_shell_loads: bad argument");
-    if (!h->assembled) return fail(GFA_ESTATE, "gfa_apply_shell_loads before gfa_assemble");
-    if (h->n_load_entries == 0) return GFA_OK;
+static int apply_load_set(gfa_t* h, gfa_t::LoadSet& L, bool shell, const double* values) {
+    if (L.n_entries == 0) return GFA_OK;
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaMemcpyAsync(h->d_load_pressure.p, pressures, (size_t)h->n_shell_loads * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(L.d_value.p, values, (size_t)L.n_loads * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     ShellLoadArgs la;
-    la.n_entries = h->n_load_entries; la.elem = h->d_load_elem.p; la.load = h->d_load_of.p;
-    la.pressure = h->d_load_pressure.p; la.area_update = h->d_load_area.p; la.out = h->d_load_out.p;
-    launch_shell_loads(eval_args(h, 0, 0.0), la, h->stream);
-    launch_gather_add(h->d_arena.p, h->d_load_seg.p, h->d_load_src.p, h->d_load_dest.p, h->d_load_out.p, h->n_load_dest, h->stream);
+    la.n_entries = L.n_entries; la.elem = L.d_elem.p; la.load = L.d_of.p;
+    la.pressure = L.d_value.p; la.area_update = L.d_flag.p; la.out = L.d_out.p;
+    if (shell) launch_shell_loads(eval_args(h, 0, 0.0), la, h->stream);
+    else launch_pipe_loads(eval_args(h, 1, 0.0), la, h->stream);
+    launch_gather_add(h->d_arena.p, L.d_seg.p, L.d_src.p, L.d_dest.p, L.d_out.p, L.n_dest, h->stream);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(h->stream));      // `pressures` is the caller's
+    CUDA_TRY(cudaStreamSynchronize(h->stream));      // `values` is the caller's
     return GFA_OK;
+}
+
+int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements, const int32_t* area_update) {
+    if (!h || n_loads < 0 || (n_loads > 0 && (!load_ptr || !load_elements || !area_update))) return fail(GFA_EINVAL, "gfa_set_shell_loads: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_set_shell_loads before gfa_set_dofs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return build_load_set(h, h->shell_loads, true, n_loads, load_ptr, load_elements, area_update, "shell load");
+}
+
+int gfa_apply_shell_loads(gfa_t* h, const double* pressures) {
+    if (!h || (h->shell_loads.n_loads > 0 && !pressures)) return fail(GFA_EINVAL, "gfa_apply_shell_loads: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_apply_shell_loads before gfa_assemble");
+    return apply_load_set(h, h->shell_loads, true, pressures);
+}
+
+int gfa_set_pipe_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements) {
+    if (!h || n_loads < 0 || (n_loads > 0 && (!load_ptr || !load_elements))) return fail(GFA_EINVAL, "gfa_set_pipe_loads: bad argument");
+    if (!h->dofs_set) return fail(GFA_ESTATE, "gfa_set_pipe_loads before gfa_set_dofs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return build_load_set(h, h->pipe_loads, false, n_loads, load_ptr, load_elements, nullptr, "pipe load");
+}
+
+int gfa_apply_pipe_loads(gfa_t* h, const double* p0i) {
+    if (!h || (h->pipe_loads.n_loads > 0 && !p0i)) return fail(GFA_EINVAL, "gfa_apply_pipe_loads: bad argument");
+    if (!h->assembled) return fail(GFA_ESTATE, "gfa_apply_pipe_loads before gfa_assemble");
+    return apply_load_set(h, h->pipe_loads, false, p0i);
 }
 
 int gfa_csr_values(gfa_t* h, int which, double* out) {

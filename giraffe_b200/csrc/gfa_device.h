@@ -53,8 +53,8 @@ GFA_HD_INLINE double* eval_ke(const EvalArgs& A, int k, int arena) {
 }
 
 constexpr int SHELL_PROP_STRIDE = 5;   // lambda, mu, thickness, stiff_drill, rho
-constexpr int BEAM_PROP_STRIDE = 51;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A, strain-energy switch (1 Beam_1, 0 Pipe_1),
-                                       // Jr = rho*(I11, I22, I33, I12) (Beam_1.cpp:587-591; zero for Pipe_1: no dynamic path)
+constexpr int BEAM_PROP_STRIDE = 52;   // D(36 row-major), R=CS triad(9 row-major E1,E2,E3), rho*A, strain-energy switch (1 Beam_1, 0 Pipe_1),
+                                       // Jr = rho*(I11, I22, I33, I12) (Beam_1.cpp:587-591), Aint = pi Di^2 / 4 (Pipe_1.cpp:1151; 0 for Beam_1)
 constexpr int SOLID_PROP_STRIDE = 3;   // lambda, mu, rho
 
 constexpr int SHELL_RESULTS = 73;      // strain_energy + 3 x (eta1 eta2 kappa1 kappa2 n1 n2 m1 m2)
@@ -199,6 +199,7 @@ struct ShellLoadArgs {
     double* out;                 // [n_entries * SHELL_LOAD_REC]
 };
 void launch_shell_loads(const EvalArgs& a, const ShellLoadArgs& l, void* stream);
+void launch_pipe_loads(const EvalArgs& a, const ShellLoadArgs& l, void* stream);     // PipeLoad: `pressure` = P0I per load, same record layout
 // vals[dest[i]] += sum of src[seg[i] .. seg[i+1]) in list order (one thread per destination: fixed summation order)
 void launch_gather_add(double* vals, const long long* seg, const long long* src, const long long* dest, const double* from, long long n_dest, void* stream);
 

@@ -1265,6 +1265,93 @@ __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     }
 }
 
+// PipeLoad internal pressure: Pipe_1::MountPipeSpecialLoads (Pipe_1.cpp:1443-1494), one thread per (load, element)
+// entry.  The kinematics are those of Mount at the displacements of the last assembly (strict chain as in physics());
+// the scalar g of the LAST Gauss point serves both points, as the member Mount leaves behind does in the reference
+// (Pipe_1.cpp:887, 1470).  Record (SHELL_LOAD_REC doubles, global axes): what is ADDED to the stiffness, row-major
+// 18 x 18 in the element's local DOF order, then what is added to P_loading.
+__global__ void pipe_load_kernel(EvalArgs A, ShellLoadArgs Ld) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Ld.n_entries) return;
+    const int e = Ld.elem[t];
+    const double p0i = Ld.pressure[Ld.load[t]];
+    double* out = Ld.out + (size_t)t * SHELL_LOAD_REC;
+    for (int i = 0; i < SHELL_LOAD_REC; i++) out[i] = 0.0;
+    int nd[3];
+#pragma unroll
+    for (int n = 0; n < 3; n++) nd[n] = A.conn[3 * (size_t)e + n];
+    const double* pr = A.props + BEAM_PROP_STRIDE * (size_t)A.prop[e];
+    const double Aint = pr[51];
+    const size_t n_gp = (size_t)A.n_el * NGP;
+    double g_last = 0.0;
+    {   // the second point's g
+        Geo go; geometry(A, e, 1, nd, pr, go);
+        Kin kn; interpolate(A, nd, go, kn);
+        double Qd[9], Xi[9];
+        s_rodrigues(kn.a, g_last, Qd, Xi);
+    }
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++) {
+        const size_t gp = (size_t)e * NGP + g;
+        Geo go; geometry(A, e, g, nd, pr, go);
+        Kin kn; interpolate(A, nd, go, kn);
+        double Qi[9], dz[3], ki[3];
+        for (int i = 0; i < 9; i++) Qi[i] = A.state[i * n_gp + gp];
+        for (int i = 0; i < 3; i++) { dz[i] = s_add(kn.du[i], A.state[(9 + i) * n_gp + gp]); ki[i] = A.state[(12 + i) * n_gp + gp]; }
+        double gg, Qd[9], Xi[9], dXi[9], Q[9], t3[3], kr[3];
+        s_rodrigues(kn.a, gg, Qd, Xi);
+        d_xi(dXi, kn.a, kn.da, gg, Xi);
+        s_mm(Q, Qd, Qi);
+        s_mtv(t3, Xi, kn.da); s_mtv(kr, Qi, t3);
+        for (int i = 0; i < 3; i++) kr[i] = s_add(kr[i], ki[i]);                  // kappa_r (:920)
+        double kip[3], e3ip[3], tf[3], tm[3], c[3], Xtc[3];
+        mv(kip, Q, kr); mv(e3ip, Q, go.e3r);
+        cross3(tf, kip, e3ip);
+        cross3(c, dz, e3ip); mtv(tm, Xi, c);
+        for (int i = 0; i < 3; i++) { tf[i] *= -p0i * Aint; tm[i] *= -p0i * Aint; }
+        cross3(c, e3ip, dz); mtv(Xtc, Xi, c);
+        double O1[9], Sc[9], K1ua[9], K1aa[9], K2ua[9], K2au[9], E3[9], tmp[9], tmp2[9];
+        skew3(Sc, c); skew3(E3, e3ip);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) O1[3 * i + j] = -0.5 * g_last * (Xtc[i] * kn.a[j] - Sc[3 * i + j]);
+        // K1ua = Kip E3 Xi + E3 dXi - E3 Kip Xi
+        mm(K2ua, E3, Xi);                                   // E3 Xi
+        skew_mul(K1ua, kip, K2ua);                          // Kip E3 Xi
+        mm(tmp, E3, dXi);
+        skew_mul(tmp2, kip, Xi); mm(Sc, E3, tmp2);          // E3 Kip Xi
+        for (int i = 0; i < 9; i++) K1ua[i] = K1ua[i] + tmp[i] - 1.0 * Sc[i];
+        skew_mul(tmp, dz, K2ua); mtm(K1aa, Xi, tmp);        // Xi^T dZ E3 Xi
+        for (int i = 0; i < 9; i++) K1aa[i] += O1[i];
+        mtm(K2au, Xi, E3);
+        // rotate the four blocks and the load to global axes: T^T (.) T with T = blockdiag(R)
+        const double* R = go.R;
+        mm(tmp, K1ua, R); mtm(K1ua, R, tmp);
+        mm(tmp, K1aa, R); mtm(K1aa, R, tmp);
+        mm(tmp, K2ua, R); mtm(K2ua, R, tmp);
+        mm(tmp, K2au, R); mtm(K2au, R, tmp);
+        double tfg[3], tmg[3];
+        mtv(tfg, R, tf); mtv(tmg, R, tm);
+        const double mult = 1.0 * go.jac, ks = mult * p0i * Aint;
+        for (int a = 0; a < 3; a++) {
+            const double Na = go.N[a];
+            for (int i = 0; i < 3; i++) {
+                out[324 + 6 * a + i] -= mult * Na * tfg[i];
+                out[324 + 6 * a + 3 + i] -= mult * Na * tmg[i];
+            }
+            for (int b = 0; b < 3; b++) {
+                const double Nb = go.N[b], dNb = go.dN[b];
+                for (int i = 0; i < 3; i++)
+                    for (int j = 0; j < 3; j++) {
+                        // N^T Kext UpsilonN: (u, alpha) = K1ua N_b + K2ua N'_b, (alpha, u) = K2au N'_b, (alpha, alpha) = K1aa N_b
+                        out[(6 * a + i) * 18 + 6 * b + 3 + j] -= ks * Na * (K1ua[3 * i + j] * Nb + K2ua[3 * i + j] * dNb);
+                        out[(6 * a + 3 + i) * 18 + 6 * b + j] -= ks * Na * (K2au[3 * i + j] * dNb);
+                        out[(6 * a + 3 + i) * 18 + 6 * b + 3 + j] -= ks * Na * (K1aa[3 * i + j] * Nb);
+                    }
+            }
+        }
+    }
+}
+
 // Beam_1::SaveLagrange (:1494-1506)
 __global__ void commit_kernel(EvalArgs A) {
     const size_t n_gp = (size_t)A.n_el * NGP;
@@ -2153,6 +2240,10 @@ int launch_fused_scatter(const FusedArgs& f, void* s) {
 void launch_gather(const GatherArgs& a, void* s) {
     if (a.n_dest <= 0) return;
     gather_kernel<<<(unsigned)((a.n_dest + 255) / 256), 256, 0, (cudaStream_t)s>>>(a);
+}
+void launch_pipe_loads(const EvalArgs& a, const ShellLoadArgs& l, void* s) {
+    if (l.n_entries <= 0) return;
+    beam::pipe_load_kernel<<<(unsigned)((l.n_entries + 63) / 64), 64, 0, (cudaStream_t)s>>>(a, l);
 }
 void launch_shell_loads(const EvalArgs& a, const ShellLoadArgs& l, void* s) {
     if (l.n_entries <= 0) return;

@@ -51,6 +51,17 @@ double GfaNodalLoad::GetValueAt(double t, int column) const {
     return table[7 * (n - 1) + column];
 }
 
+double GfaPipeLoad::GetValueAt(double t, int column) const {
+    const int n = (int)(table.size() / 5);
+    if (n == 0) return 0.0;
+    if (t <= table[0]) return table[1 + column];
+    for (int r = 0; r + 1 < n; r++) {
+        const double t0 = table[5 * r], t1 = table[5 * (r + 1)];
+        if (t <= t1) return table[5 * r + 1 + column] + (table[5 * (r + 1) + 1 + column] - table[5 * r + 1 + column]) * (t - t0) / (t1 - t0);
+    }
+    return table[5 * (n - 1) + 1 + column];
+}
+
 double GfaShellLoad::GetValueAt(double t) const {
     const int n = (int)(table.size() / 2);
     if (n == 0) return 0.0;
@@ -193,6 +204,14 @@ bool GfaHost::ReadFile(const char* path) {
                     for (int k = 0; k < 2 * nt; k++) l.table.push_back(num(i + k));
                     i += 2 * (size_t)nt;
                     shell_loads.push_back(l);
+                    continue;
+                }
+                if (tk[i] == "PipeLoad") {         // PipeLoad id ElementSet s NTimes n, rows time P0I P0E RhoI RhoE (PipeLoad.cpp:44-88)
+                    GfaPipeLoad l; l.element_set = integer(i + 3);
+                    const int nt = integer(i + 5); i += 6;
+                    for (int k = 0; k < 5 * nt; k++) l.table.push_back(num(i + k));
+                    i += 5 * (size_t)nt;
+                    pipe_loads.push_back(l);
                     continue;
                 }
                 if (tk[i] != "NodalLoad") return fail("load " + tk[i] + " stays on the host");
@@ -358,6 +377,15 @@ bool GfaHost::SetGlobalSize() {
         }
         if (gfa_set_shell_loads(h, (int32_t)shell_loads.size(), ptr.data(), elems.data(), area.data()) != GFA_OK) return fail(gfa_last_error());
     }
+    if (!pipe_loads.empty()) {          // PipeLoad::Check refuses a set with another element type (PipeLoad.cpp:91-106); so does the library
+        std::vector<int> ptr(1, 0), elems;
+        for (const GfaPipeLoad& l : pipe_loads) {
+            if (l.element_set < 1 || l.element_set > (int)element_sets.size()) return fail("PipeLoad refers to an ElementSet that does not exist");
+            for (int el1 : element_sets[l.element_set - 1]) elems.push_back(el1 - 1);
+            ptr.push_back((int)elems.size());
+        }
+        if (gfa_set_pipe_loads(h, (int32_t)pipe_loads.size(), ptr.data(), elems.data()) != GFA_OK) return fail(gfa_last_error());
+    }
     return true;
 }
 
@@ -458,6 +486,12 @@ bool GfaHost::MountLoads() {
         std::vector<double> pressures;
         for (const GfaShellLoad& l : shell_loads) pressures.push_back(l.GetValueAt(t));
         if (gfa_apply_shell_loads(h, pressures.data()) != GFA_OK) return fail(gfa_last_error());
+    }
+    // PipeLoad::Mount -> Pipe_1::MountPipeSpecialLoads (PipeLoad.cpp:117-133, Pipe_1.cpp:1443-1494): on the device too
+    if (!pipe_loads.empty()) {
+        std::vector<double> p0i;
+        for (const GfaPipeLoad& l : pipe_loads) p0i.push_back(l.GetValueAt(t, 0));
+        if (gfa_apply_pipe_loads(h, p0i.data()) != GFA_OK) return fail(gfa_last_error());
     }
     for (int w = 0; w < 4; w++)
         if (!tv[w].empty() && gfa_add_host_triplets(h, w, (int64_t)tv[w].size(), tr[w].data(), tc[w].data(), tv[w].data()) != GFA_OK) return fail(gfa_last_error());

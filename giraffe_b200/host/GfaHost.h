@@ -45,6 +45,12 @@ struct GfaShellLoad {              // ShellLoad with a numeric table (ShellLoad.
     double GetValueAt(double t) const;
 };
 
+struct GfaPipeLoad {               // PipeLoad with a numeric table (PipeLoad.h): internal pressure on an ElementSet of Pipe_1
+    int element_set = 0;
+    std::vector<double> table;     // rows: time P0I P0E RhoI RhoE
+    double GetValueAt(double t, int column) const;
+};
+
 class GfaHost {
 public:
     ~GfaHost();
@@ -69,6 +75,7 @@ public:
     std::vector<GfaNodalLoad> loads;
     std::vector<std::vector<int> > element_sets;  // ElementSet::el_list, 1-based (ElementSet.h)
     std::vector<GfaShellLoad> shell_loads;        // ShellLoad (host contributor: Shell_1::MountShellSpecialLoads)
+    std::vector<GfaPipeLoad> pipe_loads;          // PipeLoad (Pipe_1::MountPipeSpecialLoads, evaluated on the device)
     bool g_exist = false;
     double G[3] = { 0, 0, 0 };
     double end_time = 1.0, time_step = 1.0;       // first solution step (Static.cpp:43-130, Dynamic.cpp:65-222)

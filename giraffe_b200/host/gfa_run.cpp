@@ -93,9 +93,9 @@ int main(int argc, char** argv) {
     host.SetGlobalDOFs();
     if (parse_only) {
         printf("{\"nodes\": %d, \"elements\": %d, \"n_GL_free\": %d, \"n_GL_fixed\": %d, \"loads\": %zu, \"node_sets\": %zu, \"time_step\": %.17g, \"end_time\": %.17g, "
-               "\"dynamic\": %d, \"alpha\": %.17g, \"beta\": %.17g, \"update\": %d, \"beta_new\": %.17g, \"gamma_new\": %.17g, \"shell_loads\": %zu, \"element_sets\": %zu}\n",
+               "\"dynamic\": %d, \"alpha\": %.17g, \"beta\": %.17g, \"update\": %d, \"beta_new\": %.17g, \"gamma_new\": %.17g, \"shell_loads\": %zu, \"pipe_loads\": %zu, \"element_sets\": %zu}\n",
                host.number_nodes(), host.number_elements(), host.n_GL_free, host.n_GL_fixed, host.loads.size(), host.node_sets.size(), host.time_step, host.end_time,
-               host.dynamic ? 1 : 0, host.alpha, host.beta, host.update, host.beta_new, host.gamma_new, host.shell_loads.size(), host.element_sets.size());
+               host.dynamic ? 1 : 0, host.alpha, host.beta, host.update, host.beta_new, host.gamma_new, host.shell_loads.size(), host.pipe_loads.size(), host.element_sets.size());
         return 0;
     }
     if (!host.PreCalc(0)) { fprintf(stderr, "PreCalc: %s\n", host.last_error().c_str()); return 1; }
@@ -132,7 +132,7 @@ int main(int argc, char** argv) {
     double sum = 0.0, amax = 0.0, pmax = 0.0;
     for (double v : val) { sum += v; amax = fmax(amax, fabs(v)); }
     for (double v : pa) pmax = fmax(pmax, fabs(v));
-    printf("{\"nodes\": %d, \"elements\": %d, \"n_GL_free\": %d, \"n_GL_fixed\": %d, \"nnz_AA\": %zu, \"sum_AA\": %.17g, \"max_AA\": %.17g, \"max_P_A\": %.17g}\n",
-           host.number_nodes(), host.number_elements(), host.n_GL_free, host.n_GL_fixed, val.size(), sum, amax, pmax);
+    printf("{\"nodes\": %d, \"elements\": %d, \"n_GL_free\": %d, \"n_GL_fixed\": %d, \"nnz_AA\": %zu, \"sum_AA\": %.17g, \"max_AA\": %.17g, \"max_P_A\": %.17g, \"shell_loads\": %zu, \"pipe_loads\": %zu}\n",
+           host.number_nodes(), host.number_elements(), host.n_GL_free, host.n_GL_fixed, val.size(), sum, amax, pmax, host.shell_loads.size(), host.pipe_loads.size());
     return 0;
 }

@@ -38,7 +38,7 @@ def read_inp(path: str):
     i = 0
     nodes, mats, secs, shsecs, csd, pipes = {}, {}, {}, {}, {}, {}
     elems, nodesets, cons, loads = [], {}, [], []
-    elemsets, shloads = {}, []
+    elemsets, shloads, ploads = {}, [], []
     gravity = None
     info = {}
 
@@ -147,6 +147,11 @@ def read_inp(path: str):
                     table = np.array([float(t) for t in tk[i:i + 2 * nt]]).reshape(nt, 2); i += 2 * nt
                     shloads.append((es, bool(au), table))
                     continue
+                if tk[i] == "PipeLoad":       # PipeLoad id ElementSet s NTimes n, rows time P0I P0E RhoI RhoE (PipeLoad.cpp:44-88)
+                    es, nt = int(tk[i + 3]), int(tk[i + 5]); i += 6
+                    table = np.array([float(t) for t in tk[i:i + 5 * nt]]).reshape(nt, 5); i += 5 * nt
+                    ploads.append((es, table))
+                    continue
                 assert tk[i] == "NodalLoad", f"load {tk[i]} stays on the host"
                 sid, cs, nt = int(tk[i + 3]), int(tk[i + 5]), int(tk[i + 7]); i += 8
                 table = np.array([float(t) for t in tk[i:i + 7 * nt]]).reshape(nt, 7); i += 7 * nt
@@ -206,6 +211,7 @@ def read_inp(path: str):
     m.nodal_loads = [(np.array(nodesets[s], np.int32), cs, t) for s, cs, t in loads]
     m.gravity = gravity
     m.shell_loads = [(np.array(elemsets[es], np.int32), au, t) for es, au, t in shloads]
+    m.pipe_loads = [(np.array(elemsets[es], np.int32), t) for es, t in ploads]
     info["node_sets"] = nodesets
     return _finish(m), info
 
@@ -268,12 +274,13 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
         if dynamic:
             f.write(f"RayleighDamping\tAlpha\t{_r(dynamic['alpha'])}\tBeta\t{_r(dynamic['beta'])}\tUpdate\t{int(dynamic['update'])}\n"
                     f"NewmarkCoefficients\tBeta\t{_r(dynamic['beta_new'])}\tGamma\t{_r(dynamic['gamma_new'])}\n")
-        if m.shell_loads:
-            f.write(f"\nElementSets\t{len(m.shell_loads)}\n")
-            for k, (elements, _, _) in enumerate(m.shell_loads):
+        pipe_loads = getattr(m, "pipe_loads", [])
+        if m.shell_loads or pipe_loads:
+            f.write(f"\nElementSets\t{len(m.shell_loads) + len(pipe_loads)}\n")
+            for k, elements in enumerate([l[0] for l in m.shell_loads] + [l[0] for l in pipe_loads]):
                 f.write(f"ElementSet\t{k + 1}\tElements\t{len(elements)}\tList\t" + "\t".join(str(int(e)) for e in elements) + "\n")
-        if m.nodal_loads or m.shell_loads:
-            f.write(f"\nLoads\t{len(m.nodal_loads) + len(m.shell_loads)}\n")
+        if m.nodal_loads or m.shell_loads or pipe_loads:
+            f.write(f"\nLoads\t{len(m.nodal_loads) + len(m.shell_loads) + len(pipe_loads)}\n")
             for k, (nodes, cs, table) in enumerate(m.nodal_loads):
                 table = np.asarray(table, float)
                 f.write(f"NodalLoad\t{k + 1}\tNodeSet\t{len(m.constraints) + k + 1}\tCS\t{cs}\tNTimes\t{len(table)}\n")
@@ -282,6 +289,11 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
             for k, (elements, area_update, table) in enumerate(m.shell_loads):
                 table = np.asarray(table, float)
                 f.write(f"ShellLoad\t{len(m.nodal_loads) + k + 1}\tElementSet\t{k + 1}\tAreaUpdate\t{1 if area_update else 0}\tNTimes\t{len(table)}\n")
+                for row in table:
+                    f.write("\t".join(repr(float(v)) for v in row) + "\n")
+            for k, (elements, table) in enumerate(pipe_loads):
+                table = np.asarray(table, float)
+                f.write(f"PipeLoad\t{len(m.nodal_loads) + len(m.shell_loads) + k + 1}\tElementSet\t{len(m.shell_loads) + k + 1}\tNTimes\t{len(table)}\n")
                 for row in table:
                     f.write("\t".join(repr(float(v)) for v in row) + "\n")
         if m.constraints:

@@ -53,6 +53,9 @@ class Model:
     # ShellLoad (ShellLoad.h): [(element ids 1-based, area_update, table[n,2] = time, pressure)] -- a host-side
     # contributor (Load), not part of the device path
     shell_loads: list = field(default_factory=list)
+    # PipeLoad (PipeLoad.h): [(element ids 1-based, table[n,5] = time, P0I, P0E, RhoI, RhoE)] -- internal pressure on
+    # Pipe_1 elements (Pipe_1::MountPipeSpecialLoads uses P0I only), evaluated by gfa_apply_pipe_loads
+    pipe_loads: list = field(default_factory=list)
 
     @property
     def n_nodes(self) -> int:

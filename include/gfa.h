@@ -176,6 +176,19 @@ int gfa_add_host_vector(gfa_t* h, int which_vector, int64_t n, const int32_t* in
 int gfa_set_shell_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements, const int32_t* area_update);
 int gfa_apply_shell_loads(gfa_t* h, const double* pressures /* [n_loads] */);
 
+/* ---- PipeLoad internal pressure on the device ("Morison/pressure loads ... become a second
+ * kernel"; src/PipeLoad.cpp:117-133 -> Pipe_1::MountPipeSpecialLoads, src/Pipe_1.cpp:1443-1494).  Register the
+ * loads once per DOF map: load l acts on load_elements[load_ptr[l] .. load_ptr[l+1]) (0-based global element
+ * indices, all GFA_PIPE_1; the ElementSet of the reference, src/PipeLoad.cpp:91-106).  After every gfa_assemble,
+ * gfa_apply_pipe_loads(h, p0i) takes P0I = Load::GetValueAt(last_converged_time + current_time_step, 0) of every
+ * load and folds the pressure's end-cap / curvature force and its non-symmetric u-alpha, alpha-u, alpha-alpha load
+ * stiffness into the CSR values and P_A / I_A / P_B, at the displacements of that assembly.  P0E, RhoI and RhoE of
+ * the table are read by the reference and not used (src/Pipe_1.cpp:1446-1449); neither are they here.  Buoyancy and
+ * the Morison sea-current loads (src/Pipe_1.cpp:1278-1441: they need Environment::OceanData) stay host
+ * contributors. */
+int gfa_set_pipe_loads(gfa_t* h, int32_t n_loads, const int32_t* load_ptr, const int32_t* load_elements);
+int gfa_apply_pipe_loads(gfa_t* h, const double* p0i /* [n_loads] host */);
+
 /* Results.  Device pointers stay valid until the next gfa_set_dofs/destroy. */
 int gfa_csr_values(gfa_t* h, int which, double* host_out /* [nnz] */);
 int gfa_csr_values_device(gfa_t* h, int which, double** dev_ptr);

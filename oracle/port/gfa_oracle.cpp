@@ -119,6 +119,7 @@ struct BeamEl
 	double N[2][3], dN[2][3];
 	M3 Q_i[2]; V3 dz_i[2], k_i[2];
 	M3 Q_d[2]; V3 dz[2], kr[2];
+	M3 Xi_d[2], dXi_d[2]; double g_last, Aint;  // left by Mount for MountPipeSpecialLoads (g: the LAST point's, Pipe_1.cpp:887)
 	double K[18 * 18], Fint[18], P[18], energy;
 	// Newmark dynamics (Beam_1.cpp:1564-1673): committed Rodrigues vector, trial increments of Mount,
 	// section inertia (:582-596), stored Rayleigh matrix
@@ -143,6 +144,7 @@ struct World
 	std::vector<int> type, mat, secid, csid, nptr, nodes;
 	std::vector<char> is_pipe;
 	std::vector<double> pret;
+	std::vector<int> pipe_load_ptr, pipe_load_el; std::vector<double> pipe_load_p;   // PipeLoad objects (gfo_set_pipe_loads)
 	int g_on = 0; double g[3] = { 0, 0, 0 };
 	std::vector<int> cmask, gls;
 	int n_free = 0, n_fixed = 0;
@@ -464,6 +466,7 @@ void pipe_precalc(BeamEl& b, const int* nd, const double* ps, const double* cs)
 	b.D(0, 0) = ps[3]; b.D(1, 1) = ps[3]; b.D(2, 2) = ps[0]; b.D(3, 3) = ps[1]; b.D(4, 4) = ps[1]; b.D(5, 5) = ps[2];
 	b.rhoA = ps[4];
 	b.energy_on = false;
+	b.Aint = 3.1415926535897932384626433832795 * ps[10] * ps[10] / 4.0;      // Pipe_1.cpp:1151 (PI as in the reference's Matrix.h)
 	// inertia per unit length (Pipe_1.cpp:1131-1144, as written: radii squared are SUBTRACTED), no ocean data:
 	// Mr = Rho I in MountMass / MountMassModal (Pipe_1.cpp:1580-1583, 1799-1803)
 	const double rr = (ps[9] / 2.0) * (ps[9] / 2.0) - (ps[10] / 2.0) * (ps[10] / 2.0);
@@ -533,6 +536,7 @@ void beam_mount(BeamEl& b, const int* nd)
 		if (b.energy_on) b.energy += 0.5 * (1.0 * b.jac) * (tr(sig) * eps)[0];
 		for (int i = 0; i < 6; i++) { b.res[g][i] = eps[i]; b.res[g][6 + i] = sig[i]; }
 		b.Q_d[g] = Qd; b.dz[g] = dz; b.kr[g] = kap;
+		b.Xi_d[g] = Xi; b.dXi_d[g] = dXi; b.g_last = gg;
 		V3 u_d;                                                              // :722-731, 743
 		for (int k = 0; k < 3; k++)
 			for (int a = 0; a < 3; a++) u_d[k] += W.disp[6 * (size_t)(nd[a] - 1) + k] * b.N[g][a];
@@ -556,6 +560,46 @@ void beam_loads(BeamEl& b, double lfac)
 				for (int k = 0; k < 3; k++) e[6 * a + k] += mult * b.N[g][a] * W.g[k];
 	}
 	for (int i = 0; i < 18; i++) b.P[i] = b.Fint[i] - e[i];
+}
+
+// Pipe_1::MountPipeSpecialLoads (Pipe_1.cpp:1443-1494), called by PipeLoad::Mount (PipeLoad.cpp:117-133) during
+// MountLoads: internal pressure p0i on the current configuration of the pipe axis.  Uses what Mount left in the
+// element -- including the scalar g of the LAST Gauss point for both points, as the reference does.
+void pipe_pressure(BeamEl& b, double p0i)
+{
+	Mx<18, 18> T;
+	for (int k = 0; k < 6; k++) put(T, 3 * k, 3 * k, b.T3);
+	Mx<18, 18> K; Mx<18, 1> P;
+	for (int i = 0; i < 18; i++) { P[i] = b.P[i]; for (int j = 0; j < 18; j++) K(i, j) = b.K[i * 18 + j]; }
+	const double mult = 1.0 * b.jac;
+	for (int g = 0; g < 2; g++)
+	{
+		const M3 Q = b.Q_d[g] * b.Q_i[g];
+		const M3& Xi = b.Xi_d[g];
+		const V3 kip = Q * b.kr[g], e3ip = Q * b.e3r;
+		const V3 tf = (-p0i * b.Aint) * cross(kip, e3ip);
+		const V3 tm = (-p0i * b.Aint) * (tr(Xi) * cross(b.dz[g], e3ip));
+		Mx<6, 1> tl; for (int i = 0; i < 3; i++) { tl[i] = tf[i]; tl[3 + i] = tm[i]; }
+		const M3 E3 = skew(e3ip), Kip = skew(kip), dZ = skew(b.dz[g]);
+		const V3 c = cross(e3ip, b.dz[g]);
+		const V3 Xtc = tr(Xi) * c;
+		M3 outer;
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) outer(i, j) = Xtc[i] * b.a_d[g][j];
+		const M3 O1 = (-0.5 * b.g_last) * (outer - skew(c));
+		const M3 K1ua = Kip * E3 * Xi + E3 * b.dXi_d[g] - 1.0 * (E3 * skew(kip) * Xi);
+		const M3 K1aa = O1 + tr(Xi) * dZ * E3 * Xi;
+		const M3 K2ua = E3 * Xi;
+		const M3 K2au = tr(Xi) * E3;
+		Mx<6, 12> Kext;
+		put(Kext, 0, 3, K1ua); put(Kext, 3, 3, K1aa); put(Kext, 0, 9, K2ua); put(Kext, 3, 6, K2au);
+		Mx<6, 18> N; Mx<12, 18> UN;                                            // Pipe_1.cpp:1213-1273
+		for (int a = 0; a < 3; a++)
+			for (int k = 0; k < 6; k++) { N(k, 6 * a + k) = b.N[g][a]; UN(k, 6 * a + k) = b.N[g][a]; UN(6 + k, 6 * a + k) = b.dN[g][a]; }
+		const Mx<18, 1> fl = mult * (tr(T) * (tr(N) * tl));
+		P = P - fl;
+		K = K - (mult * p0i * b.Aint) * (tr(T) * ((tr(N) * Kext) * UN) * T);
+	}
+	for (int i = 0; i < 18; i++) { b.P[i] = P[i]; for (int j = 0; j < 18; j++) b.K[i * 18 + j] = K(i, j); }
 }
 
 // Beam_1.cpp:1494-1506
@@ -1047,6 +1091,16 @@ int gfo_set_elements(int n, const int* type, const int* mat, const int* sec, con
 	for (int e = 0; e < n; e++) if (W.type[e] == T_PIPE) { W.is_pipe[e] = 1; W.type[e] = T_BEAM; W.pret[e] = 0.0; }
 	return 0;
 }
+// PipeLoad objects in load-number order: element lists (0-based) and the pressure P0I each one has at the
+// evaluation time (the caller interpolates the table: Load::GetValueAt(last_converged_time + current_time_step, 0))
+int gfo_set_pipe_loads(int n_loads, const int* ptr, const int* elements, const double* p0i)
+{
+	W.pipe_load_ptr.assign(ptr, ptr + n_loads + 1);
+	W.pipe_load_el.assign(elements, elements + ptr[n_loads]);
+	W.pipe_load_p.assign(p0i, p0i + n_loads);
+	for (int e : W.pipe_load_el) if (e < 0 || e >= W.n_el || !W.is_pipe[e]) return -1;    // PipeLoad::Check (PipeLoad.cpp:91-106)
+	return 0;
+}
 int gfo_set_gravity(int on, double gx, double gy, double gz) { W.g_on = on; W.g[0] = gx; W.g[1] = gy; W.g[2] = gz; return 0; }
 int gfo_set_constraint_mask(const int* m) { W.cmask.assign(m, m + W.n_nodes); return 0; }
 
@@ -1142,6 +1196,9 @@ static int assemble(const double* disp6, double lfac, double* seconds, int dynam
 		if (W.type[e] == T_SHELL) shell_loads(W.shells[W.slot[e]], lfac);
 		else if (W.type[e] == T_BEAM) beam_loads(W.beams[W.slot[e]], lfac);
 	}
+	for (size_t l = 0; l + 1 < W.pipe_load_ptr.size(); l++)                  // MountLoads: PipeLoad::Mount, load by load
+		for (int k = W.pipe_load_ptr[l]; k < W.pipe_load_ptr[l + 1]; k++)
+			pipe_pressure(W.beams[W.slot[W.pipe_load_el[k]]], W.pipe_load_p[l]);
 	if (dynamic)
 	{
 #pragma omp parallel for schedule(static)

@@ -45,6 +45,7 @@ class PortOracle:
         L.gfo_set_elements.argtypes = [C.c_int, _I, _I, _I, _I, _I, _I, C.c_void_p]
         L.gfo_set_gravity.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
         L.gfo_set_constraint_mask.argtypes = [_I]
+        L.gfo_set_pipe_loads.argtypes = [C.c_int, _I, _I, _D]
         L.gfo_get_gls.argtypes = [_I]
         L.gfo_set_extra_triplets.argtypes = [C.c_int, C.c_long, _I, _I, _D]
         L.gfo_assemble.argtypes = [_D, C.c_double, _D]
@@ -94,6 +95,7 @@ class PortOracle:
         if L.gfo_precalc() != 0:
             raise ValueError("unsupported element type")
         self.model = m
+        self._set_pipe_loads(0.0)
         return self
 
     @property
@@ -110,8 +112,20 @@ class PortOracle:
         return g.reshape(-1, 6)
 
     def set_time(self, last_converged: float, step: float, start: float = 0.0, end: float = 1.0):
-        """Gravity ramp of a first solution step (BoolTable.cpp:84-106)."""
+        """Gravity ramp of a first solution step (BoolTable.cpp:84-106); PipeLoad pressures at the evaluation time
+        (Load::GetValueAt(last_converged_time + current_time_step, 0): linear table, Table.cpp)."""
         self.gravity_factor = (last_converged + step - start) / (end - start)
+        self._set_pipe_loads(last_converged + step)
+
+    def _set_pipe_loads(self, time: float):
+        loads = getattr(self.model, "pipe_loads", []) if self.model is not None else []
+        ptr = np.zeros(len(loads) + 1, np.int32)
+        for k, (elements, _) in enumerate(loads):
+            ptr[k + 1] = ptr[k] + len(elements)
+        el = np.concatenate([np.asarray(e, np.int32) - 1 for e, _ in loads]).astype(np.int32) if loads else np.zeros(0, np.int32)
+        p = np.array([float(np.interp(time, np.asarray(t, float)[:, 0], np.asarray(t, float)[:, 1])) for _, t in loads], np.float64)
+        if self.lib.gfo_set_pipe_loads(len(loads), ptr, np.ascontiguousarray(el), np.ascontiguousarray(p)) != 0:
+            raise ValueError("a PipeLoad names an element that is not a Pipe_1")
 
     def set_extra_triplets(self, which: str, rows, cols, vals):
         self.lib.gfo_set_extra_triplets(self.MATS[which], len(vals), np.ascontiguousarray(rows, np.int32),

@@ -35,6 +35,7 @@
 #include "NodalConstraint.h"
 #include "NodalLoad.h"
 #include "ShellLoad.h"
+#include "PipeLoad.h"
 #include "ElementSet.h"
 #include "Environment.h"
 #include "Solution.h"
@@ -331,6 +332,37 @@ int ref_add_shell_load(int n_el, const int* elements, int area_update, int n_tim
 		w += snprintf(buf.data() + w, buf.size() - w, "%.17g %.17g\n", table2[2 * r], table2[2 * r + 1]);
 	FILE* f = text_stream(buf.data());
 	ShellLoad* l = new ShellLoad();
+	bool ok = l->Read(f);
+	fclose(f);
+	if (!ok) return -1;
+	db.loads = grow(db.loads, db.number_loads);
+	db.loads[db.number_loads++] = l;
+	return l->number;
+}
+
+// PipeLoad over an ElementSet (reference PipeLoad.cpp:44-88 format): internal / external pressure on Pipe_1 elements,
+// table rows: time P0I P0E RhoI RhoE.  Goes through the reference's own reader; Pipe_1::MountPipeSpecialLoads
+// (Pipe_1.cpp:1443-1494) folds it into the element block during MountLoads.
+int ref_add_pipe_load(int n_el, const int* elements, int n_times, const double* table5)
+{
+	ElementSet* es = new ElementSet();
+	es->number = db.number_element_sets + 1;
+	es->n_el = n_el;
+	es->list = true;
+	es->el_list = new int[n_el];
+	for (int i = 0; i < n_el; i++) es->el_list[i] = elements[i];
+	db.element_sets = grow(db.element_sets, db.number_element_sets);
+	db.element_sets[db.number_element_sets++] = es;
+	std::vector<char> buf(256 + 200 * (size_t)n_times);
+	int w = snprintf(buf.data(), buf.size(), "%d ElementSet %d NTimes %d\n", db.number_loads + 1, es->number, n_times);
+	for (int r = 0; r < n_times; r++)
+	{
+		for (int k = 0; k < 5; k++)
+			w += snprintf(buf.data() + w, buf.size() - w, "%.17g ", table5[5 * r + k]);
+		w += snprintf(buf.data() + w, buf.size() - w, "\n");
+	}
+	FILE* f = text_stream(buf.data());
+	PipeLoad* l = new PipeLoad();
 	bool ok = l->Read(f);
 	fclose(f);
 	if (!ok) return -1;

@@ -49,6 +49,7 @@ class RefOracle:
         L.ref_add_nodal_constraint.argtypes = [C.c_int, _I, C.c_int]
         L.ref_add_nodal_load.argtypes = [C.c_int, _I, C.c_int, C.c_int, _D]
         L.ref_add_shell_load.argtypes = [C.c_int, _I, C.c_int, C.c_int, _D]
+        L.ref_add_pipe_load.argtypes = [C.c_int, _I, C.c_int, _D]
         L.ref_get_gls.argtypes = [_I]
         L.ref_set_time.argtypes = [C.c_double, C.c_double]
         L.ref_set_displacements.argtypes = [_D]
@@ -118,6 +119,11 @@ class RefOracle:
             table = np.ascontiguousarray(table, np.float64)
             if L.ref_add_shell_load(len(elements), elements, 1 if area_update else 0, table.shape[0], table.reshape(-1)) < 0:
                 raise ValueError("reference rejected the shell load")
+        for elements, table in getattr(m, "pipe_loads", []):
+            elements = np.ascontiguousarray(elements, np.int32)
+            table = np.ascontiguousarray(table, np.float64)
+            if L.ref_add_pipe_load(len(elements), elements, table.shape[0], table.reshape(-1)) < 0:
+                raise ValueError("reference rejected the pipe load")
         if check:
             bad = L.ref_check()
             if bad:

@@ -21,6 +21,7 @@ Newton iteration and the reference's CSR matrices (AA/AB/BA/BB) and vectors
   shell_plate.npz  6x4-cell warped Shell_1 plate with gravity (doubled
                    self-weight quirk), same sequence.
   shell_load.npz   ShellLoad follower pressure (AreaUpdate 0 and 1) folded into the shell blocks
+  pipe_load.npz    PipeLoad internal pressure on a bent Pipe_1 line; tutorial04.npz: the shipped input with its PipeLoad
                    by MountLoads: the host-contributor seam of gfa_add_host_triplets.
   dynamic_beam.npz, dynamic_shell.npz, dynamic_pipe.npz
                    Newmark path (Dynamic.cpp:303-340): UpdateDyn, MountMass,
@@ -226,8 +227,61 @@ def shell_load(R):
     print("shell_load: n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
 
 
+def pipe_load(R):
+    """PipeLoad internal pressure (PipeLoad.cpp:117-133 -> Pipe_1::MountPipeSpecialLoads, Pipe_1.cpp:1443-1494): two loads
+    on overlapping element sets of a pipe line bent by its displacements, self-weight on: two iterations, a commit
+    (so that Q_i, z'_i, kappa_i differ from the reference state) and a third iteration."""
+    m = M.pipe_line(12)
+    m.gravity = (0.0, 0.4, -9.81)
+    m.pipe_loads = [(np.array([1, 2, 3, 5, 9], np.int32), np.array([[0.0, 0.0, 0, 0, 0], [1.0, 3.0e8, 1.0e5, 900.0, 1025.0]])),
+                    (np.array([5, 6, 12], np.int32), np.array([[0.0, 2.0e7, 0, 0, 0], [1.0, -2.5e8, 0, 0, 0]]))]
+    R.load(m)
+    R.set_time(0.0, 0.7)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([0.0, 0.7])
+    z["gls"] = R.gls()
+    rng = np.random.default_rng(20240041)
+    d1 = M.mask_displacements(m, rng.uniform(-3e-2, 3e-2, (m.n_nodes, 6)))
+    for tag, d, commit_after in (("it1", d1, False), ("it2", 0.6 * d1, True), ("it3", -0.35 * d1, False)):
+        R.assemble(d, with_loads=True)
+        z[f"{tag}_disp"] = d.copy()
+        z.update(util.capture(R, tag))
+        if commit_after:
+            R.commit()
+    np.savez_compressed(os.path.join(OUT, "pipe_load.npz"), **z)
+    print("pipe_load: n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
+
+
+def tutorial04(R):
+    """inputs/tutorial04 as the reference ships it (50 Pipe_1, a NodalLoad perturbation and a PipeLoad internal pressure
+    that ramps up in the second solution step): two Newton iterations at t = 1.5 + 0.005 -- inside the pressure ramp --
+    with the loads mounted, a commit in between."""
+    from giraffe_b200.inp import read_inp
+    m, info = read_inp("/root/reference/inputs/tutorial04/tutorial04.inp")
+    assert len(m.pipe_loads) == 1 and len(m.nodal_loads) == 1
+    R.load(m)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([1.5, 0.005])
+    R.set_time(1.5, 0.005)
+    z["gls"] = R.gls()
+    rng = np.random.default_rng(20240042)
+    d1 = M.mask_displacements(m, rng.uniform(-5e-3, 5e-3, (m.n_nodes, 6)))
+    for tag, d, commit_after in (("it1", d1, True), ("it2", -0.4 * d1, False)):
+        R.assemble(d, with_loads=True)
+        z[f"{tag}_disp"] = d.copy()
+        z.update(util.capture(R, tag))
+        if commit_after:
+            R.commit()
+    np.savez_compressed(os.path.join(OUT, "tutorial04.npz"), **z)
+    print("tutorial04: n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
+
+
 if __name__ == "__main__":
     R = RefOracle(threads=1)
+    if sys.argv[1:] == ["pipe_load"]:
+        pipe_load(R)
+        tutorial04(R)
+        sys.exit(0)
     if sys.argv[1:] == ["dynamic"]:          # only the fixtures of the Newmark path
         dynamic(R)
         sys.exit(0)
@@ -239,6 +293,8 @@ if __name__ == "__main__":
         shipped_shell_mesh(R, "tutorial02")
         sys.exit(0)
     shell_load(R)
+    pipe_load(R)
+    tutorial04(R)
     dynamic(R)
     newton_steps(R)
     tutorial01(R)

@@ -724,6 +724,27 @@ def test_shell_load_on_the_device():
     asm.close()
 
 
+@pytest.mark.parametrize("name,commits", [("pipe_load", (("it1", False), ("it2", True), ("it3", False))),
+                                          ("tutorial04", (("it1", True), ("it2", False)))])
+def test_pipe_load_on_the_device(name, commits):
+    """PipeLoad internal pressure evaluated by the library's own kernel (gfa_set_pipe_loads / gfa_apply_pipe_loads)
+    against the reference-generated fixtures: a bent pipe line with two loads, and inputs/tutorial04 as shipped
+    (its NodalLoad stays a host contributor and enters through gfa_add_host_*)."""
+    from test_oracle_golden import _run_pipe_fixture
+    z = _golden(name)
+    m = util.model_from_dict(z)
+    asm = capi.Assembler(m)
+    gls, nf, nx = asm.number_dofs()
+    assert (gls.reshape(-1, 6) == z["gls"]).all()
+    asm.set_dofs(gls, nf, nx)
+    asm.set_time(*z["time"])
+    asm.set_pipe_loads(m.pipe_loads)
+    vec = {"PA": capi.P_A, "PB": capi.P_B}
+    _run_pipe_fixture(z, m, asm, f"device {name}", commits, apply_loads=asm.apply_pipe_loads,
+                      add_triplets=asm.add_host_triplets, add_vector=lambda k, i, v: asm.add_host_vector(vec[k], i, v))
+    asm.close()
+
+
 def test_random_models_against_oracle(port):
     """Seeded random variations (the oracle is pinned to the reference on the same generator by
     tests/test_oracle_vs_ref.py): random constraint masks on random nodes, sizes, warps, gravity, displacement

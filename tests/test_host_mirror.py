@@ -76,6 +76,34 @@ def test_cpp_host_sequence_matches_python_binding(tmp_path):
     assert abs(out["max_P_A"] - np.abs(pa).max()) <= 1e-12 * np.abs(pa).max()
 
 
+@pytest.mark.gpu
+def test_cpp_host_pipe_load_matches_python_binding(tmp_path):
+    """PipeLoad through the .inp writer, the C++ reader, GfaHost::SetGlobalSize (gfa_set_pipe_loads) and MountLoads
+    (gfa_apply_pipe_loads) against the Python binding of the same entry points."""
+    from giraffe_b200 import capi
+    z = np.load(os.path.join(util.GOLDEN_DIR, "pipe_load.npz"))
+    m = util.model_from_dict(z)
+    p = str(tmp_path / "pipes.inp")
+    write_inp(m, p, time_step=0.25)
+    m2, _ = read_inp(p)
+    assert len(m2.pipe_loads) == 2
+    for (e1, t1), (e2, t2) in zip(m.pipe_loads, m2.pipe_loads):
+        assert np.array_equal(e1, e2) and np.array_equal(np.asarray(t1, float), t2)
+    out = json.loads(subprocess.check_output([EXE, p]))
+    assert out["pipe_loads"] == 2
+    asm = capi.Assembler(m).set_dofs()
+    asm.set_time(0.0, 0.25)
+    asm.set_pipe_loads(m.pipe_loads)
+    asm.assemble(np.zeros((m.n_nodes, 6)))
+    no_load = asm.values("AA").copy()
+    asm.apply_pipe_loads(0.25)
+    val = asm.values("AA")
+    assert np.abs(val - no_load).max() > 0.0
+    assert out["nnz_AA"] == len(val)
+    assert abs(out["sum_AA"] - val.sum()) <= 1e-9 * np.abs(val).sum()
+    assert abs(out["max_AA"] - np.abs(val).max()) <= 1e-12 * np.abs(val).max()
+
+
 def _dynamic_model():
     m = M.concat_models([M.beam_line(6, pretension=1.0e4), M.shell_plate(3, 2, warp=0.01)])
     m.gravity = (0.0, 0.0, -9.81)

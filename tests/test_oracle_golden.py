@@ -161,6 +161,72 @@ def test_shell_load_host_contributor(port):
             port.commit()
 
 
+def _run_pipe_fixture(z, m, b, what, commits, apply_loads=None, add_triplets=None, add_vector=None):
+    """Shared by the port (CPU) and the library (GPU): iterations of a fixture whose loads (PipeLoad, and NodalLoad when
+    the model has one) were mounted by the reference."""
+    t = float(z["time"][0] + z["time"][1])
+    for tag, commit in commits:
+        disp = z[f"{tag}_disp"]
+        pa_add = pb_add = None
+        if m.nodal_loads:
+            trip, pa_add, pb_add = util.nodal_load_contribution(m, z["gls"], disp, t)
+            if add_triplets is None:                      # the port takes host triplets before its assembly
+                for w in ("AA", "AB", "BA", "BB"):
+                    b.set_extra_triplets(w, *trip[w])
+        b.assemble(disp)
+        if apply_loads is not None:
+            apply_loads(t)
+        if m.nodal_loads and add_triplets is not None:
+            for w in ("AA", "AB", "BA", "BB"):
+                if trip[w][0]:
+                    add_triplets(w, *trip[w])
+            add_vector("PA", *pa_add)
+            if pb_add[0]:
+                add_vector("PB", *pb_add)
+        util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), b.csr, f"{what} {tag}")
+        pa, ia, pb = [v.copy() for v in b.vectors()]
+        if m.nodal_loads and add_triplets is None:
+            np.add.at(pa, pa_add[0], pa_add[1]); np.add.at(pb, pb_add[0], pb_add[1])
+        util.assert_parity(z[f"{tag}_PA"], pa, f"{what} {tag} P_A")
+        util.assert_parity(z[f"{tag}_IA"], ia, f"{what} {tag} I_A")
+        util.assert_parity(z[f"{tag}_PB"], pb, f"{what} {tag} P_B")
+        if commit:
+            b.commit()
+
+
+def test_pipe_load_internal_pressure(port):
+    """PipeLoad -> Pipe_1::MountPipeSpecialLoads (Pipe_1.cpp:1443-1494) as restated in the oracle port, against what the
+    reference's own MountLoads + MountGlobal produced on a bent pipe line (two loads, overlapping element sets,
+    before and after a commit).  The pressure matters: the fixture differs from the same assembly without it."""
+    z = _load("pipe_load")
+    m = util.model_from_dict(z)
+    assert len(m.pipe_loads) == 2
+    port.load(m)
+    port.set_time(*z["time"])
+    assert (port.gls() == z["gls"]).all()
+    _run_pipe_fixture(z, m, port, "pipe_load", (("it1", False), ("it2", True), ("it3", False)))
+    # sensitivity: without the loads the same assembly is far outside the tolerance
+    saved, m.pipe_loads = m.pipe_loads, []
+    port.load(m)
+    port.set_time(*z["time"])
+    port.assemble(z["it1_disp"])
+    m.pipe_loads = saved
+    assert np.abs(port.vectors()[0] - z["it1_PA"]).max() > 1e-4 * np.abs(z["it1_PA"]).max()
+    assert np.abs(port.csr("AA")[2] - z["it1_AA_val"]).max() > 1e-6 * np.abs(z["it1_AA_val"]).max()
+
+
+def test_shipped_tutorial04_with_its_pipe_load(port):
+    """inputs/tutorial04 as shipped (50 Pipe_1, NodalLoad perturbation + PipeLoad internal pressure), inside the
+    pressure ramp of its second solution step."""
+    z = _load("tutorial04")
+    m = util.model_from_dict(z)
+    assert len(m.pipe_loads) == 1 and m.n_elements == 50
+    port.load(m)
+    port.set_time(*z["time"])
+    assert (port.gls() == z["gls"]).all()
+    _run_pipe_fixture(z, m, port, "tutorial04", (("it1", True), ("it2", False)))
+
+
 @pytest.mark.parametrize("name", ["tutorial05", "tutorial02"])
 def test_shipped_shell_meshes(port, name):
     """inputs/tutorial05 (400 Shell_1) and inputs/tutorial02 (3036 Shell_1) as the reference ships them, assembled by

@@ -110,7 +110,11 @@ def model_to_dict(m: M.Model, prefix: str = "m_") -> dict:
         "n_loads": np.array([len(m.nodal_loads)]),
         "pipe_sections": np.asarray(m.pipe_sections, float).reshape(-1, 11),
         "n_shell_loads": np.array([len(m.shell_loads)]),
+        "n_pipe_loads": np.array([len(getattr(m, "pipe_loads", []))]),
     }
+    for i, (elements, table) in enumerate(getattr(m, "pipe_loads", [])):
+        d[f"p{i}_elements"] = np.asarray(elements, np.int32)
+        d[f"p{i}_table"] = np.asarray(table, float)
     for i, (elements, area_update, table) in enumerate(m.shell_loads):
         d[f"s{i}_elements"] = np.asarray(elements, np.int32)
         d[f"s{i}_area_update"] = np.array([1 if area_update else 0])
@@ -144,6 +148,8 @@ def model_from_dict(z, prefix: str = "m_") -> M.Model:
         m.pipe_sections = np.asarray(g("pipe_sections"), float).reshape(-1, 11)
     if prefix + "n_shell_loads" in getattr(z, "files", z):
         m.shell_loads = [(g(f"s{i}_elements"), bool(g(f"s{i}_area_update")[0]), g(f"s{i}_table")) for i in range(int(g("n_shell_loads")[0]))]
+    if prefix + "n_pipe_loads" in getattr(z, "files", z):
+        m.pipe_loads = [(g(f"p{i}_elements"), g(f"p{i}_table")) for i in range(int(g("n_pipe_loads")[0]))]
     return m
 
 
