@@ -214,8 +214,8 @@ bool GfaHost::ReadFile(const char* path) {
                     pipe_loads.push_back(l);
                     continue;
                 }
-                if (tk[i] != "NodalLoad") return fail("load " + tk[i] + " stays on the host");
-                GfaNodalLoad l; l.node_set = integer(i + 3); l.cs = integer(i + 5);
+                if (tk[i] != "NodalLoad" && tk[i] != "NodalFollowerLoad") return fail("load " + tk[i] + " is outside the subset this reader keeps");
+                GfaNodalLoad l; l.follower = tk[i] == "NodalFollowerLoad"; l.node_set = integer(i + 3); l.cs = integer(i + 5);
                 const int nt = integer(i + 7); i += 8;
                 for (int k = 0; k < 7 * nt; k++) l.table.push_back(num(i + k));
                 i += 7 * (size_t)nt;
@@ -352,8 +352,8 @@ void GfaHost::SetGlobalDOFs() {
 void GfaHost::CollectLoadPattern(std::vector<int>& m, std::vector<int>& r, std::vector<int>& c) {
     for (const GfaNodalLoad& l : loads)
         for (int nd : node_sets[l.node_set - 1])
-            for (int lin = 0; lin < 3; lin++)
-                for (int col = 0; col < 3; col++) {
+            for (int lin = l.follower ? -3 : 0; lin < 3; lin++)          // NodalFollowerLoad pushes the node's whole 6 x 6 block
+                for (int col = l.follower ? -3 : 0; col < 3; col++) {
                     const int gl = GLs[6 * (size_t)(nd - 1) + 3 + lin], gc = GLs[6 * (size_t)(nd - 1) + 3 + col];
                     if (gl == 0 || gc == 0) continue;
                     m.push_back(gl > 0 ? (gc > 0 ? GFA_AA : GFA_AB) : (gc > 0 ? GFA_BA : GFA_BB));
@@ -448,6 +448,55 @@ bool GfaHost::MountLoads() {
         double mult[6];
         for (int k = 0; k < 6; k++) { int cnt = 0; for (int nd : set) cnt += active_GL[6 * (size_t)(nd - 1) + k]; mult[k] = 1.0 / cnt; }
         const double* Q = &cs[9 * (size_t)(l.cs - 1)];
+        if (l.follower) {       // NodalFollowerLoad::Mount (NodalFollowerLoad.cpp:243-325)
+            if (copy_cache.empty()) {
+                copy_cache.resize(6 * (size_t)number_nodes());
+                if (gfa_copy_coordinates(h, copy_cache.data()) != GFA_OK) return fail(gfa_last_error());
+            }
+            for (int nd : set) {
+                auto rod = [](const double* a, double& g, double* Qm, double* Xi) {
+                    const double A[9] = { 0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0 };
+                    g = 4.0 / (4.0 + (a[0] * a[0] + a[1] * a[1] + a[2] * a[2]));
+                    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+                        double aa = 0.0; for (int k = 0; k < 3; k++) aa += A[3 * i + k] * A[3 * k + j];
+                        Qm[3 * i + j] = (i == j ? 1.0 : 0.0) + g * (A[3 * i + j] + 0.5 * aa);
+                        Xi[3 * i + j] = g * ((i == j ? 1.0 : 0.0) + 0.5 * A[3 * i + j]);
+                    }
+                };
+                double g, Qc[9], Xc[9], Qd[9], Xi[9], Qi[9];
+                rod(&copy_cache[6 * (size_t)(nd - 1) + 3], g, Qc, Xc);
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double v = 0.0; for (int k = 0; k < 3; k++) v += Qc[3 * i + k] * Q[3 * j + k]; Qi[3 * i + j] = v; }   // Qi = Q(copy) * transp(CS Q)
+                const double* a = &displacements[6 * (size_t)(nd - 1) + 3];
+                rod(a, g, Qd, Xi);
+                double fl[3], ml[3], Qf[3], Qm[3], fip[3], mip[3];
+                for (int k = 0; k < 3; k++) { fl[k] = mult[k] * l.GetValueAt(t, 1 + k); ml[k] = mult[3 + k] * l.GetValueAt(t, 4 + k); }
+                for (int i = 0; i < 3; i++) { Qf[i] = Qi[3 * i] * fl[0] + Qi[3 * i + 1] * fl[1] + Qi[3 * i + 2] * fl[2]; Qm[i] = Qi[3 * i] * ml[0] + Qi[3 * i + 1] * ml[1] + Qi[3 * i + 2] * ml[2]; }
+                for (int i = 0; i < 3; i++) { fip[i] = Qd[3 * i] * Qf[0] + Qd[3 * i + 1] * Qf[1] + Qd[3 * i + 2] * Qf[2]; mip[i] = Xi[3 * i] * Qm[0] + Xi[3 * i + 1] * Qm[1] + Xi[3 * i + 2] * Qm[2]; }
+                const double Sf[9] = { 0, -fip[2], fip[1], fip[2], 0, -fip[0], -fip[1], fip[0], 0 };
+                const double Sm[9] = { 0, -Qm[2], Qm[1], Qm[2], 0, -Qm[0], -Qm[1], Qm[0], 0 };
+                double dq[36];
+                for (int q = 0; q < 36; q++) dq[q] = 0.0;
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+                    double k12 = 0.0, xo = 0.0;
+                    for (int k = 0; k < 3; k++) { k12 += Sf[3 * i + k] * Xi[3 * k + j]; xo += Xi[3 * i + k] * Qm[k]; }
+                    dq[6 * i + 3 + j] = -1.0 * k12;                                        // K12 = -skew(fip) Xi
+                    dq[6 * (3 + i) + 3 + j] = -0.5 * g * (Sm[3 * i + j] + xo * a[j]);      // K22 = -g/2 (skew(Qi m) + Xi (Qi m) alpha^T)
+                }
+                const int* gl = &GLs[6 * (size_t)(nd - 1)];
+                for (int lin = 0; lin < 6; lin++) {
+                    if (gl[lin] == 0) continue;
+                    const double v = -1.0 * (lin < 3 ? fip[lin] : mip[lin - 3]);
+                    if (gl[lin] > 0) { ia.push_back(gl[lin] - 1); va.push_back(v); } else { ib.push_back(-gl[lin] - 1); vb.push_back(v); }
+                    for (int col = 0; col < 6; col++) {
+                        const int g1 = gl[lin], g2 = gl[col];
+                        if (g2 == 0) continue;
+                        const int w = g1 > 0 ? (g2 > 0 ? GFA_AA : GFA_AB) : (g2 > 0 ? GFA_BA : GFA_BB);
+                        tr[w].push_back(abs(g1) - 1); tc[w].push_back(abs(g2) - 1); tv[w].push_back(-1.0 * dq[6 * lin + col]);
+                    }
+                }
+            }
+            continue;
+        }
         for (int nd : set) {
             double fl[3], ml[3], f[3], m[3];
             for (int k = 0; k < 3; k++) { fl[k] = mult[k] * l.GetValueAt(t, 1 + k); ml[k] = mult[3 + k] * l.GetValueAt(t, 4 + k); }
@@ -506,6 +555,7 @@ void GfaHost::UpdateDisps(const double* x_A) {
 
 bool GfaHost::SaveConfiguration() {
     if (gfa_commit_state(h) != GFA_OK) return fail(gfa_last_error());
+    copy_cache.clear();                                                  // copy_coordinates moved
     std::fill(displacements.begin(), displacements.end(), 0.0);          // Solution::Zeros of the next increment
     return true;
 }

@@ -34,6 +34,7 @@
 
 struct GfaNodalLoad {              // NodalLoad with a numeric table (NodalLoad.h, Table.h)
     int node_set = 0, cs = 0;
+    bool follower = false;         // NodalFollowerLoad (NodalFollowerLoad.h): same table, loads follow the node's rotation
     std::vector<double> table;     // rows: time FX FY FZ MX MY MZ
     double GetValueAt(double t, int column) const;   // Table::GetValueAt, linear interpolation
 };
@@ -75,6 +76,7 @@ public:
     std::vector<GfaNodalLoad> loads;
     std::vector<std::vector<int> > element_sets;  // ElementSet::el_list, 1-based (ElementSet.h)
     std::vector<GfaShellLoad> shell_loads;        // ShellLoad (host contributor: Shell_1::MountShellSpecialLoads)
+    std::vector<double> copy_cache;               // Node::copy_coordinates [n][6], fetched for NodalFollowerLoad, dropped at SaveConfiguration
     std::vector<GfaPipeLoad> pipe_loads;          // PipeLoad (Pipe_1::MountPipeSpecialLoads, evaluated on the device)
     bool g_exist = false;
     double G[3] = { 0, 0, 0 };

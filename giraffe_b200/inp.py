@@ -38,7 +38,7 @@ def read_inp(path: str):
     i = 0
     nodes, mats, secs, shsecs, csd, pipes = {}, {}, {}, {}, {}, {}
     elems, nodesets, cons, loads = [], {}, [], []
-    elemsets, shloads, ploads = {}, [], []
+    elemsets, shloads, ploads, floads = {}, [], [], []
     gravity = None
     info = {}
 
@@ -152,10 +152,11 @@ def read_inp(path: str):
                     table = np.array([float(t) for t in tk[i:i + 5 * nt]]).reshape(nt, 5); i += 5 * nt
                     ploads.append((es, table))
                     continue
-                assert tk[i] == "NodalLoad", f"load {tk[i]} stays on the host"
+                assert tk[i] in ("NodalLoad", "NodalFollowerLoad"), f"load {tk[i]} is outside the subset"
+                follower = tk[i] == "NodalFollowerLoad"      # same format (NodalFollowerLoad.cpp:56-112)
                 sid, cs, nt = int(tk[i + 3]), int(tk[i + 5]), int(tk[i + 7]); i += 8
                 table = np.array([float(t) for t in tk[i:i + 7 * nt]]).reshape(nt, 7); i += 7 * nt
-                loads.append((sid, cs, table))
+                (floads if follower else loads).append((sid, cs, table))
         elif kw == "ElementSets":        # ElementSet id Elements n List ... | Sequence Initial a Increment k (ElementSet.cpp:27-95)
             n = int(tk[i + 1]); i += 2
             for _ in range(n):
@@ -212,6 +213,7 @@ def read_inp(path: str):
     m.gravity = gravity
     m.shell_loads = [(np.array(elemsets[es], np.int32), au, t) for es, au, t in shloads]
     m.pipe_loads = [(np.array(elemsets[es], np.int32), t) for es, t in ploads]
+    m.follower_loads = [(np.array(nodesets[s], np.int32), cs, t) for s, cs, t in floads]
     info["node_sets"] = nodesets
     return _finish(m), info
 
@@ -229,7 +231,8 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
         f.write(f"Nodes\t{m.n_nodes}\n")
         for i, x in enumerate(m.xyz):
             f.write(f"Node\t{i + 1}\t{_r(x[0])}\t{_r(x[1])}\t{_r(x[2])}\n")
-        sets = [np.asarray(n) for n, _ in m.constraints] + [np.asarray(n) for n, _, _ in m.nodal_loads]
+        follower_loads = getattr(m, "follower_loads", [])
+        sets = [np.asarray(n) for n, _ in m.constraints] + [np.asarray(n) for n, _, _ in m.nodal_loads] + [np.asarray(n) for n, _, _ in follower_loads]
         if sets:
             f.write(f"\nNodeSets\t{len(sets)}\n")
             for k, s in enumerate(sets):
@@ -279,8 +282,8 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
             f.write(f"\nElementSets\t{len(m.shell_loads) + len(pipe_loads)}\n")
             for k, elements in enumerate([l[0] for l in m.shell_loads] + [l[0] for l in pipe_loads]):
                 f.write(f"ElementSet\t{k + 1}\tElements\t{len(elements)}\tList\t" + "\t".join(str(int(e)) for e in elements) + "\n")
-        if m.nodal_loads or m.shell_loads or pipe_loads:
-            f.write(f"\nLoads\t{len(m.nodal_loads) + len(m.shell_loads) + len(pipe_loads)}\n")
+        if m.nodal_loads or m.shell_loads or pipe_loads or follower_loads:
+            f.write(f"\nLoads\t{len(m.nodal_loads) + len(m.shell_loads) + len(pipe_loads) + len(follower_loads)}\n")
             for k, (nodes, cs, table) in enumerate(m.nodal_loads):
                 table = np.asarray(table, float)
                 f.write(f"NodalLoad\t{k + 1}\tNodeSet\t{len(m.constraints) + k + 1}\tCS\t{cs}\tNTimes\t{len(table)}\n")
@@ -294,6 +297,12 @@ def write_inp(m: Model, path: str, end_time: float = 1.0, time_step: float = 1.0
             for k, (elements, table) in enumerate(pipe_loads):
                 table = np.asarray(table, float)
                 f.write(f"PipeLoad\t{len(m.nodal_loads) + len(m.shell_loads) + k + 1}\tElementSet\t{len(m.shell_loads) + k + 1}\tNTimes\t{len(table)}\n")
+                for row in table:
+                    f.write("\t".join(repr(float(v)) for v in row) + "\n")
+            for k, (nodes, cs, table) in enumerate(follower_loads):
+                table = np.asarray(table, float)
+                f.write(f"NodalFollowerLoad\t{len(m.nodal_loads) + len(m.shell_loads) + len(pipe_loads) + k + 1}\tNodeSet\t{len(m.constraints) + len(m.nodal_loads) + k + 1}"
+                        f"\tCS\t{cs}\tNTimes\t{len(table)}\n")
                 for row in table:
                     f.write("\t".join(repr(float(v)) for v in row) + "\n")
         if m.constraints:

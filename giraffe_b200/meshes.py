@@ -56,6 +56,9 @@ class Model:
     # PipeLoad (PipeLoad.h): [(element ids 1-based, table[n,5] = time, P0I, P0E, RhoI, RhoE)] -- internal pressure on
     # Pipe_1 elements (Pipe_1::MountPipeSpecialLoads uses P0I only), evaluated by gfa_apply_pipe_loads
     pipe_loads: list = field(default_factory=list)
+    # NodalFollowerLoad (NodalFollowerLoad.h): [(node ids 1-based, CS id, table[n,7])] like nodal_loads; forces and moments
+    # follow the node's rotation.  A host-side Load: it enters through gfa_add_host_triplets / gfa_add_host_vector
+    follower_loads: list = field(default_factory=list)
 
     @property
     def n_nodes(self) -> int:

@@ -36,6 +36,7 @@
 #include "NodalLoad.h"
 #include "ShellLoad.h"
 #include "PipeLoad.h"
+#include "NodalFollowerLoad.h"
 #include "ElementSet.h"
 #include "Environment.h"
 #include "Solution.h"
@@ -308,6 +309,30 @@ int ref_add_nodal_load(int n, const int* nodes, int cs, int n_times, const doubl
 	bool ok = l->Read(f);
 	fclose(f);
 	if (!ok) return -1;
+	db.loads = grow(db.loads, db.number_loads);
+	db.loads[db.number_loads++] = l;
+	return l->number;
+}
+
+// NodalFollowerLoad (reference NodalFollowerLoad.cpp:56-112 format, same table as NodalLoad): forces and moments that
+// follow the node's rotation.  PreCalc allocates its per-node buffers (:144-151).
+int ref_add_nodal_follower_load(int n, const int* nodes, int cs, int n_times, const double* table7)
+{
+	std::vector<char> buf(256 + 200 * (size_t)n_times);
+	int set_id = add_node_set(n, nodes);
+	int w = snprintf(buf.data(), buf.size(), "%d NodeSet %d CS %d NTimes %d\n", db.number_loads + 1, set_id, cs, n_times);
+	for (int r = 0; r < n_times; r++)
+	{
+		for (int k = 0; k < 7; k++)
+			w += snprintf(buf.data() + w, buf.size() - w, "%.17g ", table7[7 * r + k]);
+		w += snprintf(buf.data() + w, buf.size() - w, "\n");
+	}
+	FILE* f = text_stream(buf.data());
+	NodalFollowerLoad* l = new NodalFollowerLoad();
+	bool ok = l->Read(f);
+	fclose(f);
+	if (!ok) return -1;
+	l->PreCalc();
 	db.loads = grow(db.loads, db.number_loads);
 	db.loads[db.number_loads++] = l;
 	return l->number;

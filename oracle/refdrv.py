@@ -50,6 +50,7 @@ class RefOracle:
         L.ref_add_nodal_load.argtypes = [C.c_int, _I, C.c_int, C.c_int, _D]
         L.ref_add_shell_load.argtypes = [C.c_int, _I, C.c_int, C.c_int, _D]
         L.ref_add_pipe_load.argtypes = [C.c_int, _I, C.c_int, _D]
+        L.ref_add_nodal_follower_load.argtypes = [C.c_int, _I, C.c_int, C.c_int, _D]
         L.ref_get_gls.argtypes = [_I]
         L.ref_set_time.argtypes = [C.c_double, C.c_double]
         L.ref_set_displacements.argtypes = [_D]
@@ -114,6 +115,11 @@ class RefOracle:
             table = np.ascontiguousarray(table, np.float64)
             if L.ref_add_nodal_load(len(nodes), nodes, int(cs), table.shape[0], table.reshape(-1)) < 0:
                 raise ValueError("reference rejected the nodal load")
+        for nodes, cs, table in getattr(m, "follower_loads", []):
+            nodes = np.ascontiguousarray(nodes, np.int32)
+            table = np.ascontiguousarray(table, np.float64)
+            if L.ref_add_nodal_follower_load(len(nodes), nodes, int(cs), table.shape[0], table.reshape(-1)) < 0:
+                raise ValueError("reference rejected the nodal follower load")
         for elements, area_update, table in getattr(m, "shell_loads", []):
             elements = np.ascontiguousarray(elements, np.int32)
             table = np.ascontiguousarray(table, np.float64)

@@ -21,7 +21,7 @@ Newton iteration and the reference's CSR matrices (AA/AB/BA/BB) and vectors
   shell_plate.npz  6x4-cell warped Shell_1 plate with gravity (doubled
                    self-weight quirk), same sequence.
   shell_load.npz   ShellLoad follower pressure (AreaUpdate 0 and 1) folded into the shell blocks
-  pipe_load.npz    PipeLoad internal pressure on a bent Pipe_1 line; tutorial04.npz: the shipped input with its PipeLoad
+  pipe_load.npz    PipeLoad internal pressure on a bent Pipe_1 line; tutorial04.npz / tutorial03.npz: the shipped inputs with their PipeLoad / NodalFollowerLoad
                    by MountLoads: the host-contributor seam of gfa_add_host_triplets.
   dynamic_beam.npz, dynamic_shell.npz, dynamic_pipe.npz
                    Newmark path (Dynamic.cpp:303-340): UpdateDyn, MountMass,
@@ -276,11 +276,37 @@ def tutorial04(R):
     print("tutorial04: n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
 
 
+def tutorial03(R):
+    """inputs/tutorial03 as the reference ships it (50 Pipe_1, a NodalLoad imperfection and a NodalFollowerLoad that
+    compresses the pipe in the second solution step): two Newton iterations at t = 1.5 + 0.005 with the loads
+    mounted, a commit in between (the follower load reads the committed rotations)."""
+    from giraffe_b200.inp import read_inp
+    m, info = read_inp("/root/reference/inputs/tutorial03/tutorial03.inp")
+    assert len(m.follower_loads) == 1 and len(m.nodal_loads) == 1
+    R.load(m)
+    z = util.model_to_dict(m)
+    z["time"] = np.array([1.5, 0.005])
+    R.set_time(1.5, 0.005)
+    z["gls"] = R.gls()
+    rng = np.random.default_rng(20240043)
+    d1 = M.mask_displacements(m, rng.uniform(-5e-3, 5e-3, (m.n_nodes, 6)))
+    for tag, d, commit_after in (("it1", d1, True), ("it2", -0.4 * d1, False)):
+        z[f"{tag}_copy_before"] = R.copy_coordinates()
+        R.assemble(d, with_loads=True)
+        z[f"{tag}_disp"] = d.copy()
+        z.update(util.capture(R, tag))
+        if commit_after:
+            R.commit()
+    np.savez_compressed(os.path.join(OUT, "tutorial03.npz"), **z)
+    print("tutorial03: n_free", R.n_free, "nnz_AA", len(z["it1_AA_val"]))
+
+
 if __name__ == "__main__":
     R = RefOracle(threads=1)
     if sys.argv[1:] == ["pipe_load"]:
         pipe_load(R)
         tutorial04(R)
+        tutorial03(R)
         sys.exit(0)
     if sys.argv[1:] == ["dynamic"]:          # only the fixtures of the Newmark path
         dynamic(R)
@@ -295,6 +321,7 @@ if __name__ == "__main__":
     shell_load(R)
     pipe_load(R)
     tutorial04(R)
+    tutorial03(R)
     dynamic(R)
     newton_steps(R)
     tutorial01(R)

@@ -725,11 +725,13 @@ def test_shell_load_on_the_device():
 
 
 @pytest.mark.parametrize("name,commits", [("pipe_load", (("it1", False), ("it2", True), ("it3", False))),
-                                          ("tutorial04", (("it1", True), ("it2", False)))])
+                                          ("tutorial04", (("it1", True), ("it2", False))),
+                                          ("tutorial03", (("it1", True), ("it2", False)))])
 def test_pipe_load_on_the_device(name, commits):
     """PipeLoad internal pressure evaluated by the library's own kernel (gfa_set_pipe_loads / gfa_apply_pipe_loads)
     against the reference-generated fixtures: a bent pipe line with two loads, and inputs/tutorial04 as shipped
-    (its NodalLoad stays a host contributor and enters through gfa_add_host_*)."""
+    (its NodalLoad stays a host contributor and enters through gfa_add_host_*), and inputs/tutorial03 (Pipe_1 with a
+    NodalLoad and a NodalFollowerLoad, both host contributors)."""
     from test_oracle_golden import _run_pipe_fixture
     z = _golden(name)
     m = util.model_from_dict(z)

@@ -104,6 +104,40 @@ def test_cpp_host_pipe_load_matches_python_binding(tmp_path):
     assert abs(out["max_AA"] - np.abs(val).max()) <= 1e-12 * np.abs(val).max()
 
 
+@pytest.mark.gpu
+def test_cpp_static_solve_with_a_follower_load(tmp_path, ref):
+    """NodalFollowerLoad in the C++ host mirror (GfaHost::MountLoads: Q_i from the committed rotations fetched with
+    gfa_copy_coordinates): a cantilever bent by a follower force and moment at its tip, four increments of
+    `gfa_run --solve`, against the same Newton loop through the reference's own sources."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    m = M.beam_line(8)
+    tip = m.n_nodes
+    m.follower_loads = [(np.array([tip], np.int32), 1, np.array([[0.0, 0, 0, 0, 0, 0, 0], [1.0, 1.2e6, -6.0e5, 0.0, 0.0, 1.8e6, 3.0e5]]))]
+    p = str(tmp_path / "follower.inp")
+    write_inp(m, p, end_time=1.0, time_step=0.25)
+    m2, _ = read_inp(p)
+    assert len(m2.follower_loads) == 1 and np.array_equal(m2.follower_loads[0][2], m.follower_loads[0][2])
+    out = json.loads(subprocess.check_output([EXE, "--solve", p]))
+    assert out["increments"] == 4
+    got = np.array(out["copy_coordinates"]).reshape(-1, 6)
+    ref.load(m)
+    t = 0.0
+    for inc in range(4):
+        ref.set_time(t, 0.25)
+        d = np.zeros((m.n_nodes, 6))
+        for it in range(8):
+            ref.assemble(d, with_loads=True)
+            ref.residual(None)
+            o, i, v, shape = ref.csr("AA")
+            x = spla.spsolve(sp.csr_matrix((v, i, o), shape=shape).tocsc(), ref.vectors()[0])
+            d = ref.update_displacements(x)[0]
+        ref.commit()
+        t += 0.25
+    assert np.abs(ref.copy_coordinates()[:, 3:]).max() > 0.05, "the load must rotate the tip for the test to mean anything"
+    util.assert_parity(ref.copy_coordinates(), got, "cantilever under a follower load, gfa_run --solve", tol=1e-9)
+
+
 def _dynamic_model():
     m = M.concat_models([M.beam_line(6, pretension=1.0e4), M.shell_plate(3, 2, warp=0.01)])
     m.gravity = (0.0, 0.0, -9.81)

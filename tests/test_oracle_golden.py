@@ -168,15 +168,17 @@ def _run_pipe_fixture(z, m, b, what, commits, apply_loads=None, add_triplets=Non
     for tag, commit in commits:
         disp = z[f"{tag}_disp"]
         pa_add = pb_add = None
-        if m.nodal_loads:
-            trip, pa_add, pb_add = util.nodal_load_contribution(m, z["gls"], disp, t)
+        host_loads = bool(m.nodal_loads or getattr(m, "follower_loads", []))
+        if host_loads:
+            copy = z[f"{tag}_copy_before"] if f"{tag}_copy_before" in z.files else np.zeros((m.n_nodes, 6))
+            trip, pa_add, pb_add = util.host_load_contribution(m, z["gls"], disp, copy, t)
             if add_triplets is None:                      # the port takes host triplets before its assembly
                 for w in ("AA", "AB", "BA", "BB"):
                     b.set_extra_triplets(w, *trip[w])
         b.assemble(disp)
         if apply_loads is not None:
             apply_loads(t)
-        if m.nodal_loads and add_triplets is not None:
+        if host_loads and add_triplets is not None:
             for w in ("AA", "AB", "BA", "BB"):
                 if trip[w][0]:
                     add_triplets(w, *trip[w])
@@ -185,7 +187,7 @@ def _run_pipe_fixture(z, m, b, what, commits, apply_loads=None, add_triplets=Non
                 add_vector("PB", *pb_add)
         util.assert_system_parity(lambda w: util.captured_csr(z, tag, w), b.csr, f"{what} {tag}")
         pa, ia, pb = [v.copy() for v in b.vectors()]
-        if m.nodal_loads and add_triplets is None:
+        if host_loads and add_triplets is None:
             np.add.at(pa, pa_add[0], pa_add[1]); np.add.at(pb, pb_add[0], pb_add[1])
         util.assert_parity(z[f"{tag}_PA"], pa, f"{what} {tag} P_A")
         util.assert_parity(z[f"{tag}_IA"], ia, f"{what} {tag} I_A")
@@ -225,6 +227,18 @@ def test_shipped_tutorial04_with_its_pipe_load(port):
     port.set_time(*z["time"])
     assert (port.gls() == z["gls"]).all()
     _run_pipe_fixture(z, m, port, "tutorial04", (("it1", True), ("it2", False)))
+
+
+def test_shipped_tutorial03_with_its_follower_load(port):
+    """inputs/tutorial03 as shipped (50 Pipe_1, NodalLoad + NodalFollowerLoad): the follower load is a host Load, restated
+    in tests/util.py and pushed as host triplets; the second iteration sees committed rotations."""
+    z = _load("tutorial03")
+    m = util.model_from_dict(z)
+    assert len(m.follower_loads) == 1 and m.n_elements == 50
+    port.load(m)
+    port.set_time(*z["time"])
+    assert (port.gls() == z["gls"]).all()
+    _run_pipe_fixture(z, m, port, "tutorial03", (("it1", True), ("it2", False)))
 
 
 @pytest.mark.parametrize("name", ["tutorial05", "tutorial02"])

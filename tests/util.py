@@ -111,7 +111,12 @@ def model_to_dict(m: M.Model, prefix: str = "m_") -> dict:
         "pipe_sections": np.asarray(m.pipe_sections, float).reshape(-1, 11),
         "n_shell_loads": np.array([len(m.shell_loads)]),
         "n_pipe_loads": np.array([len(getattr(m, "pipe_loads", []))]),
+        "n_follower_loads": np.array([len(getattr(m, "follower_loads", []))]),
     }
+    for i, (nodes, cs, table) in enumerate(getattr(m, "follower_loads", [])):
+        d[f"f{i}_nodes"] = np.asarray(nodes, np.int32)
+        d[f"f{i}_cs"] = np.array([cs])
+        d[f"f{i}_table"] = np.asarray(table, float)
     for i, (elements, table) in enumerate(getattr(m, "pipe_loads", [])):
         d[f"p{i}_elements"] = np.asarray(elements, np.int32)
         d[f"p{i}_table"] = np.asarray(table, float)
@@ -148,6 +153,8 @@ def model_from_dict(z, prefix: str = "m_") -> M.Model:
         m.pipe_sections = np.asarray(g("pipe_sections"), float).reshape(-1, 11)
     if prefix + "n_shell_loads" in getattr(z, "files", z):
         m.shell_loads = [(g(f"s{i}_elements"), bool(g(f"s{i}_area_update")[0]), g(f"s{i}_table")) for i in range(int(g("n_shell_loads")[0]))]
+    if prefix + "n_follower_loads" in getattr(z, "files", z):
+        m.follower_loads = [(g(f"f{i}_nodes"), int(g(f"f{i}_cs")[0]), g(f"f{i}_table")) for i in range(int(g("n_follower_loads")[0]))]
     if prefix + "n_pipe_loads" in getattr(z, "files", z):
         m.pipe_loads = [(g(f"p{i}_elements"), g(f"p{i}_table")) for i in range(int(g("n_pipe_loads")[0]))]
     return m
@@ -218,6 +225,67 @@ def nodal_load_contribution(m: M.Model, gls: np.ndarray, disp: np.ndarray, time:
                     trip[w][1].append(abs(gc) - 1)
                     trip[w][2].append(-1.0 * V[lin, col])
     return trip, pa, pb
+
+
+def nodal_follower_load_contribution(m: M.Model, gls: np.ndarray, disp: np.ndarray, copy: np.ndarray, time: float):
+    """Host restatement of NodalFollowerLoad::Mount (reference NodalFollowerLoad.cpp:243-325): forces and moments given
+    in a coordinate system that rotates with the node -- Q_i from the committed rotation (copy_coordinates[3:6]) times
+    the increment's Q / Xi.  Returns (triplets per matrix, additions to P_A, additions to P_B) like
+    nodal_load_contribution.  It pushes ALL 36 positions of the node's block (zeros in the translation columns)."""
+    trip = {w: ([], [], []) for w in ("AA", "AB", "BA", "BB")}
+    pa, pb = ([], []), ([], [])
+    active = gls != 0
+    I = np.eye(3)
+    for nodes, cs_id, table in getattr(m, "follower_loads", []):
+        table = np.asarray(table, float)
+        vals = np.array([np.interp(time, table[:, 0], table[:, k]) for k in range(1, 7)])
+        nodes = np.asarray(nodes, int)
+        nf = np.array([active[nodes - 1, k].sum() for k in range(6)], float)
+        with np.errstate(divide="ignore"):
+            mult = 1.0 / nf
+        Qcs = m.cs[cs_id - 1].reshape(3, 3)      # rows E1,E2,E3 = CoordinateSystem::Q
+        for nd in nodes:
+            a = copy[nd - 1, 3:6]
+            A = _skew(a)
+            g = 4.0 / (4.0 + a @ a)
+            Qi = (I + g * (A + 0.5 * (A @ A))) @ Qcs.T
+            a = disp[nd - 1, 3:6]
+            A = _skew(a)
+            g = 4.0 / (4.0 + a @ a)
+            Q = I + g * (A + 0.5 * (A @ A))
+            Xi = g * (I + 0.5 * A)
+            f = mult[:3] * vals[:3]
+            mo = mult[3:] * vals[3:]
+            fip = Q @ Qi @ f
+            mip = Xi @ Qi @ mo
+            K12 = -1.0 * _skew(fip) @ Xi
+            K22 = -0.5 * g * (_skew(Qi @ mo) + Xi @ np.outer(Qi @ mo, a))
+            q = np.concatenate([fip, mip])
+            dq = np.zeros((6, 6))
+            dq[:3, 3:] = K12
+            dq[3:, 3:] = K22
+            for lin in range(6):
+                gl = gls[nd - 1, lin]
+                if active[nd - 1, lin]:
+                    (pa if gl > 0 else pb)[0].append(abs(gl) - 1)
+                    (pa if gl > 0 else pb)[1].append(-1.0 * q[lin])
+                for col in range(6):
+                    gc = gls[nd - 1, col]
+                    if not active[nd - 1, col] or gl == 0:
+                        continue
+                    w = ("AA" if gc > 0 else "AB") if gl > 0 else ("BA" if gc > 0 else "BB")
+                    trip[w][0].append(abs(gl) - 1)
+                    trip[w][1].append(abs(gc) - 1)
+                    trip[w][2].append(-1.0 * dq[lin, col])
+    return trip, pa, pb
+
+
+def host_load_contribution(m: M.Model, gls: np.ndarray, disp: np.ndarray, copy: np.ndarray, time: float):
+    """NodalLoad + NodalFollowerLoad of a model, merged (what a host pushes after gfa_assemble)."""
+    t1, a1, b1 = nodal_load_contribution(m, gls, disp, time)
+    t2, a2, b2 = nodal_follower_load_contribution(m, gls, disp, copy, time)
+    trip = {w: tuple(list(t1[w][k]) + list(t2[w][k]) for k in range(3)) for w in t1}
+    return trip, (list(a1[0]) + list(a2[0]), list(a1[1]) + list(a2[1])), (list(b1[0]) + list(b2[0]), list(b1[1]) + list(b2[1]))
 
 
 def assert_results_parity(ref, got, what):
