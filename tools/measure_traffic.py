@@ -44,5 +44,8 @@ json.dump({"fp64_pipe_busy_pct": ev.get("sm__inst_executed_pipe_fp64.avg.pct_of_
            "fp64_warp_inst": ev.get("smsp__inst_executed_pipe_fp64.sum"), "kernel": step[0][1].split("(")[0],
            "source": f"tools/measure_traffic.py, {when}"},
           open(os.path.join(ROOT, "profiles", "eval_pipe_r02.json"), "w"), indent=1)
+import shutil
+for name in ("traffic_r02.json", "eval_pipe_r02.json"):      # gpurun merges gpurun_out/ back, not profiles/
+    shutil.copy(os.path.join(ROOT, "profiles", name), os.path.join(OUT, name))
 print(open(os.path.join(ROOT, "profiles", "traffic_r02.json")).read())
 print(open(os.path.join(ROOT, "profiles", "eval_pipe_r02.json")).read())
