@@ -657,49 +657,49 @@ __device__ void rot_items(const EvalArgs& A, int e, double* ke, const double* re
     (void)A; (void)e;
     double* Ke_el = ke + 192 + jj;
     const double* S0 = rec0 + S_OFF;
-    {   // rows u_a: gradient groups {u,1 ; u,2} x {alpha,1 ; alpha,2 ; alpha}
-        double m0[3][NGP][3], m2[3][NGP][3], F[3] = { 0.0, 0.0, 0.0 };
+    {   // rows u_a: gradient groups {u,1 ; u,2} x {alpha,1 ; alpha,2 ; alpha}.  The C' entries are read once; the three
+        // nodes b run through ONE copy of the code (instruction cache), re-reading only the shape functions
+        double c01[NGP][3], c03[NGP][3], c04[NGP][3], c21[NGP][3], c23[NGP][3], c24[NGP][3], f1[NGP], f3[NGP], f4[NGP];
 #pragma unroll
         for (int g = 0; g < NGP; g++) {
             const double* rec = rec0 + g * REC;
             const double* recJ = rec + jj;
             const Col cc = col_of(rec, jj);
-            const double c01[3] = { c_at<0, 0, 1>(cc), c_at<0, 1, 1>(cc), c_at<0, 2, 1>(cc) };
-            const double c03[3] = { c_at<0, 0, 3>(cc), c_at<0, 1, 3>(cc), c_at<0, 2, 3>(cc) };
-            const double c04[3] = { c_at<0, 0, 4>(cc), c_at<0, 1, 4>(cc), c_at<0, 2, 4>(cc) };
-            const double c21[3] = { c_at<2, 0, 1>(cc), c_at<2, 1, 1>(cc), c_at<2, 2, 1>(cc) };
-            const double c23[3] = { c_at<2, 0, 3>(cc), c_at<2, 1, 3>(cc), c_at<2, 2, 3>(cc) };
-            const double c24[3] = { c_at<2, 0, 4>(cc), c_at<2, 1, 4>(cc), c_at<2, 2, 4>(cc) };
-            const double f1 = recJ[F_OFF + 3], f3 = recJ[F_OFF + 9], f4 = recJ[F_OFF + 12];
+            c01[g][0] = c_at<0, 0, 1>(cc); c01[g][1] = c_at<0, 1, 1>(cc); c01[g][2] = c_at<0, 2, 1>(cc);
+            c03[g][0] = c_at<0, 0, 3>(cc); c03[g][1] = c_at<0, 1, 3>(cc); c03[g][2] = c_at<0, 2, 3>(cc);
+            c04[g][0] = c_at<0, 0, 4>(cc); c04[g][1] = c_at<0, 1, 4>(cc); c04[g][2] = c_at<0, 2, 4>(cc);
+            c21[g][0] = c_at<2, 0, 1>(cc); c21[g][1] = c_at<2, 1, 1>(cc); c21[g][2] = c_at<2, 2, 1>(cc);
+            c23[g][0] = c_at<2, 0, 3>(cc); c23[g][1] = c_at<2, 1, 3>(cc); c23[g][2] = c_at<2, 2, 3>(cc);
+            c24[g][0] = c_at<2, 0, 4>(cc); c24[g][1] = c_at<2, 1, 4>(cc); c24[g][2] = c_at<2, 2, 4>(cc);
+            f1[g] = recJ[F_OFF + 3]; f3[g] = recJ[F_OFF + 9]; f4[g] = recJ[F_OFF + 12];
+        }
+#pragma unroll 1
+        for (int b = 0; b < 3; b++) {
+            double m0[NGP][3], m2[NGP][3], F = 0.0;
 #pragma unroll
-            for (int b = 0; b < 3; b++) {
+            for (int g = 0; g < NGP; g++) {
                 const double s1 = S0[g * REC + 12 + b], s3 = S0[g * REC + 15 + b], s4 = S0[g * REC + 18 + b];
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
-                    m0[b][g][i] = fma(s4, c04[i], fma(s3, c03[i], s1 * c01[i]));
-                    m2[b][g][i] = fma(s4, c24[i], fma(s3, c23[i], s1 * c21[i]));
+                    m0[g][i] = fma(s4, c04[g][i], fma(s3, c03[g][i], s1 * c01[g][i]));
+                    m2[g][i] = fma(s4, c24[g][i], fma(s3, c23[g][i], s1 * c21[g][i]));
                 }
-                F[b] = fma(s4, f4, fma(s3, f3, fma(s1, f1, F[b])));
+                F = fma(s4, f4[g], fma(s3, f3[g], fma(s1, f1[g], F)));
             }
-        }
 #pragma unroll 1
-        for (int a = 0; a < 6; a++) {
-            double n1[NGP], n2[NGP];
-#pragma unroll
-            for (int g = 0; g < NGP; g++) { n1[g] = S0[g * REC + a]; n2[g] = S0[g * REC + 6 + a]; }
-#pragma unroll
-            for (int b = 0; b < 3; b++) {
+            for (int a = 0; a < 6; a++) {
                 double k[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
-                for (int g = 0; g < NGP; g++)
+                for (int g = 0; g < NGP; g++) {
+                    const double n1 = S0[g * REC + a], n2 = S0[g * REC + 6 + a];
 #pragma unroll
-                    for (int i = 0; i < 3; i++) k[i] = fma(n2[g], m2[b][g][i], fma(n1[g], m0[b][g][i], k[i]));
+                    for (int i = 0; i < 3; i++) k[i] = fma(n2, m2[g][i], fma(n1, m0[g][i], k[i]));
+                }
                 double* o = Ke_el + 84 * b + 9 * a;
                 o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
             }
+            pe[18 + 3 * b + jj] = F;
         }
-#pragma unroll
-        for (int b = 0; b < 3; b++) pe[18 + 3 * b + jj] = F[b];
     }
     {   // rows alpha_a: gradient groups {alpha,1 ; alpha,2 ; alpha} on both sides; one Gauss point at a time, the 27
         // sums (row node a, column node b, component i) stay in registers -- same order of additions as a loop
