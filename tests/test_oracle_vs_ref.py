@@ -145,3 +145,34 @@ def test_port_matches_reference_on_random_models(ref, port):
                 util.assert_parity(a, b, f"random trial {trial} it{it} {key}")
             ref.commit(); port.commit()
             d = -0.7 * d
+
+
+def test_port_pipe_pressure_matches_reference_sources(ref, port):
+    """PipeLoad internal pressure (Pipe_1::MountPipeSpecialLoads, Pipe_1.cpp:1443-1494) on seeded pipe lines bent by
+    large displacements, random element sets and pressures of both signs, with a commit between iterations."""
+    rng = np.random.default_rng(20240051)
+    for trial in range(4):
+        n = int(rng.integers(3, 15))
+        m = M.pipe_line(n)
+        m.gravity = (0.0, 0.3, -9.81) if trial % 2 else None
+        loads = []
+        for _ in range(int(rng.integers(1, 4))):
+            els = np.sort(rng.choice(np.arange(1, n + 1), size=int(rng.integers(1, n + 1)), replace=False)).astype(np.int32)
+            p = float(rng.uniform(-4.0e8, 4.0e8))
+            loads.append((els, np.array([[0.0, 0.1 * p, 0, 0, 0], [1.0, p, 5.0e4, 800.0, 1025.0]])))
+        m.pipe_loads = loads
+        ref.load(m)
+        port.load(m)
+        ref.set_time(0.2, 0.5)
+        port.set_time(0.2, 0.5)
+        d = M.mask_displacements(m, rng.uniform(-5e-2, 5e-2, (m.n_nodes, 6)))
+        for it in range(3):
+            ref.assemble(d, with_loads=True)
+            port.assemble(d)
+            util.assert_system_parity(ref.csr, port.csr, f"pipe pressure trial {trial} it{it}")
+            for a, b, key in zip(ref.vectors(), port.vectors(), ("PA", "IA", "PB")):
+                util.assert_parity(a, b, f"pipe pressure trial {trial} it{it} {key}")
+            if it == 0:
+                ref.commit()
+                port.commit()
+            d = -0.6 * d
