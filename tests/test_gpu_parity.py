@@ -747,6 +747,42 @@ def test_pipe_load_on_the_device(name, commits):
     asm.close()
 
 
+def test_pipe_load_random_against_oracle(port):
+    """Device pipe pressure against the oracle port (pinned to the reference on the same generator by
+    tests/test_oracle_vs_ref.py) on seeded pipe lines mixed with beams and shells: random element sets, pressures of
+    both signs, large displacements, a commit between iterations."""
+    rng = np.random.default_rng(20240052)
+    for trial in range(4):
+        n = int(rng.integers(3, 40))
+        pipes = M.pipe_line(n)
+        m = M.concat_models([M.beam_line(int(rng.integers(2, 6))), pipes, M.shell_plate(2, 2, warp=0.01)]) if trial % 2 else pipes
+        first = int(np.nonzero(m.elem_type == M.PIPE_1)[0][0]) + 1              # 1-based id of the first pipe element
+        loads = []
+        for _ in range(int(rng.integers(1, 4))):
+            els = (first + np.sort(rng.choice(np.arange(n), size=int(rng.integers(1, n + 1)), replace=False))).astype(np.int32)
+            p = float(rng.uniform(-4.0e8, 4.0e8))
+            loads.append((els, np.array([[0.0, 0.1 * p, 0, 0, 0], [1.0, p, 0, 0, 0]])))
+        m.pipe_loads = loads
+        port.load(m)
+        port.set_time(0.2, 0.5)
+        asm = capi.Assembler(m).set_dofs()
+        asm.set_time(0.2, 0.5)
+        asm.set_pipe_loads(m.pipe_loads)
+        amp = 2e-3 if trial % 2 else 3e-2          # the shell cells of the mixed models are 2 cm wide
+        d = M.mask_displacements(m, rng.uniform(-amp, amp, (m.n_nodes, 6)))
+        for it in range(3):
+            port.assemble(d)
+            asm.assemble(d)
+            asm.apply_pipe_loads(0.7)
+            util.assert_system_parity(port.csr, asm.csr, f"device pipe pressure trial {trial} it{it}")
+            for a, b, key in zip(port.vectors(), asm.vectors(), ("PA", "IA", "PB")):
+                util.assert_parity(a, b, f"device pipe pressure trial {trial} it{it} {key}")
+            if it == 0:
+                port.commit(); asm.commit()
+            d = -0.6 * d
+        asm.close()
+
+
 def test_random_models_against_oracle(port):
     """Seeded random variations (the oracle is pinned to the reference on the same generator by
     tests/test_oracle_vs_ref.py): random constraint masks on random nodes, sizes, warps, gravity, displacement
