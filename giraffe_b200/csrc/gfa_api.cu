@@ -72,6 +72,10 @@ const TypeInfo kTypes[3] = {
 // doubles per element in the Ke arena: Shell_1 stores the upper triangle plus the non-symmetric
 // rotation corner in sector-padded groups (gfa_device.h: shell_stored_offset), the others every block
 inline int arena_doubles(int slot) { return slot == 0 ? SHELL_ARENA : slot == 1 ? BEAM_ARENA : SOLID_ARENA; }
+// doubles of the classic arena a type's n elements take: whole batches for Shell_1 (batch layout, gfa_device.h)
+inline long long type_region(int slot, size_t n) {
+    return slot == 0 ? (long long)((n + SHELL_BATCH - 1) / SHELL_BATCH) * (SHELL_BATCH * SHELL_ARENA) : (long long)n * arena_doubles(slot);
+}
 // Pipe_1 shares the Beam_1 block: same Mount / MountGlobal / SaveLagrange (Pipe_1.cpp:836-974, 1027-1104),
 // other constants (PreCalc, Pipe_1.cpp:1106-1146)
 inline int type_slot(int t) { return t == GFA_SHELL_1 ? 0 : (t == GFA_BEAM_1 || t == GFA_PIPE_1) ? 1 : t == GFA_SOLID_1 ? 2 : -1; }
@@ -224,6 +228,9 @@ struct gfa_handle {
         DevBuf<long long> d_seg, d_src, d_dest;
     } shell_loads, pipe_loads;
 
+    bool replaying = false;               // gfa_set_dofs called by leave_ring_mode with the handle's own arguments
+    bool batch_layout = false;            // classic shell arena interleaved by batches of 8 elements (gfa_device.h: shell_batch_offset)
+    bool force_compact = false;           // the Newmark kernels walk an element's own region: compact layout from then on
     bool assembled = false;
     bool timing_pending = false;          // events of the last assembly not read yet (gfa_assemble_enqueue)
     float last_ms[4] = { 0, 0, 0, 0 };
@@ -240,6 +247,7 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac, EvalPass pass = PASS_ALL) {
     a.n_el = (int)t.elems.size();
     a.e_begin = 0; a.e_end = a.n_el;
     a.elist = nullptr; a.ring_chunks = 0; a.chunk_el = 1; a.chunk0 = 0; a.chunk_doubles = 0;
+    a.batch_layout = (slot == 0 && h->batch_layout) ? 1 : 0;
     a.conn = t.d_conn.p; a.prop = t.d_prop.p; a.props = t.d_props.p;
     a.pret = t.any_pret ? t.d_pret.p : nullptr;
     a.xyz = h->d_xyz.p; a.copy = h->d_copy.p; a.disp = h->d_disp.p;
@@ -262,8 +270,9 @@ EvalArgs eval_args(gfa_t* h, int slot, double gfac, EvalPass pass = PASS_ALL) {
 
 // offset (in doubles) of block (la, b) of a local element in the Ke arena; `tr` = stored transposed
 inline long long arena_block(const gfa_t* h, int slot, int local, int la, int b, bool& tr) {
-    const long long base = h->tb[slot].ke_off[local];
     tr = false;
+    if (slot == 0 && h->batch_layout) return h->tb[0].ke_base + shell_batch_offset(local, la, b, tr);
+    const long long base = h->tb[slot].ke_off[local];
     if (slot == 0) return base + shell_block_offset(la, b, tr);
     if (slot == 1) return base + beam_block_offset(la, b, tr);
     return base + solid_block_offset(la, b, tr);
@@ -450,7 +459,7 @@ int gfa_create(const gfa_model_t* m, int device, gfa_t** out) {
         for (int s = 0; s < 3 && e == cudaSuccess; s++) {
             TypeBlock& t = h->tb[s];
             t.ke_base = ke; t.pe_base = (int)pe;
-            ke += (long long)t.elems.size() * arena_doubles(s);
+            ke += type_region(s, t.elems.size());
             pe += (long long)t.elems.size() * kTypes[s].ndof;
             e = t.d_conn.upload(t.conn);
             if (e == cudaSuccess) e = t.d_prop.upload(t.prop);
@@ -535,8 +544,10 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
     CUDA_TRY(cudaSetDevice(h->device));
     h->dofs_set = false; h->assembled = false; h->vec_dirty = false;
     h->d_owned_idx.release();
-    h->shell_loads.n_loads = h->shell_loads.n_entries = 0; h->shell_loads.n_dest = 0;      // registered against the old DOF map
-    h->pipe_loads.n_loads = h->pipe_loads.n_entries = 0; h->pipe_loads.n_dest = 0;
+    if (!h->replaying) {          // registered against the old DOF map (a replay keeps the map: the load routes stay valid)
+        h->shell_loads.n_loads = h->shell_loads.n_entries = 0; h->shell_loads.n_dest = 0;
+        h->pipe_loads.n_loads = h->pipe_loads.n_entries = 0; h->pipe_loads.n_dest = 0;
+    }
     h->n_free = n_free; h->n_fixed = n_fixed;
     h->gls.assign(GLs, GLs + 6 * (size_t)h->n_nodes);
     const std::vector<int>& gls = h->gls;
@@ -718,7 +729,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             gn_iface[gn] = __builtin_popcountll(rs) > 1;
         }
     long long classic_doubles = 0;
-    for (int s = 0; s < 3; s++) classic_doubles += (long long)h->tb[s].elems.size() * arena_doubles(s);
+    for (int s = 0; s < 3; s++) classic_doubles += type_region(s, h->tb[s].elems.size());
     {
         const char* env = getenv("GFA_RING");
         const char* ekb = getenv("GFA_RING_CHUNK_KB");
@@ -733,6 +744,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
         if (const char* eg = getenv("GFA_RING_GROUP")) if (atoi(eg) >= 1) h->ring_group = atoi(eg);
         if (h->ring_serial && K < h->ring_group + 2) K = h->ring_group + 2;
         bool ring = !h->force_classic && mode != 0 && (mode == 1 || mode == 3 || classic_doubles * 8 > (long long)K * chunk_bytes);
+        h->batch_layout = false;                             // set below when the classic arena is chosen
         h->ring_note = h->force_classic ? "classic: dynamics / explicit request" : mode == 0 ? "classic (GFA_RING=1 selects the ring pipeline)" : "classic: the element arena fits the ring";
         std::vector<std::vector<unsigned char> > pinned(3);
         int ce[3] = { 1, 1, 1 };
@@ -812,6 +824,10 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
                      h->ring_serial ? "serial ring" : "ring", K, chunk_doubles * 8 / 1048576.0, tot_chunks, span, n_ring, n_pinned);
             h->ring_note = buf;
         } else {
+            {   // GFA_ARENA_LAYOUT=0 keeps the compact per-element layout (experiments)
+                const char* lay = getenv("GFA_ARENA_LAYOUT");
+                h->batch_layout = !h->force_compact && shell_batch_layout_available() && (lay && atoi(lay) == 1);     // opt-in until verified on the GPU
+            }
             h->ring_chunks = 0; h->ring_span = 0; h->total_chunks = 0; h->chunk_doubles = 0; h->ring_doubles = 0;
             for (int s = 0; s < 3; s++) {
                 TypeBlock& t = h->tb[s];
@@ -1440,10 +1456,14 @@ DynArgs dyn_args(gfa_t* h, int slot, const gfa_dynamic_t* d) {
 // A handle in ring mode keeps no complete element arena; paths that need one (the Newmark kernels work on it in
 // place) rebuild the slot map for the classic two-kernel path, once.
 int leave_ring_mode(gfa_t* h) {
-    if (!h->ring) return GFA_OK;
+    if (!h->ring && !h->batch_layout) return GFA_OK;
     h->force_classic = true;
+    h->force_compact = true;      // the Newmark kernels walk an element's own arena region
     const std::vector<int> gl = h->gls, em = h->ex_mat, er = h->ex_rows, ec = h->ex_cols;
-    return gfa_set_dofs(h, gl.data(), h->n_free, h->n_fixed, (int64_t)em.size(), em.data(), er.data(), ec.data());
+    h->replaying = true;
+    const int rc = gfa_set_dofs(h, gl.data(), h->n_free, h->n_fixed, (int64_t)em.size(), em.data(), er.data(), ec.data());
+    h->replaying = false;
+    return rc;
 }
 
 // the fused kernel's watchdog: a warp that waited longer than the time-out raised CTL_ABORT and every warp left
@@ -1492,7 +1512,7 @@ int assemble_impl(gfa_t* h, const gfa_step_t* st, const gfa_dynamic_t* dyn, bool
             }
         }
     }
-    if (dyn && h->ring) {       // the mass / damping kernels fold their terms into a complete arena in place
+    if (dyn && (h->ring || h->batch_layout)) {       // the mass / damping kernels fold their terms into a complete, compact arena in place
         int rc = leave_ring_mode(h);
         if (rc != GFA_OK) return rc;
     }
@@ -1923,9 +1943,12 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));      // interface unpack and host additions are stream-ordered
     const int n = kTypes[s].ndof;
     if (K) {
-        const int nd = arena_doubles(s), local = h->el_local[e];
+        const bool batch = s == 0 && h->batch_layout && !h->ring;
+        const int nd = batch ? SHELL_BATCH * SHELL_ARENA : arena_doubles(s), local = h->el_local[e];
         std::vector<double> blk((size_t)nd);
-        const double* src = h->d_Ke.p + h->tb[s].ke_off[local];
+        // batch layout: fetch the whole batch region and pick this element's blocks out of it
+        const double* src = batch ? h->d_Ke.p + h->tb[0].ke_base + (long long)(local / SHELL_BATCH) * (SHELL_BATCH * SHELL_ARENA)
+                                  : h->d_Ke.p + h->tb[s].ke_off[local];
         if (h->ring) {
             // the ring keeps only the last chunks: evaluate this one element again, into a scratch region
             CUDA_TRY(cudaMemcpyAsync(h->d_one.p, &local, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1941,7 +1964,8 @@ int gfa_element_block(gfa_t* h, int32_t e, double* K, double* P) {
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 bool tr = false;
-                const int off = s == 0 ? shell_block_offset(i / 3, j / 3, tr) : s == 1 ? beam_block_offset(i / 3, j / 3, tr) : solid_block_offset(i / 3, j / 3, tr);
+                const int off = batch ? (int)shell_batch_offset(local % SHELL_BATCH, i / 3, j / 3, tr)
+                              : s == 0 ? shell_block_offset(i / 3, j / 3, tr) : s == 1 ? beam_block_offset(i / 3, j / 3, tr) : solid_block_offset(i / 3, j / 3, tr);
                 K[i * n + j] = blk[(size_t)off + (tr ? (j % 3) * 3 + (i % 3) : (i % 3) * 3 + (j % 3))];
             }
     }

@@ -592,7 +592,11 @@ GFA_DI double self_weight(const EvalArgs& A, int e, int b, int jj) {
 // Translational columns, component jj, of ALL six nodes: pass kk takes B1 = kk and B2 = 5 - kk, rows
 // u_0..u_B1 of the first and u_0..u_B2 of the second (upper triangle of the symmetric u-u part) = 7
 // blocks for every kk; the rows both columns have share their shape-function loads.
+// BATCH: `ke` is the element's corner of its batch region and stored block n lies at ke + 72 n (gfa_device.h:
+// shell_batch_offset); otherwise `ke` is the element's own region (shell_stored_offset).
+template <bool BATCH>
 __device__ void uu_items(const EvalArgs& A, int e, double* ke, const double* rec0, int jj, double* pe) {
+    constexpr int GRP = BATCH ? 7 * 72 : 64, BLK = BATCH ? 72 : 9;
     const double* S0 = rec0 + S_OFF;
     double c00[NGP][3], c02[NGP][3], c20[NGP][3], c22[NGP][3], f0[NGP], f2[NGP];
 #pragma unroll
@@ -608,7 +612,7 @@ __device__ void uu_items(const EvalArgs& A, int e, double* ke, const double* rec
 #pragma unroll 1
     for (int kk = 0; kk < 3; kk++) {
         const int B1 = kk, B2 = 5 - kk;
-        double* Ke_el = ke + 64 * kk + jj;
+        double* Ke_el = ke + GRP * kk + jj;
         // m[g] = sum_q S_g[q, column] C'_g[(p, .), (q, jj)] for the two columns, p in {u,1 ; u,2}
         double m10[NGP][3], m12[NGP][3], m20[NGP][3], m22[NGP][3];
         double F1 = 0.0, F2 = 0.0;
@@ -634,7 +638,7 @@ __device__ void uu_items(const EvalArgs& A, int e, double* ke, const double* rec
                 for (int g = 0; g < NGP; g++)
 #pragma unroll
                     for (int i = 0; i < 3; i++) k[i] = fma(n2[g], m12[g][i], fma(n1[g], m10[g][i], k[i]));
-                double* o = Ke_el + 9 * a;
+                double* o = Ke_el + BLK * a;
                 o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
             }
             double k[3] = { 0.0, 0.0, 0.0 };
@@ -642,7 +646,7 @@ __device__ void uu_items(const EvalArgs& A, int e, double* ke, const double* rec
             for (int g = 0; g < NGP; g++)
 #pragma unroll
                 for (int i = 0; i < 3; i++) k[i] = fma(n2[g], m22[g][i], fma(n1[g], m20[g][i], k[i]));
-            double* o = Ke_el + 9 * (kk + 1 + a);
+            double* o = Ke_el + BLK * (kk + 1 + a);
             o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
         }
         pe[3 * B1 + jj] = F1 - self_weight(A, e, B1, jj);
@@ -653,9 +657,11 @@ __device__ void uu_items(const EvalArgs& A, int e, double* ke, const double* rec
 // Rotational columns, component jj, of ALL three mid-side nodes b: all 27 rows -- the six u rows are the
 // upper u-alpha blocks (their transposes are the alpha-u blocks), the three alpha rows are the
 // non-symmetric alpha-alpha blocks, each stored on its own.  Column (b, jj) starts at 192 + 84 b + jj.
+template <bool BATCH>
 __device__ void rot_items(const EvalArgs& A, int e, double* ke, const double* rec0, int jj, double* pe) {
     (void)A; (void)e;
-    double* Ke_el = ke + 192 + jj;
+    constexpr int COL = BATCH ? 9 * 72 : 84, BLK = BATCH ? 72 : 9;
+    double* Ke_el = ke + (BATCH ? 21 * 72 : 192) + jj;
     const double* S0 = rec0 + S_OFF;
     {   // rows u_a: gradient groups {u,1 ; u,2} x {alpha,1 ; alpha,2 ; alpha}.  The C' entries are read once; the three
         // nodes b run through ONE copy of the code (instruction cache), re-reading only the shape functions
@@ -695,7 +701,7 @@ __device__ void rot_items(const EvalArgs& A, int e, double* ke, const double* re
 #pragma unroll
                     for (int i = 0; i < 3; i++) k[i] = fma(n2, m2[g][i], fma(n1, m0[g][i], k[i]));
                 }
-                double* o = Ke_el + 84 * b + 9 * a;
+                double* o = Ke_el + COL * b + BLK * a;
                 o[0] = k[0]; o[3] = k[1]; o[6] = k[2];
             }
             pe[18 + 3 * b + jj] = F;
@@ -739,7 +745,7 @@ __device__ void rot_items(const EvalArgs& A, int e, double* ke, const double* re
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                double* o = Ke_el + 84 * b + 9 * (6 + a);
+                double* o = Ke_el + COL * b + BLK * (6 + a);
                 o[0] = k[a][b][0]; o[3] = k[a][b][1]; o[6] = k[a][b][2];
             }
     }
@@ -747,9 +753,10 @@ __device__ void rot_items(const EvalArgs& A, int e, double* ke, const double* re
 
 // One batch of `ne` <= EPW elements at list positions k0 .. k0 + ne - 1, evaluated by one warp; `smem` is the
 // warp's own smem_bytes(EPW) region.  Shared by the classic evaluation kernel and the fused ring kernel.
-template <int EPW>
+template <int EPW, bool BATCH = false>
 __device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, double* smem, int lane) {
     static_assert(EPW * 3 <= 32, "one lane per (element, component) item");
+    static_assert(!BATCH || EPW == SHELL_BATCH, "the batch layout of the arena is the 8-element batch of this kernel");
     if (lane < ne * NGP) physics(A, eval_element(A, k0 + lane / NGP), lane % NGP, smem + lane * REC);
     __syncwarp();
     double* pe = smem + EPW * NGP * REC;      // the batch's P, written out in whole sectors below
@@ -757,9 +764,10 @@ __device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, do
         const int el = lane / 3, jj = lane % 3;
         const double* rec0 = smem + el * NGP * REC;
         const int e = eval_element(A, k0 + el);
-        double* ke = eval_ke(A, k0 + el, SHELL_ARENA);
-        uu_items(A, e, ke, rec0, jj, pe + 27 * el);
-        rot_items(A, e, ke, rec0, jj, pe + 27 * el);
+        // BATCH: k0 is a multiple of 8 (classic arena, no element list): the batch's region, this element's corner
+        double* ke = BATCH ? A.Ke + (size_t)(k0 / SHELL_BATCH) * (SHELL_BATCH * SHELL_ARENA) + 9 * el : eval_ke(A, k0 + el, SHELL_ARENA);
+        uu_items<BATCH>(A, e, ke, rec0, jj, pe + 27 * el);
+        rot_items<BATCH>(A, e, ke, rec0, jj, pe + 27 * el);
     }
     __syncwarp();
     if (!A.elist) { for (int i = lane; i < ne * 27; i += 32) A.Pe[(size_t)k0 * 27 + i] = pe[i]; }
@@ -767,13 +775,13 @@ __device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, do
     __syncwarp();
 }
 
-template <int EPW>
+template <int EPW, bool BATCH = false>
 __global__ void __launch_bounds__(32) eval_kernel(EvalArgs A) {
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     for (long long batch = blockIdx.x; A.e_begin + batch * EPW < A.e_end; batch += gridDim.x) {
         const int k0 = A.e_begin + (int)(batch * EPW);
-        eval_batch<EPW>(A, k0, min(EPW, A.e_end - k0), smem, lane);
+        eval_batch<EPW, BATCH>(A, k0, min(EPW, A.e_end - k0), smem, lane);
     }
 }
 
@@ -2056,6 +2064,7 @@ int configure_kernels() {
     e = cudaFuncSetAttribute(shell::eval_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(10));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(shell::eval_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(8));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(shell::eval_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(8));
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(shell::eval_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, shell::smem_bytes(6));
     if (e != cudaSuccess) return (int)e;
@@ -2117,6 +2126,8 @@ static int resident_ctas(K kernel, int smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 32, smem) != cudaSuccess || n < 1) n = 8;
     return sm_count() * n;
 }
+// the batch layout of the shell arena belongs to the 8-element kernel (GFA_SHELL_EPW experiments keep the compact one)
+bool shell_batch_layout_available() { return shell_epw() == SHELL_BATCH; }
 void launch_shell_eval(const EvalArgs& a, void* s) {
     if (a.e_end <= a.e_begin) return;
     const int epw = shell_epw();
@@ -2143,7 +2154,10 @@ void launch_shell_eval(const EvalArgs& a, void* s) {
     case 7: shell::eval_kernel<7><<<grid, 32, shell::smem_bytes(7), st>>>(a); break;
     case 9: shell::eval_kernel<9><<<grid, 32, shell::smem_bytes(9), st>>>(a); break;
     case 6: shell::eval_kernel<6><<<grid, 32, shell::smem_bytes(6), st>>>(a); break;
-    case 8: shell::eval_kernel<8><<<grid, 32, shell::smem_bytes(8), st>>>(a); break;
+    case 8:
+        if (a.batch_layout && !a.elist && a.ring_chunks == 0 && a.e_begin % SHELL_BATCH == 0) shell::eval_kernel<8, true><<<grid, 32, shell::smem_bytes(8), st>>>(a);
+        else shell::eval_kernel<8><<<grid, 32, shell::smem_bytes(8), st>>>(a);
+        break;
     default: shell::eval_kernel<10><<<grid, 32, shell::smem_bytes(10), st>>>(a); break;
     }
 }
