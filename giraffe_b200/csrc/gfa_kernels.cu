@@ -1554,11 +1554,15 @@ GFA_DI double c_at(const double* recJ, const double* rec3J) {
     else return rec3J[C_OFF + 9 * blk(Q, P) + II];
 }
 
-__device__ void congruence_item(const EvalArgs& A, int e, double* ke, const double* rec0, int b, int jj) {
-    double K[24];
+// Columns b1 = p and b2 = 7 - p, component jj, in one item: the C' entries of a column depend on jj only and the
+// gradient table on nothing but the point, so both are read once for the two columns -- the kernel's busiest unit
+// was the L1 data pipe (77 %, 354 shared-memory loads per element; ncu, profiles/r02_notes.md), not the FP64 pipe.
+__device__ void congruence_pair(const EvalArgs& A, int e, double* ke, const double* rec0, int p, int jj) {
+    const int b1 = p, b2 = 7 - p;
+    double K1[24], K2[24];
 #pragma unroll
-    for (int i = 0; i < 24; i++) K[i] = 0.0;
-    double F = 0.0, fe = 0.0;
+    for (int i = 0; i < 24; i++) { K1[i] = 0.0; K2[i] = 0.0; }
+    double F1 = 0.0, F2 = 0.0, fe1 = 0.0, fe2 = 0.0;
     const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
 #pragma unroll 1
     for (int g = 0; g < NGP; g++) {
@@ -1566,35 +1570,53 @@ __device__ void congruence_item(const EvalArgs& A, int e, double* ke, const doub
         const double* recJ = rec + jj;
         const double* rec3J = rec + 3 * jj;
         const double* S = rec + S_OFF;
-        const double s0 = S[b], s1 = S[8 + b], s2 = S[16 + b];
-        double m[3][3];
-#define GFA_ROW(P_, I_) m[P_][I_] = s0 * c_at<P_, I_, 0>(recJ, rec3J) + s1 * c_at<P_, I_, 1>(recJ, rec3J) + s2 * c_at<P_, I_, 2>(recJ, rec3J);
+        const double s0 = S[b1], s1 = S[8 + b1], s2 = S[16 + b1];
+        const double t0 = S[b2], t1 = S[8 + b2], t2 = S[16 + b2];
+        double m[3][3], n[3][3];
+#define GFA_ROW(P_, I_) { const double c0 = c_at<P_, I_, 0>(recJ, rec3J), c1 = c_at<P_, I_, 1>(recJ, rec3J), c2 = c_at<P_, I_, 2>(recJ, rec3J); \
+                          m[P_][I_] = s0 * c0 + s1 * c1 + s2 * c2; n[P_][I_] = t0 * c0 + t1 * c1 + t2 * c2; }
         GFA_ROW(0, 0) GFA_ROW(0, 1) GFA_ROW(0, 2) GFA_ROW(1, 0) GFA_ROW(1, 1) GFA_ROW(1, 2) GFA_ROW(2, 0) GFA_ROW(2, 1) GFA_ROW(2, 2)
 #undef GFA_ROW
-        F += s0 * recJ[F_OFF] + s1 * recJ[F_OFF + 3] + s2 * recJ[F_OFF + 6];
+        {
+            const double f0 = recJ[F_OFF], f1 = recJ[F_OFF + 3], f2 = recJ[F_OFF + 6];
+            F1 += s0 * f0 + s1 * f1 + s2 * f2;
+            F2 += t0 * f0 + t1 * f1 + t2 * f2;
+        }
 #pragma unroll
-        for (int a = 0; a < 8; a++)
+        for (int a = 0; a < 8; a++) {
+            const double a0 = S[a], a1 = S[8 + a], a2 = S[16 + a];
 #pragma unroll
-            for (int ii = 0; ii < 3; ii++)
-                K[3 * a + ii] += S[a] * m[0][ii] + S[8 + a] * m[1][ii] + S[16 + a] * m[2][ii];
-        fe += rec[W_OFF] * rec[N_OFF + b] * gk;
+            for (int ii = 0; ii < 3; ii++) {
+                K1[3 * a + ii] += a0 * m[0][ii] + a1 * m[1][ii] + a2 * m[2][ii];
+                K2[3 * a + ii] += a0 * n[0][ii] + a1 * n[1][ii] + a2 * n[2][ii];
+            }
+        }
+        const double wg = rec[W_OFF];
+        fe1 += wg * rec[N_OFF + b1] * gk;
+        fe2 += wg * rec[N_OFF + b2] * gk;
     }
-    const int col = 3 * b + jj;
-    // stored blocks of this column block: rows 0..b (the tangent is symmetric)
-    double* Ke = ke + solid_stored_offset(0, b) + jj;
+    // stored blocks of a column block: rows 0..b (the tangent is symmetric)
+    double* Ke1 = ke + solid_stored_offset(0, b1) + jj;
+    double* Ke2 = ke + solid_stored_offset(0, b2) + jj;
 #pragma unroll
-    for (int rb = 0; rb < 8; rb++)
-        if (rb <= b) { Ke[9 * rb] = K[3 * rb]; Ke[9 * rb + 3] = K[3 * rb + 1]; Ke[9 * rb + 6] = K[3 * rb + 2]; }
-    A.Pe[(size_t)e * 24 + col] = F - fe;
+    for (int rb = 0; rb < 8; rb++) {
+        if (rb <= b1) { Ke1[9 * rb] = K1[3 * rb]; Ke1[9 * rb + 3] = K1[3 * rb + 1]; Ke1[9 * rb + 6] = K1[3 * rb + 2]; }
+        if (rb <= b2) { Ke2[9 * rb] = K2[3 * rb]; Ke2[9 * rb + 3] = K2[3 * rb + 1]; Ke2[9 * rb + 6] = K2[3 * rb + 2]; }
+    }
+    A.Pe[(size_t)e * 24 + 3 * b1 + jj] = F1 - fe1;
+    A.Pe[(size_t)e * 24 + 3 * b2 + jj] = F2 - fe2;
 }
 
-// one batch of `ne` <= EPW solids at list positions k0 .. (see shell::eval_batch)
+// one batch of `ne` <= EPW solids at list positions k0 .. (see shell::eval_batch): 4 elements = 32 Gauss points, then 48
+// column-pair items (1.5 rounds of the warp).  Measured on 4M solids: 13.4 ms with one column per item, 12.9 ms with
+// the pair items; 8 elements a batch (three full rounds, but 4 warps per SM) 14.5 ms; halving the items over two
+// lanes by Gauss points (three full rounds, one exchange) 14.8 ms -- the shuffles land on the same L1 data pipe
 __device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, double* smem, int lane) {
-    if (lane < ne * NGP) physics(A, eval_element(A, k0 + lane / NGP), lane % NGP, smem + lane * REC);
+    for (int gp = lane; gp < ne * NGP; gp += 32) physics(A, eval_element(A, k0 + gp / NGP), gp % NGP, smem + gp * REC);
     __syncwarp();
-    for (int it = lane; it < ne * 24; it += 32) {
-        const int el = it / 24, c = it % 24;
-        congruence_item(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, SOLID_ARENA), smem + el * NGP * REC, c / 3, c % 3);
+    for (int it = lane; it < ne * 12; it += 32) {
+        const int el = it / 12, c = it % 12;
+        congruence_pair(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, SOLID_ARENA), smem + el * NGP * REC, c / 3, c % 3);
     }
     __syncwarp();
 }
