@@ -1197,70 +1197,93 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
 }
 
 // local DOF order: node-major [u_a(3), alpha_a(3)] (Beam_1.cpp:1439-1444)
+// One item = component jj of the translational (ROT = false) or rotational columns of ALL three nodes: the C' entries
+// of a column depend on jj and on the kind of column only, so they are read once and serve the three nodes (the
+// congruence phases of all three element kernels are bound by the L1 data pipe, profiles/r02_notes.md).  Sums and
+// their order are those of one column at a time.
 template <bool ROT>
-__device__ void congruence_item(const EvalArgs& A, int e, double* ke, const double* rec0, int b, int jj) {
-    double K[18];
+__device__ void congruence_cols(const EvalArgs& A, int e, double* ke, const double* rec0, int jj) {
+    double K[3][18];
 #pragma unroll
-    for (int i = 0; i < 18; i++) K[i] = 0.0;
-    double F = 0.0, fe = 0.0;
+    for (int b = 0; b < 3; b++)
+#pragma unroll
+        for (int i = 0; i < 18; i++) K[b][i] = 0.0;
+    double F[3] = { 0.0, 0.0, 0.0 }, fe[3] = { 0.0, 0.0, 0.0 };
 #pragma unroll
     for (int g = 0; g < NGP; g++) {
         const double* rec = rec0 + g * REC;
         const double* S = rec + S_OFF;
         // gradient groups 0: u', 1: alpha', 2: alpha; the blocks (1,0) and (0,1) of C' are identically zero
-        double m0[3], m1[3], m2[3];
+        double c0[3], c1a[3], c1b[3], c2a[3], c2b[3];
 #pragma unroll
         for (int ii = 0; ii < 3; ii++) {
             const double* r0 = rec + C_OFF + 9 * ii + jj;
             const double* r1 = rec + C_OFF + 9 * (3 + ii) + jj;
             const double* r2 = rec + C_OFF + 9 * (6 + ii) + jj;
-            if (ROT) {
-                m0[ii] = S[3 + b] * r0[6];
-                m1[ii] = S[b] * r1[3] + S[3 + b] * r1[6];
-                m2[ii] = S[b] * r2[3] + S[3 + b] * r2[6];
-            } else {
-                m0[ii] = S[b] * r0[0];
-                m1[ii] = 0.0;
-                m2[ii] = S[b] * r2[0];
-            }
+            if (ROT) { c0[ii] = r0[6]; c1a[ii] = r1[3]; c1b[ii] = r1[6]; c2a[ii] = r2[3]; c2b[ii] = r2[6]; }
+            else { c0[ii] = r0[0]; c2a[ii] = r2[0]; c1a[ii] = 0.0; c1b[ii] = 0.0; c2b[ii] = 0.0; }
         }
-        F += ROT ? S[b] * rec[F_OFF + 3 + jj] + S[3 + b] * rec[F_OFF + 6 + jj] : S[b] * rec[F_OFF + jj];
+        const double f0 = ROT ? rec[F_OFF + 3 + jj] : rec[F_OFF + jj], f1 = ROT ? rec[F_OFF + 6 + jj] : 0.0;
+        double Sv[6];
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+        for (int i = 0; i < 6; i++) Sv[i] = S[i];
+        const double wg = ROT ? 0.0 : rec[W_OFF];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            double m0[3], m1[3], m2[3];
 #pragma unroll
             for (int ii = 0; ii < 3; ii++) {
-                K[6 * a + ii] += S[a] * m0[ii];
-                K[6 * a + 3 + ii] += ROT ? S[a] * m1[ii] + S[3 + a] * m2[ii] : S[3 + a] * m2[ii];
+                if (ROT) {
+                    m0[ii] = Sv[3 + b] * c0[ii];
+                    m1[ii] = Sv[b] * c1a[ii] + Sv[3 + b] * c1b[ii];
+                    m2[ii] = Sv[b] * c2a[ii] + Sv[3 + b] * c2b[ii];
+                } else {
+                    m0[ii] = Sv[b] * c0[ii];
+                    m1[ii] = 0.0;
+                    m2[ii] = Sv[b] * c2a[ii];
+                }
             }
-        if (!ROT) {
-            const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
-            fe += rec[W_OFF] * S[3 + b] * gk;                     // mult * N_b * G (:868-878)
+            F[b] += ROT ? Sv[b] * f0 + Sv[3 + b] * f1 : Sv[b] * f0;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++) {
+                    K[b][6 * a + ii] += Sv[a] * m0[ii];
+                    K[b][6 * a + 3 + ii] += ROT ? Sv[a] * m1[ii] + Sv[3 + a] * m2[ii] : Sv[3 + a] * m2[ii];
+                }
+            if (!ROT) {
+                const double gk = jj == 0 ? A.gx : jj == 1 ? A.gy : A.gz;
+                fe[b] += wg * Sv[3 + b] * gk;                     // mult * N_b * G (:868-878)
+            }
         }
     }
-    const int col = 6 * b + (ROT ? 3 : 0) + jj;
-    // stored blocks of this column block: rows 0..cb and, for a rotational column, the rotational rows below
-    const int cb = col / 3;
-    double* Ke = ke + (col % 3);
 #pragma unroll
-    for (int rb = 0; rb < 6; rb++)
-        if (beam_is_stored(rb, cb)) {
-            double* o = Ke + beam_stored_offset(rb, cb);
-            o[0] = K[3 * rb]; o[3] = K[3 * rb + 1]; o[6] = K[3 * rb + 2];
-        }
-    A.Pe[(size_t)e * 18 + col] = F - fe;
+    for (int b = 0; b < 3; b++) {
+        const int col = 6 * b + (ROT ? 3 : 0) + jj;
+        // stored blocks of this column block: rows 0..cb and, for a rotational column, the rotational rows below
+        const int cb = col / 3;
+        double* Ke = ke + (col % 3);
+#pragma unroll
+        for (int rb = 0; rb < 6; rb++)
+            if (beam_is_stored(rb, cb)) {
+                double* o = Ke + beam_stored_offset(rb, cb);
+                o[0] = K[b][3 * rb]; o[3] = K[b][3 * rb + 1]; o[6] = K[b][3 * rb + 2];
+            }
+        A.Pe[(size_t)e * 18 + col] = F[b] - fe[b];
+    }
 }
 
 // one batch of `ne` <= EPW beams at list positions k0 .. (see shell::eval_batch)
 __device__ __forceinline__ void eval_batch(const EvalArgs& A, int k0, int ne, double* smem, int lane) {
     if (lane < ne * NGP) physics(A, eval_element(A, k0 + lane / NGP), lane % NGP, smem + lane * REC);
     __syncwarp();
-    for (int it = lane; it < ne * 9; it += 32) {
-        const int el = it / 9, c = it % 9;
-        congruence_item<false>(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, BEAM_ARENA), smem + el * NGP * REC, c / 3, c % 3);
+    for (int it = lane; it < ne * 3; it += 32) {
+        const int el = it / 3;
+        congruence_cols<false>(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, BEAM_ARENA), smem + el * NGP * REC, it % 3);
     }
-    for (int it = lane; it < ne * 9; it += 32) {
-        const int el = it / 9, c = it % 9;
-        congruence_item<true>(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, BEAM_ARENA), smem + el * NGP * REC, c / 3, c % 3);
+    for (int it = lane; it < ne * 3; it += 32) {
+        const int el = it / 3;
+        congruence_cols<true>(A, eval_element(A, k0 + el), eval_ke(A, k0 + el, BEAM_ARENA), smem + el * NGP * REC, it % 3);
     }
     __syncwarp();
 }
