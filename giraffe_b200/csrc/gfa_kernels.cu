@@ -1160,7 +1160,7 @@ __device__ void physics(const EvalArgs& A, int e, int g, double* rec) {
         mm(tmp, G21, go.R); mtm(G21, go.R, tmp);
     }
     // C' = B'^T D B' + G'  (:776, :824-826) with D = blockdiag(D00, D11): the blocks (1,0) and (0,1) of C' vanish
-    // identically (they are neither stored nor read: congruence_item skips them)
+    // identically (they are neither stored nor read: congruence_cols skips them)
     double DB0[9], DB1[9];
     // column 0: B(.,0) = [B00; 0]
     d00_mul(DB0, D, B00);
