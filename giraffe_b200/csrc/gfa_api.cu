@@ -827,6 +827,7 @@ int gfa_set_dofs(gfa_t* h, const int32_t* GLs, int32_t n_free, int32_t n_fixed,
             {   // GFA_ARENA_LAYOUT=0 keeps the compact per-element layout (experiments)
                 const char* lay = getenv("GFA_ARENA_LAYOUT");
                 h->batch_layout = !h->force_compact && shell_batch_layout_available() && !(lay && atoi(lay) == 0);
+                if (!h->tb[0].elems.empty()) h->ring_note += h->batch_layout ? "; shell arena in batches of 8 elements" : "; compact shell arena";
             }
             h->ring_chunks = 0; h->ring_span = 0; h->total_chunks = 0; h->chunk_doubles = 0; h->ring_doubles = 0;
             for (int s = 0; s < 3; s++) {

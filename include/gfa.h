@@ -314,7 +314,11 @@ int gfa_last_launch_count(gfa_t* h);
  * of a step and gives bitwise the classic results, but is slower on B200 today (profiles/r02_notes.md), hence
  * opt-in: GFA_RING=1 (always) or 2 (when the arena is larger than the ring); GFA_RING_CHUNK_KB and
  * GFA_RING_CHUNKS size the ring (default 9 x 7 MB).  gfa_last_timing then reports [1] = pre-pass of the pinned
- * elements, [2] = ring kernels + vectors. */
+ * elements, [2] = ring kernels + vectors.
+ * The description also names the layout of the classic Shell_1 arena: by default the blocks of eight consecutive
+ * elements are interleaved (one store instruction of the evaluation kernel covers 576 contiguous bytes);
+ * GFA_ARENA_LAYOUT=0 keeps one region per element, and a handle switches to that layout by itself at its first
+ * gfa_assemble_dynamic (the Newmark kernels walk an element's own region; the DOF map and registered loads stay). */
 int gfa_pipeline_info(gfa_t* h, char* buf, int32_t capacity);
 
 /* ---- multi-GPU (mesh partition by element range) ----------------------
