@@ -1679,7 +1679,7 @@ __global__ void node_commit_kernel(int n_nodes, double* copy, double* disp) {
 // Scatter: MountGlobal + MountSparse for the free x free matrix and the
 // residual vectors.
 // =========================================================================
-constexpr int SCATTER_THREADS = 256;
+constexpr int SCATTER_THREADS = 128;     // measured on the 1M-shell plate: 64 / 96 / 128 / 192 / 256 / 512 threads = 1.80 / 1.79 / 1.77 / 1.83 / 1.83 / 2.04 ms (scatter + vectors)
 
 // column c of the 3x3 destination patch: D(i,c) = S(i,c), or S(c,i) when the stored block is the transposed twin
 GFA_DI void load_col(const double* Ke, unsigned off, bool tr, int c, double (&x)[3]) {
